@@ -1,0 +1,138 @@
+/*
+ * zkcnn_b200 -- C ABI of the B200-native zkCNN prover hot path.
+ *
+ * The reference (TAMUCrypto/zkCNN) has no FFI layer: its hot path is two C++ classes, `prover` (src/prover.hpp:16-78)
+ * and `hyrax_bls12_381::polyProver` (3rd/hyrax-bls12-381/src/polyProver.hpp:18-57), called directly by the verifier.
+ * This header is the boundary a drop-in puts underneath those classes: every entry point below replaces one public
+ * member of one of them (cited as file:line of /root/reference) and is what a cgo / JNI / ctypes binding would bind.
+ * zkcnn_b200/host/prover.hpp and polyProver.hpp are the C++ shims with the reference's signatures on top of it.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ or torch types.
+ *   - A field element Fr crosses as uint64_t[4] in mcl's in-memory form: little-endian limbs of a*2^256 mod r
+ *     (Montgomery), fully reduced.  `std::vector<Fr>::data()` of the reference can be passed as is.
+ *   - A G1 point crosses as uint64_t[18]: Jacobian (x, y, z), each coordinate uint64_t[6] Montgomery mod p
+ *     (R = 2^384), the layout of mcl's G1.  Points RETURNED by this library are normalised: z = 1, or
+ *     x = y = z = 0 for the point at infinity.
+ *   - All pointers are HOST pointers; the library owns every device buffer.  Calls are synchronous: outputs are
+ *     written before the call returns.
+ *   - Every function returns 0 on success and a negative value on failure; zk_last_error() describes the failure
+ *     of the calling thread's last call.  There is no CPU fallback: without a CUDA device zk_ctx_create fails.
+ *   - One zk_ctx per (process, GPU); calls on one ctx must be serialised by the caller (the reference prover is
+ *     not re-entrant either, src/prover.cpp:9).
+ */
+#ifndef ZKCNN_B200_H
+#define ZKCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZK_FR_WORDS 4
+#define ZK_G1_WORDS 18
+
+typedef struct zk_ctx zk_ctx;
+
+/* ---- library / context ------------------------------------------------------------------------------------------ */
+const char *zk_last_error(void);
+const char *zk_version(void);      /* "zkcnn_b200 <ver> sm_100a" (or "... emu" for the test-only host build) */
+int zk_device_count(void);
+zk_ctx *zk_ctx_create(int device); /* NULL on failure */
+void zk_ctx_destroy(zk_ctx *ctx);
+/* number of kernels launched through this ctx so far (bench.py's gpu_launches) */
+uint64_t zk_ctx_launch_count(const zk_ctx *ctx);
+
+/* ---- circuit + witness upload: replaces neuralNetwork's friend access to prover::C / prover::val ------------------
+ * (src/prover.hpp:48-49,76-77; src/neuralNetwork.cpp:64-68).  Gate structs are bit-identical to src/circuit.h:15-33. */
+typedef struct { uint32_t g, u; uint8_t lu, sc; } zk_uni_gate;        /* 12 bytes, == uniGate */
+typedef struct { uint32_t g, u, v; uint8_t sc, l; } zk_bin_gate;      /* 16 bytes, == binGate */
+
+/* values of enum class layerType, src/circuit.h:35-37 */
+enum {
+    ZK_LAYER_INPUT = 0, ZK_LAYER_FFT, ZK_LAYER_IFFT, ZK_LAYER_ADD_BIAS, ZK_LAYER_RELU, ZK_LAYER_SQR, ZK_LAYER_OPT_AVG_POOL,
+    ZK_LAYER_MAX_POOL, ZK_LAYER_AVG_POOL, ZK_LAYER_DOT_PROD, ZK_LAYER_PADDING, ZK_LAYER_FCONN, ZK_LAYER_NCONV,
+    ZK_LAYER_NCONV_MUL, ZK_LAYER_NCONV_ADD
+};
+
+typedef struct {                     /* the scalar members of class layer, src/circuit.h:39-74 */
+    int32_t ty;
+    uint32_t size, size_u[2], size_v[2];
+    int8_t bit_length_u[2], bit_length_v[2], bit_length, max_bl_u, max_bl_v;
+    uint8_t need_phase2;
+    uint32_t zero_start_id;
+    int8_t fft_bit_length;
+    uint64_t scale[ZK_FR_WORDS];
+    const zk_uni_gate *uni_gates; uint64_t n_uni;
+    const zk_bin_gate *bin_gates; uint64_t n_bin;
+    const uint32_t *ori_id_u;        /* size_u[0] entries */
+    const uint32_t *ori_id_v;        /* size_v[0] entries */
+} zk_layer_desc;
+
+/* layeredCircuit::size and ::two_mul (src/circuit.h:77-82, src/circuit.cpp:90-100) */
+int zk_circuit_begin(zk_ctx *ctx, uint32_t n_layers, const uint64_t *two_mul, uint32_t n_two_mul);
+int zk_circuit_layer(zk_ctx *ctx, uint32_t layer_id, const zk_layer_desc *desc);
+int zk_circuit_end(zk_ctx *ctx);     /* builds the device-resident gate schedules */
+/* prover::val[layer_id] (src/prover.hpp:49) */
+int zk_witness_layer(zk_ctx *ctx, uint32_t layer_id, const uint64_t *val, uint64_t n);
+
+/* ---- GKR prover: one entry point per public member of class prover ---------------------------------------------- */
+int zk_prover_init(zk_ctx *ctx);                                                             /* prover.cpp:17  */
+int zk_vres(zk_ctx *ctx, const uint64_t *r, uint32_t output_size, uint32_t r_size, uint64_t *out); /* :434 */
+int zk_sumcheck_init_all(zk_ctx *ctx, const uint64_t *r_0, uint32_t n);                      /* :28  */
+int zk_sumcheck_init(zk_ctx *ctx, const uint64_t *alpha, const uint64_t *beta);              /* :43  */
+int zk_sumcheck_dotprod_init_phase1(zk_ctx *ctx);                                            /* :57  */
+int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou);                          /* :155 */
+int zk_sumcheck_init_phase2(zk_ctx *ctx);                                                    /* :241 */
+int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *abcd /*4 Fr*/);  /* :103 */
+int zk_sumcheck_update1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *abc /*3 Fr*/);           /* :360 */
+int zk_sumcheck_update2(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *abc /*3 Fr*/);           /* :364 */
+int zk_sumcheck_dotprod_finalize1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_1);      /* :146 */
+int zk_sumcheck_finalize1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_0, uint64_t *claim_1); /* :459 */
+int zk_sumcheck_finalize2(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_0, uint64_t *claim_1); /* :473 */
+int zk_sumcheck_liu_init(zk_ctx *ctx, const uint64_t *s_u, const uint64_t *s_v, uint32_t n);  /* :312 */
+int zk_sumcheck_liu_update(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *abc);      /* :385 */
+int zk_sumcheck_liu_finalize(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_1);/* :487 */
+
+/* ---- Hyrax polynomial commitment: one entry point per public member of class polyProver --------------------------
+ * (3rd/hyrax-bls12-381/src/polyProver.cpp).  A ctx holds one polynomial at a time. */
+/* prover::commitInput (prover.cpp:503): zero-pads val[0] to 2^bit_length and binds it, on the device, as Z */
+int zk_poly_bind_input(zk_ctx *ctx, const uint64_t *gens, uint32_t n_gens);
+/* polyProver::polyProver(Z, gens) (polyProver.cpp:12-17) for a stand-alone polynomial */
+int zk_poly_create(zk_ctx *ctx, const uint64_t *Z, uint64_t n, const uint64_t *gens, uint32_t n_gens);
+int zk_poly_commit(zk_ctx *ctx, uint64_t *comm_out /* 2^(bl/2) points */, uint32_t n_out);     /* :19  */
+int zk_poly_evaluate(zk_ctx *ctx, const uint64_t *x, uint32_t n, uint64_t *out);              /* :36  */
+int zk_poly_init_bullet_prove(zk_ctx *ctx, const uint64_t *lx, uint32_t n_lx, const uint64_t *rx, uint32_t n_rx); /* :52 */
+int zk_poly_bullet_prove(zk_ctx *ctx, uint64_t *lcomm, uint64_t *rcomm, uint64_t *ly, uint64_t *ry);  /* :76  */
+int zk_poly_bullet_update(zk_ctx *ctx, const uint64_t *randomness);                           /* :98  */
+int zk_poly_bullet_open(zk_ctx *ctx, uint64_t *out);                                          /* :111 */
+
+/* ---- stateless primitives: the kernels behind the calls above, exposed for parity tests and micro-benchmarks ------ */
+/* out[i] = a[i] (+,-,*) b[i];  op: 0 add, 1 sub, 2 mul */
+int zk_fr_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n);
+/* initBetaTable(beta, bits, r, init)  (src/utils.cpp:168-180; also hyrax expand(), utils.cpp:29-62 with init = 1) */
+int zk_beta_table(zk_ctx *ctx, const uint64_t *r, uint32_t bits, const uint64_t *init, uint64_t *out);
+/* phiGInit (src/utils.cpp:61-103); out has 2^n (IFFT) or 2^(n-1) (FFT) entries */
+int zk_phi_table(zk_ctx *ctx, const uint64_t *rx, const uint64_t *scale, uint32_t n, int is_ifft, uint64_t *out);
+/* Runs `n_rounds` rounds of sumcheckUpdateEach on one (V, mult) pair of 2^bits entries (first `live` non-zero):
+ * round j uses previous_random = (j == 0 ? 0 : r[j-1]).  polys gets 3 Fr per round.  Returns folded tables if non-NULL. */
+int zk_fold_rounds(zk_ctx *ctx, const uint64_t *V, const uint64_t *M, uint32_t bits, uint64_t live, const uint64_t *r,
+                   uint32_t n_rounds, uint64_t *polys);
+/* out[k] = sum_j scalars[k*n + j] * bases[j]   (G1::mulVec semantics, mcl ec.hpp:1570-1597), k < n_rows */
+int zk_msm(zk_ctx *ctx, const uint64_t *bases, const uint64_t *scalars, uint64_t n, uint32_t n_rows, uint64_t *out);
+/* element-wise G1: op 0: out = a + b; 1: out = 2a; 2: out = k*a (k = b reinterpreted as Fr per element) */
+int zk_g1_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n);
+/* device self-test: inline-PTX field arithmetic against the portable implementation on n random inputs; 0 = equal */
+int zk_selftest(zk_ctx *ctx, uint64_t seed, uint32_t n);
+
+/* ---- device-timed micro-benchmarks (CUDA events on the launching stream; inputs resident in HBM) ------------------ */
+/* one K1 round on a table pair of 2^bits entries, `iters` launches; returns average ms per launch in *ms */
+int zk_bench_fold(zk_ctx *ctx, uint32_t bits, uint32_t iters, int fold, float *ms);
+int zk_bench_msm(zk_ctx *ctx, uint32_t log_rows, uint32_t log_cols, int scalar_mix, uint32_t iters, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKCNN_B200_H */

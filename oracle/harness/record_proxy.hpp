@@ -1,0 +1,99 @@
+// TEST INFRASTRUCTURE (oracle harness).  Recording proxy in front of the UNMODIFIED reference prover.
+//
+// The reference never serialises a proof: prover->verifier messages are C++ return values (src/prover.hpp:26-38,
+// hyrax/src/polyProver.hpp:22-36).  To mint golden transcripts without touching any reference file, the reference's
+// prover.cpp / polyProver.cpp are compiled with  -Dprover=ref_prover -DpolyProver=ref_polyProver  (oracle/Makefile)
+// and the reference's verifier.cpp / polyVerifier.cpp are compiled with  -include record_proxy.hpp , which
+//   1. pulls in the reference class declarations under their moved names,
+//   2. declares `class prover` / `class hyrax_bls12_381::polyProver` as thin forwarders that append every value
+//      handed to the verifier to transcript() in SURVEY.md Appendix-A order.
+// The reference headers' own include guards then keep verifier.hpp from re-declaring the classes.
+#pragma once
+#include <memory>
+#include <vector>
+#include <mcl/bls12_381.hpp>
+
+// ---- 1. hyrax prover under its moved name -------------------------------------------------------------------------
+#define polyProver ref_polyProver
+#include <hyrax-bls12-381/src/polyProver.hpp>
+#undef polyProver
+
+#include "dump_io.hpp"
+
+namespace hyrax_bls12_381 {
+class polyProver {
+public:
+    explicit polyProver(ref_polyProver &impl) : impl_(impl) {}
+    std::vector<G1> commit() {
+        auto c = impl_.commit();
+        for (auto &p : c) transcript().put(p);
+        return c;
+    }
+    Fr evaluate(const std::vector<Fr> &x) { return impl_.evaluate(x); }
+    double getPT() const { return impl_.getPT(); }
+    double getPS() const { return impl_.getPS(); }
+    void initBulletProve(const std::vector<Fr> &lx, const std::vector<Fr> &rx) { impl_.initBulletProve(lx, rx); }
+    void bulletProve(G1 &lcomm, G1 &rcomm, Fr &ly, Fr &ry) {
+        impl_.bulletProve(lcomm, rcomm, ly, ry);
+        transcript().put(lcomm); transcript().put(rcomm); transcript().put(ly); transcript().put(ry);
+    }
+    void bulletUpdate(const Fr &r) { impl_.bulletUpdate(r); }
+    Fr bulletOpen() { Fr y = impl_.bulletOpen(); transcript().put(y); return y; }
+    const std::vector<G1> &getGens() const { return impl_.getGens(); }
+private:
+    ref_polyProver &impl_;
+};
+}  // namespace hyrax_bls12_381
+
+// polyVerifier.hpp must see the proxy, not the moved class
+#include <hyrax-bls12-381/src/polyVerifier.hpp>
+
+// ---- 2. GKR prover under its moved name ---------------------------------------------------------------------------
+#define polyProver ref_polyProver
+#define prover ref_prover
+#include <prover.hpp>          // reference src/prover.hpp (pulls global_var.hpp, circuit.h, polynomial.h)
+#undef prover
+#undef polyProver
+
+class prover {
+public:
+    explicit prover(ref_prover &impl) : C(impl.C), val(impl.val), impl_(impl) {}
+    void init() { impl_.init(); }
+    void sumcheckInitAll(const vector<F>::const_iterator &r) { impl_.sumcheckInitAll(r); }
+    void sumcheckInit(const F &a, const F &b) { impl_.sumcheckInit(a, b); }
+    void sumcheckDotProdInitPhase1() { impl_.sumcheckDotProdInitPhase1(); }
+    void sumcheckInitPhase1(const F &rr) { impl_.sumcheckInitPhase1(rr); }
+    void sumcheckInitPhase2() { impl_.sumcheckInitPhase2(); }
+    cubic_poly sumcheckDotProdUpdate1(const F &r) {
+        auto p = impl_.sumcheckDotProdUpdate1(r);
+        transcript().put(p.a); transcript().put(p.b); transcript().put(p.c); transcript().put(p.d);
+        return p;
+    }
+    quadratic_poly sumcheckUpdate1(const F &r) { return rec(impl_.sumcheckUpdate1(r)); }
+    quadratic_poly sumcheckUpdate2(const F &r) { return rec(impl_.sumcheckUpdate2(r)); }
+    F Vres(const vector<F>::const_iterator &r, u32 n, u8 bl) { F v = impl_.Vres(r, n, bl); transcript().put(v); return v; }
+    void sumcheckDotProdFinalize1(const F &r, F &c1) { impl_.sumcheckDotProdFinalize1(r, c1); transcript().put(c1); }
+    void sumcheckFinalize1(const F &r, F &c0, F &c1) { impl_.sumcheckFinalize1(r, c0, c1); transcript().put(c0); transcript().put(c1); }
+    void sumcheckFinalize2(const F &r, F &c0, F &c1) { impl_.sumcheckFinalize2(r, c0, c1); transcript().put(c0); transcript().put(c1); }
+    void sumcheckLiuFinalize(const F &r, F &c1) { impl_.sumcheckLiuFinalize(r, c1); transcript().put(c1); }
+    void sumcheckLiuInit(const vector<F> &su, const vector<F> &sv) { impl_.sumcheckLiuInit(su, sv); }
+    quadratic_poly sumcheckLiuUpdate(const F &r) { return rec(impl_.sumcheckLiuUpdate(r)); }
+    hyrax_bls12_381::polyProver &commitInput(const vector<G> &gens) {
+        poly_proxy_.reset(new hyrax_bls12_381::polyProver(impl_.commitInput(gens)));
+        return *poly_proxy_;
+    }
+    double proveTime() const { return impl_.proveTime(); }
+    double proofSize() const { return impl_.proofSize(); }
+    double polyProverTime() const { return impl_.polyProverTime(); }
+    double polyProofSize() const { return impl_.polyProofSize(); }
+
+    layeredCircuit &C;
+    vector<vector<F>> &val;
+private:
+    quadratic_poly rec(const quadratic_poly &p) {
+        transcript().put(p.a); transcript().put(p.b); transcript().put(p.c);
+        return p;
+    }
+    ref_prover &impl_;
+    std::unique_ptr<hyrax_bls12_381::polyProver> poly_proxy_;
+};

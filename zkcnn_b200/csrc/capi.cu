@@ -1,0 +1,578 @@
+// C ABI implementation (include/zkcnn_b200.h).  Host-side orchestration of the sm_100a kernels; the control flow of
+// every entry point mirrors the reference member function cited in the header, the arithmetic runs on the device.
+#include "capi_sumcheck.cuh"
+#include "capi_hyrax.cuh"
+
+using namespace zk;
+
+extern "C" {
+
+const char *zk_last_error(void) { return g_last_error.c_str(); }
+
+const char *zk_version(void) {
+#ifdef ZK_EMU
+    return "zkcnn_b200 0.1 emu (test-only host build)";
+#else
+    return "zkcnn_b200 0.1 sm_100a";
+#endif
+}
+
+int zk_device_count(void) { return rt::device_count(); }
+
+zk_ctx *zk_ctx_create(int device) {
+    try {
+        ZK_REQUIRE(rt::device_count() > 0, "no CUDA device: zkcnn_b200 has no CPU fallback");
+        ZK_REQUIRE(device >= 0 && device < rt::device_count(), "bad device index");
+        rt::set_device(device);
+        std::unique_ptr<zk_ctx> c(new zk_ctx);
+        c->device = device;
+        c->stream = rt::stream_create();
+        return c.release();
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return nullptr;
+    }
+}
+
+void zk_ctx_destroy(zk_ctx *ctx) {
+    if (!ctx) return;
+    try { rt::set_device(ctx->device); rt::sync(ctx->stream); } catch (...) {}
+    rt::hfree_pinned(ctx->h_out);
+    rt::stream_destroy(ctx->stream);
+    delete ctx;
+}
+
+uint64_t zk_ctx_launch_count(const zk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- circuit ----------------------------------------------------------------------------------------------------------
+int zk_circuit_begin(zk_ctx *ctx, uint32_t n_layers, const uint64_t *two_mul, uint32_t n_two_mul) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && n_layers >= 2 && n_layers <= 255, "bad layer count");
+    ZK_REQUIRE(two_mul && n_two_mul >= 1 && n_two_mul <= 512, "bad two_mul table");
+    rt::set_device(ctx->device);
+    ctx->layers.clear();
+    ctx->layers.resize(n_layers);
+    ctx->n_layers = n_layers;
+    ctx->circuit_ready = false;
+    ctx->two_mul_h.resize(n_two_mul);
+    memcpy(ctx->two_mul_h.data(), two_mul, (size_t) n_two_mul * 32);
+    ctx->two_mul.ensure(512 * sizeof(fr_t));
+    rt::h2d(ctx->two_mul.p, two_mul, (size_t) n_two_mul * 32, ctx->stream);
+    rt::sync(ctx->stream);
+    ZK_API_END
+}
+
+int zk_circuit_layer(zk_ctx *ctx, uint32_t id, const zk_layer_desc *D) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && D && id < ctx->n_layers, "bad layer id");
+    rt::set_device(ctx->device);
+    layer_t &L = ctx->layers[id];
+    L.d = *D;
+    L.d.uni_gates = nullptr; L.d.bin_gates = nullptr; L.d.ori_id_u = nullptr; L.d.ori_id_v = nullptr;
+    L.scale = fr_load(D->scale);
+    ZK_REQUIRE(D->bit_length >= 0 && D->bit_length <= 29, "layer too large");
+    if (D->size_u[0]) {
+        ZK_REQUIRE(D->ori_id_u, "ori_id_u missing");
+        L.ori_u.ensure((size_t) D->size_u[0] * 4);
+        rt::h2d(L.ori_u.p, D->ori_id_u, (size_t) D->size_u[0] * 4, ctx->stream);
+    }
+    if (D->size_v[0]) {
+        ZK_REQUIRE(D->ori_id_v, "ori_id_v missing");
+        L.ori_v.ensure((size_t) D->size_v[0] * 4);
+        rt::h2d(L.ori_v.p, D->ori_id_v, (size_t) D->size_v[0] * 4, ctx->stream);
+    }
+    rt::sync(ctx->stream);
+    build_layer_schedules(ctx, id, D);
+    L.have_desc = true;
+    ZK_API_END
+}
+
+int zk_circuit_end(zk_ctx *ctx) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx, "null ctx");
+    for (auto &L : ctx->layers) ZK_REQUIRE(L.have_desc, "a layer was not uploaded");
+    ctx->circuit_ready = true;
+    ZK_API_END
+}
+
+int zk_witness_layer(zk_ctx *ctx, uint32_t id, const uint64_t *val, uint64_t n) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && id < ctx->n_layers && (val || n == 0), "bad witness layer");
+    rt::set_device(ctx->device);
+    layer_t &L = ctx->layers[id];
+    // layer 0 is kept zero-padded to a power of two so that Hyrax can alias it (src/prover.cpp:504-508)
+    uint64_t cap = n;
+    if (id == 0) { cap = 1; while (cap < n) cap <<= 1; }
+    L.val.ensure(std::max<uint64_t>(1, cap) * sizeof(fr_t));
+    rt::h2d(L.val.p, val, n * sizeof(fr_t), ctx->stream);
+    if (cap > n) rt::dzero(L.val.as<fr_t>() + n, (cap - n) * sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    L.n_val = n;
+    ZK_API_END
+}
+
+// ---- GKR prover -------------------------------------------------------------------------------------------------------
+int zk_prover_init(zk_ctx *ctx) {   // prover::init, src/prover.cpp:17-21
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready, "circuit not uploaded");
+    ctx->r_u.assign(ctx->n_layers + 1, {});
+    ctx->r_v.assign(ctx->n_layers + 1, {});
+    ZK_API_END
+}
+
+int zk_vres(zk_ctx *ctx, const uint64_t *r, uint32_t output_size, uint32_t r_size, uint64_t *out) {   // src/prover.cpp:434-457
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready && out, "bad arguments");
+    rt::set_device(ctx->device);
+    layer_t &L = ctx->layers[ctx->n_layers - 1];
+    ZK_REQUIRE(output_size <= L.n_val && r_size <= 24 && (r || r_size == 0), "bad output size");
+    ensure_round_scratch(ctx);
+    ctx->d_r.ensure(2 * 64 * sizeof(fr_t));
+    rt::h2d(ctx->d_r.p, r, (size_t) r_size * 32, ctx->stream);
+    ctx->vres_scratch.ensure(sizeof(fr_t) << r_size);
+    ZK_KLAUNCH(ctx, k_vres, dim3(1), dim3(kBlock), 0, L.val.as<fr_t>(), output_size, ctx->d_r.as<fr_t>(), r_size,
+               ctx->vres_scratch.as<fr_t>(), ctx->round_out.as<fr_t>());
+    rt::d2h(ctx->h_out, ctx->round_out.p, sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    fr_store(out, ctx->h_out[0]);
+    ZK_API_END
+}
+
+int zk_sumcheck_init_all(zk_ctx *ctx, const uint64_t *r_0, uint32_t n) {   // src/prover.cpp:28-36
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready && !ctx->r_u.empty(), "prover not initialised");
+    ctx->sumcheck_id = ctx->n_layers;
+    const int last_bl = ctx->layers[ctx->n_layers - 1].d.bit_length;
+    ZK_REQUIRE((int) n >= last_bl, "r_0 too short");
+    ctx->r_u[ctx->sumcheck_id].resize(last_bl);
+    for (int i = 0; i < last_bl; ++i) ctx->r_u[ctx->sumcheck_id][i] = fr_load(r_0 + 4 * i);
+    ZK_API_END
+}
+
+int zk_sumcheck_init(zk_ctx *ctx, const uint64_t *alpha, const uint64_t *beta) {   // src/prover.cpp:43-52
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready && ctx->sumcheck_id >= 1, "bad state");
+    ctx->alpha = fr_load(alpha);
+    ctx->beta = fr_load(beta);
+    --ctx->sumcheck_id;   // r_0 / r_1 are r_u / r_v of level sumcheck_id + 1 from here on
+    ZK_API_END
+}
+
+int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/prover.cpp:155-239
+    ZK_API_BEGIN
+    layer_t &L = cur_layer(ctx);
+    rt::set_device(ctx->device);
+    const zk_layer_desc &d = L.d;
+    const uint32_t id = ctx->sumcheck_id;
+    ZK_REQUIRE(id >= 1 && d.ty != ZK_LAYER_DOT_PROD, "wrong init for this layer");
+    for (int b = 0; b < 2; ++b) pair_reset(ctx->pair[b], d.bit_length_u[b], d.size_u[b]);
+    ctx->r_u[id].resize(d.max_bl_u);
+    ctx->relu_rou = fr_load(relu_rou_p);
+    ctx->add_term = fr_t::zero();
+    const std::vector<fr_t> &r0 = ctx->r_u[id + 1];
+    const std::vector<fr_t> &r1 = ctx->r_v[id + 1];
+    layer_t &prev = ctx->layers[id - 1];
+    const uint32_t tail_start = d.zero_start_id < d.size ? d.zero_start_id : 0xffffffffu;
+
+    if (d.ty == ZK_LAYER_FFT || d.ty == ZK_LAYER_IFFT) {
+        const bool is_fft = d.ty == ZK_LAYER_FFT;
+        const uint32_t fft_bl = d.fft_bit_length, fft_blh = fft_bl - 1;
+        const uint32_t cnt_bl = is_fft ? d.bit_length - fft_bl : d.bit_length - fft_blh;
+        const uint32_t cnt_len = d.size >> (is_fft ? fft_bl : fft_blh);
+        ctx->beta_g.ensure(sizeof(fr_t) << cnt_bl);
+        ctx->beta_g_entries = 1u << cnt_bl;
+        if (is_fft) {
+            ZK_REQUIRE(r0.size() >= fft_bl + cnt_bl, "r_0 too short");
+            ZK_REQUIRE(ctx->beta.is_zero() || r1.size() >= cnt_bl, "r_1 too short");
+            beta_point_t pts[2] = {{r0.data() + fft_bl, ctx->alpha}, {r1.data(), ctx->beta}};
+            build_beta(ctx, ctx->beta_g.as<fr_t>(), cnt_bl, pts, 2);
+        } else {
+            ZK_REQUIRE(r0.size() >= fft_blh + cnt_bl, "r_0 too short");
+            beta_point_t pts[1] = {{r0.data() + fft_blh, ctx->alpha}};
+            build_beta(ctx, ctx->beta_g.as<fr_t>(), cnt_bl, pts, 1);
+        }
+        // V_mult[1][u] = sum_g val[l][g << max_bl_u | u] * beta_g[g]
+        pair_t &P = ctx->pair[1];
+        ZK_REQUIRE(P.exists && d.size_u[1] == P.n_eval, "unexpected FFT layer shape");
+        ZK_REQUIRE(((uint64_t) cnt_len << d.max_bl_u) <= prev.n_val, "FFT source layer too small");
+        fr_t *V = table_init_buf(P.v, P.n_eval);
+        const uint32_t n_u = P.n_eval;
+        uint32_t n_chunks = std::max(1u, std::min(cnt_len, (uint32_t) ((ZK_SM_COUNT * 8 * kBlock) / std::max(1u, n_u))));
+        const uint32_t g_per_chunk = (cnt_len + n_chunks - 1) / n_chunks;
+        n_chunks = (cnt_len + g_per_chunk - 1) / g_per_chunk;
+        ctx->dense_partial.ensure((size_t) n_chunks * n_u * sizeof(fr_t));
+        ZK_KLAUNCH(ctx, k_dense_colsum, dim3((n_u + kBlock - 1) / kBlock, n_chunks), dim3(kBlock), 0, prev.val.as<fr_t>(),
+                   ctx->beta_g.as<fr_t>(), n_u, (uint32_t) d.max_bl_u, cnt_len, g_per_chunk, ctx->dense_partial.as<fr_t>());
+        ZK_KLAUNCH(ctx, k_colsum_finish, dim3((n_u + kBlock - 1) / kBlock), dim3(kBlock), 0, ctx->dense_partial.as<fr_t>(), n_u,
+                   n_chunks, V);
+        // mult_array[1] = phiGInit(r_0, scale)
+        fr_t *M = table_init_buf(P.m, P.n_eval);
+        ZK_REQUIRE(r0.size() >= fft_bl - (is_fft ? 0 : 1), "r_0 too short for phi table");
+        ctx->d_r.ensure(2 * 64 * sizeof(fr_t));
+        rt::h2d(ctx->d_r.p, r0.data(), std::min<size_t>(r0.size(), fft_bl) * sizeof(fr_t), ctx->stream);
+        const fr_t *pw = phi_powers(ctx, fft_bl, !is_fft);
+        ZK_KLAUNCH(ctx, k_phi_table, dim3(1), dim3(kBlock), 0, M, ctx->d_r.as<fr_t>(), pw, L.scale, (int) fft_bl, (int) !is_fft);
+    } else {
+        // V tables
+        if (ctx->pair[0].exists) {
+            fr_t *V = table_init_buf(ctx->pair[0].v, ctx->pair[0].n_eval);
+            if (d.size_u[0])
+                ZK_KLAUNCH(ctx, k_gather, dim3(grid_for(d.size_u[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
+                           L.ori_u.as<uint32_t>(), d.size_u[0]);
+        }
+        if (ctx->pair[1].exists) {
+            ZK_REQUIRE(d.size_u[1] <= prev.n_val, "previous layer witness missing");
+            ctx->pair[1].v.cur = prev.val.as<fr_t>();
+        }
+        // beta_g
+        if (d.ty == ZK_LAYER_PADDING) {
+            const uint32_t fft_blh = d.fft_bit_length - 1;
+            ZK_REQUIRE(ctx->beta_g_entries >= (1u << (d.bit_length - fft_blh)), "PADDING layer needs the FFT layer's beta_g");
+            ctx->beta_gs.ensure(sizeof(fr_t) << fft_blh);
+            beta_point_t pts[1] = {{r0.data(), fr_t::one()}};
+            ZK_REQUIRE(r0.size() >= fft_blh, "r_0 too short");
+            build_beta(ctx, ctx->beta_gs.as<fr_t>(), fft_blh, pts, 1);
+            ctx->beta_g_alt.ensure(sizeof(fr_t) << d.bit_length);
+            ZK_KLAUNCH(ctx, k_beta_outer, dim3(grid_for(1ull << d.bit_length)), dim3(kBlock), 0, ctx->beta_g_alt.as<fr_t>(),
+                       ctx->beta_g.as<fr_t>(), ctx->beta_gs.as<fr_t>(), (uint32_t) d.bit_length, fft_blh, tail_start, ctx->relu_rou);
+            std::swap(ctx->beta_g, ctx->beta_g_alt);
+        } else {
+            ctx->beta_g.ensure(sizeof(fr_t) << d.bit_length);
+            ZK_REQUIRE(r0.size() >= (size_t) d.bit_length, "r_0 too short");
+            ZK_REQUIRE(ctx->beta.is_zero() || r1.size() >= (size_t) d.bit_length, "r_1 too short");
+            beta_point_t pts[2] = {{r0.data(), ctx->alpha * L.scale}, {r1.data(), ctx->beta * L.scale}};
+            build_beta(ctx, ctx->beta_g.as<fr_t>(), d.bit_length, pts, 2, tail_start, ctx->relu_rou);
+        }
+        ctx->beta_g_entries = 1u << d.bit_length;
+        // mult tables: gate gather-reduce
+        gate_args_t A;
+        memset(&A, 0, sizeof A);
+        for (int b = 0; b < 2; ++b)
+            if (ctx->pair[b].exists) {
+                fr_t *M = table_init_buf(ctx->pair[b].m, ctx->pair[b].n_eval);
+                rt::dzero(M, (size_t) ctx->pair[b].n_eval * sizeof(fr_t), ctx->stream);
+                (b ? A.out1 : A.out0) = M;
+            }
+        A.beta_g = ctx->beta_g.as<fr_t>();
+        A.val0 = ctx->layers[0].val.as<fr_t>();
+        A.val_prev = prev.val.as<fr_t>();
+        A.two_mul = ctx->two_mul.as<fr_t>();
+        run_schedule(ctx, L.p1, 1, A);
+    }
+    ctx->round = 0;
+    ZK_API_END
+}
+
+int zk_sumcheck_init_phase2(zk_ctx *ctx) {   // src/prover.cpp:241-310
+    ZK_API_BEGIN
+    layer_t &L = cur_layer(ctx);
+    rt::set_device(ctx->device);
+    const zk_layer_desc &d = L.d;
+    const uint32_t id = ctx->sumcheck_id;
+    ZK_REQUIRE(id >= 1 && d.need_phase2, "layer has no phase 2");
+    for (int b = 0; b < 2; ++b) pair_reset(ctx->pair[b], d.bit_length_v[b], d.size_v[b]);
+    ctx->r_v[id].resize(d.max_bl_v);
+    ctx->add_term = fr_t::zero();
+    layer_t &prev = ctx->layers[id - 1];
+    const std::vector<fr_t> &ru = ctx->r_u[id];
+    ensure_round_scratch(ctx);
+
+    gate_args_t A;
+    memset(&A, 0, sizeof A);
+    A.beta_g = ctx->beta_g.as<fr_t>();
+    A.two_mul = ctx->two_mul.as<fr_t>();
+    A.vu[0] = ctx->V_u0;
+    A.vu[1] = ctx->V_u1;
+    ctx->scalar_slot.ensure(sizeof(fr_t));
+    A.out_scalar = ctx->scalar_slot.as<fr_t>();
+
+    if (d.ty == ZK_LAYER_DOT_PROD) {
+        const uint32_t fft_bl = d.fft_bit_length, cnt_bl = d.max_bl_v;
+        ZK_REQUIRE(ru.size() >= fft_bl + cnt_bl, "r_u too short");
+        ctx->beta_u.ensure(sizeof(fr_t) << cnt_bl);
+        ctx->beta_gs.ensure(sizeof(fr_t) << fft_bl);
+        beta_point_t p1[1] = {{ru.data() + fft_bl, fr_t::one()}};
+        build_beta(ctx, ctx->beta_u.as<fr_t>(), cnt_bl, p1, 1);
+        beta_point_t p2[1] = {{ru.data(), fr_t::one()}};
+        build_beta(ctx, ctx->beta_gs.as<fr_t>(), fft_bl, p2, 1);
+        pair_t &P = ctx->pair[1];
+        ZK_REQUIRE(P.exists && !ctx->pair[0].exists, "unexpected DOT_PROD shape");
+        ZK_REQUIRE(((uint64_t) d.size_v[1] << fft_bl) <= prev.n_val, "DOT_PROD source layer too small");
+        fr_t *V = table_init_buf(P.v, P.n_eval);
+        if (d.size_v[1])
+            ZK_KLAUNCH(ctx, k_dense_rowdot, dim3(d.size_v[1]), dim3(kBlock), 0, V, prev.val.as<fr_t>(), ctx->beta_gs.as<fr_t>(), fft_bl);
+        fr_t *M = table_init_buf(P.m, P.n_eval);
+        rt::dzero(M, (size_t) P.n_eval * sizeof(fr_t), ctx->stream);
+        A.out1 = M;
+        A.beta_u = ctx->beta_u.as<fr_t>();
+        run_schedule(ctx, L.p2, 2, A);
+    } else {
+        ZK_REQUIRE(ru.size() >= (size_t) d.max_bl_u, "r_u too short");
+        ctx->beta_u.ensure(sizeof(fr_t) << d.max_bl_u);
+        beta_point_t p1[1] = {{ru.data(), fr_t::one()}};
+        build_beta(ctx, ctx->beta_u.as<fr_t>(), d.max_bl_u, p1, 1);
+        if (ctx->pair[0].exists) {
+            fr_t *V = table_init_buf(ctx->pair[0].v, ctx->pair[0].n_eval);
+            if (d.size_v[0])
+                ZK_KLAUNCH(ctx, k_gather, dim3(grid_for(d.size_v[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
+                           L.ori_v.as<uint32_t>(), d.size_v[0]);
+        }
+        if (ctx->pair[1].exists) {
+            ZK_REQUIRE(d.size_v[1] <= prev.n_val, "previous layer witness missing");
+            ctx->pair[1].v.cur = prev.val.as<fr_t>();
+        }
+        for (int b = 0; b < 2; ++b)
+            if (ctx->pair[b].exists) {
+                fr_t *M = table_init_buf(ctx->pair[b].m, ctx->pair[b].n_eval);
+                rt::dzero(M, (size_t) ctx->pair[b].n_eval * sizeof(fr_t), ctx->stream);
+                (b ? A.out1 : A.out0) = M;
+            }
+        A.beta_u = ctx->beta_u.as<fr_t>();
+        run_schedule(ctx, L.p2, 2, A);
+        if (L.p2.has_scalar) {   // add_term of the uni gates (src/prover.cpp:297-300)
+            rt::d2h(ctx->h_out, ctx->scalar_slot.p, sizeof(fr_t), ctx->stream);
+            rt::sync(ctx->stream);
+            ctx->add_term = ctx->h_out[0];
+        }
+    }
+    ctx->round = 0;
+    ZK_API_END
+}
+
+static int sumcheck_update(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *abc, std::vector<fr_t> &r_arr) {   // src/prover.cpp:368-383
+    ZK_API_BEGIN
+    rt::set_device(ctx->device);
+    const fr_t prev = fr_load(prev_p);
+    if (ctx->round) {
+        ZK_REQUIRE(ctx->round - 1 < r_arr.size(), "too many rounds");
+        r_arr[ctx->round - 1] = prev;
+    }
+    ++ctx->round;
+    ctx->add_term = ctx->add_term * (fr_t::one() - prev);
+    fr_t ret[3];
+    round_quadratic(ctx, prev, 3u, ret);
+    ret[1] = ret[1] - ctx->add_term;
+    ret[2] = ret[2] + ctx->add_term;
+    for (int k = 0; k < 3; ++k) fr_store(abc + 4 * k, ret[k]);
+    ZK_API_END
+}
+
+int zk_sumcheck_update1(zk_ctx *ctx, const uint64_t *prev, uint64_t *abc) {
+    if (!ctx || !ctx->circuit_ready || ctx->sumcheck_id >= ctx->r_u.size()) { g_last_error = "bad state"; return -1; }
+    return sumcheck_update(ctx, prev, abc, ctx->r_u[ctx->sumcheck_id]);
+}
+int zk_sumcheck_update2(zk_ctx *ctx, const uint64_t *prev, uint64_t *abc) {
+    if (!ctx || !ctx->circuit_ready || ctx->sumcheck_id >= ctx->r_v.size()) { g_last_error = "bad state"; return -1; }
+    return sumcheck_update(ctx, prev, abc, ctx->r_v[ctx->sumcheck_id]);
+}
+
+int zk_sumcheck_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_0, uint64_t *claim_1) {   // src/prover.cpp:459-471
+    ZK_API_BEGIN
+    cur_layer(ctx);
+    rt::set_device(ctx->device);
+    const fr_t prev = fr_load(prev_p);
+    std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
+    ZK_REQUIRE(ctx->round >= 1 && ctx->round - 1 < ru.size(), "finalize without rounds");
+    ru[ctx->round - 1] = prev;
+    fr_t c[2];
+    final_values(ctx, prev, c);
+    ctx->V_u0 = c[0];
+    ctx->V_u1 = c[1];
+    fr_store(claim_0, c[0]);
+    fr_store(claim_1, c[1]);
+    ctx->pair[0].n_eval = ctx->pair[1].n_eval = 0;
+    ZK_API_END
+}
+
+int zk_sumcheck_finalize2(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_0, uint64_t *claim_1) {   // src/prover.cpp:473-485
+    ZK_API_BEGIN
+    cur_layer(ctx);
+    rt::set_device(ctx->device);
+    const fr_t prev = fr_load(prev_p);
+    std::vector<fr_t> &rv = ctx->r_v[ctx->sumcheck_id];
+    ZK_REQUIRE(ctx->round >= 1 && ctx->round - 1 < rv.size(), "finalize without rounds");
+    rv[ctx->round - 1] = prev;
+    fr_t c[2];
+    final_values(ctx, prev, c);
+    fr_store(claim_0, c[0]);
+    fr_store(claim_1, c[1]);
+    ctx->pair[0].n_eval = ctx->pair[1].n_eval = 0;
+    ZK_API_END
+}
+
+// ---- FFT-convolution (DOT_PROD) layer ------------------------------------------------------------------------------------
+int zk_sumcheck_dotprod_init_phase1(zk_ctx *ctx) {   // src/prover.cpp:57-95
+    ZK_API_BEGIN
+    layer_t &L = cur_layer(ctx);
+    rt::set_device(ctx->device);
+    const zk_layer_desc &d = L.d;
+    const uint32_t id = ctx->sumcheck_id;
+    ZK_REQUIRE(id >= 1 && d.ty == ZK_LAYER_DOT_PROD, "not a DOT_PROD layer");
+    const uint32_t fft_bl = d.fft_bit_length;
+    layer_t &prev = ctx->layers[id - 1];
+    pair_reset(ctx->pair[0], -1, 0);
+    pair_reset(ctx->pair[1], d.bit_length_u[1], d.size_u[1]);
+    pair_t &P = ctx->pair[1];
+    ZK_REQUIRE(P.exists && d.bit_length_u[1] >= (int) fft_bl && d.size_u[1] <= prev.n_val, "unexpected DOT_PROD shape");
+    ctx->r_u[id].resize(d.max_bl_u);
+    const std::vector<fr_t> &r0 = ctx->r_u[id + 1];
+    ZK_REQUIRE(r0.size() >= fft_bl, "r_0 too short");
+    // mult_array[1] = beta table over the frequency index
+    ctx->mdp_n = 1u << fft_bl;
+    fr_t *M = table_init_buf(ctx->mdp, ctx->mdp_n);
+    ctx->mdp.next = 0;
+    beta_point_t pts[1] = {{r0.data(), fr_t::one()}};
+    build_beta(ctx, M, fft_bl, pts, 1);
+    // here pair[1].v plays V_mult[1] (activation FFT) and pair[1].m plays V_mult[0] (sum of beta_g * weight FFT)
+    P.v.cur = prev.val.as<fr_t>();
+    fr_t *V0 = table_init_buf(P.m, P.n_eval);
+    ZK_REQUIRE(L.dp_rows == (P.n_eval >> fft_bl), "DOT_PROD schedule missing");
+    ZK_KLAUNCH(ctx, k_dotprod_axpy, dim3(grid_for(P.n_eval)), dim3(kBlock), 0, V0, prev.val.as<fr_t>(), ctx->beta_g.as<fr_t>(),
+               L.dp_rowptr.as<uint32_t>(), L.dp_gates.as<dp_gate_t>(), L.dp_rows, fft_bl);
+    ctx->round = 0;
+    ZK_API_END
+}
+
+int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *abcd) {   // src/prover.cpp:103-144
+    ZK_API_BEGIN
+    cur_layer(ctx);
+    rt::set_device(ctx->device);
+    ensure_round_scratch(ctx);
+    const fr_t prev = fr_load(prev_p);
+    std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
+    if (ctx->round) {
+        ZK_REQUIRE(ctx->round - 1 < ru.size(), "too many rounds");
+        ru[ctx->round - 1] = prev;
+    }
+    ++ctx->round;
+    const bool first = ctx->round == 1;
+    pair_t &P = ctx->pair[1];
+    ZK_REQUIRE(P.n_eval >= (first ? 2u : 4u), "DOT_PROD tables exhausted");
+    if (!first && ctx->mdp_n >= 2) {   // fold the multiplier table (src/prover.cpp:112-118)
+        const uint32_t n_out = ctx->mdp_n >> 1;
+        fr_t *out = table_fold_buf(ctx->mdp, n_out);
+        ZK_KLAUNCH(ctx, k_fold_small, dim3(grid_for(n_out)), dim3(kBlock), 0, ctx->mdp.cur, out, n_out, prev);
+        table_advance(ctx->mdp);
+        ctx->mdp_n = n_out;
+    }
+    cubic_args_t A;
+    memset(&A, 0, sizeof A);
+    A.v0_in = P.m.cur; A.v1_in = P.v.cur;
+    A.n_in = P.n_eval; A.live = P.live; A.fold = first ? 0 : 1;
+    const uint32_t n_after = first ? P.n_eval : P.n_eval >> 1;
+    if (!first) {
+        A.v0_out = table_fold_buf(P.m, n_after);
+        A.v1_out = table_fold_buf(P.v, n_after);
+    }
+    A.m_in = ctx->mdp.cur;
+    A.m_n = ctx->mdp_n;
+    const uint32_t live_pairs = first ? (P.live + 1) >> 1 : (P.live + 3) >> 2;
+    A.n_blocks = grid_for(std::max(1u, live_pairs));
+    A.r = prev;
+    A.partials = ctx->partials.as<fr_t>();
+    A.counter = ctx->counters.as<uint32_t>() + 2;
+    A.out = ctx->round_out.as<fr_t>();
+    ZK_KLAUNCH(ctx, k_round_cubic, dim3(A.n_blocks), dim3(kBlock), 0, A);
+    rt::d2h(ctx->h_out, ctx->round_out.p, 4 * sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    if (!first) {
+        table_advance(P.m);
+        table_advance(P.v);
+        P.n_eval >>= 1;
+        P.live = (P.live + 1) >> 1;
+    }
+    for (int k = 0; k < 4; ++k) fr_store(abcd + 4 * k, ctx->h_out[k]);
+    ZK_API_END
+}
+
+int zk_sumcheck_dotprod_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_1) {   // src/prover.cpp:146-153
+    ZK_API_BEGIN
+    cur_layer(ctx);
+    rt::set_device(ctx->device);
+    ensure_round_scratch(ctx);
+    const fr_t prev = fr_load(prev_p);
+    std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
+    ZK_REQUIRE(ctx->round >= 1 && ctx->round - 1 < ru.size(), "finalize without rounds");
+    ru[ctx->round - 1] = prev;
+    pair_t &P = ctx->pair[1];
+    ZK_REQUIRE(P.n_eval == 2 && ctx->mdp_n >= 1 && ctx->mdp_n <= 2, "finalize called before the last round");
+    final_fold_args_t F;
+    memset(&F, 0, sizeof F);
+    F.r = prev;
+    F.out = ctx->round_out.as<fr_t>() + 8;
+    F.v_in[0] = P.v.cur; F.live[0] = P.live; F.fold[0] = 1; F.active[0] = 1;
+    F.v_in[1] = ctx->mdp.cur; F.live[1] = ctx->mdp_n; F.fold[1] = ctx->mdp_n == 2; F.active[1] = 1;
+    ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
+    rt::d2h(ctx->h_out, ctx->round_out.p, 16 * sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    const fr_t c1 = ctx->h_out[8], m = ctx->h_out[10];
+    ctx->V_u1 = c1 * m;
+    fr_store(claim_1, c1);
+    P.n_eval = 0;
+    ZK_API_END
+}
+
+// ---- input layer ("Liu") sumcheck -----------------------------------------------------------------------------------------
+int zk_sumcheck_liu_init(zk_ctx *ctx, const uint64_t *s_u, const uint64_t *s_v, uint32_t n) {   // src/prover.cpp:312-358
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready && !ctx->r_u.empty() && n + 1 >= ctx->n_layers, "bad state");
+    rt::set_device(ctx->device);
+    ctx->sumcheck_id = 0;
+    layer_t &L0 = ctx->layers[0];
+    const zk_layer_desc &d0 = L0.d;
+    ZK_REQUIRE(L0.n_val >= d0.size, "input layer witness missing");
+    pair_reset(ctx->pair[0], -1, 0);
+    pair_reset(ctx->pair[1], d0.bit_length, d0.size);
+    pair_t &P = ctx->pair[1];
+    ctx->r_u[0].resize(d0.bit_length);
+    ctx->add_term = fr_t::zero();
+    P.v.cur = L0.val.as<fr_t>();
+    fr_t *M = table_init_buf(P.m, P.n_eval);
+    rt::dzero(M, (size_t) P.n_eval * sizeof(fr_t), ctx->stream);
+    for (uint32_t i = 1; i < ctx->n_layers; ++i) {
+        layer_t &L = ctx->layers[i];
+        for (int side = 0; side < 2; ++side) {
+            const int bl = side ? L.d.bit_length_v[0] : L.d.bit_length_u[0];
+            const uint32_t sz = side ? L.d.size_v[0] : L.d.size_u[0];
+            if (bl < 0) continue;
+            const std::vector<fr_t> &r = side ? ctx->r_v[i] : ctx->r_u[i];
+            ZK_REQUIRE(r.size() >= (size_t) bl, "challenge vector of a finished layer is too short");
+            const fr_t sigma = fr_load((side ? s_v : s_u) + 4 * (i - 1));
+            if (sigma.is_zero() || sz == 0) continue;
+            beta_point_t pts[1] = {{r.data(), sigma}};
+            halves_t H = build_halves(ctx, bl, pts, 1);
+            ZK_KLAUNCH(ctx, k_liu_scatter, dim3(grid_for(sz)), dim3(kBlock), 0, M, (side ? L.ori_v : L.ori_u).as<uint32_t>(), sz, H.f[0],
+                       H.s[0], H.first_half);
+        }
+    }
+    ctx->round = 0;
+    ZK_API_END
+}
+
+int zk_sumcheck_liu_update(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *abc) {   // src/prover.cpp:385-394
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready && ctx->sumcheck_id == 0, "bad state");
+    rt::set_device(ctx->device);
+    const fr_t prev = fr_load(prev_p);
+    ++ctx->round;
+    fr_t ret[3];
+    round_quadratic(ctx, prev, 2u, ret);
+    for (int k = 0; k < 3; ++k) fr_store(abc + 4 * k, ret[k]);
+    ZK_API_END
+}
+
+int zk_sumcheck_liu_finalize(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_1) {   // src/prover.cpp:487-497
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready && ctx->sumcheck_id == 0, "bad state");
+    rt::set_device(ctx->device);
+    const fr_t prev = fr_load(prev_p);
+    ZK_REQUIRE(ctx->round >= 1 && ctx->round - 1 < ctx->r_u[0].size(), "finalize without rounds");
+    ctx->r_u[0][ctx->round - 1] = prev;
+    fr_t c[2];
+    final_values(ctx, prev, c);
+    fr_store(claim_1, c[1]);
+    ctx->pair[1].n_eval = 0;
+    ZK_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,437 @@
+// C ABI, part 1: circuit upload and the GKR prover state machine (mirror of src/prover.cpp of the reference).
+// Included by capi.cu only.
+#pragma once
+#include "ctx.hpp"
+#include <algorithm>
+#include <cstring>
+
+namespace zk {
+
+static thread_local std::string g_last_error;
+
+#define ZK_API_BEGIN try {
+#define ZK_API_END                                            \
+    return 0;                                                 \
+    } catch (const std::exception &e) {                       \
+        zk::g_last_error = e.what();                          \
+        return -1;                                            \
+    }
+#define ZK_REQUIRE(cond, msg) do { if (!(cond)) throw zk::rt::error(msg); } while (0)
+
+static inline fr_t fr_load(const uint64_t *p) { fr_t x; memcpy(x.v, p, 32); return x; }
+static inline void fr_store(uint64_t *p, const fr_t &x) { memcpy(p, x.v, 32); }
+static inline uint32_t grid_for(uint64_t work_items) {
+    uint64_t b = (work_items + kBlock - 1) / kBlock;
+    if (b < 1) b = 1;
+    if (b > (uint64_t) kMaxGridX) b = kMaxGridX;
+    return (uint32_t) b;
+}
+#define ZK_KLAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+    do {                                                                                  \
+        ZK_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);                 \
+        ++(ctx)->launches;                                                                \
+        zk::rt::check_launch(#kernel);                                                    \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------------------------------
+// schedule construction (host, once per circuit)
+// --------------------------------------------------------------------------------------------------------------------
+struct src_t { uint32_t rowkey; gate_rec_t rec; };  // rowkey: bits 30-31 = table (0, 1, 2 = scalar), bits 0-29 = row
+
+static void build_schedule(zk_ctx *ctx, schedule_t &S, std::vector<src_t> &src, uint32_t rows0, uint32_t rows1, bool split_kind) {
+    S.n_recs = src.size();
+    S.levels.clear();
+    S.max_partials = 0;
+    S.has_scalar = false;
+    if (src.empty()) return;
+    // stable counting sort by (table, row); callers emit kind-0 sources before kind-1 so kinds stay grouped per row
+    const uint64_t nkeys = (uint64_t) rows0 + rows1 + 1;
+    auto slot = [&](uint32_t rk) -> uint64_t {
+        uint32_t t = rk >> 30, r = rk & 0x3fffffffu;
+        return t == 0 ? r : t == 1 ? (uint64_t) rows0 + r : (uint64_t) rows0 + rows1;
+    };
+    std::vector<uint32_t> cnt(nkeys + 1, 0);
+    for (auto &s : src) ++cnt[slot(s.rowkey) + 1];
+    for (uint64_t i = 0; i < nkeys; ++i) cnt[i + 1] += cnt[i];
+    std::vector<src_t> sorted(src.size());
+    for (auto &s : src) sorted[cnt[slot(s.rowkey)]++] = s;
+    std::vector<src_t>().swap(src);
+
+    // level 0 items
+    std::vector<gate_rec_t> recs(sorted.size());
+    std::vector<item_t> items;
+    std::vector<uint32_t> item_row;
+    items.reserve(sorted.size() / kItemLen + 16);
+    item_row.reserve(sorted.size() / kItemLen + 16);
+    for (size_t i = 0; i < sorted.size();) {
+        const uint32_t rk = sorted[i].rowkey;
+        const uint32_t kind = (sorted[i].rec.meta >> 16) & 3u;
+        size_t j = i;
+        while (j < sorted.size() && j - i < (size_t) kItemLen && sorted[j].rowkey == rk &&
+               (!split_kind || ((sorted[j].rec.meta >> 16) & 3u) == kind))
+            ++j;
+        item_t it;
+        it.begin = (uint32_t) i;
+        it.dest = 0;
+        it.count_flags = (uint32_t) (j - i) | (split_kind ? (kind & 1u) << 16 : 0u);
+        items.push_back(it);
+        item_row.push_back(rk);
+        i = j;
+    }
+    for (size_t i = 0; i < sorted.size(); ++i) recs[i] = sorted[i].rec;
+    std::vector<src_t>().swap(sorted);
+    S.recs.ensure(recs.size() * sizeof(gate_rec_t));
+    rt::h2d(S.recs.p, recs.data(), recs.size() * sizeof(gate_rec_t), ctx->stream);
+    rt::sync(ctx->stream);
+    std::vector<gate_rec_t>().swap(recs);
+
+    auto final_dest = [&](uint32_t rk) -> uint32_t {
+        uint32_t t = rk >> 30, r = rk & 0x3fffffffu;
+        if (t == 2) { S.has_scalar = true; return kDestFinal | kDestScalar; }
+        ZK_REQUIRE(r < 0x20000000u, "table too large for the schedule encoding");
+        return kDestFinal | (t == 1 ? kDestTable1 : 0u) | r;
+    };
+    // finish a level: rows with a single item go to the table, others get consecutive partial slots and a next level
+    for (;;) {
+        std::vector<item_t> next_items;
+        std::vector<uint32_t> next_row;
+        uint32_t n_partials = 0;
+        for (size_t i = 0; i < items.size();) {
+            size_t j = i;
+            while (j < items.size() && item_row[j] == item_row[i]) ++j;
+            if (j - i == 1) items[i].dest = final_dest(item_row[i]);
+            else {
+                const uint32_t first = n_partials;
+                for (size_t k = i; k < j; ++k) items[k].dest = n_partials++;
+                for (uint32_t b = first; b < n_partials; b += kItemLen) {
+                    item_t it;
+                    it.begin = b;
+                    it.dest = 0;
+                    it.count_flags = std::min<uint32_t>(kItemLen, n_partials - b);
+                    next_items.push_back(it);
+                    next_row.push_back(item_row[i]);
+                }
+            }
+            i = j;
+        }
+        level_t L;
+        L.n_items = (uint32_t) items.size();
+        L.n_partials = n_partials;
+        L.items.ensure(items.size() * sizeof(item_t));
+        rt::h2d(L.items.p, items.data(), items.size() * sizeof(item_t), ctx->stream);
+        rt::sync(ctx->stream);
+        S.max_partials = std::max(S.max_partials, n_partials);
+        S.levels.push_back(std::move(L));
+        if (next_items.empty()) break;
+        items.swap(next_items);
+        item_row.swap(next_row);
+    }
+}
+
+static void build_layer_schedules(zk_ctx *ctx, uint32_t id, const zk_layer_desc *D) {
+    layer_t &L = ctx->layers[id];
+    const int ty = D->ty;
+    if (id == 0 || ty == ZK_LAYER_FFT || ty == ZK_LAYER_IFFT) return;
+    auto v_abs = [&](uint32_t v) { return D->ori_id_v[v]; };
+    const uint32_t rows_u0 = D->bit_length_u[0] >= 0 ? 1u << D->bit_length_u[0] : 0;
+    const uint32_t rows_u1 = D->bit_length_u[1] >= 0 ? 1u << D->bit_length_u[1] : 0;
+    const uint32_t rows_v0 = D->bit_length_v[0] >= 0 ? 1u << D->bit_length_v[0] : 0;
+    const uint32_t rows_v1 = D->bit_length_v[1] >= 0 ? 1u << D->bit_length_v[1] : 0;
+
+    if (ty == ZK_LAYER_DOT_PROD) {
+        // phase 1: CSR by u of (g, v)  (src/prover.cpp:86-91)
+        const uint32_t fft_bl = D->fft_bit_length;
+        const uint32_t n_rows = rows_u1 >> fft_bl;
+        std::vector<uint32_t> ptr(n_rows + 1, 0);
+        for (uint64_t i = 0; i < D->n_bin; ++i) {
+            ZK_REQUIRE(D->bin_gates[i].u < n_rows, "DOT_PROD gate.u out of range");
+            ++ptr[D->bin_gates[i].u + 1];
+        }
+        for (uint32_t i = 0; i < n_rows; ++i) ptr[i + 1] += ptr[i];
+        std::vector<dp_gate_t> g(D->n_bin);
+        std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);
+        for (uint64_t i = 0; i < D->n_bin; ++i) g[fill[D->bin_gates[i].u]++] = {D->bin_gates[i].g, D->bin_gates[i].v};
+        L.dp_rows = n_rows;
+        L.dp_rowptr.ensure(ptr.size() * 4);
+        L.dp_gates.ensure(std::max<size_t>(1, g.size()) * sizeof(dp_gate_t));
+        rt::h2d(L.dp_rowptr.p, ptr.data(), ptr.size() * 4, ctx->stream);
+        rt::h2d(L.dp_gates.p, g.data(), g.size() * sizeof(dp_gate_t), ctx->stream);
+        rt::sync(ctx->stream);
+        // phase 2: mult[1][v] += beta_g[g] beta_u[u] V_u1  (src/prover.cpp:286-288)
+        std::vector<src_t> src(D->n_bin);
+        for (uint64_t i = 0; i < D->n_bin; ++i) {
+            const zk_bin_gate &G = D->bin_gates[i];
+            src[i].rowkey = (1u << 30) | G.v;
+            src[i].rec = {G.g, G.u, (1u << 16)};
+        }
+        build_schedule(ctx, L.p2, src, rows_v0, rows_v1, true);
+        return;
+    }
+
+    {   // phase 1 (src/prover.cpp:224-233)
+        std::vector<src_t> src;
+        src.reserve(D->n_uni + D->n_bin);
+        for (uint64_t i = 0; i < D->n_uni; ++i) {
+            const zk_uni_gate &G = D->uni_gates[i];
+            src_t s;
+            s.rowkey = ((G.lu != 0 ? 1u : 0u) << 30) | G.u;
+            s.rec = {G.g, 0u, (uint32_t) G.sc};
+            src.push_back(s);
+        }
+        for (uint64_t i = 0; i < D->n_bin; ++i) {
+            const zk_bin_gate &G = D->bin_gates[i];
+            const bool u_prev = G.l != 0, v_prev = (G.l & 1) != 0;   // binGate::getLayerIdU/V, src/circuit.h:31-32
+            src_t s;
+            s.rowkey = ((u_prev ? 1u : 0u) << 30) | G.u;
+            s.rec = {G.g, v_prev ? G.v : v_abs(G.v), (uint32_t) G.sc | ((v_prev ? 2u : 1u) << 16)};
+            src.push_back(s);
+        }
+        build_schedule(ctx, L.p1, src, rows_u0, rows_u1, false);
+    }
+    if (D->need_phase2) {   // phase 2 (src/prover.cpp:297-305)
+        std::vector<src_t> src;
+        src.reserve(D->n_uni + D->n_bin);
+        for (int kind = 0; kind < 2; ++kind) {
+            for (uint64_t i = 0; i < D->n_uni; ++i) {
+                const zk_uni_gate &G = D->uni_gates[i];
+                if ((G.lu != 0) != (kind != 0)) continue;
+                src_t s;
+                s.rowkey = 2u << 30;
+                s.rec = {G.g, G.u, (uint32_t) G.sc | ((uint32_t) kind << 16)};
+                src.push_back(s);
+            }
+            for (uint64_t i = 0; i < D->n_bin; ++i) {
+                const zk_bin_gate &G = D->bin_gates[i];
+                if ((G.l != 0) != (kind != 0)) continue;
+                src_t s;
+                s.rowkey = (((G.l & 1) ? 1u : 0u) << 30) | G.v;
+                s.rec = {G.g, G.u, (uint32_t) G.sc | ((uint32_t) kind << 16)};
+                src.push_back(s);
+            }
+        }
+        build_schedule(ctx, L.p2, src, rows_v0, rows_v1, true);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// helpers used by the Init* calls
+// --------------------------------------------------------------------------------------------------------------------
+struct beta_point_t { const fr_t *r; fr_t init; };   // host challenges, multiplier
+
+// uploads up to two challenge vectors and builds their half tables; returns pointers for k_beta_expand / k_liu_scatter
+struct halves_t { const fr_t *f[2] = {nullptr, nullptr}, *s[2] = {nullptr, nullptr}; uint32_t first_half = 0; };
+static halves_t build_halves(zk_ctx *ctx, uint32_t bits, const beta_point_t *pts, int n_pts) {
+    ZK_REQUIRE(bits <= 30, "beta table too large");
+    halves_t H;
+    const uint32_t fh = bits >> 1, sh = bits - fh;
+    H.first_half = fh;
+    ctx->d_r.ensure(2 * 64 * sizeof(fr_t));
+    half_args_t A;
+    memset(&A, 0, sizeof A);
+    for (int k = 0; k < n_pts; ++k) {
+        if (pts[k].init.is_zero()) continue;   // initBetaTable leaves zeros for a zero multiplier (src/utils.cpp:154-159)
+        ctx->half[2 * k].ensure(sizeof(fr_t) << fh);
+        ctx->half[2 * k + 1].ensure(sizeof(fr_t) << sh);
+        fr_t *dr = ctx->d_r.as<fr_t>() + 64 * k;
+        rt::h2d(dr, pts[k].r, bits * sizeof(fr_t), ctx->stream);
+        A.job[2 * k] = {ctx->half[2 * k].as<fr_t>(), dr, fh, pts[k].init};
+        A.job[2 * k + 1] = {ctx->half[2 * k + 1].as<fr_t>(), dr + fh, sh, fr_t::one()};
+        H.f[k] = ctx->half[2 * k].as<fr_t>();
+        H.s[k] = ctx->half[2 * k + 1].as<fr_t>();
+    }
+    ZK_KLAUNCH(ctx, k_half_tables, dim3(4), dim3(kBlock), 0, A);
+    return H;
+}
+
+static void build_beta(zk_ctx *ctx, fr_t *out, uint32_t bits, const beta_point_t *pts, int n_pts, uint32_t tail_start = 0xffffffffu,
+                       const fr_t &tail_scale = fr_t::one()) {
+    halves_t H = build_halves(ctx, bits, pts, n_pts);
+    beta_args_t B;
+    B.out = out;
+    // compact: the first present point goes to slot 0
+    int k0 = H.f[0] ? 0 : 1;
+    B.f0 = H.f[k0]; B.s0 = H.s[k0];
+    B.f1 = (k0 == 0) ? H.f[1] : nullptr; B.s1 = (k0 == 0) ? H.s[1] : nullptr;
+    B.bits = bits; B.first_half = H.first_half;
+    B.tail_start = tail_start; B.tail_scale = tail_scale;
+    ZK_KLAUNCH(ctx, k_beta_expand, dim3(grid_for(1ull << bits)), dim3(kBlock), 0, B);
+}
+
+static void run_schedule(zk_ctx *ctx, const schedule_t &S, int phase, gate_args_t A) {
+    if (S.levels.empty()) return;
+    ctx->gate_partial[0].ensure((size_t) std::max(1u, S.max_partials) * sizeof(fr_t));
+    ctx->gate_partial[1].ensure((size_t) std::max(1u, S.max_partials) * sizeof(fr_t));
+    A.recs = S.recs.as<gate_rec_t>();
+    for (size_t k = 0; k < S.levels.size(); ++k) {
+        const level_t &L = S.levels[k];
+        A.items = L.items.as<item_t>();
+        A.n_items = L.n_items;
+        A.partial = ctx->gate_partial[k & 1].as<fr_t>();
+        if (k == 0) {
+            if (phase == 1) ZK_KLAUNCH(ctx, k_gate_items_p1, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
+            else ZK_KLAUNCH(ctx, k_gate_items_p2, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
+        } else {
+            const fr_t *src = ctx->gate_partial[(k - 1) & 1].as<fr_t>();
+            ZK_KLAUNCH(ctx, k_sum_partials, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A, src);
+        }
+    }
+}
+
+static void pair_reset(pair_t &P, int8_t bit_length, uint32_t size) {
+    P.exists = bit_length >= 0;
+    P.n_eval = P.exists ? 1u << bit_length : 0;
+    P.live = size;
+    P.collapsed = false;
+    P.cv = P.cm = fr_t::zero();
+    P.v.cur = P.m.cur = nullptr;
+    P.v.next = P.m.next = 0;
+}
+static fr_t *table_init_buf(table_t &T, uint64_t entries) {
+    T.init.ensure(std::max<uint64_t>(1, entries) * sizeof(fr_t));
+    T.cur = T.init.as<fr_t>();
+    return T.init.as<fr_t>();
+}
+static fr_t *table_fold_buf(table_t &T, uint64_t entries) {
+    rt::dbuf &b = T.fold[T.next];
+    b.ensure(std::max<uint64_t>(1, entries) * sizeof(fr_t));
+    return b.as<fr_t>();
+}
+static void table_advance(table_t &T) {
+    T.cur = T.fold[T.next].as<fr_t>();
+    T.next ^= 1;
+}
+
+static void ensure_round_scratch(zk_ctx *ctx) {
+    ctx->partials.ensure((size_t) 2 * kMaxGridX * 4 * sizeof(fr_t));
+    if (!ctx->counters.p) {
+        ctx->counters.ensure(4 * sizeof(uint32_t));
+        rt::dzero(ctx->counters.p, 4 * sizeof(uint32_t), ctx->stream);
+    }
+    ctx->round_out.ensure(16 * sizeof(fr_t));
+    if (!ctx->h_out) ctx->h_out = static_cast<fr_t *>(rt::hmalloc_pinned(16 * sizeof(fr_t)));
+}
+
+// One call of sumcheckUpdateEach for both table pairs (src/prover.cpp:396-426).  `mask` selects the pairs that take part
+// (Liu: only pair 1).  Returns the sum of the pairs' round polynomials in abc[3]; add_term is updated for collapses.
+static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t abc[3]) {
+    ensure_round_scratch(ctx);
+    const bool first = ctx->round == 1;
+    round_args_t A;
+    memset(&A, 0, sizeof A);
+    A.r = prev;
+    A.partials = ctx->partials.as<fr_t>();
+    A.counters = ctx->counters.as<uint32_t>();
+    A.out = ctx->round_out.as<fr_t>();
+    final_fold_args_t F;
+    memset(&F, 0, sizeof F);
+    F.r = prev;
+    F.out = ctx->round_out.as<fr_t>() + 8;
+    bool any_quad = false, any_final = false;
+    bool quad[2] = {false, false}, fin[2] = {false, false};
+    uint32_t gx = 0;
+    for (int b = 0; b < 2; ++b) {
+        pair_t &P = ctx->pair[b];
+        if (!(mask & (1u << b)) || P.n_eval == 0) continue;
+        const uint32_t n_after = first ? P.n_eval : P.n_eval >> 1;
+        if (n_after == 1) {   // total[idx] == 1: evaluate and move the product into add_term (src/prover.cpp:400-404)
+            F.v_in[b] = P.v.cur; F.m_in[b] = P.m.cur;
+            F.live[b] = P.live; F.fold[b] = first ? 0 : 1; F.active[b] = 1;
+            fin[b] = any_final = true;
+        } else {
+            round_pair_t &R = A.pair[b];
+            R.v_in = P.v.cur; R.m_in = P.m.cur;
+            R.n_in = P.n_eval; R.live = P.live; R.fold = first ? 0 : 1;
+            if (!first) {
+                R.v_out = table_fold_buf(P.v, n_after);
+                R.m_out = table_fold_buf(P.m, n_after);
+            }
+            const uint32_t live_pairs = first ? (P.live + 1) >> 1 : (P.live + 3) >> 2;
+            R.n_blocks = grid_for(std::max<uint32_t>(1, live_pairs));
+            gx = std::max(gx, R.n_blocks);
+            quad[b] = any_quad = true;
+        }
+    }
+    if (any_quad) ZK_KLAUNCH(ctx, k_round_quad, dim3(gx, 2), dim3(kBlock), 0, A);
+    if (any_final) ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
+    if (any_quad || any_final) {
+        rt::d2h(ctx->h_out, ctx->round_out.p, 16 * sizeof(fr_t), ctx->stream);
+        rt::sync(ctx->stream);
+    }
+    abc[0] = abc[1] = abc[2] = fr_t::zero();
+    for (int b = 0; b < 2; ++b) {
+        pair_t &P = ctx->pair[b];
+        if (fin[b]) {
+            P.cv = ctx->h_out[8 + 2 * b];
+            P.cm = ctx->h_out[8 + 2 * b + 1];
+            ctx->add_term = ctx->add_term + P.cv * P.cm;
+            P.collapsed = true;
+            P.n_eval = 0;
+        } else if (quad[b]) {
+            for (int k = 0; k < 3; ++k) abc[k] = abc[k] + ctx->h_out[4 * b + k];
+            if (!first) {
+                table_advance(P.v);
+                table_advance(P.m);
+                P.n_eval >>= 1;
+                P.live = (P.live + 1) >> 1;
+            }
+        }
+    }
+}
+
+// value of V_mult[b][0] at the end of a phase (src/prover.cpp:462-463,476-477,490)
+static void final_values(zk_ctx *ctx, const fr_t &prev, fr_t out[2]) {
+    ensure_round_scratch(ctx);
+    final_fold_args_t F;
+    memset(&F, 0, sizeof F);
+    F.r = prev;
+    F.out = ctx->round_out.as<fr_t>() + 8;
+    bool any = false;
+    for (int b = 0; b < 2; ++b) {
+        pair_t &P = ctx->pair[b];
+        out[b] = fr_t::zero();
+        if (P.n_eval == 0) {
+            if (P.exists && P.collapsed) out[b] = P.cv;
+            continue;
+        }
+        ZK_REQUIRE(P.n_eval <= 2, "finalize called before the last round");
+        F.v_in[b] = P.v.cur; F.m_in[b] = nullptr;
+        F.live[b] = P.live; F.fold[b] = P.n_eval == 2; F.active[b] = 1;
+        any = true;
+    }
+    if (any) {
+        ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
+        rt::d2h(ctx->h_out, ctx->round_out.p, 16 * sizeof(fr_t), ctx->stream);
+        rt::sync(ctx->stream);
+        for (int b = 0; b < 2; ++b)
+            if (F.active[b]) out[b] = ctx->h_out[8 + 2 * b];
+    }
+}
+
+static const fr_t *phi_powers(zk_ctx *ctx, uint32_t n, bool is_ifft) {
+    // phiPowInit (src/utils.cpp:53-59): powers of getRootOfUnit(n) (or of its inverse)
+    const uint32_t key = n * 2 + (is_ifft ? 1 : 0);
+    for (auto &e : ctx->phi_pw)
+        if (e.first == key) return e.second.as<fr_t>();
+    ZK_REQUIRE(n >= 1 && n <= 24, "unsupported FFT size");
+    fr_t w;
+    memcpy(w.v, ZK_C(fr_ROOT32), 32);
+    for (uint32_t i = n; i < 32; ++i) w = w.sqr();
+    if (is_ifft) w = w.inverse();
+    std::vector<fr_t> pw((size_t) 1 << n);
+    pw[0] = fr_t::one();
+    for (size_t i = 1; i < pw.size(); ++i) pw[i] = pw[i - 1] * w;
+    rt::dbuf d;
+    d.ensure(pw.size() * sizeof(fr_t));
+    rt::h2d(d.p, pw.data(), pw.size() * sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    ctx->phi_pw.emplace_back(key, std::move(d));
+    return ctx->phi_pw.back().second.as<fr_t>();
+}
+
+static layer_t &cur_layer(zk_ctx *ctx) {
+    ZK_REQUIRE(ctx->circuit_ready, "circuit not uploaded");
+    ZK_REQUIRE(ctx->sumcheck_id < ctx->n_layers, "bad sumcheck level");
+    return ctx->layers[ctx->sumcheck_id];
+}
+
+}  // namespace zk

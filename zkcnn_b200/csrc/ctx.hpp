@@ -1,0 +1,104 @@
+// Device-resident prover state behind the C ABI (include/zkcnn_b200.h).
+#pragma once
+#include "../../include/zkcnn_b200.h"
+#include "g1.cuh"
+#include "rt.hpp"
+#include "sc_kernels.cuh"
+#include <memory>
+#include <vector>
+
+namespace zk {
+
+// ---- static gate schedules (built once per circuit at upload) -------------------------------------------------------
+struct level_t {
+    rt::dbuf items;
+    uint32_t n_items = 0;
+    uint32_t n_partials = 0;   // partial sums this level writes
+};
+struct schedule_t {
+    rt::dbuf recs;
+    uint64_t n_recs = 0;
+    std::vector<level_t> levels;
+    uint32_t max_partials = 0;
+    bool has_scalar = false;   // phase 2: uni gates feed add_term
+};
+
+struct layer_t {
+    zk_layer_desc d{};         // scalar members only (pointers nulled)
+    fr_t scale;
+    rt::dbuf ori_u, ori_v;     // device copies of ori_id_u / ori_id_v
+    schedule_t p1, p2;
+    rt::dbuf dp_rowptr, dp_gates;  // DOT_PROD phase 1: CSR by u
+    uint32_t dp_rows = 0;
+    rt::dbuf val;              // prover::val[layer]
+    uint64_t n_val = 0;
+    bool have_desc = false;
+};
+
+// one bookkeeping table in evaluation form
+struct table_t {
+    const fr_t *cur = nullptr;
+    rt::dbuf init, fold[2];
+    int next = 0;
+};
+// a (V, mult) pair that is folded in lock step (src/prover.cpp:396-426)
+struct pair_t {
+    table_t v, m;
+    uint32_t n_eval = 0;       // evaluations currently held (0: pair absent or already collapsed)
+    uint32_t live = 0;         // entries >= live are zero
+    bool exists = false;       // bit_length != -1
+    bool collapsed = false;
+    fr_t cv, cm;               // values after collapse (V_mult[b][0].b, mult_array[b][0].b)
+};
+
+// Hyrax state (3rd/hyrax-bls12-381/src/polyProver.hpp:38-54)
+struct hyrax_t {
+    bool bound = false;
+    const fr_t *Z = nullptr;   // 2^bit_length scalars on the device (aliases val[0] or z_own)
+    rt::dbuf z_own;
+    uint32_t bit_length = 0, l_bits = 0, r_bits = 0;
+    uint32_t n_gens = 0;
+    rt::dbuf gens_aff;         // n_gens affine points
+    rt::dbuf table;            // fixed-base window table: [kWindows][n_gens] affine, entry = 2^(8w) * gens[j]
+    bool table_ready = false;
+    uint64_t gens_hash = 0;
+    rt::dbuf L, R, RZ, a, a_next, coef, scal;
+    std::vector<fr_t> t;       // remaining opening point (lx)
+    fr_t scale;
+    uint32_t cur = 0;          // current length of bullet_a
+    uint32_t round = 0;
+    std::vector<fr_t> rinv;    // 1 / randomness of the finished rounds
+    rt::dbuf msm_digits, msm_out, msm_rowinfo;
+};
+
+}  // namespace zk
+
+struct zk_ctx {
+    int device = 0;
+    zk_stream_t stream{};
+    uint64_t launches = 0;
+
+    // circuit
+    uint32_t n_layers = 0;
+    std::vector<zk::layer_t> layers;
+    std::vector<zk::fr_t> two_mul_h;
+    zk::rt::dbuf two_mul;
+    bool circuit_ready = false;
+
+    // sumcheck state (members of class prover, src/prover.hpp:55-72)
+    uint32_t sumcheck_id = 0, round = 0;
+    zk::fr_t alpha, beta, relu_rou, add_term, V_u0, V_u1;
+    std::vector<std::vector<zk::fr_t>> r_u, r_v;
+    zk::pair_t pair[2];
+    zk::table_t mdp;            // DOT_PROD multiplier table (mult_array[1] of size 2^fft_bl)
+    uint32_t mdp_n = 0;
+    zk::rt::dbuf beta_g, beta_g_alt, beta_gs, beta_u;
+    uint32_t beta_g_entries = 0;
+
+    // scratch
+    zk::rt::dbuf half[4], d_r, partials, counters, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
+    zk::fr_t *h_out = nullptr;  // pinned mirror of round_out
+    std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
+
+    zk::hyrax_t hy;
+};

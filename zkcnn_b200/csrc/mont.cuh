@@ -1,0 +1,322 @@
+// Montgomery-form prime-field arithmetic for BLS12-381, usable from host and device code.
+//
+// Replaces (value-identically) the arithmetic that the reference delegates to herumi/mcl v1.22:
+//   Fr = 4x64-bit Montgomery limbs, R = 2^256  (mcl_fp_mont4L, mcl/src/asm/x86-64.s:1687)
+//   Fp = 6x64-bit Montgomery limbs, R = 2^384  (mcl_fp_mont6L, mcl/src/asm/x86-64.s:3524)
+// The in-memory form is bit-identical to mcl's (little-endian limbs, fully reduced), so a `std::vector<Fr>` of the
+// reference can be handed to the C ABI without conversion.  Here the limbs are 32-bit because
+// the B200 integer pipe is 32 bits wide.
+//
+// Two implementations of the multiplier exist: a portable one (plain C, also the host path) and an inline-PTX one
+// using mad.lo.cc/madc.hi.cc carry chains.  Both are CIOS with a (N+1)-limb running accumulator; because both moduli
+// leave >= 1 spare top bit, the accumulator never needs limb N+1 ("field arithmetic").
+#pragma once
+#include "zk_platform.cuh"
+#include "bls12_381_constants.cuh"
+
+namespace zk {
+
+#if ZK_ON_DEVICE && !defined(ZK_PORTABLE_FIELD)
+#define ZK_FIELD_PTX 1
+#else
+#define ZK_FIELD_PTX 0
+#endif
+
+#if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
+namespace ptx {
+__device__ __forceinline__ uint32_t add_cc(uint32_t x, uint32_t y) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
+__device__ __forceinline__ uint32_t addc_cc(uint32_t x, uint32_t y) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
+__device__ __forceinline__ uint32_t addc(uint32_t x, uint32_t y) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
+__device__ __forceinline__ uint32_t sub_cc(uint32_t x, uint32_t y) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
+__device__ __forceinline__ uint32_t subc_cc(uint32_t x, uint32_t y) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
+__device__ __forceinline__ uint32_t subc(uint32_t x, uint32_t y) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
+__device__ __forceinline__ uint32_t mul_lo(uint32_t x, uint32_t y) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
+__device__ __forceinline__ uint32_t mul_hi(uint32_t x, uint32_t y) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(y)); return r; }
+__device__ __forceinline__ uint32_t mad_lo_cc(uint32_t x, uint32_t y, uint32_t z) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(z)); return r; }
+__device__ __forceinline__ uint32_t madc_lo_cc(uint32_t x, uint32_t y, uint32_t z) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(z)); return r; }
+__device__ __forceinline__ uint32_t mad_hi_cc(uint32_t x, uint32_t y, uint32_t z) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(z)); return r; }
+__device__ __forceinline__ uint32_t madc_hi_cc(uint32_t x, uint32_t y, uint32_t z) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(z)); return r; }
+__device__ __forceinline__ uint32_t madc_hi(uint32_t x, uint32_t y, uint32_t z) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(z)); return r; }
+}  // namespace ptx
+#endif
+
+struct fr_cfg {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV = fr_params::INV;
+    static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fr_MOD); }
+    static ZK_HD __forceinline__ const uint32_t *one() { return ZK_C(fr_ONE); }
+    static ZK_HD __forceinline__ const uint32_t *r2() { return ZK_C(fr_R2); }
+    static ZK_HD __forceinline__ const uint32_t *modm2() { return ZK_C(fr_MODM2); }
+    static ZK_HD __forceinline__ const uint32_t *half() { return ZK_C(fr_HALF); }
+};
+struct fp_cfg {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV = fp_params::INV;
+    static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fp_MOD); }
+    static ZK_HD __forceinline__ const uint32_t *one() { return ZK_C(fp_ONE); }
+    static ZK_HD __forceinline__ const uint32_t *r2() { return ZK_C(fp_R2); }
+    static ZK_HD __forceinline__ const uint32_t *modm2() { return ZK_C(fp_MODM2); }
+    static ZK_HD __forceinline__ const uint32_t *half() { return ZK_C(fp_HALF); }
+};
+
+template <class C> struct alignas(16) mont_t {
+    static constexpr int N = C::N;
+    uint32_t v[N];
+
+    // ---- constructors / constants -------------------------------------------------------------------------------
+    static ZK_HD __forceinline__ mont_t zero() {
+        mont_t r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = 0;
+        return r;
+    }
+    static ZK_HD __forceinline__ mont_t one() {
+        mont_t r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = C::one()[i];
+        return r;
+    }
+    // canonical integer (little-endian 32-bit limbs, < modulus) -> Montgomery form
+    static ZK_HD inline mont_t from_canonical(const uint32_t *x) {
+        mont_t a, r2;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a.v[i] = x[i]; r2.v[i] = C::r2()[i]; }
+        return a * r2;
+    }
+    static ZK_HD inline mont_t from_u64(uint64_t x) {
+        uint32_t c[N];
+        for (int i = 0; i < N; ++i) c[i] = 0;
+        c[0] = (uint32_t) x;
+        c[1] = (uint32_t) (x >> 32);
+        return from_canonical(c);
+    }
+    static ZK_HD inline mont_t from_i64(int64_t x) { return x < 0 ? -from_u64((uint64_t) (-x)) : from_u64((uint64_t) x); }
+    // Montgomery form -> canonical integer
+    ZK_HD inline void to_canonical(uint32_t *out) const {
+        mont_t u;
+#pragma unroll
+        for (int i = 0; i < N; ++i) u.v[i] = i == 0 ? 1u : 0u;
+        mont_t r = *this * u;
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = r.v[i];
+    }
+
+    // ---- predicates -----------------------------------------------------------------------------------------------
+    ZK_HD __forceinline__ bool is_zero() const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) o |= v[i];
+        return o == 0;
+    }
+    ZK_HD __forceinline__ bool operator==(const mont_t &b) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) o |= v[i] ^ b.v[i];
+        return o == 0;
+    }
+    ZK_HD __forceinline__ bool operator!=(const mont_t &b) const { return !(*this == b); }
+
+    // raw little-endian comparison a >= b on limb arrays
+    static ZK_HD __forceinline__ bool ge_raw(const uint32_t *a, const uint32_t *b) {
+        for (int i = N - 1; i >= 0; --i) {
+            if (a[i] > b[i]) return true;
+            if (a[i] < b[i]) return false;
+        }
+        return true;
+    }
+
+    // ---- add / sub / neg --------------------------------------------------------------------------------------------
+    friend ZK_HD __forceinline__ mont_t operator+(const mont_t &a, const mont_t &b) {
+        mont_t s, d;
+        const uint32_t *p = C::mod();
+#if ZK_FIELD_PTX
+        s.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) s.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+        s.v[N - 1] = ptx::addc(a.v[N - 1], b.v[N - 1]);  // no carry out: both moduli leave a spare top bit
+        d.v[0] = ptx::sub_cc(s.v[0], p[0]);
+#pragma unroll
+        for (int i = 1; i < N; ++i) d.v[i] = ptx::subc_cc(s.v[i], p[i]);
+        uint32_t borrow = ptx::subc(0, 0);  // 0 - 0 - borrow = 0xffffffff if s < p
+#pragma unroll
+        for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : d.v[i];
+        return s;
+#else
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            c += (uint64_t) a.v[i] + b.v[i];
+            s.v[i] = (uint32_t) c;
+            c >>= 32;
+        }
+        int64_t bw = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bw += (int64_t) s.v[i] - (int64_t) p[i];
+            d.v[i] = (uint32_t) bw;
+            bw >>= 32;
+        }
+        return bw ? s : d;
+#endif
+    }
+    friend ZK_HD __forceinline__ mont_t operator-(const mont_t &a, const mont_t &b) {
+        mont_t d, s;
+        const uint32_t *p = C::mod();
+#if ZK_FIELD_PTX
+        d.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N; ++i) d.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+        uint32_t borrow = ptx::subc(0, 0);
+        s.v[0] = ptx::add_cc(d.v[0], p[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) s.v[i] = ptx::addc_cc(d.v[i], p[i]);
+        s.v[N - 1] = ptx::addc(d.v[N - 1], p[N - 1]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) d.v[i] = borrow ? s.v[i] : d.v[i];
+        return d;
+#else
+        int64_t bw = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bw += (int64_t) a.v[i] - (int64_t) b.v[i];
+            d.v[i] = (uint32_t) bw;
+            bw >>= 32;
+        }
+        if (!bw) return d;
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            c += (uint64_t) d.v[i] + p[i];
+            s.v[i] = (uint32_t) c;
+            c >>= 32;
+        }
+        return s;
+#endif
+    }
+    ZK_HD __forceinline__ mont_t operator-() const { return is_zero() ? *this : (zero() - *this); }
+
+    // ---- multiplication ---------------------------------------------------------------------------------------------
+    static ZK_HD __forceinline__ void mul_portable(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+        const uint32_t *p = C::mod();
+        uint32_t t[N + 1];
+#pragma unroll
+        for (int i = 0; i <= N; ++i) t[i] = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            uint64_t c = 0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                uint64_t x = (uint64_t) a[j] * b[i] + t[j] + c;
+                t[j] = (uint32_t) x;
+                c = x >> 32;
+            }
+            uint64_t top = (uint64_t) t[N] + c;  // fits: accumulator < 2^(32(N+1)), see header comment
+            uint32_t m = t[0] * C::INV;
+            c = ((uint64_t) m * p[0] + t[0]) >> 32;
+#pragma unroll
+            for (int j = 1; j < N; ++j) {
+                uint64_t x = (uint64_t) m * p[j] + t[j] + c;
+                t[j - 1] = (uint32_t) x;
+                c = x >> 32;
+            }
+            top += c;
+            t[N - 1] = (uint32_t) top;
+            t[N] = (uint32_t) (top >> 32);
+        }
+        // result < 2p: one conditional subtraction
+        uint32_t d[N];
+        int64_t bw = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bw += (int64_t) t[i] - (int64_t) p[i];
+            d[i] = (uint32_t) bw;
+            bw >>= 32;
+        }
+        bool keep = bw != 0 && t[N] == 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = keep ? t[i] : d[i];
+    }
+
+#if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
+    // t[0..N] += x[0..N-1] * y   (one low-half carry chain, one high-half carry chain)
+    static __device__ __forceinline__ void mad_row(uint32_t *t, const uint32_t *x, uint32_t y) {
+        t[0] = ptx::mad_lo_cc(x[0], y, t[0]);
+#pragma unroll
+        for (int j = 1; j < N; ++j) t[j] = ptx::madc_lo_cc(x[j], y, t[j]);
+        t[N] = ptx::addc(t[N], 0);
+        t[1] = ptx::mad_hi_cc(x[0], y, t[1]);
+#pragma unroll
+        for (int j = 1; j < N - 1; ++j) t[j + 1] = ptx::madc_hi_cc(x[j], y, t[j + 1]);
+        t[N] = ptx::madc_hi(x[N - 1], y, t[N]);
+    }
+    static __device__ __forceinline__ void mul_ptx(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+        const uint32_t *p = C::mod();
+        uint32_t pm[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) pm[i] = p[i];
+        uint32_t t[N + 2];
+#pragma unroll
+        for (int i = 0; i < N + 2; ++i) t[i] = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            mad_row(t, a, b[i]);
+            uint32_t m = t[0] * C::INV;
+            mad_row(t, pm, m);
+            // divide by 2^32: t[0] is now zero
+#pragma unroll
+            for (int j = 0; j <= N; ++j) t[j] = t[j + 1];
+        }
+        uint32_t d[N];
+        d[0] = ptx::sub_cc(t[0], pm[0]);
+#pragma unroll
+        for (int i = 1; i < N; ++i) d[i] = ptx::subc_cc(t[i], pm[i]);
+        uint32_t borrow = ptx::subc(0, 0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = borrow ? t[i] : d[i];
+    }
+#endif
+
+    friend ZK_HD __forceinline__ mont_t operator*(const mont_t &a, const mont_t &b) {
+        mont_t r;
+#if ZK_FIELD_PTX
+        mul_ptx(r.v, a.v, b.v);
+#else
+        mul_portable(r.v, a.v, b.v);
+#endif
+        return r;
+    }
+    ZK_HD __forceinline__ mont_t sqr() const { return *this * *this; }
+    ZK_HD __forceinline__ mont_t dbl() const { return *this + *this; }
+
+    // x^e for a canonical little-endian exponent of N limbs (square-and-multiply, MSB first)
+    ZK_HD inline mont_t pow_limbs(const uint32_t *e) const {
+        mont_t acc = one();
+        bool started = false;
+        for (int i = N - 1; i >= 0; --i)
+            for (int b = 31; b >= 0; --b) {
+                if (started) acc = acc.sqr();
+                if ((e[i] >> b) & 1) {
+                    acc = started ? acc * *this : *this;
+                    started = true;
+                }
+            }
+        return acc;
+    }
+    // multiplicative inverse by Fermat (0 -> 0).  Field elements are unique, so this equals mcl's Fr::inv / Fp::inv.
+    ZK_HD inline mont_t inverse() const { return pow_limbs(C::modm2()); }
+
+    // mcl's isNegative(): canonical value >= (p+1)/2  (mcl/include/mcl/fp.hpp:666-671)
+    ZK_HD inline bool is_negative() const {
+        uint32_t c[N];
+        to_canonical(c);
+        return ge_raw(c, C::half());
+    }
+};
+
+typedef mont_t<fr_cfg> fr_t;
+typedef mont_t<fp_cfg> fp_t;
+
+static_assert(sizeof(fr_t) == 32, "Fr must match mcl's 32-byte layout");
+static_assert(sizeof(fp_t) == 48, "Fp must match mcl's 48-byte layout");
+
+}  // namespace zk

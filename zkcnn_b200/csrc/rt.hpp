@@ -1,0 +1,105 @@
+// Thin runtime layer under the C ABI: device memory, copies, stream sync.  CUDA in the product; plain host memory
+// when the sources are compiled for the test-only emulator (ZK_EMU).
+#pragma once
+#include "zk_platform.cuh"
+#include <stdexcept>
+#include <string>
+
+namespace zk {
+namespace rt {
+
+struct error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#ifdef ZK_EMU
+inline void check(int, const char *) {}
+inline void set_device(int) {}
+inline int device_count() { return 1; }
+inline void *dmalloc(size_t bytes) {
+    void *p = malloc(bytes ? bytes : 1);
+    if (!p) throw error("emu: out of memory");
+    return p;
+}
+inline void dfree(void *p) { free(p); }
+inline void *hmalloc_pinned(size_t bytes) { return malloc(bytes ? bytes : 1); }
+inline void hfree_pinned(void *p) { free(p); }
+inline void h2d(void *dst, const void *src, size_t n, zk_stream_t) { memcpy(dst, src, n); }
+inline void d2h(void *dst, const void *src, size_t n, zk_stream_t) { memcpy(dst, src, n); }
+inline void d2d(void *dst, const void *src, size_t n, zk_stream_t) { memmove(dst, src, n); }
+inline void dzero(void *dst, size_t n, zk_stream_t) { memset(dst, 0, n); }
+inline zk_stream_t stream_create() { return nullptr; }
+inline void stream_destroy(zk_stream_t) {}
+inline void sync(zk_stream_t) {}
+inline void check_launch(const char *) {}
+#else
+inline void check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) throw error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+inline void set_device(int d) { check(cudaSetDevice(d), "cudaSetDevice"); }
+inline int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+inline void *dmalloc(size_t bytes) {
+    void *p = nullptr;
+    check(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc");
+    return p;
+}
+inline void dfree(void *p) { if (p) cudaFree(p); }
+inline void *hmalloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    check(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost");
+    return p;
+}
+inline void hfree_pinned(void *p) { if (p) cudaFreeHost(p); }
+inline void h2d(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s), "h2d"); }
+inline void d2h(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s), "d2h"); }
+inline void d2d(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "d2d"); }
+inline void dzero(void *dst, size_t n, zk_stream_t s) { if (n) check(cudaMemsetAsync(dst, 0, n, s), "memset"); }
+inline zk_stream_t stream_create() {
+    cudaStream_t s;
+    check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+    return s;
+}
+inline void stream_destroy(zk_stream_t s) { if (s) cudaStreamDestroy(s); }
+inline void sync(zk_stream_t s) { check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+inline void check_launch(const char *what) { check(cudaGetLastError(), what); }
+#endif
+
+// grow-only device buffer
+struct dbuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    dbuf() = default;
+    dbuf(const dbuf &) = delete;
+    dbuf &operator=(const dbuf &) = delete;
+    dbuf(dbuf &&o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    dbuf &operator=(dbuf &&o) noexcept {
+        if (this != &o) { dfree(p); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+        return *this;
+    }
+    ~dbuf() { dfree(p); }
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        dfree(p);
+        p = nullptr;
+        cap = 0;
+        p = dmalloc(bytes);
+        cap = bytes;
+    }
+    // like ensure() but keeps the old contents (device-to-device copy)
+    void ensure_keep(size_t bytes, zk_stream_t s) {
+        if (bytes <= cap) return;
+        void *q = dmalloc(bytes);
+        if (p && cap) { d2d(q, p, cap, s); sync(s); }
+        dfree(p);
+        p = q;
+        cap = bytes;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+}  // namespace rt
+}  // namespace zk

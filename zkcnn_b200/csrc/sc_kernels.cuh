@@ -1,0 +1,604 @@
+// Sumcheck kernels (GKR prover hot loops (1) and (2) of BASELINE.json north_star).
+//
+// All bookkeeping tables are kept in EVALUATION form (one Fr per entry) instead of the reference's linear_poly
+// (a,b) = (v1 - v0, v0) pairs (src/prover.cpp:13-15), which halves the HBM traffic; the round polynomials that leave
+// the device are the same field elements (field arithmetic is exact, so summation order does not matter).
+//
+//   K1  k_round_quad      prover::sumcheckUpdateEach        src/prover.cpp:396-426
+//   K2  k_round_cubic     prover::sumcheckDotProdUpdate1    src/prover.cpp:103-144
+//   K3  k_half_tables / k_beta_expand   initBetaTable + initHalfTable   src/utils.cpp:32-51,147-180
+//   K3b k_phi_table       phiGInit                          src/utils.cpp:61-103
+//   K4/K5 k_gate_items_p1 / k_gate_items_p2 / k_sum_partials   gate loops of sumcheckInitPhase1/2
+//                                                           src/prover.cpp:224-233,286-288,297-305
+//   K4b k_dense_colsum    FFT/IFFT dense contraction        src/prover.cpp:190-197
+//   K5b k_dotprod_axpy    sumcheckDotProdInitPhase1         src/prover.cpp:86-91
+//   K5  k_dense_rowdot    DOT_PROD phase-2 V table          src/prover.cpp:277-284
+//   K6  k_liu_scatter     sumcheckLiuInit                   src/prover.cpp:334-353
+#pragma once
+#include "mont.cuh"
+
+namespace zk {
+
+constexpr int kBlock = 256;          // threads per CTA for all streaming kernels
+constexpr int kMaxGridX = ZK_SM_COUNT * 8;  // persistent-style grids: a multiple of the 148 SMs
+
+// --------------------------------------------------------------------------------------------------------------------
+// vectorised global access: an Fr is two 16-byte words
+// --------------------------------------------------------------------------------------------------------------------
+ZK_HD __forceinline__ fr_t ld_fr(const fr_t *p) {
+#if ZK_ON_DEVICE
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = q[0], hi = q[1];
+    fr_t r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+ZK_HD __forceinline__ void st_fr(fr_t *p, const fr_t &x) {
+#if ZK_ON_DEVICE
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+#else
+    *p = x;
+#endif
+}
+// L2-coherent load for data produced by other CTAs of the same launch ("last CTA finishes" reductions)
+ZK_HD __forceinline__ fr_t ld_fr_cg(const fr_t *p) {
+#if ZK_ON_DEVICE
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+    fr_t r;
+    r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = lo.z; r.v[3] = lo.w;
+    r.v[4] = hi.x; r.v[5] = hi.y; r.v[6] = hi.z; r.v[7] = hi.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+// guarded load: entries at or beyond `live` are zero by construction (src/prover.cpp:409-417 clears them)
+ZK_HD __forceinline__ fr_t ld_fr_live(const fr_t *p, uint32_t idx, uint32_t live) {
+    return idx < live ? ld_fr(p + idx) : fr_t::zero();
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// CTA-wide sum of K field elements per thread; result valid in thread 0.  sh must hold K * kBlock elements.
+// --------------------------------------------------------------------------------------------------------------------
+template <int K> __device__ __forceinline__ void block_sum(fr_t (&acc)[K], fr_t *sh) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < K; ++k) sh[k * kBlock + t] = acc[k];
+    __syncthreads();
+    for (int s = kBlock / 2; s > 0; s >>= 1) {
+        if (t < s) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) sh[k * kBlock + t] = sh[k * kBlock + t] + sh[k * kBlock + t + s];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = sh[k * kBlock];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K1: one sumcheck round on up to two (V, mult) table pairs in one launch (blockIdx.y = pair).
+// --------------------------------------------------------------------------------------------------------------------
+struct round_pair_t {
+    const fr_t *v_in, *m_in;  // current tables, n_in evaluations each, entries >= live are zero
+    fr_t *v_out, *m_out;      // folded tables (n_in / 2); unused when fold == 0
+    uint32_t n_in, live;
+    uint32_t fold;            // 0: first round of a phase (previous_random = 0, src/verifier.cpp:168) -> no fold
+    uint32_t n_blocks;        // CTAs assigned to this pair (0 = pair inactive this round)
+};
+struct round_args_t {
+    round_pair_t pair[2];
+    fr_t r;                   // previous_random
+    fr_t *partials;           // [2][kMaxGridX][4]
+    uint32_t *counters;       // [2] "CTAs done" tickets, self-resetting
+    fr_t *out;                // [2][4]: (a, b, c, unused) per pair, summed over all CTAs
+};
+
+// Per output pair (v0,v1),(m0,m1) of the (folded) tables the round polynomial contributes
+//   a += (m1-m0)(v1-v0),  c += m0 v0,  b += (m1-m0) v0 + m0 (v1-v0) = m1 v1 - a - c
+// (linear_poly * linear_poly, src/polynomial.cpp:116-118, evaluated Karatsuba-style with 3 products).
+__global__ void __launch_bounds__(kBlock) k_round_quad(round_args_t A) {
+    __shared__ fr_t sh[3 * kBlock];
+    __shared__ uint32_t ticket;
+    const int b = blockIdx.y;
+    const round_pair_t P = A.pair[b];
+    if (blockIdx.x >= P.n_blocks) return;
+    const uint32_t stride = P.n_blocks * kBlock;
+    fr_t acc[3] = {fr_t::zero(), fr_t::zero(), fr_t::zero()};  // A, C, E
+    if (P.fold) {
+        const uint32_t n_pairs = P.n_in >> 2;
+        const uint32_t live_pairs = (P.live + 3) >> 2;
+        const fr_t r = A.r;
+        for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
+            const uint32_t base = i << 2;
+            fr_t x0 = ld_fr_live(P.v_in, base, P.live), x1 = ld_fr_live(P.v_in, base + 1, P.live);
+            fr_t x2 = ld_fr_live(P.v_in, base + 2, P.live), x3 = ld_fr_live(P.v_in, base + 3, P.live);
+            fr_t v0 = x0 + r * (x1 - x0);
+            fr_t v1 = x2 + r * (x3 - x2);
+            st_fr(P.v_out + 2 * i, v0);
+            st_fr(P.v_out + 2 * i + 1, v1);
+            x0 = ld_fr_live(P.m_in, base, P.live); x1 = ld_fr_live(P.m_in, base + 1, P.live);
+            x2 = ld_fr_live(P.m_in, base + 2, P.live); x3 = ld_fr_live(P.m_in, base + 3, P.live);
+            fr_t m0 = x0 + r * (x1 - x0);
+            fr_t m1 = x2 + r * (x3 - x2);
+            st_fr(P.m_out + 2 * i, m0);
+            st_fr(P.m_out + 2 * i + 1, m1);
+            acc[0] = acc[0] + (m1 - m0) * (v1 - v0);
+            acc[1] = acc[1] + m0 * v0;
+            acc[2] = acc[2] + m1 * v1;
+        }
+    } else {
+        const uint32_t n_pairs = P.n_in >> 1;
+        const uint32_t live_pairs = (P.live + 1) >> 1;
+        for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
+            fr_t v0 = ld_fr_live(P.v_in, 2 * i, P.live), v1 = ld_fr_live(P.v_in, 2 * i + 1, P.live);
+            fr_t m0 = ld_fr_live(P.m_in, 2 * i, P.live), m1 = ld_fr_live(P.m_in, 2 * i + 1, P.live);
+            acc[0] = acc[0] + (m1 - m0) * (v1 - v0);
+            acc[1] = acc[1] + m0 * v0;
+            acc[2] = acc[2] + m1 * v1;
+        }
+    }
+    block_sum<3>(acc, sh);
+    fr_t *part = A.partials + (size_t) b * kMaxGridX * 4;
+    if (threadIdx.x == 0) {
+        st_fr(part + blockIdx.x * 4 + 0, acc[0]);
+        st_fr(part + blockIdx.x * 4 + 1, acc[1]);
+        st_fr(part + blockIdx.x * 4 + 2, acc[2]);
+        __threadfence();
+        ticket = atomicAdd(A.counters + b, 1u);
+    }
+    __syncthreads();
+    if (ticket != P.n_blocks - 1) return;
+    // last CTA of this pair: fold the per-CTA partials into the round polynomial
+    __threadfence();
+    fr_t tot[3] = {fr_t::zero(), fr_t::zero(), fr_t::zero()};
+    for (uint32_t i = threadIdx.x; i < P.n_blocks; i += kBlock) {
+        tot[0] = tot[0] + ld_fr_cg(part + i * 4 + 0);
+        tot[1] = tot[1] + ld_fr_cg(part + i * 4 + 1);
+        tot[2] = tot[2] + ld_fr_cg(part + i * 4 + 2);
+    }
+    __syncthreads();
+    block_sum<3>(tot, sh);
+    if (threadIdx.x == 0) {
+        st_fr(A.out + b * 4 + 0, tot[0]);
+        st_fr(A.out + b * 4 + 1, tot[2] - tot[0] - tot[1]);
+        st_fr(A.out + b * 4 + 2, tot[1]);
+        A.counters[b] = 0;
+    }
+}
+
+// fold a 2-entry table pair down to single values (the "total == 1" collapse, src/prover.cpp:400-404, and the
+// eval(previous_random) of the Finalize calls, src/prover.cpp:146-153,459-497).  out[2*i], out[2*i+1] = v, m of pair i.
+struct final_fold_args_t {
+    const fr_t *v_in[3], *m_in[3];
+    uint32_t live[3];
+    uint32_t fold[3];  // 1: n_eval == 2 -> v0 + r (v1 - v0);  0: n_eval == 1 -> copy entry 0
+    uint32_t active[3];
+    fr_t r;
+    fr_t *out;  // [3][2]
+};
+__global__ void k_final_fold(final_fold_args_t A) {
+    const int i = threadIdx.x >> 1, which = threadIdx.x & 1;
+    if (i >= 3 || !A.active[i]) return;
+    const fr_t *p = which ? A.m_in[i] : A.v_in[i];
+    if (!p) return;
+    fr_t x0 = ld_fr_live(p, 0, A.live[i]);
+    if (A.fold[i]) {
+        fr_t x1 = ld_fr_live(p, 1, A.live[i]);
+        x0 = x0 + A.r * (x1 - x0);
+    }
+    st_fr(A.out + 2 * i + which, x0);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K2: cubic round of the FFT-convolution (DOT_PROD) layer: sum_i mult[i mod P](x) * V1[i](x) * V0[i](x)
+// The multiplier table is periodic in i (frequency index in the low fft_bl bits, src/prover.cpp:134-135).
+// --------------------------------------------------------------------------------------------------------------------
+struct cubic_args_t {
+    const fr_t *v0_in, *v1_in;  // big tables, n_in evaluations, entries >= live are zero
+    fr_t *v0_out, *v1_out;
+    const fr_t *m_in;           // multiplier table, m_n evaluations (already folded for this round by k_fold_small)
+    uint32_t n_in, live, fold;
+    uint32_t m_n;               // >= 2: pairs (m[2j], m[2j+1]) periodic with period m_n/2;  1: constant m[0]
+    uint32_t n_blocks;
+    fr_t r;
+    fr_t *partials;             // [kMaxGridX][4]
+    uint32_t *counter;
+    fr_t *out;                  // (a, b, c, d)
+};
+__global__ void __launch_bounds__(kBlock) k_round_cubic(cubic_args_t A) {
+    __shared__ fr_t sh[4 * kBlock];
+    __shared__ uint32_t ticket;
+    const uint32_t stride = A.n_blocks * kBlock;
+    fr_t acc[4] = {fr_t::zero(), fr_t::zero(), fr_t::zero(), fr_t::zero()};
+    const uint32_t n_pairs = A.fold ? A.n_in >> 2 : A.n_in >> 1;
+    const uint32_t live_pairs = A.fold ? (A.live + 3) >> 2 : (A.live + 1) >> 1;
+    const uint32_t m_pairs = A.m_n >> 1;
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
+        fr_t p0, p1, q0, q1;
+        if (A.fold) {
+            const uint32_t base = i << 2;
+            fr_t x0 = ld_fr_live(A.v0_in, base, A.live), x1 = ld_fr_live(A.v0_in, base + 1, A.live);
+            fr_t x2 = ld_fr_live(A.v0_in, base + 2, A.live), x3 = ld_fr_live(A.v0_in, base + 3, A.live);
+            p0 = x0 + A.r * (x1 - x0);
+            p1 = x2 + A.r * (x3 - x2);
+            st_fr(A.v0_out + 2 * i, p0);
+            st_fr(A.v0_out + 2 * i + 1, p1);
+            x0 = ld_fr_live(A.v1_in, base, A.live); x1 = ld_fr_live(A.v1_in, base + 1, A.live);
+            x2 = ld_fr_live(A.v1_in, base + 2, A.live); x3 = ld_fr_live(A.v1_in, base + 3, A.live);
+            q0 = x0 + A.r * (x1 - x0);
+            q1 = x2 + A.r * (x3 - x2);
+            st_fr(A.v1_out + 2 * i, q0);
+            st_fr(A.v1_out + 2 * i + 1, q1);
+        } else {
+            p0 = ld_fr_live(A.v0_in, 2 * i, A.live); p1 = ld_fr_live(A.v0_in, 2 * i + 1, A.live);
+            q0 = ld_fr_live(A.v1_in, 2 * i, A.live); q1 = ld_fr_live(A.v1_in, 2 * i + 1, A.live);
+        }
+        // quadratic  V1(x) V0(x) = qa x^2 + qb x + qc
+        fr_t dp = p1 - p0, dq = q1 - q0;
+        fr_t qa = dp * dq, qc = p0 * q0;
+        fr_t qb = p1 * q1 - qa - qc;
+        if (m_pairs) {
+            const uint32_t j = i & (m_pairs - 1);
+            fr_t m0 = ld_fr(A.m_in + 2 * j), m1 = ld_fr(A.m_in + 2 * j + 1);
+            fr_t dm = m1 - m0;
+            acc[0] = acc[0] + dm * qa;
+            acc[1] = acc[1] + dm * qb + m0 * qa;
+            acc[2] = acc[2] + dm * qc + m0 * qb;
+            acc[3] = acc[3] + m0 * qc;
+        } else {  // constant multiplier: scale once at the end
+            acc[1] = acc[1] + qa;
+            acc[2] = acc[2] + qb;
+            acc[3] = acc[3] + qc;
+        }
+    }
+    block_sum<4>(acc, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st_fr(A.partials + blockIdx.x * 4 + k, acc[k]);
+        __threadfence();
+        ticket = atomicAdd(A.counter, 1u);
+    }
+    __syncthreads();
+    if (ticket != A.n_blocks - 1) return;
+    __threadfence();
+    fr_t tot[4] = {fr_t::zero(), fr_t::zero(), fr_t::zero(), fr_t::zero()};
+    for (uint32_t i = threadIdx.x; i < A.n_blocks; i += kBlock) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tot[k] = tot[k] + ld_fr_cg(A.partials + i * 4 + k);
+    }
+    __syncthreads();
+    block_sum<4>(tot, sh);
+    if (threadIdx.x == 0) {
+        if (!m_pairs) {
+            fr_t m0 = ld_fr(A.m_in);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) tot[k] = tot[k] * m0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st_fr(A.out + k, tot[k]);
+        *A.counter = 0;
+    }
+}
+
+// in-order fold of a small table: out[i] = in[2i] + r (in[2i+1] - in[2i]),  i < n_out
+__global__ void __launch_bounds__(kBlock) k_fold_small(const fr_t *in, fr_t *out, uint32_t n_out, fr_t r) {
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_out; i += gridDim.x * kBlock) {
+        fr_t x0 = ld_fr(in + 2 * i), x1 = ld_fr(in + 2 * i + 1);
+        st_fr(out + i, x0 + r * (x1 - x0));
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K3: eq / beta tables.  initHalfTable (src/utils.cpp:32-51): f[0] = init, then for every variable i the table doubles:
+// f[j | 2^i] = f[j] r_i, f[j] -= f[j] r_i.  One CTA per half table; both halves (and both points of the 6-argument
+// overload) are built by one launch.
+// --------------------------------------------------------------------------------------------------------------------
+struct half_job_t {
+    fr_t *out;           // 2^bits entries
+    const fr_t *r;       // bits challenges
+    uint32_t bits;
+    fr_t init;
+};
+struct half_args_t { half_job_t job[4]; };
+__global__ void __launch_bounds__(kBlock) k_half_tables(half_args_t A) {
+    const half_job_t J = A.job[blockIdx.x];
+    if (!J.out) return;
+    if (threadIdx.x == 0) st_fr(J.out, J.init);
+    __syncthreads();
+    for (uint32_t i = 0; i < J.bits; ++i) {
+        const uint32_t n = 1u << i;
+        const fr_t ri = ld_fr(J.r + i);
+        for (uint32_t j = threadIdx.x; j < n; j += kBlock) {
+            fr_t x = ld_fr(J.out + j);
+            fr_t t = x * ri;
+            st_fr(J.out + (j | n), t);
+            st_fr(J.out + j, x - t);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+// out[i] = f0[i & mask] s0[i >> fh]  (+ f1[i & mask] s1[i >> fh]),   then  *= tail_scale for i >= tail_start
+// (the relu_rou scaling of the bit-decomposition rows, src/prover.cpp:221-222)
+struct beta_args_t {
+    fr_t *out;
+    const fr_t *f0, *s0, *f1, *s1;  // f1 == nullptr: single point
+    uint32_t bits, first_half;
+    uint32_t tail_start;            // >= 2^bits: no tail scaling
+    fr_t tail_scale;
+};
+__global__ void __launch_bounds__(kBlock) k_beta_expand(beta_args_t A) {
+    const uint32_t n = 1u << A.bits, mask = (1u << A.first_half) - 1;
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        fr_t x = A.f0 ? ld_fr(A.f0 + (i & mask)) * ld_fr(A.s0 + (i >> A.first_half)) : fr_t::zero();
+        if (A.f1) x = x + ld_fr(A.f1 + (i & mask)) * ld_fr(A.s1 + (i >> A.first_half));
+        if (i >= A.tail_start) x = x * A.tail_scale;
+        st_fr(A.out + i, x);
+    }
+}
+
+// PADDING layer: beta_g[g] = beta_g_prev[g >> blh] * beta_gs[g & (2^blh - 1)]   (src/prover.cpp:214-219)
+__global__ void __launch_bounds__(kBlock) k_beta_outer(fr_t *out, const fr_t *hi, const fr_t *lo, uint32_t bits, uint32_t blh,
+                                                       uint32_t tail_start, fr_t tail_scale) {
+    const uint32_t n = 1u << bits, mask = (1u << blh) - 1;
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        fr_t x = ld_fr(hi + (i >> blh)) * ld_fr(lo + (i & mask));
+        if (i >= tail_start) x = x * tail_scale;
+        st_fr(out + i, x);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K3b: phiGInit (src/utils.cpp:61-103): closed-form MLE of the (I)FFT butterfly network at the point rx.
+// One CTA; `pw` holds the 2^n powers of the 2^n-th root of unity (or of its inverse for the IFFT).
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_phi_table(fr_t *phi, const fr_t *rx, const fr_t *pw, fr_t scale, int n, int is_ifft) {
+    const fr_t one = fr_t::one();
+    if (threadIdx.x == 0) {
+        st_fr(phi, scale);
+        if (is_ifft) st_fr(phi + 1, scale);
+    }
+    __threadfence();
+    __syncthreads();
+    const int i0 = is_ifft ? 2 : 1, i1 = is_ifft ? n : n - 1;
+    for (int i = i0; i <= i1; ++i) {
+        const uint32_t half = 1u << (i - 1);
+        const int m = n - i;
+        const fr_t rm = ld_fr(rx + m);
+        const fr_t t1 = one - rm;
+        for (uint32_t b = threadIdx.x; b < half; b += kBlock) {
+            fr_t t2 = rm * ld_fr(pw + ((size_t) b << m));
+            fr_t x = ld_fr(phi + b);
+            st_fr(phi + (b ^ half), x * (t1 - t2));
+            st_fr(phi + b, x * (t1 + t2));
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (!is_ifft) {
+        const uint32_t half = 1u << (n - 1);
+        const fr_t r0 = ld_fr(rx);
+        const fr_t t1 = one - r0;
+        for (uint32_t b = threadIdx.x; b < half; b += kBlock) {
+            fr_t t2 = r0 * ld_fr(pw + b);
+            st_fr(phi + b, ld_fr(phi + b) * (t1 + t2));
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K4/K5: gate gather-reduce.  The circuit topology is static, so at upload time every phase of every layer gets a
+// schedule: gates sorted by destination row and cut into work items of <= kItemLen consecutive records; rows that span
+// several items are finished by further levels that add up the per-item partial sums.  No atomics, no ordering
+// dependence (Fr addition is exact), one thread per item.
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int kItemLen = 16;
+
+struct gate_rec_t {   // 12 bytes
+    uint32_t g;       // output gate -> index into beta_g
+    uint32_t x;       // phase 1: index of the v operand (absolute index into val[0], or index into val[l-1]);  phase 2: u
+    uint32_t meta;    // bits 0-8: sc (index into two_mul, 0 = multiply by one);  bits 16-17: kind
+};
+// phase-1 kinds: 0 = uni gate (no value factor), 1 = v operand in layer 0, 2 = v operand in layer l-1
+// phase-2 kinds: 0 = scale by V_u0, 1 = scale by V_u1
+struct item_t {       // 12 bytes
+    uint32_t begin;   // first record (level 0) or first partial (level >= 1)
+    uint32_t dest;    // bit 31: 1 = final (index into out table selected by bit 30), 0 = partial slot
+    uint32_t count_flags;  // bits 0-15: count;  bits 16-17: kind of the records (phase 2 only)
+};
+constexpr uint32_t kDestFinal = 0x80000000u, kDestTable1 = 0x40000000u, kDestScalar = 0x20000000u;
+
+struct gate_args_t {
+    const gate_rec_t *recs;
+    const item_t *items;
+    uint32_t n_items;
+    const fr_t *beta_g;
+    const fr_t *val0, *val_prev;   // phase 1: value sources
+    const fr_t *beta_u;            // phase 2
+    const fr_t *two_mul;
+    fr_t vu[2];                    // phase 2: V_u0, V_u1
+    fr_t *out0, *out1;             // mult tables
+    fr_t *out_scalar;              // phase 2: add_term accumulator slot
+    fr_t *partial;                 // partial sums written by this level
+};
+
+__device__ __forceinline__ void store_item(const gate_args_t &A, uint32_t dest, const fr_t &acc) {
+    if (dest & kDestFinal) {
+        if (dest & kDestScalar) st_fr(A.out_scalar, acc);
+        else st_fr(((dest & kDestTable1) ? A.out1 : A.out0) + (dest & 0x1fffffffu), acc);
+    } else st_fr(A.partial + dest, acc);
+}
+
+__global__ void __launch_bounds__(kBlock) k_gate_items_p1(gate_args_t A) {
+    for (uint32_t it = blockIdx.x * kBlock + threadIdx.x; it < A.n_items; it += gridDim.x * kBlock) {
+        const item_t I = A.items[it];
+        const uint32_t cnt = I.count_flags & 0xffffu;
+        fr_t acc = fr_t::zero();
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const gate_rec_t R = A.recs[I.begin + k];
+            fr_t t = ld_fr(A.beta_g + R.g);
+            const uint32_t kind = (R.meta >> 16) & 3u, sc = R.meta & 0x1ffu;
+            if (kind == 1) t = t * ld_fr(A.val0 + R.x);
+            else if (kind == 2) t = t * ld_fr(A.val_prev + R.x);
+            if (sc) t = t * ld_fr(A.two_mul + sc);
+            acc = acc + t;
+        }
+        store_item(A, I.dest, acc);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_gate_items_p2(gate_args_t A) {
+    for (uint32_t it = blockIdx.x * kBlock + threadIdx.x; it < A.n_items; it += gridDim.x * kBlock) {
+        const item_t I = A.items[it];
+        const uint32_t cnt = I.count_flags & 0xffffu;
+        fr_t acc = fr_t::zero();
+        for (uint32_t k = 0; k < cnt; ++k) {
+            const gate_rec_t R = A.recs[I.begin + k];
+            fr_t t = ld_fr(A.beta_g + R.g) * ld_fr(A.beta_u + R.x);
+            const uint32_t sc = R.meta & 0x1ffu;
+            if (sc) t = t * ld_fr(A.two_mul + sc);
+            acc = acc + t;
+        }
+        acc = acc * A.vu[(I.count_flags >> 16) & 1u];
+        store_item(A, I.dest, acc);
+    }
+}
+
+// level >= 1: add up `count` consecutive partial sums of the previous level
+__global__ void __launch_bounds__(kBlock) k_sum_partials(gate_args_t A, const fr_t *src) {
+    for (uint32_t it = blockIdx.x * kBlock + threadIdx.x; it < A.n_items; it += gridDim.x * kBlock) {
+        const item_t I = A.items[it];
+        const uint32_t cnt = I.count_flags & 0xffffu;
+        fr_t acc = fr_t::zero();
+        for (uint32_t k = 0; k < cnt; ++k) acc = acc + ld_fr(src + I.begin + k);
+        store_item(A, I.dest, acc);
+    }
+}
+
+// V table of operands that live in layer 0: V[u] = val[0][ori_id[u]]  (getCirValue, src/prover.cpp:499-501)
+__global__ void __launch_bounds__(kBlock) k_gather(fr_t *out, const fr_t *val0, const uint32_t *ori, uint32_t n) {
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr(out + i, ld_fr(val0 + ori[i]));
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K4b: FFT/IFFT layers: V[u] = sum_g val[(g << shift) | u] * beta_g[g],  u < n_u  (src/prover.cpp:190-197).
+// grid = (u blocks, g chunks); partial[chunk][u], finished by k_colsum_finish.
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_dense_colsum(const fr_t *val, const fr_t *beta_g, uint32_t n_u, uint32_t shift,
+                                                         uint32_t cnt_len, uint32_t g_per_chunk, fr_t *partial) {
+    const uint32_t u = blockIdx.x * kBlock + threadIdx.x;
+    if (u >= n_u) return;
+    const uint32_t g0 = blockIdx.y * g_per_chunk;
+    const uint32_t g1 = g0 + g_per_chunk < cnt_len ? g0 + g_per_chunk : cnt_len;
+    fr_t acc = fr_t::zero();
+    for (uint32_t g = g0; g < g1; ++g) acc = acc + ld_fr(val + (((size_t) g << shift) | u)) * ld_fr(beta_g + g);
+    st_fr(partial + (size_t) blockIdx.y * n_u + u, acc);
+}
+__global__ void __launch_bounds__(kBlock) k_colsum_finish(const fr_t *partial, uint32_t n_u, uint32_t n_chunks, fr_t *out) {
+    const uint32_t u = blockIdx.x * kBlock + threadIdx.x;
+    if (u >= n_u) return;
+    fr_t acc = fr_t::zero();
+    for (uint32_t c = 0; c < n_chunks; ++c) acc = acc + ld_fr(partial + (size_t) c * n_u + u);
+    st_fr(out + u, acc);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K5b: DOT_PROD phase 1:  V0[(u << fft_bl) | t] = sum_{gates with that u} beta_g[g] * val[(v << fft_bl) | t]
+// (src/prover.cpp:86-91).  CSR by u built at upload; one thread per (u, t), coalesced over t.
+// --------------------------------------------------------------------------------------------------------------------
+struct dp_gate_t { uint32_t g, v; };
+__global__ void __launch_bounds__(kBlock) k_dotprod_axpy(fr_t *out, const fr_t *val, const fr_t *beta_g, const uint32_t *row_ptr,
+                                                         const dp_gate_t *gates, uint32_t n_rows, uint32_t fft_bl) {
+    const uint32_t fft_len = 1u << fft_bl;
+    const size_t total = (size_t) n_rows << fft_bl;
+    for (size_t idx = (size_t) blockIdx.x * kBlock + threadIdx.x; idx < total; idx += (size_t) gridDim.x * kBlock) {
+        const uint32_t u = (uint32_t) (idx >> fft_bl), t = (uint32_t) idx & (fft_len - 1);
+        fr_t acc = fr_t::zero();
+        for (uint32_t k = row_ptr[u]; k < row_ptr[u + 1]; ++k) {
+            const dp_gate_t G = gates[k];
+            acc = acc + ld_fr(beta_g + G.g) * ld_fr(val + (((size_t) G.v << fft_bl) | t));
+        }
+        st_fr(out + idx, acc);
+    }
+}
+
+// K5 (DOT_PROD phase 2): V[v] = sum_t val[(v << fft_bl) | t] * beta_gs[t]  (src/prover.cpp:277-284); one CTA per row v
+__global__ void __launch_bounds__(kBlock) k_dense_rowdot(fr_t *out, const fr_t *val, const fr_t *beta_gs, uint32_t fft_bl) {
+    __shared__ fr_t sh[kBlock];
+    const uint32_t v = blockIdx.x, fft_len = 1u << fft_bl;
+    fr_t acc[1] = {fr_t::zero()};
+    for (uint32_t t = threadIdx.x; t < fft_len; t += kBlock)
+        acc[0] = acc[0] + ld_fr(val + (((size_t) v << fft_bl) | t)) * ld_fr(beta_gs + t);
+    block_sum<1>(acc, sh);
+    if (threadIdx.x == 0) st_fr(out + v, acc[0]);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K6: Liu init: mult[ori[h]] += beta(r, sigma)[h] for one (layer, side); beta computed on the fly from half tables.
+// Within one launch the ori[] entries are distinct (initSubset de-duplicates, src/circuit.cpp:17-23), and launches
+// are stream-ordered, so plain read-modify-write is race free.
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_liu_scatter(fr_t *mult, const uint32_t *ori, uint32_t n, const fr_t *f, const fr_t *s,
+                                                        uint32_t first_half) {
+    const uint32_t mask = (1u << first_half) - 1;
+    for (uint32_t h = blockIdx.x * kBlock + threadIdx.x; h < n; h += gridDim.x * kBlock) {
+        fr_t b = ld_fr(f + (h & mask)) * ld_fr(s + (h >> first_half));
+        const uint32_t x = ori[h];
+        st_fr(mult + x, ld_fr(mult + x) + b);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// Vres (src/prover.cpp:434-457): MLE of the (tiny) output layer at r.  One CTA, in-place halving in shared memory.
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_vres(const fr_t *val, uint32_t output_size, const fr_t *r, uint32_t r_size, fr_t *scratch,
+                                                 fr_t *out) {
+    // scratch holds 2^r_size entries
+    const uint32_t whole = 1u << r_size;
+    for (uint32_t i = threadIdx.x; i < whole; i += kBlock) st_fr(scratch + i, i < output_size ? ld_fr(val + i) : fr_t::zero());
+    __threadfence();
+    __syncthreads();
+    uint32_t n = whole;
+    for (uint32_t i = 0; i < r_size; ++i) {
+        const fr_t ri = ld_fr(r + i);
+        const uint32_t half = n >> 1;
+        // two passes so that in-place writes do not race with reads of later pairs
+        for (uint32_t base = 0; base < half; base += kBlock) {
+            const uint32_t j = base + threadIdx.x;
+            fr_t x;
+            if (j < half) {
+                fr_t x0 = ld_fr(scratch + 2 * j), x1 = ld_fr(scratch + 2 * j + 1);
+                x = x0 + ri * (x1 - x0);
+            }
+            __syncthreads();
+            if (j < half) st_fr(scratch + j, x);
+            __threadfence();
+            __syncthreads();
+        }
+        n = half;
+    }
+    if (threadIdx.x == 0) st_fr(out, ld_fr(scratch));
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// element-wise helpers (unit parity tests, Hyrax scalar bookkeeping)
+// --------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_fr_binop(const fr_t *a, const fr_t *b, fr_t *out, uint32_t n, int op) {
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        fr_t x = ld_fr(a + i), y = ld_fr(b + i);
+        st_fr(out + i, op == 0 ? x + y : op == 1 ? x - y : x * y);
+    }
+}
+
+}  // namespace zk

@@ -1,0 +1,211 @@
+// See prover.hpp.  Control flow and accounting mirror src/prover.cpp of the reference; the arithmetic is on the device.
+#include "prover.hpp"
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+static_assert(sizeof(F) == 32, "F must be 4 x 64-bit Montgomery limbs (mcl Fr layout)");
+static_assert(sizeof(uniGate) == sizeof(zk_uni_gate), "uniGate layout (src/circuit.h:15-22)");
+static_assert(sizeof(binGate) == sizeof(zk_bin_gate), "binGate layout (src/circuit.h:24-33)");
+
+static inline const uint64_t *w(const F &x) { return reinterpret_cast<const uint64_t *>(&x); }
+static inline uint64_t *w(F &x) { return reinterpret_cast<uint64_t *>(&x); }
+
+#define ZK_F_BYTES 32   /* F_BYTE_SIZE == Fr::getByteSize() */
+
+prover::prover() {}
+
+prover::~prover() {
+    poly_p.reset();
+    if (ctx_) zk_ctx_destroy(ctx_);
+}
+
+void prover::check(int rc, const char *what) const {
+    if (rc != 0) throw std::runtime_error(std::string("zkcnn_b200: ") + what + ": " + zk_last_error());
+}
+
+void prover::uploadCircuit() {
+    check(zk_circuit_begin(ctx_, C.size, w(C.two_mul[0]), (uint32_t) C.two_mul.size()), "zk_circuit_begin");
+    for (u32 i = 0; i < C.size; ++i) {
+        const layer &cur = C.circuit[i];
+        zk_layer_desc d;
+        memset(&d, 0, sizeof d);
+        d.ty = (int32_t) cur.ty;
+        d.size = cur.size;
+        for (int b = 0; b < 2; ++b) {
+            d.size_u[b] = cur.size_u[b]; d.size_v[b] = cur.size_v[b];
+            d.bit_length_u[b] = cur.bit_length_u[b]; d.bit_length_v[b] = cur.bit_length_v[b];
+        }
+        d.bit_length = cur.bit_length;
+        d.max_bl_u = cur.max_bl_u;
+        d.max_bl_v = cur.max_bl_v;
+        d.need_phase2 = cur.need_phase2;
+        d.zero_start_id = cur.zero_start_id;
+        d.fft_bit_length = cur.fft_bit_length;
+        memcpy(d.scale, &cur.scale, 32);
+        d.uni_gates = reinterpret_cast<const zk_uni_gate *>(cur.uni_gates.data());
+        d.n_uni = cur.uni_gates.size();
+        d.bin_gates = reinterpret_cast<const zk_bin_gate *>(cur.bin_gates.data());
+        d.n_bin = cur.bin_gates.size();
+        d.ori_id_u = cur.ori_id_u.data();
+        d.ori_id_v = cur.ori_id_v.data();
+        check(zk_circuit_layer(ctx_, i, &d), "zk_circuit_layer");
+    }
+    check(zk_circuit_end(ctx_), "zk_circuit_end");
+    circuit_uploaded_ = true;
+}
+
+void prover::uploadWitness() {
+    for (u32 i = 0; i < C.size; ++i)
+        check(zk_witness_layer(ctx_, i, val[i].empty() ? nullptr : w(val[i][0]), val[i].size()), "zk_witness_layer");
+}
+
+void prover::init() {   // src/prover.cpp:17-21 (+ upload of what the reference reads in place)
+    proof_size = 0;
+    upload_timer.start();
+    if (!ctx_) {
+        int dev = device_;
+        if (dev < 0) { const char *e = getenv("ZKCNN_DEVICE"); dev = e ? atoi(e) : 0; }
+        ctx_ = zk_ctx_create(dev);
+        if (!ctx_) throw std::runtime_error(std::string("zkcnn_b200: cannot create a device context: ") + zk_last_error());
+    }
+    if (!circuit_uploaded_) uploadCircuit();
+    uploadWitness();
+    check(zk_prover_init(ctx_), "zk_prover_init");
+    upload_timer.stop();
+}
+
+void prover::sumcheckInitAll(const vector<F>::const_iterator &r_0_from_v) {   // src/prover.cpp:28-36
+    u32 last_bl = C.circuit[C.size - 1].bit_length;
+    prove_timer.start();
+    check(zk_sumcheck_init_all(ctx_, last_bl ? w(r_0_from_v[0]) : nullptr, last_bl), "zk_sumcheck_init_all");
+    prove_timer.stop();
+}
+
+void prover::sumcheckInit(const F &alpha_0, const F &beta_0) {   // src/prover.cpp:43-52
+    prove_timer.start();
+    check(zk_sumcheck_init(ctx_, w(alpha_0), w(beta_0)), "zk_sumcheck_init");
+    prove_timer.stop();
+}
+
+void prover::sumcheckDotProdInitPhase1() {   // src/prover.cpp:57-95
+    prove_timer.start();
+    check(zk_sumcheck_dotprod_init_phase1(ctx_), "zk_sumcheck_dotprod_init_phase1");
+    prove_timer.stop();
+}
+
+void prover::sumcheckInitPhase1(const F &relu_rou_0) {   // src/prover.cpp:155-239
+    prove_timer.start();
+    check(zk_sumcheck_init_phase1(ctx_, w(relu_rou_0)), "zk_sumcheck_init_phase1");
+    prove_timer.stop();
+}
+
+void prover::sumcheckInitPhase2() {   // src/prover.cpp:241-310
+    prove_timer.start();
+    check(zk_sumcheck_init_phase2(ctx_), "zk_sumcheck_init_phase2");
+    prove_timer.stop();
+}
+
+cubic_poly prover::sumcheckDotProdUpdate1(const F &previous_random) {   // src/prover.cpp:103-144
+    prove_timer.start();
+    F c[4];
+    check(zk_sumcheck_dotprod_update1(ctx_, w(previous_random), w(c[0])), "zk_sumcheck_dotprod_update1");
+    cubic_poly ret(c[0], c[1], c[2], c[3]);
+    proof_size += ZK_F_BYTES * (3 + (!ret.a.isZero()));
+    prove_timer.stop();
+    if (transcript_) for (int k = 0; k < 4; ++k) transcript_->put_fr(w(c[k]));
+    return ret;
+}
+
+quadratic_poly prover::sumcheckUpdate1(const F &previous_random) {   // src/prover.cpp:360-362
+    prove_timer.start();
+    F c[3];
+    check(zk_sumcheck_update1(ctx_, w(previous_random), w(c[0])), "zk_sumcheck_update1");
+    prove_timer.stop();
+    proof_size += ZK_F_BYTES * 3;
+    if (transcript_) for (int k = 0; k < 3; ++k) transcript_->put_fr(w(c[k]));
+    return quadratic_poly(c[0], c[1], c[2]);
+}
+
+quadratic_poly prover::sumcheckUpdate2(const F &previous_random) {   // src/prover.cpp:364-366
+    prove_timer.start();
+    F c[3];
+    check(zk_sumcheck_update2(ctx_, w(previous_random), w(c[0])), "zk_sumcheck_update2");
+    prove_timer.stop();
+    proof_size += ZK_F_BYTES * 3;
+    if (transcript_) for (int k = 0; k < 3; ++k) transcript_->put_fr(w(c[k]));
+    return quadratic_poly(c[0], c[1], c[2]);
+}
+
+F prover::Vres(const vector<F>::const_iterator &r, u32 output_size, u8 r_size) {   // src/prover.cpp:434-457
+    prove_timer.start();
+    F res;
+    check(zk_vres(ctx_, r_size ? w(r[0]) : nullptr, output_size, r_size, w(res)), "zk_vres");
+    prove_timer.stop();
+    proof_size += ZK_F_BYTES;
+    if (transcript_) transcript_->put_fr(w(res));
+    return res;
+}
+
+void prover::sumcheckDotProdFinalize1(const F &previous_random, F &claim_1) {   // src/prover.cpp:146-153
+    prove_timer.start();
+    check(zk_sumcheck_dotprod_finalize1(ctx_, w(previous_random), w(claim_1)), "zk_sumcheck_dotprod_finalize1");
+    prove_timer.stop();
+    proof_size += ZK_F_BYTES * 1;
+    if (transcript_) transcript_->put_fr(w(claim_1));
+}
+
+void prover::sumcheckFinalize1(const F &previous_random, F &claim_0, F &claim_1) {   // src/prover.cpp:459-471
+    prove_timer.start();
+    check(zk_sumcheck_finalize1(ctx_, w(previous_random), w(claim_0), w(claim_1)), "zk_sumcheck_finalize1");
+    prove_timer.stop();
+    proof_size += ZK_F_BYTES * 2;
+    if (transcript_) { transcript_->put_fr(w(claim_0)); transcript_->put_fr(w(claim_1)); }
+}
+
+void prover::sumcheckFinalize2(const F &previous_random, F &claim_0, F &claim_1) {   // src/prover.cpp:473-485
+    prove_timer.start();
+    check(zk_sumcheck_finalize2(ctx_, w(previous_random), w(claim_0), w(claim_1)), "zk_sumcheck_finalize2");
+    prove_timer.stop();
+    proof_size += ZK_F_BYTES * 2;
+    if (transcript_) { transcript_->put_fr(w(claim_0)); transcript_->put_fr(w(claim_1)); }
+}
+
+void prover::sumcheckLiuFinalize(const F &previous_random, F &claim_1) {   // src/prover.cpp:487-497
+    prove_timer.start();
+    check(zk_sumcheck_liu_finalize(ctx_, w(previous_random), w(claim_1)), "zk_sumcheck_liu_finalize");
+    prove_timer.stop();
+    proof_size += ZK_F_BYTES;
+    if (transcript_) transcript_->put_fr(w(claim_1));
+}
+
+void prover::sumcheckLiuInit(const vector<F> &s_u, const vector<F> &s_v) {   // src/prover.cpp:312-358
+    if (s_u.size() + 1 < C.size || s_v.size() + 1 < C.size) throw std::out_of_range("sumcheckLiuInit: sigma vectors too short");
+    prove_timer.start();
+    check(zk_sumcheck_liu_init(ctx_, w(s_u[0]), w(s_v[0]), (uint32_t) s_u.size()), "zk_sumcheck_liu_init");
+    prove_timer.stop();
+}
+
+quadratic_poly prover::sumcheckLiuUpdate(const F &previous_random) {   // src/prover.cpp:385-394
+    prove_timer.start();
+    F c[3];
+    check(zk_sumcheck_liu_update(ctx_, w(previous_random), w(c[0])), "zk_sumcheck_liu_update");
+    prove_timer.stop();
+    proof_size += ZK_F_BYTES * 3;
+    if (transcript_) for (int k = 0; k < 3; ++k) transcript_->put_fr(w(c[k]));
+    return quadratic_poly(c[0], c[1], c[2]);
+}
+
+hyrax_bls12_381::polyProver &prover::commitInput(const vector<G> &gens) {   // src/prover.cpp:503-511
+    if (C.circuit[0].size != (1ULL << C.circuit[0].bit_length)) {
+        val[0].resize(1ULL << C.circuit[0].bit_length);
+        for (size_t i = C.circuit[0].size; i < val[0].size(); ++i) val[0][i].clear();
+    }
+#ifdef ZKCNN_DROPIN_CPU_HYRAX
+    poly_p = std::make_unique<hyrax_bls12_381::polyProver>(val[0], gens);
+#else
+    // the device copy of val[0] is already zero-padded (zk_witness_layer); nothing is uploaded again
+    poly_p = std::make_unique<hyrax_bls12_381::polyProver>(ctx_, gens, (unsigned char) C.circuit[0].bit_length, transcript_);
+#endif
+    return *poly_p;
+}

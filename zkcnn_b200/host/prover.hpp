@@ -1,0 +1,99 @@
+// Host shim with the public interface of the reference's GKR prover, class prover (src/prover.hpp:16-78).
+// Every member forwards through the C ABI (include/zkcnn_b200.h) to the device-resident prover state; the shim keeps
+// only what the reference keeps on the host side of the interface: the circuit `C`, the witness `val`, timers and
+// the proof-size counter.
+//
+// Build modes (see polyProver.hpp):
+//   ZKCNN_DROPIN           : inside the reference tree; takes the place of src/prover.hpp (same include guard), so the
+//                            reference's verifier.cpp / neuralNetwork.cpp / models.cpp compile against it unchanged.
+//   ZKCNN_DROPIN_CPU_HYRAX : additionally keep the reference's CPU polyProver (BASELINE.json config 2:
+//                            "sumcheck fold + MLE table on GPU, Hyrax MSM still CPU").
+#ifndef ZKCNN_PROVER_HPP
+#define ZKCNN_PROVER_HPP
+
+#ifdef ZKCNN_DROPIN
+#include "global_var.hpp"   // reference: src/
+#include "circuit.h"
+#include "polynomial.h"
+#else
+#include "zk_types.hpp"
+#include "polyProver.hpp"
+#endif
+#include "../../include/zkcnn_b200.h"
+#include "transcript.hpp"
+#include <memory>
+
+using std::unique_ptr;
+
+class neuralNetwork;
+class singleConv;
+class prover {
+public:
+    prover();
+    ~prover();
+    prover(const prover &) = delete;
+    prover &operator=(const prover &) = delete;
+
+    void init();
+
+    void sumcheckInitAll(const vector<F>::const_iterator &r_0_from_v);
+    void sumcheckInit(const F &alpha_0, const F &beta_0);
+    void sumcheckDotProdInitPhase1();
+    void sumcheckInitPhase1(const F &relu_rou_0);
+    void sumcheckInitPhase2();
+
+    cubic_poly sumcheckDotProdUpdate1(const F &previous_random);
+    quadratic_poly sumcheckUpdate1(const F &previous_random);
+    quadratic_poly sumcheckUpdate2(const F &previous_random);
+
+    F Vres(const vector<F>::const_iterator &r, u32 output_size, u8 r_size);
+
+    void sumcheckDotProdFinalize1(const F &previous_random, F &claim_1);
+    void sumcheckFinalize1(const F &previous_random, F &claim_0, F &claim_1);
+    void sumcheckFinalize2(const F &previous_random, F &claim_0, F &claim_1);
+    void sumcheckLiuFinalize(const F &previous_random, F &claim_1);
+
+    void sumcheckLiuInit(const vector<F> &s_u, const vector<F> &s_v);
+    quadratic_poly sumcheckLiuUpdate(const F &previous_random);
+
+    hyrax_bls12_381::polyProver &commitInput(const vector<G> &gens);
+
+    timer prove_timer;
+    double proveTime() const { return prove_timer.elapse_sec(); }
+    double proofSize() const { return (double) proof_size / 1024.0; }
+    double polyProverTime() const { return poly_p->getPT(); }
+    double polyProofSize() const { return poly_p->getPS(); }
+
+    layeredCircuit C;
+    vector<vector<F>> val;        // the output of each gate
+
+    // ---- additions of the B200 build (not in the reference interface) ----------------------------------------------
+    // CUDA device used by this prover (default: env ZKCNN_DEVICE or 0).  Call before init().
+    void setDevice(int device) { device_ = device; }
+    // record every prover->verifier message in SURVEY.md App. A order (nullptr = off)
+    void setTranscript(zkcnn_b200::Transcript *t) { transcript_ = t; }
+    // init() uploads C once; call this if C was rebuilt and must be uploaded again
+    void invalidateCircuit() { circuit_uploaded_ = false; }
+    // seconds spent uploading circuit / witness in init() (outside the prove timer, like the reference's allocations)
+    double uploadTime() const { return upload_timer.elapse_sec(); }
+    uint64_t gpuLaunches() const { return ctx_ ? zk_ctx_launch_count(ctx_) : 0; }
+    zk_ctx *context() { return ctx_; }
+    timer upload_timer;
+
+private:
+    void check(int rc, const char *what) const;
+    void uploadCircuit();
+    void uploadWitness();
+
+    zk_ctx *ctx_ = nullptr;
+    int device_ = -1;
+    bool circuit_uploaded_ = false;
+    u64 proof_size = 0;
+    zkcnn_b200::Transcript *transcript_ = nullptr;
+    unique_ptr<hyrax_bls12_381::polyProver> poly_p;
+
+    friend neuralNetwork;
+    friend singleConv;
+};
+
+#endif //ZKCNN_PROVER_HPP
