@@ -18,12 +18,12 @@ all: lib host
 lib: $(LIBDIR)/libzkcnn_b200.so
 $(LIBDIR)/libzkcnn_b200.so: $(CSRC_DEPS)
 	mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -shared $(CSRC)/capi.cu -o $@ -lcudart
+	$(NVCC) $(NVFLAGS) -Xcompiler -Wno-unknown-pragmas -shared -cudart static -Xlinker -soname=libzkcnn_b200.so $(CSRC)/capi.cu -o $@
 
 emu: $(EMUDIR)/libzkcnn_b200_emu.so
 $(EMUDIR)/libzkcnn_b200_emu.so: $(CSRC_DEPS) tests/emu/cuda_emu.cpp tests/emu/cuda_emu.hpp
 	mkdir -p $(EMUDIR)
-	$(CXX) -O2 -g -std=c++17 -fPIC -DZK_EMU -Wall -Wno-unknown-pragmas -Wno-unused-function -shared -x c++ $(CSRC)/capi.cu -x none tests/emu/cuda_emu.cpp -o $@ -lpthread
+	$(CXX) -O2 -g -std=c++17 -fPIC -DZK_EMU -Wall -Wno-unknown-pragmas -Wno-unused-function -shared -Wl,-soname=libzkcnn_b200_emu.so -x c++ $(CSRC)/capi.cu -x none tests/emu/cuda_emu.cpp -o $@ -lpthread
 
 clean:
 	rm -rf $(LIBDIR) $(EMUDIR)

@@ -59,14 +59,17 @@ int main(int argc, char **argv) {
     if (model == "vgg") net_file = argv[k++];
     int pic_cnt = atoi(argv[k++]);
     uint64_t seed = strtoull(argv[k++], nullptr, 0);
+    bool real_gens = false;
     std::string tr_out; bool shapes = false, hashes = false;
     for (; k < argc; ++k) {
         std::string a = argv[k];
         if (a == "--transcript") tr_out = argv[++k];
+        else if (a == "--gens") real_gens = std::string(argv[++k]) == "real";
         else if (a == "--shapes") shapes = true;
         else if (a == "--circuit-hash") shapes = hashes = true;
     }
 
+    if (real_gens) install_real_base_point();
     SeededStream rng(seed);
     rng.install();
 

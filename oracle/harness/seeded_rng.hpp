@@ -34,3 +34,17 @@ struct SeededStream {
     }
     void install() { mcl::fp::RandGen::setRandFunc(this, &SeededStream::read); }
 };
+
+// The shipped demos multiply getG1basePoint() by a random scalar to make the Hyrax generators (src/verifier.cpp:125),
+// but initPairing() clears that base point (mcl/include/mcl/bn.hpp:924), so every generator is the point at infinity
+// (SURVEY.md section 0, fact 3).  `--gens real` puts the standard BLS12-381 G1 generator (mcl/test/bls12_test.cpp:53-54)
+// into mcl's public static before the verifier runs, which makes the same reference code path produce
+// non-degenerate generators.  No reference file is modified.
+inline void install_real_base_point() {
+    mcl::bn::Fp x, y;
+    x.setStr("17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb", 16);
+    y.setStr("08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1", 16);
+    mcl::bn::G1 g;
+    g.set(x, y);
+    const_cast<mcl::bn::G1 &>(mcl::bn::getG1basePoint()) = g;
+}

@@ -1,14 +1,376 @@
-// C ABI, part 2: Hyrax polynomial commitment (placeholder until the MSM kernels land)
+// C ABI, part 2: Hyrax polynomial commitment (mirror of 3rd/hyrax-bls12-381/src/polyProver.cpp) and the stateless
+// primitives.  Included by capi.cu only.
 #pragma once
-#include "ctx.hpp"
-extern "C" {
-#define ZK_NOT_YET(name) { zk::g_last_error = name ": not implemented yet"; return -1; }
-int zk_poly_bind_input(zk_ctx *, const uint64_t *, uint32_t) ZK_NOT_YET("zk_poly_bind_input")
-int zk_poly_create(zk_ctx *, const uint64_t *, uint64_t, const uint64_t *, uint32_t) ZK_NOT_YET("zk_poly_create")
-int zk_poly_commit(zk_ctx *, uint64_t *, uint32_t) ZK_NOT_YET("zk_poly_commit")
-int zk_poly_evaluate(zk_ctx *, const uint64_t *, uint32_t, uint64_t *) ZK_NOT_YET("zk_poly_evaluate")
-int zk_poly_init_bullet_prove(zk_ctx *, const uint64_t *, uint32_t, const uint64_t *, uint32_t) ZK_NOT_YET("zk_poly_init_bullet_prove")
-int zk_poly_bullet_prove(zk_ctx *, uint64_t *, uint64_t *, uint64_t *, uint64_t *) ZK_NOT_YET("zk_poly_bullet_prove")
-int zk_poly_bullet_update(zk_ctx *, const uint64_t *) ZK_NOT_YET("zk_poly_bullet_update")
-int zk_poly_bullet_open(zk_ctx *, uint64_t *) ZK_NOT_YET("zk_poly_bullet_open")
+#include "capi_sumcheck.cuh"
+#include "hyrax_kernels.cuh"
+
+namespace zk {
+
+static uint64_t fnv1a64(const void *p, size_t n) {
+    const uint8_t *b = static_cast<const uint8_t *>(p);
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    return h;
 }
+
+static void msm_configure() {
+#if !defined(ZK_EMU)
+    static bool done = false;
+    if (!done) {
+        rt::check(cudaFuncSetAttribute(k_msm_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(msm_smem_t)),
+                  "cudaFuncSetAttribute(k_msm_window)");
+        done = true;
+    }
+#endif
+}
+
+// (re)build the fixed-base window table for a generator set given as host Jacobian points
+static void msm_prepare_table(zk_ctx *ctx, hyrax_t &H, const uint64_t *gens, uint32_t n_gens) {
+    const uint64_t h = fnv1a64(gens, (size_t) n_gens * sizeof(g1_jac_t)) ^ n_gens;
+    if (H.table_ready && H.gens_hash == h && H.n_gens == n_gens) return;   // same public generators as last time
+    H.n_gens = n_gens;
+    rt::dbuf tmp;
+    tmp.ensure((size_t) n_gens * sizeof(g1_jac_t));
+    rt::h2d(tmp.p, gens, (size_t) n_gens * sizeof(g1_jac_t), ctx->stream);
+    H.gens_aff.ensure((size_t) n_gens * sizeof(g1_aff_t));
+    ZK_KLAUNCH(ctx, k_g1_to_affine, dim3(grid_for(n_gens)), dim3(kBlock), 0, tmp.as<g1_jac_t>(), H.gens_aff.as<g1_aff_t>(), n_gens);
+    H.table.ensure((size_t) kMsmWindows * n_gens * sizeof(g1_aff_t));
+    ZK_KLAUNCH(ctx, k_msm_table_build, dim3((n_gens + 63) / 64), dim3(64), 0, H.gens_aff.as<g1_aff_t>(), H.table.as<g1_aff_t>(), n_gens);
+    rt::sync(ctx->stream);
+    H.gens_hash = h;
+    H.table_ready = true;
+}
+
+// out_dev[k] (normalised) = sum_j scalars[k*n + j] * G_j  for k < n_rows, generators taken from H.table
+static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n, uint32_t n_rows, g1_jac_t *out_dev) {
+    ZK_REQUIRE(H.table_ready && n <= H.n_gens, "MSM: generator table missing or too small");
+    msm_configure();
+    const uint32_t n_chunks = (uint32_t) ((n + kMsmChunk - 1) / kMsmChunk);
+    H.msm_rowinfo.ensure((size_t) n_rows * 4);
+    rt::dzero(H.msm_rowinfo.p, (size_t) n_rows * 4, ctx->stream);
+    ZK_KLAUNCH(ctx, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
+    const size_t per_row = (size_t) n_chunks * kMsmWindows;
+    H.msm_out.ensure((size_t) n_rows * per_row * sizeof(g1_jac_t));
+    msm_args_t A;
+    A.scalars = scalars_dev;
+    A.table = H.table.as<g1_aff_t>();
+    A.rowinfo = H.msm_rowinfo.as<uint32_t>();
+    A.n = n;
+    A.n_table = H.n_gens;
+    A.n_chunks = n_chunks;
+    A.partial = H.msm_out.as<g1_jac_t>();
+    // grid.x is limited to 2^31-1, grid.y to 65535: rows * chunks in x, windows in y
+    ZK_KLAUNCH(ctx, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
+    ZK_KLAUNCH(ctx, k_msm_finish, dim3((n_rows + 63) / 64), dim3(64), 0, H.msm_out.as<g1_jac_t>(), n_rows, (uint32_t) per_row, out_dev);
+}
+
+static void hyrax_bind(zk_ctx *ctx, const fr_t *Z, uint32_t bit_length, const uint64_t *gens, uint32_t n_gens) {
+    hyrax_t &H = ctx->hy;
+    H.Z = Z;
+    H.bit_length = bit_length;
+    H.r_bits = bit_length >> 1;
+    H.l_bits = bit_length - H.r_bits;
+    ZK_REQUIRE(gens && n_gens == (1u << H.l_bits), "Hyrax: need exactly 2^ceil(bl/2) generators (polyProver.cpp:26)");
+    msm_prepare_table(ctx, H, gens, n_gens);
+    H.bound = true;
+    H.cur = 0;
+    H.round = 0;
+}
+
+}  // namespace zk
+
+extern "C" {
+
+int zk_poly_bind_input(zk_ctx *ctx, const uint64_t *gens, uint32_t n_gens) {   // src/prover.cpp:503-511
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready, "circuit not uploaded");
+    zk::rt::set_device(ctx->device);
+    zk::layer_t &L0 = ctx->layers[0];
+    ZK_REQUIRE(L0.n_val >= L0.d.size && L0.val.p, "input layer witness missing");
+    zk::hyrax_bind(ctx, L0.val.as<zk::fr_t>(), (uint32_t) L0.d.bit_length, gens, n_gens);
+    ZK_API_END
+}
+
+int zk_poly_create(zk_ctx *ctx, const uint64_t *Z, uint64_t n, const uint64_t *gens, uint32_t n_gens) {   // polyProver.cpp:12-17
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && Z && n >= 1, "bad arguments");
+    zk::rt::set_device(ctx->device);
+    uint32_t bl = 0;
+    while ((1ull << bl) < n) ++bl;
+    ZK_REQUIRE(bl <= 30, "polynomial too large");
+    zk::hyrax_t &H = ctx->hy;
+    H.z_own.ensure(sizeof(zk::fr_t) << bl);
+    zk::rt::h2d(H.z_own.p, Z, n * sizeof(zk::fr_t), ctx->stream);
+    if ((1ull << bl) > n) zk::rt::dzero(H.z_own.as<zk::fr_t>() + n, ((1ull << bl) - n) * sizeof(zk::fr_t), ctx->stream);
+    zk::rt::sync(ctx->stream);
+    zk::hyrax_bind(ctx, H.z_own.as<zk::fr_t>(), bl, gens, n_gens);
+    ZK_API_END
+}
+
+int zk_poly_commit(zk_ctx *ctx, uint64_t *comm_out, uint32_t n_out) {   // polyProver.cpp:19-34
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->hy.bound && comm_out, "no polynomial bound");
+    zk::rt::set_device(ctx->device);
+    zk::hyrax_t &H = ctx->hy;
+    const uint32_t rsize = 1u << H.r_bits, lsize = 1u << H.l_bits;
+    ZK_REQUIRE(n_out == rsize, "commit: output must hold 2^(bl/2) points");
+    zk::rt::dbuf &out = H.pts_out;
+    out.ensure((size_t) rsize * sizeof(zk::g1_jac_t));
+    zk::msm_run(ctx, H, H.Z, lsize, rsize, out.as<zk::g1_jac_t>());
+    zk::rt::d2h(comm_out, out.p, (size_t) rsize * sizeof(zk::g1_jac_t), ctx->stream);
+    zk::rt::sync(ctx->stream);
+    ZK_API_END
+}
+
+int zk_poly_evaluate(zk_ctx *ctx, const uint64_t *x, uint32_t n, uint64_t *out) {   // polyProver.cpp:36-42
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && ctx->hy.bound && out && n == ctx->hy.bit_length, "evaluate: wrong number of variables");
+    rt::set_device(ctx->device);
+    hyrax_t &H = ctx->hy;
+    ensure_round_scratch(ctx);
+    std::vector<fr_t> xs(n);
+    memcpy(xs.data(), x, (size_t) n * 32);
+    rt::dbuf X;
+    X.ensure(sizeof(fr_t) << n);
+    beta_point_t pts[1] = {{xs.data(), fr_t::one()}};
+    build_beta(ctx, X.as<fr_t>(), n, pts, 1);
+    const uint32_t g = grid_for(1ull << n);
+    ZK_KLAUNCH(ctx, k_dot_long, dim3(g), dim3(kBlock), 0, H.Z, X.as<fr_t>(), 1ull << n, ctx->partials.as<fr_t>(), ctx->counters.as<uint32_t>() + 3,
+               ctx->round_out.as<fr_t>());
+    rt::d2h(ctx->h_out, ctx->round_out.p, sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    fr_store(out, ctx->h_out[0]);
+    ZK_API_END
+}
+
+int zk_poly_init_bullet_prove(zk_ctx *ctx, const uint64_t *lx, uint32_t n_lx, const uint64_t *rx, uint32_t n_rx) {   // polyProver.cpp:52-74
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && ctx->hy.bound, "no polynomial bound");
+    hyrax_t &H = ctx->hy;
+    ZK_REQUIRE(n_lx == H.l_bits && n_rx == H.r_bits && (lx || !n_lx) && (rx || !n_rx), "initBulletProve: split of the point does not match");
+    rt::set_device(ctx->device);
+    const uint32_t lsize = 1u << H.l_bits, rsize = 1u << H.r_bits;
+    H.t.resize(n_lx);
+    memcpy(H.t.data(), lx, (size_t) n_lx * 32);
+    std::vector<fr_t> rxs(n_rx);
+    memcpy(rxs.data(), rx, (size_t) n_rx * 32);
+    H.L.ensure((size_t) lsize * sizeof(fr_t));
+    H.R.ensure((size_t) rsize * sizeof(fr_t));
+    beta_point_t pl[1] = {{H.t.data(), fr_t::one()}};
+    build_beta(ctx, H.L.as<fr_t>(), n_lx, pl, 1);      // L = expand(lx)
+    beta_point_t pr[1] = {{rxs.data(), fr_t::one()}};
+    build_beta(ctx, H.R.as<fr_t>(), n_rx, pr, 1);      // R = expand(rx)
+    // RZ[i] = sum_j R[j] * Z[j * lsize + i]
+    H.a.ensure((size_t) lsize * sizeof(fr_t));
+    H.a_next.ensure((size_t) lsize * sizeof(fr_t));
+    uint32_t n_chunks = std::max(1u, std::min(rsize, (uint32_t) ((ZK_SM_COUNT * 8 * kBlock) / lsize)));
+    const uint32_t per = (rsize + n_chunks - 1) / n_chunks;
+    n_chunks = (rsize + per - 1) / per;
+    ctx->dense_partial.ensure((size_t) n_chunks * lsize * sizeof(fr_t));
+    ZK_KLAUNCH(ctx, k_dense_colsum, dim3((lsize + kBlock - 1) / kBlock, n_chunks), dim3(kBlock), 0, H.Z, H.R.as<fr_t>(), lsize, H.l_bits,
+               rsize, per, ctx->dense_partial.as<fr_t>());
+    ZK_KLAUNCH(ctx, k_colsum_finish, dim3((lsize + kBlock - 1) / kBlock), dim3(kBlock), 0, ctx->dense_partial.as<fr_t>(), lsize, n_chunks,
+               H.a.as<fr_t>());
+    // bullet_g = gens  ->  coefficient vector of ones;  bullet_a = RZ;  scale = 1
+    std::vector<fr_t> ones(lsize, fr_t::one());
+    H.coef.ensure((size_t) lsize * sizeof(fr_t));
+    rt::h2d(H.coef.p, ones.data(), (size_t) lsize * sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    H.cur = lsize;
+    H.round = 0;
+    H.scale = fr_t::one();
+    ZK_API_END
+}
+
+int zk_poly_bullet_prove(zk_ctx *ctx, uint64_t *lcomm, uint64_t *rcomm, uint64_t *ly, uint64_t *ry) {   // polyProver.cpp:76-96
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && ctx->hy.bound && ctx->hy.cur >= 2 && !ctx->hy.t.empty(), "bulletProve: nothing left to prove");
+    rt::set_device(ctx->device);
+    hyrax_t &H = ctx->hy;
+    ensure_round_scratch(ctx);
+    const uint32_t lsize = 1u << H.l_bits, m = H.cur, h = m >> 1;
+    // two MSMs over the original generators (see k_bullet_scalars)
+    H.scal.ensure((size_t) 2 * lsize * sizeof(fr_t));
+    ZK_KLAUNCH(ctx, k_bullet_scalars, dim3(grid_for(lsize)), dim3(kBlock), 0, H.a.as<fr_t>(), H.coef.as<fr_t>(), lsize, m, H.scal.as<fr_t>());
+    rt::dbuf &pts = H.pts_out;
+    pts.ensure(2 * sizeof(g1_jac_t));
+    msm_run(ctx, H, H.scal.as<fr_t>(), lsize, 2, pts.as<g1_jac_t>());
+    // ly, ry
+    ZK_KLAUNCH(ctx, k_dot2, dim3(1), dim3(kBlock), 0, H.a.as<fr_t>(), H.L.as<fr_t>(), h, ctx->round_out.as<fr_t>());
+    rt::d2h(ctx->h_out, ctx->round_out.p, 2 * sizeof(fr_t), ctx->stream);
+    g1_jac_t hp[2];
+    rt::d2h(hp, pts.p, sizeof hp, ctx->stream);
+    rt::sync(ctx->stream);
+    H.scale = H.scale * (fr_t::one() - H.t.back()).inverse();
+    fr_store(ly, ctx->h_out[0] * H.scale);
+    fr_store(ry, ctx->h_out[1] * H.scale);
+    memcpy(lcomm, &hp[0], sizeof(g1_jac_t));
+    memcpy(rcomm, &hp[1], sizeof(g1_jac_t));
+    ZK_API_END
+}
+
+int zk_poly_bullet_update(zk_ctx *ctx, const uint64_t *randomness) {   // polyProver.cpp:98-109
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && ctx->hy.bound && ctx->hy.cur >= 2 && !ctx->hy.t.empty(), "bulletUpdate: nothing left to fold");
+    rt::set_device(ctx->device);
+    hyrax_t &H = ctx->hy;
+    const fr_t r = fr_load(randomness);
+    const fr_t rinv = r.inverse();
+    const uint32_t lsize = 1u << H.l_bits, h = H.cur >> 1;
+    ZK_KLAUNCH(ctx, k_bullet_fold, dim3(grid_for(h)), dim3(kBlock), 0, H.a.as<fr_t>(), H.a_next.as<fr_t>(), h, r);
+    std::swap(H.a, H.a_next);
+    // generators fold as g[i] * r^-1 + g[i + h]: the coefficient of G_j picks up r^-1 when j lies in a lower half
+    uint32_t bit = 0;
+    while ((1u << bit) < h) ++bit;   // h == 2^bit
+    ZK_KLAUNCH(ctx, k_bullet_coef, dim3(grid_for(lsize)), dim3(kBlock), 0, H.coef.as<fr_t>(), lsize, bit, rinv);
+    H.cur = h;
+    ++H.round;
+    H.t.pop_back();
+    ZK_API_END
+}
+
+int zk_poly_bullet_open(zk_ctx *ctx, uint64_t *out) {   // polyProver.cpp:111-116
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && ctx->hy.bound && ctx->hy.cur == 1 && out, "bulletOpen: folding not finished");
+    rt::set_device(ctx->device);
+    ensure_round_scratch(ctx);
+    rt::d2h(ctx->h_out, ctx->hy.a.p, sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    fr_store(out, ctx->h_out[0]);
+    ZK_API_END
+}
+
+// ---- stateless primitives ------------------------------------------------------------------------------------------------
+int zk_fr_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && a && b && out && op >= 0 && op <= 2 && n < (1ull << 31), "bad arguments");
+    rt::set_device(ctx->device);
+    rt::dbuf da, db, dc;
+    da.ensure(n * 32); db.ensure(n * 32); dc.ensure(n * 32);
+    rt::h2d(da.p, a, n * 32, ctx->stream);
+    rt::h2d(db.p, b, n * 32, ctx->stream);
+    ZK_KLAUNCH(ctx, k_fr_binop, dim3(grid_for(n)), dim3(kBlock), 0, da.as<fr_t>(), db.as<fr_t>(), dc.as<fr_t>(), (uint32_t) n, op);
+    rt::d2h(out, dc.p, n * 32, ctx->stream);
+    rt::sync(ctx->stream);
+    ZK_API_END
+}
+
+int zk_beta_table(zk_ctx *ctx, const uint64_t *r, uint32_t bits, const uint64_t *init, uint64_t *out) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && (r || !bits) && init && out && bits <= 26, "bad arguments");
+    rt::set_device(ctx->device);
+    std::vector<fr_t> rs(bits);
+    memcpy(rs.data(), r, (size_t) bits * 32);
+    rt::dbuf d;
+    d.ensure(sizeof(fr_t) << bits);
+    beta_point_t pts[1] = {{rs.data(), fr_load(init)}};
+    build_beta(ctx, d.as<fr_t>(), bits, pts, 1);
+    rt::d2h(out, d.p, sizeof(fr_t) << bits, ctx->stream);
+    rt::sync(ctx->stream);
+    ZK_API_END
+}
+
+int zk_phi_table(zk_ctx *ctx, const uint64_t *rx, const uint64_t *scale, uint32_t n, int is_ifft, uint64_t *out) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && rx && scale && out && n >= 1 && n <= 20, "bad arguments");
+    rt::set_device(ctx->device);
+    const size_t entries = is_ifft ? (size_t) 1 << n : (size_t) 1 << (n - 1);
+    rt::dbuf d;
+    d.ensure(std::max<size_t>(2, entries) * sizeof(fr_t));
+    ctx->d_r.ensure(2 * 64 * sizeof(fr_t));
+    rt::h2d(ctx->d_r.p, rx, (size_t) (is_ifft ? n - 1 : n) * 32, ctx->stream);
+    const fr_t *pw = phi_powers(ctx, n, is_ifft != 0);
+    ZK_KLAUNCH(ctx, k_phi_table, dim3(1), dim3(kBlock), 0, d.as<fr_t>(), ctx->d_r.as<fr_t>(), pw, fr_load(scale), (int) n, is_ifft);
+    rt::d2h(out, d.p, entries * sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    ZK_API_END
+}
+
+int zk_fold_rounds(zk_ctx *ctx, const uint64_t *V, const uint64_t *M, uint32_t bits, uint64_t live, const uint64_t *r, uint32_t n_rounds,
+                   uint64_t *polys) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && V && M && polys && bits >= 1 && bits <= 28 && n_rounds >= 1 && n_rounds <= bits && live <= (1ull << bits), "bad arguments");
+    rt::set_device(ctx->device);
+    pair_t &P = ctx->pair[1];
+    pair_reset(ctx->pair[0], -1, 0);
+    pair_reset(P, (int8_t) bits, (uint32_t) live);
+    fr_t *dv = table_init_buf(P.v, 1ull << bits), *dm = table_init_buf(P.m, 1ull << bits);
+    rt::h2d(dv, V, live * 32, ctx->stream);
+    rt::h2d(dm, M, live * 32, ctx->stream);
+    ctx->add_term = fr_t::zero();
+    ctx->round = 0;
+    for (uint32_t j = 0; j < n_rounds; ++j) {
+        const fr_t prev = j == 0 ? fr_t::zero() : fr_load(r + 4 * (j - 1));
+        ++ctx->round;
+        ctx->add_term = ctx->add_term * (fr_t::one() - prev);
+        fr_t abc[3];
+        round_quadratic(ctx, prev, 2u, abc);
+        abc[1] = abc[1] - ctx->add_term;
+        abc[2] = abc[2] + ctx->add_term;
+        for (int k = 0; k < 3; ++k) fr_store(polys + (size_t) (3 * j + k) * 4, abc[k]);
+    }
+    P.n_eval = 0;
+    ZK_API_END
+}
+
+int zk_msm(zk_ctx *ctx, const uint64_t *bases, const uint64_t *scalars, uint64_t n, uint32_t n_rows, uint64_t *out) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && bases && scalars && out && n >= 1 && n <= (1u << 20) && n_rows >= 1, "bad arguments");
+    rt::set_device(ctx->device);
+    hyrax_t H;   // private table: does not disturb a bound polynomial
+    msm_prepare_table(ctx, H, bases, (uint32_t) n);
+    rt::dbuf ds, dout;
+    ds.ensure(n * n_rows * 32);
+    dout.ensure((size_t) n_rows * sizeof(g1_jac_t));
+    rt::h2d(ds.p, scalars, n * n_rows * 32, ctx->stream);
+    msm_run(ctx, H, ds.as<fr_t>(), n, n_rows, dout.as<g1_jac_t>());
+    rt::d2h(out, dout.p, (size_t) n_rows * sizeof(g1_jac_t), ctx->stream);
+    rt::sync(ctx->stream);
+    ZK_API_END
+}
+
+int zk_g1_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && a && out && op >= 0 && op <= 2 && (b || op == 1) && n < (1ull << 24), "bad arguments");
+    rt::set_device(ctx->device);
+    rt::dbuf da, db, dc;
+    da.ensure(n * sizeof(g1_jac_t));
+    dc.ensure(n * sizeof(g1_jac_t));
+    rt::h2d(da.p, a, n * sizeof(g1_jac_t), ctx->stream);
+    const size_t bsz = op == 0 ? sizeof(g1_jac_t) : sizeof(fr_t);
+    if (op != 1) { db.ensure(n * bsz); rt::h2d(db.p, b, n * bsz, ctx->stream); }
+    ZK_KLAUNCH(ctx, k_g1_vec_op, dim3((uint32_t) ((n + 63) / 64)), dim3(64), 0, da.as<g1_jac_t>(), op == 0 ? db.as<g1_jac_t>() : nullptr,
+               op == 2 ? db.as<fr_t>() : nullptr, dc.as<g1_jac_t>(), (uint32_t) n, op);
+    rt::d2h(out, dc.p, n * sizeof(g1_jac_t), ctx->stream);
+    rt::sync(ctx->stream);
+    ZK_API_END
+}
+
+int zk_selftest(zk_ctx *ctx, uint64_t seed, uint32_t n) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && n >= 1, "bad arguments");
+    rt::set_device(ctx->device);
+    rt::dbuf d;
+    d.ensure(4);
+    rt::dzero(d.p, 4, ctx->stream);
+    ZK_KLAUNCH(ctx, k_selftest, dim3(grid_for(n)), dim3(kBlock), 0, seed, n, d.as<uint32_t>());
+    uint32_t bad = 0;
+    rt::d2h(&bad, d.p, 4, ctx->stream);
+    rt::sync(ctx->stream);
+    ZK_REQUIRE(bad == 0, "device self-test: inline-PTX field arithmetic disagrees with the portable implementation");
+    ZK_API_END
+}
+
+}  // extern "C"

@@ -68,7 +68,7 @@ struct hyrax_t {
     uint32_t cur = 0;          // current length of bullet_a
     uint32_t round = 0;
     std::vector<fr_t> rinv;    // 1 / randomness of the finished rounds
-    rt::dbuf msm_digits, msm_out, msm_rowinfo;
+    rt::dbuf msm_out, msm_rowinfo, pts_out;
 };
 
 }  // namespace zk

@@ -35,8 +35,8 @@ polyProver::polyProver(const vector<Fr> &_Z, const vector<G1> &_gens)
     check(zk_poly_create(ctx_, w(_Z[0]), _Z.size(), gens.empty() ? nullptr : w(gens[0]), (uint32_t) gens.size()), "zk_poly_create");
 }
 
-polyProver::polyProver(zk_ctx *ctx, const vector<G1> &_gens, zkcnn_b200::Transcript *tr)
-    : ctx_(ctx), own_ctx_(false), gens(_gens), bit_length(0), ps(0), tr_(tr) {
+polyProver::polyProver(zk_ctx *ctx, const vector<G1> &_gens, unsigned char bl, zkcnn_b200::Transcript *tr)
+    : ctx_(ctx), own_ctx_(false), gens(_gens), bit_length(bl), ps(0), tr_(tr) {
     check(zk_poly_bind_input(ctx_, gens.empty() ? nullptr : w(gens[0]), (uint32_t) gens.size()), "zk_poly_bind_input");
 }
 
@@ -46,13 +46,56 @@ polyProver::~polyProver() {
 
 vector<G1> polyProver::commit() {   // polyProver.cpp:19-34
     pt.start();
-    vector<G1> comm_Z(gens.size() ? (size_t) 0 : 0);
-    // rsize = 2^(bl/2) rows; the library knows bl, we only need the count: lsize == gens.size(), rsize = n / lsize
-    uint32_t n_out = 0;
-    check(zk_poly_commit(ctx_, nullptr, 0) == 0 ? 0 : 0, "zk_poly_commit");
-    (void) n_out;
+    unsigned char r_bit_length = bit_length >> 1;
+    unsigned long long rsize = 1ULL << r_bit_length;
+    vector<G1> comm_Z(rsize);
+    check(zk_poly_commit(ctx_, w(comm_Z[0]), (uint32_t) rsize), "zk_poly_commit");
     pt.stop();
+    ps += ZK_G1_BYTES * comm_Z.size();
+    if (tr_) for (auto &p : comm_Z) tr_->put_g1(w(p));
     return comm_Z;
 }
+
+Fr polyProver::evaluate(const vector<Fr> &x) {   // polyProver.cpp:36-42
+    Fr res;
+    check(zk_poly_evaluate(ctx_, x.empty() ? nullptr : w(x[0]), (uint32_t) x.size(), w(res)), "zk_poly_evaluate");
+    return res;
+}
+
+double polyProver::getPT() const { return pt.elapse_sec(); }
+
+double polyProver::getPS() const { return ps / 1024.0; }   // KB
+
+void polyProver::initBulletProve(const vector<Fr> &_lx, const vector<Fr> &_rx) {   // polyProver.cpp:52-74
+    pt.start();
+    check(zk_poly_init_bullet_prove(ctx_, _lx.empty() ? nullptr : w(_lx[0]), (uint32_t) _lx.size(), _rx.empty() ? nullptr : w(_rx[0]),
+                                    (uint32_t) _rx.size()),
+          "zk_poly_init_bullet_prove");
+    pt.stop();
+}
+
+void polyProver::bulletProve(G1 &lcomm, G1 &rcomm, Fr &ly, Fr &ry) {   // polyProver.cpp:76-96
+    pt.start();
+    check(zk_poly_bullet_prove(ctx_, w(lcomm), w(rcomm), w(ly), w(ry)), "zk_poly_bullet_prove");
+    pt.stop();
+    ps += (ZK_G1_BYTES + ZK_FR_BYTES) * 2;
+    if (tr_) { tr_->put_g1(w(lcomm)); tr_->put_g1(w(rcomm)); tr_->put_fr(w(ly)); tr_->put_fr(w(ry)); }
+}
+
+void polyProver::bulletUpdate(const Fr &randomness) {   // polyProver.cpp:98-109
+    pt.start();
+    check(zk_poly_bullet_update(ctx_, w(randomness)), "zk_poly_bullet_update");
+    pt.stop();
+}
+
+Fr polyProver::bulletOpen() {   // polyProver.cpp:111-116
+    Fr y;
+    check(zk_poly_bullet_open(ctx_, w(y)), "zk_poly_bullet_open");
+    ps += ZK_FR_BYTES;
+    if (tr_) tr_->put_fr(w(y));
+    return y;
+}
+
+const vector<G1> &polyProver::getGens() const { return gens; }
 
 }  // namespace hyrax_bls12_381

@@ -12,6 +12,9 @@
 #define ZKCNN_PROVER_HPP
 
 #ifdef ZKCNN_DROPIN
+#ifndef ZKCNN_DROPIN_CPU_HYRAX
+#include "polyProver.hpp"   // ours first: its include guard keeps the reference's hyrax/src/polyProver.hpp out
+#endif
 #include "global_var.hpp"   // reference: src/
 #include "circuit.h"
 #include "polynomial.h"
