@@ -1,0 +1,168 @@
+// Circuit compiler + witness generator of the stand-alone build: turns a CNN description into the layered arithmetic
+// circuit (prover::C) and its per-layer values (prover::val) that the GKR prover consumes.
+//
+// This is the caller-side data format of the hot path, written from scratch but producing,
+// gate for gate and value for value, what the reference's neuralNetwork::create does (src/neuralNetwork.cpp:60-142 and
+// the layer builders :144-649) -- tests/test_circuit_builder.py checks per-layer hashes of gates, ori_id and values
+// against the compiled reference.  Public interface = the reference's (src/neuralNetwork.hpp:57-66, src/models.hpp).
+#pragma once
+#include "prover.hpp"
+#include <functional>
+
+enum convType { FFT, NAIVE, NAIVE_FAST };
+enum poolType { AVG, MAX, NONE };
+enum actType { RELU_ACT };
+
+struct convKernel {
+    convType ty;
+    i64 channel_out, channel_in, size, stride_bl, padding, weight_start_id, bias_start_id;
+    convKernel(convType _ty, i64 _channel_out, i64 _channel_in, i64 _size, i64 _log_stride, i64 _padding)
+        : ty(_ty), channel_out(_channel_out), channel_in(_channel_in), size(_size), stride_bl(_log_stride), padding(_padding),
+          weight_start_id(0), bias_start_id(0) {}
+    convKernel(convType _ty, i64 _channel_out, i64 _channel_in, i64 _size)
+        : convKernel(_ty, _channel_out, _channel_in, _size, 0, _size >> 1) {}
+};
+struct fconKernel {
+    i64 channel_out, channel_in, weight_start_id, bias_start_id;
+    fconKernel(i64 _channel_out, i64 _channel_in) : channel_out(_channel_out), channel_in(_channel_in), weight_start_id(0), bias_start_id(0) {}
+};
+struct poolKernel {
+    poolType ty;
+    i64 size, stride_bl, dcmp_start_id, max_start_id, max_dcmp_start_id;
+    poolKernel(poolType _ty, i64 _size, i64 _log_stride) : ty(_ty), size(_size), stride_bl(_log_stride), dcmp_start_id(0), max_start_id(0), max_dcmp_start_id(0) {}
+};
+
+// where the image and the weights come from: a whitespace-separated decimal file (the reference's format,
+// src/neuralNetwork.cpp:805-897) or an in-memory array (synthetic benchmarks)
+class NumberSource {
+public:
+    virtual ~NumberSource() {}
+    virtual double next() = 0;
+};
+
+class neuralNetwork {
+public:
+    explicit neuralNetwork(i64 psize_x, i64 psize_y, i64 pchannel, i64 pparallel, const string &i_filename, const string &c_filename,
+                           const string &o_filename);
+    virtual ~neuralNetwork() {}
+
+    void create(prover &pr, bool only_compute);
+
+    // ---- additions of the B200 build ----------------------------------------------------------------------------------
+    void setInput(std::unique_ptr<NumberSource> src) { in = std::move(src); }
+    // number of decimals create() will consume (image + all weights and biases)
+    i64 inputCount();
+    int hostThreads = 0;          // witness evaluation threads (0 = hardware concurrency)
+    vector<int> inferred;         // argmax per picture (what the reference writes to o_file)
+
+protected:
+    void initParam();
+    int getNextBit(int layer_id);
+    void refreshConvParam(i64 new_nx, i64 new_ny, const convKernel &conv);
+    void calcSizeAfterPool(const poolKernel &p);
+    void refreshFCParam(const fconKernel &fc);
+    i64 getFFTLen() const;
+    i8 getFFTBitLen() const;
+    i64 getPoolDecmpSize() const;
+
+    void prepareDecmpBit(i64 layer_id, i64 idx, i64 dcmp_id, i64 bit_shift);
+    void prepareFieldBit(const F &data, i64 dcmp_id, i64 bit_shift);
+    void prepareSignBit(i64 layer_id, i64 idx, i64 dcmp_id);
+    void prepareMax(i64 layer_id, i64 idx, i64 max_id);
+
+    void calcInputLayer(layer &circuit);
+    void calcNormalLayer(const layer &circuit, i64 layer_id);
+    void calcDotProdLayer(const layer &circuit, i64 layer_id);
+    void calcFFTLayer(const layer &circuit, i64 layer_id);
+
+    void inputLayer(layer &circuit);
+    void paddingLayer(layer &circuit, i64 &layer_id, i64 first_conv_id);
+    void fftLayer(layer &circuit, i64 &layer_id);
+    void dotProdLayer(layer &circuit, i64 &layer_id);
+    void ifftLayer(layer &circuit, i64 &layer_id);
+    void addBiasLayer(layer &circuit, i64 &layer_id, i64 first_bias_id);
+    void naiveConvLayerFast(layer &circuit, i64 &layer_id, i64 first_conv_id, i64 first_bias_id);
+    void naiveConvLayerMul(layer &circuit, i64 &layer_id, i64 first_conv_id);
+    void naiveConvLayerAdd(layer &circuit, i64 &layer_id, i64 first_bias_id);
+    void reluActConvLayer(layer &circuit, i64 &layer_id);
+    void reluActFconLayer(layer &circuit, i64 &layer_id);
+    void avgPoolingLayer(layer &circuit, i64 &layer_id);
+    void maxPoolingLayer(layeredCircuit &C, i64 &layer_id, i64 first_dcmp_id, i64 first_max_id, i64 first_max_dcmp_id);
+    void fullyConnLayer(layer &circuit, i64 &layer_id, i64 first_fc_id, i64 first_bias_id);
+
+    void readBias(i64 first_bias_id);
+    void readConvWeight(i64 first_conv_id);
+    void readFconWeight(i64 first_fc_id);
+    void printInfer(prover &pr);
+
+    vector<vector<convKernel>> conv_section;
+    vector<poolKernel> pool;
+    poolType pool_ty;
+    i64 pool_bl, pool_sz;
+    i64 pool_stride_bl, pool_stride;
+    i64 pool_layer_cnt, act_layer_cnt, conv_layer_cnt;
+    actType act_ty;
+    vector<fconKernel> full_conn;
+
+    i64 pic_size_x, pic_size_y, pic_channel, pic_parallel;
+    i64 SIZE;
+    const i64 NCONV_FAST_SIZE, NCONV_SIZE, FFT_SIZE, AVE_POOL_SIZE, FC_SIZE, RELU_SIZE;
+    i64 T;
+    const i64 Q = 9;
+    i64 Q_MAX;
+    const i64 Q_BIT_SIZE = 220;
+
+    i64 nx_in, nx_out, ny_in, ny_out, m, channel_in, channel_out, log_stride, padding;
+    i64 new_nx_in, new_ny_in;
+    i64 nx_padded_in, ny_padded_in;
+    i64 total_in_size, total_para_size, total_relu_in_size, total_ave_in_size, total_max_in_size;
+    int x_bit, w_bit, x_next_bit;
+
+    vector<vector<F>>::iterator val;
+    vector<F>::iterator two_mul;
+
+    std::unique_ptr<NumberSource> in;
+    string o_file;
+};
+
+// ---- model zoo (src/models.hpp) -------------------------------------------------------------------------------------------
+class vgg : public neuralNetwork {
+public:
+    // network description: integers = conv output channels, 'M' / 'A' = max / average pooling (src/models.cpp:18-35)
+    explicit vgg(i64 psize_x, i64 psize_y, i64 pchannel, i64 pparallel, const std::string &i_filename, const string &c_filename,
+                 const std::string &o_filename, const std::string &n_filename);
+    static std::unique_ptr<vgg> fromDescription(i64 psize, i64 pchannel, i64 pparallel, const std::string &description);
+private:
+    void configure(std::istream &config_in);
+};
+class vgg16 : public neuralNetwork {
+public:
+    explicit vgg16(i64 psize_x, i64 psize_y, i64 pchannel, i64 pparallel, poolType pool_ty, const std::string &i_filename,
+                   const string &c_filename, const std::string &o_filename);
+};
+class vgg11 : public neuralNetwork {
+public:
+    explicit vgg11(i64 psize_x, i64 psize_y, i64 pchannel, i64 pparallel, poolType pool_ty, const std::string &i_filename,
+                   const string &c_filename, const std::string &o_filename);
+};
+class lenet : public neuralNetwork {
+public:
+    explicit lenet(i64 psize_x, i64 psize_y, i64 pchannel, i64 pparallel, poolType pool_ty, const std::string &i_filename,
+                   const string &c_filename, const std::string &o_filename);
+};
+class lenetCifar : public neuralNetwork {
+public:
+    explicit lenetCifar(i64 psize_x, i64 psize_y, i64 pchannel, i64 pparallel, poolType pool_ty, const std::string &i_filename,
+                        const string &c_filename, const std::string &o_filename);
+};
+class ccnn : public neuralNetwork {
+public:
+    explicit ccnn(i64 psize_x, i64 psize_y, i64 pparallel, i64 pchannel, poolType pool_ty);
+};
+
+// host-side helpers shared with the verifier (src/utils.hpp)
+long matIdx(long x, long y, long n);
+long cubIdx(long x, long y, long z, long n, long m);
+long tesIdx(long w, long x, long y, long z, long n, long m, long l);
+F getRootOfUnit(int n);
+void fft(vector<F> &arr, int logn, bool flag);
