@@ -45,6 +45,10 @@ void zk_ctx_destroy(zk_ctx *ctx);
 /* number of kernels launched through this ctx so far (bench.py's gpu_launches) */
 uint64_t zk_ctx_launch_count(const zk_ctx *ctx);
 
+/* page-lock / unlock a caller-owned host buffer so that uploads from it are direct DMA (cudaHostRegister) */
+int zk_host_pin(const void *p, size_t bytes);
+int zk_host_unpin(const void *p);
+
 /* ---- circuit + witness upload: replaces neuralNetwork's friend access to prover::C / prover::val ------------------
  * (src/prover.hpp:48-49,76-77; src/neuralNetwork.cpp:64-68).  Gate structs are bit-identical to src/circuit.h:15-33. */
 typedef struct { uint32_t g, u; uint8_t lu, sc; } zk_uni_gate;        /* 12 bytes, == uniGate */

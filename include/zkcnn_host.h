@@ -1,0 +1,62 @@
+/*
+ * zkcnn_host -- C entry points of the stand-alone host side (circuit compiler, witness generator, protocol driver)
+ * for callers that cannot use the C++ classes directly (bench.py, the pytest suite, FFI users).
+ *
+ * This is NOT the drop-in boundary (that is include/zkcnn_b200.h, underneath class prover / polyProver); it wraps the
+ * caller side of the hot path -- what the reference's demo mains do (src/main_demo_lenet.cpp:19-40,
+ * src/main_demo_vgg.cpp:20-42): build a model, neuralNetwork::create, verifier::verify -- behind plain C.
+ * All proving arithmetic still goes through include/zkcnn_b200.h to the GPU; there is no CPU prover here.
+ */
+#ifndef ZKCNN_HOST_H
+#define ZKCNN_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkh_session zkh_session;
+
+enum {
+    ZKH_REAL_GENERATORS  = 1,  /* Hyrax generators = standard G1 generator * challenge (default: the reference's all-infinity set) */
+    ZKH_CHECK_PREDICATES = 2,  /* run the verifier-side wiring predicates and G1 checks too (full verification) */
+    ZKH_WITNESS_RESIDENT = 4,  /* keep the witness on the device between proofs (skip the host->device copy if present) */
+    ZKH_FIXED_GENERATORS = 8   /* reuse the generators of the previous proof (public parameters), keep the window table */
+};
+
+typedef struct {
+    int32_t ok;                 /* verifier accepted */
+    uint32_t n_layers;
+    uint64_t input_size;        /* gates in layer 0 (witness size) */
+    uint64_t n_fr, n_g1;        /* field elements / points in the proof */
+    uint64_t proof_bytes;       /* canonical encoding (SURVEY.md App. A order; Fr 32 B LE, G1 96 B affine) */
+    uint64_t fnv1a;             /* FNV-1a 64 of those bytes */
+    uint64_t challenges;        /* verifier challenges drawn */
+    uint64_t gpu_launches;      /* kernels launched for this proof */
+    double prove_s;             /* prover::proveTime()  (GKR part) */
+    double poly_s;              /* prover::polyProverTime()  (Hyrax part) */
+    double upload_s;            /* witness (and, first time, circuit) upload */
+    double wall_s;              /* prover.init() + verifier.verify(), wall clock */
+    double verifier_s;          /* verifier-only work inside wall_s (predicates, point checks) */
+    double gkr_kb, poly_kb;     /* proof size as the reference counts it */
+    uint64_t h2d_bytes;         /* witness bytes copied host->device for this proof */
+} zkh_stats;
+
+const char *zkh_last_error(void);
+/* model: "lenet" (32x32x1, max pooling), "lenet_cifar", "vgg11", "vgg16" (32x32x3, max pooling) or "vgg" with
+ * `network` = channel/pool description, e.g. "64 M 128 M 256 256 M 512 512 M 512 512 M" (src/models.cpp:12-41). */
+zkh_session *zkh_create(const char *model, const char *network, int pic_cnt, int device);
+void zkh_destroy(zkh_session *s);
+int64_t zkh_input_count(zkh_session *s);                                 /* decimals build() consumes */
+int zkh_input_file(zkh_session *s, const char *path);                    /* the reference's text format */
+int zkh_input_values(zkh_session *s, const double *values, uint64_t n);  /* same numbers, in memory */
+int zkh_build(zkh_session *s);                                           /* circuit + witness (neuralNetwork::create) */
+int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out);
+const uint8_t *zkh_proof(zkh_session *s, uint64_t *n_bytes);             /* proof of the last zkh_prove */
+int zkh_inferred_class(zkh_session *s, int picture);
+/* per-layer shape/hash dump in the format of oracle/harness/ref_run --circuit-hash (parity tests) */
+int zkh_circuit_dump(zkh_session *s, const char *path, int with_hashes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -44,6 +44,20 @@ void zk_ctx_destroy(zk_ctx *ctx) {
 
 uint64_t zk_ctx_launch_count(const zk_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int zk_host_pin(const void *p, size_t bytes) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(p && bytes, "bad arguments");
+    rt::host_pin(const_cast<void *>(p), bytes);
+    ZK_API_END
+}
+
+int zk_host_unpin(const void *p) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(p, "bad arguments");
+    rt::host_unpin(const_cast<void *>(p));
+    ZK_API_END
+}
+
 // ---- circuit ----------------------------------------------------------------------------------------------------------
 int zk_circuit_begin(zk_ctx *ctx, uint32_t n_layers, const uint64_t *two_mul, uint32_t n_two_mul) {
     ZK_API_BEGIN

@@ -24,6 +24,8 @@ inline void *dmalloc(size_t bytes) {
 inline void dfree(void *p) { free(p); }
 inline void *hmalloc_pinned(size_t bytes) { return malloc(bytes ? bytes : 1); }
 inline void hfree_pinned(void *p) { free(p); }
+inline void host_pin(void *, size_t) {}
+inline void host_unpin(void *) {}
 inline void h2d(void *dst, const void *src, size_t n, zk_stream_t) { memcpy(dst, src, n); }
 inline void d2h(void *dst, const void *src, size_t n, zk_stream_t) { memcpy(dst, src, n); }
 inline void d2d(void *dst, const void *src, size_t n, zk_stream_t) { memmove(dst, src, n); }
@@ -54,6 +56,8 @@ inline void *hmalloc_pinned(size_t bytes) {
     return p;
 }
 inline void hfree_pinned(void *p) { if (p) cudaFreeHost(p); }
+inline void host_pin(void *p, size_t bytes) { check(cudaHostRegister(p, bytes, cudaHostRegisterDefault), "cudaHostRegister"); }
+inline void host_unpin(void *p) { check(cudaHostUnregister(p), "cudaHostUnregister"); }
 inline void h2d(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s), "h2d"); }
 inline void d2h(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s), "d2h"); }
 inline void d2d(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "d2d"); }

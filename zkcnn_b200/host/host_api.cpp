@@ -1,0 +1,236 @@
+// C entry points of the stand-alone host side (include/zkcnn_host.h): model construction, circuit + witness build,
+// one interactive proof per call.  The flow of zkh_build + zkh_prove is the reference's demo main
+// (src/main_demo_vgg.cpp:20-42): construct the model, neuralNetwork::create(prover), verifier(&prover).verify().
+#include "../../include/zkcnn_host.h"
+#include "challenge_stream.hpp"
+#include "neuralNetwork.hpp"
+#include "verifier.hpp"
+#include <chrono>
+
+namespace {
+
+thread_local std::string g_err;
+
+class ArrayNumbers : public NumberSource {
+public:
+    ArrayNumbers(const double *v, uint64_t n) : v_(v, v + n), i_(0) {}
+    double next() override { return i_ < v_.size() ? v_[i_++] : 0.0; }
+private:
+    vector<double> v_;
+    size_t i_;
+};
+
+// whitespace-separated decimals, parsed with strtod in large blocks (the reference uses `ifstream >> double`)
+class FastFileNumbers : public NumberSource {
+public:
+    explicit FastFileNumbers(const std::string &path) : f_(fopen(path.c_str(), "rb")) {
+        if (!f_) throw std::runtime_error("cannot open input file " + path);
+        buf_.resize(1 << 22);
+    }
+    ~FastFileNumbers() override { if (f_) fclose(f_); }
+    double next() override {
+        for (;;) {
+            while (pos_ < len_ && isspace((unsigned char) buf_[pos_])) ++pos_;
+            // a token must end inside the buffer (or at EOF) before it is parsed
+            size_t e = pos_;
+            while (e < len_ && !isspace((unsigned char) buf_[e])) ++e;
+            if (pos_ < len_ && (e < len_ || eof_)) {
+                char save = buf_[e];
+                buf_[e] = 0;
+                double x = strtod(&buf_[pos_], nullptr);
+                buf_[e] = save;
+                pos_ = e;
+                return x;
+            }
+            if (eof_) return 0.0;
+            refill();
+        }
+    }
+private:
+    void refill() {
+        size_t keep = len_ - pos_;
+        memmove(&buf_[0], &buf_[pos_], keep);
+        size_t got = fread(&buf_[keep], 1, buf_.size() - 1 - keep, f_);
+        if (got == 0) eof_ = true;
+        pos_ = 0;
+        len_ = keep + got;
+    }
+    FILE *f_;
+    std::string buf_;
+    size_t pos_ = 0, len_ = 0;
+    bool eof_ = false;
+};
+
+uint64_t fnv(const void *p, size_t n, uint64_t h = 0xcbf29ce484222325ULL) {
+    auto *b = static_cast<const uint8_t *>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    return h;
+}
+
+}  // namespace
+
+struct zkh_session {
+    std::unique_ptr<neuralNetwork> nn;
+    prover p;
+    zkcnn_b200::Transcript tr;
+    vector<G> last_gens;
+    bool built = false;
+    int device = 0;
+};
+
+#define ZKH_BEGIN try {
+#define ZKH_END                          \
+    return 0;                            \
+    } catch (const std::exception &e) {  \
+        g_err = e.what();                \
+        return -1;                       \
+    }
+
+extern "C" {
+
+const char *zkh_last_error(void) { return g_err.c_str(); }
+
+zkh_session *zkh_create(const char *model, const char *network, int pic_cnt, int device) {
+    try {
+        if (!model || pic_cnt < 1) throw std::invalid_argument("zkh_create: bad arguments");
+        std::unique_ptr<zkh_session> s(new zkh_session);
+        const std::string m = model;
+        if (m == "lenet") s->nn.reset(new lenet(32, 32, 1, pic_cnt, MAX, "", "", ""));
+        else if (m == "lenet_cifar") s->nn.reset(new lenetCifar(32, 32, 3, pic_cnt, MAX, "", "", ""));
+        else if (m == "vgg11") s->nn.reset(new vgg11(32, 32, 3, pic_cnt, MAX, "", "", ""));
+        else if (m == "vgg16") s->nn.reset(new vgg16(32, 32, 3, pic_cnt, MAX, "", "", ""));
+        else if (m == "vgg") {
+            if (!network || !*network) throw std::invalid_argument("zkh_create: model \"vgg\" needs a network description");
+            s->nn = vgg::fromDescription(32, 3, pic_cnt, network);
+        } else throw std::invalid_argument("zkh_create: unknown model " + m);
+        s->device = device;
+        s->p.setDevice(device);
+        s->p.setTranscript(&s->tr);
+        return s.release();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+void zkh_destroy(zkh_session *s) { delete s; }
+
+int64_t zkh_input_count(zkh_session *s) {
+    try {
+        if (!s) throw std::invalid_argument("null session");
+        return s->nn->inputCount();
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+int zkh_input_file(zkh_session *s, const char *path) {
+    ZKH_BEGIN
+    if (!s || !path) throw std::invalid_argument("bad arguments");
+    s->nn->setInput(std::unique_ptr<NumberSource>(new FastFileNumbers(path)));
+    ZKH_END
+}
+
+int zkh_input_values(zkh_session *s, const double *values, uint64_t n) {
+    ZKH_BEGIN
+    if (!s || !values) throw std::invalid_argument("bad arguments");
+    if ((int64_t) n < s->nn->inputCount()) throw std::invalid_argument("zkh_input_values: too few values for this model");
+    s->nn->setInput(std::unique_ptr<NumberSource>(new ArrayNumbers(values, n)));
+    ZKH_END
+}
+
+int zkh_build(zkh_session *s) {
+    ZKH_BEGIN
+    if (!s) throw std::invalid_argument("null session");
+    s->p.unpinWitness();
+    s->nn->create(s->p, false);
+    s->p.invalidateCircuit();
+    s->p.pinWitness();
+    s->built = true;
+    ZKH_END
+}
+
+int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
+    ZKH_BEGIN
+    if (!s || !s->built) throw std::logic_error("zkh_prove: call zkh_build first");
+    zkcnn_b200::ScopedChallengeStream rng(seed);
+    s->tr.clear();
+    prover &p = s->p;
+    p.setWitnessResident((flags & ZKH_WITNESS_RESIDENT) != 0);
+    const double up0 = p.uploadTime(), pt0 = p.proveTime();
+    const uint64_t l0 = p.gpuLaunches();
+    auto t0 = std::chrono::steady_clock::now();
+    verifier v(&p, p.C);
+    v.checkPredicates = (flags & ZKH_CHECK_PREDICATES) != 0;
+    v.realGenerators = (flags & ZKH_REAL_GENERATORS) != 0;
+    if ((flags & ZKH_FIXED_GENERATORS) && !s->last_gens.empty()) v.fixedGenerators = &s->last_gens;
+    const bool ok = v.verify();
+    auto t1 = std::chrono::steady_clock::now();
+    s->last_gens = v.generators;
+    if (out) {
+        memset(out, 0, sizeof *out);
+        out->ok = ok;
+        out->n_layers = p.C.size;
+        out->input_size = p.C.circuit[0].size;
+        out->n_fr = s->tr.n_fr;
+        out->n_g1 = s->tr.n_g1;
+        out->proof_bytes = s->tr.bytes.size();
+        out->fnv1a = s->tr.fnv1a();
+        out->challenges = rng.stream.calls;
+        out->gpu_launches = p.gpuLaunches() - l0;
+        out->prove_s = p.proveTime() - pt0;
+        out->poly_s = p.polyProverTime();
+        out->upload_s = p.uploadTime() - up0;
+        out->wall_s = std::chrono::duration<double>(t1 - t0).count();
+        out->verifier_s = v.verifierTime() + v.verifierSlowTime() + v.polyVT;
+        out->gkr_kb = p.proofSize();
+        out->poly_kb = p.polyProofSize();
+        out->h2d_bytes = p.lastUploadBytes();
+    }
+    ZKH_END
+}
+
+const uint8_t *zkh_proof(zkh_session *s, uint64_t *n_bytes) {
+    if (!s) return nullptr;
+    if (n_bytes) *n_bytes = s->tr.bytes.size();
+    return s->tr.bytes.data();
+}
+
+int zkh_inferred_class(zkh_session *s, int picture) {
+    if (!s || picture < 0 || (size_t) picture >= s->nn->inferred.size()) return -1;
+    return s->nn->inferred[picture];
+}
+
+int zkh_circuit_dump(zkh_session *s, const char *path, int with_hashes) {
+    ZKH_BEGIN
+    if (!s || !s->built || !path) throw std::invalid_argument("bad arguments");
+    static const char *names[] = {"INPUT", "FFT", "IFFT", "ADD_BIAS", "RELU", "Sqr", "OPT_AVG_POOL", "MAX_POOL", "AVG_POOL",
+                                  "DOT_PROD", "PADDING", "FCONN", "NCONV", "NCONV_MUL", "NCONV_ADD"};
+    FILE *f = fopen(path, "w");
+    if (!f) throw std::runtime_error(std::string("cannot write ") + path);
+    const layeredCircuit &C = s->p.C;
+    for (int i = 0; i < C.size; ++i) {
+        const layer &c = C.circuit[i];
+        fprintf(f, "L %d %s size %u bl %d u0 %u %d u1 %u %d v0 %u %d v1 %u %d mbu %d mbv %d ph2 %d fftbl %d zsi %u uni %zu bin %zu", i,
+                names[(int) c.ty], c.size, (int) c.bit_length, c.size_u[0], (int) c.bit_length_u[0], c.size_u[1], (int) c.bit_length_u[1],
+                c.size_v[0], (int) c.bit_length_v[0], c.size_v[1], (int) c.bit_length_v[1], (int) c.max_bl_u, (int) c.max_bl_v,
+                (int) c.need_phase2, (int) c.fft_bit_length, c.zero_start_id, c.uni_gates.size(), c.bin_gates.size());
+        if (with_hashes) {
+            uint64_t hu = 0xcbf29ce484222325ULL, hb = hu, hv = hu;
+            for (auto &g : c.uni_gates) { u32 t[4] = {g.g, g.u, g.lu, g.sc}; hu = fnv(t, sizeof t, hu); }
+            for (auto &g : c.bin_gates) { u32 t[5] = {g.g, g.u, g.v, g.sc, g.l}; hb = fnv(t, sizeof t, hb); }
+            uint64_t hou = fnv(c.ori_id_u.data(), c.ori_id_u.size() * 4), hov = fnv(c.ori_id_v.data(), c.ori_id_v.size() * 4);
+            for (auto &x : s->p.val[i]) { uint8_t b[32]; x.serialize(b, 32); hv = fnv(b, 32, hv); }
+            uint8_t sb[32];
+            c.scale.serialize(sb, 32);
+            fprintf(f, " h_uni %016lx h_bin %016lx h_oriu %016lx h_oriv %016lx h_val %016lx nval %zu h_scale %016lx", hu, hb, hou, hov, hv,
+                    s->p.val[i].size(), fnv(sb, 32));
+        }
+        fprintf(f, "\n");
+    }
+    fclose(f);
+    ZKH_END
+}
+
+}  // extern "C"

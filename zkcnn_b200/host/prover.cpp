@@ -16,6 +16,7 @@ static inline uint64_t *w(F &x) { return reinterpret_cast<uint64_t *>(&x); }
 prover::prover() {}
 
 prover::~prover() {
+    unpinWitness();
     poly_p.reset();
     if (ctx_) zk_ctx_destroy(ctx_);
 }
@@ -56,8 +57,23 @@ void prover::uploadCircuit() {
 }
 
 void prover::uploadWitness() {
-    for (u32 i = 0; i < C.size; ++i)
+    last_upload_bytes_ = 0;
+    for (u32 i = 0; i < C.size; ++i) {
         check(zk_witness_layer(ctx_, i, val[i].empty() ? nullptr : w(val[i][0]), val[i].size()), "zk_witness_layer");
+        last_upload_bytes_ += val[i].size() * sizeof(F);
+    }
+    witness_uploaded_ = true;
+}
+
+void prover::pinWitness() {
+    unpinWitness();
+    for (auto &v : val)
+        if (!v.empty() && zk_host_pin(v.data(), v.size() * sizeof(F)) == 0) pinned_.push_back(v.data());
+}
+
+void prover::unpinWitness() {
+    for (const void *p : pinned_) zk_host_unpin(p);
+    pinned_.clear();
 }
 
 void prover::init() {   // src/prover.cpp:17-21 (+ upload of what the reference reads in place)
@@ -69,8 +85,9 @@ void prover::init() {   // src/prover.cpp:17-21 (+ upload of what the reference 
         ctx_ = zk_ctx_create(dev);
         if (!ctx_) throw std::runtime_error(std::string("zkcnn_b200: cannot create a device context: ") + zk_last_error());
     }
-    if (!circuit_uploaded_) uploadCircuit();
-    uploadWitness();
+    if (!circuit_uploaded_) { uploadCircuit(); witness_uploaded_ = false; }
+    if (!(witness_resident_ && witness_uploaded_)) uploadWitness();
+    else last_upload_bytes_ = 0;
     check(zk_prover_init(ctx_), "zk_prover_init");
     upload_timer.stop();
 }

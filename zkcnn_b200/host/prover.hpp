@@ -79,6 +79,12 @@ public:
     void invalidateCircuit() { circuit_uploaded_ = false; }
     // seconds spent uploading circuit / witness in init() (outside the prove timer, like the reference's allocations)
     double uploadTime() const { return upload_timer.elapse_sec(); }
+    // true: init() keeps the witness that is already on the device (same val as the previous proof) instead of copying it again
+    void setWitnessResident(bool on) { witness_resident_ = on; }
+    // page-lock val[] so that the witness upload is a direct DMA from host memory (call after val is final; undone by the destructor)
+    void pinWitness();
+    void unpinWitness();
+    uint64_t lastUploadBytes() const { return last_upload_bytes_; }
     uint64_t gpuLaunches() const { return ctx_ ? zk_ctx_launch_count(ctx_) : 0; }
     zk_ctx *context() { return ctx_; }
     timer upload_timer;
@@ -91,6 +97,9 @@ private:
     zk_ctx *ctx_ = nullptr;
     int device_ = -1;
     bool circuit_uploaded_ = false;
+    bool witness_resident_ = false, witness_uploaded_ = false;
+    uint64_t last_upload_bytes_ = 0;
+    std::vector<const void *> pinned_;
     u64 proof_size = 0;
     zkcnn_b200::Transcript *transcript_ = nullptr;
     unique_ptr<hyrax_bls12_381::polyProver> poly_p;

@@ -77,3 +77,4 @@ private:
 void initBetaTable(vector<F> &beta_g, u8 gLength, const F *r_0, const F *r_1, const F &alpha, const F &beta);
 void initBetaTable(vector<F> &beta_g, u8 gLength, const F *r, const F &init);
 void phiGInit(vector<F> &phi_g, const F *rx, const F &scale, int n, bool isIFFT);
+F getRootOfUnit(int n);   // neuralNetwork.cpp
