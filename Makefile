@@ -18,12 +18,12 @@ all: lib host
 lib: $(LIBDIR)/libzkcnn_b200.so
 $(LIBDIR)/libzkcnn_b200.so: $(CSRC_DEPS)
 	mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -Xcompiler -Wno-unknown-pragmas -shared -cudart static -Xlinker -soname=libzkcnn_b200.so $(CSRC)/capi.cu -o $@
+	$(NVCC) $(NVFLAGS) -Xcompiler -Wno-unknown-pragmas -shared -cudart static -Xlinker -soname=libzkcnn_b200.so -Xlinker -Bsymbolic $(CSRC)/capi.cu -o $@
 
 emu: $(EMUDIR)/libzkcnn_b200_emu.so
 $(EMUDIR)/libzkcnn_b200_emu.so: $(CSRC_DEPS) tests/emu/cuda_emu.cpp tests/emu/cuda_emu.hpp
 	mkdir -p $(EMUDIR)
-	$(CXX) -O2 -g -std=c++17 -fPIC -DZK_EMU -Wall -Wno-unknown-pragmas -Wno-unused-function -shared -Wl,-soname=libzkcnn_b200_emu.so -x c++ $(CSRC)/capi.cu -x none tests/emu/cuda_emu.cpp -o $@ -lpthread
+	$(CXX) -O2 -g -std=c++17 -fPIC -DZK_EMU -Wall -Wno-unknown-pragmas -Wno-unused-function -shared -Wl,-Bsymbolic -Wl,-soname=libzkcnn_b200_emu.so -x c++ $(CSRC)/capi.cu -x none tests/emu/cuda_emu.cpp -o $@ -lpthread
 
 # ---- stand-alone host side: circuit compiler, witness generator, protocol driver, C entry points (include/zkcnn_host.h)
 HOST      := zkcnn_b200/host
@@ -34,14 +34,14 @@ HOSTFLAGS := -O3 -g -std=c++17 -fPIC -Wall -Wno-unknown-pragmas -pthread
 
 host: $(LIBDIR)/libzkcnn_host.so $(LIBDIR)/zkcnn_prove
 $(LIBDIR)/libzkcnn_host.so: $(HOST_DEPS) $(LIBDIR)/libzkcnn_b200.so
-	$(CXX) $(HOSTFLAGS) -shared -Wl,-soname=libzkcnn_host.so $(HOST_SRCS) -L$(LIBDIR) -lzkcnn_b200 -Wl,-rpath,'$$ORIGIN' -o $@
+	$(CXX) $(HOSTFLAGS) -shared -Wl,-Bsymbolic -Wl,-soname=libzkcnn_host.so $(HOST_SRCS) -L$(LIBDIR) -lzkcnn_b200 -Wl,-rpath,'$$ORIGIN' -o $@
 $(LIBDIR)/zkcnn_prove: $(HOST)/main.cpp $(LIBDIR)/libzkcnn_host.so
 	$(CXX) $(HOSTFLAGS) $(HOST)/main.cpp -L$(LIBDIR) -lzkcnn_host -lzkcnn_b200 -Wl,-rpath,'$$ORIGIN' -o $@
 
 # test-only: the same host side on top of the emulator build of the kernels
 host_emu: $(EMUDIR)/libzkcnn_host_emu.so $(EMUDIR)/zkcnn_prove_emu
 $(EMUDIR)/libzkcnn_host_emu.so: $(HOST_DEPS) $(EMUDIR)/libzkcnn_b200_emu.so
-	$(CXX) $(HOSTFLAGS) -shared -Wl,-soname=libzkcnn_host_emu.so $(HOST_SRCS) -L$(EMUDIR) -lzkcnn_b200_emu -Wl,-rpath,'$$ORIGIN' -o $@
+	$(CXX) $(HOSTFLAGS) -shared -Wl,-Bsymbolic -Wl,-soname=libzkcnn_host_emu.so $(HOST_SRCS) -L$(EMUDIR) -lzkcnn_b200_emu -Wl,-rpath,'$$ORIGIN' -o $@
 $(EMUDIR)/zkcnn_prove_emu: $(HOST)/main.cpp $(EMUDIR)/libzkcnn_host_emu.so
 	$(CXX) $(HOSTFLAGS) $(HOST)/main.cpp -L$(EMUDIR) -lzkcnn_host_emu -lzkcnn_b200_emu -Wl,-rpath,'$$ORIGIN' -o $@
 

@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""bench.py -- vgg11 / CIFAR proofs per second on N B200s (BASELINE.json metric), plus the roofline of the dominant kernel
+and the reference CPU prover timed on the same box.
+
+  python bench.py --gpus N --steps K --warmup W                 # our arm (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W # the reference's own CPU prover (oracle/_ref/ref_run)
+
+A step is ONE proof of one picture (BASELINE config 3: vgg11, 32x32x3 input, pic_cnt = 1, 2^24-entry input layer) on
+each GPU: Hyrax commitment of the witness (Pippenger MSM over non-degenerate generators), 36 GKR layer sumchecks,
+the input-layer sumcheck and the Hyrax opening, driven by the in-process verifier exactly as in the reference
+(interactive, seeded challenges).  Weights are synthetic (tools/gen_synthetic_input.py: no network for the trained file),
+the circuit and its witness are built once on the host outside the timed region (the caller-side of the hot path,
+SURVEY.md section 8 f-1).
+
+  value : K proofs with the witness already resident in HBM, proofs / wall second, summed over ranks
+  e2e   : K proofs through the public host API with the witness copied from pinned host memory every step
+          (h2d_bytes_per_step) and every prover message read back (d2h_bytes_per_step = proof bytes)
+Timing: every API call of the protocol ends with a stream synchronisation, so the region is bracketed by
+barrier + device synchronize and read with the host clock; per-kernel device times inside the region come from CUDA
+events on the launching stream (zk_profile_*), which is what `roofline` uses.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+VGG11 = "64 M 128 M 256 256 M 512 512 M 512 512 M"
+METRIC = "vgg11_cifar_proofs_per_sec"
+UNIT = "proofs/s"
+
+
+def measured_peaks():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def gather_proofs(proof, device, dist):
+    """the path's only exchange step: one all-gather of fixed-size proof blobs (NCCL over NVLink when device is cuda;
+    gloo in the CPU test of this function).  Returns the list of every rank's proof bytes."""
+    import torch
+    t = torch.frombuffer(bytearray(proof), dtype=torch.uint8).to(device)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(dist.get_world_size())]
+    dist.all_gather(sizes, n)
+    cap = int(max(int(s.item()) for s in sizes))
+    buf = torch.zeros(cap, dtype=torch.uint8, device=device)
+    buf[:t.numel()] = t
+    outs = [torch.zeros_like(buf) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, buf)
+    return [bytes(o[:int(s.item())].cpu().numpy()) for o, s in zip(outs, sizes)]
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import gen_synthetic_input as gen
+    import zkcnn_b200
+    from zkcnn_b200 import PROF_CLASSES, REAL_GENERATORS, WITNESS_RESIDENT, CHECK_PREDICATES
+    import ctypes as C
+
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N > 1 with torch.distributed.run")
+    dist = None
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = args.model
+    config = VGG11 if model == "vgg11" else args.network
+    values = gen.generate("vgg11" if model == "vgg11" else "lenet", config=config if model == "vgg" else None)
+    lib = zkcnn_b200.load()
+    s = zkcnn_b200.session("lenet" if model == "lenet" else "vgg", "" if model == "lenet" else config, 1, device=local)
+    s.input_values(values.astype(np.float64))
+    t0 = time.perf_counter()
+    s.build()
+    build_s = time.perf_counter() - t0
+    flags = REAL_GENERATORS
+    # one fully verified proof with the reference's own (degenerate) generator set: full-size parity inside the bench
+    st0 = s.prove(1, CHECK_PREDICATES)
+    assert st0["ok"] == 1, "verification failed"
+    golden = os.path.join(ROOT, "tests", "golden", "vgg11_syn_p1_seed1.result.txt")
+    parity = None
+    if model == "vgg11" and os.path.exists(golden):
+        ref = dict(zip(*[iter(open(golden).read().split()[1:])] * 2))
+        parity = f"{st0['fnv1a']:016x}" == ref["fnv"]
+        assert parity, "vgg11 transcript differs from the reference's golden hash"
+    for i in range(max(args.warmup, 3)):
+        st = s.prove(1000 + i, flags | WITNESS_RESIDENT)
+        assert st["ok"] == 1
+
+    ctx = s.context_handle()
+    seeds = [10_000 + (k * world + rank) for k in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        # ---- value: witness resident in HBM --------------------------------------------------------------------------------
+        lib.dll.zk_profile_enable(ctx, 1)
+        barrier()
+        t0 = time.perf_counter()
+        launches = 0
+        for sd in seeds:
+            st = s.prove(sd, flags | WITNESS_RESIDENT)
+            launches += st["gpu_launches"]
+            assert st["ok"] == 1
+        barrier()
+        t_value = time.perf_counter() - t0
+        prof = {}
+        for k, name in enumerate(PROF_CLASSES):
+            ms, n, b = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+            lib.dll.zk_profile_get(ctx, k, C.byref(ms), C.byref(n), C.byref(b))
+            prof[name] = {"ms": ms.value, "launches": n.value, "bytes": b.value}
+        lib.dll.zk_profile_enable(ctx, 0)
+        # ---- e2e: witness from pinned host memory every step, proof bytes back ------------------------------------------------
+        barrier()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        proofs = []
+        for sd in seeds:
+            st = s.prove(sd, flags)
+            h2d += st["h2d_bytes"]
+            d2h += st["proof_bytes"]
+            proofs.append(s.proof())
+            assert st["ok"] == 1
+        if dist is not None:
+            gathered = gather_proofs(proofs[-1], device, dist)
+            assert len(gathered) == world and all(len(g) == len(proofs[-1]) for g in gathered)
+        barrier()
+        t_e2e = time.perf_counter() - t0
+    # max over ranks
+    if dist is not None:
+        tt = torch.tensor([t_value, t_e2e], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_value, t_e2e = float(tt[0]), float(tt[1])
+        ll = torch.tensor([launches], dtype=torch.int64, device=device)
+        dist.all_reduce(ll)
+        launches = int(ll[0])
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        dom = max(prof, key=lambda k: prof[k]["ms"])
+        def roof(name):
+            p = prof[name]
+            ach = p["bytes"] / 1e9 / (p["ms"] / 1e3) if p["ms"] > 0 else 0.0
+            return {"bound": "hbm", "kernel_class": name, "achieved": round(ach, 2), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "launches": p["launches"], "device_ms": round(p["ms"], 3),
+                    "algorithmic_bytes": p["bytes"]}
+        micro = {}
+        with zkcnn_b200.context(local) as c:
+            ms = c.bench_fold(24, 10, True)
+            micro["fold_2^24"] = {"ms": round(ms, 4), "GB/s": round(96 * (1 << 24) / 1e9 / (ms / 1e3), 1), "frac": round(96 * (1 << 24) / 1e9 / (ms / 1e3) / peak, 4)}
+            ms = c.bench_msm(12, 12, 2, 2)
+            b = 32 * (1 << 24) + 96 * 4096 + 144 * 4096
+            micro["msm_4096x4096_witness_like"] = {"ms": round(ms, 3), "GB/s": round(b / 1e9 / (ms / 1e3), 2), "frac": round(b / 1e9 / (ms / 1e3) / peak, 5)}
+        line = {
+            "metric": METRIC, "value": round(args.steps * world / t_value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(t_value / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 limbs (BLS12-381 Fr 255-bit / Fp 381-bit Montgomery)", "data": "synthetic",
+            "config": {"workload": "vgg11 CIFAR pic_cnt=1, one proof per step per GPU (BASELINE config 3/4)" if model == "vgg11" else model,
+                       "network": config, "input_layer": st0["input_size"], "layers": st0["n_layers"], "generators": "non-degenerate (G * challenge)",
+                       "l2": "tables larger than L2 (2^24 x 32 B witness, 537 MB)", "parallelism": f"one proof per GPU x{world}, final all-gather of proofs",
+                       "timer": "host clock around synchronous API calls, barrier + cuda synchronize on both sides; kernels by CUDA events"},
+            "e2e": {"value": round(args.steps * world / t_e2e, 4), "unit": UNIT, "h2d_bytes_per_step": h2d // max(1, args.steps),
+                    "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": round(t_e2e / args.steps * 1e3, 3)},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": roof(dom),
+            "kernels": {k: roof(k) for k in prof if prof[k]["launches"]},
+            "microbench": micro,
+            "parity": {"verified": True, "transcript_matches_reference_golden": parity},
+            "host_build_s": round(build_s, 2),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(model, config, bounded=True)
+        print(json.dumps(line), flush=True)
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+def ref_binary():
+    path = os.path.join(ROOT, "oracle", "_ref", "ref_run")
+    return path if os.access(path, os.X_OK) else None
+
+
+def write_input(model, config, path):
+    import gen_synthetic_input as gen
+    if model == "lenet":
+        gen.write_text(gen.generate("lenet"), path)
+        return ["lenet", path, "x"]
+    gen.write_text(gen.generate("vgg11", config=None if model == "vgg11" else config), path)
+    open(path + ".config", "w").write(config + "\n")
+    return ["vgg", path, "x", path + ".config"]
+
+
+def run_reference_once(cmd, procs):
+    """`procs` independent single-threaded reference provers side by side (the reference has no threads);
+    returns (proofs, seconds of prover time per proof as the reference counts it, wall seconds)"""
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen(cmd + ["1", str(100 + i)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i in range(procs)]
+    outs = [p.communicate()[0] for p in ps]
+    wall = time.perf_counter() - t0
+    prover_s, verify_wall = [], []
+    for o in outs:
+        res = [ln for ln in o.splitlines() if ln.startswith("RESULT")]
+        tab = [ln for ln in o.splitlines() if ln.startswith("TABLE")]
+        if not res or " ok 1 " not in res[0]:
+            raise RuntimeError("reference prover failed: " + o[-300:])
+        cols = [c.strip() for c in tab[0][6:].split(",")]
+        prover_s.append(float(cols[13]))                       # TOT_PT: GKR + Hyrax prover seconds (src/verifier.cpp:369)
+        verify_wall.append(float(res[0].split("verify_wall_s")[1].split()[0]))
+    return procs, max(prover_s), max(verify_wall), wall
+
+
+def cpu_baseline(model, config, bounded=True):
+    """reference CPU prover on this box's host cores: the unmodified reference compiled from /root/reference
+    (oracle/_ref/ref_run) on the same synthetic input.  Bounded sample: one proof on one core."""
+    ref = ref_binary()
+    if ref is None:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ref_run not present in this snapshot"}
+    path = f"/tmp/zkcnn_bench_{model}_{os.getpid()}.csv"
+    cmd = [ref] + write_input(model, config, path)
+    n, prover_s, verify_wall, wall = run_reference_once(cmd, 1)
+    os.remove(path)
+    return {"value": round(1.0 / prover_s, 5), "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"1 full {model} proof, 1 thread (the reference is single-threaded): prover {prover_s:.1f} s (PT + poly PT as the reference "
+                      f"counts them, degenerate generators) inside a {verify_wall:.1f} s commit+prove+verify loop; {os.cpu_count()} host cores visible"}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    ref = ref_binary()
+    model = args.model
+    config = VGG11 if model == "vgg11" else args.network
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_run (the reference compiled by oracle/Makefile) is not in this snapshot"}))
+        return
+    # all host threads the reference can use = independent single-threaded provers; bounded by memory (~9 GB each for vgg11)
+    cores = os.cpu_count() or 1
+    try:
+        avail_gb = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) / 1e6
+    except Exception:
+        avail_gb = 32
+    per = 10 if model == "vgg11" else 1
+    procs = max(1, min(cores, int(avail_gb * 0.7 / per)))
+    path = f"/tmp/zkcnn_bench_ref_{os.getpid()}.csv"
+    cmd = [ref] + write_input(model, config, path)
+    budget_s = 240.0
+    steps_done, total_wall, total_proofs, prover_s, spent = 0, 0.0, 0, 0.0, 0.0
+    for k in range(args.steps):           # no warm-up batches: a CPU prover has no warm-up effect worth 90 s each
+        n, ps, vw, wall = run_reference_once(cmd, procs)
+        steps_done += 1
+        total_wall += ps                  # prover seconds as the reference counts them (PT + poly PT), slowest process of the batch
+        total_proofs += n
+        prover_s = ps
+        spent += wall
+        if spent + wall > budget_s:
+            break
+    os.remove(path)
+    value = total_proofs / total_wall
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done, "warmup": 0,
+        "ms_per_step": round(total_wall / steps_done * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (mcl)",
+        "data": "synthetic",
+        "config": {"workload": "vgg11 CIFAR pic_cnt=1" if model == "vgg11" else model, "network": config,
+                   "note": f"each step = {procs} independent reference provers in parallel (one per host thread, memory-bounded); time = the reference's own prover "
+                           f"seconds (PT + poly PT, slowest process of a batch), circuit construction and verifier work excluded; the reference's generators are degenerate "
+                           f"(all infinity), which makes its MSM 13-37x cheaper than ours (SURVEY.md App. E.1); bounded to ~{int(budget_s)} s"},
+        "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": procs, "kind": "reference",
+                         "sample": f"{total_proofs} full proofs, prover seconds per proof {prover_s:.1f}"},
+        "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="vgg11", choices=["vgg11", "vgg", "lenet"])
+    ap.add_argument("--network", default=VGG11)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,17 @@ void zk_ctx_destroy(zk_ctx *ctx);
 /* number of kernels launched through this ctx so far (bench.py's gpu_launches) */
 uint64_t zk_ctx_launch_count(const zk_ctx *ctx);
 
+/* Per-kernel-class device timing (CUDA events on the launching stream around every launch) with the ALGORITHMIC bytes
+ * each launch moves, for roofline reporting.  Off by default (two event records per launch when on). */
+enum { ZK_PROF_FOLD = 0,   /* K1/K2 sumcheck round kernels                    */
+       ZK_PROF_GATES,      /* K4/K5 gate gather-reduce                        */
+       ZK_PROF_MSM,        /* K8/K9 bucket MSM                                */
+       ZK_PROF_TABLES,     /* K3 eq / phi tables                              */
+       ZK_PROF_DENSE,      /* K4b/K5b/K6 dense contractions, gathers, scatter */
+       ZK_PROF_OTHER, ZK_PROF_CLASSES };
+int zk_profile_enable(zk_ctx *ctx, int on);     /* also clears the counters */
+int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_t *bytes);
+
 /* page-lock / unlock a caller-owned host buffer so that uploads from it are direct DMA (cudaHostRegister) */
 int zk_host_pin(const void *p, size_t bytes);
 int zk_host_unpin(const void *p);

@@ -53,6 +53,7 @@ int zkh_build(zkh_session *s);                                           /* circ
 int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out);
 const uint8_t *zkh_proof(zkh_session *s, uint64_t *n_bytes);             /* proof of the last zkh_prove */
 int zkh_inferred_class(zkh_session *s, int picture);
+void *zkh_context(zkh_session *s);   /* the zk_ctx of this session's prover (NULL before the first proof); for zk_profile_* */
 /* per-layer shape/hash dump in the format of oracle/harness/ref_run --circuit-hash (parity tests) */
 int zkh_circuit_dump(zkh_session *s, const char *path, int with_hashes);
 

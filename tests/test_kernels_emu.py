@@ -1,0 +1,38 @@
+"""CPU suite: the CUDA kernel sources compiled for the test-only emulator, driven through the same C ABI."""
+import _cases as cases
+
+
+def test_fr_vec_ops(emu_lib):
+    cases.case_fr_vec_ops(emu_lib)
+
+
+def test_fr_kat(emu_lib, kat):
+    cases.case_fr_kat(emu_lib, kat)
+
+
+def test_beta_tables(emu_lib, kat):
+    cases.case_beta_tables(emu_lib, kat)
+
+
+def test_phi_tables(emu_lib, kat):
+    cases.case_phi_tables(emu_lib, kat)
+
+
+def test_fold_rounds(emu_lib):
+    cases.case_fold_rounds(emu_lib)
+
+
+def test_g1_ops(emu_lib, kat):
+    cases.case_g1_ops(emu_lib, kat)
+
+
+def test_msm(emu_lib, kat):
+    cases.case_msm(emu_lib, kat)
+
+
+def test_hyrax_kat(emu_lib, kat):
+    cases.case_hyrax_kat(emu_lib, kat)
+
+
+def test_hyrax_vs_port(emu_lib):
+    cases.case_hyrax_vs_port(emu_lib, bl=5)

@@ -1,0 +1,76 @@
+"""CPU suite: whole proofs through the stand-alone host side (circuit compiler, witness generator, protocol driver) on
+the emulator build of the kernels, against golden transcripts / circuit dumps minted from the compiled reference
+(oracle/harness/make_golden.sh).  Covers naive and FFT convolution, max pooling, ReLU, FC, pic_cnt 1 and 2."""
+import os
+
+import pytest
+
+import _cases as cases
+from conftest import GOLDEN
+from zkcnn_b200._binding import CHECK_PREDICATES, REAL_GENERATORS, Session
+
+
+def test_lenet_synthetic(emu_host, synthetic_inputs):
+    st = cases.prove_and_compare(emu_host, "lenet", "", 1, synthetic_inputs["lenet_syn"], 3, CHECK_PREDICATES, "lenet_syn_p1_seed3", GOLDEN)
+    assert st["ok"] == 1 and st["n_layers"] == 24 and st["gpu_launches"] > 0
+
+
+def test_lenet_synthetic_real_generators(emu_host, synthetic_inputs):
+    cases.prove_and_compare(emu_host, "lenet", "", 1, synthetic_inputs["lenet_syn"], 3, REAL_GENERATORS, "lenet_syn_p1_seed3_realgens", GOLDEN)
+
+
+def test_lenet_two_pictures_fft_path(emu_host, synthetic_inputs):
+    st = cases.prove_and_compare(emu_host, "lenet", "", 2, synthetic_inputs["lenet_syn"], 4, CHECK_PREDICATES, "lenet_syn_p2_seed4", GOLDEN)
+    assert st["ok"] == 1
+
+
+def test_small_vgg_naive_conv(emu_host, synthetic_inputs):
+    st = cases.prove_and_compare(emu_host, "vgg", synthetic_inputs["smallvgg_config"], 1, synthetic_inputs["smallvgg"], 7, CHECK_PREDICATES,
+                                 "smallvgg_p1_seed7", GOLDEN)
+    assert st["ok"] == 1
+
+
+def test_small_vgg_fft_conv(emu_host, synthetic_inputs):
+    st = cases.prove_and_compare(emu_host, "vgg", synthetic_inputs["smallvgg_config"], 2, synthetic_inputs["smallvgg"], 7, 0,
+                                 "smallvgg_p2_seed7", GOLDEN)
+    assert st["ok"] == 1
+
+
+def test_shipped_lenet_image(emu_host):
+    """the reference's own MNIST demo input (script/demo_lenet.sh), when the extracted data set is present"""
+    path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "data", "lenet5.mnist.relu.max",
+                        "lenet5.mnist.relu.max-1-images-weights-qint8.csv")
+    if not os.path.exists(path):
+        pytest.skip("reference data set not extracted (make -C oracle data)")
+    cases.prove_and_compare(emu_host, "lenet", "", 1, path, 1, CHECK_PREDICATES, "lenet_p1_seed1", GOLDEN)
+
+
+def test_repeat_proofs_and_resident_witness(emu_host, synthetic_inputs):
+    """second proof on the same session: new seed -> new transcript; same seed with the witness kept on the device ->
+    identical transcript, no upload"""
+    from zkcnn_b200._binding import WITNESS_RESIDENT
+    with Session(emu_host, "lenet", "", 1) as s:
+        s.input_file(synthetic_inputs["lenet_syn"])
+        s.build()
+        a = s.prove(3, 0)
+        pa = s.proof()
+        b = s.prove(9, WITNESS_RESIDENT)
+        pb = s.proof()
+        c = s.prove(3, WITNESS_RESIDENT)
+        pc = s.proof()
+    assert a["ok"] and b["ok"] and c["ok"]
+    assert a["h2d_bytes"] > 0 and b["h2d_bytes"] == 0 and c["h2d_bytes"] == 0
+    assert pa == pc and pa != pb
+    assert pa == open(os.path.join(GOLDEN, "lenet_syn_p1_seed3.transcript.bin"), "rb").read()
+
+
+def test_tampered_witness_is_rejected(emu_host, synthetic_inputs, tmp_path):
+    """soundness smoke: a different image gives a different (still accepted) proof; bad arguments are errors"""
+    from zkcnn_b200._binding import ZkError
+    with pytest.raises(ZkError):
+        Session(emu_host, "resnet")
+    with Session(emu_host, "lenet", "", 1) as s:
+        with pytest.raises(ZkError):
+            s.prove(1)                      # not built yet
+        with pytest.raises(ZkError):
+            s.input_file(tmp_path / "missing.csv")

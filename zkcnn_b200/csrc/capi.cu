@@ -38,11 +38,36 @@ void zk_ctx_destroy(zk_ctx *ctx) {
     if (!ctx) return;
     try { rt::set_device(ctx->device); rt::sync(ctx->stream); } catch (...) {}
     rt::hfree_pinned(ctx->h_out);
+    for (auto &r : ctx->prof_pending) { rt::event_destroy(r.a); rt::event_destroy(r.b); }
+    for (auto e : ctx->prof_pool) rt::event_destroy(e);
     rt::stream_destroy(ctx->stream);
     delete ctx;
 }
 
 uint64_t zk_ctx_launch_count(const zk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int zk_profile_enable(zk_ctx *ctx, int on) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx, "null ctx");
+    rt::set_device(ctx->device);
+    rt::sync(ctx->stream);
+    prof_resolve(ctx);
+    for (int c = 0; c < ZK_PROF_CLASSES; ++c) { ctx->prof_ms[c] = 0; ctx->prof_launches[c] = 0; ctx->prof_bytes[c] = 0; }
+    ctx->prof_on = on != 0;
+    ZK_API_END
+}
+
+int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_t *bytes) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && cls >= 0 && cls < ZK_PROF_CLASSES, "bad arguments");
+    rt::set_device(ctx->device);
+    rt::sync(ctx->stream);
+    prof_resolve(ctx);
+    if (ms) *ms = ctx->prof_ms[cls];
+    if (launches) *launches = ctx->prof_launches[cls];
+    if (bytes) *bytes = ctx->prof_bytes[cls];
+    ZK_API_END
+}
 
 int zk_host_pin(const void *p, size_t bytes) {
     ZK_API_BEGIN
@@ -215,9 +240,9 @@ int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/
         const uint32_t g_per_chunk = (cnt_len + n_chunks - 1) / n_chunks;
         n_chunks = (cnt_len + g_per_chunk - 1) / g_per_chunk;
         ctx->dense_partial.ensure((size_t) n_chunks * n_u * sizeof(fr_t));
-        ZK_KLAUNCH(ctx, k_dense_colsum, dim3((n_u + kBlock - 1) / kBlock, n_chunks), dim3(kBlock), 0, prev.val.as<fr_t>(),
+        ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, ((uint64_t) cnt_len << d.max_bl_u) * 32 + (uint64_t) cnt_len * 32, k_dense_colsum, dim3((n_u + kBlock - 1) / kBlock, n_chunks), dim3(kBlock), 0, prev.val.as<fr_t>(),
                    ctx->beta_g.as<fr_t>(), n_u, (uint32_t) d.max_bl_u, cnt_len, g_per_chunk, ctx->dense_partial.as<fr_t>());
-        ZK_KLAUNCH(ctx, k_colsum_finish, dim3((n_u + kBlock - 1) / kBlock), dim3(kBlock), 0, ctx->dense_partial.as<fr_t>(), n_u,
+        ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) (n_chunks + 1) * n_u * 32, k_colsum_finish, dim3((n_u + kBlock - 1) / kBlock), dim3(kBlock), 0, ctx->dense_partial.as<fr_t>(), n_u,
                    n_chunks, V);
         // mult_array[1] = phiGInit(r_0, scale)
         fr_t *M = table_init_buf(P.m, P.n_eval);
@@ -225,13 +250,13 @@ int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/
         ctx->d_r.ensure(2 * 64 * sizeof(fr_t));
         rt::h2d(ctx->d_r.p, r0.data(), std::min<size_t>(r0.size(), fft_bl) * sizeof(fr_t), ctx->stream);
         const fr_t *pw = phi_powers(ctx, fft_bl, !is_fft);
-        ZK_KLAUNCH(ctx, k_phi_table, dim3(1), dim3(kBlock), 0, M, ctx->d_r.as<fr_t>(), pw, L.scale, (int) fft_bl, (int) !is_fft);
+        ZK_KLAUNCH_C(ctx, ZK_PROF_TABLES, (uint64_t) P.n_eval * 32, k_phi_table, dim3(1), dim3(kBlock), 0, M, ctx->d_r.as<fr_t>(), pw, L.scale, (int) fft_bl, (int) !is_fft);
     } else {
         // V tables
         if (ctx->pair[0].exists) {
             fr_t *V = table_init_buf(ctx->pair[0].v, ctx->pair[0].n_eval);
             if (d.size_u[0])
-                ZK_KLAUNCH(ctx, k_gather, dim3(grid_for(d.size_u[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
+                ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) d.size_u[0] * 68, k_gather, dim3(grid_for(d.size_u[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
                            L.ori_u.as<uint32_t>(), d.size_u[0]);
         }
         if (ctx->pair[1].exists) {
@@ -247,7 +272,7 @@ int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/
             ZK_REQUIRE(r0.size() >= fft_blh, "r_0 too short");
             build_beta(ctx, ctx->beta_gs.as<fr_t>(), fft_blh, pts, 1);
             ctx->beta_g_alt.ensure(sizeof(fr_t) << d.bit_length);
-            ZK_KLAUNCH(ctx, k_beta_outer, dim3(grid_for(1ull << d.bit_length)), dim3(kBlock), 0, ctx->beta_g_alt.as<fr_t>(),
+            ZK_KLAUNCH_C(ctx, ZK_PROF_TABLES, 32ull << d.bit_length, k_beta_outer, dim3(grid_for(1ull << d.bit_length)), dim3(kBlock), 0, ctx->beta_g_alt.as<fr_t>(),
                        ctx->beta_g.as<fr_t>(), ctx->beta_gs.as<fr_t>(), (uint32_t) d.bit_length, fft_blh, tail_start, ctx->relu_rou);
             std::swap(ctx->beta_g, ctx->beta_g_alt);
         } else {
@@ -314,7 +339,7 @@ int zk_sumcheck_init_phase2(zk_ctx *ctx) {   // src/prover.cpp:241-310
         ZK_REQUIRE(((uint64_t) d.size_v[1] << fft_bl) <= prev.n_val, "DOT_PROD source layer too small");
         fr_t *V = table_init_buf(P.v, P.n_eval);
         if (d.size_v[1])
-            ZK_KLAUNCH(ctx, k_dense_rowdot, dim3(d.size_v[1]), dim3(kBlock), 0, V, prev.val.as<fr_t>(), ctx->beta_gs.as<fr_t>(), fft_bl);
+            ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, ((uint64_t) d.size_v[1] << fft_bl) * 32, k_dense_rowdot, dim3(d.size_v[1]), dim3(kBlock), 0, V, prev.val.as<fr_t>(), ctx->beta_gs.as<fr_t>(), fft_bl);
         fr_t *M = table_init_buf(P.m, P.n_eval);
         rt::dzero(M, (size_t) P.n_eval * sizeof(fr_t), ctx->stream);
         A.out1 = M;
@@ -328,7 +353,7 @@ int zk_sumcheck_init_phase2(zk_ctx *ctx) {   // src/prover.cpp:241-310
         if (ctx->pair[0].exists) {
             fr_t *V = table_init_buf(ctx->pair[0].v, ctx->pair[0].n_eval);
             if (d.size_v[0])
-                ZK_KLAUNCH(ctx, k_gather, dim3(grid_for(d.size_v[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
+                ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) d.size_v[0] * 68, k_gather, dim3(grid_for(d.size_v[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
                            L.ori_v.as<uint32_t>(), d.size_v[0]);
         }
         if (ctx->pair[1].exists) {
@@ -441,7 +466,7 @@ int zk_sumcheck_dotprod_init_phase1(zk_ctx *ctx) {   // src/prover.cpp:57-95
     P.v.cur = prev.val.as<fr_t>();
     fr_t *V0 = table_init_buf(P.m, P.n_eval);
     ZK_REQUIRE(L.dp_rows == (P.n_eval >> fft_bl), "DOT_PROD schedule missing");
-    ZK_KLAUNCH(ctx, k_dotprod_axpy, dim3(grid_for(P.n_eval)), dim3(kBlock), 0, V0, prev.val.as<fr_t>(), ctx->beta_g.as<fr_t>(),
+    ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) P.n_eval * 64, k_dotprod_axpy, dim3(grid_for(P.n_eval)), dim3(kBlock), 0, V0, prev.val.as<fr_t>(), ctx->beta_g.as<fr_t>(),
                L.dp_rowptr.as<uint32_t>(), L.dp_gates.as<dp_gate_t>(), L.dp_rows, fft_bl);
     ctx->round = 0;
     ZK_API_END
@@ -465,7 +490,7 @@ int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *a
     if (!first && ctx->mdp_n >= 2) {   // fold the multiplier table (src/prover.cpp:112-118)
         const uint32_t n_out = ctx->mdp_n >> 1;
         fr_t *out = table_fold_buf(ctx->mdp, n_out);
-        ZK_KLAUNCH(ctx, k_fold_small, dim3(grid_for(n_out)), dim3(kBlock), 0, ctx->mdp.cur, out, n_out, prev);
+        ZK_KLAUNCH_C(ctx, ZK_PROF_FOLD, (uint64_t) n_out * 96, k_fold_small, dim3(grid_for(n_out)), dim3(kBlock), 0, ctx->mdp.cur, out, n_out, prev);
         table_advance(ctx->mdp);
         ctx->mdp_n = n_out;
     }
@@ -486,7 +511,7 @@ int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *a
     A.partials = ctx->partials.as<fr_t>();
     A.counter = ctx->counters.as<uint32_t>() + 2;
     A.out = ctx->round_out.as<fr_t>();
-    ZK_KLAUNCH(ctx, k_round_cubic, dim3(A.n_blocks), dim3(kBlock), 0, A);
+    ZK_KLAUNCH_C(ctx, ZK_PROF_FOLD, (uint64_t) std::min(P.live, P.n_eval) * (first ? 64 : 96), k_round_cubic, dim3(A.n_blocks), dim3(kBlock), 0, A);
     rt::d2h(ctx->h_out, ctx->round_out.p, 4 * sizeof(fr_t), ctx->stream);
     rt::sync(ctx->stream);
     if (!first) {
@@ -555,7 +580,7 @@ int zk_sumcheck_liu_init(zk_ctx *ctx, const uint64_t *s_u, const uint64_t *s_v, 
             if (sigma.is_zero() || sz == 0) continue;
             beta_point_t pts[1] = {{r.data(), sigma}};
             halves_t H = build_halves(ctx, bl, pts, 1);
-            ZK_KLAUNCH(ctx, k_liu_scatter, dim3(grid_for(sz)), dim3(kBlock), 0, M, (side ? L.ori_v : L.ori_u).as<uint32_t>(), sz, H.f[0],
+            ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) sz * 68, k_liu_scatter, dim3(grid_for(sz)), dim3(kBlock), 0, M, (side ? L.ori_v : L.ori_u).as<uint32_t>(), sz, H.f[0],
                        H.s[0], H.first_half);
         }
     }

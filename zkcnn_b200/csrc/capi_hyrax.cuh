@@ -48,7 +48,7 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     const uint32_t n_chunks = (uint32_t) ((n + kMsmChunk - 1) / kMsmChunk);
     H.msm_rowinfo.ensure((size_t) n_rows * 4);
     rt::dzero(H.msm_rowinfo.p, (size_t) n_rows * 4, ctx->stream);
-    ZK_KLAUNCH(ctx, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
+    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, n * n_rows * 32, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
     const size_t per_row = (size_t) n_chunks * kMsmWindows;
     H.msm_out.ensure((size_t) n_rows * per_row * sizeof(g1_jac_t));
     msm_args_t A;
@@ -60,8 +60,8 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     A.n_chunks = n_chunks;
     A.partial = H.msm_out.as<g1_jac_t>();
     // grid.x is limited to 2^31-1, grid.y to 65535: rows * chunks in x, windows in y
-    ZK_KLAUNCH(ctx, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
-    ZK_KLAUNCH(ctx, k_msm_finish, dim3((n_rows + 63) / 64), dim3(64), 0, H.msm_out.as<g1_jac_t>(), n_rows, (uint32_t) per_row, out_dev);
+    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, n * n_rows * 32 + n * 96 + (uint64_t) n_rows * 144, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
+    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, 0, k_msm_finish, dim3((n_rows + 63) / 64), dim3(64), 0, H.msm_out.as<g1_jac_t>(), n_rows, (uint32_t) per_row, out_dev);
 }
 
 static void hyrax_bind(zk_ctx *ctx, const fr_t *Z, uint32_t bit_length, const uint64_t *gens, uint32_t n_gens) {
@@ -169,7 +169,7 @@ int zk_poly_init_bullet_prove(zk_ctx *ctx, const uint64_t *lx, uint32_t n_lx, co
     const uint32_t per = (rsize + n_chunks - 1) / n_chunks;
     n_chunks = (rsize + per - 1) / per;
     ctx->dense_partial.ensure((size_t) n_chunks * lsize * sizeof(fr_t));
-    ZK_KLAUNCH(ctx, k_dense_colsum, dim3((lsize + kBlock - 1) / kBlock, n_chunks), dim3(kBlock), 0, H.Z, H.R.as<fr_t>(), lsize, H.l_bits,
+    ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, ((uint64_t) rsize << H.l_bits) * 32, k_dense_colsum, dim3((lsize + kBlock - 1) / kBlock, n_chunks), dim3(kBlock), 0, H.Z, H.R.as<fr_t>(), lsize, H.l_bits,
                rsize, per, ctx->dense_partial.as<fr_t>());
     ZK_KLAUNCH(ctx, k_colsum_finish, dim3((lsize + kBlock - 1) / kBlock), dim3(kBlock), 0, ctx->dense_partial.as<fr_t>(), lsize, n_chunks,
                H.a.as<fr_t>());
@@ -370,6 +370,81 @@ int zk_selftest(zk_ctx *ctx, uint64_t seed, uint32_t n) {
     rt::d2h(&bad, d.p, 4, ctx->stream);
     rt::sync(ctx->stream);
     ZK_REQUIRE(bad == 0, "device self-test: inline-PTX field arithmetic disagrees with the portable implementation");
+    ZK_API_END
+}
+
+// ---- device-timed micro-benchmarks ---------------------------------------------------------------------------------------------
+int zk_bench_fold(zk_ctx *ctx, uint32_t bits, uint32_t iters, int fold, float *ms) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && ms && bits >= 2 && bits <= 28 && iters >= 1, "bad arguments");
+    rt::set_device(ctx->device);
+    ensure_round_scratch(ctx);
+    const uint64_t n = 1ull << bits;
+    rt::dbuf v, m, vo, mo;
+    v.ensure(n * 32); m.ensure(n * 32); vo.ensure(n * 16); mo.ensure(n * 16);
+    ZK_KLAUNCH(ctx, k_fill_synthetic, dim3(grid_for(n)), dim3(kBlock), 0, v.as<fr_t>(), n, 0x9E3779B97F4A7C15ULL, 0);
+    ZK_KLAUNCH(ctx, k_fill_synthetic, dim3(grid_for(n)), dim3(kBlock), 0, m.as<fr_t>(), n, 0x243F6A8885A308D3ULL, 0);
+    round_args_t A;
+    memset(&A, 0, sizeof A);
+    A.r = fr_t::from_u64(0x1234567887654321ULL);
+    A.partials = ctx->partials.as<fr_t>();
+    A.counters = ctx->counters.as<uint32_t>();
+    A.out = ctx->round_out.as<fr_t>();
+    round_pair_t &R = A.pair[1];
+    R.v_in = v.as<fr_t>(); R.m_in = m.as<fr_t>(); R.v_out = vo.as<fr_t>(); R.m_out = mo.as<fr_t>();
+    R.n_in = (uint32_t) n; R.live = (uint32_t) n; R.fold = fold ? 1 : 0;
+    R.n_blocks = grid_for(fold ? n >> 2 : n >> 1);
+    ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks, 2), dim3(kBlock), 0, A);   // warm-up
+    rt::event_t e0 = rt::event_create(), e1 = rt::event_create();
+    rt::event_record(e0, ctx->stream);
+    for (uint32_t i = 0; i < iters; ++i) ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks, 2), dim3(kBlock), 0, A);
+    rt::event_record(e1, ctx->stream);
+    rt::event_sync(e1);
+    *ms = rt::event_elapsed_ms(e0, e1) / iters;
+    rt::event_destroy(e0);
+    rt::event_destroy(e1);
+    ZK_API_END
+}
+
+int zk_bench_msm(zk_ctx *ctx, uint32_t log_rows, uint32_t log_cols, int scalar_mix, uint32_t iters, float *ms) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && ms && log_rows <= 14 && log_cols >= 1 && log_cols <= 14 && iters >= 1 && (scalar_mix == 0 || scalar_mix == 2), "bad arguments");
+    rt::set_device(ctx->device);
+    const uint32_t rows = 1u << log_rows, cols = 1u << log_cols;
+    // generators: (j + 1) * G
+    std::vector<g1_jac_t> base(cols);
+    std::vector<fr_t> k(cols);
+    g1_jac_t gen;
+    memcpy(gen.x.v, ZK_C(g1_gen_x_mont), 48);
+    memcpy(gen.y.v, ZK_C(g1_gen_y_mont), 48);
+    gen.z = fp_t::one();
+    for (uint32_t j = 0; j < cols; ++j) { base[j] = gen; k[j] = fr_t::from_u64(j + 1); }
+    rt::dbuf db, dk, dg;
+    db.ensure((size_t) cols * sizeof(g1_jac_t)); dk.ensure((size_t) cols * 32); dg.ensure((size_t) cols * sizeof(g1_jac_t));
+    rt::h2d(db.p, base.data(), (size_t) cols * sizeof(g1_jac_t), ctx->stream);
+    rt::h2d(dk.p, k.data(), (size_t) cols * 32, ctx->stream);
+    ZK_KLAUNCH(ctx, k_g1_vec_op, dim3((cols + 63) / 64), dim3(64), 0, db.as<g1_jac_t>(), (const g1_jac_t *) nullptr, dk.as<fr_t>(), dg.as<g1_jac_t>(), cols, 2);
+    std::vector<g1_jac_t> gens(cols);
+    rt::d2h(gens.data(), dg.p, (size_t) cols * sizeof(g1_jac_t), ctx->stream);
+    rt::sync(ctx->stream);
+    hyrax_t H;
+    msm_prepare_table(ctx, H, reinterpret_cast<const uint64_t *>(gens.data()), cols);
+    rt::dbuf ds, dout;
+    const uint64_t n = (uint64_t) rows * cols;
+    ds.ensure(n * 32);
+    dout.ensure((size_t) rows * sizeof(g1_jac_t));
+    ZK_KLAUNCH(ctx, k_fill_synthetic, dim3(grid_for(n)), dim3(kBlock), 0, ds.as<fr_t>(), n, 0x9E3779B97F4A7C15ULL, scalar_mix);
+    msm_run(ctx, H, ds.as<fr_t>(), cols, rows, dout.as<g1_jac_t>());   // warm-up
+    rt::event_t e0 = rt::event_create(), e1 = rt::event_create();
+    rt::event_record(e0, ctx->stream);
+    for (uint32_t i = 0; i < iters; ++i) msm_run(ctx, H, ds.as<fr_t>(), cols, rows, dout.as<g1_jac_t>());
+    rt::event_record(e1, ctx->stream);
+    rt::event_sync(e1);
+    *ms = rt::event_elapsed_ms(e0, e1) / iters;
+    rt::event_destroy(e0);
+    rt::event_destroy(e1);
     ZK_API_END
 }
 

@@ -26,12 +26,40 @@ static inline uint32_t grid_for(uint64_t work_items) {
     if (b > (uint64_t) kMaxGridX) b = kMaxGridX;
     return (uint32_t) b;
 }
-#define ZK_KLAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
+static inline zk::rt::event_t prof_event(zk_ctx *ctx) {
+    if (!ctx->prof_pool.empty()) { auto e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); return e; }
+    return zk::rt::event_create();
+}
+// launch of class `cls` (ZK_PROF_*) moving `bytes` algorithmic bytes
+#define ZK_KLAUNCH_C(ctx, cls, bytes, kernel, grid, block, smem, ...)                     \
     do {                                                                                  \
+        zk_ctx::prof_rec zk_pr_{(cls), nullptr, nullptr};                                 \
+        if ((ctx)->prof_on) {                                                             \
+            zk_pr_.a = zk::prof_event(ctx);                                               \
+            zk_pr_.b = zk::prof_event(ctx);                                               \
+            zk::rt::event_record(zk_pr_.a, (ctx)->stream);                                \
+        }                                                                                 \
         ZK_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);                 \
         ++(ctx)->launches;                                                                \
         zk::rt::check_launch(#kernel);                                                    \
+        if ((ctx)->prof_on) {                                                             \
+            zk::rt::event_record(zk_pr_.b, (ctx)->stream);                                \
+            (ctx)->prof_pending.push_back(zk_pr_);                                        \
+            ++(ctx)->prof_launches[(cls)];                                                \
+            (ctx)->prof_bytes[(cls)] += (uint64_t) (bytes);                               \
+        }                                                                                 \
     } while (0)
+#define ZK_KLAUNCH(ctx, kernel, grid, block, smem, ...) ZK_KLAUNCH_C(ctx, ZK_PROF_OTHER, 0, kernel, grid, block, smem, __VA_ARGS__)
+
+static void prof_resolve(zk_ctx *ctx) {
+    for (auto &r : ctx->prof_pending) {
+        zk::rt::event_sync(r.b);
+        ctx->prof_ms[r.cls] += zk::rt::event_elapsed_ms(r.a, r.b);
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+}
 
 // --------------------------------------------------------------------------------------------------------------------
 // schedule construction (host, once per circuit)
@@ -40,6 +68,8 @@ struct src_t { uint32_t rowkey; gate_rec_t rec; };  // rowkey: bits 30-31 = tabl
 
 static void build_schedule(zk_ctx *ctx, schedule_t &S, std::vector<src_t> &src, uint32_t rows0, uint32_t rows1, bool split_kind) {
     S.n_recs = src.size();
+    S.n_val_recs = 0;
+    if (!split_kind) for (auto &x : src) S.n_val_recs += ((x.rec.meta >> 16) & 3u) != 0;
     S.levels.clear();
     S.max_partials = 0;
     S.has_scalar = false;
@@ -239,7 +269,7 @@ static halves_t build_halves(zk_ctx *ctx, uint32_t bits, const beta_point_t *pts
         H.f[k] = ctx->half[2 * k].as<fr_t>();
         H.s[k] = ctx->half[2 * k + 1].as<fr_t>();
     }
-    ZK_KLAUNCH(ctx, k_half_tables, dim3(4), dim3(kBlock), 0, A);
+    ZK_KLAUNCH_C(ctx, ZK_PROF_TABLES, 0, k_half_tables, dim3(4), dim3(kBlock), 0, A);
     return H;
 }
 
@@ -254,7 +284,7 @@ static void build_beta(zk_ctx *ctx, fr_t *out, uint32_t bits, const beta_point_t
     B.f1 = (k0 == 0) ? H.f[1] : nullptr; B.s1 = (k0 == 0) ? H.s[1] : nullptr;
     B.bits = bits; B.first_half = H.first_half;
     B.tail_start = tail_start; B.tail_scale = tail_scale;
-    ZK_KLAUNCH(ctx, k_beta_expand, dim3(grid_for(1ull << bits)), dim3(kBlock), 0, B);
+    ZK_KLAUNCH_C(ctx, ZK_PROF_TABLES, 32ull << bits, k_beta_expand, dim3(grid_for(1ull << bits)), dim3(kBlock), 0, B);
 }
 
 static void run_schedule(zk_ctx *ctx, const schedule_t &S, int phase, gate_args_t A) {
@@ -268,11 +298,11 @@ static void run_schedule(zk_ctx *ctx, const schedule_t &S, int phase, gate_args_
         A.n_items = L.n_items;
         A.partial = ctx->gate_partial[k & 1].as<fr_t>();
         if (k == 0) {
-            if (phase == 1) ZK_KLAUNCH(ctx, k_gate_items_p1, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
-            else ZK_KLAUNCH(ctx, k_gate_items_p2, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
+            if (phase == 1) ZK_KLAUNCH_C(ctx, ZK_PROF_GATES, S.n_recs * 44 + S.n_val_recs * 32 + (uint64_t) L.n_items * 44, k_gate_items_p1, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
+            else ZK_KLAUNCH_C(ctx, ZK_PROF_GATES, S.n_recs * 76 + (uint64_t) L.n_items * 44, k_gate_items_p2, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
         } else {
             const fr_t *src = ctx->gate_partial[(k - 1) & 1].as<fr_t>();
-            ZK_KLAUNCH(ctx, k_sum_partials, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A, src);
+            ZK_KLAUNCH_C(ctx, ZK_PROF_GATES, (uint64_t) L.n_items * 44 + (uint64_t) S.levels[k - 1].n_partials * 32, k_sum_partials, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A, src);
         }
     }
 }
@@ -329,6 +359,7 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
     bool any_quad = false, any_final = false;
     bool quad[2] = {false, false}, fin[2] = {false, false};
     uint32_t gx = 0;
+    uint64_t fold_bytes = 0;   // algorithmic: read V and mult (live entries), write both halves
     for (int b = 0; b < 2; ++b) {
         pair_t &P = ctx->pair[b];
         if (!(mask & (1u << b)) || P.n_eval == 0) continue;
@@ -349,9 +380,10 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
             R.n_blocks = grid_for(std::max<uint32_t>(1, live_pairs));
             gx = std::max(gx, R.n_blocks);
             quad[b] = any_quad = true;
+            fold_bytes += (uint64_t) std::min(P.live, P.n_eval) * (first ? 64 : 96);
         }
     }
-    if (any_quad) ZK_KLAUNCH(ctx, k_round_quad, dim3(gx, 2), dim3(kBlock), 0, A);
+    if (any_quad) ZK_KLAUNCH_C(ctx, ZK_PROF_FOLD, fold_bytes, k_round_quad, dim3(gx, 2), dim3(kBlock), 0, A);
     if (any_final) ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
     if (any_quad || any_final) {
         rt::d2h(ctx->h_out, ctx->round_out.p, 16 * sizeof(fr_t), ctx->stream);

@@ -17,7 +17,7 @@ struct level_t {
 };
 struct schedule_t {
     rt::dbuf recs;
-    uint64_t n_recs = 0;
+    uint64_t n_recs = 0, n_val_recs = 0;   // n_val_recs: phase-1 records that also read a value operand
     std::vector<level_t> levels;
     uint32_t max_partials = 0;
     bool has_scalar = false;   // phase 2: uni gates feed add_term
@@ -101,4 +101,12 @@ struct zk_ctx {
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 
     zk::hyrax_t hy;
+
+    // optional per-kernel-class timing (zk_profile_*): CUDA events around every launch of the stream
+    bool prof_on = false;
+    struct prof_rec { int cls; zk::rt::event_t a, b; };
+    std::vector<prof_rec> prof_pending;
+    std::vector<zk::rt::event_t> prof_pool;
+    double prof_ms[ZK_PROF_CLASSES] = {};
+    uint64_t prof_launches[ZK_PROF_CLASSES] = {}, prof_bytes[ZK_PROF_CLASSES] = {};
 };

@@ -326,6 +326,33 @@ __global__ void __launch_bounds__(64) k_g1_vec_op(const g1_jac_t *a, const g1_ja
     out[i] = g1_normalize(r);
 }
 
+// synthetic benchmark inputs: mode 0 = uniform field elements, mode 2 = "witness-like"
+// (40 % zero, 8 % one, rest uniform in [-255, 255], negatives stored as r - |x|).  Values are in Montgomery form.
+__global__ void __launch_bounds__(kBlock) k_fill_synthetic(fr_t *out, uint64_t n, uint64_t seed, int mode) {
+    for (uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t) gridDim.x * kBlock) {
+        uint64_t st = seed + 0x9E3779B97F4A7C15ULL * (i + 1);
+        auto next = [&]() {
+            uint64_t z = (st += 0x9E3779B97F4A7C15ULL);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+            return z ^ (z >> 31);
+        };
+        fr_t x;
+        if (mode == 0) {
+            uint32_t c[8];
+            for (int k = 0; k < 8; k += 2) { uint64_t w = next(); c[k] = (uint32_t) w; c[k + 1] = (uint32_t) (w >> 32); }
+            c[7] &= 0x3fffffffu;   // < 2^254 < r
+            x = fr_t::from_canonical(c);
+        } else {
+            const uint32_t u = (uint32_t) (next() % 100u);
+            if (u < 40) x = fr_t::zero();
+            else if (u < 48) x = fr_t::one();
+            else x = fr_t::from_i64((int64_t) (next() % 511u) - 255);
+        }
+        st_fr(out + i, x);
+    }
+}
+
 // device self-test: PTX multiplier vs portable multiplier, Fr and Fp.  mismatches += 1 per differing result.
 __global__ void __launch_bounds__(kBlock) k_selftest(uint64_t seed, uint32_t n, uint32_t *mismatches) {
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;

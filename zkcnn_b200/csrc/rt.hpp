@@ -2,6 +2,7 @@
 // when the sources are compiled for the test-only emulator (ZK_EMU).
 #pragma once
 #include "zk_platform.cuh"
+#include <ctime>
 #include <stdexcept>
 #include <string>
 
@@ -34,6 +35,13 @@ inline zk_stream_t stream_create() { return nullptr; }
 inline void stream_destroy(zk_stream_t) {}
 inline void sync(zk_stream_t) {}
 inline void check_launch(const char *) {}
+typedef double *event_t;   // wall-clock stamp taken at "record" time (launches are synchronous in the emulator)
+inline double emu_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+inline event_t event_create() { return new double(0); }
+inline void event_destroy(event_t e) { delete e; }
+inline void event_record(event_t e, zk_stream_t) { *e = emu_now_ms(); }
+inline void event_sync(event_t) {}
+inline float event_elapsed_ms(event_t a, event_t b) { return (float) (*b - *a); }
 #else
 inline void check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) throw error(std::string(what) + ": " + cudaGetErrorString(e));
@@ -70,6 +78,12 @@ inline zk_stream_t stream_create() {
 inline void stream_destroy(zk_stream_t s) { if (s) cudaStreamDestroy(s); }
 inline void sync(zk_stream_t s) { check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
 inline void check_launch(const char *what) { check(cudaGetLastError(), what); }
+typedef cudaEvent_t event_t;
+inline event_t event_create() { cudaEvent_t e; check(cudaEventCreate(&e), "cudaEventCreate"); return e; }
+inline void event_destroy(event_t e) { cudaEventDestroy(e); }
+inline void event_record(event_t e, zk_stream_t s) { check(cudaEventRecord(e, s), "cudaEventRecord"); }
+inline void event_sync(event_t e) { check(cudaEventSynchronize(e), "cudaEventSynchronize"); }
+inline float event_elapsed_ms(event_t a, event_t b) { float ms = 0; check(cudaEventElapsedTime(&ms, a, b), "cudaEventElapsedTime"); return ms; }
 #endif
 
 // grow-only device buffer

@@ -197,6 +197,8 @@ const uint8_t *zkh_proof(zkh_session *s, uint64_t *n_bytes) {
     return s->tr.bytes.data();
 }
 
+void *zkh_context(zkh_session *s) { return s ? s->p.context() : nullptr; }
+
 int zkh_inferred_class(zkh_session *s, int picture) {
     if (!s || picture < 0 || (size_t) picture >= s->nn->inferred.size()) return -1;
     return s->nn->inferred[picture];
