@@ -139,6 +139,8 @@ int zk_fold_rounds(zk_ctx *ctx, const uint64_t *V, const uint64_t *M, uint32_t b
 int zk_msm(zk_ctx *ctx, const uint64_t *bases, const uint64_t *scalars, uint64_t n, uint32_t n_rows, uint64_t *out);
 /* element-wise G1: op 0: out = a + b; 1: out = 2a; 2: out = k*a (k = b reinterpreted as Fr per element) */
 int zk_g1_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n);
+/* out[i] = scalars[i] * base for ONE base point (fixed-base comb; the verifier's generator set-up, src/verifier.cpp:121-126) */
+int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scalars, uint64_t n, uint64_t *out);
 /* device self-test: inline-PTX field arithmetic against the portable implementation on n random inputs; 0 = equal */
 int zk_selftest(zk_ctx *ctx, uint64_t seed, uint32_t n);
 

@@ -197,3 +197,36 @@ def prove_and_compare(hostlib, model, network, pic_cnt, input_path, seed, flags,
         # polyProver.cpp:81-82 vs polyVerifier.cpp:58); the drop-in reproduces exactly that outcome
         assert st["ok"] == int(ref["ok"])
     return st
+
+
+def case_msm_many_rows(lib, n=64, rows=20, seed=808):
+    """>= 16 rows over one generator set: the small-multiples path (k_msm_small) with the bucket kernel in wide-only mode;
+    rows mix zero / one-byte / wide / sign-boundary scalars, one row is all zero, one base is the point at infinity"""
+    rng = O.SplitMix64(seed)
+    pts = [O.g1_mul(O.G1_GEN, rng.fr()) for _ in range(n)]
+    pts[3] = None
+    ks = rand_fr(rng, n * rows, "witness")
+    ks[0:n] = [0] * n                                         # an all-zero row
+    ks[n:2 * n] = [(rng.next() % 511 - 255) % O.R for _ in range(n)]   # a row with no wide scalar at all
+    ks[2 * n] , ks[2 * n + 1], ks[2 * n + 2], ks[2 * n + 3] = 255, O.R - 255, 256, O.R - 256   # both sides of the one-byte boundary
+    ks[3 * n + 5] = (O.R - 1) // 2
+    ks[3 * n + 6] = (O.R + 1) // 2
+    with Context(lib) as ctx:
+        got = g1_from_words(ctx.msm(g1_to_words(pts), fr_to_words(ks), rows))
+    assert got == [O.g1_mul_vec(pts, ks[i * n:(i + 1) * n]) for i in range(rows)]
+    assert got[0] is None
+
+
+def case_fixed_base_mul(lib, kat):
+    g = kat["g1"]
+    p, k = P(g["P"]), H(g["k"])
+    rng = O.SplitMix64(909)
+    ks = [k, 0, 1, O.R - 1, 255, 256, 1 << 200] + [rng.fr() for _ in range(5)]
+    with Context(lib) as ctx:
+        got = g1_from_words(ctx.g1_fixed_base_mul(g1_to_words([p])[0], fr_to_words(ks)))
+        assert got == [O.g1_mul(p, x) for x in ks]
+        assert got[0] == P(g["mul"])
+        # a second base point invalidates the cached comb table
+        got = g1_from_words(ctx.g1_fixed_base_mul(g1_to_words([O.G1_GEN])[0], fr_to_words(ks[:4])))
+        assert got == [O.g1_mul(O.G1_GEN, x) for x in ks[:4]]
+        assert g1_from_words(ctx.g1_fixed_base_mul(g1_to_words([None])[0], fr_to_words([5]))) == [None]

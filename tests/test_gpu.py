@@ -49,6 +49,12 @@ def test_msm(gpu_lib, kat):
     cases.case_msm(gpu_lib, kat, random_sizes=((40, 3), (300, 2)))
 
 
+def test_msm_many_rows_and_fixed_base(gpu_lib, kat):
+    cases.case_msm_many_rows(gpu_lib, n=64, rows=20)
+    cases.case_msm_many_rows(gpu_lib, n=300, rows=33, seed=818)
+    cases.case_fixed_base_mul(gpu_lib, kat)
+
+
 def test_hyrax(gpu_lib, kat):
     cases.case_hyrax_kat(gpu_lib, kat)
     cases.case_hyrax_vs_port(gpu_lib, bl=7)

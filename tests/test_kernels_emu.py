@@ -36,3 +36,15 @@ def test_hyrax_kat(emu_lib, kat):
 
 def test_hyrax_vs_port(emu_lib):
     cases.case_hyrax_vs_port(emu_lib, bl=5)
+
+
+def test_msm_many_rows(emu_lib):
+    cases.case_msm_many_rows(emu_lib, n=40, rows=17)
+
+
+def test_fixed_base_mul(emu_lib, kat):
+    cases.case_fixed_base_mul(emu_lib, kat)
+
+
+def test_hyrax_vs_port_small_path(emu_lib):
+    cases.case_hyrax_vs_port(emu_lib, bl=8, seed=1001)     # 16 commitment rows: the small-multiples path

@@ -95,6 +95,7 @@ class Lib:
         d.zk_fold_rounds.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint32, C.c_uint64, _u64p, C.c_uint32, _u64p]
         d.zk_msm.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint64, C.c_uint32, _u64p]
         d.zk_g1_vec_op.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint64]
+        d.zk_g1_fixed_base_mul.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint64, _u64p]
         d.zk_selftest.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
         d.zk_bench_fold.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
         d.zk_bench_msm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_float)]
@@ -195,6 +196,13 @@ class Context:
             b = np.ascontiguousarray(b, dtype=np.uint64)
         out = np.empty_like(a)
         self._check(self.lib.dll.zk_g1_vec_op(self.h, op, _ptr(a), _ptr(b), _ptr(out), len(a)), "zk_g1_vec_op")
+        return out
+
+    def g1_fixed_base_mul(self, base, scalars):
+        base = np.ascontiguousarray(base, dtype=np.uint64).reshape(18)
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        out = np.empty((len(scalars), 18), dtype=np.uint64)
+        self._check(self.lib.dll.zk_g1_fixed_base_mul(self.h, _ptr(base), _ptr(scalars), len(scalars), _ptr(out)), "zk_g1_fixed_base_mul")
         return out
 
     def bench_fold(self, bits, iters=20, fold=True):

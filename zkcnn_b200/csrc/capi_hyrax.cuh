@@ -3,6 +3,7 @@
 #pragma once
 #include "capi_sumcheck.cuh"
 #include "hyrax_kernels.cuh"
+#include "msm_kernels.cuh"
 
 namespace zk {
 
@@ -39,16 +40,50 @@ static void msm_prepare_table(zk_ctx *ctx, hyrax_t &H, const uint64_t *gens, uin
     rt::sync(ctx->stream);
     H.gens_hash = h;
     H.table_ready = true;
+    H.mult_ready = false;
+}
+
+// small-multiples table M[j][d-1] = d * G_j for the current generator set (msm_kernels.cuh); built on first use
+constexpr uint32_t kMultiplesMaxGens = 1u << 13;   // 8192 generators -> 200 MB
+static void msm_prepare_multiples(zk_ctx *ctx, hyrax_t &H) {
+    if (H.mult_ready) return;
+    H.mult.ensure((size_t) H.n_gens * kMultiples * sizeof(g1_aff_t));
+    const uint32_t threads = H.n_gens * kMulThreadsPerGen;
+    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, (uint64_t) H.n_gens * kMultiples * 96, k_msm_multiples_build, dim3((threads + 127) / 128), dim3(128), 0,
+                 H.gens_aff.as<g1_aff_t>(), H.mult.as<g1_aff_t>(), H.n_gens);
+    H.mult_ready = true;
 }
 
 // out_dev[k] (normalised) = sum_j scalars[k*n + j] * G_j  for k < n_rows, generators taken from H.table
 static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n, uint32_t n_rows, g1_jac_t *out_dev) {
     ZK_REQUIRE(H.table_ready && n <= H.n_gens, "MSM: generator table missing or too small");
     msm_configure();
-    const uint32_t n_chunks = (uint32_t) ((n + kMsmChunk - 1) / kMsmChunk);
     H.msm_rowinfo.ensure((size_t) n_rows * 4);
     rt::dzero(H.msm_rowinfo.p, (size_t) n_rows * 4, ctx->stream);
-    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, n * n_rows * 32, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
+    const uint64_t alg_bytes = n * n_rows * 32 + n * 96 + (uint64_t) n_rows * 144;
+    // many rows over one generator set: the one-byte scalars go through the small-multiples table, the bucket kernel
+    // below only sees what is left (rows whose widest leftover is 0 bytes leave it at once)
+    const bool small_path = n_rows >= 16 && H.n_gens <= kMultiplesMaxGens;
+    uint32_t n_seg = 0;
+    if (small_path) {
+        msm_prepare_multiples(ctx, H);
+        const uint32_t seg_len = (uint32_t) std::min<uint64_t>(n, 2048);
+        n_seg = (uint32_t) ((n + seg_len - 1) / seg_len);
+        H.msm_small.ensure((size_t) n_rows * n_seg * sizeof(g1_jac_t));
+        msm_small_args_t S;
+        S.scalars = scalars_dev;
+        S.table = H.mult.as<g1_aff_t>();
+        S.n = n;
+        S.n_rows = n_rows; S.n_seg = n_seg; S.seg_len = seg_len;
+        S.partial = H.msm_small.as<g1_jac_t>();
+        S.rowinfo = H.msm_rowinfo.as<uint32_t>();
+        const uint64_t warps = (uint64_t) n_rows * n_seg;
+        ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, alg_bytes, k_msm_small, dim3((uint32_t) ((warps + kSmallWarps - 1) / kSmallWarps)), dim3(kSmallWarps * 32), 0, S);
+    } else {
+        ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, 0, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
+    }
+    const uint32_t chunk = n_rows <= 8 ? std::min<uint32_t>(2048, kMsmChunk) : kMsmChunk;   // few rows: more CTAs per row
+    const uint32_t n_chunks = (uint32_t) ((n + chunk - 1) / chunk);
     const size_t per_row = (size_t) n_chunks * kMsmWindows;
     H.msm_out.ensure((size_t) n_rows * per_row * sizeof(g1_jac_t));
     msm_args_t A;
@@ -58,10 +93,13 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     A.n = n;
     A.n_table = H.n_gens;
     A.n_chunks = n_chunks;
+    A.chunk = chunk;
+    A.wide_only = small_path ? 1u : 0u;
     A.partial = H.msm_out.as<g1_jac_t>();
     // grid.x is limited to 2^31-1, grid.y to 65535: rows * chunks in x, windows in y
-    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, n * n_rows * 32 + n * 96 + (uint64_t) n_rows * 144, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
-    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, 0, k_msm_finish, dim3((n_rows + 63) / 64), dim3(64), 0, H.msm_out.as<g1_jac_t>(), n_rows, (uint32_t) per_row, out_dev);
+    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
+    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kSmallWarps - 1) / kSmallWarps), dim3(kSmallWarps * 32), 0,
+                 small_path ? H.msm_small.as<g1_jac_t>() : (const g1_jac_t *) nullptr, n_seg, H.msm_out.as<g1_jac_t>(), (uint32_t) per_row, n_rows, out_dev);
 }
 
 static void hyrax_bind(zk_ctx *ctx, const fr_t *Z, uint32_t bit_length, const uint64_t *gens, uint32_t n_gens) {
@@ -353,6 +391,36 @@ int zk_g1_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint
     ZK_KLAUNCH(ctx, k_g1_vec_op, dim3((uint32_t) ((n + 63) / 64)), dim3(64), 0, da.as<g1_jac_t>(), op == 0 ? db.as<g1_jac_t>() : nullptr,
                op == 2 ? db.as<fr_t>() : nullptr, dc.as<g1_jac_t>(), (uint32_t) n, op);
     rt::d2h(out, dc.p, n * sizeof(g1_jac_t), ctx->stream);
+    rt::sync(ctx->stream);
+    ZK_API_END
+}
+
+int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scalars, uint64_t n, uint64_t *out) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && base && scalars && out && n >= 1 && n < (1ull << 24), "bad arguments");
+    rt::set_device(ctx->device);
+    const uint64_t h = fnv1a64(base, sizeof(g1_jac_t));
+    if (!ctx->fb_ready || ctx->fb_hash != h) {   // comb[w][d-1] = d * 2^(8w) * base
+        rt::dbuf jb, ab, win;
+        jb.ensure(sizeof(g1_jac_t)); ab.ensure(sizeof(g1_aff_t)); win.ensure((size_t) kMsmWindows * sizeof(g1_aff_t));
+        rt::h2d(jb.p, base, sizeof(g1_jac_t), ctx->stream);
+        ZK_KLAUNCH(ctx, k_g1_to_affine, dim3(1), dim3(kBlock), 0, jb.as<g1_jac_t>(), ab.as<g1_aff_t>(), 1u);
+        ZK_KLAUNCH(ctx, k_msm_table_build, dim3(1), dim3(64), 0, ab.as<g1_aff_t>(), win.as<g1_aff_t>(), 1u);
+        ctx->fb_comb.ensure((size_t) kMsmWindows * kMultiples * sizeof(g1_aff_t));
+        ZK_KLAUNCH(ctx, k_msm_multiples_build, dim3((kMsmWindows * kMulThreadsPerGen + 127) / 128), dim3(128), 0, win.as<g1_aff_t>(),
+                   ctx->fb_comb.as<g1_aff_t>(), (uint32_t) kMsmWindows);
+        rt::sync(ctx->stream);
+        ctx->fb_hash = h;
+        ctx->fb_ready = true;
+    }
+    rt::dbuf dk, dout;
+    dk.ensure(n * 32);
+    dout.ensure(n * sizeof(g1_jac_t));
+    rt::h2d(dk.p, scalars, n * 32, ctx->stream);
+    ZK_KLAUNCH(ctx, k_fixed_base_mul, dim3((uint32_t) ((n + 127) / 128)), dim3(128), 0, ctx->fb_comb.as<g1_aff_t>(), dk.as<fr_t>(), (uint32_t) n,
+               dout.as<g1_jac_t>());
+    rt::d2h(out, dout.p, n * sizeof(g1_jac_t), ctx->stream);
     rt::sync(ctx->stream);
     ZK_API_END
 }

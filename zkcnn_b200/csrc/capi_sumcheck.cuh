@@ -4,12 +4,41 @@
 #include "ctx.hpp"
 #include <algorithm>
 #include <cstring>
+#include <ctime>
 
 namespace zk {
 
 static thread_local std::string g_last_error;
 
-#define ZK_API_BEGIN try {
+// ZK_TRACE=1: wall time per C-ABI entry point, printed at exit (where does the host-side latency go?)
+struct api_trace_t {
+    struct row { const char *name; uint64_t calls; double us; };
+    std::vector<row> rows;
+    bool on = getenv("ZK_TRACE") != nullptr;
+    ~api_trace_t() {
+        if (!on) return;
+        std::sort(rows.begin(), rows.end(), [](const row &a, const row &b) { return a.us > b.us; });
+        for (auto &r : rows) fprintf(stderr, "[zk_trace] %-36s calls %8lu total %10.3f ms  avg %9.2f us\n", r.name, (unsigned long) r.calls, r.us / 1e3, r.us / r.calls);
+    }
+    void add(const char *name, double us) {
+        for (auto &r : rows) if (r.name == name) { ++r.calls; r.us += us; return; }
+        rows.push_back({name, 1, us});
+    }
+};
+static api_trace_t g_api_trace;
+struct api_scope_t {
+    const char *name;
+    timespec t0;
+    explicit api_scope_t(const char *n) : name(n) { if (g_api_trace.on) clock_gettime(CLOCK_MONOTONIC, &t0); }
+    ~api_scope_t() {
+        if (!g_api_trace.on) return;
+        timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        g_api_trace.add(name, (t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_nsec - t0.tv_nsec) * 1e-3);
+    }
+};
+
+#define ZK_API_BEGIN zk::api_scope_t zk_api_scope_(__func__); try {
 #define ZK_API_END                                            \
     return 0;                                                 \
     } catch (const std::exception &e) {                       \

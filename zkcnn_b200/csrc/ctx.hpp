@@ -61,6 +61,8 @@ struct hyrax_t {
     rt::dbuf gens_aff;         // n_gens affine points
     rt::dbuf table;            // fixed-base window table: [kWindows][n_gens] affine, entry = 2^(8w) * gens[j]
     bool table_ready = false;
+    rt::dbuf mult;             // small-multiples table [n_gens][255] affine, entry = d * gens[j]  (msm_kernels.cuh)
+    bool mult_ready = false;
     uint64_t gens_hash = 0;
     rt::dbuf L, R, RZ, a, a_next, coef, scal;
     std::vector<fr_t> t;       // remaining opening point (lx)
@@ -68,7 +70,7 @@ struct hyrax_t {
     uint32_t cur = 0;          // current length of bullet_a
     uint32_t round = 0;
     std::vector<fr_t> rinv;    // 1 / randomness of the finished rounds
-    rt::dbuf msm_out, msm_rowinfo, pts_out;
+    rt::dbuf msm_out, msm_small, msm_rowinfo, pts_out;
 };
 
 }  // namespace zk
@@ -101,6 +103,9 @@ struct zk_ctx {
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 
     zk::hyrax_t hy;
+    zk::rt::dbuf fb_comb;       // zk_g1_fixed_base_mul: comb table of the last base point
+    uint64_t fb_hash = 0;
+    bool fb_ready = false;
 
     // optional per-kernel-class timing (zk_profile_*): CUDA events around every launch of the stream
     bool prof_on = false;

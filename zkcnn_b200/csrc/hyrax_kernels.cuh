@@ -120,6 +120,8 @@ struct msm_args_t {
     uint64_t n;              // row length (== number of generators used)
     uint32_t n_table;        // generators in the table (row stride of the table)
     uint32_t n_chunks;       // CTAs per row and window
+    uint32_t chunk;          // entries per CTA (<= kMsmChunk)
+    uint32_t wide_only;      // 1: scalars that fit one byte are skipped (the small-multiples path took them, msm_kernels.cuh)
     g1_jac_t *partial;       // [n_rows][n_chunks][kMsmWindows] window sums
 };
 
@@ -133,8 +135,8 @@ __global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
         if (t == 0) *dst = g1_jac_t::inf();
         return;
     }
-    const uint64_t base = (uint64_t) chunk * kMsmChunk;
-    const uint32_t nc = (uint32_t) (A.n - base < (uint64_t) kMsmChunk ? A.n - base : (uint64_t) kMsmChunk);
+    const uint64_t base = (uint64_t) chunk * A.chunk;
+    const uint32_t nc = (uint32_t) (A.n - base < (uint64_t) A.chunk ? A.n - base : (uint64_t) A.chunk);
     const fr_t *sc = A.scalars + (uint64_t) row * A.n + base;
     const g1_aff_t *T = A.table + (size_t) w * A.n_table + base;
 
@@ -149,8 +151,9 @@ __global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
         uint32_t d = 0, neg = 0;
         if (!s.is_zero()) {
             uint32_t mag[8];
-            scalar_sign_mag(s, mag, neg);
+            const uint32_t nb = scalar_sign_mag(s, mag, neg);
             d = (mag[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+            if (A.wide_only && nb <= 1) d = 0;
         }
         S->dig[j] = (uint8_t) d;
         S->sgn[j] = (uint8_t) neg;

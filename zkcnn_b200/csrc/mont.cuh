@@ -46,6 +46,7 @@ struct fr_cfg {
     static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fr_MOD); }
     static ZK_HD __forceinline__ const uint32_t *one() { return ZK_C(fr_ONE); }
     static ZK_HD __forceinline__ const uint32_t *r2() { return ZK_C(fr_R2); }
+    static ZK_HD __forceinline__ const uint32_t *r3() { return ZK_C(fr_R3); }
     static ZK_HD __forceinline__ const uint32_t *modm2() { return ZK_C(fr_MODM2); }
     static ZK_HD __forceinline__ const uint32_t *half() { return ZK_C(fr_HALF); }
 };
@@ -55,6 +56,7 @@ struct fp_cfg {
     static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fp_MOD); }
     static ZK_HD __forceinline__ const uint32_t *one() { return ZK_C(fp_ONE); }
     static ZK_HD __forceinline__ const uint32_t *r2() { return ZK_C(fp_R2); }
+    static ZK_HD __forceinline__ const uint32_t *r3() { return ZK_C(fp_R3); }
     static ZK_HD __forceinline__ const uint32_t *modm2() { return ZK_C(fp_MODM2); }
     static ZK_HD __forceinline__ const uint32_t *half() { return ZK_C(fp_HALF); }
 };
@@ -302,8 +304,73 @@ template <class C> struct alignas(16) mont_t {
             }
         return acc;
     }
-    // multiplicative inverse by Fermat (0 -> 0).  Field elements are unique, so this equals mcl's Fr::inv / Fp::inv.
-    ZK_HD inline mont_t inverse() const { return pow_limbs(C::modm2()); }
+    // multiplicative inverse by Fermat (0 -> 0); kept as the cross-check of inverse()
+    ZK_HD inline mont_t inverse_fermat() const { return pow_limbs(C::modm2()); }
+
+    // ---- raw multi-limb helpers for the binary inversion ---------------------------------------------------------------
+    static ZK_HD __forceinline__ bool raw_is_one(const uint32_t *a) {
+        uint32_t o = a[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < N; ++i) o |= a[i];
+        return o == 0;
+    }
+    static ZK_HD __forceinline__ void raw_shr1(uint32_t *a, uint32_t top_in) {   // a = (top_in : a) >> 1
+#pragma unroll
+        for (int i = 0; i < N - 1; ++i) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+        a[N - 1] = (a[N - 1] >> 1) | (top_in << 31);
+    }
+    static ZK_HD __forceinline__ uint32_t raw_add(uint32_t *a, const uint32_t *b) {   // a += b, returns the carry out
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            c += (uint64_t) a[i] + b[i];
+            a[i] = (uint32_t) c;
+            c >>= 32;
+        }
+        return (uint32_t) c;
+    }
+    static ZK_HD __forceinline__ void raw_sub(uint32_t *a, const uint32_t *b) {   // a -= b (caller guarantees a >= b or wraps on purpose)
+        int64_t bw = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bw += (int64_t) a[i] - (int64_t) b[i];
+            a[i] = (uint32_t) bw;
+            bw >>= 32;
+        }
+    }
+    // x = x / 2 mod p
+    static ZK_HD __forceinline__ void raw_half_mod(uint32_t *x, const uint32_t *p) {
+        uint32_t carry = 0;
+        if (x[0] & 1u) carry = raw_add(x, p);
+        raw_shr1(x, carry);
+    }
+    // x = x - y mod p  (x, y < p)
+    static ZK_HD __forceinline__ void raw_sub_mod(uint32_t *x, const uint32_t *y, const uint32_t *p) {
+        const bool ge = ge_raw(x, y);
+        raw_sub(x, y);
+        if (!ge) raw_add(x, p);
+    }
+    // Multiplicative inverse (0 -> 0) by the binary extended Euclidean algorithm on the Montgomery representative
+    // (about 2 log2(p) shift/subtract steps instead of the ~1.5 log2(p) field multiplications of Fermat: ~8x fewer
+    // instructions for Fp).  Field elements are unique, so the value equals mcl's Fr::inv / Fp::inv.
+    ZK_HD inline mont_t inverse() const {
+        if (is_zero()) return *this;
+        uint32_t pm[N], u[N], w[N], x1[N], x2[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { pm[i] = C::mod()[i]; u[i] = v[i]; w[i] = pm[i]; x1[i] = i == 0 ? 1u : 0u; x2[i] = 0u; }
+        while (!raw_is_one(u) && !raw_is_one(w)) {
+            while (!(u[0] & 1u)) { raw_shr1(u, 0); raw_half_mod(x1, pm); }
+            while (!(w[0] & 1u)) { raw_shr1(w, 0); raw_half_mod(x2, pm); }
+            if (ge_raw(u, w)) { raw_sub(u, w); raw_sub_mod(x1, x2, pm); }
+            else { raw_sub(w, u); raw_sub_mod(x2, x1, pm); }
+        }
+        // (a R)^-1 = a^-1 R^-1 as a plain integer; one Montgomery multiplication by R^3 brings it to a^-1 R
+        mont_t r, r3;
+        const bool first = raw_is_one(u);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { r.v[i] = first ? x1[i] : x2[i]; r3.v[i] = C::r3()[i]; }
+        return r * r3;
+    }
 
     // mcl's isNegative(): canonical value >= (p+1)/2  (mcl/include/mcl/fp.hpp:666-671)
     ZK_HD inline bool is_negative() const {

@@ -1,0 +1,193 @@
+// Small-scalar fast path of the Hyrax commitment MSM (K8) and fixed-base scalar multiplication.
+//
+// The zkCNN witness is tiny-valued (hard part 3): 40 % of the 2^24 scalars are zero and 99.9 % of the
+// rest satisfy |x| <= 255 once mcl's sign convention is applied.  All sqrt(n) commitment rows share one generator set,
+// so a table of small multiples  M[j][d-1] = d * G_j  (d = 1..255, affine, 96 B)  turns a row commitment into ONE mixed
+// addition per non-zero scalar -- no buckets, no window reduction:
+//     comm[i] = sum_j sign(z_ij) * M[j][|z_ij|]          (k_msm_small)
+// The table is 255 * 96 B per generator (100 MB for the 4096 vgg11 generators, L2-resident for the most part) and is
+// rebuilt whenever the generator set changes (k_msm_multiples_build, ~20 field multiplications per entry thanks to one
+// shared inversion per 32 entries).  Scalars wider than one byte are left to the generic bucket kernel (k_msm_window in
+// "wide only" mode) and both partial results meet in k_msm_finish_rows.
+#pragma once
+#include "hyrax_kernels.cuh"
+
+namespace zk {
+
+constexpr int kMultiples = 255;          // d = 1 .. 255
+constexpr int kMulSeg = 32;              // table entries produced by one thread (one shared inversion)
+constexpr int kMulThreadsPerGen = 8;     // 8 * 32 = 256 >= 255
+
+// ---- M[j][d-1] = d * G_j ------------------------------------------------------------------------------------------------
+// thread (j, s) produces d = 32 s + 1 .. 32 s + 32: a chain of mixed additions in Jacobian form, then ONE inversion of the
+// product of all z (Montgomery's trick) to normalise the 32 points.
+__global__ void __launch_bounds__(128) k_msm_multiples_build(const g1_aff_t *gens, g1_aff_t *table, uint32_t n) {
+    const uint32_t idx = blockIdx.x * 128 + threadIdx.x;
+    const uint32_t j = idx / kMulThreadsPerGen, s = idx % kMulThreadsPerGen;
+    if (j >= n) return;
+    const g1_aff_t G = gens[j];
+    g1_aff_t *out = table + (size_t) j * kMultiples + s * kMulSeg;
+    const int cnt = (s + 1) * kMulSeg > kMultiples ? kMultiples - s * kMulSeg : kMulSeg;
+    if (G.is_inf()) {
+        for (int k = 0; k < cnt; ++k) out[k] = g1_aff_t::inf();
+        return;
+    }
+    // B = (32 s) * G
+    g1_jac_t B = g1_jac_t::inf();
+    if (s) {
+        g1_jac_t p32 = g1_jac_t::from_affine(G);
+        for (int k = 0; k < 5; ++k) p32 = g1_dbl(p32);
+        B = p32;
+        for (uint32_t t = 1; t < s; ++t) B = g1_add(B, p32);
+    }
+    fp_t zs[kMulSeg], pre[kMulSeg];
+    fp_t run = fp_t::one();
+    for (int k = 0; k < cnt; ++k) {
+        B = g1_add_mixed(B, G);          // (32 s + k + 1) * G; never infinity: G has prime order r > 255
+        out[k].x = B.x;
+        out[k].y = B.y;
+        zs[k] = B.z;
+        run = run * B.z;
+        pre[k] = run;
+    }
+    fp_t inv = run.inverse();
+    for (int k = cnt - 1; k >= 0; --k) {
+        const fp_t zi = k ? inv * pre[k - 1] : inv;      // 1 / z_k
+        inv = inv * zs[k];
+        const fp_t zi2 = zi.sqr();
+        out[k].x = out[k].x * zi2;
+        out[k].y = out[k].y * zi2 * zi;
+    }
+}
+
+// ---- one warp per (row, segment): comm partial = sum of table points selected by the small scalars ---------------------------
+struct msm_small_args_t {
+    const fr_t *scalars;       // [n_rows][n]
+    const g1_aff_t *table;     // [n][255]
+    uint64_t n;
+    uint32_t n_rows, n_seg, seg_len;   // seg_len <= 65536
+    g1_jac_t *partial;         // [n_rows][n_seg]
+    uint32_t *rowinfo;         // widest magnitude (bytes) among the scalars that do NOT fit one byte, per row (atomicMax)
+};
+constexpr int kSmallWarps = 8;
+
+__global__ void __launch_bounds__(kSmallWarps * 32) k_msm_small(msm_small_args_t A) {
+    __shared__ g1_jac_t sh[kSmallWarps * 32];
+    __shared__ uint32_t queue[kSmallWarps][64];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t gw = (uint64_t) blockIdx.x * kSmallWarps + warp;
+    const bool active = gw < (uint64_t) A.n_rows * A.n_seg;   // idle warps of the last CTA keep walking through the barriers
+    const uint32_t row = active ? (uint32_t) (gw / A.n_seg) : 0u, seg = active ? (uint32_t) (gw % A.n_seg) : 0u;
+    const uint64_t base = (uint64_t) seg * A.seg_len;
+    const uint64_t end = !active ? base : base + A.seg_len < A.n ? base + A.seg_len : A.n;
+    const fr_t *sc = A.scalars + (uint64_t) row * A.n;
+    uint32_t *q = queue[warp];
+    g1_jac_t acc = g1_jac_t::inf();
+    uint32_t head = 0, pending = 0, wide = 0;
+    (void) q; (void) head; (void) pending;   // unused by the (uncompacted) emulator path
+
+    auto consume = [&](uint32_t code) {
+        const uint32_t j = code & 0xffffu, d = (code >> 16) & 0xffu, neg = code >> 24;
+        const g1_aff_t *e = A.table + ((base + j) * kMultiples + (d - 1));
+        g1_aff_t pt;
+        pt.x = ld_fp(&e->x);
+        pt.y = ld_fp(&e->y);
+        if (neg) pt.y = -pt.y;
+        acc = g1_add_mixed(acc, pt);
+    };
+
+    for (uint64_t b = base; b < end; b += 32) {
+        const uint64_t j = b + lane;
+        uint32_t code = 0;
+        if (j < end) {
+            const fr_t s = ld_fr(sc + j);
+            if (!s.is_zero()) {
+                uint32_t mag[8], neg;
+                const uint32_t nb = scalar_sign_mag(s, mag, neg);
+                if (nb > 1) wide = wide > nb ? wide : nb;
+                else code = (uint32_t) (j - base) | (mag[0] << 16) | (neg << 24);
+            }
+        }
+        // compact the non-zero small scalars of these 32 entries into the warp's queue, so that every lane of the warp
+        // has a point addition to do whenever the queue is drained (the witness is 40 % zeros)
+#if ZK_ON_DEVICE
+        const uint32_t mask = __ballot_sync(0xffffffffu, code != 0);
+        const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+        if (code) q[(head + pending + rank) & 63u] = code;
+        pending += __popc(mask);
+        __syncwarp();
+        if (pending >= 32) {
+            const uint32_t c = q[(head + lane) & 63u];
+            head = (head + 32) & 63u;
+            pending -= 32;
+            __syncwarp();
+            consume(c);
+        }
+#else
+        if (code) consume(code);
+#endif
+    }
+#if ZK_ON_DEVICE
+    if (lane < pending) consume(q[(head + lane) & 63u]);
+#endif
+    if (wide) atomicMax(A.rowinfo + row, wide);
+    // warp-level sum of the 32 accumulators
+    g1_jac_t *my = sh + threadIdx.x;
+    *my = acc;
+    __syncwarp();
+    for (uint32_t st = 16; st > 0; st >>= 1) {
+        if (lane < st) *my = g1_add(*my, my[st]);
+        __syncwarp();
+    }
+    if (active && lane == 0) A.partial[gw] = *my;
+}
+
+// ---- out[row] = normalised (sum of the row's small-path partials + sum of its bucket-path partials); one warp per row ------------
+__global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_jac_t *small, uint32_t n_small, const g1_jac_t *bucket,
+                                                                        uint32_t n_bucket, uint32_t n_rows, g1_jac_t *out) {
+    __shared__ g1_jac_t sh[kSmallWarps * 32];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t row = blockIdx.x * kSmallWarps + warp;
+    const bool active = row < n_rows;
+    if (!active) n_small = n_bucket = 0;
+    g1_jac_t acc = g1_jac_t::inf();
+    for (uint32_t k = lane; k < n_small; k += 32) {
+        const g1_jac_t p = small[(size_t) row * n_small + k];
+        if (!p.is_inf()) acc = g1_add(acc, p);
+    }
+    for (uint32_t k = lane; k < n_bucket; k += 32) {
+        const g1_jac_t p = bucket[(size_t) row * n_bucket + k];
+        if (!p.is_inf()) acc = g1_add(acc, p);
+    }
+    g1_jac_t *my = sh + threadIdx.x;
+    *my = acc;
+    __syncwarp();
+    for (uint32_t st = 16; st > 0; st >>= 1) {
+        if (lane < st) *my = g1_add(*my, my[st]);
+        __syncwarp();
+    }
+    if (active && lane == 0) out[row] = g1_normalize(*my);
+}
+
+// ---- fixed-base scalar multiplication: out[i] = k_i * B for ONE base point ------------------------------------------------------
+// comb[w][d-1] = d * 2^(8w) * B (32 x 255 affine entries, built by k_msm_table_build + k_msm_multiples_build);
+// every product is 32 table look-ups and mixed additions.
+__global__ void __launch_bounds__(128) k_fixed_base_mul(const g1_aff_t *comb, const fr_t *k, uint32_t n, g1_jac_t *out) {
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c[8];
+    ld_fr(k + i).to_canonical(c);
+    g1_jac_t acc = g1_jac_t::inf();
+    for (int w = 0; w < kMsmWindows; ++w) {
+        const uint32_t d = (c[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+        if (!d) continue;
+        const g1_aff_t *e = comb + ((size_t) w * kMultiples + (d - 1));
+        g1_aff_t pt;
+        pt.x = ld_fp(&e->x);
+        pt.y = ld_fp(&e->y);
+        acc = g1_add_mixed(acc, pt);
+    }
+    out[i] = g1_normalize(acc);
+}
+
+}  // namespace zk

@@ -67,8 +67,12 @@ void prover::uploadWitness() {
 
 void prover::pinWitness() {
     unpinWitness();
+    if (getenv("ZKCNN_NO_PIN")) return;
+    // commitInput() later pads val[0] to 2^bit_length in place (src/prover.cpp:504-508): make room now so that the
+    // vector is not reallocated after it has been page-locked
+    if (!val.empty() && C.size) val[0].reserve((size_t) 1 << C.circuit[0].bit_length);
     for (auto &v : val)
-        if (!v.empty() && zk_host_pin(v.data(), v.size() * sizeof(F)) == 0) pinned_.push_back(v.data());
+        if (!v.empty() && zk_host_pin(v.data(), v.capacity() * sizeof(F)) == 0) pinned_.push_back(v.data());
 }
 
 void prover::unpinWitness() {

@@ -17,7 +17,8 @@ void g1_words_to_affine_le(const uint64_t *w, uint8_t out[96]) {
     memcpy(&p, w, sizeof p);
     memset(out, 0, 96);
     if (p.is_inf()) return;
-    zk::g1_aff_t a = zk::g1_to_affine(p);
+    // points returned by the library are already normalised (z = 1): no field inversion on the host for those
+    zk::g1_aff_t a = p.z == zk::fp_t::one() ? zk::g1_aff_t{p.x, p.y} : zk::g1_to_affine(p);
     uint32_t c[12];
     a.x.to_canonical(c);
     memcpy(out, c, 48);

@@ -194,9 +194,9 @@ bool verifier::verify() {   // src/verifier.cpp:118-130
         if (fixedGenerators->size() != n_gens) throw std::invalid_argument("verifier: fixedGenerators has the wrong size");
         generators = *fixedGenerators;
     } else if (realGenerators) {
-        vector<G> base(n_gens, G::generator());
+        const G base = G::generator();
         generators.assign(n_gens, G());
-        require(zk_g1_vec_op(p->context(), 2, w(base[0]), w(k[0]), w(generators[0]), n_gens), "zk_g1_vec_op(mul)");
+        require(zk_g1_fixed_base_mul(p->context(), w(base), w(k[0]), n_gens, w(generators[0])), "zk_g1_fixed_base_mul");
     } else generators.assign(n_gens, G());   // reference default: base point cleared by initPairing -> all infinity
     poly_v.reset(new hyrax_bls12_381::polyVerifier(p->commitInput(generators), generators, p->context(), checkPredicates));
     return verifyInnerLayers() && verifyFirstLayer() && verifyInput();
