@@ -38,6 +38,7 @@ void zk_ctx_destroy(zk_ctx *ctx) {
     if (!ctx) return;
     try { rt::set_device(ctx->device); rt::sync(ctx->stream); } catch (...) {}
     rt::hfree_pinned(ctx->h_out);
+    rt::hfree_pinned(ctx->res_h);
     for (auto &r : ctx->prof_pending) { rt::event_destroy(r.a); rt::event_destroy(r.b); }
     for (auto e : ctx->prof_pool) rt::event_destroy(e);
     rt::stream_destroy(ctx->stream);
@@ -510,17 +511,18 @@ int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *a
     A.r = prev;
     A.partials = ctx->partials.as<fr_t>();
     A.counter = ctx->counters.as<uint32_t>() + 2;
-    A.out = ctx->round_out.as<fr_t>();
+    A.out = ctx->res_d;
+    A.flag = ctx->flag_d;
+    A.seq = ++ctx->seq;
     ZK_KLAUNCH_C(ctx, ZK_PROF_FOLD, (uint64_t) std::min(P.live, P.n_eval) * (first ? 64 : 96), k_round_cubic, dim3(A.n_blocks), dim3(kBlock), 0, A);
-    rt::d2h(ctx->h_out, ctx->round_out.p, 4 * sizeof(fr_t), ctx->stream);
-    rt::sync(ctx->stream);
+    wait_mailbox(ctx);
     if (!first) {
         table_advance(P.m);
         table_advance(P.v);
         P.n_eval >>= 1;
         P.live = (P.live + 1) >> 1;
     }
-    for (int k = 0; k < 4; ++k) fr_store(abcd + 4 * k, ctx->h_out[k]);
+    for (int k = 0; k < 4; ++k) fr_store(abcd + 4 * k, ctx->res_h[k]);
     ZK_API_END
 }
 
@@ -538,13 +540,14 @@ int zk_sumcheck_dotprod_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t 
     final_fold_args_t F;
     memset(&F, 0, sizeof F);
     F.r = prev;
-    F.out = ctx->round_out.as<fr_t>() + 8;
+    F.out = ctx->res_d + 8;
     F.v_in[0] = P.v.cur; F.live[0] = P.live; F.fold[0] = 1; F.active[0] = 1;
     F.v_in[1] = ctx->mdp.cur; F.live[1] = ctx->mdp_n; F.fold[1] = ctx->mdp_n == 2; F.active[1] = 1;
+    F.flag = ctx->flag_d;
+    F.seq = ++ctx->seq;
     ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
-    rt::d2h(ctx->h_out, ctx->round_out.p, 16 * sizeof(fr_t), ctx->stream);
-    rt::sync(ctx->stream);
-    const fr_t c1 = ctx->h_out[8], m = ctx->h_out[10];
+    wait_mailbox(ctx);
+    const fr_t c1 = ctx->res_h[8], m = ctx->res_h[10];
     ctx->V_u1 = c1 * m;
     fr_store(claim_1, c1);
     P.n_eval = 0;

@@ -30,13 +30,16 @@ static void msm_prepare_table(zk_ctx *ctx, hyrax_t &H, const uint64_t *gens, uin
     const uint64_t h = fnv1a64(gens, (size_t) n_gens * sizeof(g1_jac_t)) ^ n_gens;
     if (H.table_ready && H.gens_hash == h && H.n_gens == n_gens) return;   // same public generators as last time
     H.n_gens = n_gens;
-    rt::dbuf tmp;
+    rt::dbuf &tmp = H.gens_jac;
     tmp.ensure((size_t) n_gens * sizeof(g1_jac_t));
     rt::h2d(tmp.p, gens, (size_t) n_gens * sizeof(g1_jac_t), ctx->stream);
     H.gens_aff.ensure((size_t) n_gens * sizeof(g1_aff_t));
     ZK_KLAUNCH(ctx, k_g1_to_affine, dim3(grid_for(n_gens)), dim3(kBlock), 0, tmp.as<g1_jac_t>(), H.gens_aff.as<g1_aff_t>(), n_gens);
     H.table.ensure((size_t) kMsmWindows * n_gens * sizeof(g1_aff_t));
-    ZK_KLAUNCH(ctx, k_msm_table_build, dim3((n_gens + 63) / 64), dim3(64), 0, H.gens_aff.as<g1_aff_t>(), H.table.as<g1_aff_t>(), n_gens);
+    H.table_scratch.ensure((size_t) 2 * kMsmWindows * n_gens * sizeof(fp_t));
+    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, (uint64_t) kMsmWindows * n_gens * 96, k_msm_table_build, dim3((n_gens + kTableBuildBlock - 1) / kTableBuildBlock),
+                 dim3(kTableBuildBlock), 0, H.gens_aff.as<g1_aff_t>(), H.table.as<g1_aff_t>(), H.table_scratch.as<fp_t>(),
+                 H.table_scratch.as<fp_t>() + (size_t) kMsmWindows * n_gens, n_gens);
     rt::sync(ctx->stream);
     H.gens_hash = h;
     H.table_ready = true;
@@ -402,11 +405,13 @@ int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scal
     rt::set_device(ctx->device);
     const uint64_t h = fnv1a64(base, sizeof(g1_jac_t));
     if (!ctx->fb_ready || ctx->fb_hash != h) {   // comb[w][d-1] = d * 2^(8w) * base
-        rt::dbuf jb, ab, win;
+        rt::dbuf jb, ab, win, scr;
         jb.ensure(sizeof(g1_jac_t)); ab.ensure(sizeof(g1_aff_t)); win.ensure((size_t) kMsmWindows * sizeof(g1_aff_t));
+        scr.ensure((size_t) 2 * kMsmWindows * sizeof(fp_t));
         rt::h2d(jb.p, base, sizeof(g1_jac_t), ctx->stream);
         ZK_KLAUNCH(ctx, k_g1_to_affine, dim3(1), dim3(kBlock), 0, jb.as<g1_jac_t>(), ab.as<g1_aff_t>(), 1u);
-        ZK_KLAUNCH(ctx, k_msm_table_build, dim3(1), dim3(64), 0, ab.as<g1_aff_t>(), win.as<g1_aff_t>(), 1u);
+        ZK_KLAUNCH(ctx, k_msm_table_build, dim3(1), dim3(kTableBuildBlock), 0, ab.as<g1_aff_t>(), win.as<g1_aff_t>(), scr.as<fp_t>(),
+                   scr.as<fp_t>() + kMsmWindows, 1u);
         ctx->fb_comb.ensure((size_t) kMsmWindows * kMultiples * sizeof(g1_aff_t));
         ZK_KLAUNCH(ctx, k_msm_multiples_build, dim3((kMsmWindows * kMulThreadsPerGen + 127) / 128), dim3(128), 0, win.as<g1_aff_t>(),
                    ctx->fb_comb.as<g1_aff_t>(), (uint32_t) kMsmWindows);
@@ -414,7 +419,7 @@ int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scal
         ctx->fb_hash = h;
         ctx->fb_ready = true;
     }
-    rt::dbuf dk, dout;
+    rt::dbuf &dk = ctx->fb_k, &dout = ctx->fb_out;
     dk.ensure(n * 32);
     dout.ensure(n * sizeof(g1_jac_t));
     rt::h2d(dk.p, scalars, n * 32, ctx->stream);

@@ -3,6 +3,7 @@
 #pragma once
 #include "ctx.hpp"
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <ctime>
 
@@ -363,11 +364,42 @@ static void table_advance(table_t &T) {
 static void ensure_round_scratch(zk_ctx *ctx) {
     ctx->partials.ensure((size_t) 2 * kMaxGridX * 4 * sizeof(fr_t));
     if (!ctx->counters.p) {
-        ctx->counters.ensure(4 * sizeof(uint32_t));
-        rt::dzero(ctx->counters.p, 4 * sizeof(uint32_t), ctx->stream);
+        ctx->counters.ensure(8 * sizeof(uint32_t));
+        rt::dzero(ctx->counters.p, 8 * sizeof(uint32_t), ctx->stream);
     }
     ctx->round_out.ensure(16 * sizeof(fr_t));
     if (!ctx->h_out) ctx->h_out = static_cast<fr_t *>(rt::hmalloc_pinned(16 * sizeof(fr_t)));
+    if (!ctx->res_h) {
+        ctx->res_h = static_cast<fr_t *>(rt::hmalloc_mapped(32 * sizeof(fr_t) + 64));
+        ctx->res_d = static_cast<fr_t *>(rt::mapped_device_ptr(ctx->res_h));
+        ctx->flag_h = reinterpret_cast<uint32_t *>(ctx->res_h + 32);
+        ctx->flag_d = reinterpret_cast<uint32_t *>(ctx->res_d + 32);
+    }
+}
+
+// wait until the kernel that was given (flag_d, seq) has published its results into res_h
+static void wait_mailbox(zk_ctx *ctx) {
+#ifndef ZK_EMU
+    volatile uint32_t *f = ctx->flag_h;
+    uint64_t spins = 0;
+    timespec t0{};
+    while (*f != ctx->seq) {
+        if (++spins == 200000) clock_gettime(CLOCK_MONOTONIC, &t0);   // ~ms without an answer: start watching the stream and the clock
+        else if (spins > 200000 && (spins & 0xffff) == 0) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) rt::check(q, "sumcheck round kernel");
+            if (q == cudaSuccess && *f != ctx->seq) throw rt::error("sumcheck round kernel finished without publishing its result");
+            timespec t1;
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if (t1.tv_sec - t0.tv_sec > 20) throw rt::error("sumcheck round kernel did not publish its result within 20 s");
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+#endif
+    if (*ctx->flag_h != ctx->seq) throw rt::error("result mailbox out of sequence");
 }
 
 // One call of sumcheckUpdateEach for both table pairs (src/prover.cpp:396-426).  `mask` selects the pairs that take part
@@ -380,11 +412,11 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
     A.r = prev;
     A.partials = ctx->partials.as<fr_t>();
     A.counters = ctx->counters.as<uint32_t>();
-    A.out = ctx->round_out.as<fr_t>();
+    A.out = ctx->res_d;
     final_fold_args_t F;
     memset(&F, 0, sizeof F);
     F.r = prev;
-    F.out = ctx->round_out.as<fr_t>() + 8;
+    F.out = ctx->res_d + 8;
     bool any_quad = false, any_final = false;
     bool quad[2] = {false, false}, fin[2] = {false, false};
     uint32_t gx = 0;
@@ -412,23 +444,26 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
             fold_bytes += (uint64_t) std::min(P.live, P.n_eval) * (first ? 64 : 96);
         }
     }
+    // the last kernel of the round publishes the sequence number the host waits on
+    ++ctx->seq;
+    A.n_pairs = (quad[0] ? 1u : 0u) + (quad[1] ? 1u : 0u);
+    if (any_final) { F.flag = ctx->flag_d; F.seq = ctx->seq; }
+    else { A.flag = ctx->flag_d; A.seq = ctx->seq; }
     if (any_quad) ZK_KLAUNCH_C(ctx, ZK_PROF_FOLD, fold_bytes, k_round_quad, dim3(gx, 2), dim3(kBlock), 0, A);
     if (any_final) ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
-    if (any_quad || any_final) {
-        rt::d2h(ctx->h_out, ctx->round_out.p, 16 * sizeof(fr_t), ctx->stream);
-        rt::sync(ctx->stream);
-    }
+    if (any_quad || any_final) wait_mailbox(ctx);
+    const fr_t *h_res = ctx->res_h;
     abc[0] = abc[1] = abc[2] = fr_t::zero();
     for (int b = 0; b < 2; ++b) {
         pair_t &P = ctx->pair[b];
         if (fin[b]) {
-            P.cv = ctx->h_out[8 + 2 * b];
-            P.cm = ctx->h_out[8 + 2 * b + 1];
+            P.cv = h_res[8 + 2 * b];
+            P.cm = h_res[8 + 2 * b + 1];
             ctx->add_term = ctx->add_term + P.cv * P.cm;
             P.collapsed = true;
             P.n_eval = 0;
         } else if (quad[b]) {
-            for (int k = 0; k < 3; ++k) abc[k] = abc[k] + ctx->h_out[4 * b + k];
+            for (int k = 0; k < 3; ++k) abc[k] = abc[k] + h_res[4 * b + k];
             if (!first) {
                 table_advance(P.v);
                 table_advance(P.m);
@@ -445,7 +480,7 @@ static void final_values(zk_ctx *ctx, const fr_t &prev, fr_t out[2]) {
     final_fold_args_t F;
     memset(&F, 0, sizeof F);
     F.r = prev;
-    F.out = ctx->round_out.as<fr_t>() + 8;
+    F.out = ctx->res_d + 8;
     bool any = false;
     for (int b = 0; b < 2; ++b) {
         pair_t &P = ctx->pair[b];
@@ -460,11 +495,12 @@ static void final_values(zk_ctx *ctx, const fr_t &prev, fr_t out[2]) {
         any = true;
     }
     if (any) {
+        F.flag = ctx->flag_d;
+        F.seq = ++ctx->seq;
         ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
-        rt::d2h(ctx->h_out, ctx->round_out.p, 16 * sizeof(fr_t), ctx->stream);
-        rt::sync(ctx->stream);
+        wait_mailbox(ctx);
         for (int b = 0; b < 2; ++b)
-            if (F.active[b]) out[b] = ctx->h_out[8 + 2 * b];
+            if (F.active[b]) out[b] = ctx->res_h[8 + 2 * b];
     }
 }
 

@@ -59,8 +59,10 @@ struct hyrax_t {
     uint32_t bit_length = 0, l_bits = 0, r_bits = 0;
     uint32_t n_gens = 0;
     rt::dbuf gens_aff;         // n_gens affine points
+    rt::dbuf gens_jac;         // upload staging
     rt::dbuf table;            // fixed-base window table: [kWindows][n_gens] affine, entry = 2^(8w) * gens[j]
     bool table_ready = false;
+    rt::dbuf table_scratch;    // z's and prefix products of the table build
     rt::dbuf mult;             // small-multiples table [n_gens][255] affine, entry = d * gens[j]  (msm_kernels.cuh)
     bool mult_ready = false;
     uint64_t gens_hash = 0;
@@ -100,9 +102,15 @@ struct zk_ctx {
     // scratch
     zk::rt::dbuf half[4], d_r, partials, counters, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
     zk::fr_t *h_out = nullptr;  // pinned mirror of round_out
+    // result mailbox of the per-round kernels: mapped pinned host memory the last CTA writes directly, followed by a
+    // sequence number; the host spins on the sequence number instead of copying + synchronising the stream
+    zk::fr_t *res_h = nullptr, *res_d = nullptr;          // [32] host / device view
+    uint32_t *flag_h = nullptr, *flag_d = nullptr;
+    uint32_t seq = 0;
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 
     zk::hyrax_t hy;
+    zk::rt::dbuf fb_k, fb_out;
     zk::rt::dbuf fb_comb;       // zk_g1_fixed_base_mul: comb table of the last base point
     uint64_t fb_hash = 0;
     bool fb_ready = false;

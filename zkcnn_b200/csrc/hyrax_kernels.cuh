@@ -74,18 +74,38 @@ __global__ void __launch_bounds__(kBlock) k_g1_to_affine(const g1_jac_t *in, g1_
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) out[i] = g1_to_affine(in[i]);
 }
 
-// T[w][j] = 2^(8w) * G_j, affine.  One thread per generator (one-off per generator set).
-__global__ void __launch_bounds__(64) k_msm_table_build(const g1_aff_t *gens, g1_aff_t *table, uint32_t n) {
-    const uint32_t j = blockIdx.x * 64 + threadIdx.x;
+// T[w][j] = 2^(8w) * G_j, affine.  One thread per generator (once per generator set): a chain of 248 doublings in Jacobian
+// form, then ONE inversion for all 31 points (Montgomery's trick; zs / pre are [31][n] scratch for the z's and their prefix
+// products).  32-thread CTAs spread the n chains over as many SMs as possible: the chain is latency bound.
+constexpr int kTableBuildBlock = 32;
+__global__ void __launch_bounds__(kTableBuildBlock) k_msm_table_build(const g1_aff_t *gens, g1_aff_t *table, fp_t *zs, fp_t *pre, uint32_t n) {
+    const uint32_t j = blockIdx.x * kTableBuildBlock + threadIdx.x;
     if (j >= n) return;
-    g1_aff_t a = gens[j];
+    const g1_aff_t a = gens[j];
     table[j] = a;
+    if (a.is_inf()) {
+        for (int w = 1; w < kMsmWindows; ++w) table[(size_t) w * n + j] = g1_aff_t::inf();
+        return;
+    }
     g1_jac_t p = g1_jac_t::from_affine(a);
+    fp_t run = fp_t::one();
     for (int w = 1; w < kMsmWindows; ++w) {
-        for (int k = 0; k < 8; ++k) p = g1_dbl(p);
-        a = g1_to_affine(p);
-        table[(size_t) w * n + j] = a;
-        p = g1_jac_t::from_affine(a);
+        for (int k = 0; k < 8; ++k) p = g1_dbl(p);          // never infinity: G_j has prime order
+        g1_aff_t *e = table + (size_t) w * n + j;
+        e->x = p.x;
+        e->y = p.y;
+        run = run * p.z;
+        zs[(size_t) (w - 1) * n + j] = p.z;
+        pre[(size_t) (w - 1) * n + j] = run;
+    }
+    fp_t inv = run.inverse();
+    for (int w = kMsmWindows - 1; w >= 1; --w) {
+        const fp_t zi = w > 1 ? inv * pre[(size_t) (w - 2) * n + j] : inv;   // 1 / z_w
+        inv = inv * zs[(size_t) (w - 1) * n + j];
+        const fp_t zi2 = zi.sqr();
+        g1_aff_t *e = table + (size_t) w * n + j;
+        e->x = e->x * zi2;
+        e->y = e->y * zi2 * zi;
     }
 }
 

@@ -278,14 +278,31 @@ template <class C> struct alignas(16) mont_t {
     }
 #endif
 
-    friend ZK_HD __forceinline__ mont_t operator*(const mont_t &a, const mont_t &b) {
+#if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
+    // ONE out-of-line copy of the fully unrolled multiplier per field.  Inlining it at every use makes the hot loops tens
+    // of thousands of straight-line instructions long and the kernels instruction-fetch bound (ncu: "no instruction" was
+    // the top stall reason of K1 and K8, profiles/r01_*); as a called function the 300 / 600 instructions stay resident
+    // in the instruction cache and the operands travel in registers.
+    static __device__ __noinline__ mont_t mul_call(mont_t a, mont_t b) {
         mont_t r;
-#if ZK_FIELD_PTX
         mul_ptx(r.v, a.v, b.v);
-#else
-        mul_portable(r.v, a.v, b.v);
-#endif
         return r;
+    }
+#endif
+    friend ZK_HD __forceinline__ mont_t operator*(const mont_t &a, const mont_t &b) {
+#if ZK_FIELD_PTX
+#ifdef ZK_INLINE_FIELD_MUL
+        mont_t r;
+        mul_ptx(r.v, a.v, b.v);
+        return r;
+#else
+        return mul_call(a, b);
+#endif
+#else
+        mont_t r;
+        mul_portable(r.v, a.v, b.v);
+        return r;
+#endif
     }
     ZK_HD __forceinline__ mont_t sqr() const { return *this * *this; }
     ZK_HD __forceinline__ mont_t dbl() const { return *this + *this; }

@@ -25,6 +25,8 @@ inline void *dmalloc(size_t bytes) {
 inline void dfree(void *p) { free(p); }
 inline void *hmalloc_pinned(size_t bytes) { return malloc(bytes ? bytes : 1); }
 inline void hfree_pinned(void *p) { free(p); }
+inline void *hmalloc_mapped(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
+inline void *mapped_device_ptr(void *h) { return h; }
 inline void host_pin(void *, size_t) {}
 inline void host_unpin(void *) {}
 inline void h2d(void *dst, const void *src, size_t n, zk_stream_t) { memcpy(dst, src, n); }
@@ -64,6 +66,18 @@ inline void *hmalloc_pinned(size_t bytes) {
     return p;
 }
 inline void hfree_pinned(void *p) { if (p) cudaFreeHost(p); }
+// pinned host memory the device can write directly (zero-copy result mailbox)
+inline void *hmalloc_mapped(size_t bytes) {
+    void *p = nullptr;
+    check(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc(mapped)");
+    memset(p, 0, bytes);
+    return p;
+}
+inline void *mapped_device_ptr(void *h) {
+    void *d = nullptr;
+    check(cudaHostGetDevicePointer(&d, h, 0), "cudaHostGetDevicePointer");
+    return d;
+}
 inline void host_pin(void *p, size_t bytes) { check(cudaHostRegister(p, bytes, cudaHostRegisterDefault), "cudaHostRegister"); }
 inline void host_unpin(void *p) { check(cudaHostUnregister(p), "cudaHostUnregister"); }
 inline void h2d(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s), "h2d"); }

@@ -99,9 +99,20 @@ struct round_args_t {
     round_pair_t pair[2];
     fr_t r;                   // previous_random
     fr_t *partials;           // [2][kMaxGridX][4]
-    uint32_t *counters;       // [2] "CTAs done" tickets, self-resetting
-    fr_t *out;                // [2][4]: (a, b, c, unused) per pair, summed over all CTAs
+    uint32_t *counters;       // [0..1] "CTAs done" tickets per pair, [4] "pairs done"; self-resetting
+    fr_t *out;                // [2][4]: (a, b, c, unused) per pair, summed over all CTAs (may be mapped host memory)
+    uint32_t *flag;           // != nullptr: after the last pair has written `out`, publish `seq` here (mapped host memory)
+    uint32_t seq, n_pairs;    // n_pairs = pairs with n_blocks > 0
 };
+// make the results visible to the host, then raise the sequence number it is spinning on
+__device__ __forceinline__ void publish(uint32_t *flag, uint32_t seq) {
+#if ZK_ON_DEVICE
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(flag) = seq;
+#else
+    *flag = seq;
+#endif
+}
 
 // Per output pair (v0,v1),(m0,m1) of the (folded) tables the round polynomial contributes
 //   a += (m1-m0)(v1-v0),  c += m0 v0,  b += (m1-m0) v0 + m0 (v1-v0) = m1 v1 - a - c
@@ -173,6 +184,13 @@ __global__ void __launch_bounds__(kBlock) k_round_quad(round_args_t A) {
         st_fr(A.out + b * 4 + 1, tot[2] - tot[0] - tot[1]);
         st_fr(A.out + b * 4 + 2, tot[1]);
         A.counters[b] = 0;
+        if (A.flag) {
+            __threadfence();
+            if (atomicAdd(A.counters + 4, 1u) == A.n_pairs - 1) {
+                A.counters[4] = 0;
+                publish(A.flag, A.seq);
+            }
+        }
     }
 }
 
@@ -185,18 +203,25 @@ struct final_fold_args_t {
     uint32_t active[3];
     fr_t r;
     fr_t *out;  // [3][2]
+    uint32_t *flag;   // see round_args_t
+    uint32_t seq;
 };
 __global__ void k_final_fold(final_fold_args_t A) {
     const int i = threadIdx.x >> 1, which = threadIdx.x & 1;
-    if (i >= 3 || !A.active[i]) return;
-    const fr_t *p = which ? A.m_in[i] : A.v_in[i];
-    if (!p) return;
-    fr_t x0 = ld_fr_live(p, 0, A.live[i]);
-    if (A.fold[i]) {
-        fr_t x1 = ld_fr_live(p, 1, A.live[i]);
-        x0 = x0 + A.r * (x1 - x0);
+    const fr_t *p = (i < 3 && A.active[i]) ? (which ? A.m_in[i] : A.v_in[i]) : nullptr;
+    if (p) {
+        fr_t x0 = ld_fr_live(p, 0, A.live[i]);
+        if (A.fold[i]) {
+            fr_t x1 = ld_fr_live(p, 1, A.live[i]);
+            x0 = x0 + A.r * (x1 - x0);
+        }
+        st_fr(A.out + 2 * i + which, x0);
     }
-    st_fr(A.out + 2 * i + which, x0);
+    if (A.flag) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) publish(A.flag, A.seq);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -214,6 +239,8 @@ struct cubic_args_t {
     fr_t *partials;             // [kMaxGridX][4]
     uint32_t *counter;
     fr_t *out;                  // (a, b, c, d)
+    uint32_t *flag;             // see round_args_t
+    uint32_t seq;
 };
 __global__ void __launch_bounds__(kBlock) k_round_cubic(cubic_args_t A) {
     __shared__ fr_t sh[4 * kBlock];
@@ -287,6 +314,7 @@ __global__ void __launch_bounds__(kBlock) k_round_cubic(cubic_args_t A) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) st_fr(A.out + k, tot[k]);
         *A.counter = 0;
+        if (A.flag) publish(A.flag, A.seq);
     }
 }
 
