@@ -40,10 +40,18 @@ __device__ __forceinline__ uint32_t madc_hi(uint32_t x, uint32_t y, uint32_t z) 
 }  // namespace ptx
 #endif
 
+#if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
+// run-time copies of the moduli (not `const`: the compiler must not turn the limbs into immediates, see mul_wide)
+static __device__ __constant__ uint32_t d_fr_MOD_rt[9] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u, 0xffffffffu};
+static __device__ __constant__ uint32_t d_fp_MOD_rt[13] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau, 0xfffcfffdu};
+#endif
 struct fr_cfg {
     static constexpr int N = 8;
     static constexpr uint32_t INV = fr_params::INV;
     static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fr_MOD); }
+#if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
+    static __device__ __forceinline__ const uint32_t *mod_rt() { return d_fr_MOD_rt; }
+#endif
     static ZK_HD __forceinline__ const uint32_t *one() { return ZK_C(fr_ONE); }
     static ZK_HD __forceinline__ const uint32_t *r2() { return ZK_C(fr_R2); }
     static ZK_HD __forceinline__ const uint32_t *r3() { return ZK_C(fr_R3); }
@@ -54,6 +62,9 @@ struct fp_cfg {
     static constexpr int N = 12;
     static constexpr uint32_t INV = fp_params::INV;
     static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fp_MOD); }
+#if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
+    static __device__ __forceinline__ const uint32_t *mod_rt() { return d_fp_MOD_rt; }
+#endif
     static ZK_HD __forceinline__ const uint32_t *one() { return ZK_C(fp_ONE); }
     static ZK_HD __forceinline__ const uint32_t *r2() { return ZK_C(fp_R2); }
     static ZK_HD __forceinline__ const uint32_t *r3() { return ZK_C(fp_R3); }
@@ -276,6 +287,87 @@ template <class C> struct alignas(16) mont_t {
 #pragma unroll
         for (int i = 0; i < N; ++i) r[i] = borrow ? t[i] : d[i];
     }
+
+    // ---- "wide" multiplier: even/odd column accumulators ---------------------------------------------------------------
+    // The pairs  mad.lo.cc a,b,lo ; madc.hi.cc a,b,hi  below are what ptxas turns into ONE  IMAD.WIDE.U32(.X)  each, so a
+    // Montgomery multiplication costs 2 N^2 wide multiply-adds plus O(N) glue instead of 4 N^2 half products and as many
+    // carry fix-ups.  Two accumulators E ("even") and O ("odd", one limb higher) hold the running value  E + 2^32 O; the
+    // products a[j] b_i land in E for even j and in O for odd j, so every wide result is limb-aligned with its
+    // accumulator and each accumulator needs a single carry chain per row.  Dividing by 2^32 after the reduction row is
+    // free: the two accumulators swap roles (the old O is the new E).
+    //   acc[j], acc[j+1] += x[j] * y  for j = 0, 2, ..   (one carry chain; the carry out stays in CC.CF)
+    static __device__ __forceinline__ void wide_cmad(uint32_t *acc, const uint32_t *x, uint32_t y) {
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(x[0]), "r"(y));
+#pragma unroll
+        for (int j = 2; j < N; j += 2)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[j]), "+r"(acc[j + 1]) : "r"(x[j]), "r"(y));
+    }
+    //   acc[j], acc[j+1] = x[j] * y + (acc[j+2], acc[j+3])   (shift down by two limbs while accumulating; consumes CC.CF)
+    static __device__ __forceinline__ void wide_madc_rshift(uint32_t *acc, const uint32_t *x, uint32_t y) {
+#pragma unroll
+        for (int j = 0; j < N - 2; j += 2)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                         : "=r"(acc[j]), "=r"(acc[j + 1]) : "r"(x[j]), "r"(y), "r"(acc[j + 2]), "r"(acc[j + 3]));
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=r"(acc[N - 2]), "=r"(acc[N - 1]) : "r"(x[N - 2]), "r"(y));
+    }
+    //   acc[j], acc[j+1] = x[j] * y
+    static __device__ __forceinline__ void wide_mul(uint32_t *acc, const uint32_t *x, uint32_t y) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2)
+            asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(acc[j]), "=r"(acc[j + 1]) : "r"(x[j]), "r"(y));
+    }
+    // one row: (E + 2^32 O) <- ((E + 2^32 O) / 2^32 [previous row's pending shift]) + a * bi + m * p, with E[0] == 0 after
+    template <bool FIRST> static __device__ __forceinline__ void wide_row(uint32_t *E, uint32_t *O, const uint32_t *a, uint32_t bi,
+                                                                          const uint32_t *pm) {
+        if (FIRST) {
+            wide_mul(O, a + 1, bi);
+            wide_mul(E, a, bi);
+        } else {
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(O[1]));
+            wide_madc_rshift(O, a + 1, bi);
+            wide_cmad(E, a, bi);
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(O[N - 1]));
+        }
+        // m = E[0] * (-p^-1) with the factor read from constant memory: for Fr it is 0xffffffff and, seen as an immediate,
+        // ptxas turns the product into a negation and then no longer fuses the m * p pairs below into IMAD.WIDE
+        uint32_t m;
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(m) : "r"(E[0]), "r"(pm[N]));
+        wide_cmad(O, pm + 1, m);   // no carry out: the running value stays below 2^(32 N + 32) (spare top bit of p)
+        wide_cmad(E, pm, m);
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(O[N - 1]));
+    }
+    static __device__ __forceinline__ void mul_wide(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+        static_assert(N % 2 == 0, "even limb count");
+#ifdef ZK_WIDE_MOD_IMM
+        const uint32_t *p = C::mod();
+#else
+        const uint32_t *p = C::mod_rt();
+#endif
+        uint32_t pm[N + 1];
+#pragma unroll
+        for (int i = 0; i < N; ++i) pm[i] = p[i];
+        pm[N] = C::mod_rt()[N];   // -p^-1 mod 2^32, deliberately opaque to the compiler (see wide_row)
+        uint32_t E[N], O[N];
+        wide_row<true>(E, O, a, b[0], pm);
+        wide_row<false>(O, E, a, b[1], pm);
+#pragma unroll
+        for (int i = 2; i < N; i += 2) {
+            wide_row<false>(E, O, a, b[i], pm);
+            wide_row<false>(O, E, a, b[i + 1], pm);
+        }
+        // merge: value = (E >> 32) + O
+        asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(O[1]));
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(E[i]) : "r"(O[i + 1]));
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[N - 1]));
+        uint32_t d[N];
+        d[0] = ptx::sub_cc(E[0], pm[0]);
+#pragma unroll
+        for (int i = 1; i < N; ++i) d[i] = ptx::subc_cc(E[i], pm[i]);
+        uint32_t borrow = ptx::subc(0, 0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = borrow ? E[i] : d[i];
+    }
 #endif
 
 #if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
@@ -285,7 +377,11 @@ template <class C> struct alignas(16) mont_t {
     // in the instruction cache and the operands travel in registers.
     static __device__ __noinline__ mont_t mul_call(mont_t a, mont_t b) {
         mont_t r;
+#ifdef ZK_FIELD_MUL_CIOS
         mul_ptx(r.v, a.v, b.v);
+#else
+        mul_wide(r.v, a.v, b.v);
+#endif
         return r;
     }
 #endif
@@ -293,7 +389,11 @@ template <class C> struct alignas(16) mont_t {
 #if ZK_FIELD_PTX
 #ifdef ZK_INLINE_FIELD_MUL
         mont_t r;
+#ifdef ZK_FIELD_MUL_CIOS
         mul_ptx(r.v, a.v, b.v);
+#else
+        mul_wide(r.v, a.v, b.v);
+#endif
         return r;
 #else
         return mul_call(a, b);
