@@ -52,7 +52,9 @@ enum { ZK_PROF_FOLD = 0,   /* K1/K2 sumcheck round kernels                    */
        ZK_PROF_MSM,        /* K8/K9 bucket MSM                                */
        ZK_PROF_TABLES,     /* K3 eq / phi tables                              */
        ZK_PROF_DENSE,      /* K4b/K5b/K6 dense contractions, gathers, scatter */
-       ZK_PROF_OTHER, ZK_PROF_CLASSES };
+       ZK_PROF_OTHER,
+       ZK_PROF_FOLD_SMALL, /* K1/K2 rounds on tables < 32 MiB: latency-bound   */
+       ZK_PROF_CLASSES };
 int zk_profile_enable(zk_ctx *ctx, int on);     /* also clears the counters */
 int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_t *bytes);
 

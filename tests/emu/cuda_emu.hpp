@@ -91,6 +91,17 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int srcLane, int w
     return zkemu_shfl(v, src);
 }
 
+// redux.sync: sum over the (full) warp of the calling thread
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    uint64_t *buf = zkemu::exchange_buf();
+    buf[threadIdx.x] = v;
+    zkemu::sync_threads();
+    const unsigned w0 = threadIdx.x & ~31u;
+    unsigned s = 0;
+    for (unsigned t = w0; t < w0 + 32 && t < blockDim.x; ++t) s += (unsigned) buf[t];
+    zkemu::sync_threads();
+    return s;
+}
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

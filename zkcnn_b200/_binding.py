@@ -117,7 +117,7 @@ class Lib:
         return self.dll.zk_last_error().decode()
 
 
-PROF_CLASSES = ("fold", "gates", "msm", "tables", "dense", "other")
+PROF_CLASSES = ("fold", "gates", "msm", "tables", "dense", "other", "fold_small")
 
 
 class Context:

@@ -461,17 +461,17 @@ int zk_bench_fold(zk_ctx *ctx, uint32_t bits, uint32_t iters, int fold, float *m
     round_args_t A;
     memset(&A, 0, sizeof A);
     A.r = fr_t::from_u64(0x1234567887654321ULL);
-    A.partials = ctx->partials.as<fr_t>();
-    A.counters = ctx->counters.as<uint32_t>();
+    A.acc = ctx->round_acc.as<unsigned long long>();
+    A.counter = ctx->counters.as<uint32_t>();
     A.out = ctx->round_out.as<fr_t>();
     round_pair_t &R = A.pair[1];
     R.v_in = v.as<fr_t>(); R.m_in = m.as<fr_t>(); R.v_out = vo.as<fr_t>(); R.m_out = mo.as<fr_t>();
     R.n_in = (uint32_t) n; R.live = (uint32_t) n; R.fold = fold ? 1 : 0;
-    R.n_blocks = grid_for(fold ? n >> 2 : n >> 1);
-    ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks, 2), dim3(kBlock), 0, A);   // warm-up
+    R.n_blocks = round_grid_for(fold ? n >> 2 : n >> 1);
+    ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks), dim3(kRoundBlock), 0, A);   // warm-up
     rt::event_t e0 = rt::event_create(), e1 = rt::event_create();
     rt::event_record(e0, ctx->stream);
-    for (uint32_t i = 0; i < iters; ++i) ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks, 2), dim3(kBlock), 0, A);
+    for (uint32_t i = 0; i < iters; ++i) ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks), dim3(kRoundBlock), 0, A);
     rt::event_record(e1, ctx->stream);
     rt::event_sync(e1);
     *ms = rt::event_elapsed_ms(e0, e1) / iters;

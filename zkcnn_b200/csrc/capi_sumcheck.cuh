@@ -367,6 +367,10 @@ static void ensure_round_scratch(zk_ctx *ctx) {
         ctx->counters.ensure(8 * sizeof(uint32_t));
         rt::dzero(ctx->counters.p, 8 * sizeof(uint32_t), ctx->stream);
     }
+    if (!ctx->round_acc.p) {   // grid-wide limb sums of k_round_quad: zero between launches (the kernel clears them itself)
+        ctx->round_acc.ensure(64 * sizeof(unsigned long long));
+        rt::dzero(ctx->round_acc.p, 64 * sizeof(unsigned long long), ctx->stream);
+    }
     ctx->round_out.ensure(16 * sizeof(fr_t));
     if (!ctx->h_out) ctx->h_out = static_cast<fr_t *>(rt::hmalloc_pinned(16 * sizeof(fr_t)));
     if (!ctx->res_h) {
@@ -375,6 +379,11 @@ static void ensure_round_scratch(zk_ctx *ctx) {
         ctx->flag_h = reinterpret_cast<uint32_t *>(ctx->res_h + 32);
         ctx->flag_d = reinterpret_cast<uint32_t *>(ctx->res_d + 32);
     }
+}
+// CTAs for one table pair of a sumcheck round: one output pair per thread while the machine has room, then grid-stride
+static inline uint32_t round_grid_for(uint64_t live_pairs) {
+    const uint64_t g = (live_pairs + kRoundBlock - 1) / kRoundBlock;
+    return (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(g, kRoundMaxGrid));
 }
 
 // wait until the kernel that was given (flag_d, seq) has published its results into res_h
@@ -410,8 +419,8 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
     round_args_t A;
     memset(&A, 0, sizeof A);
     A.r = prev;
-    A.partials = ctx->partials.as<fr_t>();
-    A.counters = ctx->counters.as<uint32_t>();
+    A.acc = ctx->round_acc.as<unsigned long long>();
+    A.counter = ctx->counters.as<uint32_t>();
     A.out = ctx->res_d;
     final_fold_args_t F;
     memset(&F, 0, sizeof F);
@@ -438,22 +447,24 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
                 R.m_out = table_fold_buf(P.m, n_after);
             }
             const uint32_t live_pairs = first ? (P.live + 1) >> 1 : (P.live + 3) >> 2;
-            R.n_blocks = grid_for(std::max<uint32_t>(1, live_pairs));
-            gx = std::max(gx, R.n_blocks);
+            R.n_blocks = round_grid_for(live_pairs);
+            gx += R.n_blocks;
             quad[b] = any_quad = true;
             fold_bytes += (uint64_t) std::min(P.live, P.n_eval) * (first ? 64 : 96);
         }
     }
     // the last kernel of the round publishes the sequence number the host waits on
     ++ctx->seq;
-    A.n_pairs = (quad[0] ? 1u : 0u) + (quad[1] ? 1u : 0u);
     if (any_final) { F.flag = ctx->flag_d; F.seq = ctx->seq; }
     else { A.flag = ctx->flag_d; A.seq = ctx->seq; }
-    if (any_quad) ZK_KLAUNCH_C(ctx, ZK_PROF_FOLD, fold_bytes, k_round_quad, dim3(gx, 2), dim3(kBlock), 0, A);
+    // rounds that stream less than 32 MiB are bound by launch + reduction latency, not by HBM: they are accounted separately
+    if (any_quad) ZK_KLAUNCH_C(ctx, fold_bytes >= (32u << 20) ? ZK_PROF_FOLD : ZK_PROF_FOLD_SMALL, fold_bytes, k_round_quad, dim3(gx), dim3(kRoundBlock), 0, A);
     if (any_final) ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
     if (any_quad || any_final) wait_mailbox(ctx);
     const fr_t *h_res = ctx->res_h;
     abc[0] = abc[1] = abc[2] = fr_t::zero();
+    if (any_quad)
+        for (int k = 0; k < 3; ++k) abc[k] = h_res[k];   // already summed over both pairs by the kernel
     for (int b = 0; b < 2; ++b) {
         pair_t &P = ctx->pair[b];
         if (fin[b]) {
@@ -463,7 +474,6 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
             P.collapsed = true;
             P.n_eval = 0;
         } else if (quad[b]) {
-            for (int k = 0; k < 3; ++k) abc[k] = abc[k] + h_res[4 * b + k];
             if (!first) {
                 table_advance(P.v);
                 table_advance(P.m);

@@ -100,7 +100,7 @@ struct zk_ctx {
     uint32_t beta_g_entries = 0;
 
     // scratch
-    zk::rt::dbuf half[4], d_r, partials, counters, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
+    zk::rt::dbuf half[4], d_r, partials, counters, round_acc, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
     zk::fr_t *h_out = nullptr;  // pinned mirror of round_out
     // result mailbox of the per-round kernels: mapped pinned host memory the last CTA writes directly, followed by a
     // sequence number; the host spins on the sequence number instead of copying + synchronising the stream

@@ -402,6 +402,20 @@ __global__ void __launch_bounds__(kBlock) k_selftest(uint64_t seed, uint32_t n, 
         bad += ((a + b) - b) != a;
         bad += ((a - b) + b) != a;
         bad += (a * (b + a)) != (x + a * a);
+        // lazy reduction: three unreduced products summed, reduced once == sum of the reduced products
+        fr_lazy_t acc;
+        acc.clear();
+        acc.mac(a, b); acc.mac(a, a); acc.mac(b, b);
+        const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t top[8] = {acc.w[16], 0, 0, 0, 0, 0, 0, 0};
+        bad += montgomery_of_wide<fr_cfg>(acc.w, acc.w + 8, top) != (x + a * a + b * b);
+        // ... and of a sum of field elements seen as a plain integer (chunk 1 of the same formula)
+        uint32_t s9[9];
+        uint64_t cy = 0;
+        for (int k = 0; k < 8; ++k) { cy += (uint64_t) a.v[k] + b.v[k] + x.v[k]; s9[k] = (uint32_t) cy; cy >>= 32; }
+        s9[8] = (uint32_t) cy;
+        top[0] = s9[8];
+        bad += montgomery_of_wide<fr_cfg>(zero8, s9, top) != (a + b + x);
     }
     {
         fp_t x = c * d, y;

@@ -47,6 +47,8 @@ static __device__ __constant__ uint32_t d_fp_MOD_rt[13] = {0xffffaaabu, 0xb9feff
 #endif
 struct fr_cfg {
     static constexpr int N = 8;
+    // r = ... ffffffff 00000001 in its two low limbs: m * r[0] = m and m * r[1] = (m << 32) - m need no multiplier
+    static constexpr bool LOW_LIMBS_SPECIAL = true;
     static constexpr uint32_t INV = fr_params::INV;
     static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fr_MOD); }
 #if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
@@ -60,6 +62,7 @@ struct fr_cfg {
 };
 struct fp_cfg {
     static constexpr int N = 12;
+    static constexpr bool LOW_LIMBS_SPECIAL = false;
     static constexpr uint32_t INV = fp_params::INV;
     static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fp_MOD); }
 #if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
@@ -332,7 +335,30 @@ template <class C> struct alignas(16) mont_t {
         // ptxas turns the product into a negation and then no longer fuses the m * p pairs below into IMAD.WIDE
         uint32_t m;
         asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(m) : "r"(E[0]), "r"(pm[N]));
-        wide_cmad(O, pm + 1, m);   // no carry out: the running value stays below 2^(32 N + 32) (spare top bit of p)
+        wide_reduce_cmad(E, O, pm, m);
+    }
+    // (E + 2^32 O) += m * p, which clears E[0].  No carry out of O: the running value stays below 2^(32 N + 32) (spare
+    // top bit of p).  For Fr the two low limbs of the modulus are 1 and 2^32 - 1, so their products with m are formed on
+    // the integer ALU (which idles while the multiplier pipe is the bottleneck): 6 instead of 8 wide multiply-adds per row.
+    static __device__ __forceinline__ void wide_reduce_cmad(uint32_t *E, uint32_t *O, const uint32_t *pm, uint32_t m) {
+#ifndef ZK_NO_SPECIAL_MODULUS
+        if (C::LOW_LIMBS_SPECIAL) {
+            const uint32_t lo1 = 0u - m, hi1 = m - (m != 0u ? 1u : 0u);   // m * (2^32 - 1) = (m << 32) - m
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(O[0]) : "r"(lo1));
+            asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(O[1]) : "r"(hi1));
+#pragma unroll
+            for (int j = 2; j < N; j += 2)
+                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(O[j]), "+r"(O[j + 1]) : "r"(pm[j + 1]), "r"(m));
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(m));   // m * 1: the sum is 0 mod 2^32 by the choice of m
+            asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(E[1]));
+#pragma unroll
+            for (int j = 2; j < N; j += 2)
+                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(E[j]), "+r"(E[j + 1]) : "r"(pm[j]), "r"(m));
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(O[N - 1]));
+            return;
+        }
+#endif
+        wide_cmad(O, pm + 1, m);
         wide_cmad(E, pm, m);
         asm volatile("addc.u32 %0, %0, 0;" : "+r"(O[N - 1]));
     }
@@ -367,6 +393,35 @@ template <class C> struct alignas(16) mont_t {
         uint32_t borrow = ptx::subc(0, 0);
 #pragma unroll
         for (int i = 0; i < N; ++i) r[i] = borrow ? E[i] : d[i];
+    }
+    // ---- unreduced product t[0 .. 2N-1] = a * b as plain integers (the multiplication half of mul_wide) ----------------
+    // Same even/odd column scheme: `t` collects the limb-aligned wide products, `odd` the ones shifted by one limb.
+    //   row: odd[0..N-1] += x[1,3,..] * y with the top pair written fresh; even[0..N-1] += x[0,2,..] * y; the carry out of
+    //   the even chain lands in odd[N-1], whose fresh high half has room for it.
+    static __device__ __forceinline__ void wide_raw_row(uint32_t *odd, uint32_t *even, const uint32_t *x, uint32_t y) {
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(odd[0]), "+r"(odd[1]) : "r"(x[1]), "r"(y));
+#pragma unroll
+        for (int j = 2; j < N - 2; j += 2)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(odd[j]), "+r"(odd[j + 1]) : "r"(x[j + 1]), "r"(y));
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=r"(odd[N - 2]), "=r"(odd[N - 1]) : "r"(x[N - 1]), "r"(y));
+        wide_cmad(even, x, y);
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(odd[N - 1]));
+    }
+    static __device__ __forceinline__ void mul_raw_wide(uint32_t *t, const uint32_t *a, const uint32_t *b) {
+        uint32_t odd[2 * N - 2];
+        wide_mul(t, a, b[0]);
+        wide_mul(odd, a + 1, b[0]);
+        wide_raw_row(t + 2, odd, a, b[1]);
+#pragma unroll
+        for (int i = 2; i < N; i += 2) {
+            wide_raw_row(odd + i, t + i, a, b[i]);
+            wide_raw_row(t + i + 2, odd + i, a, b[i + 1]);
+        }
+        // merge: t += odd << 32
+        asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(t[1]) : "r"(odd[0]));
+#pragma unroll
+        for (int i = 1; i < 2 * N - 2; ++i) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(t[i + 1]) : "r"(odd[i]));
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(t[2 * N - 1]));
     }
 #endif
 
@@ -499,6 +554,70 @@ template <class C> struct alignas(16) mont_t {
 
 typedef mont_t<fr_cfg> fr_t;
 typedef mont_t<fp_cfg> fp_t;
+
+// ---- lazy reduction ---------------------------------------------------------------------------------------------------
+// A running sum of UNREDUCED products  T = sum_i a_i * b_i  kept as a plain integer of 2N + 1 limbs (one limb of head
+// room: 2^32 products).  Only the multiplication half of a Montgomery multiplication is paid per term; the value
+// T / R mod p that the sum of the reduced products would have is recovered once, by montgomery_of_wide().  Field
+// arithmetic is exact, so the result is the same field element whichever way it is computed.
+template <class C> struct lazy_acc_t {
+    static constexpr int N = C::N;
+    static constexpr int W = 2 * N + 1;
+    uint32_t w[W];
+    ZK_HD __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < W; ++i) w[i] = 0;
+    }
+    ZK_HD __forceinline__ void mac(const mont_t<C> &a, const mont_t<C> &b) {
+#if ZK_FIELD_PTX
+        uint32_t t[2 * N];
+        mont_t<C>::mul_raw_wide(t, a.v, b.v);
+        asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(w[0]) : "r"(t[0]));
+#pragma unroll
+        for (int i = 1; i < 2 * N; ++i) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(w[i]) : "r"(t[i]));
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(w[2 * N]));
+#else
+        uint32_t t[2 * N];
+#pragma unroll
+        for (int i = 0; i < 2 * N; ++i) t[i] = 0;
+        for (int i = 0; i < N; ++i) {
+            uint64_t c = 0;
+            for (int j = 0; j < N; ++j) {
+                uint64_t x = (uint64_t) a.v[j] * b.v[i] + t[i + j] + c;
+                t[i + j] = (uint32_t) x;
+                c = x >> 32;
+            }
+            t[i + N] = (uint32_t) c;
+        }
+        uint64_t c = 0;
+        for (int i = 0; i < 2 * N; ++i) {
+            c += (uint64_t) w[i] + t[i];
+            w[i] = (uint32_t) c;
+            c >>= 32;
+        }
+        w[2 * N] += (uint32_t) c;
+#endif
+    }
+};
+// T / R mod p for a plain integer T = c0 + c1 R + c2 R^2 given as three N-limb chunks:
+//   T / R = c0 / R + c1 + c2 R  =  mul(c0, 1) + mul(c1, R mod p) + mul(c2, R^2 mod p)   with mul(x, y) = x y / R.
+// The multiplier wants operands below p, so each chunk first loses its multiples of p (R / p < 3 for Fr).
+template <class C> ZK_HD inline mont_t<C> montgomery_of_wide(const uint32_t *c0, const uint32_t *c1, const uint32_t *c2) {
+    constexpr int N = C::N;
+    mont_t<C> x[3], y[3];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        x[0].v[i] = c0[i]; x[1].v[i] = c1[i]; x[2].v[i] = c2[i];
+        y[0].v[i] = i == 0 ? 1u : 0u; y[1].v[i] = C::one()[i]; y[2].v[i] = C::r2()[i];
+    }
+    uint32_t pm[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) pm[i] = C::mod()[i];
+    for (int k = 0; k < 3; ++k)
+        while (mont_t<C>::ge_raw(x[k].v, pm)) mont_t<C>::raw_sub(x[k].v, pm);
+    return x[0] * y[0] + x[1] * y[1] + x[2] * y[2];
+}
+typedef lazy_acc_t<fr_cfg> fr_lazy_t;
 
 static_assert(sizeof(fr_t) == 32, "Fr must match mcl's 32-byte layout");
 static_assert(sizeof(fp_t) == 48, "Fp must match mcl's 48-byte layout");

@@ -86,8 +86,75 @@ template <int K> __device__ __forceinline__ void block_sum(fr_t (&acc)[K], fr_t 
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// K1: one sumcheck round on up to two (V, mult) table pairs in one launch (blockIdx.y = pair).
+// Exact grid-wide sum of K 32-bit limbs per thread (K <= 64): the integers  sum_threads limb[k]  for every k.
+//   warp:  redux.sync on the 16-bit halves of each limb (32 x 65535 < 2^21, no overflow) -> one 64-bit sum per limb
+//   CTA :  the warps' sums meet in shared memory, thread k adds them and issues ONE 64-bit red.global.add
+//   grid:  "last CTA finishes": the CTA that draws the last ticket reads the K totals back (and clears them for the
+//          next launch); they are left in sh_tot[0..K-1] for it.  Returns true in that CTA only (uniformly).
+// Used for sums of field elements (K = 8 per element) and of unreduced products (K = 17): integer addition is exact,
+// so the order of the atomics does not matter and the result is bit-reproducible.
 // --------------------------------------------------------------------------------------------------------------------
+template <int K, int BLOCK>
+__device__ __forceinline__ bool grid_limb_sum(const uint32_t (&limb)[K], unsigned long long *acc, uint32_t *counter, uint32_t n_ctas,
+                                              unsigned long long *sh_warp /* [BLOCK/32][K] */, unsigned long long *sh_tot /* [K] */,
+                                              uint32_t *sh_ticket) {
+    static_assert(K <= BLOCK, "one thread per limb in the CTA stage");
+    constexpr int NW = BLOCK / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t lo = __reduce_add_sync(0xffffffffu, limb[k] & 0xffffu);
+        const uint32_t hi = __reduce_add_sync(0xffffffffu, limb[k] >> 16);
+        if (lane == (k & 31)) sh_warp[warp * K + k] = (unsigned long long) lo + ((unsigned long long) hi << 16);
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += sh_warp[w * K + threadIdx.x];
+        if (n_ctas == 1) sh_tot[threadIdx.x] = t;
+        else if (t) atomicAdd(acc + threadIdx.x, t);
+        __threadfence();
+    }
+    __syncthreads();
+    if (n_ctas == 1) return true;
+    if (threadIdx.x == 0) *sh_ticket = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (*sh_ticket != n_ctas - 1) return false;
+    __threadfence();
+    if (threadIdx.x < K) {
+#if ZK_ON_DEVICE
+        sh_tot[threadIdx.x] = __ldcg(acc + threadIdx.x);
+#else
+        sh_tot[threadIdx.x] = acc[threadIdx.x];
+#endif
+        acc[threadIdx.x] = 0;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+    __syncthreads();
+    return true;
+}
+// carry-propagate `n` 64-bit limb sums (weight 2^(32 k)) into n + 2 32-bit limbs
+ZK_HD __forceinline__ void limb_sums_normalise(const unsigned long long *tot, int n, uint32_t *out) {
+    unsigned long long c = 0;
+    for (int k = 0; k < n; ++k) {
+        const unsigned long long lo = (tot[k] & 0xffffffffull) + (c & 0xffffffffull);
+        out[k] = (uint32_t) lo;
+        c = (tot[k] >> 32) + (c >> 32) + (lo >> 32);
+    }
+    out[n] = (uint32_t) c;
+    out[n + 1] = (uint32_t) (c >> 32);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// K1: one sumcheck round on up to two (V, mult) table pairs in one launch.  CTAs [0, pair[0].n_blocks) work on pair 0,
+// the rest on pair 1; the round polynomial that leaves the device is the SUM over both pairs (the caller adds them
+// anyway, src/prover.cpp:368-383).
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int kRoundBlock = 128;                 // 4 warps: one per SM sub-partition
+constexpr int kRoundMaxGrid = ZK_SM_COUNT * 4;   // 4 resident CTAs per SM (<= 128 registers per thread)
+constexpr int kRoundLimbs = 3 * fr_lazy_t::W;    // three unreduced sums of 17 limbs
+
 struct round_pair_t {
     const fr_t *v_in, *m_in;  // current tables, n_in evaluations each, entries >= live are zero
     fr_t *v_out, *m_out;      // folded tables (n_in / 2); unused when fold == 0
@@ -98,11 +165,11 @@ struct round_pair_t {
 struct round_args_t {
     round_pair_t pair[2];
     fr_t r;                   // previous_random
-    fr_t *partials;           // [2][kMaxGridX][4]
-    uint32_t *counters;       // [0..1] "CTAs done" tickets per pair, [4] "pairs done"; self-resetting
-    fr_t *out;                // [2][4]: (a, b, c, unused) per pair, summed over all CTAs (may be mapped host memory)
-    uint32_t *flag;           // != nullptr: after the last pair has written `out`, publish `seq` here (mapped host memory)
-    uint32_t seq, n_pairs;    // n_pairs = pairs with n_blocks > 0
+    unsigned long long *acc;  // [kRoundLimbs] grid-wide limb sums: zero on entry, zero again on exit
+    uint32_t *counter;        // "CTAs done" ticket; self-resetting
+    fr_t *out;                // (a, b, c), summed over both pairs (may be mapped host memory)
+    uint32_t *flag;           // != nullptr: after `out` is written, publish `seq` here (mapped host memory)
+    uint32_t seq;
 };
 // make the results visible to the host, then raise the sequence number it is spinning on
 __device__ __forceinline__ void publish(uint32_t *flag, uint32_t seq) {
@@ -116,81 +183,94 @@ __device__ __forceinline__ void publish(uint32_t *flag, uint32_t seq) {
 
 // Per output pair (v0,v1),(m0,m1) of the (folded) tables the round polynomial contributes
 //   a += (m1-m0)(v1-v0),  c += m0 v0,  b += (m1-m0) v0 + m0 (v1-v0) = m1 v1 - a - c
-// (linear_poly * linear_poly, src/polynomial.cpp:116-118, evaluated Karatsuba-style with 3 products).
-__global__ void __launch_bounds__(kBlock) k_round_quad(round_args_t A) {
-    __shared__ fr_t sh[3 * kBlock];
-    __shared__ uint32_t ticket;
-    const int b = blockIdx.y;
-    const round_pair_t P = A.pair[b];
-    if (blockIdx.x >= P.n_blocks) return;
-    const uint32_t stride = P.n_blocks * kBlock;
-    fr_t acc[3] = {fr_t::zero(), fr_t::zero(), fr_t::zero()};  // A, C, E
-    if (P.fold) {
-        const uint32_t n_pairs = P.n_in >> 2;
-        const uint32_t live_pairs = (P.live + 3) >> 2;
+// (linear_poly * linear_poly, src/polynomial.cpp:116-118, evaluated Karatsuba-style with 3 products).  The three sums
+// are accumulated unreduced (fr_lazy_t): the four fold multiplications per output pair are full Montgomery
+// multiplications (their results are stored), the three products only pay the multiplication half.
+__global__ void __launch_bounds__(kRoundBlock, 4) k_round_quad(round_args_t A) {
+    __shared__ unsigned long long sh_warp[(kRoundBlock / 32) * kRoundLimbs];
+    __shared__ unsigned long long sh_tot[kRoundLimbs];
+    __shared__ uint32_t sh_ticket;
+    __shared__ fr_t sh_fr[12];
+    const uint32_t nb0 = A.pair[0].n_blocks, nb = nb0 + A.pair[1].n_blocks;
+    const bool second = blockIdx.x >= nb0;
+    const fr_t *v_in = second ? A.pair[1].v_in : A.pair[0].v_in, *m_in = second ? A.pair[1].m_in : A.pair[0].m_in;
+    fr_t *v_out = second ? A.pair[1].v_out : A.pair[0].v_out, *m_out = second ? A.pair[1].m_out : A.pair[0].m_out;
+    const uint32_t n_in = second ? A.pair[1].n_in : A.pair[0].n_in, live = second ? A.pair[1].live : A.pair[0].live;
+    const uint32_t fold = second ? A.pair[1].fold : A.pair[0].fold;
+    const uint32_t bx = second ? blockIdx.x - nb0 : blockIdx.x;
+    const uint32_t stride = (second ? A.pair[1].n_blocks : nb0) * kRoundBlock;
+    fr_lazy_t acc[3];  // A, C, E
+    acc[0].clear(); acc[1].clear(); acc[2].clear();
+    if (fold) {
+        const uint32_t n_pairs = n_in >> 2;
+        const uint32_t live_pairs = (live + 3) >> 2;
         const fr_t r = A.r;
-        for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
+        for (uint32_t i = bx * kRoundBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
             const uint32_t base = i << 2;
-            fr_t x0 = ld_fr_live(P.v_in, base, P.live), x1 = ld_fr_live(P.v_in, base + 1, P.live);
-            fr_t x2 = ld_fr_live(P.v_in, base + 2, P.live), x3 = ld_fr_live(P.v_in, base + 3, P.live);
-            fr_t v0 = x0 + r * (x1 - x0);
-            fr_t v1 = x2 + r * (x3 - x2);
-            st_fr(P.v_out + 2 * i, v0);
-            st_fr(P.v_out + 2 * i + 1, v1);
-            x0 = ld_fr_live(P.m_in, base, P.live); x1 = ld_fr_live(P.m_in, base + 1, P.live);
-            x2 = ld_fr_live(P.m_in, base + 2, P.live); x3 = ld_fr_live(P.m_in, base + 3, P.live);
-            fr_t m0 = x0 + r * (x1 - x0);
-            fr_t m1 = x2 + r * (x3 - x2);
-            st_fr(P.m_out + 2 * i, m0);
-            st_fr(P.m_out + 2 * i + 1, m1);
-            acc[0] = acc[0] + (m1 - m0) * (v1 - v0);
-            acc[1] = acc[1] + m0 * v0;
-            acc[2] = acc[2] + m1 * v1;
+            fr_t x0 = ld_fr_live(v_in, base, live), x1 = ld_fr_live(v_in, base + 1, live);
+            fr_t x2 = ld_fr_live(v_in, base + 2, live), x3 = ld_fr_live(v_in, base + 3, live);
+            fr_t y0 = ld_fr_live(m_in, base, live), y1 = ld_fr_live(m_in, base + 1, live);
+            fr_t y2 = ld_fr_live(m_in, base + 2, live), y3 = ld_fr_live(m_in, base + 3, live);
+            const fr_t v0 = x0 + r * (x1 - x0);
+            const fr_t v1 = x2 + r * (x3 - x2);
+            st_fr(v_out + 2 * i, v0);
+            st_fr(v_out + 2 * i + 1, v1);
+            const fr_t m0 = y0 + r * (y1 - y0);
+            const fr_t m1 = y2 + r * (y3 - y2);
+            st_fr(m_out + 2 * i, m0);
+            st_fr(m_out + 2 * i + 1, m1);
+            acc[0].mac(m1 - m0, v1 - v0);
+            acc[1].mac(m0, v0);
+            acc[2].mac(m1, v1);
         }
     } else {
-        const uint32_t n_pairs = P.n_in >> 1;
-        const uint32_t live_pairs = (P.live + 1) >> 1;
-        for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
-            fr_t v0 = ld_fr_live(P.v_in, 2 * i, P.live), v1 = ld_fr_live(P.v_in, 2 * i + 1, P.live);
-            fr_t m0 = ld_fr_live(P.m_in, 2 * i, P.live), m1 = ld_fr_live(P.m_in, 2 * i + 1, P.live);
-            acc[0] = acc[0] + (m1 - m0) * (v1 - v0);
-            acc[1] = acc[1] + m0 * v0;
-            acc[2] = acc[2] + m1 * v1;
+        const uint32_t n_pairs = n_in >> 1;
+        const uint32_t live_pairs = (live + 1) >> 1;
+        for (uint32_t i = bx * kRoundBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
+            const fr_t v0 = ld_fr_live(v_in, 2 * i, live), v1 = ld_fr_live(v_in, 2 * i + 1, live);
+            const fr_t m0 = ld_fr_live(m_in, 2 * i, live), m1 = ld_fr_live(m_in, 2 * i + 1, live);
+            acc[0].mac(m1 - m0, v1 - v0);
+            acc[1].mac(m0, v0);
+            acc[2].mac(m1, v1);
         }
     }
-    block_sum<3>(acc, sh);
-    fr_t *part = A.partials + (size_t) b * kMaxGridX * 4;
-    if (threadIdx.x == 0) {
-        st_fr(part + blockIdx.x * 4 + 0, acc[0]);
-        st_fr(part + blockIdx.x * 4 + 1, acc[1]);
-        st_fr(part + blockIdx.x * 4 + 2, acc[2]);
-        __threadfence();
-        ticket = atomicAdd(A.counters + b, 1u);
-    }
-    __syncthreads();
-    if (ticket != P.n_blocks - 1) return;
-    // last CTA of this pair: fold the per-CTA partials into the round polynomial
-    __threadfence();
-    fr_t tot[3] = {fr_t::zero(), fr_t::zero(), fr_t::zero()};
-    for (uint32_t i = threadIdx.x; i < P.n_blocks; i += kBlock) {
-        tot[0] = tot[0] + ld_fr_cg(part + i * 4 + 0);
-        tot[1] = tot[1] + ld_fr_cg(part + i * 4 + 1);
-        tot[2] = tot[2] + ld_fr_cg(part + i * 4 + 2);
-    }
-    __syncthreads();
-    block_sum<3>(tot, sh);
-    if (threadIdx.x == 0) {
-        st_fr(A.out + b * 4 + 0, tot[0]);
-        st_fr(A.out + b * 4 + 1, tot[2] - tot[0] - tot[1]);
-        st_fr(A.out + b * 4 + 2, tot[1]);
-        A.counters[b] = 0;
-        if (A.flag) {
-            __threadfence();
-            if (atomicAdd(A.counters + 4, 1u) == A.n_pairs - 1) {
-                A.counters[4] = 0;
-                publish(A.flag, A.seq);
-            }
+    uint32_t limb[kRoundLimbs];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < fr_lazy_t::W; ++j) limb[k * fr_lazy_t::W + j] = acc[k].w[j];
+    if (!grid_limb_sum<kRoundLimbs, kRoundBlock>(limb, A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
+    // last CTA: thread (k, c) turns chunk c of sum k into its share of the field element, then three threads add up
+    if (threadIdx.x < 9) {
+        const int k = threadIdx.x / 3, c = threadIdx.x % 3;
+        uint32_t t[fr_lazy_t::W + 2 + 5];
+        limb_sums_normalise(sh_tot + k * fr_lazy_t::W, fr_lazy_t::W, t);
+#pragma unroll
+        for (int j = fr_lazy_t::W + 2; j < fr_lazy_t::W + 7; ++j) t[j] = 0;
+        fr_t x, y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x.v[j] = t[8 * c + j];
+            y.v[j] = c == 0 ? (j == 0 ? 1u : 0u) : c == 1 ? fr_cfg::one()[j] : fr_cfg::r2()[j];
         }
+        uint32_t pm[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pm[j] = fr_cfg::mod()[j];
+        while (fr_t::ge_raw(x.v, pm)) fr_t::raw_sub(x.v, pm);   // the multiplier wants operands below r (at most two steps)
+        st_fr(sh_fr + threadIdx.x, x * y);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const fr_t s = sh_fr[3 * threadIdx.x] + sh_fr[3 * threadIdx.x + 1] + sh_fr[3 * threadIdx.x + 2];
+        st_fr(sh_fr + 9 + threadIdx.x, s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const fr_t a = sh_fr[9], c = sh_fr[10], e = sh_fr[11];
+        st_fr(A.out + 0, a);
+        st_fr(A.out + 1, e - a - c);
+        st_fr(A.out + 2, c);
+        if (A.flag) publish(A.flag, A.seq);
     }
 }
 
