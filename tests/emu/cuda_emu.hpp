@@ -92,13 +92,14 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int srcLane, int w
 }
 
 // redux.sync: sum over the (full) warp of the calling thread
-static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     uint64_t *buf = zkemu::exchange_buf();
     buf[threadIdx.x] = v;
     zkemu::sync_threads();
     const unsigned w0 = threadIdx.x & ~31u;
     unsigned s = 0;
-    for (unsigned t = w0; t < w0 + 32 && t < blockDim.x; ++t) s += (unsigned) buf[t];
+    for (unsigned t = w0; t < w0 + 32 && t < blockDim.x; ++t)
+        if (mask >> (t - w0) & 1u) s += (unsigned) buf[t];
     zkemu::sync_threads();
     return s;
 }

@@ -467,11 +467,17 @@ int zk_bench_fold(zk_ctx *ctx, uint32_t bits, uint32_t iters, int fold, float *m
     round_pair_t &R = A.pair[1];
     R.v_in = v.as<fr_t>(); R.m_in = m.as<fr_t>(); R.v_out = vo.as<fr_t>(); R.m_out = mo.as<fr_t>();
     R.n_in = (uint32_t) n; R.live = (uint32_t) n; R.fold = fold ? 1 : 0;
-    R.n_blocks = round_grid_for(fold ? n >> 2 : n >> 1);
-    ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks), dim3(kRoundBlock), 0, A);   // warm-up
+    const uint64_t out_pairs = fold ? n >> 2 : n >> 1;
+    const bool thin = out_pairs <= kThinMaxPairs;   // same choice as round_quadratic()
+    R.n_blocks = thin ? (uint32_t) ((out_pairs + kRoundBlock / 4 - 1) / (kRoundBlock / 4)) : round_grid_for(out_pairs);
+    auto launch = [&]() {
+        if (thin) ZK_KLAUNCH(ctx, k_round_quad_thin, dim3(R.n_blocks), dim3(kRoundBlock), 0, A);
+        else ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks), dim3(kRoundBlock), 0, A);
+    };
+    launch();   // warm-up
     rt::event_t e0 = rt::event_create(), e1 = rt::event_create();
     rt::event_record(e0, ctx->stream);
-    for (uint32_t i = 0; i < iters; ++i) ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks), dim3(kRoundBlock), 0, A);
+    for (uint32_t i = 0; i < iters; ++i) launch();
     rt::event_record(e1, ctx->stream);
     rt::event_sync(e1);
     *ms = rt::event_elapsed_ms(e0, e1) / iters;

@@ -374,12 +374,25 @@ static void ensure_round_scratch(zk_ctx *ctx) {
     ctx->round_out.ensure(16 * sizeof(fr_t));
     if (!ctx->h_out) ctx->h_out = static_cast<fr_t *>(rt::hmalloc_pinned(16 * sizeof(fr_t)));
     if (!ctx->res_h) {
-        ctx->res_h = static_cast<fr_t *>(rt::hmalloc_mapped(32 * sizeof(fr_t) + 64));
+        ctx->res_h = static_cast<fr_t *>(rt::hmalloc_mapped(32 * sizeof(fr_t) + 256));
+        memset(ctx->res_h, 0, 32 * sizeof(fr_t) + 256);
         ctx->res_d = static_cast<fr_t *>(rt::mapped_device_ptr(ctx->res_h));
         ctx->flag_h = reinterpret_cast<uint32_t *>(ctx->res_h + 32);
         ctx->flag_d = reinterpret_cast<uint32_t *>(ctx->res_d + 32);
+        ctx->tag_h = reinterpret_cast<uint32_t *>(ctx->res_h + 36);   // 128 bytes, 128-byte aligned: the tagged mailbox of k_round_quad
+        ctx->tag_d = reinterpret_cast<uint32_t *>(ctx->res_d + 36);
     }
 }
+// k_round_quad_thin up to this many output pairs per table (default 2^14: 2 x 512 CTAs of 128 threads, one pass);
+// ZK_THIN_MAX_PAIRS overrides it for experiments (0 = never)
+static inline uint32_t thin_max_pairs() {
+    static const uint32_t v = [] {
+        const char *e = getenv("ZK_THIN_MAX_PAIRS");
+        return e ? (uint32_t) strtoul(e, nullptr, 0) : 1u << 14;
+    }();
+    return v;
+}
+#define kThinMaxPairs (thin_max_pairs())
 // CTAs for one table pair of a sumcheck round: one output pair per thread while the machine has room, then grid-stride
 static inline uint32_t round_grid_for(uint64_t live_pairs) {
     const uint64_t g = (live_pairs + kRoundBlock - 1) / kRoundBlock;
@@ -411,6 +424,38 @@ static void wait_mailbox(zk_ctx *ctx) {
     if (*ctx->flag_h != ctx->seq) throw rt::error("result mailbox out of sequence");
 }
 
+// wait for the eight tagged words of publish_tagged() and unpack (a, b, c)
+static void wait_tagged(zk_ctx *ctx, fr_t abc[3]) {
+    volatile uint32_t *box = ctx->tag_h;
+#ifndef ZK_EMU
+    uint64_t spins = 0;
+    timespec t0{};
+    for (;;) {
+        bool all = true;
+        for (int j = 0; j < 8; ++j) all = all && box[4 * j + 3] == ctx->seq;
+        if (all) break;
+        if (++spins == 200000) clock_gettime(CLOCK_MONOTONIC, &t0);
+        else if (spins > 200000 && (spins & 0xffff) == 0) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) rt::check(q, "sumcheck round kernel");
+            timespec t1;
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            if (t1.tv_sec - t0.tv_sec > 20) throw rt::error("sumcheck round kernel did not publish its result within 20 s");
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+#endif
+    uint32_t w[24];
+    for (int j = 0; j < 8; ++j) {
+        if (box[4 * j + 3] != ctx->seq) throw rt::error("result mailbox out of sequence");
+        w[3 * j] = box[4 * j]; w[3 * j + 1] = box[4 * j + 1]; w[3 * j + 2] = box[4 * j + 2];
+    }
+    for (int k = 0; k < 3; ++k) memcpy(abc[k].v, w + 8 * k, 32);
+}
+
 // One call of sumcheckUpdateEach for both table pairs (src/prover.cpp:396-426).  `mask` selects the pairs that take part
 // (Liu: only pair 1).  Returns the sum of the pairs' round polynomials in abc[3]; add_term is updated for collapses.
 static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t abc[3]) {
@@ -428,7 +473,7 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
     F.out = ctx->res_d + 8;
     bool any_quad = false, any_final = false;
     bool quad[2] = {false, false}, fin[2] = {false, false};
-    uint32_t gx = 0;
+    uint32_t gx = 0, max_live_pairs = 0, pairs_of[2] = {0, 0};
     uint64_t fold_bytes = 0;   // algorithmic: read V and mult (live entries), write both halves
     for (int b = 0; b < 2; ++b) {
         pair_t &P = ctx->pair[b];
@@ -447,8 +492,8 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
                 R.m_out = table_fold_buf(P.m, n_after);
             }
             const uint32_t live_pairs = first ? (P.live + 1) >> 1 : (P.live + 3) >> 2;
-            R.n_blocks = round_grid_for(live_pairs);
-            gx += R.n_blocks;
+            max_live_pairs = std::max(max_live_pairs, live_pairs);
+            pairs_of[b] = live_pairs;
             quad[b] = any_quad = true;
             fold_bytes += (uint64_t) std::min(P.live, P.n_eval) * (first ? 64 : 96);
         }
@@ -456,15 +501,27 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
     // the last kernel of the round publishes the sequence number the host waits on
     ++ctx->seq;
     if (any_final) { F.flag = ctx->flag_d; F.seq = ctx->seq; }
-    else { A.flag = ctx->flag_d; A.seq = ctx->seq; }
+    else { A.tagged = reinterpret_cast<uint4 *>(ctx->tag_d); A.seq = ctx->seq; }
+    // tables up to 2^16 entries: four lanes per output pair (latency), beyond: one thread per output pair, grid-stride (throughput)
+    const bool thin = max_live_pairs <= kThinMaxPairs;
+    for (int b = 0; b < 2; ++b)
+        if (quad[b]) {
+            const uint32_t live_pairs = std::max(1u, std::min(pairs_of[b], first ? A.pair[b].n_in >> 1 : A.pair[b].n_in >> 2));
+            A.pair[b].n_blocks = thin ? (live_pairs + kRoundBlock / 4 - 1) / (kRoundBlock / 4) : round_grid_for(live_pairs);
+            gx += A.pair[b].n_blocks;
+        }
     // rounds that stream less than 32 MiB are bound by launch + reduction latency, not by HBM: they are accounted separately
-    if (any_quad) ZK_KLAUNCH_C(ctx, fold_bytes >= (32u << 20) ? ZK_PROF_FOLD : ZK_PROF_FOLD_SMALL, fold_bytes, k_round_quad, dim3(gx), dim3(kRoundBlock), 0, A);
+    const int cls = fold_bytes >= (32u << 20) ? ZK_PROF_FOLD : ZK_PROF_FOLD_SMALL;
+    if (any_quad && thin) ZK_KLAUNCH_C(ctx, cls, fold_bytes, k_round_quad_thin, dim3(gx), dim3(kRoundBlock), 0, A);
+    else if (any_quad) ZK_KLAUNCH_C(ctx, cls, fold_bytes, k_round_quad, dim3(gx), dim3(kRoundBlock), 0, A);
     if (any_final) ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
-    if (any_quad || any_final) wait_mailbox(ctx);
     const fr_t *h_res = ctx->res_h;
     abc[0] = abc[1] = abc[2] = fr_t::zero();
-    if (any_quad)
-        for (int k = 0; k < 3; ++k) abc[k] = h_res[k];   // already summed over both pairs by the kernel
+    if (any_final) {
+        wait_mailbox(ctx);
+        if (any_quad)
+            for (int k = 0; k < 3; ++k) abc[k] = h_res[k];   // already summed over both pairs by the kernel
+    } else if (any_quad) wait_tagged(ctx, abc);
     for (int b = 0; b < 2; ++b) {
         pair_t &P = ctx->pair[b];
         if (fin[b]) {

@@ -106,6 +106,7 @@ struct zk_ctx {
     // sequence number; the host spins on the sequence number instead of copying + synchronising the stream
     zk::fr_t *res_h = nullptr, *res_d = nullptr;          // [32] host / device view
     uint32_t *flag_h = nullptr, *flag_d = nullptr;
+    uint32_t *tag_h = nullptr, *tag_d = nullptr;          // [32] tagged mailbox (publish_tagged)
     uint32_t seq = 0;
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 

@@ -94,19 +94,12 @@ template <int K> __device__ __forceinline__ void block_sum(fr_t (&acc)[K], fr_t 
 // Used for sums of field elements (K = 8 per element) and of unreduced products (K = 17): integer addition is exact,
 // so the order of the atomics does not matter and the result is bit-reproducible.
 // --------------------------------------------------------------------------------------------------------------------
+// CTA + grid stages: sh_warp[w * K + k] holds warp w's sum of limb k (written by the caller, no barrier yet)
 template <int K, int BLOCK>
-__device__ __forceinline__ bool grid_limb_sum(const uint32_t (&limb)[K], unsigned long long *acc, uint32_t *counter, uint32_t n_ctas,
-                                              unsigned long long *sh_warp /* [BLOCK/32][K] */, unsigned long long *sh_tot /* [K] */,
-                                              uint32_t *sh_ticket) {
+__device__ __forceinline__ bool grid_limb_sum_finish(unsigned long long *acc, uint32_t *counter, uint32_t n_ctas, unsigned long long *sh_warp /* [BLOCK/32][K] */,
+                                                     unsigned long long *sh_tot /* [K] */, uint32_t *sh_ticket) {
     static_assert(K <= BLOCK, "one thread per limb in the CTA stage");
     constexpr int NW = BLOCK / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const uint32_t lo = __reduce_add_sync(0xffffffffu, limb[k] & 0xffffu);
-        const uint32_t hi = __reduce_add_sync(0xffffffffu, limb[k] >> 16);
-        if (lane == (k & 31)) sh_warp[warp * K + k] = (unsigned long long) lo + ((unsigned long long) hi << 16);
-    }
     __syncthreads();
     if (threadIdx.x < K) {
         unsigned long long t = 0;
@@ -133,6 +126,19 @@ __device__ __forceinline__ bool grid_limb_sum(const uint32_t (&limb)[K], unsigne
     if (threadIdx.x == 0) *counter = 0;
     __syncthreads();
     return true;
+}
+template <int K, int BLOCK>
+__device__ __forceinline__ bool grid_limb_sum(const uint32_t (&limb)[K], unsigned long long *acc, uint32_t *counter, uint32_t n_ctas,
+                                              unsigned long long *sh_warp /* [BLOCK/32][K] */, unsigned long long *sh_tot /* [K] */,
+                                              uint32_t *sh_ticket) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t lo = __reduce_add_sync(0xffffffffu, limb[k] & 0xffffu);
+        const uint32_t hi = __reduce_add_sync(0xffffffffu, limb[k] >> 16);
+        if (lane == (k & 31)) sh_warp[warp * K + k] = (unsigned long long) lo + ((unsigned long long) hi << 16);
+    }
+    return grid_limb_sum_finish<K, BLOCK>(acc, counter, n_ctas, sh_warp, sh_tot, sh_ticket);
 }
 // carry-propagate `n` 64-bit limb sums (weight 2^(32 k)) into n + 2 32-bit limbs
 ZK_HD __forceinline__ void limb_sums_normalise(const unsigned long long *tot, int n, uint32_t *out) {
@@ -170,7 +176,26 @@ struct round_args_t {
     fr_t *out;                // (a, b, c), summed over both pairs (may be mapped host memory)
     uint32_t *flag;           // != nullptr: after `out` is written, publish `seq` here (mapped host memory)
     uint32_t seq;
+    uint4 *tagged;            // != nullptr: publish (a, b, c) as 8 self-validating 16-byte words instead (see publish_tagged)
 };
+// Fence-free result mailbox: the 24 result words leave as eight 16-byte stores {w0, w1, w2, seq}.  Each store reaches
+// host memory as one write, so a word whose tag equals the awaited sequence number carries valid data: no
+// __threadfence_system() (1.4 us on B200, tools/latbench.cu) between data and flag.
+__device__ __forceinline__ void publish_tagged(uint4 *box, const fr_t &a, const fr_t &b, const fr_t &c, uint32_t seq) {
+    uint32_t w[24];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { w[j] = a.v[j]; w[8 + j] = b.v[j]; w[16 + j] = c.v[j]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#if ZK_ON_DEVICE
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(box + j), "r"(w[3 * j]), "r"(w[3 * j + 1]), "r"(w[3 * j + 2]), "r"(seq) : "memory");
+#else
+        uint4 q;
+        q.x = w[3 * j]; q.y = w[3 * j + 1]; q.z = w[3 * j + 2]; q.w = seq;
+        box[j] = q;
+#endif
+    }
+}
 // make the results visible to the host, then raise the sequence number it is spinning on
 __device__ __forceinline__ void publish(uint32_t *flag, uint32_t seq) {
 #if ZK_ON_DEVICE
@@ -179,6 +204,46 @@ __device__ __forceinline__ void publish(uint32_t *flag, uint32_t seq) {
 #else
     *flag = seq;
 #endif
+}
+
+// Last CTA of a round kernel: sh_tot holds the three exact limb sums (A, C, E; 17 limbs each, weight 2^(32 j)).
+// Thread (k, c) turns chunk c of sum k into its share of the field element, three threads add up, thread 0 publishes
+// (a, b, c) = (A, E - A - C, C).
+__device__ __forceinline__ void round_quad_publish(const round_args_t &A, const unsigned long long *sh_tot, fr_t *sh_fr /* [12] */) {
+    if (threadIdx.x < 9) {
+        const int k = threadIdx.x / 3, c = threadIdx.x % 3;
+        uint32_t t[fr_lazy_t::W + 2 + 5];
+        limb_sums_normalise(sh_tot + k * fr_lazy_t::W, fr_lazy_t::W, t);
+#pragma unroll
+        for (int j = fr_lazy_t::W + 2; j < fr_lazy_t::W + 7; ++j) t[j] = 0;
+        fr_t x, y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x.v[j] = t[8 * c + j];
+            y.v[j] = c == 0 ? (j == 0 ? 1u : 0u) : c == 1 ? fr_cfg::one()[j] : fr_cfg::r2()[j];
+        }
+        uint32_t pm[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pm[j] = fr_cfg::mod()[j];
+        while (fr_t::ge_raw(x.v, pm)) fr_t::raw_sub(x.v, pm);   // the multiplier wants operands below r (at most two steps)
+        st_fr(sh_fr + threadIdx.x, x * y);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const fr_t s = sh_fr[3 * threadIdx.x] + sh_fr[3 * threadIdx.x + 1] + sh_fr[3 * threadIdx.x + 2];
+        st_fr(sh_fr + 9 + threadIdx.x, s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const fr_t a = sh_fr[9], c = sh_fr[10], e = sh_fr[11];
+        if (A.tagged) publish_tagged(A.tagged, a, e - a - c, c, A.seq);
+        else {
+            st_fr(A.out + 0, a);
+            st_fr(A.out + 1, e - a - c);
+            st_fr(A.out + 2, c);
+            if (A.flag) publish(A.flag, A.seq);
+        }
+    }
 }
 
 // Per output pair (v0,v1),(m0,m1) of the (folded) tables the round polynomial contributes
@@ -240,38 +305,84 @@ __global__ void __launch_bounds__(kRoundBlock, 4) k_round_quad(round_args_t A) {
 #pragma unroll
         for (int j = 0; j < fr_lazy_t::W; ++j) limb[k * fr_lazy_t::W + j] = acc[k].w[j];
     if (!grid_limb_sum<kRoundLimbs, kRoundBlock>(limb, A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
-    // last CTA: thread (k, c) turns chunk c of sum k into its share of the field element, then three threads add up
-    if (threadIdx.x < 9) {
-        const int k = threadIdx.x / 3, c = threadIdx.x % 3;
-        uint32_t t[fr_lazy_t::W + 2 + 5];
-        limb_sums_normalise(sh_tot + k * fr_lazy_t::W, fr_lazy_t::W, t);
+    round_quad_publish(A, sh_tot, sh_fr);
+}
+
+// K1, latency-bound rounds (tables up to 2^16 entries): the seven multiplications of an output pair are spread over
+// FOUR lanes, so the critical path of a round is one fold multiplication + one unreduced product instead of seven
+// multiplications in a row.  Lane roles within a quad (lanes 4q .. 4q+3 work on output pair q):
+//   fold round:   role 0: v0 = fold(V[4q], V[4q+1])   role 1: v1 = fold(V[4q+2], V[4q+3])   role 2: m0   role 3: m1
+//                 then three shuffle exchanges hand role 0 (v0, m0) -> C, role 1 (v1, m1) -> E, role 2 (dm, dv) -> A
+//   first round:  role 0: (v0, m0) -> C   role 1: (v1, m1) -> E   role 2: loads all four -> A
+// Each lane's unreduced product goes through role-masked redux into the same exact limb sums as k_round_quad.
+__global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A) {
+    __shared__ unsigned long long sh_warp[(kRoundBlock / 32) * kRoundLimbs];
+    __shared__ unsigned long long sh_tot[kRoundLimbs];
+    __shared__ uint32_t sh_ticket;
+    __shared__ fr_t sh_fr[12];
+    const uint32_t nb0 = A.pair[0].n_blocks, nb = nb0 + A.pair[1].n_blocks;
+    const bool second = blockIdx.x >= nb0;
+    const fr_t *v_in = second ? A.pair[1].v_in : A.pair[0].v_in, *m_in = second ? A.pair[1].m_in : A.pair[0].m_in;
+    fr_t *v_out = second ? A.pair[1].v_out : A.pair[0].v_out, *m_out = second ? A.pair[1].m_out : A.pair[0].m_out;
+    const uint32_t n_in = second ? A.pair[1].n_in : A.pair[0].n_in, live = second ? A.pair[1].live : A.pair[0].live;
+    const uint32_t fold = second ? A.pair[1].fold : A.pair[0].fold;
+    const uint32_t bx = second ? blockIdx.x - nb0 : blockIdx.x;
+    const uint32_t stride = (second ? A.pair[1].n_blocks : nb0) * (kRoundBlock / 4);   // output pairs per grid pass
+    const uint32_t role = threadIdx.x & 3u, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t lim_n = fold ? n_in >> 2 : n_in >> 1, lim_l = fold ? (live + 3) >> 2 : (live + 1) >> 1;
+    const uint32_t limit = lim_n < lim_l ? lim_n : lim_l;
+    fr_lazy_t acc;
+    acc.clear();
+    const fr_t r = A.r;
+    // the trip count is CTA-uniform (the CTA's first pair decides): every lane takes part in the shuffles
+    for (uint32_t q0 = bx * (kRoundBlock / 4); q0 < limit; q0 += stride) {
+        const uint32_t q = q0 + (threadIdx.x >> 2);
+        const bool on = q < limit;
+        fr_t a_op = fr_t::zero(), b_op = fr_t::zero();
+        if (fold) {
+            const fr_t *src = role < 2 ? v_in : m_in;
+            const uint32_t idx = 4 * q + 2 * (role & 1u);
+            const fr_t x0 = on ? ld_fr_live(src, idx, live) : fr_t::zero(), x1 = on ? ld_fr_live(src, idx + 1, live) : fr_t::zero();
+            const fr_t y = x0 + r * (x1 - x0);
+            if (on) st_fr((role < 2 ? v_out : m_out) + 2 * q + (role & 1u), y);
+            fr_t o1, o2, d, d2;
 #pragma unroll
-        for (int j = fr_lazy_t::W + 2; j < fr_lazy_t::W + 7; ++j) t[j] = 0;
-        fr_t x, y;
+            for (int j = 0; j < 8; ++j) o1.v[j] = __shfl_xor_sync(0xffffffffu, y.v[j], 1);
+            d = (role & 1u) ? y - o1 : o1 - y;   // (entry 1) - (entry 0) of this lane's table
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            x.v[j] = t[8 * c + j];
-            y.v[j] = c == 0 ? (j == 0 ? 1u : 0u) : c == 1 ? fr_cfg::one()[j] : fr_cfg::r2()[j];
+            for (int j = 0; j < 8; ++j) {
+                o2.v[j] = __shfl_xor_sync(0xffffffffu, y.v[j], 2);
+                d2.v[j] = __shfl_xor_sync(0xffffffffu, d.v[j], 2);
+            }
+            if (role < 2) { a_op = y; b_op = o2; }          // v0 m0 (role 0), v1 m1 (role 1)
+            else if (role == 2) { a_op = d; b_op = d2; }    // (m1 - m0)(v1 - v0)
+        } else if (on) {
+            if (role < 2) {
+                a_op = ld_fr_live(v_in, 2 * q + role, live);
+                b_op = ld_fr_live(m_in, 2 * q + role, live);
+            } else if (role == 2) {
+                a_op = ld_fr_live(v_in, 2 * q + 1, live) - ld_fr_live(v_in, 2 * q, live);
+                b_op = ld_fr_live(m_in, 2 * q + 1, live) - ld_fr_live(m_in, 2 * q, live);
+            }
         }
-        uint32_t pm[8];
+        acc.mac(a_op, b_op);
+    }
+    // warp sums per role: role 2 -> A (slot 0), role 0 -> C (slot 1), role 1 -> E (slot 2); role 3 carries zeros.  Full-mask
+    // redux with the other roles' lanes contributing zero: member masks narrower than the warp are emulated in software
+    // (measured 420 clk per redux against 12.5, tools/latbench.cu).
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pm[j] = fr_cfg::mod()[j];
-        while (fr_t::ge_raw(x.v, pm)) fr_t::raw_sub(x.v, pm);   // the multiplier wants operands below r (at most two steps)
-        st_fr(sh_fr + threadIdx.x, x * y);
+    for (int sl = 0; sl < 3; ++sl) {
+        const bool mine = role == (sl == 0 ? 2u : sl == 1 ? 0u : 1u);
+#pragma unroll
+        for (int k = 0; k < fr_lazy_t::W; ++k) {
+            const uint32_t x = mine ? acc.w[k] : 0u;
+            const uint32_t lo = __reduce_add_sync(0xffffffffu, x & 0xffffu);
+            const uint32_t hi = __reduce_add_sync(0xffffffffu, x >> 16);
+            if (lane == (uint32_t) (k & 31)) sh_warp[warp * kRoundLimbs + sl * fr_lazy_t::W + k] = (unsigned long long) lo + ((unsigned long long) hi << 16);
+        }
     }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        const fr_t s = sh_fr[3 * threadIdx.x] + sh_fr[3 * threadIdx.x + 1] + sh_fr[3 * threadIdx.x + 2];
-        st_fr(sh_fr + 9 + threadIdx.x, s);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const fr_t a = sh_fr[9], c = sh_fr[10], e = sh_fr[11];
-        st_fr(A.out + 0, a);
-        st_fr(A.out + 1, e - a - c);
-        st_fr(A.out + 2, c);
-        if (A.flag) publish(A.flag, A.seq);
-    }
+    if (!grid_limb_sum_finish<kRoundLimbs, kRoundBlock>(A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
+    round_quad_publish(A, sh_tot, sh_fr);
 }
 
 // fold a 2-entry table pair down to single values (the "total == 1" collapse, src/prover.cpp:400-404, and the
