@@ -58,6 +58,11 @@ enum { ZK_PROF_FOLD = 0,   /* K1/K2 sumcheck round kernels                    */
 int zk_profile_enable(zk_ctx *ctx, int on);     /* also clears the counters */
 int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_t *bytes);
 
+/* Kernel-selection thresholds of the sumcheck rounds (tests and experiments; defaults in parentheses):
+ *   "thin_max_pairs"   (16384)  rounds with at most this many output pairs per table use k_round_quad_thin
+ *   "tma_min_entries"  (131072) fold rounds on tables of at least this many entries use the TMA-staged k_round_quad_tma */
+int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value);
+
 /* page-lock / unlock a caller-owned host buffer so that uploads from it are direct DMA (cudaHostRegister) */
 int zk_host_pin(const void *p, size_t bytes);
 int zk_host_unpin(const void *p);

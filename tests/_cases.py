@@ -80,11 +80,14 @@ def case_phi_tables(lib, kat, extra=((9, True), (11, False))):
             assert fr_from_words(got) == O.phi_g_init(rx, scale, n, ifft)
 
 
-def case_fold_rounds(lib, shapes=((1, 2), (2, 3), (3, 8), (5, 17), (7, 100), (10, 1024), (11, 1025))):
+def case_fold_rounds(lib, shapes=((1, 2), (2, 3), (3, 8), (5, 17), (7, 100), (10, 1024), (11, 1025)), tunables=None):
     """K1 against the reference-layout restatement; ragged `live` sizes hit the zero-padding rule, bits == rounds hits
-    the collapse into add_term (src/prover.cpp:400-404,409-417)"""
+    the collapse into add_term (src/prover.cpp:400-404,409-417).  `tunables` steers the kernel selection
+    (zk_set_tunable) so that every variant of the round kernel meets the same cases."""
     rng = O.SplitMix64(404)
     with Context(lib) as ctx:
+        for k, v in (tunables or {}).items():
+            ctx.set_tunable(k, v)
         for bits, live in shapes:
             for mix in ("uniform", "witness"):
                 V, M = rand_fr(rng, live, mix), rand_fr(rng, live)

@@ -41,6 +41,16 @@ def test_fold_rounds(gpu_lib):
     cases.case_fold_rounds(gpu_lib, shapes=((1, 2), (2, 3), (3, 8), (5, 17), (7, 100), (10, 1024), (11, 1025), (13, 5000), (14, 16384)))
 
 
+def test_fold_rounds_every_kernel_variant(gpu_lib):
+    shapes = ((2, 3), (5, 17), (7, 100), (8, 255), (9, 512), (10, 1000), (12, 4096), (13, 5000), (13, 8065))
+    # four lanes per output pair everywhere (k_round_quad_thin with a grid-stride loop when forced onto larger tables)
+    cases.case_fold_rounds(gpu_lib, shapes=shapes, tunables={"thin_max_pairs": 1 << 30})
+    # one thread per output pair, plain loads (k_round_quad)
+    cases.case_fold_rounds(gpu_lib, shapes=shapes, tunables={"thin_max_pairs": 0, "tma_min_entries": 1 << 40})
+    # TMA-staged (k_round_quad_tma) from 128-entry tables on: full row blocks through the swizzled boxes, ragged tails guarded
+    cases.case_fold_rounds(gpu_lib, shapes=shapes, tunables={"thin_max_pairs": 0, "tma_min_entries": 128})
+
+
 def test_g1_ops(gpu_lib, kat):
     cases.case_g1_ops(gpu_lib, kat)
 

@@ -88,6 +88,7 @@ class Lib:
         d.zk_ctx_launch_count.restype = C.c_uint64
         d.zk_ctx_launch_count.argtypes = [C.c_void_p]
         d.zk_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        d.zk_set_tunable.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
         d.zk_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), _u64p, _u64p]
         d.zk_fr_vec_op.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint64]
         d.zk_beta_table.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, _u64p]
@@ -143,6 +144,9 @@ class Context:
     def _check(self, rc, what):
         if rc != 0:
             raise ZkError(f"{what}: {self.lib.last_error()}")
+
+    def set_tunable(self, name, value):
+        self._check(self.lib.dll.zk_set_tunable(self.h, name.encode(), int(value)), "zk_set_tunable")
 
     def launches(self):
         return int(self.lib.dll.zk_ctx_launch_count(self.h))

@@ -47,6 +47,16 @@ void zk_ctx_destroy(zk_ctx *ctx) {
 
 uint64_t zk_ctx_launch_count(const zk_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && name, "bad arguments");
+    const std::string n(name);
+    if (n == "thin_max_pairs") ctx->thin_max_pairs = (uint32_t) value;
+    else if (n == "tma_min_entries") ctx->tma_min_entries = value;
+    else ZK_REQUIRE(false, "unknown tunable");
+    ZK_API_END
+}
+
 int zk_profile_enable(zk_ctx *ctx, int on) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx, "null ctx");

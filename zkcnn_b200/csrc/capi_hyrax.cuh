@@ -468,10 +468,15 @@ int zk_bench_fold(zk_ctx *ctx, uint32_t bits, uint32_t iters, int fold, float *m
     R.v_in = v.as<fr_t>(); R.m_in = m.as<fr_t>(); R.v_out = vo.as<fr_t>(); R.m_out = mo.as<fr_t>();
     R.n_in = (uint32_t) n; R.live = (uint32_t) n; R.fold = fold ? 1 : 0;
     const uint64_t out_pairs = fold ? n >> 2 : n >> 1;
-    const bool thin = out_pairs <= kThinMaxPairs;   // same choice as round_quadratic()
+    const bool thin = out_pairs <= ctx->thin_max_pairs;   // same choices as round_quadratic()
     R.n_blocks = thin ? (uint32_t) ((out_pairs + kRoundBlock / 4 - 1) / (kRoundBlock / 4)) : round_grid_for(out_pairs);
+    const uint32_t limit_pairs[2] = {0, (uint32_t) out_pairs};
+    (void) limit_pairs;
     auto launch = [&]() {
         if (thin) ZK_KLAUNCH(ctx, k_round_quad_thin, dim3(R.n_blocks), dim3(kRoundBlock), 0, A);
+#ifndef ZK_EMU
+        else if (fold && n >= ctx->tma_min_entries) launch_round_tma(ctx, ZK_PROF_OTHER, 0, A, limit_pairs);
+#endif
         else ZK_KLAUNCH(ctx, k_round_quad, dim3(R.n_blocks), dim3(kRoundBlock), 0, A);
     };
     launch();   // warm-up

@@ -383,16 +383,53 @@ static void ensure_round_scratch(zk_ctx *ctx) {
         ctx->tag_d = reinterpret_cast<uint32_t *>(ctx->res_d + 36);
     }
 }
-// k_round_quad_thin up to this many output pairs per table (default 2^14: 2 x 512 CTAs of 128 threads, one pass);
-// ZK_THIN_MAX_PAIRS overrides it for experiments (0 = never)
-static inline uint32_t thin_max_pairs() {
-    static const uint32_t v = [] {
-        const char *e = getenv("ZK_THIN_MAX_PAIRS");
-        return e ? (uint32_t) strtoul(e, nullptr, 0) : 1u << 14;
+#ifndef ZK_EMU
+// the input tables of a fold round as TMA tensor maps: (n_in / 4) rows of 32 x u32 (= four entries), box 32 x 32 rows,
+// 128-byte swizzle.  cuTensorMapEncodeTiled comes from the driver through the runtime (no link-time dependency on libcuda).
+static void encode_rows_map(CUtensorMap *tm, const fr_t *table, uint32_t n_in) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        rt::check(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q), "cudaGetDriverEntryPoint");
+        if (!p || q != cudaDriverEntryPointSuccess) throw rt::error("cuTensorMapEncodeTiled is not available");
+        return reinterpret_cast<encode_fn>(p);
     }();
-    return v;
+    const cuuint64_t gdim[2] = {32, n_in / 4};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {32, 32}, estride[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<fr_t *>(table), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw rt::error("cuTensorMapEncodeTiled failed (" + std::to_string((int) r) + ")");
 }
-#define kThinMaxPairs (thin_max_pairs())
+static void launch_round_tma(zk_ctx *ctx, int cls, uint64_t bytes, round_args_t &A, const uint32_t limit_pairs[2]) {
+    static const bool attr_set = [] {
+        rt::check(cudaFuncSetAttribute(k_round_quad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmemBytes), "cudaFuncSetAttribute");
+        return true;
+    }();
+    (void) attr_set;
+    round_tma_args_t T;
+    memset(&T, 0, sizeof T);
+    // one wave: the resident CTAs are split between the pairs in proportion to their row blocks
+    uint64_t groups[2], total = 0;
+    for (int b = 0; b < 2; ++b) { groups[b] = A.pair[b].n_in ? (limit_pairs[b] + 31) / 32 : 0; total += groups[b]; }
+    uint32_t gx = 0;
+    for (int b = 0; b < 2; ++b) {
+        if (!groups[b]) { A.pair[b].n_blocks = 0; continue; }
+        const uint64_t want = (groups[b] + kRoundBlock / 32 - 1) / (kRoundBlock / 32);
+        const uint64_t share = std::max<uint64_t>(1, (uint64_t) kTmaMaxGrid * groups[b] / total);
+        A.pair[b].n_blocks = (uint32_t) std::min(want, share);
+        gx += A.pair[b].n_blocks;
+        if (A.pair[b].n_in >= 128) {
+            encode_rows_map(&T.tm[b][0], A.pair[b].v_in, A.pair[b].n_in);
+            encode_rows_map(&T.tm[b][1], A.pair[b].m_in, A.pair[b].n_in);
+        }
+    }
+    T.R = A;
+    ZK_KLAUNCH_C(ctx, cls, bytes, k_round_quad_tma, dim3(gx), dim3(kRoundBlock), kTmaSmemBytes, T);
+}
+#endif
 // CTAs for one table pair of a sumcheck round: one output pair per thread while the machine has room, then grid-stride
 static inline uint32_t round_grid_for(uint64_t live_pairs) {
     const uint64_t g = (live_pairs + kRoundBlock - 1) / kRoundBlock;
@@ -502,17 +539,24 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
     ++ctx->seq;
     if (any_final) { F.flag = ctx->flag_d; F.seq = ctx->seq; }
     else { A.tagged = reinterpret_cast<uint4 *>(ctx->tag_d); A.seq = ctx->seq; }
-    // tables up to 2^16 entries: four lanes per output pair (latency), beyond: one thread per output pair, grid-stride (throughput)
-    const bool thin = max_live_pairs <= kThinMaxPairs;
+    // tables up to 2^16 entries: four lanes per output pair (latency); beyond: one thread per output pair, grid-stride
+    // (throughput), fed by TMA once the tables are large enough to stream from HBM
+    const bool thin = max_live_pairs <= ctx->thin_max_pairs;
+    uint32_t limit_pairs[2] = {0, 0};
+    uint64_t max_n_in = 0;
     for (int b = 0; b < 2; ++b)
         if (quad[b]) {
-            const uint32_t live_pairs = std::max(1u, std::min(pairs_of[b], first ? A.pair[b].n_in >> 1 : A.pair[b].n_in >> 2));
-            A.pair[b].n_blocks = thin ? (live_pairs + kRoundBlock / 4 - 1) / (kRoundBlock / 4) : round_grid_for(live_pairs);
+            limit_pairs[b] = std::max(1u, std::min(pairs_of[b], first ? A.pair[b].n_in >> 1 : A.pair[b].n_in >> 2));
+            A.pair[b].n_blocks = thin ? (limit_pairs[b] + kRoundBlock / 4 - 1) / (kRoundBlock / 4) : round_grid_for(limit_pairs[b]);
             gx += A.pair[b].n_blocks;
+            max_n_in = std::max<uint64_t>(max_n_in, A.pair[b].n_in);
         }
     // rounds that stream less than 32 MiB are bound by launch + reduction latency, not by HBM: they are accounted separately
     const int cls = fold_bytes >= (32u << 20) ? ZK_PROF_FOLD : ZK_PROF_FOLD_SMALL;
     if (any_quad && thin) ZK_KLAUNCH_C(ctx, cls, fold_bytes, k_round_quad_thin, dim3(gx), dim3(kRoundBlock), 0, A);
+#ifndef ZK_EMU
+    else if (any_quad && !first && max_n_in >= ctx->tma_min_entries) launch_round_tma(ctx, cls, fold_bytes, A, limit_pairs);
+#endif
     else if (any_quad) ZK_KLAUNCH_C(ctx, cls, fold_bytes, k_round_quad, dim3(gx), dim3(kRoundBlock), 0, A);
     if (any_final) ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
     const fr_t *h_res = ctx->res_h;

@@ -108,6 +108,8 @@ struct zk_ctx {
     uint32_t *flag_h = nullptr, *flag_d = nullptr;
     uint32_t *tag_h = nullptr, *tag_d = nullptr;          // [32] tagged mailbox (publish_tagged)
     uint32_t seq = 0;
+    uint32_t thin_max_pairs = 1u << 14;      // see zk_set_tunable
+    uint64_t tma_min_entries = 1ull << 17;
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 
     zk::hyrax_t hy;

@@ -16,6 +16,9 @@
 //   K6  k_liu_scatter     sumcheckLiuInit                   src/prover.cpp:334-353
 #pragma once
 #include "mont.cuh"
+#ifndef ZK_EMU
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 
 namespace zk {
 
@@ -158,7 +161,10 @@ ZK_HD __forceinline__ void limb_sums_normalise(const unsigned long long *tot, in
 // anyway, src/prover.cpp:368-383).
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int kRoundBlock = 128;                 // 4 warps: one per SM sub-partition
-constexpr int kRoundMaxGrid = ZK_SM_COUNT * 4;   // 4 resident CTAs per SM (<= 128 registers per thread)
+#ifndef ZK_ROUND_CTAS_PER_SM
+#define ZK_ROUND_CTAS_PER_SM 4
+#endif
+constexpr int kRoundMaxGrid = ZK_SM_COUNT * ZK_ROUND_CTAS_PER_SM;   // resident CTAs per SM (4: <= 128 registers per thread)
 constexpr int kRoundLimbs = 3 * fr_lazy_t::W;    // three unreduced sums of 17 limbs
 
 struct round_pair_t {
@@ -251,7 +257,10 @@ __device__ __forceinline__ void round_quad_publish(const round_args_t &A, const 
 // (linear_poly * linear_poly, src/polynomial.cpp:116-118, evaluated Karatsuba-style with 3 products).  The three sums
 // are accumulated unreduced (fr_lazy_t): the four fold multiplications per output pair are full Montgomery
 // multiplications (their results are stored), the three products only pay the multiplication half.
-__global__ void __launch_bounds__(kRoundBlock, 4) k_round_quad(round_args_t A) {
+#ifndef ZK_ROUND_CTAS_PER_SM
+#define ZK_ROUND_CTAS_PER_SM 4
+#endif
+__global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_quad(round_args_t A) {
     __shared__ unsigned long long sh_warp[(kRoundBlock / 32) * kRoundLimbs];
     __shared__ unsigned long long sh_tot[kRoundLimbs];
     __shared__ uint32_t sh_ticket;
@@ -272,6 +281,12 @@ __global__ void __launch_bounds__(kRoundBlock, 4) k_round_quad(round_args_t A) {
         const fr_t r = A.r;
         for (uint32_t i = bx * kRoundBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
             const uint32_t base = i << 2;
+#if defined(ZK_ROUND_PREFETCH) && ZK_ON_DEVICE
+            if (i + stride < n_pairs) {   // next iteration's two 128-byte rows
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(v_in + base + 4 * stride));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(m_in + base + 4 * stride));
+            }
+#endif
             fr_t x0 = ld_fr_live(v_in, base, live), x1 = ld_fr_live(v_in, base + 1, live);
             fr_t x2 = ld_fr_live(v_in, base + 2, live), x3 = ld_fr_live(v_in, base + 3, live);
             fr_t y0 = ld_fr_live(m_in, base, live), y1 = ld_fr_live(m_in, base + 1, live);
@@ -384,6 +399,155 @@ __global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A)
     if (!grid_limb_sum_finish<kRoundLimbs, kRoundBlock>(A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
     round_quad_publish(A, sh_tot, sh_fr);
 }
+
+#if !defined(ZK_EMU)
+// --------------------------------------------------------------------------------------------------------------------
+// K1, HBM-streaming rounds (tables of 2^17 entries and more): the same arithmetic as k_round_quad, fed by TMA.
+// A warp owns a double-buffered pair of 4 KB boxes per table: 32 rows of 128 bytes, one row = the four input entries of
+// one output pair.  One elected lane issues cp.async.bulk.tensor for the NEXT row block of V and of mult while the warp
+// multiplies the current one; the boxes land in shared memory with the 128-byte swizzle (16-byte chunk c of row q sits at
+// chunk c ^ (q & 7)), so each lane reads its own row with conflict-free LDS.128 and no LSU/L1 traffic or registers are
+// spent on data in flight.  Completion is tracked by one mbarrier per (warp, stage) with a transaction count of 8 KB.
+// Row blocks that are not completely live (the last one of a table) take the guarded global-load path.
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int kTmaCtasPerSm = 3;
+constexpr int kTmaMaxGrid = ZK_SM_COUNT * kTmaCtasPerSm;
+constexpr uint32_t kTmaBoxBytes = 4096;                                     // 32 rows x 128 bytes
+constexpr uint32_t kTmaWarpBytes = 2 /* stages */ * 2 /* tables */ * kTmaBoxBytes;
+constexpr uint32_t kTmaSmemBytes = (kRoundBlock / 32) * kTmaWarpBytes + 1024;   // + slack to align the boxes to 1 KB
+
+struct alignas(64) round_tma_args_t {
+    round_args_t R;
+    CUtensorMap tm[2][2];    // [pair][V, mult]: the input tables as (n_in / 4) rows of 32 x u32, box 32 x 32, SWIZZLE_128B
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_rows(uint32_t dst, const CUtensorMap *tm, uint32_t row0, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(0), "r"(row0), "r"(bar) : "memory");
+}
+__device__ __forceinline__ fr_t lds_fr_swz(uint32_t row_base, uint32_t row, int entry) {   // entry 0..3 of the row
+    fr_t x;
+    const uint32_t a0 = row_base + (((2 * entry) ^ (row & 7u)) << 4), a1 = row_base + (((2 * entry + 1) ^ (row & 7u)) << 4);
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.v[0]), "=r"(x.v[1]), "=r"(x.v[2]), "=r"(x.v[3]) : "r"(a0));
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.v[4]), "=r"(x.v[5]), "=r"(x.v[6]), "=r"(x.v[7]) : "r"(a1));
+    return x;
+}
+// the multiplier inlined (the four fold multiplications of an output pair are independent: their carry chains interleave)
+__device__ __forceinline__ fr_t fr_mul_inline(const fr_t &a, const fr_t &b) {
+    fr_t r;
+    fr_t::mul_wide(r.v, a.v, b.v);
+    return r;
+}
+
+__global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(const __grid_constant__ round_tma_args_t T) {
+    extern __shared__ __align__(1024) unsigned char dyn_smem[];
+    __shared__ unsigned long long sh_warp[(kRoundBlock / 32) * kRoundLimbs];
+    __shared__ unsigned long long sh_tot[kRoundLimbs];
+    __shared__ uint32_t sh_ticket;
+    __shared__ fr_t sh_fr[12];
+    __shared__ __align__(8) unsigned long long sh_bar[(kRoundBlock / 32) * 2];
+    const round_args_t &A = T.R;
+    const uint32_t nb0 = A.pair[0].n_blocks, nb = nb0 + A.pair[1].n_blocks;
+    const bool second = blockIdx.x >= nb0;
+    const fr_t *v_in = second ? A.pair[1].v_in : A.pair[0].v_in, *m_in = second ? A.pair[1].m_in : A.pair[0].m_in;
+    fr_t *v_out = second ? A.pair[1].v_out : A.pair[0].v_out, *m_out = second ? A.pair[1].m_out : A.pair[0].m_out;
+    const uint32_t n_in = second ? A.pair[1].n_in : A.pair[0].n_in, live = second ? A.pair[1].live : A.pair[0].live;
+    const CUtensorMap *tm_v = second ? &T.tm[1][0] : &T.tm[0][0], *tm_m = second ? &T.tm[1][1] : &T.tm[0][1];
+    const uint32_t bx = second ? blockIdx.x - nb0 : blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_pairs = n_in >> 2, live_pairs = (live + 3) >> 2;
+    const uint32_t limit = n_pairs < live_pairs ? n_pairs : live_pairs;        // output pairs with any live input
+    const uint32_t n_groups = (limit + 31) >> 5;                               // row blocks of 32 output pairs
+    const uint32_t full_groups = (live >> 2) >> 5 < n_groups ? (live >> 2) >> 5 : n_groups;   // blocks whose 128 inputs are all live
+    const uint32_t gstride = (second ? A.pair[1].n_blocks : nb0) * (kRoundBlock / 32);
+
+    const uint32_t box0 = ((smem_addr(dyn_smem) + 1023u) & ~1023u) + warp * kTmaWarpBytes;   // [stage][table] boxes of this warp
+    const uint32_t bar0 = smem_addr(sh_bar + 2 * warp);
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    fr_lazy_t acc[3];  // A, C, E
+    acc[0].clear(); acc[1].clear(); acc[2].clear();
+    const fr_t r = A.r;
+    uint32_t stage = 0, parity = 0;   // bit s of `parity`: phase to wait for on stage s
+    uint32_t g = bx * (kRoundBlock / 32) + warp;
+    if (g < full_groups && lane == 0) {
+        mbar_expect_tx(bar0, 2 * kTmaBoxBytes);
+        tma_load_rows(box0, tm_v, g * 32, bar0);
+        tma_load_rows(box0 + kTmaBoxBytes, tm_m, g * 32, bar0);
+    }
+    for (; g < n_groups; g += gstride) {
+        const uint32_t gn = g + gstride;
+        __syncwarp();   // every lane is done reading the other stage (previous iteration)
+        if (gn < full_groups && lane == 0) {
+            const uint32_t b = bar0 + 8 * (stage ^ 1u), dst = box0 + (stage ^ 1u) * 2 * kTmaBoxBytes;
+            mbar_expect_tx(b, 2 * kTmaBoxBytes);
+            tma_load_rows(dst, tm_v, gn * 32, b);
+            tma_load_rows(dst + kTmaBoxBytes, tm_m, gn * 32, b);
+        }
+        const uint32_t i = g * 32 + lane;   // output pair of this lane
+        fr_t x0, x1, x2, x3, y0, y1, y2, y3;
+        if (g < full_groups) {
+            mbar_wait(bar0 + 8 * stage, (parity >> stage) & 1u);
+            parity ^= 1u << stage;
+            const uint32_t vrow = box0 + stage * 2 * kTmaBoxBytes + lane * 128u, mrow = vrow + kTmaBoxBytes;
+            x0 = lds_fr_swz(vrow, lane, 0); x1 = lds_fr_swz(vrow, lane, 1); x2 = lds_fr_swz(vrow, lane, 2); x3 = lds_fr_swz(vrow, lane, 3);
+            y0 = lds_fr_swz(mrow, lane, 0); y1 = lds_fr_swz(mrow, lane, 1); y2 = lds_fr_swz(mrow, lane, 2); y3 = lds_fr_swz(mrow, lane, 3);
+        } else {
+            const uint32_t base = i << 2;
+            const bool on = i < limit;
+            x0 = on ? ld_fr_live(v_in, base, live) : fr_t::zero(); x1 = on ? ld_fr_live(v_in, base + 1, live) : fr_t::zero();
+            x2 = on ? ld_fr_live(v_in, base + 2, live) : fr_t::zero(); x3 = on ? ld_fr_live(v_in, base + 3, live) : fr_t::zero();
+            y0 = on ? ld_fr_live(m_in, base, live) : fr_t::zero(); y1 = on ? ld_fr_live(m_in, base + 1, live) : fr_t::zero();
+            y2 = on ? ld_fr_live(m_in, base + 2, live) : fr_t::zero(); y3 = on ? ld_fr_live(m_in, base + 3, live) : fr_t::zero();
+        }
+        const fr_t v0 = x0 + fr_mul_inline(r, x1 - x0);
+        const fr_t v1 = x2 + fr_mul_inline(r, x3 - x2);
+        const fr_t m0 = y0 + fr_mul_inline(r, y1 - y0);
+        const fr_t m1 = y2 + fr_mul_inline(r, y3 - y2);
+        if (i < limit) {
+            st_fr(v_out + 2 * i, v0);
+            st_fr(v_out + 2 * i + 1, v1);
+            st_fr(m_out + 2 * i, m0);
+            st_fr(m_out + 2 * i + 1, m1);
+        }
+        acc[0].mac(m1 - m0, v1 - v0);
+        acc[1].mac(m0, v0);
+        acc[2].mac(m1, v1);
+        stage ^= 1u;
+    }
+    uint32_t limb[kRoundLimbs];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < fr_lazy_t::W; ++j) limb[k * fr_lazy_t::W + j] = acc[k].w[j];
+    if (!grid_limb_sum<kRoundLimbs, kRoundBlock>(limb, A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
+    round_quad_publish(A, sh_tot, sh_fr);
+}
+#endif  // !ZK_EMU
 
 // fold a 2-entry table pair down to single values (the "total == 1" collapse, src/prover.cpp:400-404, and the
 // eval(previous_random) of the Finalize calls, src/prover.cpp:146-153,459-497).  out[2*i], out[2*i+1] = v, m of pair i.
