@@ -402,10 +402,13 @@ __global__ void __launch_bounds__(kBlock) k_selftest(uint64_t seed, uint32_t n, 
         bad += ((a + b) - b) != a;
         bad += ((a - b) + b) != a;
         bad += (a * (b + a)) != (x + a * a);
+        // unreduced difference as the second operand of a multiplication
+        bad += (a * fr_t::sub_lazy(b, a)) != (a * (b - a));
+        bad += (b * fr_t::sub_lazy(a, a)) != fr_t::zero();
         // lazy reduction: three unreduced products summed, reduced once == sum of the reduced products
         fr_lazy_t acc;
         acc.clear();
-        acc.mac(a, b); acc.mac(a, a); acc.mac(b, b);
+        acc.mac(a, b); acc.mac(fr_t::sub_lazy(a, fr_t::zero()), a); acc.mac(b, fr_t::sub_lazy(b, fr_t::zero()));
         const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t top[8] = {acc.w[16], 0, 0, 0, 0, 0, 0, 0};
         bad += montgomery_of_wide<fr_cfg>(acc.w, acc.w + 8, top) != (x + a * a + b * b);

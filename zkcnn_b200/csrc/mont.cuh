@@ -48,7 +48,10 @@ static __device__ __constant__ uint32_t d_fp_MOD_rt[13] = {0xffffaaabu, 0xb9feff
 struct fr_cfg {
     static constexpr int N = 8;
     // r = ... ffffffff 00000001 in its two low limbs: m * r[0] = m and m * r[1] = (m << 32) - m need no multiplier
-    static constexpr bool LOW_LIMBS_SPECIAL = true;
+    // (wide_reduce_cmad).  Measured on B200 it does not pay: 16 wide multiply-adds fewer but 48 integer-ALU instructions
+    // more per multiplication leave the throughput at 65-67 Gmul/s either way and the fold kernel 2 % slower
+    // (tools/mulbench.cu, DESIGN.md "cost model"), so the generic path stays the default.
+    static constexpr bool LOW_LIMBS_SPECIAL = false;
     static constexpr uint32_t INV = fr_params::INV;
     static ZK_HD __forceinline__ const uint32_t *mod() { return ZK_C(fr_MOD); }
 #if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
@@ -210,6 +213,39 @@ template <class C> struct alignas(16) mont_t {
 #endif
     }
     ZK_HD __forceinline__ mont_t operator-() const { return is_zero() ? *this : (zero() - *this); }
+    // a - b + p in (0, 2p): a difference that is NOT brought back below p (16 instructions instead of 25).  Valid as the
+    // SECOND operand of a multiplication (the product still ends below 2p before the final conditional subtraction) and
+    // as either operand of lazy_acc_t::mac; never stored.
+    static ZK_HD __forceinline__ mont_t sub_lazy(const mont_t &a, const mont_t &b) {
+        mont_t t;
+        const uint32_t *p = C::mod();
+#if ZK_FIELD_PTX
+        t.v[0] = ptx::add_cc(a.v[0], p[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) t.v[i] = ptx::addc_cc(a.v[i], p[i]);
+        t.v[N - 1] = ptx::addc(a.v[N - 1], p[N - 1]);
+        t.v[0] = ptx::sub_cc(t.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) t.v[i] = ptx::subc_cc(t.v[i], b.v[i]);
+        t.v[N - 1] = ptx::subc(t.v[N - 1], b.v[N - 1]);
+#else
+        uint64_t c = 0;
+        int64_t bw = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            c += (uint64_t) a.v[i] + p[i];
+            t.v[i] = (uint32_t) c;
+            c >>= 32;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            bw += (int64_t) t.v[i] - (int64_t) b.v[i];
+            t.v[i] = (uint32_t) bw;
+            bw >>= 32;
+        }
+#endif
+        return t;
+    }
 
     // ---- multiplication ---------------------------------------------------------------------------------------------
     static ZK_HD __forceinline__ void mul_portable(uint32_t *r, const uint32_t *a, const uint32_t *b) {

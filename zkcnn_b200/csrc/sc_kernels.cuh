@@ -291,15 +291,15 @@ __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_qua
             fr_t x2 = ld_fr_live(v_in, base + 2, live), x3 = ld_fr_live(v_in, base + 3, live);
             fr_t y0 = ld_fr_live(m_in, base, live), y1 = ld_fr_live(m_in, base + 1, live);
             fr_t y2 = ld_fr_live(m_in, base + 2, live), y3 = ld_fr_live(m_in, base + 3, live);
-            const fr_t v0 = x0 + r * (x1 - x0);
-            const fr_t v1 = x2 + r * (x3 - x2);
+            const fr_t v0 = x0 + r * fr_t::sub_lazy(x1, x0);
+            const fr_t v1 = x2 + r * fr_t::sub_lazy(x3, x2);
             st_fr(v_out + 2 * i, v0);
             st_fr(v_out + 2 * i + 1, v1);
-            const fr_t m0 = y0 + r * (y1 - y0);
-            const fr_t m1 = y2 + r * (y3 - y2);
+            const fr_t m0 = y0 + r * fr_t::sub_lazy(y1, y0);
+            const fr_t m1 = y2 + r * fr_t::sub_lazy(y3, y2);
             st_fr(m_out + 2 * i, m0);
             st_fr(m_out + 2 * i + 1, m1);
-            acc[0].mac(m1 - m0, v1 - v0);
+            acc[0].mac(fr_t::sub_lazy(m1, m0), fr_t::sub_lazy(v1, v0));
             acc[1].mac(m0, v0);
             acc[2].mac(m1, v1);
         }
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_qua
         for (uint32_t i = bx * kRoundBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
             const fr_t v0 = ld_fr_live(v_in, 2 * i, live), v1 = ld_fr_live(v_in, 2 * i + 1, live);
             const fr_t m0 = ld_fr_live(m_in, 2 * i, live), m1 = ld_fr_live(m_in, 2 * i + 1, live);
-            acc[0].mac(m1 - m0, v1 - v0);
+            acc[0].mac(fr_t::sub_lazy(m1, m0), fr_t::sub_lazy(v1, v0));
             acc[1].mac(m0, v0);
             acc[2].mac(m1, v1);
         }
@@ -358,12 +358,12 @@ __global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A)
             const fr_t *src = role < 2 ? v_in : m_in;
             const uint32_t idx = 4 * q + 2 * (role & 1u);
             const fr_t x0 = on ? ld_fr_live(src, idx, live) : fr_t::zero(), x1 = on ? ld_fr_live(src, idx + 1, live) : fr_t::zero();
-            const fr_t y = x0 + r * (x1 - x0);
+            const fr_t y = x0 + r * fr_t::sub_lazy(x1, x0);
             if (on) st_fr((role < 2 ? v_out : m_out) + 2 * q + (role & 1u), y);
             fr_t o1, o2, d, d2;
 #pragma unroll
             for (int j = 0; j < 8; ++j) o1.v[j] = __shfl_xor_sync(0xffffffffu, y.v[j], 1);
-            d = (role & 1u) ? y - o1 : o1 - y;   // (entry 1) - (entry 0) of this lane's table
+            d = (role & 1u) ? fr_t::sub_lazy(y, o1) : fr_t::sub_lazy(o1, y);   // (entry 1) - (entry 0) of this lane's table
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 o2.v[j] = __shfl_xor_sync(0xffffffffu, y.v[j], 2);
@@ -376,8 +376,8 @@ __global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A)
                 a_op = ld_fr_live(v_in, 2 * q + role, live);
                 b_op = ld_fr_live(m_in, 2 * q + role, live);
             } else if (role == 2) {
-                a_op = ld_fr_live(v_in, 2 * q + 1, live) - ld_fr_live(v_in, 2 * q, live);
-                b_op = ld_fr_live(m_in, 2 * q + 1, live) - ld_fr_live(m_in, 2 * q, live);
+                a_op = fr_t::sub_lazy(ld_fr_live(v_in, 2 * q + 1, live), ld_fr_live(v_in, 2 * q, live));
+                b_op = fr_t::sub_lazy(ld_fr_live(m_in, 2 * q + 1, live), ld_fr_live(m_in, 2 * q, live));
             }
         }
         acc.mac(a_op, b_op);
@@ -410,10 +410,17 @@ __global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A)
 // spent on data in flight.  Completion is tracked by one mbarrier per (warp, stage) with a transaction count of 8 KB.
 // Row blocks that are not completely live (the last one of a table) take the guarded global-load path.
 // --------------------------------------------------------------------------------------------------------------------
-constexpr int kTmaCtasPerSm = 3;
+#ifndef ZK_TMA_STAGES
+#define ZK_TMA_STAGES 2
+#endif
+#ifndef ZK_TMA_CTAS
+#define ZK_TMA_CTAS 3
+#endif
+constexpr int kTmaStages = ZK_TMA_STAGES;   // 2: next block lands while this one is multiplied; 1: refill as soon as the block is in registers
+constexpr int kTmaCtasPerSm = ZK_TMA_CTAS;
 constexpr int kTmaMaxGrid = ZK_SM_COUNT * kTmaCtasPerSm;
 constexpr uint32_t kTmaBoxBytes = 4096;                                     // 32 rows x 128 bytes
-constexpr uint32_t kTmaWarpBytes = 2 /* stages */ * 2 /* tables */ * kTmaBoxBytes;
+constexpr uint32_t kTmaWarpBytes = kTmaStages * 2 /* tables */ * kTmaBoxBytes;
 constexpr uint32_t kTmaSmemBytes = (kRoundBlock / 32) * kTmaWarpBytes + 1024;   // + slack to align the boxes to 1 KB
 
 struct alignas(64) round_tma_args_t {
@@ -456,6 +463,11 @@ __device__ __forceinline__ fr_t fr_mul_inline(const fr_t &a, const fr_t &b) {
     fr_t::mul_wide(r.v, a.v, b.v);
     return r;
 }
+#ifdef ZK_TMA_MUL_CALL
+#define ZK_TMA_MUL(a, b) ((a) * (b))
+#else
+#define ZK_TMA_MUL(a, b) fr_mul_inline(a, b)
+#endif
 
 __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(const __grid_constant__ round_tma_args_t T) {
     extern __shared__ __align__(1024) unsigned char dyn_smem[];
@@ -501,19 +513,22 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(c
     }
     for (; g < n_groups; g += gstride) {
         const uint32_t gn = g + gstride;
-        __syncwarp();   // every lane is done reading the other stage (previous iteration)
-        if (gn < full_groups && lane == 0) {
-            const uint32_t b = bar0 + 8 * (stage ^ 1u), dst = box0 + (stage ^ 1u) * 2 * kTmaBoxBytes;
-            mbar_expect_tx(b, 2 * kTmaBoxBytes);
-            tma_load_rows(dst, tm_v, gn * 32, b);
-            tma_load_rows(dst + kTmaBoxBytes, tm_m, gn * 32, b);
+        if (kTmaStages == 2) {
+            __syncwarp();   // every lane is done reading the other stage (previous iteration)
+            if (gn < full_groups && lane == 0) {
+                const uint32_t b = bar0 + 8 * (stage ^ 1u), dst = box0 + (stage ^ 1u) * 2 * kTmaBoxBytes;
+                mbar_expect_tx(b, 2 * kTmaBoxBytes);
+                tma_load_rows(dst, tm_v, gn * 32, b);
+                tma_load_rows(dst + kTmaBoxBytes, tm_m, gn * 32, b);
+            }
         }
         const uint32_t i = g * 32 + lane;   // output pair of this lane
         fr_t x0, x1, x2, x3, y0, y1, y2, y3;
         if (g < full_groups) {
-            mbar_wait(bar0 + 8 * stage, (parity >> stage) & 1u);
-            parity ^= 1u << stage;
-            const uint32_t vrow = box0 + stage * 2 * kTmaBoxBytes + lane * 128u, mrow = vrow + kTmaBoxBytes;
+            const uint32_t st = kTmaStages == 2 ? stage : 0u;
+            mbar_wait(bar0 + 8 * st, (parity >> st) & 1u);
+            parity ^= 1u << st;
+            const uint32_t vrow = box0 + st * 2 * kTmaBoxBytes + lane * 128u, mrow = vrow + kTmaBoxBytes;
             x0 = lds_fr_swz(vrow, lane, 0); x1 = lds_fr_swz(vrow, lane, 1); x2 = lds_fr_swz(vrow, lane, 2); x3 = lds_fr_swz(vrow, lane, 3);
             y0 = lds_fr_swz(mrow, lane, 0); y1 = lds_fr_swz(mrow, lane, 1); y2 = lds_fr_swz(mrow, lane, 2); y3 = lds_fr_swz(mrow, lane, 3);
         } else {
@@ -524,17 +539,30 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(c
             y0 = on ? ld_fr_live(m_in, base, live) : fr_t::zero(); y1 = on ? ld_fr_live(m_in, base + 1, live) : fr_t::zero();
             y2 = on ? ld_fr_live(m_in, base + 2, live) : fr_t::zero(); y3 = on ? ld_fr_live(m_in, base + 3, live) : fr_t::zero();
         }
-        const fr_t v0 = x0 + fr_mul_inline(r, x1 - x0);
-        const fr_t v1 = x2 + fr_mul_inline(r, x3 - x2);
-        const fr_t m0 = y0 + fr_mul_inline(r, y1 - y0);
-        const fr_t m1 = y2 + fr_mul_inline(r, y3 - y2);
+        const fr_t dx0 = fr_t::sub_lazy(x1, x0), dx1 = fr_t::sub_lazy(x3, x2), dy0 = fr_t::sub_lazy(y1, y0), dy1 = fr_t::sub_lazy(y3, y2);
+        if (kTmaStages == 1) {
+            // single buffer: the subtractions above consumed all sixteen loaded registers, so every lane's LDS has
+            // completed (in-order issue); `dep` makes the refill depend on them so that it cannot be scheduled earlier
+            uint32_t dep = dx0.v[0] ^ dx1.v[0] ^ dy0.v[0] ^ dy1.v[0] ^ dx0.v[7] ^ dx1.v[7] ^ dy0.v[7] ^ dy1.v[7];
+            dep = (uint32_t) __popc(dep) >> 6;   // always 0, opaque to the compiler
+            __syncwarp();
+            if (gn < full_groups && lane == 0) {
+                mbar_expect_tx(bar0, 2 * kTmaBoxBytes);
+                tma_load_rows(box0, tm_v, gn * 32 + dep, bar0);
+                tma_load_rows(box0 + kTmaBoxBytes, tm_m, gn * 32 + dep, bar0);
+            }
+        }
+        const fr_t v0 = x0 + ZK_TMA_MUL(r, dx0);
+        const fr_t v1 = x2 + ZK_TMA_MUL(r, dx1);
+        const fr_t m0 = y0 + ZK_TMA_MUL(r, dy0);
+        const fr_t m1 = y2 + ZK_TMA_MUL(r, dy1);
         if (i < limit) {
             st_fr(v_out + 2 * i, v0);
             st_fr(v_out + 2 * i + 1, v1);
             st_fr(m_out + 2 * i, m0);
             st_fr(m_out + 2 * i + 1, m1);
         }
-        acc[0].mac(m1 - m0, v1 - v0);
+        acc[0].mac(fr_t::sub_lazy(m1, m0), fr_t::sub_lazy(v1, v0));
         acc[1].mac(m0, v0);
         acc[2].mac(m1, v1);
         stage ^= 1u;
