@@ -109,7 +109,7 @@ def run_ours(args):
     import torch
     import gen_synthetic_input as gen
     import zkcnn_b200
-    from zkcnn_b200 import PROF_CLASSES, REAL_GENERATORS, WITNESS_RESIDENT, CHECK_PREDICATES
+    from zkcnn_b200 import PROF_CLASSES, REAL_GENERATORS, WITNESS_RESIDENT, CHECK_PREDICATES, ROUND_BY_ROUND
     import ctypes as C
 
     rank, world, local = dist_env()
@@ -136,7 +136,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     s.build()
     build_s = time.perf_counter() - t0
-    flags = REAL_GENERATORS
+    flags = REAL_GENERATORS | (ROUND_BY_ROUND if args.round_by_round else 0)
     # one fully verified proof with the reference's own (degenerate) generator set: full-size parity inside the bench
     st0 = s.prove(1, CHECK_PREDICATES)
     assert st0["ok"] == 1, "verification failed"
@@ -217,6 +217,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "u32 limbs (BLS12-381 Fr 255-bit / Fp 381-bit Montgomery)", "data": "synthetic",
             "config": {"workload": "vgg11 CIFAR pic_cnt=1, one proof per step per GPU (BASELINE config 3/4)" if model == "vgg11" else model,
                        "network": config, "input_layer": st0["input_size"], "layers": st0["n_layers"], "generators": "non-degenerate (G * challenge)",
+                       "rounds": "one device call per sumcheck round" if args.round_by_round else "one device call per sumcheck phase (challenges of a phase are drawn before its rounds, as in src/verifier.cpp:156-160)",
                        "l2": "tables larger than L2 (2^24 x 32 B witness, 537 MB)", "parallelism": f"one proof per GPU x{world}, final all-gather of proofs",
                        "timer": "host clock around synchronous API calls, barrier + cuda synchronize on both sides; kernels by CUDA events"},
             "e2e": {"value": round(args.steps * world / t_e2e, 4), "unit": UNIT, "h2d_bytes_per_step": h2d // max(1, args.steps),
@@ -343,6 +344,7 @@ def main():
     ap.add_argument("--model", default="vgg11", choices=["vgg11", "vgg", "lenet"])
     ap.add_argument("--network", default=VGG11)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--round-by-round", action="store_true", help="one device round trip per sumcheck round (the reference's call pattern) instead of one per phase")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

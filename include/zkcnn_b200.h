@@ -111,6 +111,12 @@ int zk_sumcheck_init_phase2(zk_ctx *ctx);                                       
 int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *abcd /*4 Fr*/);  /* :103 */
 int zk_sumcheck_update1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *abc /*3 Fr*/);           /* :360 */
 int zk_sumcheck_update2(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *abc /*3 Fr*/);           /* :364 */
+/* Every round of one phase in one call, queued on the device without a host round trip in between: which = 1 / 2 for
+ * sumcheckUpdate1 / sumcheckUpdate2 of the current layer, 0 for sumcheckLiuUpdate.  previous_randoms[j] is the argument
+ * round j would get (previous_randoms[0] = 0); abc receives n_rounds x 3 Fr, the same values the per-round calls return.
+ * The reference's verifier draws all challenges of a phase before its first round (src/verifier.cpp:156-160,207,275-279),
+ * which is what makes this call possible for its own driver loop; the per-round entry points above stay the drop-in API. */
+int zk_sumcheck_update_batch(zk_ctx *ctx, int which, const uint64_t *previous_randoms, uint32_t n_rounds, uint64_t *abc);
 int zk_sumcheck_dotprod_finalize1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_1);      /* :146 */
 int zk_sumcheck_finalize1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_0, uint64_t *claim_1); /* :459 */
 int zk_sumcheck_finalize2(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_0, uint64_t *claim_1); /* :473 */

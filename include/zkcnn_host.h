@@ -20,7 +20,10 @@ enum {
     ZKH_REAL_GENERATORS  = 1,  /* Hyrax generators = standard G1 generator * challenge (default: the reference's all-infinity set) */
     ZKH_CHECK_PREDICATES = 2,  /* run the verifier-side wiring predicates and G1 checks too (full verification) */
     ZKH_WITNESS_RESIDENT = 4,  /* keep the witness on the device between proofs (skip the host->device copy if present) */
-    ZKH_FIXED_GENERATORS = 8   /* reuse the generators of the previous proof (public parameters), keep the window table */
+    ZKH_FIXED_GENERATORS = 8,  /* reuse the generators of the previous proof (public parameters), keep the window table */
+    ZKH_ROUND_BY_ROUND   = 16  /* one device round trip per sumcheck round (the reference's call pattern) instead of one per phase:
+                                 the verifier draws a phase's challenges before its first round either way (src/verifier.cpp:156-160),
+                                 so the transcript is the same; default is per phase (zk_sumcheck_update_batch) */
 };
 
 typedef struct {

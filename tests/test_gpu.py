@@ -10,7 +10,7 @@ import pytest
 
 import _cases as cases
 from conftest import GOLDEN, ROOT
-from zkcnn_b200._binding import (CHECK_PREDICATES, REAL_GENERATORS, WITNESS_RESIDENT, Context, Session, fr_from_words, fr_to_words,
+from zkcnn_b200._binding import (CHECK_PREDICATES, REAL_GENERATORS, ROUND_BY_ROUND, WITNESS_RESIDENT, Context, Session, fr_from_words, fr_to_words,
                                  g1_from_words, g1_to_words)
 
 pytestmark = pytest.mark.gpu
@@ -79,6 +79,9 @@ def test_hyrax(gpu_lib, kat):
     ("vgg", "small", 1, "smallvgg", 7, CHECK_PREDICATES, "smallvgg_p1_seed7"),
     ("vgg", "small", 2, "smallvgg", 7, CHECK_PREDICATES, "smallvgg_p2_seed7"),
     ("vgg", "small", 1, "smallvgg", 8, REAL_GENERATORS, "smallvgg_p1_seed8_realgens"),
+    # the reference's call pattern (one device round trip per sumcheck round) instead of one call per phase
+    ("lenet", "", 1, "lenet_syn", 3, CHECK_PREDICATES | ROUND_BY_ROUND, "lenet_syn_p1_seed3"),
+    ("vgg", "small", 1, "smallvgg", 7, CHECK_PREDICATES | ROUND_BY_ROUND, "smallvgg_p1_seed7"),
 ])
 def test_transcripts(gpu_host, synthetic_inputs, model, net, pics, inp, seed, flags, golden):
     net = synthetic_inputs["smallvgg_config"] if net == "small" else net
@@ -124,6 +127,9 @@ def test_vgg11_full_size(gpu_host, tmp_path):
         assert st2["fnv1a"] == st["fnv1a"] and st2["h2d_bytes"] == 0
         st3 = s.prove(1, WITNESS_RESIDENT | REAL_GENERATORS)
         assert st3["ok"] == 1 and st3["n_g1"] == st["n_g1"] and st3["fnv1a"] != st["fnv1a"]
+        # one device round trip per sumcheck round (the reference's call pattern): the same transcript
+        st4 = s.prove(1, WITNESS_RESIDENT | ROUND_BY_ROUND)
+        assert st4["ok"] == 1 and st4["fnv1a"] == st["fnv1a"]
 
 
 def test_fold_invariants_full_size(gpu_lib):

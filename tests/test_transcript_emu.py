@@ -36,6 +36,15 @@ def test_small_vgg_fft_conv(emu_host, synthetic_inputs):
     assert st["ok"] == 1
 
 
+def test_round_by_round_driver_gives_the_same_transcript(emu_host, synthetic_inputs):
+    """the default driver hands the device a whole phase of challenges at once (zk_sumcheck_update_batch); with
+    ZKH_ROUND_BY_ROUND it makes the reference's one call per round -- same messages, same order"""
+    from zkcnn_b200._binding import ROUND_BY_ROUND
+    cases.prove_and_compare(emu_host, "lenet", "", 1, synthetic_inputs["lenet_syn"], 3, CHECK_PREDICATES | ROUND_BY_ROUND, "lenet_syn_p1_seed3", GOLDEN)
+    cases.prove_and_compare(emu_host, "vgg", synthetic_inputs["smallvgg_config"], 1, synthetic_inputs["smallvgg"], 7, ROUND_BY_ROUND,
+                            "smallvgg_p1_seed7", GOLDEN)
+
+
 def test_shipped_lenet_image(emu_host):
     """the reference's own MNIST demo input (script/demo_lenet.sh), when the extracted data set is present"""
     path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "data", "lenet5.mnist.relu.max",

@@ -87,6 +87,36 @@ __global__ void k_lat(const fr_t *in, fr_t *out, long long *cyc) {
     TIC();
     __syncthreads();
     TOC();
+    // 12: 4 dependent Fp multiplications; 13: 4 dependent PAIRS of Fp multiplications (8 products)
+    fp_t fa, fb;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) { fa.v[j] = a.v[j & 7] ^ (j * 77u); fb.v[j] = b.v[j & 7] + j; }
+    fa.v[11] &= 0x0fffffffu; fb.v[11] &= 0x0fffffffu;
+    TIC();
+    fa = fa * fb; fa = fa * fb; fa = fa * fb; fa = fa * fb;
+    TOC();
+    fp_t fc = fb;
+    TIC();
+    {
+        fp_t::pair_t q = fp_t::mul2(fa, fb, fc, fb);
+        q = fp_t::mul2(q.a, fb, q.b, fa);
+        q = fp_t::mul2(q.a, fb, q.b, fa);
+        q = fp_t::mul2(q.a, fb, q.b, fa);
+        fa = q.a; fc = q.b;
+    }
+    TOC();
+    // 14: 4 dependent pairs of Fr multiplications
+    fr_t ra = a, rb = b;
+    TIC();
+    {
+        fr_t::pair_t q = fr_t::mul2(ra, b, rb, a);
+        q = fr_t::mul2(q.a, b, q.b, a);
+        q = fr_t::mul2(q.a, b, q.b, a);
+        q = fr_t::mul2(q.a, b, q.b, a);
+        ra = q.a; rb = q.b;
+    }
+    TOC();
+    if (fa.v[0] == 0x12345u && fc.v[3] == 7u) out[1] = ra + rb;
     out[threadIdx.x] = c + o + w;
     if (s == 0x12345678u) out[0] = a;
 }
@@ -109,7 +139,8 @@ int main() {
     cudaMemcpy(din, h.data(), h.size() * sizeof(fr_t), cudaMemcpyHostToDevice);
     const char *names[] = {"4 x mul_call (dependent)", "8 x field add/sub", "4 x lazy mac", "34 x redux full mask", "34 x redux role masks",
                            "24 x shfl", "warp sum by shuffles (1 fr)", "global load (cold) + use", "__threadfence", "atomicAdd ticket",
-                           "__threadfence_system", "__syncthreads"};
+                           "__threadfence_system", "__syncthreads", "4 x Fp mul_call (dependent)", "4 x Fp mul2 pairs (dependent)",
+                           "4 x Fr mul2 pairs (dependent)"};
     for (int rep = 0; rep < 3; ++rep) {
         cudaMemset(dc, 0, 64 * sizeof(long long));
         k_lat<<<1, 32>>>(din, dout, dc);
@@ -118,7 +149,7 @@ int main() {
         cudaMemcpy(c, dc, sizeof c, cudaMemcpyDeviceToHost);
         if (rep == 0) continue;
         printf("rep %d\n", rep);
-        for (int i = 0; i < 12; ++i) printf("  %-32s %8lld clk\n", names[i], c[i]);
+        for (int i = 0; i < 15; ++i) printf("  %-32s %8lld clk\n", names[i], c[i]);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;

@@ -39,6 +39,7 @@ void zk_ctx_destroy(zk_ctx *ctx) {
     try { rt::set_device(ctx->device); rt::sync(ctx->stream); } catch (...) {}
     rt::hfree_pinned(ctx->h_out);
     rt::hfree_pinned(ctx->res_h);
+    if (ctx->batch_h) rt::hfree_pinned(ctx->batch_h);
     for (auto &r : ctx->prof_pending) { rt::event_destroy(r.a); rt::event_destroy(r.b); }
     for (auto e : ctx->prof_pool) rt::event_destroy(e);
     rt::stream_destroy(ctx->stream);
@@ -414,6 +415,38 @@ int zk_sumcheck_update1(zk_ctx *ctx, const uint64_t *prev, uint64_t *abc) {
 int zk_sumcheck_update2(zk_ctx *ctx, const uint64_t *prev, uint64_t *abc) {
     if (!ctx || !ctx->circuit_ready || ctx->sumcheck_id >= ctx->r_v.size()) { g_last_error = "bad state"; return -1; }
     return sumcheck_update(ctx, prev, abc, ctx->r_v[ctx->sumcheck_id]);
+}
+
+// All rounds of one phase in one call (see round_quadratic_batch): which = 1 / 2: sumcheckUpdate1 / sumcheckUpdate2 of the
+// current layer, 0: sumcheckLiuUpdate.  prevs[j] is the previous_random of round j (prevs[0] = 0), abc receives n x 3 Fr.
+int zk_sumcheck_update_batch(zk_ctx *ctx, int which, const uint64_t *prevs_p, uint32_t n_rounds, uint64_t *abc) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ctx->circuit_ready && prevs_p && abc && n_rounds >= 1 && which >= 0 && which <= 2, "bad arguments");
+    rt::set_device(ctx->device);
+    std::vector<fr_t> prevs(n_rounds);
+    for (uint32_t j = 0; j < n_rounds; ++j) prevs[j] = fr_load(prevs_p + 4 * j);
+    if (which == 0) {
+        ZK_REQUIRE(ctx->sumcheck_id == 0 && ctx->round == 0, "bad state");
+        round_quadratic_batch(ctx, prevs.data(), n_rounds, 2u, [&](uint32_t j, const round_rec_t &rec, const fr_t *h_res) {
+            fr_t ret[3];
+            round_quadratic_book(ctx, rec, h_res, ret);
+            for (int k = 0; k < 3; ++k) fr_store(abc + 12 * j + 4 * k, ret[k]);
+        });
+    } else {
+        ZK_REQUIRE(ctx->sumcheck_id < ctx->r_u.size() && ctx->round == 0, "bad state");
+        std::vector<fr_t> &r_arr = which == 1 ? ctx->r_u[ctx->sumcheck_id] : ctx->r_v[ctx->sumcheck_id];
+        ZK_REQUIRE(n_rounds <= r_arr.size() + 1, "too many rounds");
+        for (uint32_t j = 1; j < n_rounds; ++j) r_arr[j - 1] = prevs[j];
+        round_quadratic_batch(ctx, prevs.data(), n_rounds, 3u, [&](uint32_t j, const round_rec_t &rec, const fr_t *h_res) {
+            ctx->add_term = ctx->add_term * (fr_t::one() - prevs[j]);   // src/prover.cpp:375-378
+            fr_t ret[3];
+            round_quadratic_book(ctx, rec, h_res, ret);
+            ret[1] = ret[1] - ctx->add_term;
+            ret[2] = ret[2] + ctx->add_term;
+            for (int k = 0; k < 3; ++k) fr_store(abc + 12 * j + 4 * k, ret[k]);
+        });
+    }
+    ZK_API_END
 }
 
 int zk_sumcheck_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_0, uint64_t *claim_1) {   // src/prover.cpp:459-471

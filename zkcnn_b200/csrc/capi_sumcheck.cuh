@@ -493,23 +493,32 @@ static void wait_tagged(zk_ctx *ctx, fr_t abc[3]) {
     for (int k = 0; k < 3; ++k) memcpy(abc[k].v, w + 8 * k, 32);
 }
 
-// One call of sumcheckUpdateEach for both table pairs (src/prover.cpp:396-426).  `mask` selects the pairs that take part
-// (Liu: only pair 1).  Returns the sum of the pairs' round polynomials in abc[3]; add_term is updated for collapses.
-static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t abc[3]) {
+// Which table pairs took part in a round and how: what the host needs to book the round's results.
+struct round_rec_t {
+    bool any_quad = false, any_final = false, first = false;
+    bool quad[2] = {false, false}, fin[2] = {false, false};
+};
+// Launch the kernels of one round.  slot_d == nullptr: interactive round, the results go to the host mailbox and are
+// awaited by the caller (round_quadratic).  Otherwise the results are left at slot_d (16 Fr: abc at 0, collapse values at
+// 8) and nothing is awaited: the table sizes, grids and collapses of a round do not depend on its data, so a whole phase
+// can be queued back to back (round_quadratic_batch).  The host-side table state is advanced either way.
+static round_rec_t round_quadratic_launch(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t *slot_d) {
     ensure_round_scratch(ctx);
     const bool first = ctx->round == 1;
+    round_rec_t rec;
+    rec.first = first;
     round_args_t A;
     memset(&A, 0, sizeof A);
     A.r = prev;
     A.acc = ctx->round_acc.as<unsigned long long>();
     A.counter = ctx->counters.as<uint32_t>();
-    A.out = ctx->res_d;
+    A.out = slot_d ? slot_d : ctx->res_d;
     final_fold_args_t F;
     memset(&F, 0, sizeof F);
     F.r = prev;
-    F.out = ctx->res_d + 8;
-    bool any_quad = false, any_final = false;
-    bool quad[2] = {false, false}, fin[2] = {false, false};
+    F.out = (slot_d ? slot_d : ctx->res_d) + 8;
+    bool &any_quad = rec.any_quad, &any_final = rec.any_final;
+    bool (&quad)[2] = rec.quad, (&fin)[2] = rec.fin;
     uint32_t gx = 0, max_live_pairs = 0, pairs_of[2] = {0, 0};
     uint64_t fold_bytes = 0;   // algorithmic: read V and mult (live entries), write both halves
     for (int b = 0; b < 2; ++b) {
@@ -536,9 +545,11 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
         }
     }
     // the last kernel of the round publishes the sequence number the host waits on
-    ++ctx->seq;
-    if (any_final) { F.flag = ctx->flag_d; F.seq = ctx->seq; }
-    else { A.tagged = reinterpret_cast<uint4 *>(ctx->tag_d); A.seq = ctx->seq; }
+    if (!slot_d) {
+        ++ctx->seq;
+        if (any_final) { F.flag = ctx->flag_d; F.seq = ctx->seq; }
+        else { A.tagged = reinterpret_cast<uint4 *>(ctx->tag_d); A.seq = ctx->seq; }
+    }
     // tables up to 2^16 entries: four lanes per output pair (latency); beyond: one thread per output pair, grid-stride
     // (throughput), fed by TMA once the tables are large enough to stream from HBM
     const bool thin = max_live_pairs <= ctx->thin_max_pairs;
@@ -559,30 +570,67 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
 #endif
     else if (any_quad) ZK_KLAUNCH_C(ctx, cls, fold_bytes, k_round_quad, dim3(gx), dim3(kRoundBlock), 0, A);
     if (any_final) ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
-    const fr_t *h_res = ctx->res_h;
-    abc[0] = abc[1] = abc[2] = fr_t::zero();
-    if (any_final) {
-        wait_mailbox(ctx);
-        if (any_quad)
-            for (int k = 0; k < 3; ++k) abc[k] = h_res[k];   // already summed over both pairs by the kernel
-    } else if (any_quad) wait_tagged(ctx, abc);
+    // the table state follows from the sizes alone
     for (int b = 0; b < 2; ++b) {
         pair_t &P = ctx->pair[b];
         if (fin[b]) {
+            P.collapsed = true;
+            P.n_eval = 0;
+        } else if (quad[b] && !first) {
+            table_advance(P.v);
+            table_advance(P.m);
+            P.n_eval >>= 1;
+            P.live = (P.live + 1) >> 1;
+        }
+    }
+    return rec;
+}
+// book the results of a round (h_res: host copy of its 16-Fr result block): collapse values into add_term, (a, b, c) out
+static void round_quadratic_book(zk_ctx *ctx, const round_rec_t &rec, const fr_t *h_res, fr_t abc[3]) {
+    abc[0] = abc[1] = abc[2] = fr_t::zero();
+    if (rec.any_quad)
+        for (int k = 0; k < 3; ++k) abc[k] = h_res[k];   // already summed over both pairs by the kernel
+    for (int b = 0; b < 2; ++b)
+        if (rec.fin[b]) {
+            pair_t &P = ctx->pair[b];
             P.cv = h_res[8 + 2 * b];
             P.cm = h_res[8 + 2 * b + 1];
             ctx->add_term = ctx->add_term + P.cv * P.cm;
-            P.collapsed = true;
-            P.n_eval = 0;
-        } else if (quad[b]) {
-            if (!first) {
-                table_advance(P.v);
-                table_advance(P.m);
-                P.n_eval >>= 1;
-                P.live = (P.live + 1) >> 1;
-            }
         }
+}
+// One call of sumcheckUpdateEach for both table pairs (src/prover.cpp:396-426).  `mask` selects the pairs that take part
+// (Liu: only pair 1).  Returns the sum of the pairs' round polynomials in abc[3]; add_term is updated for collapses.
+static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t abc[3]) {
+    const round_rec_t rec = round_quadratic_launch(ctx, prev, mask, nullptr);
+    if (rec.any_final) {
+        wait_mailbox(ctx);
+        round_quadratic_book(ctx, rec, ctx->res_h, abc);
+    } else if (rec.any_quad) {
+        fr_t got[16];
+        wait_tagged(ctx, got);
+        round_quadratic_book(ctx, rec, got, abc);
+    } else round_quadratic_book(ctx, rec, ctx->res_h, abc);
+}
+// A whole phase queued without waiting for the host in between: round j folds with prevs[j] (prevs[0] = 0).  Legitimate
+// because the verifier draws every challenge of a phase BEFORE its first round (src/verifier.cpp:156-160, 207, 275-279):
+// the prover messages are the same field elements as in the round-by-round protocol, in the same order.  `hook` books
+// round j on the host (add_term scaling, collapse values) once all results are back.
+template <class Hook> static void round_quadratic_batch(zk_ctx *ctx, const fr_t *prevs, uint32_t n_rounds, unsigned mask, Hook hook) {
+    ensure_round_scratch(ctx);
+    ctx->batch_res.ensure((size_t) n_rounds * 16 * sizeof(fr_t));
+    if (ctx->batch_cap < n_rounds) {
+        if (ctx->batch_h) rt::hfree_pinned(ctx->batch_h);
+        ctx->batch_h = static_cast<fr_t *>(rt::hmalloc_pinned((size_t) n_rounds * 16 * sizeof(fr_t)));
+        ctx->batch_cap = n_rounds;
     }
+    std::vector<round_rec_t> recs(n_rounds);
+    for (uint32_t j = 0; j < n_rounds; ++j) {
+        ++ctx->round;
+        recs[j] = round_quadratic_launch(ctx, prevs[j], mask, ctx->batch_res.as<fr_t>() + (size_t) j * 16);
+    }
+    rt::d2h(ctx->batch_h, ctx->batch_res.p, (size_t) n_rounds * 16 * sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    for (uint32_t j = 0; j < n_rounds; ++j) hook(j, recs[j], ctx->batch_h + (size_t) j * 16);
 }
 
 // value of V_mult[b][0] at the end of a phase (src/prover.cpp:462-463,476-477,490)

@@ -106,6 +106,9 @@ struct zk_ctx {
     // sequence number; the host spins on the sequence number instead of copying + synchronising the stream
     zk::fr_t *res_h = nullptr, *res_d = nullptr;          // [32] host / device view
     uint32_t *flag_h = nullptr, *flag_d = nullptr;
+    zk::rt::dbuf batch_res;                               // [rounds][16] result blocks of a batched phase
+    zk::fr_t *batch_h = nullptr;
+    uint32_t batch_cap = 0;
     uint32_t *tag_h = nullptr, *tag_d = nullptr;          // [32] tagged mailbox (publish_tagged)
     uint32_t seq = 0;
     uint32_t thin_max_pairs = 1u << 14;      // see zk_set_tunable

@@ -430,6 +430,47 @@ template <class C> struct alignas(16) mont_t {
 #pragma unroll
         for (int i = 0; i < N; ++i) r[i] = borrow ? E[i] : d[i];
     }
+    // Two independent multiplications with their rows interleaved in program order: the carry chains of the two products
+    // do not depend on each other, so a single warp keeps the multiplier pipe busy while one chain waits for its carry.
+    // A lone warp needs ~2340 clk per Fp multiplication against a pipe time of 1152 (tools/latbench.cu): the pair costs
+    // about as much as one.  This is what the latency-bound curve kernels (few warps per SM, long dependent chains of
+    // point operations) are built on.
+    static __device__ __forceinline__ void mul_wide2(uint32_t *r0, const uint32_t *a0, const uint32_t *b0, uint32_t *r1, const uint32_t *a1,
+                                                     const uint32_t *b1) {
+        const uint32_t *p = C::mod_rt();
+        uint32_t pm[N + 1];
+#pragma unroll
+        for (int i = 0; i <= N; ++i) pm[i] = p[i];
+        uint32_t E0[N], O0[N], E1[N], O1[N];
+        wide_row<true>(E0, O0, a0, b0[0], pm);
+        wide_row<true>(E1, O1, a1, b1[0], pm);
+        wide_row<false>(O0, E0, a0, b0[1], pm);
+        wide_row<false>(O1, E1, a1, b1[1], pm);
+#pragma unroll
+        for (int i = 2; i < N; i += 2) {
+            wide_row<false>(E0, O0, a0, b0[i], pm);
+            wide_row<false>(E1, O1, a1, b1[i], pm);
+            wide_row<false>(O0, E0, a0, b0[i + 1], pm);
+            wide_row<false>(O1, E1, a1, b1[i + 1], pm);
+        }
+        wide_finish(r0, E0, O0, pm);
+        wide_finish(r1, E1, O1, pm);
+    }
+    // merge (E >> 32) + O and subtract p once if needed
+    static __device__ __forceinline__ void wide_finish(uint32_t *r, uint32_t *E, const uint32_t *O, const uint32_t *pm) {
+        asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(O[1]));
+#pragma unroll
+        for (int i = 1; i < N - 1; ++i) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(E[i]) : "r"(O[i + 1]));
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[N - 1]));
+        uint32_t d[N];
+        d[0] = ptx::sub_cc(E[0], pm[0]);
+#pragma unroll
+        for (int i = 1; i < N; ++i) d[i] = ptx::subc_cc(E[i], pm[i]);
+        uint32_t borrow = ptx::subc(0, 0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = borrow ? E[i] : d[i];
+    }
+
     // ---- unreduced product t[0 .. 2N-1] = a * b as plain integers (the multiplication half of mul_wide) ----------------
     // Same even/odd column scheme: `t` collects the limb-aligned wide products, `odd` the ones shifted by one limb.
     //   row: odd[0..N-1] += x[1,3,..] * y with the top pair written fresh; even[0..N-1] += x[0,2,..] * y; the carry out of
@@ -476,6 +517,25 @@ template <class C> struct alignas(16) mont_t {
         return r;
     }
 #endif
+    struct pair_t { mont_t a, b; };
+#if !defined(ZK_EMU) && !defined(ZK_HOST_ONLY)
+    static __device__ __noinline__ pair_t mul2_call(mont_t a0, mont_t b0, mont_t a1, mont_t b1) {
+        pair_t r;
+        mul_wide2(r.a.v, a0.v, b0.v, r.b.v, a1.v, b1.v);
+        return r;
+    }
+#endif
+    // (a0 * b0, a1 * b1)
+    static ZK_HD __forceinline__ pair_t mul2(const mont_t &a0, const mont_t &b0, const mont_t &a1, const mont_t &b1) {
+#if ZK_FIELD_PTX
+        return mul2_call(a0, b0, a1, b1);
+#else
+        pair_t r;
+        r.a = a0 * b0;
+        r.b = a1 * b1;
+        return r;
+#endif
+    }
     friend ZK_HD __forceinline__ mont_t operator*(const mont_t &a, const mont_t &b) {
 #if ZK_FIELD_PTX
 #ifdef ZK_INLINE_FIELD_MUL

@@ -164,6 +164,7 @@ int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
     verifier v(&p, p.C);
     v.checkPredicates = (flags & ZKH_CHECK_PREDICATES) != 0;
     v.realGenerators = (flags & ZKH_REAL_GENERATORS) != 0;
+    v.batchRounds = (flags & ZKH_ROUND_BY_ROUND) == 0;
     if ((flags & ZKH_FIXED_GENERATORS) && !s->last_gens.empty()) v.fixedGenerators = &s->last_gens;
     const bool ok = v.verify();
     auto t1 = std::chrono::steady_clock::now();

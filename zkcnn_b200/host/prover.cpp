@@ -217,6 +217,24 @@ quadratic_poly prover::sumcheckLiuUpdate(const F &previous_random) {   // src/pr
     return quadratic_poly(c[0], c[1], c[2]);
 }
 
+vector<quadratic_poly> prover::sumcheckUpdateAll(int which, const vector<F> &r, int n_rounds) {
+    vector<quadratic_poly> polys;
+    if (n_rounds <= 0) return polys;
+    prove_timer.start();
+    vector<F> prevs(n_rounds), c((size_t) 3 * n_rounds);
+    prevs[0].clear();
+    for (int j = 1; j < n_rounds; ++j) prevs[j] = r[j - 1];
+    check(zk_sumcheck_update_batch(ctx_, which, w(prevs[0]), (uint32_t) n_rounds, w(c[0])), "zk_sumcheck_update_batch");
+    prove_timer.stop();
+    proof_size += (u64) ZK_F_BYTES * 3 * n_rounds;
+    polys.reserve(n_rounds);
+    for (int j = 0; j < n_rounds; ++j) {
+        if (transcript_) for (int k = 0; k < 3; ++k) transcript_->put_fr(w(c[3 * j + k]));
+        polys.emplace_back(c[3 * j], c[3 * j + 1], c[3 * j + 2]);
+    }
+    return polys;
+}
+
 hyrax_bls12_381::polyProver &prover::commitInput(const vector<G> &gens) {   // src/prover.cpp:503-511
     if (C.circuit[0].size != (1ULL << C.circuit[0].bit_length)) {
         val[0].resize(1ULL << C.circuit[0].bit_length);

@@ -59,6 +59,11 @@ public:
     void sumcheckLiuInit(const vector<F> &s_u, const vector<F> &s_v);
     quadratic_poly sumcheckLiuUpdate(const F &previous_random);
 
+    // Not in the reference: every round of a phase in one device call (zk_sumcheck_update_batch).  which = 1 / 2 / 0 stands
+    // for sumcheckUpdate1 / sumcheckUpdate2 / sumcheckLiuUpdate; r holds the phase's challenges, drawn by the verifier before
+    // the first round (src/verifier.cpp:156-160,207,275-279); round j is folded with r[j - 1].  Returns the n_rounds messages.
+    vector<quadratic_poly> sumcheckUpdateAll(int which, const vector<F> &r, int n_rounds);
+
     hyrax_bls12_381::polyProver &commitInput(const vector<G> &gens);
 
     timer prove_timer;

@@ -308,6 +308,8 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
         else p->sumcheckInitPhase1(relu_rou);
 
         F prev = F_ZERO;
+        vector<quadratic_poly> all;
+        if (batchRounds && !dot) all = p->sumcheckUpdateAll(1, r_u[i], cur.max_bl_u);
         for (int j = 0; j < cur.max_bl_u; ++j) {
             F at0p1, atr;
             if (dot) {
@@ -315,7 +317,7 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
                 at0p1 = poly.d + poly.eval(F_ONE);
                 atr = poly.eval(r_u[i][j]);
             } else {
-                quadratic_poly poly = p->sumcheckUpdate1(prev);
+                quadratic_poly poly = batchRounds ? all[j] : p->sumcheckUpdate1(prev);
                 at0p1 = poly.c + poly.eval(F_ONE);
                 atr = poly.eval(r_u[i][j]);
             }
@@ -343,8 +345,9 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
             total_timer.stop();
             p->sumcheckInitPhase2();
             prev = F_ZERO;
+            if (batchRounds) all = p->sumcheckUpdateAll(2, r_v[i], cur.max_bl_v);
             for (int j = 0; j < cur.max_bl_v; ++j) {
-                quadratic_poly poly = p->sumcheckUpdate2(prev);
+                quadratic_poly poly = batchRounds ? all[j] : p->sumcheckUpdate2(prev);
                 if (poly.c + poly.eval(F_ONE) != sum) {
                     fprintf(stderr, "Verification fail, phase2, circuit level %d, current bit %d, total is %d\n", (int) i, j, (int) cur.max_bl_v);
                     return false;
@@ -398,8 +401,10 @@ bool verifier::verifyFirstLayer() {   // src/verifier.cpp:268-357
 
     p->sumcheckLiuInit(sig_u, sig_v);
     F prev = F_ZERO;
+    vector<quadratic_poly> all;
+    if (batchRounds) all = p->sumcheckUpdateAll(0, r_u[0], in.bit_length);
     for (int j = 0; j < in.bit_length; ++j) {
-        quadratic_poly poly = p->sumcheckLiuUpdate(prev);
+        quadratic_poly poly = batchRounds ? all[j] : p->sumcheckLiuUpdate(prev);
         if (poly.c + poly.eval(F_ONE) != sum) {
             fprintf(stderr, "Liu fail, circuit 0, current bit %d\n", j);
             return false;

@@ -47,6 +47,8 @@ public:
     // false (reference behaviour): generators are getG1basePoint() * random with the base point cleared by initPairing,
     // i.e. all infinity (src/verifier.cpp:125, mcl bn.hpp:924).  true: the standard G1 generator is used as base point.
     bool realGenerators = false;
+    // one device call per phase (prover::sumcheckUpdateAll) instead of one per round; the messages and their order are the same
+    bool batchRounds = true;
     // Hyrax generators are public parameters; when set, they are reused instead of redrawn (the challenge stream is
     // still advanced as if they had been drawn)
     const vector<G> *fixedGenerators = nullptr;
