@@ -99,6 +99,10 @@ int zk_circuit_layer(zk_ctx *ctx, uint32_t layer_id, const zk_layer_desc *desc);
 int zk_circuit_end(zk_ctx *ctx);     /* builds the device-resident gate schedules */
 /* prover::val[layer_id] (src/prover.hpp:49) */
 int zk_witness_layer(zk_ctx *ctx, uint32_t layer_id, const uint64_t *val, uint64_t n);
+/* double-buffered upload: copy the NEXT proof's prover::val[layer_id] on a second stream while the current proof runs
+ * (val must stay valid and unchanged until the commit), then make all prefetched layers current */
+int zk_witness_layer_prefetch(zk_ctx *ctx, uint32_t layer_id, const uint64_t *val, uint64_t n);
+int zk_witness_commit_prefetch(zk_ctx *ctx);
 
 /* ---- GKR prover: one entry point per public member of class prover ---------------------------------------------- */
 int zk_prover_init(zk_ctx *ctx);                                                             /* prover.cpp:17  */

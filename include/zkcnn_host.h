@@ -21,6 +21,8 @@ enum {
     ZKH_CHECK_PREDICATES = 2,  /* run the verifier-side wiring predicates and G1 checks too (full verification) */
     ZKH_WITNESS_RESIDENT = 4,  /* keep the witness on the device between proofs (skip the host->device copy if present) */
     ZKH_FIXED_GENERATORS = 8,  /* reuse the generators of the previous proof (public parameters), keep the window table */
+    ZKH_PREFETCH_NEXT    = 32, /* once this proof has its witness, start copying the witness for the NEXT zkh_prove on a second stream
+                                 (double buffering: the copy overlaps this proof; the next proof adopts it instead of uploading) */
     ZKH_ROUND_BY_ROUND   = 16  /* one device round trip per sumcheck round (the reference's call pattern) instead of one per phase:
                                  the verifier draws a phase's challenges before its first round either way (src/verifier.cpp:156-160),
                                  so the transcript is the same; default is per phase (zk_sumcheck_update_batch) */
@@ -54,6 +56,9 @@ int zkh_input_file(zkh_session *s, const char *path);                    /* the 
 int zkh_input_values(zkh_session *s, const double *values, uint64_t n);  /* same numbers, in memory */
 int zkh_build(zkh_session *s);                                           /* circuit + witness (neuralNetwork::create) */
 int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out);
+/* start the host->device copy of the witness for the next zkh_prove now, on a second stream (what ZKH_PREFETCH_NEXT does
+ * from inside a proof) */
+int zkh_prefetch_witness(zkh_session *s);
 const uint8_t *zkh_proof(zkh_session *s, uint64_t *n_bytes);             /* proof of the last zkh_prove */
 int zkh_inferred_class(zkh_session *s, int picture);
 void *zkh_context(zkh_session *s);   /* the zk_ctx of this session's prover (NULL before the first proof); for zk_profile_* */

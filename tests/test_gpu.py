@@ -10,7 +10,7 @@ import pytest
 
 import _cases as cases
 from conftest import GOLDEN, ROOT
-from zkcnn_b200._binding import (CHECK_PREDICATES, REAL_GENERATORS, ROUND_BY_ROUND, WITNESS_RESIDENT, Context, Session, fr_from_words, fr_to_words,
+from zkcnn_b200._binding import (CHECK_PREDICATES, PREFETCH_NEXT, REAL_GENERATORS, ROUND_BY_ROUND, WITNESS_RESIDENT, Context, Session, fr_from_words, fr_to_words,
                                  g1_from_words, g1_to_words)
 
 pytestmark = pytest.mark.gpu
@@ -130,6 +130,13 @@ def test_vgg11_full_size(gpu_host, tmp_path):
         # one device round trip per sumcheck round (the reference's call pattern): the same transcript
         st4 = s.prove(1, WITNESS_RESIDENT | ROUND_BY_ROUND)
         assert st4["ok"] == 1 and st4["fnv1a"] == st["fnv1a"]
+        # double-buffered witness: this proof uploads and starts the copy for the next one (SM-driven, from mapped host memory),
+        # the next one adopts it
+        st5 = s.prove(1, PREFETCH_NEXT)
+        st6 = s.prove(1, PREFETCH_NEXT)
+        st7 = s.prove(1, 0)
+        for x in (st5, st6, st7):
+            assert x["ok"] == 1 and x["fnv1a"] == st["fnv1a"] and x["h2d_bytes"] > 0
 
 
 def test_fold_invariants_full_size(gpu_lib):

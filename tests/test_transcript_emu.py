@@ -7,7 +7,7 @@ import pytest
 
 import _cases as cases
 from conftest import GOLDEN
-from zkcnn_b200._binding import CHECK_PREDICATES, REAL_GENERATORS, Session
+from zkcnn_b200._binding import CHECK_PREDICATES, PREFETCH_NEXT, REAL_GENERATORS, Session
 
 
 def test_lenet_synthetic(emu_host, synthetic_inputs):
@@ -70,6 +70,23 @@ def test_repeat_proofs_and_resident_witness(emu_host, synthetic_inputs):
     assert a["ok"] and b["ok"] and c["ok"]
     assert a["h2d_bytes"] > 0 and b["h2d_bytes"] == 0 and c["h2d_bytes"] == 0
     assert pa == pc and pa != pb
+    assert pa == open(os.path.join(GOLDEN, "lenet_syn_p1_seed3.transcript.bin"), "rb").read()
+
+
+def test_prefetched_witness_gives_the_same_proofs(emu_host, synthetic_inputs):
+    """double-buffered upload: the witness of the next proof is copied while the current one runs; transcripts unchanged"""
+    with Session(emu_host, "lenet", "", 1) as s:
+        s.input_file(synthetic_inputs["lenet_syn"])
+        s.build()
+        a = s.prove(3, PREFETCH_NEXT)     # uploads, then starts the copy for the next proof
+        pa = s.proof()
+        b = s.prove(9, PREFETCH_NEXT)     # adopts the prefetched copy, starts the next one
+        s.prefetch_witness()              # explicit call: replaces the pending copy
+        c = s.prove(3, 0)
+        pc = s.proof()
+    assert a["ok"] and b["ok"] and c["ok"] and pa == pc
+    # (the first proof pads val[0] to a power of two on the host, src/prover.cpp:504-508: later copies are that much longer)
+    assert 0 < a["h2d_bytes"] <= b["h2d_bytes"] <= c["h2d_bytes"]
     assert pa == open(os.path.join(GOLDEN, "lenet_syn_p1_seed3.transcript.bin"), "rb").read()
 
 

@@ -268,7 +268,7 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-REAL_GENERATORS, CHECK_PREDICATES, WITNESS_RESIDENT, FIXED_GENERATORS, ROUND_BY_ROUND = 1, 2, 4, 8, 16
+REAL_GENERATORS, CHECK_PREDICATES, WITNESS_RESIDENT, FIXED_GENERATORS, ROUND_BY_ROUND, PREFETCH_NEXT = 1, 2, 4, 8, 16, 32
 
 
 class HostLib:
@@ -288,6 +288,7 @@ class HostLib:
         d.zkh_input_file.argtypes = [C.c_void_p, C.c_char_p]
         d.zkh_input_values.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64]
         d.zkh_build.argtypes = [C.c_void_p]
+        d.zkh_prefetch_witness.argtypes = [C.c_void_p]
         d.zkh_prove.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(Stats)]
         d.zkh_proof.restype = C.POINTER(C.c_uint8)
         d.zkh_proof.argtypes = [C.c_void_p, _u64p]
@@ -336,6 +337,9 @@ class Session:
 
     def build(self):
         self._check(self.lib.dll.zkh_build(self.h), "zkh_build")
+
+    def prefetch_witness(self):
+        self._check(self.lib.dll.zkh_prefetch_witness(self.h), "zkh_prefetch_witness")
 
     def prove(self, seed, flags=0):
         st = Stats()

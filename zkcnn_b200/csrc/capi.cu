@@ -40,8 +40,10 @@ void zk_ctx_destroy(zk_ctx *ctx) {
     rt::hfree_pinned(ctx->h_out);
     rt::hfree_pinned(ctx->res_h);
     if (ctx->batch_h) rt::hfree_pinned(ctx->batch_h);
+    if (ctx->stage_h) rt::hfree_pinned(ctx->stage_h);
     for (auto &r : ctx->prof_pending) { rt::event_destroy(r.a); rt::event_destroy(r.b); }
     for (auto e : ctx->prof_pool) rt::event_destroy(e);
+    if (ctx->copy_stream) { try { rt::sync(ctx->copy_stream); } catch (...) {} rt::stream_destroy(ctx->copy_stream); }
     rt::stream_destroy(ctx->stream);
     delete ctx;
 }
@@ -159,6 +161,70 @@ int zk_witness_layer(zk_ctx *ctx, uint32_t id, const uint64_t *val, uint64_t n) 
     if (cap > n) rt::dzero(L.val.as<fr_t>() + n, (cap - n) * sizeof(fr_t), ctx->stream);
     rt::sync(ctx->stream);
     L.n_val = n;
+    ZK_API_END
+}
+
+// The NEXT proof's witness, copied on a second stream while the current proof is running (double buffering of the
+// host->device transfer).  The host buffer must stay valid until zk_witness_commit_prefetch.
+int zk_witness_layer_prefetch(zk_ctx *ctx, uint32_t id, const uint64_t *val, uint64_t n) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && id < ctx->n_layers && (val || n == 0), "bad witness layer");
+    rt::set_device(ctx->device);
+    if (!ctx->copy_stream) ctx->copy_stream = rt::stream_create(false);
+    layer_t &L = ctx->layers[id];
+    uint64_t cap = n;
+    if (id == 0) { cap = 1; while (cap < n) cap <<= 1; }
+    L.val_next.ensure(std::max<uint64_t>(1, cap) * sizeof(fr_t));
+    // In pieces, with at most two of them queued: copies of different streams are served in submission order, so a small
+    // host->device copy of the running proof (challenges, generators) would otherwise wait for this whole layer (the
+    // 2^24-entry input layer alone is 10 ms of PCIe time).  The pacing blocks the caller: call this from a helper thread.
+    const size_t piece = 4u << 20, bytes = n * sizeof(fr_t);
+    // preferred: the SMs pull the layer out of mapped host memory (k_copy_from_host), leaving the copy engine to the proof
+#ifndef ZK_EMU   // (the test emulator runs one grid at a time: no launches from the helper thread there)
+    const void *mapped = bytes ? rt::host_device_ptr(val) : nullptr;
+    if (mapped && bytes % 16 == 0) {
+        ZK_LAUNCH(k_copy_from_host, dim3(bytes >= (64u << 20) ? 32 : 8), dim3(kBlock), 0, ctx->copy_stream, static_cast<uint4 *>(L.val_next.p),
+                  static_cast<const uint4 *>(mapped), (uint64_t) (bytes / 16));
+        rt::check_launch("k_copy_from_host");
+        if (cap > n) rt::dzero(L.val_next.as<fr_t>() + n, (cap - n) * sizeof(fr_t), ctx->copy_stream);
+        L.n_val_next = n;
+        L.next_ready = true;
+        return 0;
+    }
+    cudaEvent_t ev[2];
+    for (auto &e : ev) rt::check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+#endif
+    size_t k = 0;
+    for (size_t off = 0; off < bytes; off += piece, ++k) {
+#ifndef ZK_EMU
+        if (k >= 2) rt::check(cudaEventSynchronize(ev[k & 1]), "cudaEventSynchronize");
+#endif
+        rt::h2d(static_cast<char *>(L.val_next.p) + off, reinterpret_cast<const char *>(val) + off, std::min(piece, bytes - off), ctx->copy_stream);
+#ifndef ZK_EMU
+        rt::check(cudaEventRecord(ev[k & 1], ctx->copy_stream), "cudaEventRecord");
+#endif
+    }
+#ifndef ZK_EMU
+    for (auto &e : ev) cudaEventDestroy(e);
+#endif
+    if (cap > n) rt::dzero(L.val_next.as<fr_t>() + n, (cap - n) * sizeof(fr_t), ctx->copy_stream);
+    L.n_val_next = n;
+    L.next_ready = true;
+    ZK_API_END
+}
+// wait for the prefetched layers and make them the current witness (the previous buffers become the next shadow copies)
+int zk_witness_commit_prefetch(zk_ctx *ctx) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx, "null ctx");
+    rt::set_device(ctx->device);
+    if (ctx->copy_stream) rt::sync(ctx->copy_stream);
+    rt::sync(ctx->stream);
+    for (auto &L : ctx->layers)
+        if (L.next_ready) {
+            std::swap(L.val, L.val_next);
+            L.n_val = L.n_val_next;
+            L.next_ready = false;
+        }
     ZK_API_END
 }
 

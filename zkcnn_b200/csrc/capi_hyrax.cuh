@@ -32,7 +32,7 @@ static void msm_prepare_table(zk_ctx *ctx, hyrax_t &H, const uint64_t *gens, uin
     H.n_gens = n_gens;
     rt::dbuf &tmp = H.gens_jac;
     tmp.ensure((size_t) n_gens * sizeof(g1_jac_t));
-    rt::h2d(tmp.p, gens, (size_t) n_gens * sizeof(g1_jac_t), ctx->stream);
+    h2d_staged(ctx, tmp.p, gens, (size_t) n_gens * sizeof(g1_jac_t));
     H.gens_aff.ensure((size_t) n_gens * sizeof(g1_aff_t));
     ZK_KLAUNCH(ctx, k_g1_to_affine, dim3(grid_for(n_gens)), dim3(kBlock), 0, tmp.as<g1_jac_t>(), H.gens_aff.as<g1_aff_t>(), n_gens);
     H.table.ensure((size_t) kMsmWindows * n_gens * sizeof(g1_aff_t));
@@ -158,8 +158,7 @@ int zk_poly_commit(zk_ctx *ctx, uint64_t *comm_out, uint32_t n_out) {   // polyP
     zk::rt::dbuf &out = H.pts_out;
     out.ensure((size_t) rsize * sizeof(zk::g1_jac_t));
     zk::msm_run(ctx, H, H.Z, lsize, rsize, out.as<zk::g1_jac_t>());
-    zk::rt::d2h(comm_out, out.p, (size_t) rsize * sizeof(zk::g1_jac_t), ctx->stream);
-    zk::rt::sync(ctx->stream);
+    zk::d2h_staged(ctx, comm_out, out.p, (size_t) rsize * sizeof(zk::g1_jac_t));
     ZK_API_END
 }
 
@@ -422,11 +421,10 @@ int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scal
     rt::dbuf &dk = ctx->fb_k, &dout = ctx->fb_out;
     dk.ensure(n * 32);
     dout.ensure(n * sizeof(g1_jac_t));
-    rt::h2d(dk.p, scalars, n * 32, ctx->stream);
+    h2d_staged(ctx, dk.p, scalars, n * 32);
     ZK_KLAUNCH(ctx, k_fixed_base_mul, dim3((uint32_t) ((n + 127) / 128)), dim3(128), 0, ctx->fb_comb.as<g1_aff_t>(), dk.as<fr_t>(), (uint32_t) n,
                dout.as<g1_jac_t>());
-    rt::d2h(out, dout.p, n * sizeof(g1_jac_t), ctx->stream);
-    rt::sync(ctx->stream);
+    d2h_staged(ctx, out, dout.p, n * sizeof(g1_jac_t));
     ZK_API_END
 }
 

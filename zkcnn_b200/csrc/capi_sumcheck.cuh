@@ -361,6 +361,33 @@ static void table_advance(table_t &T) {
     T.next ^= 1;
 }
 
+// Transfers between PAGEABLE caller memory and the device, staged through a page-locked buffer of the context: a pageable
+// cudaMemcpyAsync is served in order with every other copy in flight, including the witness prefetch on the copy stream
+// (10 ms), a copy from/to pinned memory is not.  Both helpers leave the stream synchronised.
+constexpr size_t kStageBytes = 1u << 20;
+static void *stage_buf(zk_ctx *ctx) {
+    if (!ctx->stage_h) ctx->stage_h = rt::hmalloc_pinned(kStageBytes);
+    return ctx->stage_h;
+}
+static void h2d_staged(zk_ctx *ctx, void *dst, const void *src, size_t n) {
+    char *st = static_cast<char *>(stage_buf(ctx));
+    for (size_t off = 0; off < n; off += kStageBytes) {
+        const size_t len = std::min(kStageBytes, n - off);
+        memcpy(st, static_cast<const char *>(src) + off, len);
+        rt::h2d(static_cast<char *>(dst) + off, st, len, ctx->stream);
+        rt::sync(ctx->stream);
+    }
+}
+static void d2h_staged(zk_ctx *ctx, void *dst, const void *src, size_t n) {
+    char *st = static_cast<char *>(stage_buf(ctx));
+    for (size_t off = 0; off < n; off += kStageBytes) {
+        const size_t len = std::min(kStageBytes, n - off);
+        rt::d2h(st, static_cast<const char *>(src) + off, len, ctx->stream);
+        rt::sync(ctx->stream);
+        memcpy(static_cast<char *>(dst) + off, st, len);
+    }
+}
+
 static void ensure_round_scratch(zk_ctx *ctx) {
     ctx->partials.ensure((size_t) 2 * kMaxGridX * 4 * sizeof(fr_t));
     if (!ctx->counters.p) {

@@ -32,6 +32,9 @@ struct layer_t {
     uint32_t dp_rows = 0;
     rt::dbuf val;              // prover::val[layer]
     uint64_t n_val = 0;
+    rt::dbuf val_next;         // shadow copy filled by zk_witness_layer_prefetch (the next proof's witness)
+    uint64_t n_val_next = 0;
+    bool next_ready = false;
     bool have_desc = false;
 };
 
@@ -80,6 +83,7 @@ struct hyrax_t {
 struct zk_ctx {
     int device = 0;
     zk_stream_t stream{};
+    zk_stream_t copy_stream{};   // witness prefetch (zk_witness_layer_prefetch): overlaps the running proof
     uint64_t launches = 0;
 
     // circuit
@@ -108,6 +112,7 @@ struct zk_ctx {
     uint32_t *flag_h = nullptr, *flag_d = nullptr;
     zk::rt::dbuf batch_res;                               // [rounds][16] result blocks of a batched phase
     zk::fr_t *batch_h = nullptr;
+    void *stage_h = nullptr;                              // page-locked staging buffer (h2d_staged / d2h_staged)
     uint32_t batch_cap = 0;
     uint32_t *tag_h = nullptr, *tag_d = nullptr;          // [32] tagged mailbox (publish_tagged)
     uint32_t seq = 0;

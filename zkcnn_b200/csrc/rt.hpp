@@ -3,8 +3,11 @@
 #pragma once
 #include "zk_platform.cuh"
 #include <ctime>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 
 namespace zk {
 namespace rt {
@@ -28,12 +31,13 @@ inline void hfree_pinned(void *p) { free(p); }
 inline void *hmalloc_mapped(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
 inline void *mapped_device_ptr(void *h) { return h; }
 inline void host_pin(void *, size_t) {}
+inline const void *host_device_ptr(const void *p) { return p; }
 inline void host_unpin(void *) {}
 inline void h2d(void *dst, const void *src, size_t n, zk_stream_t) { memcpy(dst, src, n); }
 inline void d2h(void *dst, const void *src, size_t n, zk_stream_t) { memcpy(dst, src, n); }
 inline void d2d(void *dst, const void *src, size_t n, zk_stream_t) { memmove(dst, src, n); }
 inline void dzero(void *dst, size_t n, zk_stream_t) { memset(dst, 0, n); }
-inline zk_stream_t stream_create() { return nullptr; }
+inline zk_stream_t stream_create(bool = true) { return nullptr; }
 inline void stream_destroy(zk_stream_t) {}
 inline void sync(zk_stream_t) {}
 inline void check_launch(const char *) {}
@@ -54,12 +58,62 @@ inline int device_count() {
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
+// Device memory comes from a small caching pool: cudaFree (and often cudaMalloc) synchronises the whole device, which
+// would stall the witness copy that runs on a second stream during a proof, and the per-call scratch buffers of the API
+// would pay hundreds of microseconds each.  Freed blocks are kept (up to kPoolLimit bytes) and handed out again to
+// requests of at least half their size.  All kernels of a context run on ONE stream, so a recycled block
+// is never touched by its previous owner after the new owner's first use.
+struct pool_t {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void *> free_blocks;   // (device, bytes) -> block
+    std::unordered_map<void *, std::pair<int, size_t>> live;      // block -> (device, bytes)
+    size_t cached = 0;
+};
+inline pool_t &pool() { static pool_t *P = new pool_t; return *P; }   // leaked on purpose: no destruction-order problems at exit
+constexpr size_t kPoolLimit = 24ull << 30;
 inline void *dmalloc(size_t bytes) {
+    bytes = ((bytes ? bytes : 1) + 511) & ~(size_t) 511;
+    int dev = 0;
+    check(cudaGetDevice(&dev), "cudaGetDevice");
+    pool_t &P = pool();
+    {
+        std::lock_guard<std::mutex> g(P.m);
+        auto it = P.free_blocks.lower_bound({dev, bytes});
+        if (it != P.free_blocks.end() && it->first.first == dev && it->first.second <= 2 * bytes) {
+            void *p = it->second;
+            P.cached -= it->first.second;
+            P.live[p] = it->first;
+            P.free_blocks.erase(it);
+            return p;
+        }
+    }
     void *p = nullptr;
-    check(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc");
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {   // give the cache back and try once more
+        cudaGetLastError();
+        std::lock_guard<std::mutex> g(P.m);
+        for (auto &kv : P.free_blocks) cudaFree(kv.second);
+        P.free_blocks.clear();
+        P.cached = 0;
+        e = cudaMalloc(&p, bytes);
+    }
+    check(e, "cudaMalloc");
+    std::lock_guard<std::mutex> g(P.m);
+    P.live[p] = {dev, bytes};
     return p;
 }
-inline void dfree(void *p) { if (p) cudaFree(p); }
+inline void dfree(void *p) {
+    if (!p) return;
+    pool_t &P = pool();
+    std::lock_guard<std::mutex> g(P.m);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) { cudaFree(p); return; }
+    const auto key = it->second;
+    P.live.erase(it);
+    if (P.cached + key.second > kPoolLimit) { cudaFree(p); return; }
+    P.free_blocks.emplace(key, p);
+    P.cached += key.second;
+}
 inline void *hmalloc_pinned(size_t bytes) {
     void *p = nullptr;
     check(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost");
@@ -78,15 +132,24 @@ inline void *mapped_device_ptr(void *h) {
     check(cudaHostGetDevicePointer(&d, h, 0), "cudaHostGetDevicePointer");
     return d;
 }
-inline void host_pin(void *p, size_t bytes) { check(cudaHostRegister(p, bytes, cudaHostRegisterDefault), "cudaHostRegister"); }
+inline void host_pin(void *p, size_t bytes) { check(cudaHostRegister(p, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable), "cudaHostRegister"); }
+// device-side address of page-locked, mapped host memory (nullptr if the range is not mapped)
+inline const void *host_device_ptr(const void *p) {
+    void *d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void *>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return d;
+}
 inline void host_unpin(void *p) { check(cudaHostUnregister(p), "cudaHostUnregister"); }
 inline void h2d(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s), "h2d"); }
 inline void d2h(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s), "d2h"); }
 inline void d2d(void *dst, const void *src, size_t n, zk_stream_t s) { if (n) check(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, s), "d2d"); }
 inline void dzero(void *dst, size_t n, zk_stream_t s) { if (n) check(cudaMemsetAsync(dst, 0, n, s), "memset"); }
-inline zk_stream_t stream_create() {
+// high = true: the proof stream (greatest priority); false: background copies (least priority)
+inline zk_stream_t stream_create(bool high = true) {
     cudaStream_t s;
-    check(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+    int lo = 0, hi = 0;
+    check(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
+    check(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? hi : lo), "cudaStreamCreate");
     return s;
 }
 inline void stream_destroy(zk_stream_t s) { if (s) cudaStreamDestroy(s); }

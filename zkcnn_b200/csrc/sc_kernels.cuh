@@ -577,6 +577,20 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(c
 }
 #endif  // !ZK_EMU
 
+// Copy from MAPPED, page-locked host memory by the SMs (zero-copy loads over PCIe) instead of the copy engine: the DMA queue
+// serves copies in submission order whatever their stream, so a 10 ms witness prefetch on the copy engine delays every small
+// host->device copy of the proof that runs meanwhile; loads issued by a few low-priority CTAs do not.  Four independent
+// 16-byte loads per thread keep ~64 KB per CTA in flight.
+__global__ void __launch_bounds__(kBlock) k_copy_from_host(uint4 *dst, const uint4 *src, uint64_t n16) {
+    const uint64_t stride = (uint64_t) gridDim.x * kBlock;
+    uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < n16; i += stride) dst[i] = src[i];
+}
+
 // fold a 2-entry table pair down to single values (the "total == 1" collapse, src/prover.cpp:400-404, and the
 // eval(previous_random) of the Finalize calls, src/prover.cpp:146-153,459-497).  out[2*i], out[2*i+1] = v, m of pair i.
 struct final_fold_args_t {

@@ -151,6 +151,13 @@ int zkh_build(zkh_session *s) {
     ZKH_END
 }
 
+int zkh_prefetch_witness(zkh_session *s) {
+    ZKH_BEGIN
+    if (!s || !s->built) throw std::logic_error("zkh_prefetch_witness: call zkh_build first");
+    s->p.prefetchWitness();
+    ZKH_END
+}
+
 int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
     ZKH_BEGIN
     if (!s || !s->built) throw std::logic_error("zkh_prove: call zkh_build first");
@@ -158,6 +165,7 @@ int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
     s->tr.clear();
     prover &p = s->p;
     p.setWitnessResident((flags & ZKH_WITNESS_RESIDENT) != 0);
+    p.setPrefetchNext((flags & ZKH_PREFETCH_NEXT) != 0);
     const double up0 = p.uploadTime(), pt0 = p.proveTime();
     const uint64_t l0 = p.gpuLaunches();
     auto t0 = std::chrono::steady_clock::now();

@@ -16,6 +16,7 @@ static inline uint64_t *w(F &x) { return reinterpret_cast<uint64_t *>(&x); }
 prover::prover() {}
 
 prover::~prover() {
+    joinPrefetch();
     unpinWitness();
     poly_p.reset();
     if (ctx_) zk_ctx_destroy(ctx_);
@@ -76,8 +77,29 @@ void prover::pinWitness() {
 }
 
 void prover::unpinWitness() {
+    joinPrefetch();   // a copy in flight reads these buffers
     for (const void *p : pinned_) zk_host_unpin(p);
     pinned_.clear();
+}
+
+void prover::joinPrefetch() {
+    if (prefetch_thread_.joinable()) prefetch_thread_.join();
+}
+
+void prover::prefetchWitness() {
+    if (!ctx_ || !circuit_uploaded_) return;   // nothing to overlap with before the first proof
+    joinPrefetch();
+    prefetch_bytes_ = 0;
+    prefetch_error_.clear();
+    for (int i = 0; i < C.size; ++i) prefetch_bytes_ += val[i].size() * sizeof(F);
+    prefetch_thread_ = std::thread([this] {
+        for (int i = 0; i < C.size; ++i)
+            if (zk_witness_layer_prefetch(ctx_, i, val[i].empty() ? nullptr : w(val[i][0]), val[i].size()) != 0) {
+                prefetch_error_ = zk_last_error();
+                return;
+            }
+    });
+    prefetch_pending_ = true;
 }
 
 void prover::init() {   // src/prover.cpp:17-21 (+ upload of what the reference reads in place)
@@ -90,8 +112,16 @@ void prover::init() {   // src/prover.cpp:17-21 (+ upload of what the reference 
         if (!ctx_) throw std::runtime_error(std::string("zkcnn_b200: cannot create a device context: ") + zk_last_error());
     }
     if (!circuit_uploaded_) { uploadCircuit(); witness_uploaded_ = false; }
-    if (!(witness_resident_ && witness_uploaded_)) uploadWitness();
+    joinPrefetch();
+    if (prefetch_pending_ && !prefetch_error_.empty()) throw std::runtime_error("zkcnn_b200: witness prefetch: " + prefetch_error_);
+    if (prefetch_pending_ && circuit_uploaded_) {
+        check(zk_witness_commit_prefetch(ctx_), "zk_witness_commit_prefetch");
+        last_upload_bytes_ = prefetch_bytes_;
+        witness_uploaded_ = true;
+    } else if (!(witness_resident_ && witness_uploaded_)) uploadWitness();
     else last_upload_bytes_ = 0;
+    prefetch_pending_ = false;
+    if (prefetch_next_) prefetchWitness();
     check(zk_prover_init(ctx_), "zk_prover_init");
     upload_timer.stop();
 }

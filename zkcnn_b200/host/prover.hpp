@@ -25,6 +25,8 @@
 #include "../../include/zkcnn_b200.h"
 #include "transcript.hpp"
 #include <memory>
+#include <string>
+#include <thread>
 
 using std::unique_ptr;
 
@@ -86,6 +88,9 @@ public:
     double uploadTime() const { return upload_timer.elapse_sec(); }
     // true: init() keeps the witness that is already on the device (same val as the previous proof) instead of copying it again
     void setWitnessResident(bool on) { witness_resident_ = on; }
+    // start copying val[] for the NEXT proof on a second stream (it overlaps the proof that is running); the next init() adopts it
+    void prefetchWitness();
+    void setPrefetchNext(bool on) { prefetch_next_ = on; }   // init() starts the next proof's copy once it has its own witness
     // page-lock val[] so that the witness upload is a direct DMA from host memory (call after val is final; undone by the destructor)
     void pinWitness();
     void unpinWitness();
@@ -102,7 +107,11 @@ private:
     zk_ctx *ctx_ = nullptr;
     int device_ = -1;
     bool circuit_uploaded_ = false;
-    bool witness_resident_ = false, witness_uploaded_ = false;
+    bool witness_resident_ = false, witness_uploaded_ = false, prefetch_pending_ = false, prefetch_next_ = false;
+    uint64_t prefetch_bytes_ = 0;
+    std::thread prefetch_thread_;      // paces the copy (zk_witness_layer_prefetch blocks while it does)
+    std::string prefetch_error_;
+    void joinPrefetch();
     uint64_t last_upload_bytes_ = 0;
     std::vector<const void *> pinned_;
     u64 proof_size = 0;

@@ -3,6 +3,7 @@
 // small helpers (challenge drawing, round checking, wiring-predicate evaluation on host threads) instead of the
 // reference's timer-interleaved loops.  Field arithmetic is exact, so the eq/phi tables here may be built in any order.
 #include "verifier.hpp"
+#include <chrono>
 #include "challenge_stream.hpp"
 #include <array>
 #include <functional>
@@ -186,6 +187,7 @@ static void drawChallenges(vector<F> &v, size_t n) {
 }
 
 bool verifier::verify() {   // src/verifier.cpp:118-130
+    const auto t0 = std::chrono::steady_clock::now();
     const u8 logn = C.circuit[0].bit_length;
     const u64 n_gens = 1ULL << (logn - (logn >> 1));
     vector<F> k;
@@ -198,8 +200,20 @@ bool verifier::verify() {   // src/verifier.cpp:118-130
         generators.assign(n_gens, G());
         require(zk_g1_fixed_base_mul(p->context(), w(base), w(k[0]), n_gens, w(generators[0])), "zk_g1_fixed_base_mul");
     } else generators.assign(n_gens, G());   // reference default: base point cleared by initPairing -> all infinity
+    static const bool trace = getenv("ZKH_TRACE") != nullptr;   // stderr: wall time of the stages of one proof
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t1 = now();
     poly_v.reset(new hyrax_bls12_381::polyVerifier(p->commitInput(generators), generators, p->context(), checkPredicates));
-    return verifyInnerLayers() && verifyFirstLayer() && verifyInput();
+    const auto t2 = now();
+    const bool ok1 = verifyInnerLayers();
+    const auto t3 = now();
+    const bool ok2 = ok1 && verifyFirstLayer();
+    const auto t4 = now();
+    const bool ok3 = ok2 && verifyInput();
+    const auto t5 = now();
+    if (trace) fprintf(stderr, "ZKH_TRACE generators %.2f ms  commit %.2f ms  inner layers %.2f ms  input layer %.2f ms  opening %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5));
+    return ok3;
 }
 
 F verifier::getFinalValue(const F &claim_u0, const F &claim_u1, const F &claim_v0, const F &claim_v1) {   // src/verifier.cpp:25-34
