@@ -1,5 +1,3 @@
-mkdir -p gpurun_out
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/s4_bench4.json 2> gpurun_out/s4_bench4.err
-cut -c1-300 gpurun_out/s4_bench4.json; tail -3 gpurun_out/s4_bench4.err
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-prefetch --round-by-round > gpurun_out/s4_bench4_rbr.json 2> gpurun_out/s4_bench4_rbr.err
-cut -c1-300 gpurun_out/s4_bench4_rbr.json
+timeout 600 python -m pytest tests -m gpu -x -q -k "msm or hyrax or lenet_syn_p1_seed3_realgens" 2>&1 | tail -2
+python tools/microbench.py msm 12 12 2 3
+ZKH_TRACE=1 python tools/_trace_probe.py resident 2>&1 | grep -E "ZKH_TRACE|resident" | tail -3

@@ -8,7 +8,6 @@ cap() {  # name regex skip count cmd...
     name=$1; rx=$2; skip=$3; cnt=$4; shift 4
     timeout 600 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -f -o /tmp/prof_$name "$@" > /tmp/ncu_$name.log 2>&1
     ncu -i /tmp/prof_$name.ncu-rep --page raw --csv > $OUT/ncu_${name}_${TAG}_raw.csv 2>/dev/null
-    ncu -i /tmp/prof_$name.ncu-rep --page details --csv > $OUT/ncu_${name}_${TAG}_details.csv 2>/dev/null
     ncu -i /tmp/prof_$name.ncu-rep --page source --csv > /tmp/src_$name.csv 2>/dev/null
     # per-instruction page is large: keep the 150 hottest SASS lines by samples
     python3 - "$name" "$TAG" <<'PY'
@@ -26,10 +25,9 @@ try:
 except Exception as e:
     print("source page:", e)
 PY
-    sz=$(stat -c %s /tmp/prof_$name.ncu-rep 2>/dev/null || echo 0)
-    if [ "$sz" -lt 12000000 ] && [ "$sz" -gt 0 ]; then cp /tmp/prof_$name.ncu-rep $OUT/prof_${name}_${TAG}.ncu-rep; fi
-    echo "$name: rep $sz bytes"; tail -2 /tmp/ncu_$name.log
+    echo "$name:"; tail -1 /tmp/ncu_$name.log
 }
-cap fold k_round_quad 1 1 python tools/microbench.py fold 24 2
+cap fold_tma k_round_quad_tma 1 1 python tools/microbench.py fold 24 2
+cap fold_thin k_round_quad_thin 1 1 python tools/microbench.py fold 12 2
 cap msm_small k_msm_small 1 1 python tools/microbench.py msm 12 12 2 1
 cap msm_window k_msm_window 1 1 python tools/microbench.py msm 1 12 0 1

@@ -85,7 +85,7 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     } else {
         ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, 0, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
     }
-    const uint32_t chunk = n_rows <= 8 ? std::min<uint32_t>(2048, kMsmChunk) : kMsmChunk;   // few rows: more CTAs per row
+    const uint32_t chunk = n_rows <= 8 ? std::min<uint32_t>(ctx->msm_few_rows_chunk, kMsmChunk) : kMsmChunk;   // few rows: more CTAs per row
     const uint32_t n_chunks = (uint32_t) ((n + chunk - 1) / chunk);
     const size_t per_row = (size_t) n_chunks * kMsmWindows;
     H.msm_out.ensure((size_t) n_rows * per_row * sizeof(g1_jac_t));

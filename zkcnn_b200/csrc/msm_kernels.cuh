@@ -69,9 +69,12 @@ struct msm_small_args_t {
     g1_jac_t *partial;         // [n_rows][n_seg]
     uint32_t *rowinfo;         // widest magnitude (bytes) among the scalars that do NOT fit one byte, per row (atomicMax)
 };
-constexpr int kSmallWarps = 8;
+#ifndef ZK_SMALL_WARPS
+#define ZK_SMALL_WARPS 4
+#endif
+constexpr int kSmallWarps = ZK_SMALL_WARPS;   // 4 warps per CTA: three CTAs (12 warps) fit the register file of an SM, one 8-warp CTA would be alone
 
-__global__ void __launch_bounds__(kSmallWarps * 32) k_msm_small(msm_small_args_t A) {
+__global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_msm_small(msm_small_args_t A) {
     __shared__ g1_jac_t sh[kSmallWarps * 32];
     __shared__ uint32_t queue[kSmallWarps][64];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
