@@ -44,6 +44,7 @@ void zk_ctx_destroy(zk_ctx *ctx) {
     for (auto &r : ctx->prof_pending) { rt::event_destroy(r.a); rt::event_destroy(r.b); }
     for (auto e : ctx->prof_pool) rt::event_destroy(e);
     if (ctx->copy_stream) { try { rt::sync(ctx->copy_stream); } catch (...) {} rt::stream_destroy(ctx->copy_stream); }
+    if (ctx->aux_stream) { try { rt::sync(ctx->aux_stream); } catch (...) {} rt::stream_destroy(ctx->aux_stream); }
     rt::stream_destroy(ctx->stream);
     delete ctx;
 }

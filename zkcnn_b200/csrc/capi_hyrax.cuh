@@ -37,13 +37,30 @@ static void msm_prepare_table(zk_ctx *ctx, hyrax_t &H, const uint64_t *gens, uin
     ZK_KLAUNCH(ctx, k_g1_to_affine, dim3(grid_for(n_gens)), dim3(kBlock), 0, tmp.as<g1_jac_t>(), H.gens_aff.as<g1_aff_t>(), n_gens);
     H.table.ensure((size_t) kMsmWindows * n_gens * sizeof(g1_aff_t));
     H.table_scratch.ensure((size_t) 2 * kMsmWindows * n_gens * sizeof(fp_t));
+    // The window table is a chain of 248 doublings per generator: latency bound, a few hundred resident threads.  It runs on a
+    // side stream next to the small-multiples build and the commitment's k_msm_small (which do not need it); the main stream
+    // waits for it right before the first k_msm_window (msm_wait_table).
+#ifndef ZK_EMU
+    if (!ctx->aux_stream) ctx->aux_stream = rt::stream_create(true);
+    rt::stream_wait_stream(ctx->aux_stream, ctx->stream);
+    ZK_KLAUNCH_S(ctx, ctx->aux_stream, ZK_PROF_MSM, (uint64_t) kMsmWindows * n_gens * 96, k_msm_table_build, dim3((n_gens + kTableBuildBlock - 1) / kTableBuildBlock),
+                 dim3(kTableBuildBlock), 0, H.gens_aff.as<g1_aff_t>(), H.table.as<g1_aff_t>(), H.table_scratch.as<fp_t>(),
+                 H.table_scratch.as<fp_t>() + (size_t) kMsmWindows * n_gens, n_gens);
+    H.table_pending = true;
+#else
     ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, (uint64_t) kMsmWindows * n_gens * 96, k_msm_table_build, dim3((n_gens + kTableBuildBlock - 1) / kTableBuildBlock),
                  dim3(kTableBuildBlock), 0, H.gens_aff.as<g1_aff_t>(), H.table.as<g1_aff_t>(), H.table_scratch.as<fp_t>(),
                  H.table_scratch.as<fp_t>() + (size_t) kMsmWindows * n_gens, n_gens);
-    rt::sync(ctx->stream);
+#endif
     H.gens_hash = h;
     H.table_ready = true;
     H.mult_ready = false;
+}
+
+static void msm_wait_table(zk_ctx *ctx, hyrax_t &H) {
+    if (!H.table_pending) return;
+    rt::stream_wait_stream(ctx->stream, ctx->aux_stream);
+    H.table_pending = false;
 }
 
 // small-multiples table M[j][d-1] = d * G_j for the current generator set (msm_kernels.cuh); built on first use
@@ -99,6 +116,7 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     A.chunk = chunk;
     A.wide_only = small_path ? 1u : 0u;
     A.partial = H.msm_out.as<g1_jac_t>();
+    msm_wait_table(ctx, H);
     // grid.x is limited to 2^31-1, grid.y to 65535: rows * chunks in x, windows in y
     ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
     ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kSmallWarps - 1) / kSmallWarps), dim3(kSmallWarps * 32), 0,

@@ -61,19 +61,22 @@ static inline zk::rt::event_t prof_event(zk_ctx *ctx) {
     return zk::rt::event_create();
 }
 // launch of class `cls` (ZK_PROF_*) moving `bytes` algorithmic bytes
-#define ZK_KLAUNCH_C(ctx, cls, bytes, kernel, grid, block, smem, ...)                     \
+#define ZK_KLAUNCH_C(ctx, cls, bytes, kernel, grid, block, smem, ...) \
+    ZK_KLAUNCH_S(ctx, (ctx)->stream, cls, bytes, kernel, grid, block, smem, __VA_ARGS__)
+// the same on an explicit stream (side work that overlaps the main stream, e.g. the window-table build)
+#define ZK_KLAUNCH_S(ctx, strm, cls, bytes, kernel, grid, block, smem, ...)               \
     do {                                                                                  \
         zk_ctx::prof_rec zk_pr_{(cls), nullptr, nullptr};                                 \
         if ((ctx)->prof_on) {                                                             \
             zk_pr_.a = zk::prof_event(ctx);                                               \
             zk_pr_.b = zk::prof_event(ctx);                                               \
-            zk::rt::event_record(zk_pr_.a, (ctx)->stream);                                \
+            zk::rt::event_record(zk_pr_.a, (strm));                                       \
         }                                                                                 \
-        ZK_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);                 \
+        ZK_LAUNCH(kernel, grid, block, smem, (strm), __VA_ARGS__);                        \
         ++(ctx)->launches;                                                                \
         zk::rt::check_launch(#kernel);                                                    \
         if ((ctx)->prof_on) {                                                             \
-            zk::rt::event_record(zk_pr_.b, (ctx)->stream);                                \
+            zk::rt::event_record(zk_pr_.b, (strm));                                       \
             (ctx)->prof_pending.push_back(zk_pr_);                                        \
             ++(ctx)->prof_launches[(cls)];                                                \
             (ctx)->prof_bytes[(cls)] += (uint64_t) (bytes);                               \

@@ -65,6 +65,7 @@ struct hyrax_t {
     rt::dbuf gens_jac;         // upload staging
     rt::dbuf table;            // fixed-base window table: [kWindows][n_gens] affine, entry = 2^(8w) * gens[j]
     bool table_ready = false;
+    bool table_pending = false;   // the build is queued on the side stream; the main stream has not waited for it yet
     rt::dbuf table_scratch;    // z's and prefix products of the table build
     rt::dbuf mult;             // small-multiples table [n_gens][255] affine, entry = d * gens[j]  (msm_kernels.cuh)
     bool mult_ready = false;
@@ -83,6 +84,7 @@ struct hyrax_t {
 struct zk_ctx {
     int device = 0;
     zk_stream_t stream{};
+    zk_stream_t aux_stream{};    // side work of the main stream (window-table build next to the commitment)
     zk_stream_t copy_stream{};   // witness prefetch (zk_witness_layer_prefetch): overlaps the running proof
     uint64_t launches = 0;
 

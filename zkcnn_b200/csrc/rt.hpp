@@ -40,6 +40,7 @@ inline void dzero(void *dst, size_t n, zk_stream_t) { memset(dst, 0, n); }
 inline zk_stream_t stream_create(bool = true) { return nullptr; }
 inline void stream_destroy(zk_stream_t) {}
 inline void sync(zk_stream_t) {}
+inline void stream_wait_stream(zk_stream_t, zk_stream_t) {}
 inline void check_launch(const char *) {}
 typedef double *event_t;   // wall-clock stamp taken at "record" time (launches are synchronous in the emulator)
 inline double emu_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
@@ -154,6 +155,14 @@ inline zk_stream_t stream_create(bool high = true) {
 }
 inline void stream_destroy(zk_stream_t s) { if (s) cudaStreamDestroy(s); }
 inline void sync(zk_stream_t s) { check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+// make stream `s` wait (on the device) for everything queued on `other` so far
+inline void stream_wait_stream(zk_stream_t s, zk_stream_t other) {
+    cudaEvent_t e;
+    check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    check(cudaEventRecord(e, other), "cudaEventRecord");
+    check(cudaStreamWaitEvent(s, e, 0), "cudaStreamWaitEvent");
+    cudaEventDestroy(e);
+}
 inline void check_launch(const char *what) { check(cudaGetLastError(), what); }
 typedef cudaEvent_t event_t;
 inline event_t event_create() { cudaEvent_t e; check(cudaEventCreate(&e), "cudaEventCreate"); return e; }

@@ -266,9 +266,12 @@ vector<quadratic_poly> prover::sumcheckUpdateAll(int which, const vector<F> &r, 
 }
 
 hyrax_bls12_381::polyProver &prover::commitInput(const vector<G> &gens) {   // src/prover.cpp:503-511
-    if (C.circuit[0].size != (1ULL << C.circuit[0].bit_length)) {
+    // pad val[0] with zeros to 2^bit_length (src/prover.cpp:504-508); once: the padding stays zero between proofs, and clearing
+    // 3.9 M elements of page-locked memory again would cost ~10 ms per vgg11 proof
+    if (val[0].size() != (1ULL << C.circuit[0].bit_length)) {
+        const size_t old = val[0].size();
         val[0].resize(1ULL << C.circuit[0].bit_length);
-        for (size_t i = C.circuit[0].size; i < val[0].size(); ++i) val[0][i].clear();
+        for (size_t i = old; i < val[0].size(); ++i) val[0][i].clear();
     }
 #ifdef ZKCNN_DROPIN_CPU_HYRAX
     poly_p = std::make_unique<hyrax_bls12_381::polyProver>(val[0], gens);
