@@ -412,6 +412,22 @@ __global__ void __launch_bounds__(kBlock) k_selftest(uint64_t seed, uint32_t n, 
         const uint32_t zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t top[8] = {acc.w[16], 0, 0, 0, 0, 0, 0, 0};
         bad += montgomery_of_wide<fr_cfg>(acc.w, acc.w + 8, top) != (x + a * a + b * b);
+        // the short reduction (<= 16 products of reduced operands) and the single-integer Montgomery reduction under it
+        {
+            fr_lazy_t l16;
+            l16.clear();
+            fr_t want = fr_t::zero();
+            for (int k = 0; k < 16; ++k) {
+                const fr_t u = (k & 1) ? a : b, w = (k & 2) ? x : ((k & 4) ? a : b);
+                l16.mac(u, w);
+                want = want + u * w;
+            }
+            bad += fr_lazy_reduce_upto16(l16) != want;
+            fr_lazy_t one_prod;
+            one_prod.clear();
+            one_prod.mac(a, b);
+            bad += fr_lazy_reduce_upto16(one_prod) != x;
+        }
         // ... and of a sum of field elements seen as a plain integer (chunk 1 of the same formula)
         uint32_t s9[9];
         uint64_t cy = 0;

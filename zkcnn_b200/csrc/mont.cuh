@@ -471,6 +471,43 @@ template <class C> struct alignas(16) mont_t {
         for (int i = 0; i < N; ++i) r[i] = borrow ? E[i] : d[i];
     }
 
+    // ---- Montgomery reduction of ONE N-limb integer: r = t / R mod p (t any value below R), fully reduced ----------------
+    // The rows of mul_wide with a = 1: the a * b_i term is the single limb t[i] entering at limb 0.
+    static __device__ __forceinline__ void redc_wide(uint32_t *r, const uint32_t *t) {
+        const uint32_t *p = C::mod_rt();
+        uint32_t pm[N + 1];
+#pragma unroll
+        for (int i = 0; i <= N; ++i) pm[i] = p[i];
+        uint32_t E[N], O[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { E[i] = 0; O[i] = 0; }
+        E[0] = t[0];
+        {
+            uint32_t m;
+            asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(m) : "r"(E[0]), "r"(pm[N]));
+            wide_reduce_cmad(E, O, pm, m);
+        }
+#pragma unroll
+        for (int i = 1; i < N; ++i) {
+            uint32_t *X = (i & 1) ? O : E, *Y = (i & 1) ? E : O;   // X: aligned at limb 0 after the shift, Y: shifts down by two limbs
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(X[0]) : "r"(Y[1]));
+#pragma unroll
+            for (int j = 0; j < N - 2; ++j) asm volatile("addc.cc.u32 %0, %1, 0;" : "=r"(Y[j]) : "r"(Y[j + 2]));
+            asm volatile("addc.u32 %0, 0, 0;" : "=r"(Y[N - 2]));
+            Y[N - 1] = 0;
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(X[0]) : "r"(t[i]));
+#pragma unroll
+            for (int j = 1; j < N; ++j) asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(X[j]));
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(Y[N - 1]));
+            uint32_t m;
+            asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(m) : "r"(X[0]), "r"(pm[N]));
+            wide_reduce_cmad(X, Y, pm, m);
+        }
+        // after N rows the roles are: N even -> the value is (E >> 32) + O with E the accumulator whose limb 0 is zero
+        if (N & 1) wide_finish(r, O, E, pm);
+        else wide_finish(r, E, O, pm);
+    }
+
     // ---- unreduced product t[0 .. 2N-1] = a * b as plain integers (the multiplication half of mul_wide) ----------------
     // Same even/odd column scheme: `t` collects the limb-aligned wide products, `odd` the ones shifted by one limb.
     //   row: odd[0..N-1] += x[1,3,..] * y with the top pair written fresh; even[0..N-1] += x[0,2,..] * y; the carry out of
@@ -695,6 +732,38 @@ template <class C> struct lazy_acc_t {
 #endif
     }
 };
+template <class C> ZK_HD inline mont_t<C> montgomery_of_wide(const uint32_t *c0, const uint32_t *c1, const uint32_t *c2);
+// Reduction of a lazy accumulator that holds at most 16 products of REDUCED operands (Fr): T < 16 p^2 < 7.25 p R.
+//   U = T >> 256 (9 limbs, < 7.25 p) is brought below p by the ladder 4p, 2p, p;  T' = U' R + (T mod R) < p R, so
+//   T' / R = redc(T mod R) + U'  is below 2p: one field addition finishes.  Cost: 64 wide multiply-adds instead of the
+//   3 x 128 of montgomery_of_wide; same field element.
+ZK_HD __forceinline__ fr_t fr_lazy_reduce_upto16(const lazy_acc_t<fr_cfg> &a) {
+#if ZK_FIELD_PTX
+    uint32_t u[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) u[i] = a.w[8 + i];
+    const uint32_t *mult = ZK_C(fr_MULT9);
+#pragma unroll
+    for (int k = 2; k >= 0; --k) {
+        uint32_t d[9];
+        d[0] = ptx::sub_cc(u[0], mult[9 * k]);
+#pragma unroll
+        for (int i = 1; i < 9; ++i) d[i] = ptx::subc_cc(u[i], mult[9 * k + i]);
+        const uint32_t borrow = ptx::subc(0, 0);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) u[i] = borrow ? u[i] : d[i];
+    }
+    fr_t lo, hi;
+    fr_t::redc_wide(lo.v, a.w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hi.v[i] = u[i];
+    return lo + hi;
+#else
+    uint32_t top[8] = {a.w[16], 0, 0, 0, 0, 0, 0, 0};
+    return montgomery_of_wide<fr_cfg>(a.w, a.w + 8, top);
+#endif
+}
+
 // T / R mod p for a plain integer T = c0 + c1 R + c2 R^2 given as three N-limb chunks:
 //   T / R = c0 / R + c1 + c2 R  =  mul(c0, 1) + mul(c1, R mod p) + mul(c2, R^2 mod p)   with mul(x, y) = x y / R.
 // The multiplier wants operands below p, so each chunk first loses its multiples of p (R / p < 3 for Fr).

@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(kBlock) k_phi_table(fr_t *phi, const fr_t *rx,
 // several items are finished by further levels that add up the per-item partial sums.  No atomics, no ordering
 // dependence (Fr addition is exact), one thread per item.
 // --------------------------------------------------------------------------------------------------------------------
-constexpr int kItemLen = 16;
+constexpr int kItemLen = 16;   // <= 16: the bound fr_lazy_reduce_upto16 relies on
 
 struct gate_rec_t {   // 12 bytes
     uint32_t g;       // output gate -> index into beta_g
@@ -865,21 +865,26 @@ __device__ __forceinline__ void store_item(const gate_args_t &A, uint32_t dest, 
     } else st_fr(A.partial + dest, acc);
 }
 
+// An item's <= 16 products are accumulated unreduced (lazy_acc_t) and reduced once (fr_lazy_reduce_upto16): these kernels
+// are bound by the field multiplications (116 M binary gates x 2 phases for vgg11), not by the gathers.
 __global__ void __launch_bounds__(kBlock) k_gate_items_p1(gate_args_t A) {
     for (uint32_t it = blockIdx.x * kBlock + threadIdx.x; it < A.n_items; it += gridDim.x * kBlock) {
         const item_t I = A.items[it];
         const uint32_t cnt = I.count_flags & 0xffffu;
-        fr_t acc = fr_t::zero();
+        fr_lazy_t acc;
+        acc.clear();
         for (uint32_t k = 0; k < cnt; ++k) {
             const gate_rec_t R = A.recs[I.begin + k];
-            fr_t t = ld_fr(A.beta_g + R.g);
+            const fr_t bg = ld_fr(A.beta_g + R.g);
             const uint32_t kind = (R.meta >> 16) & 3u, sc = R.meta & 0x1ffu;
-            if (kind == 1) t = t * ld_fr(A.val0 + R.x);
-            else if (kind == 2) t = t * ld_fr(A.val_prev + R.x);
-            if (sc) t = t * ld_fr(A.two_mul + sc);
-            acc = acc + t;
+            if (kind == 0) acc.mac(bg, sc ? ld_fr(A.two_mul + sc) : fr_t::one());
+            else {
+                const fr_t v = ld_fr((kind == 1 ? A.val0 : A.val_prev) + R.x);
+                if (sc) acc.mac(bg * v, ld_fr(A.two_mul + sc));
+                else acc.mac(bg, v);
+            }
         }
-        store_item(A, I.dest, acc);
+        store_item(A, I.dest, fr_lazy_reduce_upto16(acc));
     }
 }
 
@@ -887,16 +892,16 @@ __global__ void __launch_bounds__(kBlock) k_gate_items_p2(gate_args_t A) {
     for (uint32_t it = blockIdx.x * kBlock + threadIdx.x; it < A.n_items; it += gridDim.x * kBlock) {
         const item_t I = A.items[it];
         const uint32_t cnt = I.count_flags & 0xffffu;
-        fr_t acc = fr_t::zero();
+        fr_lazy_t acc;
+        acc.clear();
         for (uint32_t k = 0; k < cnt; ++k) {
             const gate_rec_t R = A.recs[I.begin + k];
-            fr_t t = ld_fr(A.beta_g + R.g) * ld_fr(A.beta_u + R.x);
+            const fr_t bg = ld_fr(A.beta_g + R.g), bu = ld_fr(A.beta_u + R.x);
             const uint32_t sc = R.meta & 0x1ffu;
-            if (sc) t = t * ld_fr(A.two_mul + sc);
-            acc = acc + t;
+            if (sc) acc.mac(bg * bu, ld_fr(A.two_mul + sc));
+            else acc.mac(bg, bu);
         }
-        acc = acc * A.vu[(I.count_flags >> 16) & 1u];
-        store_item(A, I.dest, acc);
+        store_item(A, I.dest, fr_lazy_reduce_upto16(acc) * A.vu[(I.count_flags >> 16) & 1u]);
     }
 }
 
