@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Prove vgg11 a few times and print the wall time per proof.  usage: probe_proofs.py resident|prefetch [n]
+ZKH_TRACE=1 adds the wall time of the stages of each proof, ZK_TRACE=1 the time per C-ABI entry point (at exit)."""
 import sys, os, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

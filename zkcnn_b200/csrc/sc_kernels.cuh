@@ -564,7 +564,9 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(c
         }
         acc[0].mac(fr_t::sub_lazy(m1, m0), fr_t::sub_lazy(v1, v0));
         acc[1].mac(m0, v0);
+#ifndef ZK_EXPERIMENT_SKIP_THIRD_PRODUCT   // timing experiment only (wrong results): what deriving b from the previous round would save
         acc[2].mac(m1, v1);
+#endif
         stage ^= 1u;
     }
     uint32_t limb[kRoundLimbs];
