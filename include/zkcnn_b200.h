@@ -60,7 +60,9 @@ int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_
 
 /* Kernel-selection thresholds of the sumcheck rounds (tests and experiments; defaults in parentheses):
  *   "thin_max_pairs"   (16384)  rounds with at most this many output pairs per table use k_round_quad_thin
- *   "tma_min_entries"  (131072) fold rounds on tables of at least this many entries use the TMA-staged k_round_quad_tma */
+ *   "tma_min_entries"  (131072) fold rounds on tables of at least this many entries use the TMA-staged k_round_quad_tma
+ *   "derive_b"         (1)      streaming rounds take b from the previous round's polynomial (0: always three products)
+ *   "msm_few_rows_chunk" (2048) entries per CTA of the bucket kernel for MSMs of at most 8 rows */
 int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value);
 
 /* page-lock / unlock a caller-owned host buffer so that uploads from it are direct DMA (cudaHostRegister) */

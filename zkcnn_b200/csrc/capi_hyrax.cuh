@@ -485,6 +485,8 @@ int zk_bench_fold(zk_ctx *ctx, uint32_t bits, uint32_t iters, int fold, float *m
     R.n_in = (uint32_t) n; R.live = (uint32_t) n; R.fold = fold ? 1 : 0;
     const uint64_t out_pairs = fold ? n >> 2 : n >> 1;
     const bool thin = out_pairs <= ctx->thin_max_pairs;   // same choices as round_quadratic()
+    A.state = ctx->round_state.as<fr_t>();
+    A.derive_b[1] = fold && ctx->derive_b_enabled ? 1u : 0u;   // as in every fold round after the first of a phase
     R.n_blocks = thin ? (uint32_t) ((out_pairs + kRoundBlock / 4 - 1) / (kRoundBlock / 4)) : round_grid_for(out_pairs);
     const uint32_t limit_pairs[2] = {0, (uint32_t) out_pairs};
     (void) limit_pairs;

@@ -342,6 +342,7 @@ static void run_schedule(zk_ctx *ctx, const schedule_t &S, int phase, gate_args_
 
 static void pair_reset(pair_t &P, int8_t bit_length, uint32_t size) {
     P.exists = bit_length >= 0;
+    P.poly_round = 0;
     P.n_eval = P.exists ? 1u << bit_length : 0;
     P.live = size;
     P.collapsed = false;
@@ -398,8 +399,10 @@ static void ensure_round_scratch(zk_ctx *ctx) {
         rt::dzero(ctx->counters.p, 8 * sizeof(uint32_t), ctx->stream);
     }
     if (!ctx->round_acc.p) {   // grid-wide limb sums of k_round_quad: zero between launches (the kernel clears them itself)
-        ctx->round_acc.ensure(64 * sizeof(unsigned long long));
-        rt::dzero(ctx->round_acc.p, 64 * sizeof(unsigned long long), ctx->stream);
+        ctx->round_acc.ensure(128 * sizeof(unsigned long long));
+        rt::dzero(ctx->round_acc.p, 128 * sizeof(unsigned long long), ctx->stream);
+        ctx->round_state.ensure(8 * sizeof(fr_t));
+        rt::dzero(ctx->round_state.p, 8 * sizeof(fr_t), ctx->stream);
     }
     ctx->round_out.ensure(16 * sizeof(fr_t));
     if (!ctx->h_out) ctx->h_out = static_cast<fr_t *>(rt::hmalloc_pinned(16 * sizeof(fr_t)));
@@ -592,6 +595,17 @@ static round_rec_t round_quadratic_launch(zk_ctx *ctx, const fr_t &prev, unsigne
             gx += A.pair[b].n_blocks;
             max_n_in = std::max<uint64_t>(max_n_in, A.pair[b].n_in);
         }
+    if (!thin) {
+        // streaming kernels keep each pair's round polynomial on the device; a pair whose previous round went through one of
+        // them gets its b coefficient from that polynomial instead of a third product (see round_args_t::derive_b)
+        A.state = ctx->round_state.as<fr_t>();
+        for (int b = 0; b < 2; ++b)
+            if (quad[b]) {
+                pair_t &P = ctx->pair[b];
+                A.derive_b[b] = (!first && ctx->derive_b_enabled && P.poly_round + 1 == ctx->round) ? 1u : 0u;
+                P.poly_round = ctx->round;
+            }
+    }
     // rounds that stream less than 32 MiB are bound by launch + reduction latency, not by HBM: they are accounted separately
     const int cls = fold_bytes >= (32u << 20) ? ZK_PROF_FOLD : ZK_PROF_FOLD_SMALL;
     if (any_quad && thin) ZK_KLAUNCH_C(ctx, cls, fold_bytes, k_round_quad_thin, dim3(gx), dim3(kRoundBlock), 0, A);

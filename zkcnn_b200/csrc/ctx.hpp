@@ -49,6 +49,7 @@ struct pair_t {
     table_t v, m;
     uint32_t n_eval = 0;       // evaluations currently held (0: pair absent or already collapsed)
     uint32_t live = 0;         // entries >= live are zero
+    uint32_t poly_round = 0;   // round whose polynomial of this pair is in zk_ctx::round_state (0: none); see round_args_t::derive_b
     bool exists = false;       // bit_length != -1
     bool collapsed = false;
     fr_t cv, cm;               // values after collapse (V_mult[b][0].b, mult_array[b][0].b)
@@ -106,7 +107,7 @@ struct zk_ctx {
     uint32_t beta_g_entries = 0;
 
     // scratch
-    zk::rt::dbuf half[4], d_r, partials, counters, round_acc, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
+    zk::rt::dbuf half[4], d_r, partials, counters, round_acc, round_state, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
     zk::fr_t *h_out = nullptr;  // pinned mirror of round_out
     // result mailbox of the per-round kernels: mapped pinned host memory the last CTA writes directly, followed by a
     // sequence number; the host spins on the sequence number instead of copying + synchronising the stream
@@ -120,6 +121,7 @@ struct zk_ctx {
     uint32_t seq = 0;
     uint32_t thin_max_pairs = 1u << 14;      // see zk_set_tunable
     uint64_t tma_min_entries = 1ull << 17;
+    uint32_t derive_b_enabled = 1;           // streaming rounds: b from the previous round's polynomial (0: always three products)
     uint32_t msm_few_rows_chunk = 2048;      // entries per CTA of k_msm_window when an MSM has at most 8 rows
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 

@@ -130,6 +130,49 @@ __device__ __forceinline__ bool grid_limb_sum_finish(unsigned long long *acc, ui
     __syncthreads();
     return true;
 }
+// The same for CTAs that each own one SLICE of a wider set of sums: this CTA adds its K limbs at `offset`, the last CTA gets
+// all K_TOTAL totals in sh_tot.  (k_round_quad / k_round_quad_tma: one slice of 51 limbs per table pair.)
+template <int K, int K_TOTAL, int BLOCK>
+__device__ __forceinline__ bool grid_limb_sum_slice(const uint32_t (&limb)[K], uint32_t offset, unsigned long long *acc, uint32_t *counter, uint32_t n_ctas,
+                                                    unsigned long long *sh_warp /* [BLOCK/32][K] */, unsigned long long *sh_tot /* [K_TOTAL] */,
+                                                    uint32_t *sh_ticket) {
+    static_assert(K <= BLOCK && K_TOTAL <= BLOCK, "one thread per limb in the CTA stage");
+    constexpr int NW = BLOCK / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t lo = __reduce_add_sync(0xffffffffu, limb[k] & 0xffffu);
+        const uint32_t hi = __reduce_add_sync(0xffffffffu, limb[k] >> 16);
+        if (lane == (k & 31)) sh_warp[warp * K + k] = (unsigned long long) lo + ((unsigned long long) hi << 16);
+    }
+    if (n_ctas == 1 && threadIdx.x < K_TOTAL) sh_tot[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < K) {
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += sh_warp[w * K + threadIdx.x];
+        if (n_ctas == 1) sh_tot[offset + threadIdx.x] = t;
+        else if (t) atomicAdd(acc + offset + threadIdx.x, t);
+        __threadfence();
+    }
+    __syncthreads();
+    if (n_ctas == 1) return true;
+    if (threadIdx.x == 0) *sh_ticket = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (*sh_ticket != n_ctas - 1) return false;
+    __threadfence();
+    if (threadIdx.x < K_TOTAL) {
+#if ZK_ON_DEVICE
+        sh_tot[threadIdx.x] = __ldcg(acc + threadIdx.x);
+#else
+        sh_tot[threadIdx.x] = acc[threadIdx.x];
+#endif
+        acc[threadIdx.x] = 0;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+    __syncthreads();
+    return true;
+}
 template <int K, int BLOCK>
 __device__ __forceinline__ bool grid_limb_sum(const uint32_t (&limb)[K], unsigned long long *acc, uint32_t *counter, uint32_t n_ctas,
                                               unsigned long long *sh_warp /* [BLOCK/32][K] */, unsigned long long *sh_tot /* [K] */,
@@ -183,6 +226,12 @@ struct round_args_t {
     uint32_t *flag;           // != nullptr: after `out` is written, publish `seq` here (mapped host memory)
     uint32_t seq;
     uint4 *tagged;            // != nullptr: publish (a, b, c) as 8 self-validating 16-byte words instead (see publish_tagged)
+    // streaming kernels only (k_round_quad, k_round_quad_tma): the round polynomial of each pair is kept on the device, and
+    // derive_b[p] != 0 says that state[p] holds pair p's polynomial of the PREVIOUS round.  Then the third product is skipped:
+    // the folded tables satisfy  sum_i m_i v_i = P_prev(r)  (a table identity: every entry is the old pair evaluated at r), i.e.
+    // P(0) + P(1) = P_prev(r), so  b = P_prev(r) - 2c - a.
+    fr_t *state;              // [2][4]: (a, b, c, -) per pair
+    uint32_t derive_b[2];
 };
 // Fence-free result mailbox: the 24 result words leave as eight 16-byte stores {w0, w1, w2, seq}.  Each store reaches
 // host memory as one write, so a word whose tag equals the awaited sequence number carries valid data: no
@@ -252,6 +301,61 @@ __device__ __forceinline__ void round_quad_publish(const round_args_t &A, const 
     }
 }
 
+// The per-pair version for the streaming kernels: sh_tot holds [pair][A, C, E][17 limbs]; sh_fr needs 26 elements.
+__device__ __forceinline__ void round_quad_publish_pairs(const round_args_t &A, const unsigned long long *sh_tot, fr_t *sh_fr /* [26] */) {
+    if (threadIdx.x < 18) {
+        const int k = threadIdx.x / 3, c = threadIdx.x % 3;   // k = pair * 3 + sum
+        uint32_t t[fr_lazy_t::W + 2 + 5];
+        limb_sums_normalise(sh_tot + k * fr_lazy_t::W, fr_lazy_t::W, t);
+#pragma unroll
+        for (int j = fr_lazy_t::W + 2; j < fr_lazy_t::W + 7; ++j) t[j] = 0;
+        fr_t x, y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x.v[j] = t[8 * c + j];
+            y.v[j] = c == 0 ? (j == 0 ? 1u : 0u) : c == 1 ? fr_cfg::one()[j] : fr_cfg::r2()[j];
+        }
+        uint32_t pm[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pm[j] = fr_cfg::mod()[j];
+        while (fr_t::ge_raw(x.v, pm)) fr_t::raw_sub(x.v, pm);
+        st_fr(sh_fr + threadIdx.x, x * y);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {   // sum k of pair p
+        const fr_t s = sh_fr[3 * threadIdx.x] + sh_fr[3 * threadIdx.x + 1] + sh_fr[3 * threadIdx.x + 2];
+        st_fr(sh_fr + 18 + threadIdx.x, s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {   // one thread per pair: (a, b, c) of the pair, kept for the next round
+        const int p = threadIdx.x;
+        const fr_t a = sh_fr[18 + 3 * p], c = sh_fr[19 + 3 * p], e = sh_fr[20 + 3 * p];
+        fr_t b;
+        if (A.derive_b[p]) {
+            const fr_t pa = ld_fr(A.state + 4 * p), pb = ld_fr(A.state + 4 * p + 1), pc = ld_fr(A.state + 4 * p + 2);
+            const fr_t at_r = (pa * A.r + pb) * A.r + pc;     // P_prev(r) = P(0) + P(1)
+            b = at_r - c - c - a;
+        } else b = e - a - c;
+        if (A.pair[p].n_blocks) {
+            st_fr(A.state + 4 * p, a);
+            st_fr(A.state + 4 * p + 1, b);
+            st_fr(A.state + 4 * p + 2, c);
+        }
+        st_fr(sh_fr + 24 + p, b);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const fr_t a = sh_fr[18] + sh_fr[21], b = sh_fr[24] + sh_fr[25], c = sh_fr[19] + sh_fr[22];
+        if (A.tagged) publish_tagged(A.tagged, a, b, c, A.seq);
+        else {
+            st_fr(A.out + 0, a);
+            st_fr(A.out + 1, b);
+            st_fr(A.out + 2, c);
+            if (A.flag) publish(A.flag, A.seq);
+        }
+    }
+}
+
 // Per output pair (v0,v1),(m0,m1) of the (folded) tables the round polynomial contributes
 //   a += (m1-m0)(v1-v0),  c += m0 v0,  b += (m1-m0) v0 + m0 (v1-v0) = m1 v1 - a - c
 // (linear_poly * linear_poly, src/polynomial.cpp:116-118, evaluated Karatsuba-style with 3 products).  The three sums
@@ -262,9 +366,9 @@ __device__ __forceinline__ void round_quad_publish(const round_args_t &A, const 
 #endif
 __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_quad(round_args_t A) {
     __shared__ unsigned long long sh_warp[(kRoundBlock / 32) * kRoundLimbs];
-    __shared__ unsigned long long sh_tot[kRoundLimbs];
+    __shared__ unsigned long long sh_tot[2 * kRoundLimbs];
     __shared__ uint32_t sh_ticket;
-    __shared__ fr_t sh_fr[12];
+    __shared__ fr_t sh_fr[26];
     const uint32_t nb0 = A.pair[0].n_blocks, nb = nb0 + A.pair[1].n_blocks;
     const bool second = blockIdx.x >= nb0;
     const fr_t *v_in = second ? A.pair[1].v_in : A.pair[0].v_in, *m_in = second ? A.pair[1].m_in : A.pair[0].m_in;
@@ -273,6 +377,7 @@ __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_qua
     const uint32_t fold = second ? A.pair[1].fold : A.pair[0].fold;
     const uint32_t bx = second ? blockIdx.x - nb0 : blockIdx.x;
     const uint32_t stride = (second ? A.pair[1].n_blocks : nb0) * kRoundBlock;
+    const bool derive = (second ? A.derive_b[1] : A.derive_b[0]) != 0;   // b comes from the previous round: no E
     fr_lazy_t acc[3];  // A, C, E
     acc[0].clear(); acc[1].clear(); acc[2].clear();
     if (fold) {
@@ -301,7 +406,7 @@ __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_qua
             st_fr(m_out + 2 * i + 1, m1);
             acc[0].mac(fr_t::sub_lazy(m1, m0), fr_t::sub_lazy(v1, v0));
             acc[1].mac(m0, v0);
-            acc[2].mac(m1, v1);
+            if (!derive) acc[2].mac(m1, v1);
         }
     } else {
         const uint32_t n_pairs = n_in >> 1;
@@ -319,8 +424,8 @@ __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_qua
     for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int j = 0; j < fr_lazy_t::W; ++j) limb[k * fr_lazy_t::W + j] = acc[k].w[j];
-    if (!grid_limb_sum<kRoundLimbs, kRoundBlock>(limb, A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
-    round_quad_publish(A, sh_tot, sh_fr);
+    if (!grid_limb_sum_slice<kRoundLimbs, 2 * kRoundLimbs, kRoundBlock>(limb, second ? kRoundLimbs : 0, A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
+    round_quad_publish_pairs(A, sh_tot, sh_fr);
 }
 
 // K1, latency-bound rounds (tables up to 2^16 entries): the seven multiplications of an output pair are spread over
@@ -472,9 +577,9 @@ __device__ __forceinline__ fr_t fr_mul_inline(const fr_t &a, const fr_t &b) {
 __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(const __grid_constant__ round_tma_args_t T) {
     extern __shared__ __align__(1024) unsigned char dyn_smem[];
     __shared__ unsigned long long sh_warp[(kRoundBlock / 32) * kRoundLimbs];
-    __shared__ unsigned long long sh_tot[kRoundLimbs];
+    __shared__ unsigned long long sh_tot[2 * kRoundLimbs];
     __shared__ uint32_t sh_ticket;
-    __shared__ fr_t sh_fr[12];
+    __shared__ fr_t sh_fr[26];
     __shared__ __align__(8) unsigned long long sh_bar[(kRoundBlock / 32) * 2];
     const round_args_t &A = T.R;
     const uint32_t nb0 = A.pair[0].n_blocks, nb = nb0 + A.pair[1].n_blocks;
@@ -490,6 +595,7 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(c
     const uint32_t n_groups = (limit + 31) >> 5;                               // row blocks of 32 output pairs
     const uint32_t full_groups = (live >> 2) >> 5 < n_groups ? (live >> 2) >> 5 : n_groups;   // blocks whose 128 inputs are all live
     const uint32_t gstride = (second ? A.pair[1].n_blocks : nb0) * (kRoundBlock / 32);
+    const bool derive = (second ? A.derive_b[1] : A.derive_b[0]) != 0;   // b comes from the previous round: no E
 
     const uint32_t box0 = ((smem_addr(dyn_smem) + 1023u) & ~1023u) + warp * kTmaWarpBytes;   // [stage][table] boxes of this warp
     const uint32_t bar0 = smem_addr(sh_bar + 2 * warp);
@@ -564,9 +670,7 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(c
         }
         acc[0].mac(fr_t::sub_lazy(m1, m0), fr_t::sub_lazy(v1, v0));
         acc[1].mac(m0, v0);
-#ifndef ZK_EXPERIMENT_SKIP_THIRD_PRODUCT   // timing experiment only (wrong results): what deriving b from the previous round would save
-        acc[2].mac(m1, v1);
-#endif
+        if (!derive) acc[2].mac(m1, v1);
         stage ^= 1u;
     }
     uint32_t limb[kRoundLimbs];
@@ -574,8 +678,8 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_quad_tma(c
     for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int j = 0; j < fr_lazy_t::W; ++j) limb[k * fr_lazy_t::W + j] = acc[k].w[j];
-    if (!grid_limb_sum<kRoundLimbs, kRoundBlock>(limb, A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
-    round_quad_publish(A, sh_tot, sh_fr);
+    if (!grid_limb_sum_slice<kRoundLimbs, 2 * kRoundLimbs, kRoundBlock>(limb, second ? kRoundLimbs : 0, A.acc, A.counter, nb, sh_warp, sh_tot, &sh_ticket)) return;
+    round_quad_publish_pairs(A, sh_tot, sh_fr);
 }
 #endif  // !ZK_EMU
 
