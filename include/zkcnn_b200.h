@@ -62,6 +62,7 @@ int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_
  *   "thin_max_pairs"   (16384)  rounds with at most this many output pairs per table use k_round_quad_thin
  *   "tma_min_entries"  (131072) fold rounds on tables of at least this many entries use the TMA-staged k_round_quad_tma
  *   "derive_b"         (1)      streaming rounds take b from the previous round's polynomial (0: always three products)
+ *   "pdl"              (1)      k_round_quad_thin is launched with programmatic stream serialization
  *   "msm_few_rows_chunk" (2048) entries per CTA of the bucket kernel for MSMs of at most 8 rows */
 int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value);
 

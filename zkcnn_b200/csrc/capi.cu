@@ -58,6 +58,7 @@ int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
     if (n == "thin_max_pairs") ctx->thin_max_pairs = (uint32_t) value;
     else if (n == "tma_min_entries") ctx->tma_min_entries = value;
     else if (n == "derive_b") ctx->derive_b_enabled = value ? 1u : 0u;
+    else if (n == "pdl") ctx->pdl_enabled = value ? 1u : 0u;
     else if (n == "msm_few_rows_chunk") ctx->msm_few_rows_chunk = (uint32_t) std::max<uint64_t>(256, std::min<uint64_t>(value, kMsmChunk));
     else ZK_REQUIRE(false, "unknown tunable");
     ZK_API_END

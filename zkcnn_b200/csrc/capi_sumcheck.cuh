@@ -526,6 +526,29 @@ static void wait_tagged(zk_ctx *ctx, fr_t abc[3]) {
     for (int k = 0; k < 3; ++k) memcpy(abc[k].v, w + 8 * k, 32);
 }
 
+// k_round_quad_thin with programmatic dependent launch: its CTAs are placed (and its parameters fetched) while the previous
+// kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches memory.  With per-launch
+// profiling events in the stream the overlap cannot happen, so the plain launch is used there.
+static void launch_round_thin(zk_ctx *ctx, int cls, uint64_t bytes, uint32_t gx, const round_args_t &A) {
+#ifndef ZK_EMU
+    if (!ctx->prof_on && ctx->pdl_enabled) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(gx);
+        cfg.blockDim = dim3(kRoundBlock);
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        rt::check(cudaLaunchKernelEx(&cfg, k_round_quad_thin, A), "k_round_quad_thin");
+        ++ctx->launches;
+        return;
+    }
+#endif
+    ZK_KLAUNCH_C(ctx, cls, bytes, k_round_quad_thin, dim3(gx), dim3(kRoundBlock), 0, A);
+}
+
 // Which table pairs took part in a round and how: what the host needs to book the round's results.
 struct round_rec_t {
     bool any_quad = false, any_final = false, first = false;
@@ -608,7 +631,7 @@ static round_rec_t round_quadratic_launch(zk_ctx *ctx, const fr_t &prev, unsigne
     }
     // rounds that stream less than 32 MiB are bound by launch + reduction latency, not by HBM: they are accounted separately
     const int cls = fold_bytes >= (32u << 20) ? ZK_PROF_FOLD : ZK_PROF_FOLD_SMALL;
-    if (any_quad && thin) ZK_KLAUNCH_C(ctx, cls, fold_bytes, k_round_quad_thin, dim3(gx), dim3(kRoundBlock), 0, A);
+    if (any_quad && thin) launch_round_thin(ctx, cls, fold_bytes, gx, A);
 #ifndef ZK_EMU
     else if (any_quad && !first && max_n_in >= ctx->tma_min_entries) launch_round_tma(ctx, cls, fold_bytes, A, limit_pairs);
 #endif

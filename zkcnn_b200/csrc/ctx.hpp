@@ -121,6 +121,7 @@ struct zk_ctx {
     uint32_t seq = 0;
     uint32_t thin_max_pairs = 1u << 14;      // see zk_set_tunable
     uint64_t tma_min_entries = 1ull << 17;
+    uint32_t pdl_enabled = 1;                // k_round_quad_thin launched with programmatic stream serialization
     uint32_t derive_b_enabled = 1;           // streaming rounds: b from the previous round's polynomial (0: always three products)
     uint32_t msm_few_rows_chunk = 2048;      // entries per CTA of k_msm_window when an MSM has at most 8 rows
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft

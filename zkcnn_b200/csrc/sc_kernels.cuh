@@ -440,6 +440,13 @@ __global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A)
     __shared__ unsigned long long sh_tot[kRoundLimbs];
     __shared__ uint32_t sh_ticket;
     __shared__ fr_t sh_fr[12];
+#if ZK_ON_DEVICE
+    // programmatic dependent launch (the host launches this kernel with programmaticStreamSerialization): the CTAs may be
+    // scheduled while the previous kernel of the stream is still running; nothing it wrote is touched before this wait.  Then
+    // the next launch is allowed in turn, so at most one future kernel is ever parked behind a running one.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     const uint32_t nb0 = A.pair[0].n_blocks, nb = nb0 + A.pair[1].n_blocks;
     const bool second = blockIdx.x >= nb0;
     const fr_t *v_in = second ? A.pair[1].v_in : A.pair[0].v_in, *m_in = second ? A.pair[1].m_in : A.pair[0].m_in;
