@@ -338,7 +338,7 @@ int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/
         if (ctx->pair[0].exists) {
             fr_t *V = table_init_buf(ctx->pair[0].v, ctx->pair[0].n_eval);
             if (d.size_u[0])
-                ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) d.size_u[0] * 68, k_gather, dim3(grid_for(d.size_u[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
+                ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, (uint64_t) d.size_u[0] * 68, k_gather, dim3(grid_for(d.size_u[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
                            L.ori_u.as<uint32_t>(), d.size_u[0]);
         }
         if (ctx->pair[1].exists) {
@@ -354,7 +354,7 @@ int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/
             ZK_REQUIRE(r0.size() >= fft_blh, "r_0 too short");
             build_beta(ctx, ctx->beta_gs.as<fr_t>(), fft_blh, pts, 1);
             ctx->beta_g_alt.ensure(sizeof(fr_t) << d.bit_length);
-            ZK_KLAUNCH_C(ctx, ZK_PROF_TABLES, 32ull << d.bit_length, k_beta_outer, dim3(grid_for(1ull << d.bit_length)), dim3(kBlock), 0, ctx->beta_g_alt.as<fr_t>(),
+            ZK_KLAUNCH_PDL(ctx, ZK_PROF_TABLES, 32ull << d.bit_length, k_beta_outer, dim3(grid_for(1ull << d.bit_length)), dim3(kBlock), 0, ctx->beta_g_alt.as<fr_t>(),
                        ctx->beta_g.as<fr_t>(), ctx->beta_gs.as<fr_t>(), (uint32_t) d.bit_length, fft_blh, tail_start, ctx->relu_rou);
             std::swap(ctx->beta_g, ctx->beta_g_alt);
         } else {
@@ -435,7 +435,7 @@ int zk_sumcheck_init_phase2(zk_ctx *ctx) {   // src/prover.cpp:241-310
         if (ctx->pair[0].exists) {
             fr_t *V = table_init_buf(ctx->pair[0].v, ctx->pair[0].n_eval);
             if (d.size_v[0])
-                ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) d.size_v[0] * 68, k_gather, dim3(grid_for(d.size_v[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
+                ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, (uint64_t) d.size_v[0] * 68, k_gather, dim3(grid_for(d.size_v[0])), dim3(kBlock), 0, V, ctx->layers[0].val.as<fr_t>(),
                            L.ori_v.as<uint32_t>(), d.size_v[0]);
         }
         if (ctx->pair[1].exists) {
@@ -658,7 +658,7 @@ int zk_sumcheck_dotprod_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t 
     F.v_in[1] = ctx->mdp.cur; F.live[1] = ctx->mdp_n; F.fold[1] = ctx->mdp_n == 2; F.active[1] = 1;
     F.flag = ctx->flag_d;
     F.seq = ++ctx->seq;
-    ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_final_fold, dim3(1), dim3(32), 0, F);
     wait_mailbox(ctx);
     const fr_t c1 = ctx->res_h[8], m = ctx->res_h[10];
     ctx->V_u1 = c1 * m;
@@ -696,7 +696,7 @@ int zk_sumcheck_liu_init(zk_ctx *ctx, const uint64_t *s_u, const uint64_t *s_v, 
             if (sigma.is_zero() || sz == 0) continue;
             beta_point_t pts[1] = {{r.data(), sigma}};
             halves_t H = build_halves(ctx, bl, pts, 1);
-            ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) sz * 68, k_liu_scatter, dim3(grid_for(sz)), dim3(kBlock), 0, M, (side ? L.ori_v : L.ori_u).as<uint32_t>(), sz, H.f[0],
+            ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, (uint64_t) sz * 68, k_liu_scatter, dim3(grid_for(sz)), dim3(kBlock), 0, M, (side ? L.ori_v : L.ori_u).as<uint32_t>(), sz, H.f[0],
                        H.s[0], H.first_half);
         }
     }

@@ -83,6 +83,29 @@ static inline zk::rt::event_t prof_event(zk_ctx *ctx) {
         }                                                                                 \
     } while (0)
 #define ZK_KLAUNCH(ctx, kernel, grid, block, smem, ...) ZK_KLAUNCH_C(ctx, ZK_PROF_OTHER, 0, kernel, grid, block, smem, __VA_ARGS__)
+// for kernels that start with ZK_PDL_ENTRY() (sc_kernels.cuh): programmatic dependent launch on the main stream; with
+// per-launch profiling events in the stream the overlap cannot happen, so the plain launch is used there
+#ifndef ZK_EMU
+#define ZK_KLAUNCH_PDL(ctx, cls, bytes, kernel, grid, block, smem, ...)                                       \
+    do {                                                                                                      \
+        if (!(ctx)->prof_on && (ctx)->pdl_enabled) {                                                          \
+            cudaLaunchConfig_t zk_cfg_ = {};                                                                  \
+            zk_cfg_.gridDim = (grid);                                                                         \
+            zk_cfg_.blockDim = (block);                                                                       \
+            zk_cfg_.dynamicSmemBytes = (smem);                                                                \
+            zk_cfg_.stream = (ctx)->stream;                                                                   \
+            cudaLaunchAttribute zk_attr_[1];                                                                  \
+            zk_attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+            zk_attr_[0].val.programmaticStreamSerializationAllowed = 1;                                       \
+            zk_cfg_.attrs = zk_attr_;                                                                         \
+            zk_cfg_.numAttrs = 1;                                                                             \
+            zk::rt::check(cudaLaunchKernelEx(&zk_cfg_, kernel, __VA_ARGS__), #kernel);                        \
+            ++(ctx)->launches;                                                                                \
+        } else ZK_KLAUNCH_C(ctx, cls, bytes, kernel, grid, block, smem, __VA_ARGS__);                         \
+    } while (0)
+#else
+#define ZK_KLAUNCH_PDL(ctx, cls, bytes, kernel, grid, block, smem, ...) ZK_KLAUNCH_C(ctx, cls, bytes, kernel, grid, block, smem, __VA_ARGS__)
+#endif
 
 static void prof_resolve(zk_ctx *ctx) {
     for (auto &r : ctx->prof_pending) {
@@ -302,7 +325,7 @@ static halves_t build_halves(zk_ctx *ctx, uint32_t bits, const beta_point_t *pts
         H.f[k] = ctx->half[2 * k].as<fr_t>();
         H.s[k] = ctx->half[2 * k + 1].as<fr_t>();
     }
-    ZK_KLAUNCH_C(ctx, ZK_PROF_TABLES, 0, k_half_tables, dim3(4), dim3(kBlock), 0, A);
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_TABLES, 0, k_half_tables, dim3(4), dim3(kBlock), 0, A);
     return H;
 }
 
@@ -317,7 +340,7 @@ static void build_beta(zk_ctx *ctx, fr_t *out, uint32_t bits, const beta_point_t
     B.f1 = (k0 == 0) ? H.f[1] : nullptr; B.s1 = (k0 == 0) ? H.s[1] : nullptr;
     B.bits = bits; B.first_half = H.first_half;
     B.tail_start = tail_start; B.tail_scale = tail_scale;
-    ZK_KLAUNCH_C(ctx, ZK_PROF_TABLES, 32ull << bits, k_beta_expand, dim3(grid_for(1ull << bits)), dim3(kBlock), 0, B);
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_TABLES, 32ull << bits, k_beta_expand, dim3(grid_for(1ull << bits)), dim3(kBlock), 0, B);
 }
 
 static void run_schedule(zk_ctx *ctx, const schedule_t &S, int phase, gate_args_t A) {
@@ -331,11 +354,11 @@ static void run_schedule(zk_ctx *ctx, const schedule_t &S, int phase, gate_args_
         A.n_items = L.n_items;
         A.partial = ctx->gate_partial[k & 1].as<fr_t>();
         if (k == 0) {
-            if (phase == 1) ZK_KLAUNCH_C(ctx, ZK_PROF_GATES, S.n_recs * 44 + S.n_val_recs * 32 + (uint64_t) L.n_items * 44, k_gate_items_p1, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
-            else ZK_KLAUNCH_C(ctx, ZK_PROF_GATES, S.n_recs * 76 + (uint64_t) L.n_items * 44, k_gate_items_p2, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
+            if (phase == 1) ZK_KLAUNCH_PDL(ctx, ZK_PROF_GATES, S.n_recs * 44 + S.n_val_recs * 32 + (uint64_t) L.n_items * 44, k_gate_items_p1, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
+            else ZK_KLAUNCH_PDL(ctx, ZK_PROF_GATES, S.n_recs * 76 + (uint64_t) L.n_items * 44, k_gate_items_p2, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A);
         } else {
             const fr_t *src = ctx->gate_partial[(k - 1) & 1].as<fr_t>();
-            ZK_KLAUNCH_C(ctx, ZK_PROF_GATES, (uint64_t) L.n_items * 44 + (uint64_t) S.levels[k - 1].n_partials * 32, k_sum_partials, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A, src);
+            ZK_KLAUNCH_PDL(ctx, ZK_PROF_GATES, (uint64_t) L.n_items * 44 + (uint64_t) S.levels[k - 1].n_partials * 32, k_sum_partials, dim3(grid_for(L.n_items)), dim3(kBlock), 0, A, src);
         }
     }
 }
@@ -530,23 +553,7 @@ static void wait_tagged(zk_ctx *ctx, fr_t abc[3]) {
 // kernel of the stream drains; the kernel itself waits (griddepcontrol.wait) before it touches memory.  With per-launch
 // profiling events in the stream the overlap cannot happen, so the plain launch is used there.
 static void launch_round_thin(zk_ctx *ctx, int cls, uint64_t bytes, uint32_t gx, const round_args_t &A) {
-#ifndef ZK_EMU
-    if (!ctx->prof_on && ctx->pdl_enabled) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(gx);
-        cfg.blockDim = dim3(kRoundBlock);
-        cfg.stream = ctx->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        rt::check(cudaLaunchKernelEx(&cfg, k_round_quad_thin, A), "k_round_quad_thin");
-        ++ctx->launches;
-        return;
-    }
-#endif
-    ZK_KLAUNCH_C(ctx, cls, bytes, k_round_quad_thin, dim3(gx), dim3(kRoundBlock), 0, A);
+    ZK_KLAUNCH_PDL(ctx, cls, bytes, k_round_quad_thin, dim3(gx), dim3(kRoundBlock), 0, A);
 }
 
 // Which table pairs took part in a round and how: what the host needs to book the round's results.
@@ -635,8 +642,8 @@ static round_rec_t round_quadratic_launch(zk_ctx *ctx, const fr_t &prev, unsigne
 #ifndef ZK_EMU
     else if (any_quad && !first && max_n_in >= ctx->tma_min_entries) launch_round_tma(ctx, cls, fold_bytes, A, limit_pairs);
 #endif
-    else if (any_quad) ZK_KLAUNCH_C(ctx, cls, fold_bytes, k_round_quad, dim3(gx), dim3(kRoundBlock), 0, A);
-    if (any_final) ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
+    else if (any_quad) ZK_KLAUNCH_PDL(ctx, cls, fold_bytes, k_round_quad, dim3(gx), dim3(kRoundBlock), 0, A);
+    if (any_final) ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_final_fold, dim3(1), dim3(32), 0, F);
     // the table state follows from the sizes alone
     for (int b = 0; b < 2; ++b) {
         pair_t &P = ctx->pair[b];
@@ -723,7 +730,7 @@ static void final_values(zk_ctx *ctx, const fr_t &prev, fr_t out[2]) {
     if (any) {
         F.flag = ctx->flag_d;
         F.seq = ++ctx->seq;
-        ZK_KLAUNCH(ctx, k_final_fold, dim3(1), dim3(32), 0, F);
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_final_fold, dim3(1), dim3(32), 0, F);
         wait_mailbox(ctx);
         for (int b = 0; b < 2; ++b)
             if (F.active[b]) out[b] = ctx->res_h[8 + 2 * b];
