@@ -23,6 +23,7 @@ enum {
     ZKH_FIXED_GENERATORS = 8,  /* reuse the generators of the previous proof (public parameters), keep the window table */
     ZKH_PREFETCH_NEXT    = 32, /* once this proof has its witness, start copying the witness for the NEXT zkh_prove on a second stream
                                  (double buffering: the copy overlaps this proof; the next proof adopts it instead of uploading) */
+    ZKH_NO_HASH          = 64, /* leave zkh_stats.fnv1a at 0 (the FNV-1a of the 0.5 MB transcript costs 0.7 ms per vgg11 proof) */
     ZKH_ROUND_BY_ROUND   = 16  /* one device round trip per sumcheck round (the reference's call pattern) instead of one per phase:
                                  the verifier draws a phase's challenges before its first round either way (src/verifier.cpp:156-160),
                                  so the transcript is the same; default is per phase (zk_sumcheck_update_batch) */

@@ -268,7 +268,7 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-REAL_GENERATORS, CHECK_PREDICATES, WITNESS_RESIDENT, FIXED_GENERATORS, ROUND_BY_ROUND, PREFETCH_NEXT = 1, 2, 4, 8, 16, 32
+REAL_GENERATORS, CHECK_PREDICATES, WITNESS_RESIDENT, FIXED_GENERATORS, ROUND_BY_ROUND, PREFETCH_NEXT, NO_HASH = 1, 2, 4, 8, 16, 32, 64
 
 
 class HostLib:

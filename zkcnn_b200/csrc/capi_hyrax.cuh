@@ -100,7 +100,7 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         const uint64_t warps = (uint64_t) n_rows * n_seg;
         ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, alg_bytes, k_msm_small, dim3((uint32_t) ((warps + kSmallWarps - 1) / kSmallWarps)), dim3(kSmallWarps * 32), 0, S);
     } else {
-        ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, 0, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
     }
     const uint32_t chunk = n_rows <= 8 ? std::min<uint32_t>(ctx->msm_few_rows_chunk, kMsmChunk) : kMsmChunk;   // few rows: more CTAs per row
     const uint32_t n_chunks = (uint32_t) ((n + chunk - 1) / chunk);
@@ -116,10 +116,12 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     A.chunk = chunk;
     A.wide_only = small_path ? 1u : 0u;
     A.partial = H.msm_out.as<g1_jac_t>();
+    const bool waited = H.table_pending;   // a cross-stream wait sits between this launch and its predecessor: plain launch then
     msm_wait_table(ctx, H);
     // grid.x is limited to 2^31-1, grid.y to 65535: rows * chunks in x, windows in y
-    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
-    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kSmallWarps - 1) / kSmallWarps), dim3(kSmallWarps * 32), 0,
+    if (waited) ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
+    else ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kSmallWarps - 1) / kSmallWarps), dim3(kSmallWarps * 32), 0,
                  small_path ? H.msm_small.as<g1_jac_t>() : (const g1_jac_t *) nullptr, n_seg, H.msm_out.as<g1_jac_t>(), (uint32_t) per_row, n_rows, out_dev);
 }
 
@@ -252,12 +254,12 @@ int zk_poly_bullet_prove(zk_ctx *ctx, uint64_t *lcomm, uint64_t *rcomm, uint64_t
     const uint32_t lsize = 1u << H.l_bits, m = H.cur, h = m >> 1;
     // two MSMs over the original generators (see k_bullet_scalars)
     H.scal.ensure((size_t) 2 * lsize * sizeof(fr_t));
-    ZK_KLAUNCH(ctx, k_bullet_scalars, dim3(grid_for(lsize)), dim3(kBlock), 0, H.a.as<fr_t>(), H.coef.as<fr_t>(), lsize, m, H.scal.as<fr_t>());
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_bullet_scalars, dim3(grid_for(lsize)), dim3(kBlock), 0, H.a.as<fr_t>(), H.coef.as<fr_t>(), lsize, m, H.scal.as<fr_t>());
     rt::dbuf &pts = H.pts_out;
     pts.ensure(2 * sizeof(g1_jac_t));
     msm_run(ctx, H, H.scal.as<fr_t>(), lsize, 2, pts.as<g1_jac_t>());
     // ly, ry
-    ZK_KLAUNCH(ctx, k_dot2, dim3(1), dim3(kBlock), 0, H.a.as<fr_t>(), H.L.as<fr_t>(), h, ctx->round_out.as<fr_t>());
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_dot2, dim3(1), dim3(kBlock), 0, H.a.as<fr_t>(), H.L.as<fr_t>(), h, ctx->round_out.as<fr_t>());
     rt::d2h(ctx->h_out, ctx->round_out.p, 2 * sizeof(fr_t), ctx->stream);
     g1_jac_t hp[2];
     rt::d2h(hp, pts.p, sizeof hp, ctx->stream);
@@ -279,12 +281,12 @@ int zk_poly_bullet_update(zk_ctx *ctx, const uint64_t *randomness) {   // polyPr
     const fr_t r = fr_load(randomness);
     const fr_t rinv = r.inverse();
     const uint32_t lsize = 1u << H.l_bits, h = H.cur >> 1;
-    ZK_KLAUNCH(ctx, k_bullet_fold, dim3(grid_for(h)), dim3(kBlock), 0, H.a.as<fr_t>(), H.a_next.as<fr_t>(), h, r);
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_bullet_fold, dim3(grid_for(h)), dim3(kBlock), 0, H.a.as<fr_t>(), H.a_next.as<fr_t>(), h, r);
     std::swap(H.a, H.a_next);
     // generators fold as g[i] * r^-1 + g[i + h]: the coefficient of G_j picks up r^-1 when j lies in a lower half
     uint32_t bit = 0;
     while ((1u << bit) < h) ++bit;   // h == 2^bit
-    ZK_KLAUNCH(ctx, k_bullet_coef, dim3(grid_for(lsize)), dim3(kBlock), 0, H.coef.as<fr_t>(), lsize, bit, rinv);
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_bullet_coef, dim3(grid_for(lsize)), dim3(kBlock), 0, H.coef.as<fr_t>(), lsize, bit, rinv);
     H.cur = h;
     ++H.round;
     H.t.pop_back();

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kTableBuildBlock) k_msm_table_build(const g1_a
 
 // widest magnitude (in bytes) per row
 __global__ void __launch_bounds__(kBlock) k_msm_rowinfo(const fr_t *scalars, uint64_t n, uint32_t n_rows, uint32_t *rowinfo) {
+    ZK_PDL_ENTRY();
     const uint64_t total = n * n_rows;
     for (uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x; i < total; i += (uint64_t) gridDim.x * kBlock) {
         fr_t s = ld_fr(scalars + i);
@@ -147,6 +148,7 @@ struct msm_args_t {
 
 // grid = (n_rows * n_chunks, kMsmWindows)
 __global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
+    ZK_PDL_ENTRY();
     ZK_DYN_SMEM(msm_smem_t, S);
     const uint32_t t = threadIdx.x;
     const uint32_t row = blockIdx.x / A.n_chunks, chunk = blockIdx.x % A.n_chunks, w = blockIdx.y;
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(64) k_msm_finish(const g1_jac_t *partial, uint
 // (h full scalar multiplications per round) the coefficients are folded and each round's two MSMs run over the
 // ORIGINAL generators with scalars a_k[j mod m] * c_k(j):  rows[0] takes the j with (j mod m) < h, rows[1] the others.
 __global__ void __launch_bounds__(kBlock) k_bullet_scalars(const fr_t *a, const fr_t *coef, uint32_t n, uint32_t m, fr_t *rows) {
+    ZK_PDL_ENTRY();
     const uint32_t h = m >> 1;
     for (uint32_t j = blockIdx.x * kBlock + threadIdx.x; j < n; j += gridDim.x * kBlock) {
         const uint32_t i = j & (m - 1);
@@ -291,16 +294,19 @@ __global__ void __launch_bounds__(kBlock) k_bullet_scalars(const fr_t *a, const 
 }
 // coef[j] *= rinv where bit `bit` of j is clear
 __global__ void __launch_bounds__(kBlock) k_bullet_coef(fr_t *coef, uint32_t n, uint32_t bit, fr_t rinv) {
+    ZK_PDL_ENTRY();
     for (uint32_t j = blockIdx.x * kBlock + threadIdx.x; j < n; j += gridDim.x * kBlock)
         if (!((j >> bit) & 1u)) st_fr(coef + j, ld_fr(coef + j) * rinv);
 }
 // a'[i] = a[i] * r + a[i + h]   (polyProver.cpp:103)
 __global__ void __launch_bounds__(kBlock) k_bullet_fold(const fr_t *a, fr_t *out, uint32_t h, fr_t r) {
+    ZK_PDL_ENTRY();
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < h; i += gridDim.x * kBlock)
         st_fr(out + i, ld_fr(a + i) * r + ld_fr(a + i + h));
 }
 // out[0] = sum_{i<h} a[i] L[i],  out[1] = sum_{i<h} a[i+h] L[i]   (polyProver.cpp:88-91); one CTA
 __global__ void __launch_bounds__(kBlock) k_dot2(const fr_t *a, const fr_t *L, uint32_t h, fr_t *out) {
+    ZK_PDL_ENTRY();
     __shared__ fr_t sh[2 * kBlock];
     fr_t acc[2] = {fr_t::zero(), fr_t::zero()};
     for (uint32_t i = threadIdx.x; i < h; i += kBlock) {

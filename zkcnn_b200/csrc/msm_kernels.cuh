@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
 // ---- out[row] = normalised (sum of the row's small-path partials + sum of its bucket-path partials); one warp per row ------------
 __global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_jac_t *small, uint32_t n_small, const g1_jac_t *bucket,
                                                                         uint32_t n_bucket, uint32_t n_rows, g1_jac_t *out) {
+    ZK_PDL_ENTRY();
     __shared__ g1_jac_t sh[kSmallWarps * 32];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t row = blockIdx.x * kSmallWarps + warp;

@@ -185,7 +185,7 @@ int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
         out->n_fr = s->tr.n_fr;
         out->n_g1 = s->tr.n_g1;
         out->proof_bytes = s->tr.bytes.size();
-        out->fnv1a = s->tr.fnv1a();
+        out->fnv1a = (flags & ZKH_NO_HASH) ? 0 : s->tr.fnv1a();
         out->challenges = rng.stream.calls;
         out->gpu_launches = p.gpuLaunches() - l0;
         out->prove_s = p.proveTime() - pt0;

@@ -52,7 +52,7 @@ vector<G1> polyProver::commit() {   // polyProver.cpp:19-34
     check(zk_poly_commit(ctx_, w(comm_Z[0]), (uint32_t) rsize), "zk_poly_commit");
     pt.stop();
     ps += ZK_G1_BYTES * comm_Z.size();
-    if (tr_) for (auto &p : comm_Z) tr_->put_g1(w(p));
+    if (tr_ && !comm_Z.empty()) tr_->put_g1_many(w(comm_Z[0]), comm_Z.size());
     return comm_Z;
 }
 

@@ -33,6 +33,8 @@ struct Transcript {
         bytes.insert(bytes.end(), b, b + 96);
         ++n_g1;
     }
+    // many points at once (the 2^(bl/2) row commitments): the conversions are independent, a few host threads share them
+    void put_g1_many(const uint64_t *w, size_t n);
     uint64_t fnv1a() const {
         uint64_t h = 0xcbf29ce484222325ULL;
         for (uint8_t b : bytes) { h ^= b; h *= 0x100000001b3ULL; }
