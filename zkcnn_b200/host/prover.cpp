@@ -57,11 +57,18 @@ void prover::uploadCircuit() {
     circuit_uploaded_ = true;
 }
 
+// entries of val[i] that carry data: commitInput() pads val[0] with zeros up to a power of two on the host
+// (src/prover.cpp:504-508); the device pads its copy itself, so the padding (124 MB for vgg11) never crosses PCIe
+size_t prover::witnessLength(u32 i) const {
+    return i == 0 ? std::min<size_t>(val[0].size(), C.circuit[0].size) : val[i].size();
+}
+
 void prover::uploadWitness() {
     last_upload_bytes_ = 0;
     for (u32 i = 0; i < C.size; ++i) {
-        check(zk_witness_layer(ctx_, i, val[i].empty() ? nullptr : w(val[i][0]), val[i].size()), "zk_witness_layer");
-        last_upload_bytes_ += val[i].size() * sizeof(F);
+        const size_t n = witnessLength(i);
+        check(zk_witness_layer(ctx_, i, n ? w(val[i][0]) : nullptr, n), "zk_witness_layer");
+        last_upload_bytes_ += n * sizeof(F);
     }
     witness_uploaded_ = true;
 }
@@ -91,10 +98,10 @@ void prover::prefetchWitness() {
     joinPrefetch();
     prefetch_bytes_ = 0;
     prefetch_error_.clear();
-    for (int i = 0; i < C.size; ++i) prefetch_bytes_ += val[i].size() * sizeof(F);
+    for (int i = 0; i < C.size; ++i) prefetch_bytes_ += witnessLength(i) * sizeof(F);
     prefetch_thread_ = std::thread([this] {
         for (int i = 0; i < C.size; ++i)
-            if (zk_witness_layer_prefetch(ctx_, i, val[i].empty() ? nullptr : w(val[i][0]), val[i].size()) != 0) {
+            if (zk_witness_layer_prefetch(ctx_, i, witnessLength(i) ? w(val[i][0]) : nullptr, witnessLength(i)) != 0) {
                 prefetch_error_ = zk_last_error();
                 return;
             }

@@ -103,6 +103,7 @@ private:
     void check(int rc, const char *what) const;
     void uploadCircuit();
     void uploadWitness();
+    size_t witnessLength(u32 layer) const;
 
     zk_ctx *ctx_ = nullptr;
     int device_ = -1;
