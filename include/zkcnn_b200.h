@@ -106,6 +106,11 @@ int zk_witness_layer(zk_ctx *ctx, uint32_t layer_id, const uint64_t *val, uint64
  * (val must stay valid and unchanged until the commit), then make all prefetched layers current */
 int zk_witness_layer_prefetch(zk_ctx *ctx, uint32_t layer_id, const uint64_t *val, uint64_t n);
 int zk_witness_commit_prefetch(zk_ctx *ctx);
+/* prover::val[layer_id] in a compact encoding (8 instead of 32 bytes per element over PCIe): small[i] = the value as a signed
+ * 64-bit integer (mcl's sign convention), except at wide_idx[0..n_wide), whose full Montgomery values are wide_val[];
+ * prefetch != 0: into the shadow buffer on the copy stream, made current by zk_witness_commit_prefetch */
+int zk_witness_layer_compact(zk_ctx *ctx, uint32_t layer_id, const int64_t *small, uint64_t n, const uint32_t *wide_idx, const uint64_t *wide_val,
+                             uint32_t n_wide, int prefetch);
 
 /* ---- GKR prover: one entry point per public member of class prover ---------------------------------------------- */
 int zk_prover_init(zk_ctx *ctx);                                                             /* prover.cpp:17  */

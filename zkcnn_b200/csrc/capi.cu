@@ -216,6 +216,59 @@ int zk_witness_layer_prefetch(zk_ctx *ctx, uint32_t id, const uint64_t *val, uin
     L.next_ready = true;
     ZK_API_END
 }
+// prover::val[layer_id] in the compact encoding: small[i] is the value as a signed 64-bit integer (mcl's sign convention: a
+// field element >= (r+1)/2 is negative), except at the n_wide positions wide_idx[], whose full values are wide_val[] (and
+// whose small[] entry is ignored).  prefetch != 0: into the shadow buffer, on the copy stream (see zk_witness_layer_prefetch).
+int zk_witness_layer_compact(zk_ctx *ctx, uint32_t id, const int64_t *small, uint64_t n, const uint32_t *wide_idx, const uint64_t *wide_val,
+                             uint32_t n_wide, int prefetch) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && id < ctx->n_layers && (small || n == 0) && (n_wide == 0 || (wide_idx && wide_val)), "bad witness layer");
+    rt::set_device(ctx->device);
+    if (prefetch && !ctx->copy_stream) ctx->copy_stream = rt::stream_create(false);
+    zk_stream_t strm = prefetch ? ctx->copy_stream : ctx->stream;
+    layer_t &L = ctx->layers[id];
+    uint64_t cap = n;
+    if (id == 0) { cap = 1; while (cap < n) cap <<= 1; }
+    rt::dbuf &dst = prefetch ? L.val_next : L.val;
+    dst.ensure(std::max<uint64_t>(1, cap) * sizeof(fr_t));
+    fr_t *out = dst.as<fr_t>();
+#ifdef ZK_EMU
+    for (uint64_t i = 0; i < n; ++i) out[i] = fr_t::from_i64(small[i]);   // (no kernel launches from a helper thread on the emulator)
+    for (uint32_t i = 0; i < n_wide; ++i) memcpy(out + wide_idx[i], wide_val + 4 * (size_t) i, sizeof(fr_t));
+#else
+    if (n) {
+        const void *src = rt::host_device_ptr(small);   // page-locked + mapped: the SMs read it in place
+        if (!src) {
+            L.compact_stage.ensure(n * 8);
+            rt::h2d(L.compact_stage.p, small, n * 8, strm);
+            src = L.compact_stage.p;
+        }
+        ZK_LAUNCH(k_expand_i64, dim3(n >= (1u << 22) ? 64 : 8), dim3(kBlock), 0, strm, out, static_cast<const long long *>(src), n);
+        rt::check_launch("k_expand_i64");
+        ++ctx->launches;
+    }
+    if (n_wide) {
+        const size_t val_off = ((size_t) n_wide * 4 + 31) & ~(size_t) 31;   // indices first, then the 32-byte values
+        L.wide_stage.ensure(val_off + (size_t) n_wide * 32);
+        uint32_t *di = L.wide_stage.as<uint32_t>();
+        fr_t *dv = reinterpret_cast<fr_t *>(static_cast<char *>(L.wide_stage.p) + val_off);
+        rt::h2d(di, wide_idx, (size_t) n_wide * 4, strm);
+        rt::h2d(dv, wide_val, (size_t) n_wide * 32, strm);
+        ZK_LAUNCH(k_scatter_fr, dim3(grid_for(n_wide)), dim3(kBlock), 0, strm, out, di, dv, n_wide);
+        rt::check_launch("k_scatter_fr");
+        ++ctx->launches;
+    }
+#endif
+    if (cap > n) rt::dzero(out + n, (cap - n) * sizeof(fr_t), strm);
+    if (prefetch) {
+        L.n_val_next = n;
+        L.next_ready = true;
+    } else {
+        rt::sync(strm);
+        L.n_val = n;
+    }
+    ZK_API_END
+}
 // wait for the prefetched layers and make them the current witness (the previous buffers become the next shadow copies)
 int zk_witness_commit_prefetch(zk_ctx *ctx) {
     ZK_API_BEGIN

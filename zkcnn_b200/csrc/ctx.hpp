@@ -35,6 +35,7 @@ struct layer_t {
     rt::dbuf val_next;         // shadow copy filled by zk_witness_layer_prefetch (the next proof's witness)
     uint64_t n_val_next = 0;
     bool next_ready = false;
+    rt::dbuf compact_stage, wide_stage;   // zk_witness_layer_compact: staging of the int64 values (when not mapped) and of the wide ones
     bool have_desc = false;
 };
 

@@ -714,6 +714,26 @@ __global__ void __launch_bounds__(kBlock) k_copy_from_host(uint4 *dst, const uin
     for (; i < n16; i += stride) dst[i] = src[i];
 }
 
+// Compact witness: most witness values are small signed integers (quantised activations, weights, bit decompositions), so
+// the host keeps them as int64 (8 bytes instead of 32 over PCIe) and the device rebuilds the Montgomery form: one
+// multiplication by R^2 per element.  `in` may be mapped host memory (zero-copy loads, see k_copy_from_host); four
+// independent loads per thread keep the link busy.  Values that do not fit go through k_scatter_fr afterwards.
+__global__ void __launch_bounds__(kBlock) k_expand_i64(fr_t *out, const long long *in, uint64_t n) {
+    const uint64_t stride = (uint64_t) gridDim.x * kBlock;
+    uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const long long a = in[i], b = in[i + stride], c = in[i + 2 * stride], d = in[i + 3 * stride];
+        st_fr(out + i, fr_t::from_i64(a));
+        st_fr(out + i + stride, fr_t::from_i64(b));
+        st_fr(out + i + 2 * stride, fr_t::from_i64(c));
+        st_fr(out + i + 3 * stride, fr_t::from_i64(d));
+    }
+    for (; i < n; i += stride) st_fr(out + i, fr_t::from_i64(in[i]));
+}
+__global__ void __launch_bounds__(kBlock) k_scatter_fr(fr_t *out, const uint32_t *idx, const fr_t *val, uint32_t n) {
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr(out + idx[i], ld_fr(val + i));
+}
+
 // fold a 2-entry table pair down to single values (the "total == 1" collapse, src/prover.cpp:400-404, and the
 // eval(previous_random) of the Finalize calls, src/prover.cpp:146-153,459-497).  out[2*i], out[2*i+1] = v, m of pair i.
 struct final_fold_args_t {

@@ -1,5 +1,6 @@
 // See prover.hpp.  Control flow and accounting mirror src/prover.cpp of the reference; the arithmetic is on the device.
 #include "prover.hpp"
+#include <algorithm>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -67,8 +68,14 @@ void prover::uploadWitness() {
     last_upload_bytes_ = 0;
     for (u32 i = 0; i < C.size; ++i) {
         const size_t n = witnessLength(i);
-        check(zk_witness_layer(ctx_, i, n ? w(val[i][0]) : nullptr, n), "zk_witness_layer");
-        last_upload_bytes_ += n * sizeof(F);
+        if (compact_ready_) {
+            check(zk_witness_layer_compact(ctx_, i, compact_[i].data(), n, wide_idx_[i].data(), wide_idx_[i].empty() ? nullptr : w(wide_val_[i][0]),
+                                           (uint32_t) wide_idx_[i].size(), 0), "zk_witness_layer_compact");
+            last_upload_bytes_ += compactBytes(i);
+        } else {
+            check(zk_witness_layer(ctx_, i, n ? w(val[i][0]) : nullptr, n), "zk_witness_layer");
+            last_upload_bytes_ += n * sizeof(F);
+        }
     }
     witness_uploaded_ = true;
 }
@@ -79,12 +86,66 @@ void prover::pinWitness() {
     // commitInput() later pads val[0] to 2^bit_length in place (src/prover.cpp:504-508): make room now so that the
     // vector is not reallocated after it has been page-locked
     if (!val.empty() && C.size) val[0].reserve((size_t) 1 << C.circuit[0].bit_length);
+#ifndef ZKCNN_DROPIN   // (with the reference's own mcl types the shim has no view of the limbs: plain 32-byte upload there)
+    if (!getenv("ZKCNN_NO_COMPACT")) {
+        // with the compact encoding only the int64 arrays cross PCIe: those are the buffers to page-lock
+        buildCompactWitness();
+        for (auto &c : compact_)
+            if (!c.empty() && zk_host_pin(c.data(), c.capacity() * sizeof(int64_t)) == 0) pinned_.push_back(c.data());
+        return;
+    }
+#endif
     for (auto &v : val)
         if (!v.empty() && zk_host_pin(v.data(), v.capacity() * sizeof(F)) == 0) pinned_.push_back(v.data());
 }
 
+// int64 image of the witness: |x| < 2^62 under mcl's sign convention (a value >= (r+1)/2 stands for x - r) -> compact_, anything
+// else -> (index, value) in the wide lists.  Done once per witness (part of zkh_build), on a few host threads.
+void prover::buildCompactWitness() {
+#ifndef ZKCNN_DROPIN
+    compact_.assign(C.size, {});
+    wide_idx_.assign(C.size, {});
+    wide_val_.assign(C.size, {});
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    for (u32 l = 0; l < C.size; ++l) {
+        const size_t n = witnessLength(l);
+        compact_[l].assign(n, 0);
+        std::vector<std::vector<uint32_t>> wide(hw);
+        auto work = [&](unsigned t) {
+            const size_t b = n * t / hw, e = n * (t + 1) / hw;
+            for (size_t i = b; i < e; ++i) {
+                uint32_t c[8];
+                val[l][i].v.to_canonical(c);
+                bool small = !(c[2] | c[3] | c[4] | c[5] | c[6] | c[7]) && c[1] < (1u << 30);
+                int64_t x = (int64_t) ((uint64_t) c[0] | ((uint64_t) c[1] << 32));
+                if (!small) {   // maybe negative: r - c
+                    const uint32_t *p = zk::fr_cfg::mod();
+                    uint32_t d[8];
+                    int64_t bw = 0;
+                    for (int k = 0; k < 8; ++k) { bw += (int64_t) p[k] - (int64_t) c[k]; d[k] = (uint32_t) bw; bw >>= 32; }
+                    if (!(d[2] | d[3] | d[4] | d[5] | d[6] | d[7]) && d[1] < (1u << 30)) {
+                        small = true;
+                        x = -(int64_t) ((uint64_t) d[0] | ((uint64_t) d[1] << 32));
+                    }
+                }
+                if (small) compact_[l][i] = x;
+                else wide[t].push_back((uint32_t) i);
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < hw; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+        for (auto &wv : wide)
+            for (uint32_t i : wv) { wide_idx_[l].push_back(i); wide_val_[l].push_back(val[l][i]); }
+    }
+    compact_ready_ = true;
+#endif
+}
+
 void prover::unpinWitness() {
     joinPrefetch();   // a copy in flight reads these buffers
+    compact_ready_ = false;
     for (const void *p : pinned_) zk_host_unpin(p);
     pinned_.clear();
 }
@@ -98,10 +159,12 @@ void prover::prefetchWitness() {
     joinPrefetch();
     prefetch_bytes_ = 0;
     prefetch_error_.clear();
-    for (int i = 0; i < C.size; ++i) prefetch_bytes_ += witnessLength(i) * sizeof(F);
+    for (int i = 0; i < C.size; ++i) prefetch_bytes_ += compact_ready_ ? compactBytes(i) : witnessLength(i) * sizeof(F);
     prefetch_thread_ = std::thread([this] {
         for (int i = 0; i < C.size; ++i)
-            if (zk_witness_layer_prefetch(ctx_, i, witnessLength(i) ? w(val[i][0]) : nullptr, witnessLength(i)) != 0) {
+            if ((compact_ready_ ? zk_witness_layer_compact(ctx_, i, compact_[i].data(), witnessLength(i), wide_idx_[i].data(),
+                                                           wide_idx_[i].empty() ? nullptr : w(wide_val_[i][0]), (uint32_t) wide_idx_[i].size(), 1)
+                                : zk_witness_layer_prefetch(ctx_, i, witnessLength(i) ? w(val[i][0]) : nullptr, witnessLength(i))) != 0) {
                 prefetch_error_ = zk_last_error();
                 return;
             }

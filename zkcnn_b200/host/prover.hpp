@@ -104,6 +104,13 @@ private:
     void uploadCircuit();
     void uploadWitness();
     size_t witnessLength(u32 layer) const;
+    // compact witness (built by pinWitness): int64 per element + the few elements that do not fit; what actually crosses PCIe
+    void buildCompactWitness();
+    std::vector<std::vector<int64_t>> compact_;
+    std::vector<std::vector<uint32_t>> wide_idx_;
+    std::vector<std::vector<F>> wide_val_;
+    bool compact_ready_ = false;
+    uint64_t compactBytes(u32 layer) const { return compact_[layer].size() * 8 + wide_idx_[layer].size() * 36; }
 
     zk_ctx *ctx_ = nullptr;
     int device_ = -1;
