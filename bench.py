@@ -248,8 +248,9 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": round(args.steps * world / t_value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(t_value / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 limbs (BLS12-381 Fr 255-bit / Fp 381-bit Montgomery)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "vgg11 CIFAR pic_cnt=1, one proof per step per GPU (BASELINE config 3/4)" if model == "vgg11" else model,
+                       "arithmetic": "exact modular integer arithmetic on 32-bit limbs: BLS12-381 Fr (255-bit) and Fp (381-bit) in Montgomery form",
                        "network": config, "input_layer": st0["input_size"], "layers": st0["n_layers"], "generators": "non-degenerate (G * challenge)",
                        "rounds": "one device call per sumcheck round" if args.round_by_round else "one device call per sumcheck phase (challenges of a phase are drawn before its rounds, as in src/verifier.cpp:156-160)",
                        "l2": "tables larger than L2 (2^24 x 32 B witness, 537 MB)", "parallelism": f"one proof per GPU x{world}, final all-gather of proofs",
@@ -361,7 +362,7 @@ def run_reference(args):
     value = total_proofs / total_wall
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done, "warmup": 0,
-        "ms_per_step": round(total_wall / steps_done * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (mcl)",
+        "ms_per_step": round(total_wall / steps_done * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": "vgg11 CIFAR pic_cnt=1" if model == "vgg11" else model, "network": config,
                    "note": f"each step = {procs} independent reference provers in parallel (one per host thread, memory-bounded); time = the reference's own prover "
