@@ -189,6 +189,8 @@ def run_ours(args):
             assert st["ok"] == 1
         if not args.no_prefetch:
             s.prove(2999, flags)              # adopts the pending copy: the timed region starts with nothing in flight
+        if dist is not None:
+            gather_proofs(s.proof(), device, dist)   # warm-up of the exchange step too (first-use set-up of the collective)
         barrier()
         t0 = time.perf_counter()
         h2d = d2h = 0
