@@ -244,17 +244,18 @@ __global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
         }
     }
     __syncthreads();
-    // sum_b b * B_b : every thread scales its bucket (8-bit double-and-add), then a tree sum
+    // sum_b b * B_b = sum_{k = 1..255} S_k with the suffix sums S_k = sum_{b >= k} B_b: a parallel suffix scan (8 steps of one
+    // addition per thread, ping-pong between `bucket` and `first`, which is free by now) and a tree sum of S_1..S_255 -- 16
+    // dependent point additions instead of the 8 doublings + up to 8 additions + 8 tree levels of scaling every bucket by b.
     {
-        g1_jac_t P = S->bucket[t];
-        g1_jac_t acc = g1_jac_t::inf();
-        if (t >= 1 && !P.is_inf()) {
-            for (int bit = 7; bit >= 0; --bit) {
-                acc = g1_dbl(acc);
-                if ((t >> bit) & 1u) acc = g1_add(acc, P);
-            }
+        g1_jac_t *in = S->bucket, *out = S->first;
+        for (uint32_t d = 1; d < (uint32_t) kMsmBuckets; d <<= 1) {
+            out[t] = t + d < (uint32_t) kMsmBuckets ? g1_add(in[t], in[t + d]) : in[t];
+            __syncthreads();
+            g1_jac_t *tmp = in; in = out; out = tmp;
         }
-        S->bucket[t] = acc;
+        // 8 steps: the result is back in S->bucket; bucket 0 is empty by construction and its suffix sum is not a term
+        if (t == 0) S->bucket[0] = g1_jac_t::inf();
     }
     __syncthreads();
     for (uint32_t s = kBlock / 2; s > 0; s >>= 1) {
