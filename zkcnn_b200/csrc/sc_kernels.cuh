@@ -376,9 +376,6 @@ __device__ __forceinline__ void round_quad_publish_pairs(const round_args_t &A, 
 // (linear_poly * linear_poly, src/polynomial.cpp:116-118, evaluated Karatsuba-style with 3 products).  The three sums
 // are accumulated unreduced (fr_lazy_t): the four fold multiplications per output pair are full Montgomery
 // multiplications (their results are stored), the three products only pay the multiplication half.
-#ifndef ZK_ROUND_CTAS_PER_SM
-#define ZK_ROUND_CTAS_PER_SM 4
-#endif
 __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_quad(round_args_t A) {
     ZK_PDL_ENTRY();
     __shared__ unsigned long long sh_warp[(kRoundBlock / 32) * kRoundLimbs];
@@ -402,12 +399,6 @@ __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_qua
         const fr_t r = A.r;
         for (uint32_t i = bx * kRoundBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
             const uint32_t base = i << 2;
-#if defined(ZK_ROUND_PREFETCH) && ZK_ON_DEVICE
-            if (i + stride < n_pairs) {   // next iteration's two 128-byte rows
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(v_in + base + 4 * stride));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(m_in + base + 4 * stride));
-            }
-#endif
             fr_t x0 = ld_fr_live(v_in, base, live), x1 = ld_fr_live(v_in, base + 1, live);
             fr_t x2 = ld_fr_live(v_in, base + 2, live), x3 = ld_fr_live(v_in, base + 3, live);
             fr_t y0 = ld_fr_live(m_in, base, live), y1 = ld_fr_live(m_in, base + 1, live);
@@ -532,6 +523,8 @@ __global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A)
 // spent on data in flight.  Completion is tracked by one mbarrier per (warp, stage) with a transaction count of 8 KB.
 // Row blocks that are not completely live (the last one of a table) take the guarded global-load path.
 // --------------------------------------------------------------------------------------------------------------------
+// (compile-time variants measured in round 1, all within 2 % of each other at 2^24 entries: one stage refilled as soon as the
+//  block is in registers with 4 or 5 CTAs per SM, the out-of-line multiplier; the arithmetic, not the feeding, sets the pace)
 #ifndef ZK_TMA_STAGES
 #define ZK_TMA_STAGES 2
 #endif
