@@ -63,6 +63,9 @@ int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_
  *   "tma_min_entries"  (131072) fold rounds on tables of at least this many entries use the TMA-staged k_round_quad_tma
  *   "derive_b"         (1)      streaming rounds take b from the previous round's polynomial (0: always three products)
  *   "pdl"              (1)      k_round_quad_thin is launched with programmatic stream serialization
+ *   "cubic_tma"        (1)      DOT_PROD fold rounds on tables of at least tma_min_entries use k_round_cubic_tma
+ *   "cubic_max_grid"   (none)   cap on the CTAs of a K2 launch (tests: several iterations per thread on small tables)
+ *   "cubic_factored_min_iters" (4) k_round_cubic switches to the factored form from this many output pairs per thread
  *   "msm_few_rows_chunk" (2048) entries per CTA of the bucket kernel for MSMs of at most 8 rows */
 int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value);
 
@@ -129,6 +132,9 @@ int zk_sumcheck_update2(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *
  * The reference's verifier draws all challenges of a phase before its first round (src/verifier.cpp:156-160,207,275-279),
  * which is what makes this call possible for its own driver loop; the per-round entry points above stay the drop-in API. */
 int zk_sumcheck_update_batch(zk_ctx *ctx, int which, const uint64_t *previous_randoms, uint32_t n_rounds, uint64_t *abc);
+/* The same for the DOT_PROD phase: every sumcheckDotProdUpdate1 round of the current layer in one call (the verifier draws
+ * r_u[i] before the first round for these layers too, src/verifier.cpp:156-160); abcd receives n_rounds x 4 Fr. */
+int zk_sumcheck_dotprod_update_batch(zk_ctx *ctx, const uint64_t *previous_randoms, uint32_t n_rounds, uint64_t *abcd);
 int zk_sumcheck_dotprod_finalize1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_1);      /* :146 */
 int zk_sumcheck_finalize1(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_0, uint64_t *claim_1); /* :459 */
 int zk_sumcheck_finalize2(zk_ctx *ctx, const uint64_t *previous_random, uint64_t *claim_0, uint64_t *claim_1); /* :473 */
@@ -160,6 +166,11 @@ int zk_phi_table(zk_ctx *ctx, const uint64_t *rx, const uint64_t *scale, uint32_
  * round j uses previous_random = (j == 0 ? 0 : r[j-1]).  polys gets 3 Fr per round.  Returns folded tables if non-NULL. */
 int zk_fold_rounds(zk_ctx *ctx, const uint64_t *V, const uint64_t *M, uint32_t bits, uint64_t live, const uint64_t *r,
                    uint32_t n_rounds, uint64_t *polys);
+/* Runs `n_rounds` rounds of sumcheckDotProdUpdate1 (src/prover.cpp:103-144) on stand-alone tables: mult has 2^m_bits entries
+ * (mult_array[1]), V0 / V1 have 2^bits entries of which the first live0 / live1 are non-zero (V_mult[0] / V_mult[1];
+ * live0 <= live1).  Round j uses previous_random = (j == 0 ? 0 : r[j-1]).  polys gets 4 Fr (a, b, c, d) per round. */
+int zk_cubic_rounds(zk_ctx *ctx, const uint64_t *mult, uint32_t m_bits, const uint64_t *V0, uint64_t live0, const uint64_t *V1, uint64_t live1, uint32_t bits,
+                    const uint64_t *r, uint32_t n_rounds, uint64_t *polys);
 /* out[k] = sum_j scalars[k*n + j] * bases[j]   (G1::mulVec semantics, mcl ec.hpp:1570-1597), k < n_rows */
 int zk_msm(zk_ctx *ctx, const uint64_t *bases, const uint64_t *scalars, uint64_t n, uint32_t n_rows, uint64_t *out);
 /* element-wise G1: op 0: out = a + b; 1: out = 2a; 2: out = k*a (k = b reinterpreted as Fr per element) */

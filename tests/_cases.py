@@ -97,6 +97,26 @@ def case_fold_rounds(lib, shapes=((1, 2), (2, 3), (3, 8), (5, 17), (7, 100), (10
                 assert [tuple(fr_from_words(got[j])) for j in range(bits)] == want, (bits, live, mix)
 
 
+def case_cubic_rounds(lib, shapes=((1, 0, 2, 2), (3, 1, 5, 8), (5, 2, 12, 29), (8, 3, 100, 250), (10, 4, 301, 1024), (11, 6, 700, 1500), (12, 12, 4096, 4096)),
+                      tunables=None):
+    """K2 against the reference-layout restatement of sumcheckDotProdUpdate1 (src/prover.cpp:103-144): (bits, m_bits, live0,
+    live1) -- V_mult[0] is zero from live0 on (rows without gates), both tables from live1 on; m_bits < bits makes the
+    multiplier periodic, then constant after m_bits + 1 rounds; m_bits == bits hits the last-round corner."""
+    rng = O.SplitMix64(414)
+    with Context(lib) as ctx:
+        for k, v in (tunables or {}).items():
+            ctx.set_tunable(k, v)
+        for bits, m_bits, live0, live1 in shapes:
+            mult = rand_fr(rng, 1 << m_bits)
+            V0 = rand_fr(rng, live0) + [0] * (live1 - live0)
+            V1 = rand_fr(rng, live1, "witness")
+            ch = rand_fr(rng, bits)
+            st = O.DotProdState(mult, V0, V1, bits, live1)
+            want = [O.sumcheck_dotprod_update1(st, 0 if j == 0 else ch[j - 1]) for j in range(bits)]
+            got = ctx.cubic_rounds(fr_to_words(mult), fr_to_words(V0[:live0]), fr_to_words(V1), bits, fr_to_words(ch), bits)
+            assert [tuple(fr_from_words(got[j])) for j in range(bits)] == want, (bits, m_bits, live0, live1)
+
+
 def case_g1_ops(lib, kat):
     g = kat["g1"]
     p, q, k = P(g["P"]), P(g["Q"]), H(g["k"])

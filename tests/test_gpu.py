@@ -51,6 +51,19 @@ def test_fold_rounds_every_kernel_variant(gpu_lib):
     cases.case_fold_rounds(gpu_lib, shapes=shapes, tunables={"thin_max_pairs": 0, "tma_min_entries": 128})
 
 
+def test_cubic_rounds_every_kernel_variant(gpu_lib):
+    # K2 (sumcheckDotProdUpdate1) against the port: default selection, factored / direct forms forced, TMA-staged from 128 entries on
+    cases.case_cubic_rounds(gpu_lib)
+    cases.case_cubic_rounds(gpu_lib, tunables={"cubic_factored_min_iters": 1, "cubic_tma": 0})
+    cases.case_cubic_rounds(gpu_lib, tunables={"cubic_factored_min_iters": 1 << 30, "cubic_tma": 0})
+    shapes = ((8, 3, 100, 250), (10, 4, 301, 1024), (11, 6, 700, 1500), (12, 12, 4096, 4096), (13, 5, 2048, 8192), (14, 7, 5000, 13000), (14, 2, 16384, 16384))
+    cases.case_cubic_rounds(gpu_lib, shapes=shapes, tunables={"tma_min_entries": 128})
+    # several iterations per thread / per warp: the grid stays a multiple of the multiplier period
+    multi = ((11, 10, 1500, 2048), (12, 9, 2500, 4000), (14, 12, 9000, 16000))
+    cases.case_cubic_rounds(gpu_lib, shapes=multi, tunables={"cubic_max_grid": 5, "cubic_tma": 0})
+    cases.case_cubic_rounds(gpu_lib, shapes=multi, tunables={"cubic_max_grid": 40, "tma_min_entries": 128})
+
+
 def test_g1_ops(gpu_lib, kat):
     cases.case_g1_ops(gpu_lib, kat)
 
@@ -137,6 +150,31 @@ def test_vgg11_full_size(gpu_host, tmp_path):
         st7 = s.prove(1, 0)
         for x in (st5, st6, st7):
             assert x["ok"] == 1 and x["fnv1a"] == st["fnv1a"] and x["h2d_bytes"] > 0
+
+
+@pytest.mark.parametrize("model,pics", [("vgg11", 2), ("vgg16", 2)])
+def test_fft_path_full_size(gpu_host, tmp_path, model, pics):
+    """BASELINE config 5 (the batched, FFT-convolution path: pic_cnt > 1 switches every convolution to
+    PADDING -> FFT -> DOT_PROD -> IFFT, src/models.cpp:12-41,43-96): K2 cubic rounds, K4b / K5b dense passes on tables of up to
+    2^26 entries.  Circuit dump (gates, ori_id, every layer's values) and transcript hash must equal what the compiled reference
+    produced for the same synthetic input and seed (tests/golden/*_p2_seed1.*, minted by oracle/harness/make_golden.sh --full)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_synthetic_input as gen
+    values = gen.generate(model)
+    name = f"{model}_syn_p{pics}_seed1"
+    with Session(gpu_host, "vgg", gen.CONFIGS[model], pics) as s:
+        s.input_values(values.astype(np.float64))
+        s.build()
+        dump = tmp_path / "c.txt"
+        s.circuit_dump(dump, True)
+        assert dump.read_text() == open(os.path.join(GOLDEN, name + ".circuit.txt")).read()
+        st = s.prove(1, 0)
+        ref = dict(zip(*[iter(open(os.path.join(GOLDEN, name + ".result.txt")).read().split()[1:])] * 2))
+        assert st["ok"] == 1 and st["proof_bytes"] == int(ref["bytes"]) and f"{st['fnv1a']:016x}" == ref["fnv"]
+        assert st["challenges"] == int(ref["challenges"])
+        # the reference's call pattern (one device round trip per round) and full verification give the same transcript
+        st2 = s.prove(1, WITNESS_RESIDENT | ROUND_BY_ROUND | CHECK_PREDICATES)
+        assert st2["ok"] == 1 and st2["fnv1a"] == st["fnv1a"]
 
 
 def test_fold_invariants_full_size(gpu_lib):

@@ -22,6 +22,17 @@ def test_fold_rounds(emu_lib):
     cases.case_fold_rounds(emu_lib)
 
 
+def test_cubic_rounds(emu_lib):
+    small = ((1, 0, 2, 2), (3, 1, 5, 8), (5, 2, 12, 29), (8, 3, 100, 250), (10, 4, 301, 1024))
+    cases.case_cubic_rounds(emu_lib, shapes=small)                                            # default selection
+    cases.case_cubic_rounds(emu_lib, shapes=small, tunables={"cubic_factored_min_iters": 1})         # factored form everywhere
+    cases.case_cubic_rounds(emu_lib, shapes=small, tunables={"cubic_factored_min_iters": 1 << 30})   # direct form everywhere
+    # several iterations per thread with a multiplier period of more than one CTA: the grid must stay a multiple of the period
+    multi = ((11, 10, 1500, 2048), (12, 9, 2500, 4000))
+    cases.case_cubic_rounds(emu_lib, shapes=multi, tunables={"cubic_max_grid": 5})
+    cases.case_cubic_rounds(emu_lib, shapes=multi, tunables={"cubic_max_grid": 3, "cubic_factored_min_iters": 1 << 30})
+
+
 def test_g1_ops(emu_lib, kat):
     cases.case_g1_ops(emu_lib, kat)
 

@@ -94,6 +94,7 @@ class Lib:
         d.zk_beta_table.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, _u64p]
         d.zk_phi_table.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint32, C.c_int, _u64p]
         d.zk_fold_rounds.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint32, C.c_uint64, _u64p, C.c_uint32, _u64p]
+        d.zk_cubic_rounds.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, C.c_uint64, _u64p, C.c_uint64, C.c_uint32, _u64p, C.c_uint32, _u64p]
         d.zk_msm.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint64, C.c_uint32, _u64p]
         d.zk_g1_vec_op.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint64]
         d.zk_g1_fixed_base_mul.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint64, _u64p]
@@ -184,6 +185,19 @@ class Context:
         self._check(self.lib.dll.zk_fold_rounds(self.h, _ptr(V), _ptr(M), bits, len(V), _ptr(r) if len(r) else None, n_rounds, _ptr(out)),
                     "zk_fold_rounds")
         return out.reshape(n_rounds, 3, 4)
+
+    def cubic_rounds(self, mult, V0, V1, bits, r, n_rounds):
+        """K2: n_rounds of sumcheckDotProdUpdate1 on stand-alone tables (len(mult) a power of two; len(V0) <= len(V1) <= 2^bits)"""
+        mult = np.ascontiguousarray(mult, dtype=np.uint64).reshape(-1, 4)
+        V0 = np.ascontiguousarray(V0, dtype=np.uint64).reshape(-1, 4)
+        V1 = np.ascontiguousarray(V1, dtype=np.uint64).reshape(-1, 4)
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(-1, 4)
+        m_bits = len(mult).bit_length() - 1
+        assert len(mult) == 1 << m_bits
+        out = np.empty((n_rounds * 4, 4), dtype=np.uint64)
+        self._check(self.lib.dll.zk_cubic_rounds(self.h, _ptr(mult), m_bits, _ptr(V0), len(V0), _ptr(V1), len(V1), bits, _ptr(r) if len(r) else None, n_rounds,
+                                                 _ptr(out)), "zk_cubic_rounds")
+        return out.reshape(n_rounds, 4, 4)
 
     def msm(self, bases, scalars, n_rows=1):
         bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 18)

@@ -59,6 +59,9 @@ int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
     else if (n == "tma_min_entries") ctx->tma_min_entries = value;
     else if (n == "derive_b") ctx->derive_b_enabled = value ? 1u : 0u;
     else if (n == "pdl") ctx->pdl_enabled = value ? 1u : 0u;
+    else if (n == "cubic_tma") ctx->cubic_tma_enabled = value ? 1u : 0u;
+    else if (n == "cubic_max_grid") ctx->cubic_max_grid = (uint32_t) std::max<uint64_t>(1, value);
+    else if (n == "cubic_factored_min_iters") ctx->cubic_factored_min_iters = (uint32_t) std::max<uint64_t>(1, value);
     else if (n == "msm_few_rows_chunk") ctx->msm_few_rows_chunk = (uint32_t) std::max<uint64_t>(256, std::min<uint64_t>(value, kMsmChunk));
     else ZK_REQUIRE(false, "unknown tunable");
     ZK_API_END
@@ -473,8 +476,12 @@ int zk_sumcheck_init_phase2(zk_ctx *ctx) {   // src/prover.cpp:241-310
         ZK_REQUIRE(P.exists && !ctx->pair[0].exists, "unexpected DOT_PROD shape");
         ZK_REQUIRE(((uint64_t) d.size_v[1] << fft_bl) <= prev.n_val, "DOT_PROD source layer too small");
         fr_t *V = table_init_buf(P.v, P.n_eval);
-        if (d.size_v[1])
-            ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, ((uint64_t) d.size_v[1] << fft_bl) * 32, k_dense_rowdot, dim3(d.size_v[1]), dim3(kBlock), 0, V, prev.val.as<fr_t>(), ctx->beta_gs.as<fr_t>(), fft_bl);
+        if (d.size_v[1]) {
+            const uint32_t lanes = std::max(1u, std::min(32u, (1u << fft_bl) / 8));   // lanes per row: eight terms each, up to a warp
+            const uint32_t groups = (d.size_v[1] + kBlock / lanes - 1) / (kBlock / lanes);
+            ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, ((uint64_t) d.size_v[1] << fft_bl) * 32 + (uint64_t) d.size_v[1] * 32, k_dense_rowdot, dim3(std::min<uint32_t>(groups, kMaxGridX)),
+                           dim3(kBlock), 0, V, prev.val.as<fr_t>(), ctx->beta_gs.as<fr_t>(), d.size_v[1], fft_bl, lanes);
+        }
         fr_t *M = table_init_buf(P.m, P.n_eval);
         rt::dzero(M, (size_t) P.n_eval * sizeof(fr_t), ctx->stream);
         A.out1 = M;
@@ -629,21 +636,114 @@ int zk_sumcheck_dotprod_init_phase1(zk_ctx *ctx) {   // src/prover.cpp:57-95
     ctx->mdp.next = 0;
     beta_point_t pts[1] = {{r0.data(), fr_t::one()}};
     build_beta(ctx, M, fft_bl, pts, 1);
-    // here pair[1].v plays V_mult[1] (activation FFT) and pair[1].m plays V_mult[0] (sum of beta_g * weight FFT)
+    // here pair[1].v plays V_mult[1] (activation FFT | weight FFT) and pair[1].m plays V_mult[0] (sum of beta_g * weight FFT).
+    // Only rows u that carry a gate are ever written by the reference's loop (src/prover.cpp:86-91): V_mult[0] is zero from
+    // row dp_rows_live on, which the round kernels use (cubic_args_t::live0).
     P.v.cur = prev.val.as<fr_t>();
     fr_t *V0 = table_init_buf(P.m, P.n_eval);
-    ZK_REQUIRE(L.dp_rows == (P.n_eval >> fft_bl), "DOT_PROD schedule missing");
-    ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) P.n_eval * 64, k_dotprod_axpy, dim3(grid_for(P.n_eval)), dim3(kBlock), 0, V0, prev.val.as<fr_t>(), ctx->beta_g.as<fr_t>(),
-               L.dp_rowptr.as<uint32_t>(), L.dp_gates.as<dp_gate_t>(), L.dp_rows, fft_bl);
+    ZK_REQUIRE(L.dp_rows == (P.n_eval >> fft_bl) && L.dp_rows_live <= L.dp_rows, "DOT_PROD schedule missing");
+    ctx->dp_live0 = std::min<uint32_t>(L.dp_rows_live << fft_bl, P.live);
+    const uint64_t n_out = (uint64_t) L.dp_rows_live << fft_bl;
+    if (n_out)
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, (uint64_t) d.n_bin * (32ull << fft_bl) + n_out * 32, k_dotprod_axpy, dim3(grid_for(n_out)), dim3(kBlock), 0, V0,
+                       prev.val.as<fr_t>(), ctx->beta_g.as<fr_t>(), L.dp_rowptr.as<uint32_t>(), L.dp_gates.as<dp_gate_t>(), L.dp_rows_live, fft_bl);
     ctx->round = 0;
     ZK_API_END
 }
+
+namespace zk {
+// One call of sumcheckDotProdUpdate1 (src/prover.cpp:103-144) queued on the stream.  slot_d == nullptr: interactive round, the
+// four coefficients go to the host mailbox (the caller waits); otherwise they are left at slot_d.  The host-side table state
+// follows from the sizes alone.
+static void cubic_round_launch(zk_ctx *ctx, const fr_t &prev, fr_t *slot_d) {
+    ensure_round_scratch(ctx);
+    if (!ctx->cubic_acc.p) {
+        ctx->cubic_acc.ensure(kCubicLimbs * sizeof(unsigned long long));
+        rt::dzero(ctx->cubic_acc.p, kCubicLimbs * sizeof(unsigned long long), ctx->stream);
+    }
+    const bool first = ctx->round == 1;
+    pair_t &P = ctx->pair[1];
+    ZK_REQUIRE(P.n_eval >= (first ? 2u : 4u), "DOT_PROD tables exhausted");
+    cubic_args_t A;
+    memset(&A, 0, sizeof A);
+    A.v1_in = P.v.cur; A.v0_in = P.m.cur;
+    A.n_in = P.n_eval; A.live1 = std::min(P.live, P.n_eval); A.live0 = std::min(ctx->dp_live0, A.live1); A.fold = first ? 0 : 1;
+    const uint32_t n_after = first ? P.n_eval : P.n_eval >> 1;
+    if (!first) {
+        A.v1_out = table_fold_buf(P.v, n_after);
+        A.v0_out = table_fold_buf(P.m, n_after);
+    }
+    A.m_in = ctx->mdp.cur;
+    A.m_n = ctx->mdp_n;
+    const bool m_fold = !first && ctx->mdp_n >= 2;   // the multiplier table is folded inside the round kernel (src/prover.cpp:112-118)
+    const uint32_t cur_n = m_fold ? ctx->mdp_n >> 1 : ctx->mdp_n;
+    if (m_fold) A.m_out = table_fold_buf(ctx->mdp, cur_n);
+    A.r = prev;
+    A.acc = ctx->cubic_acc.as<unsigned long long>();
+    A.counter = ctx->counters.as<uint32_t>() + 2;
+    if (slot_d) A.out = slot_d;
+    else { A.out = ctx->res_d; A.flag = ctx->flag_d; A.seq = ++ctx->seq; }
+
+    const uint32_t n_pairs = first ? P.n_eval >> 1 : P.n_eval >> 2;
+    const uint32_t P0 = std::min(n_pairs, first ? (A.live0 + 1) >> 1 : (A.live0 + 3) >> 2);
+    const uint32_t P1 = std::min(n_pairs, first ? (A.live1 + 1) >> 1 : (A.live1 + 3) >> 2);
+    const uint32_t period = cur_n >= 2 ? cur_n >> 1 : 1;              // output pairs per period of the multiplier
+    const uint32_t unit = std::max(1u, period / kRoundBlock);          // CTAs per period: a multi-iteration grid is a multiple of it
+    const uint64_t bytes = first ? (uint64_t) A.live0 * 64 : (uint64_t) A.live1 * 48 + (uint64_t) A.live0 * 48;
+    const int cls = bytes >= (32u << 20) ? ZK_PROF_FOLD : ZK_PROF_FOLD_SMALL;
+    auto pick_nb0 = [&](uint64_t want, uint64_t share) -> uint32_t {
+        if (want <= share) return (uint32_t) std::max<uint64_t>(1, want);   // at most one iteration per thread: any grid will do
+        return (uint32_t) std::max<uint64_t>(unit, share / unit * unit);
+    };
+#ifndef ZK_EMU
+    if (!first && P.n_eval >= ctx->tma_min_entries && ctx->cubic_tma_enabled) {
+        static const bool attr_set = [] {
+            rt::check(cudaFuncSetAttribute(k_round_cubic_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmemBytes), "cudaFuncSetAttribute");
+            return true;
+        }();
+        (void) attr_set;
+        cubic_tma_args_t T;
+        memset(&T, 0, sizeof T);
+        const uint32_t max_grid = std::min<uint32_t>(kTmaMaxGrid, ctx->cubic_max_grid);
+        const uint64_t G0 = (P0 + 31) >> 5, G1 = (P1 + 31) >> 5, it1 = (G1 - G0 + 1) >> 1;
+        const uint64_t w0 = G0 * 704, w1 = it1 * 512;                 // wide multiply-adds per warp iteration (4 folds + 3 products | 4 folds)
+        const uint64_t want0 = (G0 + kRoundBlock / 32 - 1) / (kRoundBlock / 32), want1 = (it1 + kRoundBlock / 32 - 1) / (kRoundBlock / 32);
+        A.nb0 = pick_nb0(want0, std::max<uint64_t>(1, (uint64_t) max_grid * w0 / std::max<uint64_t>(1, w0 + w1)));
+        A.nb1 = it1 ? (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(want1, max_grid > A.nb0 ? max_grid - A.nb0 : 1)) : 0;
+        encode_rows_map(&T.tm_v1, A.v1_in, A.n_in);
+        encode_rows_map(&T.tm_v0, A.v0_in, A.n_in);
+        T.C = A;
+        ZK_KLAUNCH_C(ctx, cls, bytes, k_round_cubic_tma, dim3(A.nb0 + A.nb1), dim3(kRoundBlock), kTmaSmemBytes, T);
+    } else
+#endif
+    {
+        const uint32_t max_grid = std::min<uint32_t>(ZK_SM_COUNT * 3, ctx->cubic_max_grid);   // three CTAs per SM resident
+        const uint64_t want0 = (P0 + kRoundBlock - 1) / kRoundBlock, want1 = first ? 0 : (P1 - P0 + kRoundBlock - 1) / kRoundBlock;
+        const uint64_t w0 = (uint64_t) P0 * (first ? 192 : 704), w1 = (uint64_t) (first ? 0 : P1 - P0) * 256;
+        A.nb0 = pick_nb0(want0, std::max<uint64_t>(1, (uint64_t) max_grid * w0 / std::max<uint64_t>(1, w0 + w1)));
+        A.nb1 = want1 ? (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(want1, max_grid > A.nb0 ? max_grid - A.nb0 : 1)) : 0;
+        const uint64_t iters = ((uint64_t) P0 + (uint64_t) A.nb0 * kRoundBlock - 1) / ((uint64_t) A.nb0 * kRoundBlock);
+        if (iters >= ctx->cubic_factored_min_iters) ZK_KLAUNCH_PDL(ctx, cls, bytes, k_round_cubic<true>, dim3(A.nb0 + A.nb1), dim3(kRoundBlock), 0, A);
+        else ZK_KLAUNCH_PDL(ctx, cls, bytes, k_round_cubic<false>, dim3(A.nb0 + A.nb1), dim3(kRoundBlock), 0, A);
+    }
+    if (m_fold) {
+        table_advance(ctx->mdp);
+        ctx->mdp_n = cur_n;
+    }
+    if (!first) {
+        table_advance(P.m);
+        table_advance(P.v);
+        P.n_eval >>= 1;
+        P.live = (P.live + 1) >> 1;
+        ctx->dp_live0 = (ctx->dp_live0 + 1) >> 1;
+    }
+}
+}  // namespace zk
 
 int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *abcd) {   // src/prover.cpp:103-144
     ZK_API_BEGIN
     cur_layer(ctx);
     rt::set_device(ctx->device);
-    ensure_round_scratch(ctx);
     const fr_t prev = fr_load(prev_p);
     std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
     if (ctx->round) {
@@ -651,44 +751,66 @@ int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *a
         ru[ctx->round - 1] = prev;
     }
     ++ctx->round;
-    const bool first = ctx->round == 1;
-    pair_t &P = ctx->pair[1];
-    ZK_REQUIRE(P.n_eval >= (first ? 2u : 4u), "DOT_PROD tables exhausted");
-    if (!first && ctx->mdp_n >= 2) {   // fold the multiplier table (src/prover.cpp:112-118)
-        const uint32_t n_out = ctx->mdp_n >> 1;
-        fr_t *out = table_fold_buf(ctx->mdp, n_out);
-        ZK_KLAUNCH_C(ctx, ZK_PROF_FOLD, (uint64_t) n_out * 96, k_fold_small, dim3(grid_for(n_out)), dim3(kBlock), 0, ctx->mdp.cur, out, n_out, prev);
-        table_advance(ctx->mdp);
-        ctx->mdp_n = n_out;
-    }
-    cubic_args_t A;
-    memset(&A, 0, sizeof A);
-    A.v0_in = P.m.cur; A.v1_in = P.v.cur;
-    A.n_in = P.n_eval; A.live = P.live; A.fold = first ? 0 : 1;
-    const uint32_t n_after = first ? P.n_eval : P.n_eval >> 1;
-    if (!first) {
-        A.v0_out = table_fold_buf(P.m, n_after);
-        A.v1_out = table_fold_buf(P.v, n_after);
-    }
-    A.m_in = ctx->mdp.cur;
-    A.m_n = ctx->mdp_n;
-    const uint32_t live_pairs = first ? (P.live + 1) >> 1 : (P.live + 3) >> 2;
-    A.n_blocks = grid_for(std::max(1u, live_pairs));
-    A.r = prev;
-    A.partials = ctx->partials.as<fr_t>();
-    A.counter = ctx->counters.as<uint32_t>() + 2;
-    A.out = ctx->res_d;
-    A.flag = ctx->flag_d;
-    A.seq = ++ctx->seq;
-    ZK_KLAUNCH_C(ctx, ZK_PROF_FOLD, (uint64_t) std::min(P.live, P.n_eval) * (first ? 64 : 96), k_round_cubic, dim3(A.n_blocks), dim3(kBlock), 0, A);
+    cubic_round_launch(ctx, prev, nullptr);
     wait_mailbox(ctx);
-    if (!first) {
-        table_advance(P.m);
-        table_advance(P.v);
-        P.n_eval >>= 1;
-        P.live = (P.live + 1) >> 1;
-    }
     for (int k = 0; k < 4; ++k) fr_store(abcd + 4 * k, ctx->res_h[k]);
+    ZK_API_END
+}
+
+// every round of the DOT_PROD phase in one call (see zk_sumcheck_update_batch): abcd receives n_rounds x 4 Fr
+int zk_sumcheck_dotprod_update_batch(zk_ctx *ctx, const uint64_t *prevs_p, uint32_t n_rounds, uint64_t *abcd) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && prevs_p && abcd && n_rounds >= 1, "bad arguments");
+    cur_layer(ctx);
+    rt::set_device(ctx->device);
+    std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
+    ZK_REQUIRE(ctx->round == 0 && n_rounds <= ru.size() + 1, "bad state");
+    ensure_round_scratch(ctx);
+    ctx->batch_res.ensure((size_t) n_rounds * 16 * sizeof(fr_t));
+    if (ctx->batch_cap < n_rounds) {
+        if (ctx->batch_h) rt::hfree_pinned(ctx->batch_h);
+        ctx->batch_h = static_cast<fr_t *>(rt::hmalloc_pinned((size_t) n_rounds * 16 * sizeof(fr_t)));
+        ctx->batch_cap = n_rounds;
+    }
+    for (uint32_t j = 0; j < n_rounds; ++j) {
+        const fr_t prev = fr_load(prevs_p + 4 * j);
+        if (j) ru[j - 1] = prev;
+        ++ctx->round;
+        cubic_round_launch(ctx, prev, ctx->batch_res.as<fr_t>() + (size_t) j * 16);
+    }
+    rt::d2h(ctx->batch_h, ctx->batch_res.p, (size_t) n_rounds * 16 * sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    for (uint32_t j = 0; j < n_rounds; ++j)
+        for (int k = 0; k < 4; ++k) fr_store(abcd + 16 * (size_t) j + 4 * k, ctx->batch_h[(size_t) j * 16 + k]);
+    ZK_API_END
+}
+
+int zk_cubic_rounds(zk_ctx *ctx, const uint64_t *mult, uint32_t m_bits, const uint64_t *V0, uint64_t live0, const uint64_t *V1, uint64_t live1, uint32_t bits,
+                    const uint64_t *r, uint32_t n_rounds, uint64_t *polys) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && mult && V0 && V1 && polys && bits >= 1 && bits <= 28 && m_bits <= 12 && m_bits <= bits && n_rounds >= 1 && n_rounds <= bits &&
+                   live0 <= live1 && live1 <= (1ull << bits) && live1 >= 1 && (r || n_rounds == 1), "bad arguments");
+    rt::set_device(ctx->device);
+    pair_t &P = ctx->pair[1];
+    pair_reset(ctx->pair[0], -1, 0);
+    pair_reset(P, (int8_t) bits, (uint32_t) live1);
+    fr_t *dv1 = table_init_buf(P.v, 1ull << bits), *dv0 = table_init_buf(P.m, 1ull << bits);
+    rt::h2d(dv1, V1, live1 * 32, ctx->stream);
+    rt::h2d(dv0, V0, live0 * 32, ctx->stream);
+    ctx->mdp_n = 1u << m_bits;
+    fr_t *dm = table_init_buf(ctx->mdp, ctx->mdp_n);
+    ctx->mdp.next = 0;
+    rt::h2d(dm, mult, (size_t) ctx->mdp_n * 32, ctx->stream);
+    ctx->dp_live0 = (uint32_t) live0;
+    ctx->round = 0;
+    for (uint32_t j = 0; j < n_rounds; ++j) {
+        const fr_t prev = j == 0 ? fr_t::zero() : fr_load(r + 4 * (j - 1));
+        ++ctx->round;
+        cubic_round_launch(ctx, prev, nullptr);
+        wait_mailbox(ctx);
+        for (int k = 0; k < 4; ++k) fr_store(polys + (size_t) (4 * j + k) * 4, ctx->res_h[k]);
+    }
+    P.n_eval = 0;
     ZK_API_END
 }
 

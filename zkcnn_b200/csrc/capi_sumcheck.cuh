@@ -229,10 +229,13 @@ static void build_layer_schedules(zk_ctx *ctx, uint32_t id, const zk_layer_desc 
         const uint32_t fft_bl = D->fft_bit_length;
         const uint32_t n_rows = rows_u1 >> fft_bl;
         std::vector<uint32_t> ptr(n_rows + 1, 0);
+        uint32_t rows_live = 0;
         for (uint64_t i = 0; i < D->n_bin; ++i) {
             ZK_REQUIRE(D->bin_gates[i].u < n_rows, "DOT_PROD gate.u out of range");
             ++ptr[D->bin_gates[i].u + 1];
+            rows_live = std::max(rows_live, D->bin_gates[i].u + 1);
         }
+        L.dp_rows_live = rows_live;
         for (uint32_t i = 0; i < n_rows; ++i) ptr[i + 1] += ptr[i];
         std::vector<dp_gate_t> g(D->n_bin);
         std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);

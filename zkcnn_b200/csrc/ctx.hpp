@@ -4,6 +4,7 @@
 #include "g1.cuh"
 #include "rt.hpp"
 #include "sc_kernels.cuh"
+#include "cubic_kernels.cuh"
 #include <memory>
 #include <vector>
 
@@ -30,6 +31,7 @@ struct layer_t {
     schedule_t p1, p2;
     rt::dbuf dp_rowptr, dp_gates;  // DOT_PROD phase 1: CSR by u
     uint32_t dp_rows = 0;
+    uint32_t dp_rows_live = 0;     // rows u < dp_rows_live carry gates: V_mult[0] of the DOT_PROD phase is zero beyond them
     rt::dbuf val;              // prover::val[layer]
     uint64_t n_val = 0;
     rt::dbuf val_next;         // shadow copy filled by zk_witness_layer_prefetch (the next proof's witness)
@@ -104,11 +106,12 @@ struct zk_ctx {
     zk::pair_t pair[2];
     zk::table_t mdp;            // DOT_PROD multiplier table (mult_array[1] of size 2^fft_bl)
     uint32_t mdp_n = 0;
+    uint32_t dp_live0 = 0;      // live entries of V_mult[0] in the DOT_PROD phase (cubic_args_t::live0)
     zk::rt::dbuf beta_g, beta_g_alt, beta_gs, beta_u;
     uint32_t beta_g_entries = 0;
 
     // scratch
-    zk::rt::dbuf half[4], d_r, partials, counters, round_acc, round_state, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
+    zk::rt::dbuf half[4], d_r, partials, counters, round_acc, cubic_acc, round_state, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
     zk::fr_t *h_out = nullptr;  // pinned mirror of round_out
     // result mailbox of the per-round kernels: mapped pinned host memory the last CTA writes directly, followed by a
     // sequence number; the host spins on the sequence number instead of copying + synchronising the stream
@@ -124,6 +127,9 @@ struct zk_ctx {
     uint64_t tma_min_entries = 1ull << 17;
     uint32_t pdl_enabled = 1;                // k_round_quad_thin launched with programmatic stream serialization
     uint32_t derive_b_enabled = 1;           // streaming rounds: b from the previous round's polynomial (0: always three products)
+    uint32_t cubic_tma_enabled = 1;          // DOT_PROD fold rounds on large tables use k_round_cubic_tma
+    uint32_t cubic_max_grid = 1u << 20;       // cap on the CTAs of a K2 launch (tests: forces several iterations per thread on small tables)
+    uint32_t cubic_factored_min_iters = 4;   // k_round_cubic: factored form from this many output pairs per thread
     uint32_t msm_few_rows_chunk = 2048;      // entries per CTA of k_msm_window when an MSM has at most 8 rows
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 

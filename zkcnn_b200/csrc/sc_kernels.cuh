@@ -5,14 +5,14 @@
 // the device are the same field elements (field arithmetic is exact, so summation order does not matter).
 //
 //   K1  k_round_quad      prover::sumcheckUpdateEach        src/prover.cpp:396-426
-//   K2  k_round_cubic     prover::sumcheckDotProdUpdate1    src/prover.cpp:103-144
+//   K2  k_round_cubic / k_round_cubic_tma   prover::sumcheckDotProdUpdate1   src/prover.cpp:103-144   (cubic_kernels.cuh)
 //   K3  k_half_tables / k_beta_expand   initBetaTable + initHalfTable   src/utils.cpp:32-51,147-180
 //   K3b k_phi_table       phiGInit                          src/utils.cpp:61-103
 //   K4/K5 k_gate_items_p1 / k_gate_items_p2 / k_sum_partials   gate loops of sumcheckInitPhase1/2
 //                                                           src/prover.cpp:224-233,286-288,297-305
-//   K4b k_dense_colsum    FFT/IFFT dense contraction        src/prover.cpp:190-197
-//   K5b k_dotprod_axpy    sumcheckDotProdInitPhase1         src/prover.cpp:86-91
-//   K5  k_dense_rowdot    DOT_PROD phase-2 V table          src/prover.cpp:277-284
+//   K4b k_dense_colsum    FFT/IFFT dense contraction        src/prover.cpp:190-197   (cubic_kernels.cuh)
+//   K5b k_dotprod_axpy    sumcheckDotProdInitPhase1         src/prover.cpp:86-91     (cubic_kernels.cuh)
+//   K5  k_dense_rowdot    DOT_PROD phase-2 V table          src/prover.cpp:277-284   (cubic_kernels.cuh)
 //   K6  k_liu_scatter     sumcheckLiuInit                   src/prover.cpp:334-353
 #pragma once
 #include "mont.cuh"
@@ -759,108 +759,6 @@ __global__ void k_final_fold(final_fold_args_t A) {
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// K2: cubic round of the FFT-convolution (DOT_PROD) layer: sum_i mult[i mod P](x) * V1[i](x) * V0[i](x)
-// The multiplier table is periodic in i (frequency index in the low fft_bl bits, src/prover.cpp:134-135).
-// --------------------------------------------------------------------------------------------------------------------
-struct cubic_args_t {
-    const fr_t *v0_in, *v1_in;  // big tables, n_in evaluations, entries >= live are zero
-    fr_t *v0_out, *v1_out;
-    const fr_t *m_in;           // multiplier table, m_n evaluations (already folded for this round by k_fold_small)
-    uint32_t n_in, live, fold;
-    uint32_t m_n;               // >= 2: pairs (m[2j], m[2j+1]) periodic with period m_n/2;  1: constant m[0]
-    uint32_t n_blocks;
-    fr_t r;
-    fr_t *partials;             // [kMaxGridX][4]
-    uint32_t *counter;
-    fr_t *out;                  // (a, b, c, d)
-    uint32_t *flag;             // see round_args_t
-    uint32_t seq;
-};
-__global__ void __launch_bounds__(kBlock) k_round_cubic(cubic_args_t A) {
-    __shared__ fr_t sh[4 * kBlock];
-    __shared__ uint32_t ticket;
-    const uint32_t stride = A.n_blocks * kBlock;
-    fr_t acc[4] = {fr_t::zero(), fr_t::zero(), fr_t::zero(), fr_t::zero()};
-    const uint32_t n_pairs = A.fold ? A.n_in >> 2 : A.n_in >> 1;
-    const uint32_t live_pairs = A.fold ? (A.live + 3) >> 2 : (A.live + 1) >> 1;
-    const uint32_t m_pairs = A.m_n >> 1;
-    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_pairs && i < live_pairs; i += stride) {
-        fr_t p0, p1, q0, q1;
-        if (A.fold) {
-            const uint32_t base = i << 2;
-            fr_t x0 = ld_fr_live(A.v0_in, base, A.live), x1 = ld_fr_live(A.v0_in, base + 1, A.live);
-            fr_t x2 = ld_fr_live(A.v0_in, base + 2, A.live), x3 = ld_fr_live(A.v0_in, base + 3, A.live);
-            p0 = x0 + A.r * (x1 - x0);
-            p1 = x2 + A.r * (x3 - x2);
-            st_fr(A.v0_out + 2 * i, p0);
-            st_fr(A.v0_out + 2 * i + 1, p1);
-            x0 = ld_fr_live(A.v1_in, base, A.live); x1 = ld_fr_live(A.v1_in, base + 1, A.live);
-            x2 = ld_fr_live(A.v1_in, base + 2, A.live); x3 = ld_fr_live(A.v1_in, base + 3, A.live);
-            q0 = x0 + A.r * (x1 - x0);
-            q1 = x2 + A.r * (x3 - x2);
-            st_fr(A.v1_out + 2 * i, q0);
-            st_fr(A.v1_out + 2 * i + 1, q1);
-        } else {
-            p0 = ld_fr_live(A.v0_in, 2 * i, A.live); p1 = ld_fr_live(A.v0_in, 2 * i + 1, A.live);
-            q0 = ld_fr_live(A.v1_in, 2 * i, A.live); q1 = ld_fr_live(A.v1_in, 2 * i + 1, A.live);
-        }
-        // quadratic  V1(x) V0(x) = qa x^2 + qb x + qc
-        fr_t dp = p1 - p0, dq = q1 - q0;
-        fr_t qa = dp * dq, qc = p0 * q0;
-        fr_t qb = p1 * q1 - qa - qc;
-        if (m_pairs) {
-            const uint32_t j = i & (m_pairs - 1);
-            fr_t m0 = ld_fr(A.m_in + 2 * j), m1 = ld_fr(A.m_in + 2 * j + 1);
-            fr_t dm = m1 - m0;
-            acc[0] = acc[0] + dm * qa;
-            acc[1] = acc[1] + dm * qb + m0 * qa;
-            acc[2] = acc[2] + dm * qc + m0 * qb;
-            acc[3] = acc[3] + m0 * qc;
-        } else {  // constant multiplier: scale once at the end
-            acc[1] = acc[1] + qa;
-            acc[2] = acc[2] + qb;
-            acc[3] = acc[3] + qc;
-        }
-    }
-    block_sum<4>(acc, sh);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) st_fr(A.partials + blockIdx.x * 4 + k, acc[k]);
-        __threadfence();
-        ticket = atomicAdd(A.counter, 1u);
-    }
-    __syncthreads();
-    if (ticket != A.n_blocks - 1) return;
-    __threadfence();
-    fr_t tot[4] = {fr_t::zero(), fr_t::zero(), fr_t::zero(), fr_t::zero()};
-    for (uint32_t i = threadIdx.x; i < A.n_blocks; i += kBlock) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) tot[k] = tot[k] + ld_fr_cg(A.partials + i * 4 + k);
-    }
-    __syncthreads();
-    block_sum<4>(tot, sh);
-    if (threadIdx.x == 0) {
-        if (!m_pairs) {
-            fr_t m0 = ld_fr(A.m_in);
-#pragma unroll
-            for (int k = 1; k < 4; ++k) tot[k] = tot[k] * m0;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) st_fr(A.out + k, tot[k]);
-        *A.counter = 0;
-        if (A.flag) publish(A.flag, A.seq);
-    }
-}
-
-// in-order fold of a small table: out[i] = in[2i] + r (in[2i+1] - in[2i]),  i < n_out
-__global__ void __launch_bounds__(kBlock) k_fold_small(const fr_t *in, fr_t *out, uint32_t n_out, fr_t r) {
-    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n_out; i += gridDim.x * kBlock) {
-        fr_t x0 = ld_fr(in + 2 * i), x1 = ld_fr(in + 2 * i + 1);
-        st_fr(out + i, x0 + r * (x1 - x0));
-    }
-}
-
-// --------------------------------------------------------------------------------------------------------------------
 // K3: eq / beta tables.  initHalfTable (src/utils.cpp:32-51): f[0] = init, then for every variable i the table doubles:
 // f[j | 2^i] = f[j] r_i, f[j] -= f[j] r_i.  One CTA per half table; both halves (and both points of the 6-argument
 // overload) are built by one launch.
@@ -1063,59 +961,6 @@ __global__ void __launch_bounds__(kBlock) k_sum_partials(gate_args_t A, const fr
 __global__ void __launch_bounds__(kBlock) k_gather(fr_t *out, const fr_t *val0, const uint32_t *ori, uint32_t n) {
     ZK_PDL_ENTRY();
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr(out + i, ld_fr(val0 + ori[i]));
-}
-
-// --------------------------------------------------------------------------------------------------------------------
-// K4b: FFT/IFFT layers: V[u] = sum_g val[(g << shift) | u] * beta_g[g],  u < n_u  (src/prover.cpp:190-197).
-// grid = (u blocks, g chunks); partial[chunk][u], finished by k_colsum_finish.
-// --------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_dense_colsum(const fr_t *val, const fr_t *beta_g, uint32_t n_u, uint32_t shift,
-                                                         uint32_t cnt_len, uint32_t g_per_chunk, fr_t *partial) {
-    const uint32_t u = blockIdx.x * kBlock + threadIdx.x;
-    if (u >= n_u) return;
-    const uint32_t g0 = blockIdx.y * g_per_chunk;
-    const uint32_t g1 = g0 + g_per_chunk < cnt_len ? g0 + g_per_chunk : cnt_len;
-    fr_t acc = fr_t::zero();
-    for (uint32_t g = g0; g < g1; ++g) acc = acc + ld_fr(val + (((size_t) g << shift) | u)) * ld_fr(beta_g + g);
-    st_fr(partial + (size_t) blockIdx.y * n_u + u, acc);
-}
-__global__ void __launch_bounds__(kBlock) k_colsum_finish(const fr_t *partial, uint32_t n_u, uint32_t n_chunks, fr_t *out) {
-    const uint32_t u = blockIdx.x * kBlock + threadIdx.x;
-    if (u >= n_u) return;
-    fr_t acc = fr_t::zero();
-    for (uint32_t c = 0; c < n_chunks; ++c) acc = acc + ld_fr(partial + (size_t) c * n_u + u);
-    st_fr(out + u, acc);
-}
-
-// --------------------------------------------------------------------------------------------------------------------
-// K5b: DOT_PROD phase 1:  V0[(u << fft_bl) | t] = sum_{gates with that u} beta_g[g] * val[(v << fft_bl) | t]
-// (src/prover.cpp:86-91).  CSR by u built at upload; one thread per (u, t), coalesced over t.
-// --------------------------------------------------------------------------------------------------------------------
-struct dp_gate_t { uint32_t g, v; };
-__global__ void __launch_bounds__(kBlock) k_dotprod_axpy(fr_t *out, const fr_t *val, const fr_t *beta_g, const uint32_t *row_ptr,
-                                                         const dp_gate_t *gates, uint32_t n_rows, uint32_t fft_bl) {
-    const uint32_t fft_len = 1u << fft_bl;
-    const size_t total = (size_t) n_rows << fft_bl;
-    for (size_t idx = (size_t) blockIdx.x * kBlock + threadIdx.x; idx < total; idx += (size_t) gridDim.x * kBlock) {
-        const uint32_t u = (uint32_t) (idx >> fft_bl), t = (uint32_t) idx & (fft_len - 1);
-        fr_t acc = fr_t::zero();
-        for (uint32_t k = row_ptr[u]; k < row_ptr[u + 1]; ++k) {
-            const dp_gate_t G = gates[k];
-            acc = acc + ld_fr(beta_g + G.g) * ld_fr(val + (((size_t) G.v << fft_bl) | t));
-        }
-        st_fr(out + idx, acc);
-    }
-}
-
-// K5 (DOT_PROD phase 2): V[v] = sum_t val[(v << fft_bl) | t] * beta_gs[t]  (src/prover.cpp:277-284); one CTA per row v
-__global__ void __launch_bounds__(kBlock) k_dense_rowdot(fr_t *out, const fr_t *val, const fr_t *beta_gs, uint32_t fft_bl) {
-    __shared__ fr_t sh[kBlock];
-    const uint32_t v = blockIdx.x, fft_len = 1u << fft_bl;
-    fr_t acc[1] = {fr_t::zero()};
-    for (uint32_t t = threadIdx.x; t < fft_len; t += kBlock)
-        acc[0] = acc[0] + ld_fr(val + (((size_t) v << fft_bl) | t)) * ld_fr(beta_gs + t);
-    block_sum<1>(acc, sh);
-    if (threadIdx.x == 0) st_fr(out + v, acc[0]);
 }
 
 // --------------------------------------------------------------------------------------------------------------------

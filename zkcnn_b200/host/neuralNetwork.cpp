@@ -2,6 +2,7 @@
 // src/neuralNetwork.cpp of the reference (cited per function), because the order in which input-layer operands are first
 // used fixes the table layout of every sumcheck (layeredCircuit::initSubset) and therefore the proof transcript.
 #include "neuralNetwork.hpp"
+#include <functional>
 #include <thread>
 
 using std::vector;
@@ -761,38 +762,104 @@ void neuralNetwork::calcNormalLayer(const layer &circuit, i64 layer_id) {
         for (auto &x : out) x = x * circuit.scale;
 }
 
+// run body(first, last) over [0, n) on the host threads (blocks of a layer are independent)
+static void parallelBlocks(size_t n, int hostThreads, const std::function<void(size_t, size_t)> &body) {
+    unsigned nt = hostThreads > 0 ? (unsigned) hostThreads : std::max(1u, std::thread::hardware_concurrency());
+    nt = (unsigned) std::min<size_t>(std::min(nt, 64u), std::max<size_t>(1, n));
+    if (nt == 1) { body(0, n); return; }
+    vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t] { body(n * t / nt, n * (t + 1) / nt); });
+    for (auto &t : th) t.join();
+}
+
+// out[g block] += src[u block] .* src[v block] (:934-944); gates are grouped by output block so that threads never share one
 void neuralNetwork::calcDotProdLayer(const layer &circuit, i64 layer_id) {
     vector<F> &out = val[layer_id];
     out.assign(circuit.size, F());
     const int fft_bit = circuit.fft_bit_length;
     const u32 fft_len = 1u << fft_bit;
     const vector<F> &src = val[layer_id - 1];
-    for (const auto &g : circuit.bin_gates)
-        for (u32 s = 0; s < fft_len; ++s)
-            out[(size_t) g.g << fft_bit | s] += src[(size_t) g.u << fft_bit | s] * src[(size_t) g.v << fft_bit | s];
+    const size_t n_out = circuit.size >> fft_bit;
+    vector<u32> first(n_out + 1, 0), order(circuit.bin_gates.size());
+    for (const auto &g : circuit.bin_gates) ++first.at(g.g + 1);
+    for (size_t i = 0; i < n_out; ++i) first[i + 1] += first[i];
+    {
+        vector<u32> fill(first.begin(), first.end() - 1);
+        for (u32 i = 0; i < circuit.bin_gates.size(); ++i) order[fill[circuit.bin_gates[i].g]++] = i;
+    }
+    parallelBlocks(n_out, hostThreads, [&](size_t b, size_t e) {
+        for (size_t o = b; o < e; ++o)
+            for (u32 k = first[o]; k < first[o + 1]; ++k) {
+                const binGate &g = circuit.bin_gates[order[k]];
+                const F *x = &src.at(((size_t) g.u << fft_bit) + fft_len - 1) - (fft_len - 1), *y = &src.at(((size_t) g.v << fft_bit) + fft_len - 1) - (fft_len - 1);
+                F *d = &out[o << fft_bit];
+                for (u32 s = 0; s < fft_len; ++s) d[s] += x[s] * y[s];
+            }
+    });
 }
 
-void neuralNetwork::calcFFTLayer(const layer &circuit, i64 layer_id) {
+// radix-2 NTT of one block with shared bit-reversal and twiddle tables (the transform of fft() above, src/utils.cpp:105-145)
+struct NttPlan {
+    int logn;
+    bool inverse;
+    vector<u32> rev;
+    vector<F> w;
+    F ilen;
+    NttPlan(int logn_, bool inv) : logn(logn_), inverse(inv), rev(1u << logn_), w(1u << logn_) {
+        const u32 len = 1u << logn;
+        rev[0] = 0;
+        for (u32 i = 1; i < len; ++i) rev[i] = rev[i >> 1] >> 1 | (i & 1) << (logn - 1);
+        w[0] = F_ONE;
+        if (len > 1) {
+            w[1] = getRootOfUnit(logn);
+            if (inverse) F::inv(w[1], w[1]);
+            for (u32 i = 2; i < len; ++i) w[i] = w[i - 1] * w[1];
+        }
+        F::inv(ilen, F((u64) len));
+    }
+    void run(F *arr) const {
+        const u32 len = 1u << logn;
+        for (u32 i = 0; i < len; ++i)
+            if (rev[i] < i) std::swap(arr[i], arr[rev[i]]);
+        for (u32 span = 2; span <= len; span <<= 1) {
+            const u32 half = span >> 1, step = len / span;
+            for (u32 j = 0; j < len; j += span)
+                for (u32 k = 0; k < half; ++k) {
+                    const F u = arr[j + k], v = arr[j + k + half] * w[step * k];
+                    arr[j + k] = u + v;
+                    arr[j + k + half] = u - v;
+                }
+        }
+        if (inverse)
+            for (u32 i = 0; i < len; ++i) arr[i] = arr[i] * ilen;
+    }
+};
+
+void neuralNetwork::calcFFTLayer(const layer &circuit, i64 layer_id) {   // :946-965
     const i64 fft_len = 1LL << circuit.fft_bit_length, fft_lenh = fft_len >> 1;
     const bool inverse = circuit.ty == layerType::IFFT;
     vector<F> &out = val[layer_id];
     const vector<F> &src = val[layer_id - 1];
     out.assign(circuit.size, F());
-    vector<F> arr(fft_len);
-    if (!inverse) {   // half-length blocks, zero-extended, forward transform
-        for (i64 c = 0, d = 0; d < (i64) circuit.size; c += fft_lenh, d += fft_len) {
-            for (i64 j = 0; j < fft_lenh; ++j) arr[j] = src.at(c + j);
-            for (i64 j = fft_lenh; j < fft_len; ++j) arr[j].clear();
-            fft(arr, circuit.fft_bit_length, false);
-            for (i64 j = 0; j < fft_len; ++j) out.at(d + j) = arr[j];
+    const NttPlan plan(circuit.fft_bit_length, inverse);
+    const size_t n_blocks = inverse ? (circuit.size + fft_lenh - 1) / fft_lenh : (circuit.size + fft_len - 1) / fft_len;
+    if ((inverse ? n_blocks * fft_len : n_blocks * fft_lenh) > src.size() || (inverse ? n_blocks * fft_lenh : n_blocks * fft_len) > out.size())
+        throw std::out_of_range("calcFFTLayer: layer sizes are not whole FFT blocks");
+    parallelBlocks(n_blocks, hostThreads, [&](size_t b, size_t e) {
+        vector<F> arr(fft_len);
+        for (size_t k = b; k < e; ++k) {
+            if (!inverse) {   // half-length block, zero-extended, forward transform
+                for (i64 j = 0; j < fft_lenh; ++j) arr[j] = src[k * fft_lenh + j];
+                for (i64 j = fft_lenh; j < fft_len; ++j) arr[j].clear();
+                plan.run(arr.data());
+                for (i64 j = 0; j < fft_len; ++j) out[k * fft_len + j] = arr[j];
+            } else {          // full block, inverse transform, keep the first half
+                for (i64 j = 0; j < fft_len; ++j) arr[j] = src[k * fft_len + j];
+                plan.run(arr.data());
+                for (i64 j = 0; j < fft_lenh; ++j) out[k * fft_lenh + j] = arr[j];
+            }
         }
-    } else {          // full blocks, inverse transform, keep the first half
-        for (i64 c = 0, d = 0; c < (i64) circuit.size; c += fft_lenh, d += fft_len) {
-            for (i64 j = 0; j < fft_len; ++j) arr[j] = src.at(d + j);
-            fft(arr, circuit.fft_bit_length, true);
-            for (i64 j = 0; j < fft_lenh; ++j) out.at(c + j) = arr[j];
-        }
-    }
+    });
 }
 
 int neuralNetwork::getNextBit(int layer_id) {   // :967-977

@@ -335,6 +335,24 @@ vector<quadratic_poly> prover::sumcheckUpdateAll(int which, const vector<F> &r, 
     return polys;
 }
 
+vector<cubic_poly> prover::sumcheckDotProdUpdateAll(const vector<F> &r, int n_rounds) {
+    vector<cubic_poly> polys;
+    if (n_rounds <= 0) return polys;
+    prove_timer.start();
+    vector<F> prevs(n_rounds), c((size_t) 4 * n_rounds);
+    prevs[0].clear();
+    for (int j = 1; j < n_rounds; ++j) prevs[j] = r[j - 1];
+    check(zk_sumcheck_dotprod_update_batch(ctx_, w(prevs[0]), (uint32_t) n_rounds, w(c[0])), "zk_sumcheck_dotprod_update_batch");
+    prove_timer.stop();
+    polys.reserve(n_rounds);
+    for (int j = 0; j < n_rounds; ++j) {
+        proof_size += ZK_F_BYTES * (3 + (!c[4 * j].isZero()));   // src/prover.cpp:137
+        if (transcript_) for (int k = 0; k < 4; ++k) transcript_->put_fr(w(c[4 * j + k]));
+        polys.emplace_back(c[4 * j], c[4 * j + 1], c[4 * j + 2], c[4 * j + 3]);
+    }
+    return polys;
+}
+
 hyrax_bls12_381::polyProver &prover::commitInput(const vector<G> &gens) {   // src/prover.cpp:503-511
     // pad val[0] with zeros to 2^bit_length (src/prover.cpp:504-508); once: the padding stays zero between proofs, and clearing
     // 3.9 M elements of page-locked memory again would cost ~10 ms per vgg11 proof

@@ -65,6 +65,8 @@ public:
     // for sumcheckUpdate1 / sumcheckUpdate2 / sumcheckLiuUpdate; r holds the phase's challenges, drawn by the verifier before
     // the first round (src/verifier.cpp:156-160,207,275-279); round j is folded with r[j - 1].  Returns the n_rounds messages.
     vector<quadratic_poly> sumcheckUpdateAll(int which, const vector<F> &r, int n_rounds);
+    // the same for the cubic rounds of a DOT_PROD layer (sumcheckDotProdUpdate1, zk_sumcheck_dotprod_update_batch)
+    vector<cubic_poly> sumcheckDotProdUpdateAll(const vector<F> &r, int n_rounds);
 
     hyrax_bls12_381::polyProver &commitInput(const vector<G> &gens);
 

@@ -323,11 +323,13 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
 
         F prev = F_ZERO;
         vector<quadratic_poly> all;
+        vector<cubic_poly> all_dot;
         if (batchRounds && !dot) all = p->sumcheckUpdateAll(1, r_u[i], cur.max_bl_u);
+        if (batchRounds && dot) all_dot = p->sumcheckDotProdUpdateAll(r_u[i], cur.max_bl_u);
         for (int j = 0; j < cur.max_bl_u; ++j) {
             F at0p1, atr;
             if (dot) {
-                cubic_poly poly = p->sumcheckDotProdUpdate1(prev);
+                cubic_poly poly = batchRounds ? all_dot[j] : p->sumcheckDotProdUpdate1(prev);
                 at0p1 = poly.d + poly.eval(F_ONE);
                 atr = poly.eval(r_u[i][j]);
             } else {
