@@ -111,7 +111,7 @@ def run_ours(args):
     import torch
     import gen_synthetic_input as gen
     import zkcnn_b200
-    from zkcnn_b200 import PROF_CLASSES, REAL_GENERATORS, WITNESS_RESIDENT, CHECK_PREDICATES, ROUND_BY_ROUND, PREFETCH_NEXT, NO_HASH
+    from zkcnn_b200 import PROF_CLASSES, REAL_GENERATORS, WITNESS_RESIDENT, CHECKED_ALL, PROVER_ONLY, ROUND_BY_ROUND, PREFETCH_NEXT, NO_HASH
     import ctypes as C
 
     rank, world, local = dist_env()
@@ -139,10 +139,10 @@ def run_ours(args):
     s.build()
     build_s = time.perf_counter() - t0
     # NO_HASH: the FNV-1a of the transcript is a statistic of zkh_prove, not part of the proof (the proof bytes are produced and read back)
-    flags = REAL_GENERATORS | NO_HASH | (ROUND_BY_ROUND if args.round_by_round else 0)
+    flags = REAL_GENERATORS | NO_HASH | PROVER_ONLY | (ROUND_BY_ROUND if args.round_by_round else 0)
     # one fully verified proof with the reference's own (degenerate) generator set: full-size parity inside the bench
-    st0 = s.prove(1, CHECK_PREDICATES)
-    assert st0["ok"] == 1, "verification failed"
+    st0 = s.prove(1, 0)
+    assert st0["ok"] == 1 and st0["checks"] == CHECKED_ALL, "verification failed"
     golden = os.path.join(ROOT, "tests", "golden", "vgg11_syn_p1_seed1.result.txt")
     parity = None
     if model == "vgg11" and os.path.exists(golden):

@@ -18,19 +18,25 @@ typedef struct zkh_session zkh_session;
 
 enum {
     ZKH_REAL_GENERATORS  = 1,  /* Hyrax generators = standard G1 generator * challenge (default: the reference's all-infinity set) */
-    ZKH_CHECK_PREDICATES = 2,  /* run the verifier-side wiring predicates and G1 checks too (full verification) */
+    ZKH_CHECK_PREDICATES = 2,  /* accepted for compatibility: full verification is the default */
     ZKH_WITNESS_RESIDENT = 4,  /* keep the witness on the device between proofs (skip the host->device copy if present) */
     ZKH_FIXED_GENERATORS = 8,  /* reuse the generators of the previous proof (public parameters), keep the window table */
     ZKH_PREFETCH_NEXT    = 32, /* once this proof has its witness, start copying the witness for the NEXT zkh_prove on a second stream
                                  (double buffering: the copy overlaps this proof; the next proof adopts it instead of uploading) */
     ZKH_NO_HASH          = 64, /* leave zkh_stats.fnv1a at 0 (the FNV-1a of the 0.5 MB transcript costs 0.7 ms per vgg11 proof) */
+    ZKH_PROVER_ONLY      = 128,/* prover-only timing: the verifier keeps its per-round sum checks and the field-side checks of the opening but
+                                 skips the wiring predicates (getFinalValue), the input-layer "gr" recomputation and every G1 check of the
+                                 Hyrax opening (src/verifier.cpp:36-116,307-325; polyVerifier.cpp:25-27,53-58); zkh_stats.checks says what ran */
+    ZKH_CSPRNG_CHALLENGES = 256, /* draw the challenges from the operating system's CSPRNG like the reference (Fr::setByCSPRNG,
+                                 src/verifier.cpp:124,139,...) instead of the seeded stream: `seed` is ignored, the transcript is not reproducible */
+    ZKH_FIAT_SHAMIR      = 512,/* non-interactive mode: every challenge is derived from the transcript so far (see host/challenge_stream.hpp) */
     ZKH_ROUND_BY_ROUND   = 16  /* one device round trip per sumcheck round (the reference's call pattern) instead of one per phase:
                                  the verifier draws a phase's challenges before its first round either way (src/verifier.cpp:156-160),
                                  so the transcript is the same; default is per phase (zk_sumcheck_update_batch) */
 };
 
 typedef struct {
-    int32_t ok;                 /* verifier accepted */
+    int32_t ok;                 /* verifier accepted (every check listed in `checks` passed) */
     uint32_t n_layers;
     uint64_t input_size;        /* gates in layer 0 (witness size) */
     uint64_t n_fr, n_g1;        /* field elements / points in the proof */
@@ -45,7 +51,15 @@ typedef struct {
     double verifier_s;          /* verifier-only work inside wall_s (predicates, point checks) */
     double gkr_kb, poly_kb;     /* proof size as the reference counts it */
     uint64_t h2d_bytes;         /* witness bytes copied host->device for this proof */
+    uint32_t checks;            /* what the verifier checked: ZKH_CHECKED_* */
+    uint32_t reserved;
 } zkh_stats;
+enum {
+    ZKH_CHECKED_ROUND_SUMS = 1,   /* p(0) + p(1) = claim for every sumcheck round; y and bulletOpen of the opening */
+    ZKH_CHECKED_PREDICATES = 2,   /* per-layer getFinalValue (wiring predicates) */
+    ZKH_CHECKED_INPUT_GR   = 4,   /* input-layer sumcheck against the recomputed gr */
+    ZKH_CHECKED_G1         = 8    /* comm_RZ, generator folds and the final point equation of the Hyrax opening */
+};
 
 const char *zkh_last_error(void);
 /* model: "lenet" (32x32x1, max pooling), "lenet_cifar", "vgg11", "vgg16" (32x32x3, max pooling) or "vgg" with

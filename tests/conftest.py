@@ -70,6 +70,18 @@ def synthetic_inputs(tmp_path_factory):
     return out
 
 
+@pytest.fixture(scope="session")
+def mnist_input(tmp_path_factory):
+    """BASELINE config 1: the reference's shipped LeNet5 / MNIST input (62 730 decimals: one 32x32 image, then the weights;
+    data/lenet5.mnist.relu.max/lenet5.mnist.relu.max-1-images-weights-qint8.csv of the reference's data.tar.gz,
+    script/demo_lenet.sh:14-18), committed gzip-compressed as a test fixture"""
+    import gzip
+    path = os.path.join(tmp_path_factory.mktemp("mnist"), "lenet5_mnist.csv")
+    with gzip.open(os.path.join(GOLDEN, "lenet5_mnist_input.csv.gz"), "rb") as f, open(path, "wb") as g:
+        g.write(f.read())
+    return path
+
+
 def golden_bytes(name):
     return open(os.path.join(GOLDEN, name + ".transcript.bin"), "rb").read()
 

@@ -10,7 +10,7 @@ import pytest
 
 import _cases as cases
 from conftest import GOLDEN, ROOT
-from zkcnn_b200._binding import (CHECK_PREDICATES, PREFETCH_NEXT, REAL_GENERATORS, ROUND_BY_ROUND, WITNESS_RESIDENT, Context, Session, fr_from_words, fr_to_words,
+from zkcnn_b200._binding import (CHECKED_ALL, CHECK_PREDICATES, PROVER_ONLY, PREFETCH_NEXT, REAL_GENERATORS, ROUND_BY_ROUND, WITNESS_RESIDENT, Context, Session, fr_from_words, fr_to_words,
                                  g1_from_words, g1_to_words)
 
 pytestmark = pytest.mark.gpu
@@ -86,6 +86,9 @@ def test_hyrax(gpu_lib, kat):
 
 # ---- whole proofs against the reference's transcripts ---------------------------------------------------------------------
 @pytest.mark.parametrize("model,net,pics,inp,seed,flags,golden", [
+    # BASELINE config 1: the reference's shipped MNIST input (script/demo_lenet.sh), degenerate and real generators
+    ("lenet", "", 1, "mnist", 1, 0, "lenet_p1_seed1"),
+    ("lenet", "", 1, "mnist", 1, REAL_GENERATORS, "lenet_p1_seed1_realgens"),
     ("lenet", "", 1, "lenet_syn", 3, CHECK_PREDICATES, "lenet_syn_p1_seed3"),
     ("lenet", "", 1, "lenet_syn", 3, REAL_GENERATORS | CHECK_PREDICATES, "lenet_syn_p1_seed3_realgens"),
     ("lenet", "", 2, "lenet_syn", 4, CHECK_PREDICATES, "lenet_syn_p2_seed4"),
@@ -96,9 +99,9 @@ def test_hyrax(gpu_lib, kat):
     ("lenet", "", 1, "lenet_syn", 3, CHECK_PREDICATES | ROUND_BY_ROUND, "lenet_syn_p1_seed3"),
     ("vgg", "small", 1, "smallvgg", 7, CHECK_PREDICATES | ROUND_BY_ROUND, "smallvgg_p1_seed7"),
 ])
-def test_transcripts(gpu_host, synthetic_inputs, model, net, pics, inp, seed, flags, golden):
+def test_transcripts(gpu_host, synthetic_inputs, mnist_input, model, net, pics, inp, seed, flags, golden):
     net = synthetic_inputs["smallvgg_config"] if net == "small" else net
-    st = cases.prove_and_compare(gpu_host, model, net, pics, synthetic_inputs[inp], seed, flags, golden, GOLDEN)
+    st = cases.prove_and_compare(gpu_host, model, net, pics, mnist_input if inp == "mnist" else synthetic_inputs[inp], seed, flags, golden, GOLDEN)
     assert st["gpu_launches"] > 100
 
 
@@ -116,7 +119,7 @@ def test_against_the_reference_run_here(gpu_host, synthetic_inputs, tmp_path):
         with Session(gpu_host, "lenet", "", 1) as s:
             s.input_file(synthetic_inputs["lenet_syn"])
             s.build()
-            s.prove(12345, flag)
+            s.prove(12345, flag | PROVER_ONLY)
             assert s.proof() == out.read_bytes()
 
 
@@ -136,18 +139,19 @@ def test_vgg11_full_size(gpu_host, tmp_path):
         ref = dict(zip(*[iter(open(os.path.join(GOLDEN, "vgg11_syn_p1_seed1.result.txt")).read().split()[1:])] * 2))
         assert st["ok"] == 1 and st["proof_bytes"] == int(ref["bytes"]) and f"{st['fnv1a']:016x}" == ref["fnv"]
         # the same proof again with the witness resident, then with non-degenerate generators
-        st2 = s.prove(1, WITNESS_RESIDENT)
-        assert st2["fnv1a"] == st["fnv1a"] and st2["h2d_bytes"] == 0
-        st3 = s.prove(1, WITNESS_RESIDENT | REAL_GENERATORS)
+        assert st["checks"] == CHECKED_ALL          # full verification is the default
+        st2 = s.prove(1, WITNESS_RESIDENT | PROVER_ONLY)
+        assert st2["fnv1a"] == st["fnv1a"] and st2["h2d_bytes"] == 0 and st2["checks"] == 1
+        st3 = s.prove(1, WITNESS_RESIDENT | REAL_GENERATORS | PROVER_ONLY)
         assert st3["ok"] == 1 and st3["n_g1"] == st["n_g1"] and st3["fnv1a"] != st["fnv1a"]
         # one device round trip per sumcheck round (the reference's call pattern): the same transcript
-        st4 = s.prove(1, WITNESS_RESIDENT | ROUND_BY_ROUND)
+        st4 = s.prove(1, WITNESS_RESIDENT | ROUND_BY_ROUND | PROVER_ONLY)
         assert st4["ok"] == 1 and st4["fnv1a"] == st["fnv1a"]
         # double-buffered witness: this proof uploads and starts the copy for the next one (SM-driven, from mapped host memory),
         # the next one adopts it
-        st5 = s.prove(1, PREFETCH_NEXT)
-        st6 = s.prove(1, PREFETCH_NEXT)
-        st7 = s.prove(1, 0)
+        st5 = s.prove(1, PREFETCH_NEXT | PROVER_ONLY)
+        st6 = s.prove(1, PREFETCH_NEXT | PROVER_ONLY)
+        st7 = s.prove(1, PROVER_ONLY)
         for x in (st5, st6, st7):
             assert x["ok"] == 1 and x["fnv1a"] == st["fnv1a"] and x["h2d_bytes"] > 0
 
@@ -173,7 +177,8 @@ def test_fft_path_full_size(gpu_host, tmp_path, model, pics):
         assert st["ok"] == 1 and st["proof_bytes"] == int(ref["bytes"]) and f"{st['fnv1a']:016x}" == ref["fnv"]
         assert st["challenges"] == int(ref["challenges"])
         # the reference's call pattern (one device round trip per round) and full verification give the same transcript
-        st2 = s.prove(1, WITNESS_RESIDENT | ROUND_BY_ROUND | CHECK_PREDICATES)
+        assert st["checks"] == CHECKED_ALL
+        st2 = s.prove(1, WITNESS_RESIDENT | ROUND_BY_ROUND | PROVER_ONLY)
         assert st2["ok"] == 1 and st2["fnv1a"] == st["fnv1a"]
 
 

@@ -45,13 +45,11 @@ def test_round_by_round_driver_gives_the_same_transcript(emu_host, synthetic_inp
                             "smallvgg_p1_seed7", GOLDEN)
 
 
-def test_shipped_lenet_image(emu_host):
-    """the reference's own MNIST demo input (script/demo_lenet.sh), when the extracted data set is present"""
-    path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "data", "lenet5.mnist.relu.max",
-                        "lenet5.mnist.relu.max-1-images-weights-qint8.csv")
-    if not os.path.exists(path):
-        pytest.skip("reference data set not extracted (make -C oracle data)")
-    cases.prove_and_compare(emu_host, "lenet", "", 1, path, 1, CHECK_PREDICATES, "lenet_p1_seed1", GOLDEN)
+def test_shipped_lenet_image(emu_host, mnist_input):
+    """BASELINE config 1: the reference's own MNIST demo input (script/demo_lenet.sh), degenerate and real generators"""
+    st = cases.prove_and_compare(emu_host, "lenet", "", 1, mnist_input, 1, 0, "lenet_p1_seed1", GOLDEN)
+    assert st["ok"] == 1 and st["checks"] == 15
+    cases.prove_and_compare(emu_host, "lenet", "", 1, mnist_input, 1, REAL_GENERATORS, "lenet_p1_seed1_realgens", GOLDEN)
 
 
 def test_repeat_proofs_and_resident_witness(emu_host, synthetic_inputs):
@@ -88,6 +86,46 @@ def test_prefetched_witness_gives_the_same_proofs(emu_host, synthetic_inputs):
     # (the first proof pads val[0] to a power of two on the host, src/prover.cpp:504-508: later copies are that much longer)
     assert 0 < a["h2d_bytes"] <= b["h2d_bytes"] <= c["h2d_bytes"]
     assert pa == open(os.path.join(GOLDEN, "lenet_syn_p1_seed3.transcript.bin"), "rb").read()
+
+
+def test_rebuild_after_prefetch(emu_host, synthetic_inputs, mnist_input):
+    """a proof that prefetched the NEXT witness, then a new input and a rebuild: the stale shadow copy must not be adopted
+    (the circuit upload clears the device layers), with and without the resident-witness flag"""
+    from zkcnn_b200._binding import WITNESS_RESIDENT
+    with Session(emu_host, "lenet", "", 1) as s:
+        s.input_file(synthetic_inputs["lenet_syn"])
+        s.build()
+        a = s.prove(3, PREFETCH_NEXT)
+        assert a["ok"] == 1 and s.proof() == open(os.path.join(GOLDEN, "lenet_syn_p1_seed3.transcript.bin"), "rb").read()
+        s.input_file(mnist_input)
+        s.build()
+        b = s.prove(1, WITNESS_RESIDENT)
+        assert b["ok"] == 1 and b["h2d_bytes"] > 0
+        assert s.proof() == open(os.path.join(GOLDEN, "lenet_p1_seed1.transcript.bin"), "rb").read()
+        c = s.prove(1, WITNESS_RESIDENT)
+        assert c["ok"] == 1 and c["h2d_bytes"] == 0 and s.proof() == open(os.path.join(GOLDEN, "lenet_p1_seed1.transcript.bin"), "rb").read()
+
+
+def test_challenge_sources(emu_host, synthetic_inputs):
+    """seeded (default), the operating system's CSPRNG (the reference's Fr::setByCSPRNG) and Fiat-Shamir challenges"""
+    from zkcnn_b200._binding import CSPRNG_CHALLENGES, FIAT_SHAMIR, PROVER_ONLY
+    with Session(emu_host, "lenet", "", 1) as s:
+        s.input_file(synthetic_inputs["lenet_syn"])
+        s.build()
+        a = s.prove(3, CSPRNG_CHALLENGES)
+        pa = s.proof()
+        b = s.prove(3, CSPRNG_CHALLENGES)
+        pb = s.proof()
+        assert a["ok"] == 1 and b["ok"] == 1 and a["checks"] == 15 and pa != pb and len(pa) == len(pb)
+        # Fiat-Shamir: accepted under full verification, reproducible, seed-separated, and every challenge drawn after the message it answers
+        c = s.prove(3, FIAT_SHAMIR)
+        pc = s.proof()
+        d = s.prove(3, FIAT_SHAMIR)
+        e = s.prove(4, FIAT_SHAMIR)
+        assert c["ok"] == 1 and c["checks"] == 15 and s.proof() != pc and d["fnv1a"] == c["fnv1a"] and e["fnv1a"] != c["fnv1a"]
+        assert pc != open(os.path.join(GOLDEN, "lenet_syn_p1_seed3.transcript.bin"), "rb").read()
+        p = s.prove(3, PROVER_ONLY)
+        assert p["ok"] == 1 and p["checks"] == 1 and s.proof() == open(os.path.join(GOLDEN, "lenet_syn_p1_seed3.transcript.bin"), "rb").read()
 
 
 def test_tampered_witness_is_rejected(emu_host, synthetic_inputs, tmp_path):

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import gen_synthetic_input as gen
 import zkcnn_b200
-from zkcnn_b200 import PROF_CLASSES, REAL_GENERATORS, WITNESS_RESIDENT
+from zkcnn_b200 import PROF_CLASSES, PROVER_ONLY, REAL_GENERATORS, WITNESS_RESIDENT
 model, pics = sys.argv[1], int(sys.argv[2])
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 lib = zkcnn_b200.load()
@@ -16,11 +16,11 @@ s.input_values(gen.generate(model).astype(np.float64))
 t0 = time.perf_counter(); s.build(); print(f"build {time.perf_counter() - t0:.1f} s", file=sys.stderr)
 t0 = time.perf_counter(); st = s.prove(1, 0); print(f"first proof (upload + schedules) {time.perf_counter() - t0:.2f} s fnv {st['fnv1a']:016x} ok {st['ok']} launches {st['gpu_launches']}", file=sys.stderr)
 for i in range(n):
-    t0 = time.perf_counter(); st = s.prove(100 + i, REAL_GENERATORS | WITNESS_RESIDENT)
+    t0 = time.perf_counter(); st = s.prove(100 + i, REAL_GENERATORS | WITNESS_RESIDENT | PROVER_ONLY)
     print(f"resident {i}: {(time.perf_counter() - t0) * 1e3:.2f} ms  prove_s {st['prove_s']:.4f} poly_s {st['poly_s']:.4f} launches {st['gpu_launches']}", file=sys.stderr)
 ctx = s.context_handle()
 lib.dll.zk_profile_enable(ctx, 1)
-t0 = time.perf_counter(); s.prove(100, REAL_GENERATORS | WITNESS_RESIDENT); wall = time.perf_counter() - t0
+t0 = time.perf_counter(); s.prove(100, REAL_GENERATORS | WITNESS_RESIDENT | PROVER_ONLY); wall = time.perf_counter() - t0
 out = {"model": model, "pics": pics, "profiled_wall_ms": round(wall * 1e3, 2)}
 for k, name in enumerate(PROF_CLASSES):
     ms, cnt, b = C.c_double(0), C.c_uint64(0), C.c_uint64(0)

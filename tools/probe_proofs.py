@@ -7,13 +7,13 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import gen_synthetic_input as gen
 import zkcnn_b200
-from zkcnn_b200 import REAL_GENERATORS, WITNESS_RESIDENT, PREFETCH_NEXT
+from zkcnn_b200 import PROVER_ONLY, REAL_GENERATORS, WITNESS_RESIDENT, PREFETCH_NEXT
 mode = sys.argv[1]
 values = gen.generate("vgg11")
 s = zkcnn_b200.session("vgg", "64 M 128 M 256 256 M 512 512 M 512 512 M", 1, device=0)
 s.input_values(values.astype(np.float64)); s.build()
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 for i in range(n):
-    fl = REAL_GENERATORS | (WITNESS_RESIDENT if mode == "resident" else PREFETCH_NEXT)
+    fl = REAL_GENERATORS | PROVER_ONLY | (WITNESS_RESIDENT if mode == "resident" else PREFETCH_NEXT)
     t0 = time.perf_counter(); st = s.prove(100 + i, fl); print(mode, i, f"{(time.perf_counter()-t0)*1e3:.2f} ms", file=sys.stderr)
 s.close()

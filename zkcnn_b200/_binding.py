@@ -276,13 +276,17 @@ class Stats(C.Structure):
     _fields_ = [("ok", C.c_int32), ("n_layers", C.c_uint32), ("input_size", C.c_uint64), ("n_fr", C.c_uint64), ("n_g1", C.c_uint64),
                 ("proof_bytes", C.c_uint64), ("fnv1a", C.c_uint64), ("challenges", C.c_uint64), ("gpu_launches", C.c_uint64),
                 ("prove_s", C.c_double), ("poly_s", C.c_double), ("upload_s", C.c_double), ("wall_s", C.c_double),
-                ("verifier_s", C.c_double), ("gkr_kb", C.c_double), ("poly_kb", C.c_double), ("h2d_bytes", C.c_uint64)]
+                ("verifier_s", C.c_double), ("gkr_kb", C.c_double), ("poly_kb", C.c_double), ("h2d_bytes", C.c_uint64), ("checks", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 REAL_GENERATORS, CHECK_PREDICATES, WITNESS_RESIDENT, FIXED_GENERATORS, ROUND_BY_ROUND, PREFETCH_NEXT, NO_HASH = 1, 2, 4, 8, 16, 32, 64
+PROVER_ONLY, CSPRNG_CHALLENGES, FIAT_SHAMIR = 128, 256, 512
+CHECKED_ROUND_SUMS, CHECKED_PREDICATES, CHECKED_INPUT_GR, CHECKED_G1 = 1, 2, 4, 8
+CHECKED_ALL = 15
 
 
 class HostLib:

@@ -161,8 +161,11 @@ int zkh_prefetch_witness(zkh_session *s) {
 int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
     ZKH_BEGIN
     if (!s || !s->built) throw std::logic_error("zkh_prove: call zkh_build first");
-    zkcnn_b200::ScopedChallengeStream rng(seed);
+    const bool os_rng = (flags & ZKH_CSPRNG_CHALLENGES) != 0;
+    zkcnn_b200::ScopedChallengeStream rng(seed, os_rng ? zkcnn_b200::ChallengeStream::OS_CSPRNG
+                                                : (flags & ZKH_FIAT_SHAMIR) ? zkcnn_b200::ChallengeStream::FIAT_SHAMIR : zkcnn_b200::ChallengeStream::SEEDED);
     s->tr.clear();
+    rng.stream.transcript = &s->tr;
     prover &p = s->p;
     p.setWitnessResident((flags & ZKH_WITNESS_RESIDENT) != 0);
     p.setPrefetchNext((flags & ZKH_PREFETCH_NEXT) != 0);
@@ -170,9 +173,10 @@ int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
     const uint64_t l0 = p.gpuLaunches();
     auto t0 = std::chrono::steady_clock::now();
     verifier v(&p, p.C);
-    v.checkPredicates = (flags & ZKH_CHECK_PREDICATES) != 0;
+    v.checkPredicates = (flags & ZKH_PROVER_ONLY) == 0;   // full verification unless the caller asks for prover-only timing
     v.realGenerators = (flags & ZKH_REAL_GENERATORS) != 0;
     v.batchRounds = (flags & ZKH_ROUND_BY_ROUND) == 0;
+    v.fiatShamir = (flags & ZKH_FIAT_SHAMIR) != 0 && !os_rng;
     if ((flags & ZKH_FIXED_GENERATORS) && !s->last_gens.empty()) v.fixedGenerators = &s->last_gens;
     const bool ok = v.verify();
     auto t1 = std::chrono::steady_clock::now();
@@ -196,6 +200,7 @@ int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
         out->gkr_kb = p.proofSize();
         out->poly_kb = p.polyProofSize();
         out->h2d_bytes = p.lastUploadBytes();
+        out->checks = ZKH_CHECKED_ROUND_SUMS | (v.checkPredicates ? ZKH_CHECKED_PREDICATES | ZKH_CHECKED_INPUT_GR | ZKH_CHECKED_G1 : 0);
     }
     ZKH_END
 }

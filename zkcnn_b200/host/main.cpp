@@ -3,7 +3,7 @@
 //
 //   zkcnn_prove lenet <input.csv> <pic_cnt> <seed> [options]
 //   zkcnn_prove vgg   <input.csv> "<network description>" <pic_cnt> <seed> [options]
-// options: --gens real|degenerate   --check (full verification)   --round-by-round (one device call per sumcheck round)   --transcript out.bin   --circuit-hash out.txt
+// options: --gens real|degenerate   --prover-only (skip the verifier's wiring predicates and G1 checks; full verification is the default)   --csprng (challenges from the OS CSPRNG, like the reference)   --fiat-shamir   --round-by-round (one device call per sumcheck round)   --transcript out.bin   --circuit-hash out.txt
 //          --repeat N (prove N times, witness resident after the first)   --device D
 #include "../../include/zkcnn_host.h"
 #include <cstdio>
@@ -30,7 +30,10 @@ int main(int argc, char **argv) {
     for (; k < argc; ++k) {
         const std::string a = argv[k];
         if (a == "--gens" && k + 1 < argc) { if (std::string(argv[++k]) == "real") flags |= ZKH_REAL_GENERATORS; }
-        else if (a == "--check") flags |= ZKH_CHECK_PREDICATES;
+        else if (a == "--check") flags |= ZKH_CHECK_PREDICATES;   // (the default; kept for old command lines)
+        else if (a == "--prover-only") flags |= ZKH_PROVER_ONLY;
+        else if (a == "--csprng") flags |= ZKH_CSPRNG_CHALLENGES;
+        else if (a == "--fiat-shamir") flags |= ZKH_FIAT_SHAMIR;
         else if (a == "--round-by-round") flags |= ZKH_ROUND_BY_ROUND;
         else if (a == "--transcript" && k + 1 < argc) tr_out = argv[++k];
         else if (a == "--circuit-hash" && k + 1 < argc) hash_out = argv[++k];

@@ -145,6 +145,9 @@ void prover::buildCompactWitness() {
 
 void prover::unpinWitness() {
     joinPrefetch();   // a copy in flight reads these buffers
+    // the host witness is about to change: neither the device copy nor a prefetched shadow copy describes it any more
+    prefetch_pending_ = false;
+    witness_uploaded_ = false;
     compact_ready_ = false;
     for (const void *p : pinned_) zk_host_unpin(p);
     pinned_.clear();

@@ -85,7 +85,8 @@ public:
     // record every prover->verifier message in SURVEY.md App. A order (nullptr = off)
     void setTranscript(zkcnn_b200::Transcript *t) { transcript_ = t; }
     // init() uploads C once; call this if C was rebuilt and must be uploaded again
-    void invalidateCircuit() { circuit_uploaded_ = false; }
+    // (a rebuilt circuit also invalidates the witness on the device and any prefetched copy of it)
+    void invalidateCircuit() { joinPrefetch(); circuit_uploaded_ = false; witness_uploaded_ = false; prefetch_pending_ = false; }
     // seconds spent uploading circuit / witness in init() (outside the prove timer, like the reference's allocations)
     double uploadTime() const { return upload_timer.elapse_sec(); }
     // true: init() keeps the witness that is already on the device (same val as the previous proof) instead of copying it again

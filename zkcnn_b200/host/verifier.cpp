@@ -314,7 +314,8 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
 
         // ---- phase 1: all challenges of the phase are drawn before its rounds (src/verifier.cpp:156-160)
         total_timer.start();
-        drawChallenges(r_u[i], cur.max_bl_u);
+        if (fiatShamir) r_u[i].assign(cur.max_bl_u, F());   // drawn round by round, after the message each one answers
+        else drawChallenges(r_u[i], cur.max_bl_u);
         if (cur.zero_start_id < cur.size) relu_rou.setByCSPRNG();
         else relu_rou = F_ONE;
         total_timer.stop();
@@ -324,16 +325,19 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
         F prev = F_ZERO;
         vector<quadratic_poly> all;
         vector<cubic_poly> all_dot;
-        if (batchRounds && !dot) all = p->sumcheckUpdateAll(1, r_u[i], cur.max_bl_u);
-        if (batchRounds && dot) all_dot = p->sumcheckDotProdUpdateAll(r_u[i], cur.max_bl_u);
+        const bool batch = batchRounds && !fiatShamir;
+        if (batch && !dot) all = p->sumcheckUpdateAll(1, r_u[i], cur.max_bl_u);
+        if (batch && dot) all_dot = p->sumcheckDotProdUpdateAll(r_u[i], cur.max_bl_u);
         for (int j = 0; j < cur.max_bl_u; ++j) {
             F at0p1, atr;
             if (dot) {
-                cubic_poly poly = batchRounds ? all_dot[j] : p->sumcheckDotProdUpdate1(prev);
+                cubic_poly poly = batch ? all_dot[j] : p->sumcheckDotProdUpdate1(prev);
+                if (fiatShamir) r_u[i][j].setByCSPRNG();
                 at0p1 = poly.d + poly.eval(F_ONE);
                 atr = poly.eval(r_u[i][j]);
             } else {
-                quadratic_poly poly = batchRounds ? all[j] : p->sumcheckUpdate1(prev);
+                quadratic_poly poly = batch ? all[j] : p->sumcheckUpdate1(prev);
+                if (fiatShamir) r_u[i][j].setByCSPRNG();
                 at0p1 = poly.c + poly.eval(F_ONE);
                 atr = poly.eval(r_u[i][j]);
             }
@@ -357,13 +361,15 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
         // ---- phase 2
         if (cur.need_phase2) {
             total_timer.start();
-            drawChallenges(r_v[i], cur.max_bl_v);
+            if (fiatShamir) r_v[i].assign(cur.max_bl_v, F());
+            else drawChallenges(r_v[i], cur.max_bl_v);
             total_timer.stop();
             p->sumcheckInitPhase2();
             prev = F_ZERO;
-            if (batchRounds) all = p->sumcheckUpdateAll(2, r_v[i], cur.max_bl_v);
+            if (batch) all = p->sumcheckUpdateAll(2, r_v[i], cur.max_bl_v);
             for (int j = 0; j < cur.max_bl_v; ++j) {
-                quadratic_poly poly = batchRounds ? all[j] : p->sumcheckUpdate2(prev);
+                quadratic_poly poly = batch ? all[j] : p->sumcheckUpdate2(prev);
+                if (fiatShamir) r_v[i][j].setByCSPRNG();
                 if (poly.c + poly.eval(F_ONE) != sum) {
                     fprintf(stderr, "Verification fail, phase2, circuit level %d, current bit %d, total is %d\n", (int) i, j, (int) cur.max_bl_v);
                     return false;
@@ -407,7 +413,8 @@ bool verifier::verifyFirstLayer() {   // src/verifier.cpp:268-357
     total_timer.start();
     drawChallenges(sig_u, C.size - 1);
     drawChallenges(sig_v, C.size - 1);
-    drawChallenges(r_u[0], in.bit_length);
+    if (fiatShamir) r_u[0].assign(in.bit_length, F());
+    else drawChallenges(r_u[0], in.bit_length);
     F sum = F_ZERO;
     for (int i = 1; i < C.size; ++i) {
         if (C.circuit[i].bit_length_u[0] != -1) sum += sig_u[i - 1] * final_claim_u0[i];
@@ -418,9 +425,11 @@ bool verifier::verifyFirstLayer() {   // src/verifier.cpp:268-357
     p->sumcheckLiuInit(sig_u, sig_v);
     F prev = F_ZERO;
     vector<quadratic_poly> all;
-    if (batchRounds) all = p->sumcheckUpdateAll(0, r_u[0], in.bit_length);
+    const bool batch = batchRounds && !fiatShamir;
+    if (batch) all = p->sumcheckUpdateAll(0, r_u[0], in.bit_length);
     for (int j = 0; j < in.bit_length; ++j) {
-        quadratic_poly poly = batchRounds ? all[j] : p->sumcheckLiuUpdate(prev);
+        quadratic_poly poly = batch ? all[j] : p->sumcheckLiuUpdate(prev);
+        if (fiatShamir) r_u[0][j].setByCSPRNG();
         if (poly.c + poly.eval(F_ONE) != sum) {
             fprintf(stderr, "Liu fail, circuit 0, current bit %d\n", j);
             return false;

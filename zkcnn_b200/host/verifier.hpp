@@ -49,6 +49,10 @@ public:
     bool realGenerators = false;
     // one device call per phase (prover::sumcheckUpdateAll) instead of one per round; the messages and their order are the same
     bool batchRounds = true;
+    // Fiat-Shamir mode (the active ChallengeStream derives every challenge from the transcript so far): a round's challenge is
+    // drawn AFTER the round's message instead of before the phase (src/verifier.cpp:156-160 draws them up front, which is only
+    // sound for an interactive verifier), so the rounds go one by one
+    bool fiatShamir = false;
     // Hyrax generators are public parameters; when set, they are reused instead of redrawn (the challenge stream is
     // still advanced as if they had been drawn)
     const vector<G> *fixedGenerators = nullptr;

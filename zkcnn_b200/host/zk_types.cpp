@@ -6,8 +6,35 @@
 namespace zkcnn_b200 {
 
 ChallengeStream *&active_challenge_stream() {
-    static ChallengeStream *s = nullptr;
+    static thread_local ChallengeStream *s = nullptr;
     return s;
+}
+
+static void os_random(uint8_t *out, size_t n) {
+    static FILE *f = fopen("/dev/urandom", "rb");
+    if (!f || fread(out, 1, n, f) != n) throw std::runtime_error("cannot read /dev/urandom");
+}
+
+void ChallengeStream::read(uint8_t *out, size_t n) {
+    if (mode == OS_CSPRNG) { os_random(out, n); ++calls; return; }
+    if (mode == FIAT_SHAMIR) {
+        auto absorb = [&](const uint8_t *b, size_t len) { for (size_t i = 0; i < len; ++i) { fs_hash ^= b[i]; fs_hash *= 0x100000001b3ULL; } };
+        if (transcript && transcript->bytes.size() > fs_pos) {
+            absorb(transcript->bytes.data() + fs_pos, transcript->bytes.size() - fs_pos);
+            fs_pos = transcript->bytes.size();
+        }
+        uint64_t h = fs_hash;
+        const uint64_t tag[2] = {seed, calls};
+        const uint8_t *tb = reinterpret_cast<const uint8_t *>(tag);
+        for (size_t i = 0; i < sizeof tag; ++i) { h ^= tb[i]; h *= 0x100000001b3ULL; }
+        state = h;
+    }
+    for (size_t i = 0; i < n; i += 8) {
+        uint64_t w = next();
+        size_t m = n - i < 8 ? n - i : 8;
+        memcpy(out + i, &w, m);
+    }
+    ++calls;
 }
 
 void challenge_bytes(uint8_t *out, size_t n) {
@@ -15,11 +42,10 @@ void challenge_bytes(uint8_t *out, size_t n) {
         s->read(out, n);
         return;
     }
-    static FILE *f = fopen("/dev/urandom", "rb");
-    if (!f || fread(out, 1, n, f) != n) throw std::runtime_error("cannot read /dev/urandom");
+    os_random(out, n);
 }
 
-ScopedChallengeStream::ScopedChallengeStream(uint64_t seed) : stream(seed), saved(active_challenge_stream()) {
+ScopedChallengeStream::ScopedChallengeStream(uint64_t seed, ChallengeStream::Mode mode) : stream(seed, mode), saved(active_challenge_stream()) {
     active_challenge_stream() = &stream;
 }
 ScopedChallengeStream::~ScopedChallengeStream() { active_challenge_stream() = saved; }
