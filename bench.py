@@ -106,10 +106,58 @@ def gather_proofs(proof, device, dist):
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
+NETWORKS = {"vgg11": VGG11, "vgg16": "64 64 M 128 128 M 256 256 256 M 512 512 512 M 512 512 512 M"}
+
+
+def synthetic_values(model, config, image_seed=None):
+    """seeded synthetic weights (+ the golden image, or a different seeded image when image_seed is given)"""
+    import numpy as np
+    import gen_synthetic_input as gen
+    v = gen.generate("lenet" if model == "lenet" else "vgg11", config=None if model == "lenet" else config).astype(np.float64)
+    if image_seed is not None:
+        n_img = 32 * 32 * (1 if model == "lenet" else 3)
+        v[:n_img] = np.random.default_rng(image_seed).random(n_img, dtype=np.float32)
+    return v
+
+
+def run_parallel(sessions, jobs):
+    """jobs[m] = list of (seed, flags) for session m; every session proves its list on its own host thread (the C calls release the
+    GIL), i.e. len(sessions) proofs are in flight on the GPU.  Returns per-session lists of (stats, proof bytes)."""
+    out = [[] for _ in sessions]
+    err = []
+
+    def work(m):
+        try:
+            for seed, fl in jobs[m]:
+                st = sessions[m].prove(seed, fl)
+                out[m].append((st, sessions[m].proof()))
+        except Exception as e:   # noqa: BLE001
+            err.append(e)
+
+    if len(sessions) == 1:
+        work(0)
+    else:
+        th = [threading.Thread(target=work, args=(m,)) for m in range(len(sessions))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+    if err:
+        raise err[0]
+    return out
+
+
+def fnv1a(data):
+    h = 0xcbf29ce484222325
+    for i in range(0, len(data), 1 << 16):
+        for b in data[i:i + (1 << 16)]:
+            h = ((h ^ b) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
 def run_ours(args):
     import numpy as np
     import torch
-    import gen_synthetic_input as gen
     import zkcnn_b200
     from zkcnn_b200 import PROF_CLASSES, REAL_GENERATORS, WITNESS_RESIDENT, CHECKED_ALL, PROVER_ONLY, ROUND_BY_ROUND, PREFETCH_NEXT, NO_HASH
     import ctypes as C
@@ -129,50 +177,64 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    model = args.model
-    config = VGG11 if model == "vgg11" else args.network
-    values = gen.generate("vgg11" if model == "vgg11" else "lenet", config=config if model == "vgg" else None)
+    model, pics, M = args.model, args.pics, max(1, args.inflight)
+    config = NETWORKS.get(model, args.network)
     lib = zkcnn_b200.load()
-    s = zkcnn_b200.session("lenet" if model == "lenet" else "vgg", "" if model == "lenet" else config, 1, device=local)
-    s.input_values(values.astype(np.float64))
-    t0 = time.perf_counter()
-    s.build()
-    build_s = time.perf_counter() - t0
+    # M independent provers per GPU (own zk_ctx, own stream, own witness): M proofs in flight.  Session 0 of rank 0 proves the golden image
+    # (transcript parity inside the bench), every other session its own seeded image: the proofs of a step are of DISTINCT pictures.
+    sessions, build_s = [], 0.0
+    for m in range(M):
+        s = zkcnn_b200.session("lenet" if model == "lenet" else "vgg", "" if model == "lenet" else config, pics, device=local)
+        s.input_values(synthetic_values(model, config, None if (rank == 0 and m == 0) else 7000 + rank * M + m))
+        t0 = time.perf_counter()
+        s.build()
+        build_s = max(build_s, time.perf_counter() - t0)
+        sessions.append(s)
+    s0 = sessions[0]
     # NO_HASH: the FNV-1a of the transcript is a statistic of zkh_prove, not part of the proof (the proof bytes are produced and read back)
+    # PROVER_ONLY: the timed proofs skip the verifier-side wiring predicates and G1 checks (the reference arm counts prover seconds only, too)
     flags = REAL_GENERATORS | NO_HASH | PROVER_ONLY | (ROUND_BY_ROUND if args.round_by_round else 0)
-    # one fully verified proof with the reference's own (degenerate) generator set: full-size parity inside the bench
-    st0 = s.prove(1, 0)
-    assert st0["ok"] == 1 and st0["checks"] == CHECKED_ALL, "verification failed"
-    golden = os.path.join(ROOT, "tests", "golden", "vgg11_syn_p1_seed1.result.txt")
-    parity = None
-    if model == "vgg11" and os.path.exists(golden):
-        ref = dict(zip(*[iter(open(golden).read().split()[1:])] * 2))
-        parity = f"{st0['fnv1a']:016x}" == ref["fnv"]
-        assert parity, "vgg11 transcript differs from the reference's golden hash"
-    for i in range(max(args.warmup, 3)):
-        st = s.prove(1000 + i, flags | WITNESS_RESIDENT)
-        assert st["ok"] == 1
+    parity = {"verified": False}
+    if rank == 0:
+        # one FULLY VERIFIED proof with the reference's own (degenerate) generator set, and one with real generators: both transcripts against
+        # hashes minted from the compiled reference on the same input and seed (tests/golden)
+        st0 = s0.prove(1, 0)
+        assert st0["ok"] == 1 and st0["checks"] == CHECKED_ALL, "verification failed"
+        parity["verified"] = True
+        for key, seed, fl, gname in (("transcript_matches_reference_golden", 1, None, f"{model}_syn_p{pics}_seed1"),
+                                     ("real_generator_transcript_matches_reference", 10000, REAL_GENERATORS | PROVER_ONLY, f"{model}_syn_p{pics}_seed10000_realgens")):
+            golden = os.path.join(ROOT, "tests", "golden", gname + ".result.txt")
+            if not os.path.exists(golden):
+                parity[key] = None
+                continue
+            ref = dict(zip(*[iter(open(golden).read().split()[1:])] * 2))
+            st = st0 if fl is None else s0.prove(seed, fl | WITNESS_RESIDENT)
+            parity[key] = f"{st['fnv1a']:016x}" == ref["fnv"] and st["proof_bytes"] == int(ref["bytes"])
+            assert parity[key], f"{gname}: transcript differs from the reference's golden hash"
+    else:
+        st0 = s0.prove(1, PROVER_ONLY)
+    W = max(args.warmup, 3)
+    run_parallel(sessions, [[(1000 + i, flags | WITNESS_RESIDENT) for i in range(W)] for _ in sessions])
 
-    ctx = s.context_handle()
+    ctx = s0.context_handle()
     seeds = [10_000 + (k * world + rank) for k in range(args.steps)]
+    share = [seeds[m::M] for m in range(M)]          # K proofs per GPU per timed region, dealt round-robin to the M provers
     with ClockSampler(local) as clocks:
         # ---- value: K proofs, witness resident in HBM, no instrumentation ---------------------------------------------------
         barrier()
         t0 = time.perf_counter()
-        launches = 0
-        for sd in seeds:
-            st = s.prove(sd, flags | WITNESS_RESIDENT)
-            launches += st["gpu_launches"]
-            assert st["ok"] == 1
+        res = run_parallel(sessions, [[(sd, flags | WITNESS_RESIDENT) for sd in share[m]] for m in range(M)])
         barrier()
         t_value = time.perf_counter() - t0
-        # ---- roofline pass: the same K proofs again with CUDA events around every launch (per kernel class); the events
-        #      cost ~2 us per launch on ~1800 launches per proof, which is why `value` is not taken from this pass
+        launches = sum(st["gpu_launches"] for r in res for st, _ in r)
+        assert all(st["ok"] == 1 for r in res for st, _ in r)
+        # ---- roofline pass: K proofs on ONE prover with CUDA events around every launch (per kernel class); the events cost ~2 us per
+        #      launch and switch the programmatic dependent launches off, which is why `value` is not taken from this pass
         lib.dll.zk_profile_enable(ctx, 1)
         barrier()
         t0 = time.perf_counter()
         for sd in seeds:
-            st = s.prove(sd, flags | WITNESS_RESIDENT)
+            st = s0.prove(sd, flags | WITNESS_RESIDENT)
             assert st["ok"] == 1
         barrier()
         t_prof = time.perf_counter() - t0
@@ -182,28 +244,23 @@ def run_ours(args):
             lib.dll.zk_profile_get(ctx, k, C.byref(ms), C.byref(n), C.byref(b))
             prof[name] = {"ms": ms.value, "launches": n.value, "bytes": b.value}
         lib.dll.zk_profile_enable(ctx, 0)
-        # ---- e2e: every step copies its witness from pinned host memory and reads the proof back; the copy for step k + 1
-        #      is issued on a second stream as soon as step k has its own witness (double buffering), step 0's copy is exposed
-        for i in range(max(args.warmup, 3)):   # warm-up of THIS path: shadow buffers, copy kernel, mapped host memory
-            st = s.prove(2000 + i, flags | (0 if args.no_prefetch else PREFETCH_NEXT))
-            assert st["ok"] == 1
-        if not args.no_prefetch:
-            s.prove(2999, flags)              # adopts the pending copy: the timed region starts with nothing in flight
+        # ---- e2e: every step copies its witness from pinned host memory and reads the proof back; each prover issues the copy for its next
+        #      proof on a second stream as soon as the current proof has its own witness (double buffering); the K proofs of every rank are
+        #      exchanged by one all-gather at the end
+        pf = 0 if args.no_prefetch else PREFETCH_NEXT
+        run_parallel(sessions, [[(2000 + i, flags | pf) for i in range(W)] + ([(2999, flags)] if pf else []) for _ in sessions])
         if dist is not None:
-            gather_proofs(s.proof(), device, dist)   # warm-up of the exchange step too (first-use set-up of the collective)
+            gather_proofs(s0.proof() * len(seeds), device, dist)   # warm-up of the exchange step too (first-use set-up of the collective)
         barrier()
         t0 = time.perf_counter()
-        h2d = d2h = 0
-        proofs = []
-        for k, sd in enumerate(seeds):
-            st = s.prove(sd, flags | (PREFETCH_NEXT if not args.no_prefetch and k + 1 < len(seeds) else 0))
-            h2d += st["h2d_bytes"]
-            d2h += st["proof_bytes"]
-            proofs.append(s.proof())
-            assert st["ok"] == 1
+        res = run_parallel(sessions, [[(sd, flags | (pf if k + 1 < len(share[m]) else 0)) for k, sd in enumerate(share[m])] for m in range(M)])
+        proofs = [p for r in res for _, p in r]
+        h2d = sum(st["h2d_bytes"] for r in res for st, _ in r)
+        d2h = sum(st["proof_bytes"] for r in res for st, _ in r)
+        assert all(st["ok"] == 1 for r in res for st, _ in r) and len(proofs) == len(seeds)
         if dist is not None:
-            gathered = gather_proofs(proofs[-1], device, dist)
-            assert len(gathered) == world and all(len(g) == len(proofs[-1]) for g in gathered)
+            gathered = gather_proofs(b"".join(proofs), device, dist)
+            assert len(gathered) == world and all(len(g) == sum(map(len, proofs)) for g in gathered)
         barrier()
         t_e2e = time.perf_counter() - t0
     # max over ranks
@@ -217,50 +274,66 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        dom = max(prof, key=lambda k: prof[k]["ms"])
         notes = {
-            "msm": "integer-ALU bound by construction (one 7M+4S mixed addition, ~3500 IMAD.WIDE, per 32-byte scalar): the HBM fraction is reported "
-                   "because the metric asks for it; see DESIGN.md section 4 for the multiplier-pipe view",
-            "fold": "HBM-streaming sumcheck rounds (>= 32 MiB per launch): k_round_quad_tma and the first round of each phase (k_round_quad)",
+            "msm": "integer-ALU bound by construction (one mixed point addition = 11 Fp multiplications = ~3500 IMAD.WIDE per 32-byte scalar): the HBM "
+                   "fraction is reported because the metric asks for it; alu_frac = measured Fp multiplications of the class / device time / the Fp "
+                   "multiplier rate measured in this run (microbench.fp_mul)",
+            "fold": "HBM-streaming sumcheck rounds (>= 32 MiB per launch): k_round_quad_tma / k_round_cubic_tma and the first round of each phase",
             "fold_small": "sumcheck rounds on tables < 32 MiB: bound by launch + reduction latency, not by HBM",
             "gates": "gather-reduce over the gate lists (random 32-byte reads)",
+            "dense": "dense passes of the FFT-convolution path (K4b / K5b), layer-0 gathers and the input-layer scatter (K6)",
         }
         ncu = {}
         try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_dram_bytes.json")))
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_dram_bytes.json")))
         except Exception:
             pass
-        def roof(name):
-            p = prof[name]
-            ach = p["bytes"] / 1e9 / (p["ms"] / 1e3) if p["ms"] > 0 else 0.0
-            r = {"bound": "hbm", "kernel_class": name, "achieved": round(ach, 2), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                 "frac": round(ach / peak, 4), "traffic": None, "launches": p["launches"], "device_ms": round(p["ms"], 3),
-                 "algorithmic_bytes": p["bytes"]}
-            if name in notes:
-                r["note"] = notes[name]
-            return r
         micro = {}
         with zkcnn_b200.context(local) as c:
             ms = c.bench_fold(24, 10, True)
             micro["fold_2^24"] = {"kernel": "k_round_quad_tma", "ms": round(ms, 4), "algorithmic_bytes": 96 * (1 << 24), "GB/s": round(96 * (1 << 24) / 1e9 / (ms / 1e3), 1),
                                   "frac": round(96 * (1 << 24) / 1e9 / (ms / 1e3) / peak, 4), "traffic": ncu.get("k_round_quad_tma_2^24")}
-            ms = c.bench_msm(12, 12, 2, 2)
+            if hasattr(c, "bench_cubic"):
+                ms = c.bench_cubic(24, 7, 10)
+                micro["cubic_fold_2^24"] = {"kernel": "k_round_cubic_tma", "ms": round(ms, 4), "algorithmic_bytes": 96 * (1 << 24), "GB/s": round(96 * (1 << 24) / 1e9 / (ms / 1e3), 1),
+                                            "frac": round(96 * (1 << 24) / 1e9 / (ms / 1e3) / peak, 4), "traffic": ncu.get("k_round_cubic_tma_2^24"),
+                                            "note": "V_mult[0] live over the whole table (batched activations as large as the weights): 4 folds + 3 products per output pair"}
             b = 32 * (1 << 24) + 96 * 4096 + 144 * 4096
-            micro["msm_4096x4096_witness_like"] = {"ms": round(ms, 3), "GB/s": round(b / 1e9 / (ms / 1e3), 2), "frac": round(b / 1e9 / (ms / 1e3) / peak, 5)}
+            for name, mix in (("msm_4096x4096_witness_like", 2), ("msm_4096x4096_uniform_fr", 0)):
+                ms = c.bench_msm(12, 12, mix, 2)
+                micro[name] = {"ms": round(ms, 3), "GB/s": round(b / 1e9 / (ms / 1e3), 2), "frac": round(b / 1e9 / (ms / 1e3) / peak, 5), "Mscalars/s": round((1 << 24) / ms / 1e3, 1)}
+            if hasattr(c, "bench_fp_mul"):
+                micro["fp_mul"] = {"G_mul_per_s": round(c.bench_fp_mul(), 2), "note": "Fp (381-bit) Montgomery multiplications, all SMs busy: the ALU-side peak of the MSM kernels"}
+
+        def roof(name):
+            p = prof[name]
+            ach = p["bytes"] / 1e9 / (p["ms"] / 1e3) if p["ms"] > 0 else 0.0
+            r = {"bound": "alu" if name == "msm" else "latency" if name in ("fold_small", "other") else "hbm", "kernel_class": name, "achieved": round(ach, 2), "peak": peak,
+                 "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu.get("class_" + name), "launches": p["launches"],
+                 "device_ms": round(p["ms"], 3), "algorithmic_bytes": p["bytes"]}
+            if name in notes:
+                r["note"] = notes[name]
+            return r
+        dom = max(prof, key=lambda k: prof[k]["ms"])
+        P = args.steps * world
         line = {
-            "metric": METRIC, "value": round(args.steps * world / t_value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(t_value / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC if model == "vgg11" and pics == 1 else f"{model}_p{pics}_proofs_per_sec", "value": round(P / t_value, 4), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": round(t_value / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "vgg11 CIFAR pic_cnt=1, one proof per step per GPU (BASELINE config 3/4)" if model == "vgg11" else model,
+            "config": {"workload": (f"{model} CIFAR pic_cnt={pics}, one proof per step per GPU" + (" (BASELINE config 3/4)" if model == "vgg11" and pics == 1 else
+                                    " (BASELINE config 5: batched pictures, FFT-convolution path)" if pics > 1 else "")),
                        "arithmetic": "exact modular integer arithmetic on 32-bit limbs: BLS12-381 Fr (255-bit) and Fp (381-bit) in Montgomery form",
-                       "network": config, "input_layer": st0["input_size"], "layers": st0["n_layers"], "generators": "non-degenerate (G * challenge)",
+                       "network": config, "pictures_per_proof": pics, "input_layer": st0["input_size"], "layers": st0["n_layers"], "generators": "non-degenerate (G * challenge)",
+                       "proofs_in_flight_per_gpu": M,
                        "rounds": "one device call per sumcheck round" if args.round_by_round else "one device call per sumcheck phase (challenges of a phase are drawn before its rounds, as in src/verifier.cpp:156-160)",
-                       "l2": "tables larger than L2 (2^24 x 32 B witness, 537 MB)", "parallelism": f"one proof per GPU x{world}, final all-gather of proofs",
+                       "l2": "tables larger than L2 (2^24 x 32 B witness, 537 MB)", "parallelism": f"one proof stream per GPU x{world} ({M} provers in flight each, distinct pictures), final all-gather of all K proofs of every rank",
                        "timer": "host clock around synchronous API calls, barrier + cuda synchronize on both sides; value and e2e un-instrumented; per-kernel-class device "
-                                "times from a second pass of the same K proofs with CUDA events around every launch on the launching stream (profiled_ms_per_step)",
-                       "e2e_upload": "per step from pinned host memory, synchronous" if args.no_prefetch else "per step from pinned host memory, issued one step ahead on a copy stream (double-buffered witness)"},
-            "e2e": {"value": round(args.steps * world / t_e2e, 4), "unit": UNIT, "h2d_bytes_per_step": h2d // max(1, args.steps),
-                    "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": round(t_e2e / args.steps * 1e3, 3)},
+                                "times from a separate pass of K proofs on one prover with CUDA events around every launch on the launching stream (profiled_ms_per_step)",
+                       "e2e_upload": ("per step from pinned host memory, synchronous" if args.no_prefetch else "per step from pinned host memory, issued one step ahead on a copy stream (double-buffered witness)")
+                                     + "; the witness of a picture is built on the host outside the timed region (host_build_s per picture: see SURVEY section 8 f-1)"},
+            "e2e": {"value": round(P / t_e2e, 4), "unit": UNIT, "h2d_bytes_per_step": h2d // max(1, args.steps),
+                    "d2h_bytes_per_step": d2h // max(1, args.steps), "ms_per_step": round(t_e2e / args.steps * 1e3, 3), "host_build_s_per_picture_not_included": round(build_s / pics, 2)},
+            "pictures_per_s": round(P * pics / t_value, 3),
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": roof(dom),
@@ -268,13 +341,14 @@ def run_ours(args):
             "profiled_ms_per_step": round(t_prof / args.steps * 1e3, 3),
             "kernels": {k: roof(k) for k in prof if prof[k]["launches"]},
             "microbench": micro,
-            "parity": {"verified": True, "transcript_matches_reference_golden": parity},
+            "parity": parity,
             "host_build_s": round(build_s, 2),
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(model, config, bounded=True)
+            line["cpu_baseline"] = cpu_baseline(model, config, pics, bounded=True)
         print(json.dumps(line), flush=True)
-    s.close()
+    for s in sessions:
+        s.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -290,16 +364,16 @@ def write_input(model, config, path):
     if model == "lenet":
         gen.write_text(gen.generate("lenet"), path)
         return ["lenet", path, "x"]
-    gen.write_text(gen.generate("vgg11", config=None if model == "vgg11" else config), path)
+    gen.write_text(gen.generate("vgg11", config=config), path)
     open(path + ".config", "w").write(config + "\n")
     return ["vgg", path, "x", path + ".config"]
 
 
-def run_reference_once(cmd, procs):
+def run_reference_once(cmd, procs, pics=1):
     """`procs` independent single-threaded reference provers side by side (the reference has no threads);
     returns (proofs, seconds of prover time per proof as the reference counts it, wall seconds)"""
     t0 = time.perf_counter()
-    ps = [subprocess.Popen(cmd + ["1", str(100 + i)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i in range(procs)]
+    ps = [subprocess.Popen(cmd + [str(pics), str(100 + i)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i in range(procs)]
     outs = [p.communicate()[0] for p in ps]
     wall = time.perf_counter() - t0
     prover_s, verify_wall = [], []
@@ -314,7 +388,7 @@ def run_reference_once(cmd, procs):
     return procs, max(prover_s), max(verify_wall), wall
 
 
-def cpu_baseline(model, config, bounded=True):
+def cpu_baseline(model, config, pics=1, bounded=True):
     """reference CPU prover on this box's host cores: the unmodified reference compiled from /root/reference
     (oracle/_ref/ref_run) on the same synthetic input.  Bounded sample: one proof on one core."""
     ref = ref_binary()
@@ -322,10 +396,10 @@ def cpu_baseline(model, config, bounded=True):
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ref_run not present in this snapshot"}
     path = f"/tmp/zkcnn_bench_{model}_{os.getpid()}.csv"
     cmd = [ref] + write_input(model, config, path)
-    n, prover_s, verify_wall, wall = run_reference_once(cmd, 1)
+    n, prover_s, verify_wall, wall = run_reference_once(cmd, 1, pics)
     os.remove(path)
     return {"value": round(1.0 / prover_s, 5), "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": f"1 full {model} proof, 1 thread (the reference is single-threaded): prover {prover_s:.1f} s (PT + poly PT as the reference "
+            "sample": f"1 full {model} pic_cnt={pics} proof, 1 thread (the reference is single-threaded): prover {prover_s:.1f} s (PT + poly PT as the reference "
                       f"counts them, degenerate generators) inside a {verify_wall:.1f} s commit+prove+verify loop; {os.cpu_count()} host cores visible"}
 
 
@@ -334,8 +408,8 @@ def run_reference(args):
     if rank != 0:
         return
     ref = ref_binary()
-    model = args.model
-    config = VGG11 if model == "vgg11" else args.network
+    model, pics = args.model, args.pics
+    config = NETWORKS.get(model, args.network)
     if ref is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_run (the reference compiled by oracle/Makefile) is not in this snapshot"}))
         return
@@ -345,14 +419,14 @@ def run_reference(args):
         avail_gb = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) / 1e6
     except Exception:
         avail_gb = 32
-    per = 10 if model == "vgg11" else 1
+    per = 1 if model == "lenet" else (10 if model == "vgg11" else 14) * (1 if pics == 1 else 1.3 * pics)   # GB of RSS per reference process (measured)
     procs = max(1, min(cores, int(avail_gb * 0.7 / per)))
     path = f"/tmp/zkcnn_bench_ref_{os.getpid()}.csv"
     cmd = [ref] + write_input(model, config, path)
     budget_s = 240.0
     steps_done, total_wall, total_proofs, prover_s, spent = 0, 0.0, 0, 0.0, 0.0
     for k in range(args.steps):           # no warm-up batches: a CPU prover has no warm-up effect worth 90 s each
-        n, ps, vw, wall = run_reference_once(cmd, procs)
+        n, ps, vw, wall = run_reference_once(cmd, procs, pics)
         steps_done += 1
         total_wall += ps                  # prover seconds as the reference counts them (PT + poly PT), slowest process of the batch
         total_proofs += n
@@ -363,10 +437,11 @@ def run_reference(args):
     os.remove(path)
     value = total_proofs / total_wall
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done, "warmup": 0,
+        "impl": "reference", "metric": METRIC if model == "vgg11" and pics == 1 else f"{model}_p{pics}_proofs_per_sec", "value": round(value, 5), "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done, "warmup": 0,
         "ms_per_step": round(total_wall / steps_done * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "vgg11 CIFAR pic_cnt=1" if model == "vgg11" else model, "network": config,
+        "config": {"workload": (f"{model} CIFAR pic_cnt={pics}, one proof per step per GPU" + (" (BASELINE config 3/4)" if model == "vgg11" and pics == 1 else
+                                " (BASELINE config 5: batched pictures, FFT-convolution path)" if pics > 1 else "")), "network": config, "pictures_per_proof": pics,
                    "note": f"each step = {procs} independent reference provers in parallel (one per host thread, memory-bounded); time = the reference's own prover "
                            f"seconds (PT + poly PT, slowest process of a batch), circuit construction and verifier work excluded; the reference's generators are degenerate "
                            f"(all infinity), which makes its MSM 13-37x cheaper than ours (SURVEY.md App. E.1); bounded to ~{int(budget_s)} s"},
@@ -382,7 +457,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--model", default="vgg11", choices=["vgg11", "vgg", "lenet"])
+    ap.add_argument("--model", default="vgg11", choices=["vgg11", "vgg16", "vgg", "lenet"])
+    ap.add_argument("--pics", type=int, default=1, help="pictures per proof (pic_cnt); > 1 switches the convolutions to the FFT path (BASELINE config 5)")
+    ap.add_argument("--inflight", type=int, default=2, help="independent provers (own context, stream and witness) per GPU, each on its own host thread")
     ap.add_argument("--network", default=VGG11)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: upload each witness at the start of its own proof (no overlap)")

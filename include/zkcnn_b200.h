@@ -183,6 +183,10 @@ int zk_selftest(zk_ctx *ctx, uint64_t seed, uint32_t n);
 /* ---- device-timed micro-benchmarks (CUDA events on the launching stream; inputs resident in HBM) ------------------ */
 /* one K1 round on a table pair of 2^bits entries, `iters` launches; returns average ms per launch in *ms */
 int zk_bench_fold(zk_ctx *ctx, uint32_t bits, uint32_t iters, int fold, float *ms);
+/* one K2 (cubic) fold round on tables of 2^bits entries with V_mult[0] live over the first 2^live0_bits and a multiplier of 2^m_bits entries */
+int zk_bench_cubic(zk_ctx *ctx, uint32_t bits, uint32_t live0_bits, uint32_t m_bits, uint32_t iters, float *ms);
+/* sustained Fr (is_fp = 0) / Fp (is_fp = 1) Montgomery multiplications per second with every SM busy, in 10^9 per second: the ALU-side peak */
+int zk_bench_field_mul(zk_ctx *ctx, int is_fp, float *gmul_per_s);
 int zk_bench_msm(zk_ctx *ctx, uint32_t log_rows, uint32_t log_cols, int scalar_mix, uint32_t iters, float *ms);
 
 #ifdef __cplusplus

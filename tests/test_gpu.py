@@ -105,6 +105,36 @@ def test_transcripts(gpu_host, synthetic_inputs, mnist_input, model, net, pics, 
     assert st["gpu_launches"] > 100
 
 
+def test_proofs_in_flight_on_one_gpu(gpu_host, synthetic_inputs, mnist_input):
+    """three provers (own context, stream, witness, challenge stream) driven from three host threads on one GPU, several proofs each:
+    every transcript must be the golden one of its (input, seed) whatever the interleaving of the kernels"""
+    import threading
+    jobs = [("lenet", "", 1, mnist_input, 1, 0, "lenet_p1_seed1"),
+            ("lenet", "", 2, synthetic_inputs["lenet_syn"], 4, 0, "lenet_syn_p2_seed4"),
+            ("vgg", synthetic_inputs["smallvgg_config"], 1, synthetic_inputs["smallvgg"], 8, REAL_GENERATORS | PROVER_ONLY, "smallvgg_p1_seed8_realgens")]
+    errors = []
+
+    def work(model, net, pics, inp, seed, flags, golden):
+        try:
+            want = open(os.path.join(GOLDEN, golden + ".transcript.bin"), "rb").read()
+            with Session(gpu_host, model, net, pics) as s:
+                s.input_file(inp)
+                s.build()
+                for k in range(4):
+                    st = s.prove(seed, flags | (WITNESS_RESIDENT if k else 0))
+                    assert s.proof() == want, golden
+                    assert st["ok"] == 1 or flags & REAL_GENERATORS
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+
+
 def test_against_the_reference_run_here(gpu_host, synthetic_inputs, tmp_path):
     """a seed no golden file holds: the compiled reference (oracle/_ref/ref_run, built from /root/reference by
     oracle/Makefile) proves on this box's CPU and the GPU transcript must be byte-identical"""

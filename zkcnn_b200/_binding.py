@@ -100,6 +100,8 @@ class Lib:
         d.zk_g1_fixed_base_mul.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint64, _u64p]
         d.zk_selftest.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
         d.zk_bench_fold.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
+        d.zk_bench_cubic.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+        d.zk_bench_field_mul.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         d.zk_bench_msm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_float)]
         d.zk_poly_create.argtypes = [C.c_void_p, _u64p, C.c_uint64, _u64p, C.c_uint32]
         d.zk_poly_commit.argtypes = [C.c_void_p, _u64p, C.c_uint32]
@@ -227,6 +229,16 @@ class Context:
         ms = C.c_float(0)
         self._check(self.lib.dll.zk_bench_fold(self.h, bits, iters, int(fold), C.byref(ms)), "zk_bench_fold")
         return ms.value
+
+    def bench_cubic(self, bits, m_bits=7, iters=10, live0_bits=None):
+        ms = C.c_float(0)
+        self._check(self.lib.dll.zk_bench_cubic(self.h, bits, bits if live0_bits is None else live0_bits, m_bits, iters, C.byref(ms)), "zk_bench_cubic")
+        return ms.value
+
+    def bench_fp_mul(self, fp=True):
+        g = C.c_float(0)
+        self._check(self.lib.dll.zk_bench_field_mul(self.h, int(fp), C.byref(g)), "zk_bench_field_mul")
+        return g.value
 
     def bench_msm(self, log_rows, log_cols, scalar_mix=2, iters=3):
         ms = C.c_float(0)

@@ -36,17 +36,20 @@ zk_ctx *zk_ctx_create(int device) {
 
 void zk_ctx_destroy(zk_ctx *ctx) {
     if (!ctx) return;
-    try { rt::set_device(ctx->device); rt::sync(ctx->stream); } catch (...) {}
+    zk_stream_t s0 = ctx->stream, s1 = ctx->aux_stream, s2 = ctx->copy_stream;
+    try { rt::set_device(ctx->device); } catch (...) {}
+    for (zk_stream_t s : {s2, s1, s0})
+        if (s) { try { rt::sync(s); } catch (...) {} }
+    rt::unbind();   // everything is synchronised: the buffers freed below need no fence (and the streams are about to go)
     rt::hfree_pinned(ctx->h_out);
     rt::hfree_pinned(ctx->res_h);
     if (ctx->batch_h) rt::hfree_pinned(ctx->batch_h);
     if (ctx->stage_h) rt::hfree_pinned(ctx->stage_h);
     for (auto &r : ctx->prof_pending) { rt::event_destroy(r.a); rt::event_destroy(r.b); }
     for (auto e : ctx->prof_pool) rt::event_destroy(e);
-    if (ctx->copy_stream) { try { rt::sync(ctx->copy_stream); } catch (...) {} rt::stream_destroy(ctx->copy_stream); }
-    if (ctx->aux_stream) { try { rt::sync(ctx->aux_stream); } catch (...) {} rt::stream_destroy(ctx->aux_stream); }
-    rt::stream_destroy(ctx->stream);
     delete ctx;
+    for (zk_stream_t s : {s2, s1, s0})
+        if (s) rt::stream_destroy(s);
 }
 
 uint64_t zk_ctx_launch_count(const zk_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -70,7 +73,7 @@ int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
 int zk_profile_enable(zk_ctx *ctx, int on) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx, "null ctx");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     rt::sync(ctx->stream);
     prof_resolve(ctx);
     for (int c = 0; c < ZK_PROF_CLASSES; ++c) { ctx->prof_ms[c] = 0; ctx->prof_launches[c] = 0; ctx->prof_bytes[c] = 0; }
@@ -81,7 +84,7 @@ int zk_profile_enable(zk_ctx *ctx, int on) {
 int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_t *bytes) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && cls >= 0 && cls < ZK_PROF_CLASSES, "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     rt::sync(ctx->stream);
     prof_resolve(ctx);
     if (ms) *ms = ctx->prof_ms[cls];
@@ -109,7 +112,7 @@ int zk_circuit_begin(zk_ctx *ctx, uint32_t n_layers, const uint64_t *two_mul, ui
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && n_layers >= 2 && n_layers <= 255, "bad layer count");
     ZK_REQUIRE(two_mul && n_two_mul >= 1 && n_two_mul <= 512, "bad two_mul table");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     ctx->layers.clear();
     ctx->layers.resize(n_layers);
     ctx->n_layers = n_layers;
@@ -125,7 +128,7 @@ int zk_circuit_begin(zk_ctx *ctx, uint32_t n_layers, const uint64_t *two_mul, ui
 int zk_circuit_layer(zk_ctx *ctx, uint32_t id, const zk_layer_desc *D) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && D && id < ctx->n_layers, "bad layer id");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     layer_t &L = ctx->layers[id];
     L.d = *D;
     L.d.uni_gates = nullptr; L.d.bin_gates = nullptr; L.d.ori_id_u = nullptr; L.d.ori_id_v = nullptr;
@@ -158,7 +161,7 @@ int zk_circuit_end(zk_ctx *ctx) {
 int zk_witness_layer(zk_ctx *ctx, uint32_t id, const uint64_t *val, uint64_t n) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && id < ctx->n_layers && (val || n == 0), "bad witness layer");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     layer_t &L = ctx->layers[id];
     // layer 0 is kept zero-padded to a power of two so that Hyrax can alias it (src/prover.cpp:504-508)
     uint64_t cap = n;
@@ -176,7 +179,7 @@ int zk_witness_layer(zk_ctx *ctx, uint32_t id, const uint64_t *val, uint64_t n) 
 int zk_witness_layer_prefetch(zk_ctx *ctx, uint32_t id, const uint64_t *val, uint64_t n) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && id < ctx->n_layers && (val || n == 0), "bad witness layer");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     if (!ctx->copy_stream) ctx->copy_stream = rt::stream_create(false);
     layer_t &L = ctx->layers[id];
     uint64_t cap = n;
@@ -226,7 +229,7 @@ int zk_witness_layer_compact(zk_ctx *ctx, uint32_t id, const int64_t *small, uin
                              uint32_t n_wide, int prefetch) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && id < ctx->n_layers && (small || n == 0) && (n_wide == 0 || (wide_idx && wide_val)), "bad witness layer");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     if (prefetch && !ctx->copy_stream) ctx->copy_stream = rt::stream_create(false);
     zk_stream_t strm = prefetch ? ctx->copy_stream : ctx->stream;
     layer_t &L = ctx->layers[id];
@@ -276,7 +279,7 @@ int zk_witness_layer_compact(zk_ctx *ctx, uint32_t id, const int64_t *small, uin
 int zk_witness_commit_prefetch(zk_ctx *ctx) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx, "null ctx");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     if (ctx->copy_stream) rt::sync(ctx->copy_stream);
     rt::sync(ctx->stream);
     for (auto &L : ctx->layers)
@@ -300,7 +303,7 @@ int zk_prover_init(zk_ctx *ctx) {   // prover::init, src/prover.cpp:17-21
 int zk_vres(zk_ctx *ctx, const uint64_t *r, uint32_t output_size, uint32_t r_size, uint64_t *out) {   // src/prover.cpp:434-457
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && ctx->circuit_ready && out, "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     layer_t &L = ctx->layers[ctx->n_layers - 1];
     ZK_REQUIRE(output_size <= L.n_val && r_size <= 24 && (r || r_size == 0), "bad output size");
     ensure_round_scratch(ctx);
@@ -338,7 +341,7 @@ int zk_sumcheck_init(zk_ctx *ctx, const uint64_t *alpha, const uint64_t *beta) {
 int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/prover.cpp:155-239
     ZK_API_BEGIN
     layer_t &L = cur_layer(ctx);
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const zk_layer_desc &d = L.d;
     const uint32_t id = ctx->sumcheck_id;
     ZK_REQUIRE(id >= 1 && d.ty != ZK_LAYER_DOT_PROD, "wrong init for this layer");
@@ -373,15 +376,8 @@ int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/
         ZK_REQUIRE(P.exists && d.size_u[1] == P.n_eval, "unexpected FFT layer shape");
         ZK_REQUIRE(((uint64_t) cnt_len << d.max_bl_u) <= prev.n_val, "FFT source layer too small");
         fr_t *V = table_init_buf(P.v, P.n_eval);
-        const uint32_t n_u = P.n_eval;
-        uint32_t n_chunks = std::max(1u, std::min(cnt_len, (uint32_t) ((ZK_SM_COUNT * 8 * kBlock) / std::max(1u, n_u))));
-        const uint32_t g_per_chunk = (cnt_len + n_chunks - 1) / n_chunks;
-        n_chunks = (cnt_len + g_per_chunk - 1) / g_per_chunk;
-        ctx->dense_partial.ensure((size_t) n_chunks * n_u * sizeof(fr_t));
-        ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, ((uint64_t) cnt_len << d.max_bl_u) * 32 + (uint64_t) cnt_len * 32, k_dense_colsum, dim3((n_u + kBlock - 1) / kBlock, n_chunks), dim3(kBlock), 0, prev.val.as<fr_t>(),
-                   ctx->beta_g.as<fr_t>(), n_u, (uint32_t) d.max_bl_u, cnt_len, g_per_chunk, ctx->dense_partial.as<fr_t>());
-        ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, (uint64_t) (n_chunks + 1) * n_u * 32, k_colsum_finish, dim3((n_u + kBlock - 1) / kBlock), dim3(kBlock), 0, ctx->dense_partial.as<fr_t>(), n_u,
-                   n_chunks, V);
+        ZK_REQUIRE(P.n_eval == (1u << d.max_bl_u), "unexpected FFT layer shape");
+        dense_colsum(ctx, prev.val.as<fr_t>(), ctx->beta_g.as<fr_t>(), (uint32_t) d.max_bl_u, cnt_len, V);
         // mult_array[1] = phiGInit(r_0, scale)
         fr_t *M = table_init_buf(P.m, P.n_eval);
         ZK_REQUIRE(r0.size() >= fft_bl - (is_fft ? 0 : 1), "r_0 too short for phi table");
@@ -443,7 +439,7 @@ int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/
 int zk_sumcheck_init_phase2(zk_ctx *ctx) {   // src/prover.cpp:241-310
     ZK_API_BEGIN
     layer_t &L = cur_layer(ctx);
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const zk_layer_desc &d = L.d;
     const uint32_t id = ctx->sumcheck_id;
     ZK_REQUIRE(id >= 1 && d.need_phase2, "layer has no phase 2");
@@ -522,7 +518,7 @@ int zk_sumcheck_init_phase2(zk_ctx *ctx) {   // src/prover.cpp:241-310
 
 static int sumcheck_update(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *abc, std::vector<fr_t> &r_arr) {   // src/prover.cpp:368-383
     ZK_API_BEGIN
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const fr_t prev = fr_load(prev_p);
     if (ctx->round) {
         ZK_REQUIRE(ctx->round - 1 < r_arr.size(), "too many rounds");
@@ -552,7 +548,7 @@ int zk_sumcheck_update2(zk_ctx *ctx, const uint64_t *prev, uint64_t *abc) {
 int zk_sumcheck_update_batch(zk_ctx *ctx, int which, const uint64_t *prevs_p, uint32_t n_rounds, uint64_t *abc) {
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && ctx->circuit_ready && prevs_p && abc && n_rounds >= 1 && which >= 0 && which <= 2, "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     std::vector<fr_t> prevs(n_rounds);
     for (uint32_t j = 0; j < n_rounds; ++j) prevs[j] = fr_load(prevs_p + 4 * j);
     if (which == 0) {
@@ -582,7 +578,7 @@ int zk_sumcheck_update_batch(zk_ctx *ctx, int which, const uint64_t *prevs_p, ui
 int zk_sumcheck_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_0, uint64_t *claim_1) {   // src/prover.cpp:459-471
     ZK_API_BEGIN
     cur_layer(ctx);
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const fr_t prev = fr_load(prev_p);
     std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
     ZK_REQUIRE(ctx->round >= 1 && ctx->round - 1 < ru.size(), "finalize without rounds");
@@ -600,7 +596,7 @@ int zk_sumcheck_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_0
 int zk_sumcheck_finalize2(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_0, uint64_t *claim_1) {   // src/prover.cpp:473-485
     ZK_API_BEGIN
     cur_layer(ctx);
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const fr_t prev = fr_load(prev_p);
     std::vector<fr_t> &rv = ctx->r_v[ctx->sumcheck_id];
     ZK_REQUIRE(ctx->round >= 1 && ctx->round - 1 < rv.size(), "finalize without rounds");
@@ -617,7 +613,7 @@ int zk_sumcheck_finalize2(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_0
 int zk_sumcheck_dotprod_init_phase1(zk_ctx *ctx) {   // src/prover.cpp:57-95
     ZK_API_BEGIN
     layer_t &L = cur_layer(ctx);
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const zk_layer_desc &d = L.d;
     const uint32_t id = ctx->sumcheck_id;
     ZK_REQUIRE(id >= 1 && d.ty == ZK_LAYER_DOT_PROD, "not a DOT_PROD layer");
@@ -743,7 +739,7 @@ static void cubic_round_launch(zk_ctx *ctx, const fr_t &prev, fr_t *slot_d) {
 int zk_sumcheck_dotprod_update1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *abcd) {   // src/prover.cpp:103-144
     ZK_API_BEGIN
     cur_layer(ctx);
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const fr_t prev = fr_load(prev_p);
     std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
     if (ctx->round) {
@@ -762,7 +758,7 @@ int zk_sumcheck_dotprod_update_batch(zk_ctx *ctx, const uint64_t *prevs_p, uint3
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && prevs_p && abcd && n_rounds >= 1, "bad arguments");
     cur_layer(ctx);
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
     ZK_REQUIRE(ctx->round == 0 && n_rounds <= ru.size() + 1, "bad state");
     ensure_round_scratch(ctx);
@@ -790,7 +786,7 @@ int zk_cubic_rounds(zk_ctx *ctx, const uint64_t *mult, uint32_t m_bits, const ui
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && mult && V0 && V1 && polys && bits >= 1 && bits <= 28 && m_bits <= 12 && m_bits <= bits && n_rounds >= 1 && n_rounds <= bits &&
                    live0 <= live1 && live1 <= (1ull << bits) && live1 >= 1 && (r || n_rounds == 1), "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     pair_t &P = ctx->pair[1];
     pair_reset(ctx->pair[0], -1, 0);
     pair_reset(P, (int8_t) bits, (uint32_t) live1);
@@ -814,10 +810,71 @@ int zk_cubic_rounds(zk_ctx *ctx, const uint64_t *mult, uint32_t m_bits, const ui
     ZK_API_END
 }
 
+// ---- micro-benchmarks of the K2 kernels and of the field multiplier (CUDA events on the launching stream) -------------------------
+// sustained Fp (is_fp != 0) or Fr multiplications per second, in units of 10^9
+int zk_bench_field_mul(zk_ctx *ctx, int is_fp, float *gmul_per_s) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && gmul_per_s, "bad arguments");
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
+    const uint32_t grid = ZK_SM_COUNT * 8, iters = 2000;
+    rt::dbuf out;
+    out.ensure((size_t) grid * kBlock * sizeof(fp_t));
+    rt::event_t e0 = rt::event_create(), e1 = rt::event_create();
+    for (int pass = 0; pass < 2; ++pass) {   // pass 0 warms up
+        rt::event_record(e0, ctx->stream);
+        if (is_fp) ZK_KLAUNCH(ctx, k_mul_chain<fp_t>, dim3(grid), dim3(kBlock), 0, out.as<fp_t>(), iters, 7ull);
+        else ZK_KLAUNCH(ctx, k_mul_chain<fr_t>, dim3(grid), dim3(kBlock), 0, out.as<fr_t>(), iters, 7ull);
+        rt::event_record(e1, ctx->stream);
+        rt::event_sync(e1);
+    }
+    *gmul_per_s = (float) ((double) grid * kBlock * iters * 2 / (rt::event_elapsed_ms(e0, e1) * 1e-3) / 1e9);
+    rt::event_destroy(e0);
+    rt::event_destroy(e1);
+    ZK_API_END
+}
+
+// one K2 fold round on tables of 2^bits entries (V_mult[0] live over the first 2^live0_bits), multiplier period 2^m_bits
+int zk_bench_cubic(zk_ctx *ctx, uint32_t bits, uint32_t live0_bits, uint32_t m_bits, uint32_t iters, float *ms) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && ms && bits >= 3 && bits <= 27 && live0_bits <= bits && m_bits >= 1 && m_bits <= 12 && m_bits < bits && iters >= 1, "bad arguments");
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
+    const uint64_t n = 1ull << bits;
+    pair_t &P = ctx->pair[1];
+    pair_reset(ctx->pair[0], -1, 0);
+    rt::event_t e0 = rt::event_create(), e1 = rt::event_create();
+    float total = 0;
+    for (uint32_t i = 0; i <= iters; ++i) {   // iteration 0 warms up; every iteration starts from fresh full-size tables
+        pair_reset(P, (int8_t) bits, (uint32_t) n);
+        fr_t *dv1 = table_init_buf(P.v, n), *dv0 = table_init_buf(P.m, n);
+        if (i == 0) {
+            ZK_KLAUNCH(ctx, k_fill_synthetic, dim3(grid_for(n)), dim3(kBlock), 0, dv1, n, 0x9E3779B97F4A7C15ULL, 0);
+            ZK_KLAUNCH(ctx, k_fill_synthetic, dim3(grid_for(n)), dim3(kBlock), 0, dv0, n, 0x243F6A8885A308D3ULL, 0);
+        }
+        ctx->mdp_n = 1u << m_bits;
+        fr_t *dm = table_init_buf(ctx->mdp, ctx->mdp_n);
+        ctx->mdp.next = 0;
+        if (i == 0) ZK_KLAUNCH(ctx, k_fill_synthetic, dim3(grid_for(ctx->mdp_n)), dim3(kBlock), 0, dm, (uint64_t) ctx->mdp_n, 0x13198A2E03707344ULL, 0);
+        ctx->dp_live0 = 1u << live0_bits;
+        ctx->round = 2;   // a fold round (not the first of its phase)
+        ensure_round_scratch(ctx);
+        ctx->batch_res.ensure(16 * sizeof(fr_t));
+        rt::event_record(e0, ctx->stream);
+        cubic_round_launch(ctx, fr_t::from_u64(0x1234567887654321ULL), ctx->batch_res.as<fr_t>());
+        rt::event_record(e1, ctx->stream);
+        rt::event_sync(e1);
+        if (i) total += rt::event_elapsed_ms(e0, e1);
+    }
+    P.n_eval = 0;
+    *ms = total / iters;
+    rt::event_destroy(e0);
+    rt::event_destroy(e1);
+    ZK_API_END
+}
+
 int zk_sumcheck_dotprod_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_1) {   // src/prover.cpp:146-153
     ZK_API_BEGIN
     cur_layer(ctx);
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     ensure_round_scratch(ctx);
     const fr_t prev = fr_load(prev_p);
     std::vector<fr_t> &ru = ctx->r_u[ctx->sumcheck_id];
@@ -846,7 +903,7 @@ int zk_sumcheck_dotprod_finalize1(zk_ctx *ctx, const uint64_t *prev_p, uint64_t 
 int zk_sumcheck_liu_init(zk_ctx *ctx, const uint64_t *s_u, const uint64_t *s_v, uint32_t n) {   // src/prover.cpp:312-358
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && ctx->circuit_ready && !ctx->r_u.empty() && n + 1 >= ctx->n_layers, "bad state");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     ctx->sumcheck_id = 0;
     layer_t &L0 = ctx->layers[0];
     const zk_layer_desc &d0 = L0.d;
@@ -882,7 +939,7 @@ int zk_sumcheck_liu_init(zk_ctx *ctx, const uint64_t *s_u, const uint64_t *s_v, 
 int zk_sumcheck_liu_update(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *abc) {   // src/prover.cpp:385-394
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && ctx->circuit_ready && ctx->sumcheck_id == 0, "bad state");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const fr_t prev = fr_load(prev_p);
     ++ctx->round;
     fr_t ret[3];
@@ -894,7 +951,7 @@ int zk_sumcheck_liu_update(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *abc) {
 int zk_sumcheck_liu_finalize(zk_ctx *ctx, const uint64_t *prev_p, uint64_t *claim_1) {   // src/prover.cpp:487-497
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && ctx->circuit_ready && ctx->sumcheck_id == 0, "bad state");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const fr_t prev = fr_load(prev_p);
     ZK_REQUIRE(ctx->round >= 1 && ctx->round - 1 < ctx->r_u[0].size(), "finalize without rounds");
     ctx->r_u[0][ctx->round - 1] = prev;

@@ -16,12 +16,12 @@ static uint64_t fnv1a64(const void *p, size_t n) {
 
 static void msm_configure() {
 #if !defined(ZK_EMU)
-    static bool done = false;
-    if (!done) {
+    static const bool done = [] {   // (thread-safe: several contexts may start at once)
         rt::check(cudaFuncSetAttribute(k_msm_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(msm_smem_t)),
                   "cudaFuncSetAttribute(k_msm_window)");
-        done = true;
-    }
+        return true;
+    }();
+    (void) done;
 #endif
 }
 
@@ -145,7 +145,7 @@ extern "C" {
 int zk_poly_bind_input(zk_ctx *ctx, const uint64_t *gens, uint32_t n_gens) {   // src/prover.cpp:503-511
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && ctx->circuit_ready, "circuit not uploaded");
-    zk::rt::set_device(ctx->device);
+    zk::rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     zk::layer_t &L0 = ctx->layers[0];
     ZK_REQUIRE(L0.n_val >= L0.d.size && L0.val.p, "input layer witness missing");
     zk::hyrax_bind(ctx, L0.val.as<zk::fr_t>(), (uint32_t) L0.d.bit_length, gens, n_gens);
@@ -155,7 +155,7 @@ int zk_poly_bind_input(zk_ctx *ctx, const uint64_t *gens, uint32_t n_gens) {   /
 int zk_poly_create(zk_ctx *ctx, const uint64_t *Z, uint64_t n, const uint64_t *gens, uint32_t n_gens) {   // polyProver.cpp:12-17
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && Z && n >= 1, "bad arguments");
-    zk::rt::set_device(ctx->device);
+    zk::rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     uint32_t bl = 0;
     while ((1ull << bl) < n) ++bl;
     ZK_REQUIRE(bl <= 30, "polynomial too large");
@@ -171,7 +171,7 @@ int zk_poly_create(zk_ctx *ctx, const uint64_t *Z, uint64_t n, const uint64_t *g
 int zk_poly_commit(zk_ctx *ctx, uint64_t *comm_out, uint32_t n_out) {   // polyProver.cpp:19-34
     ZK_API_BEGIN
     ZK_REQUIRE(ctx && ctx->hy.bound && comm_out, "no polynomial bound");
-    zk::rt::set_device(ctx->device);
+    zk::rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     zk::hyrax_t &H = ctx->hy;
     const uint32_t rsize = 1u << H.r_bits, lsize = 1u << H.l_bits;
     ZK_REQUIRE(n_out == rsize, "commit: output must hold 2^(bl/2) points");
@@ -186,7 +186,7 @@ int zk_poly_evaluate(zk_ctx *ctx, const uint64_t *x, uint32_t n, uint64_t *out) 
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && ctx->hy.bound && out && n == ctx->hy.bit_length, "evaluate: wrong number of variables");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     hyrax_t &H = ctx->hy;
     ensure_round_scratch(ctx);
     std::vector<fr_t> xs(n);
@@ -210,7 +210,7 @@ int zk_poly_init_bullet_prove(zk_ctx *ctx, const uint64_t *lx, uint32_t n_lx, co
     ZK_REQUIRE(ctx && ctx->hy.bound, "no polynomial bound");
     hyrax_t &H = ctx->hy;
     ZK_REQUIRE(n_lx == H.l_bits && n_rx == H.r_bits && (lx || !n_lx) && (rx || !n_rx), "initBulletProve: split of the point does not match");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const uint32_t lsize = 1u << H.l_bits, rsize = 1u << H.r_bits;
     H.t.resize(n_lx);
     memcpy(H.t.data(), lx, (size_t) n_lx * 32);
@@ -225,14 +225,7 @@ int zk_poly_init_bullet_prove(zk_ctx *ctx, const uint64_t *lx, uint32_t n_lx, co
     // RZ[i] = sum_j R[j] * Z[j * lsize + i]
     H.a.ensure((size_t) lsize * sizeof(fr_t));
     H.a_next.ensure((size_t) lsize * sizeof(fr_t));
-    uint32_t n_chunks = std::max(1u, std::min(rsize, (uint32_t) ((ZK_SM_COUNT * 8 * kBlock) / lsize)));
-    const uint32_t per = (rsize + n_chunks - 1) / n_chunks;
-    n_chunks = (rsize + per - 1) / per;
-    ctx->dense_partial.ensure((size_t) n_chunks * lsize * sizeof(fr_t));
-    ZK_KLAUNCH_C(ctx, ZK_PROF_DENSE, ((uint64_t) rsize << H.l_bits) * 32, k_dense_colsum, dim3((lsize + kBlock - 1) / kBlock, n_chunks), dim3(kBlock), 0, H.Z, H.R.as<fr_t>(), lsize, H.l_bits,
-               rsize, per, ctx->dense_partial.as<fr_t>());
-    ZK_KLAUNCH(ctx, k_colsum_finish, dim3((lsize + kBlock - 1) / kBlock), dim3(kBlock), 0, ctx->dense_partial.as<fr_t>(), lsize, n_chunks,
-               H.a.as<fr_t>());
+    dense_colsum(ctx, H.Z, H.R.as<fr_t>(), H.l_bits, rsize, H.a.as<fr_t>());
     // bullet_g = gens  ->  coefficient vector of ones;  bullet_a = RZ;  scale = 1
     std::vector<fr_t> ones(lsize, fr_t::one());
     H.coef.ensure((size_t) lsize * sizeof(fr_t));
@@ -248,7 +241,7 @@ int zk_poly_bullet_prove(zk_ctx *ctx, uint64_t *lcomm, uint64_t *rcomm, uint64_t
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && ctx->hy.bound && ctx->hy.cur >= 2 && !ctx->hy.t.empty(), "bulletProve: nothing left to prove");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     hyrax_t &H = ctx->hy;
     ensure_round_scratch(ctx);
     const uint32_t lsize = 1u << H.l_bits, m = H.cur, h = m >> 1;
@@ -276,7 +269,7 @@ int zk_poly_bullet_update(zk_ctx *ctx, const uint64_t *randomness) {   // polyPr
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && ctx->hy.bound && ctx->hy.cur >= 2 && !ctx->hy.t.empty(), "bulletUpdate: nothing left to fold");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     hyrax_t &H = ctx->hy;
     const fr_t r = fr_load(randomness);
     const fr_t rinv = r.inverse();
@@ -297,7 +290,7 @@ int zk_poly_bullet_open(zk_ctx *ctx, uint64_t *out) {   // polyProver.cpp:111-11
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && ctx->hy.bound && ctx->hy.cur == 1 && out, "bulletOpen: folding not finished");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     ensure_round_scratch(ctx);
     rt::d2h(ctx->h_out, ctx->hy.a.p, sizeof(fr_t), ctx->stream);
     rt::sync(ctx->stream);
@@ -310,7 +303,7 @@ int zk_fr_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && a && b && out && op >= 0 && op <= 2 && n < (1ull << 31), "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     rt::dbuf da, db, dc;
     da.ensure(n * 32); db.ensure(n * 32); dc.ensure(n * 32);
     rt::h2d(da.p, a, n * 32, ctx->stream);
@@ -325,7 +318,7 @@ int zk_beta_table(zk_ctx *ctx, const uint64_t *r, uint32_t bits, const uint64_t 
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && (r || !bits) && init && out && bits <= 26, "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     std::vector<fr_t> rs(bits);
     memcpy(rs.data(), r, (size_t) bits * 32);
     rt::dbuf d;
@@ -341,7 +334,7 @@ int zk_phi_table(zk_ctx *ctx, const uint64_t *rx, const uint64_t *scale, uint32_
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && rx && scale && out && n >= 1 && n <= 20, "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const size_t entries = is_ifft ? (size_t) 1 << n : (size_t) 1 << (n - 1);
     rt::dbuf d;
     d.ensure(std::max<size_t>(2, entries) * sizeof(fr_t));
@@ -359,7 +352,7 @@ int zk_fold_rounds(zk_ctx *ctx, const uint64_t *V, const uint64_t *M, uint32_t b
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && V && M && polys && bits >= 1 && bits <= 28 && n_rounds >= 1 && n_rounds <= bits && live <= (1ull << bits), "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     pair_t &P = ctx->pair[1];
     pair_reset(ctx->pair[0], -1, 0);
     pair_reset(P, (int8_t) bits, (uint32_t) live);
@@ -386,7 +379,7 @@ int zk_msm(zk_ctx *ctx, const uint64_t *bases, const uint64_t *scalars, uint64_t
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && bases && scalars && out && n >= 1 && n <= (1u << 20) && n_rows >= 1, "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     hyrax_t H;   // private table: does not disturb a bound polynomial
     msm_prepare_table(ctx, H, bases, (uint32_t) n);
     rt::dbuf ds, dout;
@@ -403,7 +396,7 @@ int zk_g1_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && a && out && op >= 0 && op <= 2 && (b || op == 1) && n < (1ull << 24), "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     rt::dbuf da, db, dc;
     da.ensure(n * sizeof(g1_jac_t));
     dc.ensure(n * sizeof(g1_jac_t));
@@ -421,7 +414,7 @@ int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scal
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && base && scalars && out && n >= 1 && n < (1ull << 24), "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const uint64_t h = fnv1a64(base, sizeof(g1_jac_t));
     if (!ctx->fb_ready || ctx->fb_hash != h) {   // comb[w][d-1] = d * 2^(8w) * base
         rt::dbuf jb, ab, win, scr;
@@ -452,7 +445,7 @@ int zk_selftest(zk_ctx *ctx, uint64_t seed, uint32_t n) {
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && n >= 1, "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     rt::dbuf d;
     d.ensure(4);
     rt::dzero(d.p, 4, ctx->stream);
@@ -469,7 +462,7 @@ int zk_bench_fold(zk_ctx *ctx, uint32_t bits, uint32_t iters, int fold, float *m
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && ms && bits >= 2 && bits <= 28 && iters >= 1, "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     ensure_round_scratch(ctx);
     const uint64_t n = 1ull << bits;
     rt::dbuf v, m, vo, mo;
@@ -515,7 +508,7 @@ int zk_bench_msm(zk_ctx *ctx, uint32_t log_rows, uint32_t log_cols, int scalar_m
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && ms && log_rows <= 14 && log_cols >= 1 && log_cols <= 14 && iters >= 1 && (scalar_mix == 0 || scalar_mix == 2), "bad arguments");
-    rt::set_device(ctx->device);
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     const uint32_t rows = 1u << log_rows, cols = 1u << log_cols;
     // generators: (j + 1) * G
     std::vector<g1_jac_t> base(cols);

@@ -366,6 +366,20 @@ static void run_schedule(zk_ctx *ctx, const schedule_t &S, int phase, gate_args_
     }
 }
 
+// out[u] = sum_{g < n_g} val[(g << shift) | u] * weight[g] for u < 2^shift  (k_dense_colsum + k_colsum_finish)
+static void dense_colsum(zk_ctx *ctx, const fr_t *val, const fr_t *weight, uint32_t shift, uint64_t n_g, fr_t *out) {
+    const uint32_t n_u = 1u << shift;
+    const uint64_t total = n_g << shift;
+    // threads: a multiple of the column count (a thread keeps its column), at most 8 CTAs per SM, at least ~8 elements each
+    uint64_t T = std::max<uint64_t>(std::max<uint32_t>(n_u, kBlock), std::min<uint64_t>((uint64_t) ZK_SM_COUNT * 8 * kBlock, (total / 8 + n_u - 1) / n_u * n_u));
+    T = (T + std::max<uint32_t>(n_u, kBlock) - 1) / std::max<uint32_t>(n_u, kBlock) * std::max<uint32_t>(n_u, kBlock);
+    const uint32_t per_u = (uint32_t) (T / n_u);
+    ctx->dense_partial.ensure(T * sizeof(fr_t));
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, total * 32 + n_g * 32, k_dense_colsum, dim3((uint32_t) (T / kBlock)), dim3(kBlock), 0, val, weight, shift, total, ctx->dense_partial.as<fr_t>());
+    const uint32_t groups = (n_u + kBlock / 32 - 1) / (kBlock / 32);
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, T * 32 + (uint64_t) n_u * 32, k_colsum_finish, dim3(std::min<uint32_t>(groups, kMaxGridX)), dim3(kBlock), 0, ctx->dense_partial.as<fr_t>(), n_u, per_u, out);
+}
+
 static void pair_reset(pair_t &P, int8_t bit_length, uint32_t size) {
     P.exists = bit_length >= 0;
     P.poly_round = 0;

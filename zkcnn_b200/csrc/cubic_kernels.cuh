@@ -357,27 +357,45 @@ __global__ void __launch_bounds__(kBlock) k_dotprod_axpy(fr_t *out, const fr_t *
     }
 }
 
-// K4b: FFT/IFFT layers: V[u] = sum_g val[(g << shift) | u] * beta_g[g],  u < n_u  (src/prover.cpp:190-197).
-// grid = (u blocks, g chunks); partial[chunk][u], finished by k_colsum_finish.
-__global__ void __launch_bounds__(kBlock) k_dense_colsum(const fr_t *val, const fr_t *beta_g, uint32_t n_u, uint32_t shift, uint32_t cnt_len,
-                                                         uint32_t g_per_chunk, fr_t *partial) {
+// K4b: FFT/IFFT layers: V[u] = sum_g val[(g << shift) | u] * beta_g[g],  u < 2^shift  (src/prover.cpp:190-197); the same shape
+// is the R^T Z pass of the Hyrax opening (polyProver.cpp:66-68).  `val` is a row-major [n_g][2^shift] matrix, i.e. ONE linear
+// array: thread t of T (T a multiple of 2^shift, so a thread keeps its column) streams elements t, t + T, ... with unreduced
+// accumulation and leaves one partial sum; k_colsum_finish adds the T / 2^shift partials of a column with one warp per column
+// (columns can be as few as 16 while the rows number hundreds of thousands: a thread per column would add them one by one).
+__global__ void __launch_bounds__(kBlock) k_dense_colsum(const fr_t *val, const fr_t *beta_g, uint32_t shift, uint64_t total, fr_t *partial) {
     ZK_PDL_ENTRY();
-    const uint32_t u = blockIdx.x * kBlock + threadIdx.x;
-    if (u >= n_u) return;
-    const uint32_t g0 = blockIdx.y * g_per_chunk;
-    const uint32_t g1 = g0 + g_per_chunk < cnt_len ? g0 + g_per_chunk : cnt_len;
+    const uint64_t T = (uint64_t) gridDim.x * kBlock, t = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
     fr_lazy_t acc;
     acc.clear();
-    for (uint32_t g = g0; g < g1; ++g) acc.mac(ld_fr(val + (((size_t) g << shift) | u)), ld_fr(beta_g + g));
-    st_fr(partial + (size_t) blockIdx.y * n_u + u, g1 - g0 <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
+    uint32_t cnt = 0;
+    for (uint64_t i = t; i < total; i += T, ++cnt) acc.mac(ld_fr(val + i), ld_fr(beta_g + (i >> shift)));
+    st_fr(partial + t, cnt <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
 }
-__global__ void __launch_bounds__(kBlock) k_colsum_finish(const fr_t *partial, uint32_t n_u, uint32_t n_chunks, fr_t *out) {
+// out[u] = sum_k partial[u + k * n_u], k < per_u; one warp per column u
+__global__ void __launch_bounds__(kBlock) k_colsum_finish(const fr_t *partial, uint32_t n_u, uint32_t per_u, fr_t *out) {
     ZK_PDL_ENTRY();
-    const uint32_t u = blockIdx.x * kBlock + threadIdx.x;
-    if (u >= n_u) return;
-    fr_t acc = fr_t::zero();
-    for (uint32_t c = 0; c < n_chunks; ++c) acc = acc + ld_fr(partial + (size_t) c * n_u + u);
-    st_fr(out + u, acc);
+    const uint32_t lane = threadIdx.x & 31u, wpc = kBlock / 32;
+    const uint32_t n_groups = (n_u + wpc - 1) / wpc;
+    for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {   // CTA-uniform trip count: every lane takes part in the shuffles
+        const uint32_t u = grp * wpc + (threadIdx.x >> 5);
+        fr_t acc = fr_t::zero();
+        if (u < n_u) {
+            uint32_t k = lane;
+            for (; k + 96 < per_u; k += 128) {   // four independent loads in flight
+                const fr_t a = ld_fr(partial + u + (size_t) k * n_u), b = ld_fr(partial + u + (size_t) (k + 32) * n_u);
+                const fr_t c = ld_fr(partial + u + (size_t) (k + 64) * n_u), d = ld_fr(partial + u + (size_t) (k + 96) * n_u);
+                acc = acc + ((a + b) + (c + d));
+            }
+            for (; k < per_u; k += 32) acc = acc + ld_fr(partial + u + (size_t) k * n_u);
+        }
+        for (uint32_t d = 16; d; d >>= 1) {
+            fr_t o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = __shfl_xor_sync(0xffffffffu, acc.v[j], d);
+            acc = acc + o;
+        }
+        if (lane == 0 && u < n_u) st_fr(out + u, acc);
+    }
 }
 
 // K5 (DOT_PROD phase 2): V[v] = sum_t val[(v << fft_bl) | t] * beta_gs[t]  (src/prover.cpp:277-284).
@@ -408,6 +426,14 @@ __global__ void __launch_bounds__(kBlock) k_dense_rowdot(fr_t *out, const fr_t *
         }
         if (sub == 0 && v < n_rows) st_fr(out + v, fr_lazy_reduce_any(acc));
     }
+}
+
+// micro-benchmark (zk_bench_field_mul): two independent dependent-multiplication chains per thread: the sustained multiplication rate with every SM busy
+template <class F> __global__ void __launch_bounds__(kBlock) k_mul_chain(F *out, uint32_t iters, uint64_t seed) {
+    F x = F::from_u64(seed + blockIdx.x * kBlock + threadIdx.x + 2), y = F::from_u64(seed * 3 + threadIdx.x + 5), a = x, b = y;
+    for (uint32_t i = 0; i < iters; ++i) { a = a * x; b = b * y; }
+    a = a + b;
+    if (a.v[0] == 0x12345678u && a.v[1] == 0x9abcdef0u) out[blockIdx.x * kBlock + threadIdx.x] = a;   // (keeps the chain alive; practically never taken)
 }
 
 }  // namespace zk

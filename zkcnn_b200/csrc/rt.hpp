@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 namespace zk {
 namespace rt {
@@ -19,6 +20,8 @@ struct error : std::runtime_error {
 #ifdef ZK_EMU
 inline void check(int, const char *) {}
 inline void set_device(int) {}
+inline void bind(int, zk_stream_t, zk_stream_t = nullptr, zk_stream_t = nullptr) {}
+inline void unbind() {}
 inline int device_count() { return 1; }
 inline void *dmalloc(size_t bytes) {
     void *p = malloc(bytes ? bytes : 1);
@@ -62,16 +65,42 @@ inline int device_count() {
 // Device memory comes from a small caching pool: cudaFree (and often cudaMalloc) synchronises the whole device, which
 // would stall the witness copy that runs on a second stream during a proof, and the per-call scratch buffers of the API
 // would pay hundreds of microseconds each.  Freed blocks are kept (up to kPoolLimit bytes) and handed out again to
-// requests of at least half their size.  All kernels of a context run on ONE stream, so a recycled block
-// is never touched by its previous owner after the new owner's first use.
+// requests of at least half their size.
+// The pool is shared by every context of the process (several proofs may be in flight on one device, each context with its
+// own streams and host thread), so a freed block carries one event per stream of the context that freed it (bind()), recorded
+// at the time of the free: the block is only handed out again once those events have completed, i.e. once no kernel or copy
+// queued by its previous owner can still touch it.
+struct pool_block_t {
+    void *p;
+    std::vector<cudaEvent_t> fence;
+};
 struct pool_t {
     std::mutex m;
-    std::multimap<std::pair<int, size_t>, void *> free_blocks;   // (device, bytes) -> block
-    std::unordered_map<void *, std::pair<int, size_t>> live;      // block -> (device, bytes)
+    std::multimap<std::pair<int, size_t>, pool_block_t> free_blocks;   // (device, bytes) -> block
+    std::unordered_map<void *, std::pair<int, size_t>> live;           // block -> (device, bytes)
     size_t cached = 0;
 };
 inline pool_t &pool() { static pool_t *P = new pool_t; return *P; }   // leaked on purpose: no destruction-order problems at exit
-constexpr size_t kPoolLimit = 24ull << 30;
+constexpr size_t kPoolLimit = 48ull << 30;
+// the streams of the context the calling thread is working for (set at every C-ABI entry)
+struct bound_t { zk_stream_t s[3] = {nullptr, nullptr, nullptr}; };
+inline bound_t &bound() { static thread_local bound_t b; return b; }
+inline void bind(int device, zk_stream_t s0, zk_stream_t s1 = nullptr, zk_stream_t s2 = nullptr) {
+    set_device(device);
+    bound_t &b = bound();
+    b.s[0] = s0; b.s[1] = s1; b.s[2] = s2;
+}
+inline void unbind() { bound() = bound_t(); }
+inline bool fence_done(pool_block_t &b) {
+    for (cudaEvent_t e : b.fence) {
+        const cudaError_t q = cudaEventQuery(e);
+        if (q == cudaErrorNotReady) return false;
+        if (q != cudaSuccess) cudaGetLastError();   // a failed stream: nothing of it will run any more
+    }
+    for (cudaEvent_t e : b.fence) cudaEventDestroy(e);
+    b.fence.clear();
+    return true;
+}
 inline void *dmalloc(size_t bytes) {
     bytes = ((bytes ? bytes : 1) + 511) & ~(size_t) 511;
     int dev = 0;
@@ -79,9 +108,9 @@ inline void *dmalloc(size_t bytes) {
     pool_t &P = pool();
     {
         std::lock_guard<std::mutex> g(P.m);
-        auto it = P.free_blocks.lower_bound({dev, bytes});
-        if (it != P.free_blocks.end() && it->first.first == dev && it->first.second <= 2 * bytes) {
-            void *p = it->second;
+        for (auto it = P.free_blocks.lower_bound({dev, bytes}); it != P.free_blocks.end() && it->first.first == dev && it->first.second <= 2 * bytes; ++it) {
+            if (!fence_done(it->second)) continue;   // its previous owner may still be using it: look at the next candidate
+            void *p = it->second.p;
             P.cached -= it->first.second;
             P.live[p] = it->first;
             P.free_blocks.erase(it);
@@ -92,8 +121,12 @@ inline void *dmalloc(size_t bytes) {
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e == cudaErrorMemoryAllocation) {   // give the cache back and try once more
         cudaGetLastError();
+        cudaDeviceSynchronize();
         std::lock_guard<std::mutex> g(P.m);
-        for (auto &kv : P.free_blocks) cudaFree(kv.second);
+        for (auto &kv : P.free_blocks) {
+            for (cudaEvent_t ev : kv.second.fence) cudaEventDestroy(ev);
+            cudaFree(kv.second.p);
+        }
         P.free_blocks.clear();
         P.cached = 0;
         e = cudaMalloc(&p, bytes);
@@ -106,13 +139,25 @@ inline void *dmalloc(size_t bytes) {
 inline void dfree(void *p) {
     if (!p) return;
     pool_t &P = pool();
+    std::pair<int, size_t> key;
+    {
+        std::lock_guard<std::mutex> g(P.m);
+        auto it = P.live.find(p);
+        if (it == P.live.end()) { cudaFree(p); return; }
+        key = it->second;
+        P.live.erase(it);
+        if (P.cached + key.second > kPoolLimit) { cudaFree(p); return; }
+    }
+    pool_block_t b;
+    b.p = p;
+    for (zk_stream_t s : bound().s)
+        if (s) {
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(e, s) != cudaSuccess) { cudaGetLastError(); continue; }
+            b.fence.push_back(e);
+        }
     std::lock_guard<std::mutex> g(P.m);
-    auto it = P.live.find(p);
-    if (it == P.live.end()) { cudaFree(p); return; }
-    const auto key = it->second;
-    P.live.erase(it);
-    if (P.cached + key.second > kPoolLimit) { cudaFree(p); return; }
-    P.free_blocks.emplace(key, p);
+    P.free_blocks.emplace(key, std::move(b));
     P.cached += key.second;
 }
 inline void *hmalloc_pinned(size_t bytes) {
