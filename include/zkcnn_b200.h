@@ -166,6 +166,12 @@ int zk_phi_table(zk_ctx *ctx, const uint64_t *rx, const uint64_t *scale, uint32_
  * round j uses previous_random = (j == 0 ? 0 : r[j-1]).  polys gets 3 Fr per round.  Returns folded tables if non-NULL. */
 int zk_fold_rounds(zk_ctx *ctx, const uint64_t *V, const uint64_t *M, uint32_t bits, uint64_t live, const uint64_t *r,
                    uint32_t n_rounds, uint64_t *polys);
+/* The same on TWO table pairs folded in lock step, as prover::sumcheckUpdate does (src/prover.cpp:368-383): pair 0 (2^bits0 entries,
+ * bits0 < 0: absent) and pair 1; a pair that is exhausted first collapses into add_term.  n_rounds <= max(bits0, bits1). */
+int zk_fold_rounds2(zk_ctx *ctx, const uint64_t *V0, const uint64_t *M0, int32_t bits0, uint64_t live0, const uint64_t *V1, const uint64_t *M1, int32_t bits1,
+                    uint64_t live1, const uint64_t *r, uint32_t n_rounds, uint64_t *polys);
+/* prover::Vres (src/prover.cpp:434-457) on a stand-alone vector: the multilinear extension of values[0..n) at r[0..r_size) */
+int zk_mle_eval(zk_ctx *ctx, const uint64_t *values, uint32_t n, const uint64_t *r, uint32_t r_size, uint64_t *out);
 /* Runs `n_rounds` rounds of sumcheckDotProdUpdate1 (src/prover.cpp:103-144) on stand-alone tables: mult has 2^m_bits entries
  * (mult_array[1]), V0 / V1 have 2^bits entries of which the first live0 / live1 are non-zero (V_mult[0] / V_mult[1];
  * live0 <= live1).  Round j uses previous_random = (j == 0 ? 0 : r[j-1]).  polys gets 4 Fr (a, b, c, d) per round. */
@@ -177,6 +183,10 @@ int zk_msm(zk_ctx *ctx, const uint64_t *bases, const uint64_t *scalars, uint64_t
 int zk_g1_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n);
 /* out[i] = scalars[i] * base for ONE base point (fixed-base comb; the verifier's generator set-up, src/verifier.cpp:121-126) */
 int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scalars, uint64_t n, uint64_t *out);
+/* FNV-1a-64 over the canonical 32-byte little-endian encodings of a bookkeeping table of the sumcheck in progress (entries beyond
+ * the live part count as zeros), and its entry count: sel 0 / 1 = V / mult table of pair 0, 2 / 3 = of pair 1, 4 = the multiplier
+ * table of a DOT_PROD phase.  For per-function parity tests against the reference's tables (oracle/harness: --dump-dir). */
+int zk_debug_table_hash(zk_ctx *ctx, int sel, uint64_t *fnv1a, uint64_t *n_entries);
 /* device self-test: inline-PTX field arithmetic against the portable implementation on n random inputs; 0 = equal */
 int zk_selftest(zk_ctx *ctx, uint64_t seed, uint32_t n);
 

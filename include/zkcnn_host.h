@@ -79,6 +79,9 @@ int zkh_inferred_class(zkh_session *s, int picture);
 void *zkh_context(zkh_session *s);   /* the zk_ctx of this session's prover (NULL before the first proof); for zk_profile_* */
 /* per-layer shape/hash dump in the format of oracle/harness/ref_run --circuit-hash (parity tests) */
 int zkh_circuit_dump(zkh_session *s, const char *path, int with_hashes);
+/* test hook: the following zkh_prove calls append the hashes of the prover's bookkeeping tables after every Init* call to `path` (format of
+ * oracle/harness/ref_run --dump-dir: per-function parity against the reference); NULL switches it off */
+int zkh_table_dump(zkh_session *s, const char *path);
 
 #ifdef __cplusplus
 }

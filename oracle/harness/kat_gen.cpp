@@ -6,6 +6,9 @@
 #define polyProver ref_polyProver
 #define prover ref_prover
 #include <hyrax-bls12-381/src/polyProver.hpp>
+#define private public   // (access only: the fold / cubic / Vres KATs call the reference prover's private round functions on hand-made tables)
+#include <prover.hpp>
+#undef private
 #include <utils.hpp>
 #include "seeded_rng.hpp"
 #include <cstdio>
@@ -154,8 +157,99 @@ int main() {
             printf("  {\"lcomm\": %s, \"rcomm\": %s, \"ly\": %s, \"ry\": %s, \"randomness\": %s}%s\n", pt(lc).c_str(), pt(rc).c_str(), hx(ly).c_str(),
                    hx(ry).c_str(), hx(rho).c_str(), j == lbl - 1 ? "" : ",");
         }
-        printf(" ], \"open\": %s, \"rsize\": %d, \"rbl\": %d}\n", hx(hp.bulletOpen()).c_str(), 1 << rbl, rbl);
+        printf(" ], \"open\": %s, \"rsize\": %d, \"rbl\": %d},\n", hx(hp.bulletOpen()).c_str(), 1 << rbl, rbl);
     }
+    // ---- K1: prover::sumcheckUpdate / sumcheckUpdateEach (src/prover.cpp:368-383,396-426) on hand-made table pairs: two pairs of
+    //      different sizes (the smaller one collapses into add_term on the way), ragged live sizes
+    printf("\"fold\": [\n");
+    const int fold_cases[][4] = {{5, 19, 3, 5}, {4, 16, -1, 0}, {6, 33, 6, 64}, {3, 5, 1, 2}};   // {bits1, live1, bits0 (-1: absent), live0}
+    for (int ci = 0; ci < 4; ++ci) {
+        const int b1 = fold_cases[ci][0], l1 = fold_cases[ci][1], b0 = fold_cases[ci][2], l0 = fold_cases[ci][3];
+        ref_prover rp;
+        vector<Fr> V[2], M[2];
+        const int bl[2] = {b0, b1}, lv[2] = {l0, l1};
+        for (int b = 0; b < 2; ++b) {
+            rp.total[b] = bl[b] >= 0 ? 1u << bl[b] : 0;
+            rp.total_size[b] = lv[b];
+            rp.V_mult[b].resize(rp.total[b]);
+            rp.mult_array[b].resize(rp.total[b]);
+            for (u32 i = 0; i < rp.total[b]; ++i) {
+                Fr v = (int) i < lv[b] ? (i % 3 ? small_signed() : rnd()) : Fr(0), m = (int) i < lv[b] ? rnd() : Fr(0);
+                if ((int) i < lv[b]) { V[b].push_back(v); M[b].push_back(m); }
+                rp.V_mult[b][i] = v;
+                rp.mult_array[b][i] = m;
+            }
+        }
+        const int rounds = b1 > b0 ? b1 : b0;
+        vector<Fr> ch(rounds);
+        for (auto &x : ch) x = rnd();
+        rp.r_u.assign(2, vector<Fr>(rounds));
+        rp.sumcheck_id = 1;
+        rp.round = 0;
+        rp.add_term.clear();
+        printf(" {\"bits\": [%d, %d], \"V0\": %s, \"M0\": %s, \"V1\": %s, \"M1\": %s, \"r\": %s, \"polys\": [", b0, b1, arr(V[0]).c_str(), arr(M[0]).c_str(),
+               arr(V[1]).c_str(), arr(M[1]).c_str(), arr(ch).c_str());
+        for (int j = 0; j < rounds; ++j) {
+            quadratic_poly q = rp.sumcheckUpdate(j ? ch[j - 1] : Fr(0), rp.r_u[1]);
+            printf("%s[%s,%s,%s]", j ? "," : "", hx(q.a).c_str(), hx(q.b).c_str(), hx(q.c).c_str());
+        }
+        printf("], \"add_term\": %s}%s\n", hx(rp.add_term).c_str(), ci == 3 ? "" : ",");
+    }
+    printf("],\n");
+    // ---- K2: prover::sumcheckDotProdUpdate1 (src/prover.cpp:103-144): multiplier over 2^m_bits frequencies, V_mult[0] zero beyond live0
+    printf("\"cubic\": [\n");
+    const int cubic_cases[][4] = {{5, 2, 12, 29}, {6, 3, 40, 64}, {4, 4, 16, 16}, {7, 1, 30, 100}};   // {bits, m_bits, live0, live1}
+    for (int ci = 0; ci < 4; ++ci) {
+        const int bits = cubic_cases[ci][0], mb = cubic_cases[ci][1], l0 = cubic_cases[ci][2], l1 = cubic_cases[ci][3];
+        ref_prover rp;
+        rp.total[0] = 1u << mb;
+        rp.total[1] = 1u << bits;
+        rp.total_size[1] = l1;
+        rp.mult_array[1].resize(rp.total[0]);
+        rp.V_mult[0].resize(rp.total[1]);
+        rp.V_mult[1].resize(rp.total[1]);
+        vector<Fr> mult(rp.total[0]), V0(l0), V1(l1);
+        for (auto &x : mult) x = rnd();
+        for (auto &x : V0) x = rnd();
+        for (size_t i = 0; i < V1.size(); ++i) V1[i] = i % 2 ? small_signed() : rnd();
+        for (u32 i = 0; i < rp.total[0]; ++i) rp.mult_array[1][i] = mult[i];
+        for (u32 i = 0; i < rp.total[1]; ++i) {
+            rp.V_mult[0][i] = (int) i < l0 ? V0[i] : Fr(0);
+            rp.V_mult[1][i] = (int) i < l1 ? V1[i] : Fr(0);
+        }
+        vector<Fr> ch(bits);
+        for (auto &x : ch) x = rnd();
+        rp.r_u.assign(2, vector<Fr>(bits));
+        rp.sumcheck_id = 1;
+        rp.round = 0;
+        printf(" {\"bits\": %d, \"m_bits\": %d, \"mult\": %s, \"V0\": %s, \"V1\": %s, \"r\": %s, \"polys\": [", bits, mb, arr(mult).c_str(), arr(V0).c_str(),
+               arr(V1).c_str(), arr(ch).c_str());
+        for (int j = 0; j < bits; ++j) {
+            cubic_poly q = rp.sumcheckDotProdUpdate1(j ? ch[j - 1] : Fr(0));
+            printf("%s[%s,%s,%s,%s]", j ? "," : "", hx(q.a).c_str(), hx(q.b).c_str(), hx(q.c).c_str(), hx(q.d).c_str());
+        }
+        Fr claim;
+        rp.sumcheckDotProdFinalize1(ch[bits - 1], claim);
+        printf("], \"claim_1\": %s, \"V_u1\": %s}%s\n", hx(claim).c_str(), hx(rp.V_u1).c_str(), ci == 3 ? "" : ",");
+    }
+    printf("],\n");
+    // ---- K6b: prover::Vres (src/prover.cpp:434-457): MLE of a short output layer at r
+    printf("\"vres\": [\n");
+    const int vres_cases[][2] = {{10, 4}, {16, 4}, {1, 0}, {5, 3}};   // {output_size, r_size}
+    for (int ci = 0; ci < 4; ++ci) {
+        const int n = vres_cases[ci][0], rs = vres_cases[ci][1];
+        ref_prover rp;
+        rp.C.size = 2;
+        rp.val.assign(2, vector<Fr>());
+        rp.val[1].resize(n);
+        for (auto &x : rp.val[1]) x = small_signed() + rnd();
+        vector<Fr> r(rs + 1);
+        for (auto &x : r) x = rnd();
+        Fr out = rp.Vres(r.begin(), n, rs);
+        r.resize(rs);
+        printf(" {\"values\": %s, \"r\": %s, \"out\": %s}%s\n", arr(rp.val[1]).c_str(), arr(r).c_str(), hx(out).c_str(), ci == 3 ? "" : ",");
+    }
+    printf("]\n");
     printf("}\n");
     return 0;
 }

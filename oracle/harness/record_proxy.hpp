@@ -51,9 +51,27 @@ private:
 // ---- 2. GKR prover under its moved name ---------------------------------------------------------------------------
 #define polyProver ref_polyProver
 #define prover ref_prover
+#define private public         // (access only, the layout is unchanged: lets the proxy dump the bookkeeping tables after each Init*)
 #include <prover.hpp>          // reference src/prover.hpp (pulls global_var.hpp, circuit.h, polynomial.h)
+#undef private
 #undef prover
 #undef polyProver
+
+// --dump-dir: after every Init* call of the reference prover, one line per table pair with the FNV-1a of the table VALUES
+// (canonical 32-byte little-endian encodings, entries [0, total)), in the format of zkcnn_b200's prover::dumpTables:
+//   T <layer> <tag> <b> n <entries> v <hash of V_mult[b]> m <hash of mult_array[b]>
+// tag: p1 / p2 = sumcheckInitPhase1/2, dp1 = sumcheckDotProdInitPhase1 (b = 0: V_mult[0] and the 2^fft_bl multiplier table,
+// b = 1: V_mult[1]), liu = sumcheckLiuInit.  Per-function parity for K4, K4b, K5, K5b, K6 on every layer of a proof.
+inline FILE *&table_dump_file() { static FILE *f = nullptr; return f; }
+inline uint64_t table_fnv(const vector<linear_poly> &t, size_t n) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (size_t i = 0; i < n && i < t.size(); ++i) {
+        uint8_t b[32];
+        t[i].b.serialize(b, 32);
+        for (int k = 0; k < 32; ++k) { h ^= b[k]; h *= 0x100000001b3ULL; }
+    }
+    return h;
+}
 
 class prover {
 public:
@@ -61,9 +79,19 @@ public:
     void init() { impl_.init(); }
     void sumcheckInitAll(const vector<F>::const_iterator &r) { impl_.sumcheckInitAll(r); }
     void sumcheckInit(const F &a, const F &b) { impl_.sumcheckInit(a, b); }
-    void sumcheckDotProdInitPhase1() { impl_.sumcheckDotProdInitPhase1(); }
-    void sumcheckInitPhase1(const F &rr) { impl_.sumcheckInitPhase1(rr); }
-    void sumcheckInitPhase2() { impl_.sumcheckInitPhase2(); }
+    void dumpTables(const char *tag, bool dot = false, int first_b = 0) {
+        FILE *f = table_dump_file();
+        if (!f) return;
+        for (int b = first_b; b < 2; ++b) {
+            const size_t n = dot ? impl_.total[1] : impl_.total[b];
+            const uint64_t hv = table_fnv(impl_.V_mult[b], n);
+            const uint64_t hm = dot ? (b == 0 ? table_fnv(impl_.mult_array[1], impl_.total[0]) : table_fnv(impl_.mult_array[1], 0)) : table_fnv(impl_.mult_array[b], n);
+            fprintf(f, "T %d %s %d n %zu v %016lx m %016lx\n", (int) impl_.sumcheck_id, tag, b, n, hv, hm);
+        }
+    }
+    void sumcheckDotProdInitPhase1() { impl_.sumcheckDotProdInitPhase1(); dumpTables("dp1", true); }
+    void sumcheckInitPhase1(const F &rr) { impl_.sumcheckInitPhase1(rr); dumpTables("p1"); }
+    void sumcheckInitPhase2() { impl_.sumcheckInitPhase2(); dumpTables("p2"); }
     cubic_poly sumcheckDotProdUpdate1(const F &r) {
         auto p = impl_.sumcheckDotProdUpdate1(r);
         transcript().put(p.a); transcript().put(p.b); transcript().put(p.c); transcript().put(p.d);
@@ -76,7 +104,7 @@ public:
     void sumcheckFinalize1(const F &r, F &c0, F &c1) { impl_.sumcheckFinalize1(r, c0, c1); transcript().put(c0); transcript().put(c1); }
     void sumcheckFinalize2(const F &r, F &c0, F &c1) { impl_.sumcheckFinalize2(r, c0, c1); transcript().put(c0); transcript().put(c1); }
     void sumcheckLiuFinalize(const F &r, F &c1) { impl_.sumcheckLiuFinalize(r, c1); transcript().put(c1); }
-    void sumcheckLiuInit(const vector<F> &su, const vector<F> &sv) { impl_.sumcheckLiuInit(su, sv); }
+    void sumcheckLiuInit(const vector<F> &su, const vector<F> &sv) { impl_.sumcheckLiuInit(su, sv); dumpTables("liu", false, 1); }
     quadratic_poly sumcheckLiuUpdate(const F &r) { return rec(impl_.sumcheckLiuUpdate(r)); }
     hyrax_bls12_381::polyProver &commitInput(const vector<G> &gens) {
         poly_proxy_.reset(new hyrax_bls12_381::polyProver(impl_.commitInput(gens)));

@@ -67,6 +67,11 @@ int main(int argc, char **argv) {
         else if (a == "--gens") real_gens = std::string(argv[++k]) == "real";
         else if (a == "--shapes") shapes = true;
         else if (a == "--circuit-hash") shapes = hashes = true;
+        else if (a == "--dump-dir" && k + 1 < argc) {   // per-call table hashes (record_proxy.hpp: dumpTables) -> DIR/tables.txt
+            std::string path = std::string(argv[++k]) + "/tables.txt";
+            table_dump_file() = fopen(path.c_str(), "w");
+            if (!table_dump_file()) { fprintf(stderr, "cannot write %s\n", path.c_str()); return 3; }
+        }
     }
 
     if (real_gens) install_real_base_point();
@@ -94,6 +99,7 @@ int main(int argc, char **argv) {
     printf("TABLE ");
     for (auto &s : output_tb) printf("%s, ", s.c_str());
     puts("");
+    if (table_dump_file()) fclose(table_dump_file());
     if (!tr_out.empty() && !transcript().save(tr_out)) { fprintf(stderr, "cannot write %s\n", tr_out.c_str()); return 3; }
     return ok ? 0 : 1;
 }

@@ -117,6 +117,48 @@ def case_cubic_rounds(lib, shapes=((1, 0, 2, 2), (3, 1, 5, 8), (5, 2, 12, 29), (
             assert [tuple(fr_from_words(got[j])) for j in range(bits)] == want, (bits, m_bits, live0, live1)
 
 
+def case_round_kats(lib, kat, tunables=None):
+    """K1 / K2 / K6b against known answers minted by calling the REFERENCE prover's own round functions on hand-made tables
+    (oracle/harness/kat_gen.cpp: sumcheckUpdate, sumcheckDotProdUpdate1, Vres; tests/golden/kat.json)"""
+    with Context(lib) as ctx:
+        for k, v in (tunables or {}).items():
+            ctx.set_tunable(k, v)
+        for c in kat["fold"]:
+            b0, b1 = c["bits"]
+            V0, M0, V1, M1 = ([H(x) for x in c[k]] for k in ("V0", "M0", "V1", "M1"))
+            ch = [H(x) for x in c["r"]]
+            n = len(c["polys"])
+            got = ctx.fold_rounds2(fr_to_words(V0) if b0 >= 0 else None, fr_to_words(M0) if b0 >= 0 else None, b0, fr_to_words(V1), fr_to_words(M1), b1,
+                                   fr_to_words(ch), n)
+            assert [tuple(fr_from_words(got[j])) for j in range(n)] == [tuple(H(x) for x in p) for p in c["polys"]], c["bits"]
+        for c in kat["cubic"]:
+            mult, V0, V1, ch = ([H(x) for x in c[k]] for k in ("mult", "V0", "V1", "r"))
+            got = ctx.cubic_rounds(fr_to_words(mult), fr_to_words(V0), fr_to_words(V1), c["bits"], fr_to_words(ch), c["bits"])
+            assert [tuple(fr_from_words(got[j])) for j in range(c["bits"])] == [tuple(H(x) for x in p) for p in c["polys"]], (c["bits"], c["m_bits"])
+        for c in kat["vres"]:
+            got = ctx.mle_eval(fr_to_words([H(x) for x in c["values"]]), fr_to_words([H(x) for x in c["r"]]))
+            assert fr_from_words(got) == [H(c["out"])]
+
+
+def tables_and_compare(hostlib, model, network, pic_cnt, input_path, seed, golden_name, golden_dir, device=0):
+    """per-function parity of the Init* calls (K4, K4b, K5, K5b, K6): the hashes of the prover's bookkeeping tables after every
+    sumcheckInitPhase1/2, sumcheckDotProdInitPhase1 and sumcheckLiuInit of a whole proof against the reference's own tables
+    (ref_run --dump-dir, tests/golden/*.tables.txt); a difference names the layer and the phase"""
+    import tempfile
+    with Session(hostlib, model, network, pic_cnt, device) as s:
+        s.input_file(input_path)
+        s.build()
+        with tempfile.NamedTemporaryFile("r", suffix=".txt") as f:
+            s.table_dump(f.name)
+            st = s.prove(seed, PROVER_ONLY)
+            s.table_dump(None)
+            mine = f.read().splitlines()
+    want = open(os.path.join(golden_dir, golden_name + ".tables.txt")).read().splitlines()
+    assert st["ok"] == 1 and len(mine) == len(want) and len(want) > 20
+    bad = [(a, b) for a, b in zip(mine, want) if a != b]
+    assert not bad, f"first differing table: ours {bad[0][0]!r} reference {bad[0][1]!r}"
+
+
 def case_g1_ops(lib, kat):
     g = kat["g1"]
     p, q, k = P(g["P"]), P(g["Q"]), H(g["k"])

@@ -64,6 +64,8 @@ def synthetic_inputs(tmp_path_factory):
     for name, model, seed, cfg in (("lenet_syn", "lenet", 11, None), ("smallvgg", "vgg11", 5, manifest["smallvgg_config"])):
         path = os.path.join(d, name + ".csv")
         gen.write_text(gen.generate(model, seed, cfg), path)
+        if cfg:
+            open(path + ".config", "w").write(cfg + "\n")     # the network description file of the reference's `vgg` model class
         digest = hashlib.sha256(open(path, "rb").read()).hexdigest()
         assert digest == manifest[name], f"synthetic input {name} differs from the one the goldens were made with (numpy RNG changed?)"
         out[name] = path

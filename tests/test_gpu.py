@@ -64,6 +64,22 @@ def test_cubic_rounds_every_kernel_variant(gpu_lib):
     cases.case_cubic_rounds(gpu_lib, shapes=multi, tunables={"cubic_max_grid": 40, "tma_min_entries": 128})
 
 
+def test_round_kats_from_the_reference(gpu_lib, kat):
+    cases.case_round_kats(gpu_lib, kat)
+    cases.case_round_kats(gpu_lib, kat, tunables={"thin_max_pairs": 0, "tma_min_entries": 1 << 40, "cubic_factored_min_iters": 1, "cubic_tma": 0})
+    cases.case_round_kats(gpu_lib, kat, tunables={"thin_max_pairs": 0, "tma_min_entries": 8})
+
+
+@pytest.mark.parametrize("model,net,pics,inp,seed,golden", [
+    ("lenet", "", 1, "lenet_syn", 3, "lenet_syn_p1_seed3"),
+    ("lenet", "", 2, "lenet_syn", 4, "lenet_syn_p2_seed4"),
+    ("vgg", "small", 2, "smallvgg", 7, "smallvgg_p2_seed7"),
+])
+def test_init_tables_against_the_reference(gpu_host, synthetic_inputs, model, net, pics, inp, seed, golden):
+    net = synthetic_inputs["smallvgg_config"] if net == "small" else net
+    cases.tables_and_compare(gpu_host, model, net, pics, synthetic_inputs[inp], seed, golden, GOLDEN)
+
+
 def test_g1_ops(gpu_lib, kat):
     cases.case_g1_ops(gpu_lib, kat)
 

@@ -33,6 +33,11 @@ def test_cubic_rounds(emu_lib):
     cases.case_cubic_rounds(emu_lib, shapes=multi, tunables={"cubic_max_grid": 3, "cubic_factored_min_iters": 1 << 30})
 
 
+def test_round_kats_from_the_reference(emu_lib, kat):
+    cases.case_round_kats(emu_lib, kat)
+    cases.case_round_kats(emu_lib, kat, tunables={"thin_max_pairs": 0, "cubic_factored_min_iters": 1})
+
+
 def test_g1_ops(emu_lib, kat):
     cases.case_g1_ops(emu_lib, kat)
 

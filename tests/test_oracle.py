@@ -118,3 +118,22 @@ def test_fold_is_a_sumcheck():
         for j, (a, b, c) in enumerate(polys):
             assert (c + a + b + c) % O.R == claim
             claim = (a * ch[j] * ch[j] + b * ch[j] + c) % O.R
+
+
+def test_round_functions_against_reference_kats(kat):
+    """the port's fold / cubic round / Vres against known answers minted by calling the REFERENCE prover's own (private) round
+    functions on hand-made tables (oracle/harness/kat_gen.cpp -> tests/golden/kat.json): pins the restatement itself"""
+    for c in kat["fold"]:
+        b0, b1 = c["bits"]
+        V0, M0, V1, M1 = ([H(x) for x in c[k]] for k in ("V0", "M0", "V1", "M1"))
+        ch = [H(x) for x in c["r"]]
+        pairs = ([O.FoldState(V0, M0, b0)] if b0 >= 0 else []) + [O.FoldState(V1, M1, b1)]
+        n = len(c["polys"])
+        assert O.sumcheck_rounds(pairs, ch, n) == [tuple(H(x) for x in p) for p in c["polys"]], c["bits"]
+    for c in kat["cubic"]:
+        mult, V0, V1, ch = ([H(x) for x in c[k]] for k in ("mult", "V0", "V1", "r"))
+        st = O.DotProdState(mult, V0, V1, c["bits"], len(V1))
+        got = [O.sumcheck_dotprod_update1(st, 0 if j == 0 else ch[j - 1]) for j in range(c["bits"])]
+        assert got == [tuple(H(x) for x in p) for p in c["polys"]], (c["bits"], c["m_bits"])
+    for c in kat["vres"]:
+        assert O.vres([H(x) for x in c["values"]], [H(x) for x in c["r"]]) == H(c["out"])

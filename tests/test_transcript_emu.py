@@ -36,6 +36,15 @@ def test_small_vgg_fft_conv(emu_host, synthetic_inputs):
     assert st["ok"] == 1
 
 
+@pytest.mark.parametrize("model,net,pics,inp,seed,golden", [
+    ("lenet", "", 2, "lenet_syn", 4, "lenet_syn_p2_seed4"),
+    ("vgg", "small", 2, "smallvgg", 7, "smallvgg_p2_seed7"),
+])
+def test_init_tables_against_the_reference(emu_host, synthetic_inputs, model, net, pics, inp, seed, golden):
+    net = synthetic_inputs["smallvgg_config"] if net == "small" else net
+    cases.tables_and_compare(emu_host, model, net, pics, synthetic_inputs[inp], seed, golden, GOLDEN)
+
+
 def test_round_by_round_driver_gives_the_same_transcript(emu_host, synthetic_inputs):
     """the default driver hands the device a whole phase of challenges at once (zk_sumcheck_update_batch); with
     ZKH_ROUND_BY_ROUND it makes the reference's one call per round -- same messages, same order"""

@@ -94,6 +94,8 @@ class Lib:
         d.zk_beta_table.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, _u64p]
         d.zk_phi_table.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint32, C.c_int, _u64p]
         d.zk_fold_rounds.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint32, C.c_uint64, _u64p, C.c_uint32, _u64p]
+        d.zk_fold_rounds2.argtypes = [C.c_void_p, _u64p, _u64p, C.c_int32, C.c_uint64, _u64p, _u64p, C.c_int32, C.c_uint64, _u64p, C.c_uint32, _u64p]
+        d.zk_mle_eval.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, C.c_uint32, _u64p]
         d.zk_cubic_rounds.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, C.c_uint64, _u64p, C.c_uint64, C.c_uint32, _u64p, C.c_uint32, _u64p]
         d.zk_msm.argtypes = [C.c_void_p, _u64p, _u64p, C.c_uint64, C.c_uint32, _u64p]
         d.zk_g1_vec_op.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint64]
@@ -187,6 +189,24 @@ class Context:
         self._check(self.lib.dll.zk_fold_rounds(self.h, _ptr(V), _ptr(M), bits, len(V), _ptr(r) if len(r) else None, n_rounds, _ptr(out)),
                     "zk_fold_rounds")
         return out.reshape(n_rounds, 3, 4)
+
+    def fold_rounds2(self, V0, M0, bits0, V1, M1, bits1, r, n_rounds):
+        """K1 on two table pairs in lock step (prover::sumcheckUpdate); bits0 < 0: pair 0 absent"""
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in (V0, M0, V1, M1)]
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(-1, 4)
+        out = np.empty((n_rounds * 3, 4), dtype=np.uint64)
+        n0 = 0 if arrs[0] is None else len(arrs[0])
+        n1 = 0 if arrs[2] is None else len(arrs[2])
+        self._check(self.lib.dll.zk_fold_rounds2(self.h, _ptr(arrs[0]), _ptr(arrs[1]), bits0, n0, _ptr(arrs[2]), _ptr(arrs[3]), bits1, n1,
+                                                 _ptr(r) if len(r) else None, n_rounds, _ptr(out)), "zk_fold_rounds2")
+        return out.reshape(n_rounds, 3, 4)
+
+    def mle_eval(self, values, r):
+        values = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(-1, 4)
+        out = np.empty(4, dtype=np.uint64)
+        self._check(self.lib.dll.zk_mle_eval(self.h, _ptr(values), len(values), _ptr(r) if len(r) else None, len(r), _ptr(out)), "zk_mle_eval")
+        return out
 
     def cubic_rounds(self, mult, V0, V1, bits, r, n_rounds):
         """K2: n_rounds of sumcheckDotProdUpdate1 on stand-alone tables (len(mult) a power of two; len(V0) <= len(V1) <= 2^bits)"""
@@ -324,6 +344,7 @@ class HostLib:
         d.zkh_proof.argtypes = [C.c_void_p, _u64p]
         d.zkh_inferred_class.argtypes = [C.c_void_p, C.c_int]
         d.zkh_circuit_dump.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        d.zkh_table_dump.argtypes = [C.c_void_p, C.c_char_p]
         d.zkh_context.restype = C.c_void_p
         d.zkh_context.argtypes = [C.c_void_p]
 
@@ -386,6 +407,10 @@ class Session:
 
     def circuit_dump(self, path, with_hashes=True):
         self._check(self.lib.dll.zkh_circuit_dump(self.h, str(path).encode(), int(with_hashes)), "zkh_circuit_dump")
+
+    def table_dump(self, path):
+        """test hook: hashes of the bookkeeping tables after every Init* call of the following proofs -> path (None: off)"""
+        self._check(self.lib.dll.zkh_table_dump(self.h, str(path).encode() if path is not None else None), "zkh_table_dump")
 
     def context_handle(self):
         """the zk_ctx of this session's prover (for zk_profile_*); None before the first proof"""

@@ -346,6 +346,7 @@ int zk_sumcheck_init_phase1(zk_ctx *ctx, const uint64_t *relu_rou_p) {   // src/
     const uint32_t id = ctx->sumcheck_id;
     ZK_REQUIRE(id >= 1 && d.ty != ZK_LAYER_DOT_PROD, "wrong init for this layer");
     for (int b = 0; b < 2; ++b) pair_reset(ctx->pair[b], d.bit_length_u[b], d.size_u[b]);
+    ctx->in_dotprod_p1 = false;
     ctx->r_u[id].resize(d.max_bl_u);
     ctx->relu_rou = fr_load(relu_rou_p);
     ctx->add_term = fr_t::zero();
@@ -444,6 +445,7 @@ int zk_sumcheck_init_phase2(zk_ctx *ctx) {   // src/prover.cpp:241-310
     const uint32_t id = ctx->sumcheck_id;
     ZK_REQUIRE(id >= 1 && d.need_phase2, "layer has no phase 2");
     for (int b = 0; b < 2; ++b) pair_reset(ctx->pair[b], d.bit_length_v[b], d.size_v[b]);
+    ctx->in_dotprod_p1 = false;
     ctx->r_v[id].resize(d.max_bl_v);
     ctx->add_term = fr_t::zero();
     layer_t &prev = ctx->layers[id - 1];
@@ -639,6 +641,7 @@ int zk_sumcheck_dotprod_init_phase1(zk_ctx *ctx) {   // src/prover.cpp:57-95
     fr_t *V0 = table_init_buf(P.m, P.n_eval);
     ZK_REQUIRE(L.dp_rows == (P.n_eval >> fft_bl) && L.dp_rows_live <= L.dp_rows, "DOT_PROD schedule missing");
     ctx->dp_live0 = std::min<uint32_t>(L.dp_rows_live << fft_bl, P.live);
+    ctx->in_dotprod_p1 = true;
     const uint64_t n_out = (uint64_t) L.dp_rows_live << fft_bl;
     if (n_out)
         ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, (uint64_t) d.n_bin * (32ull << fft_bl) + n_out * 32, k_dotprod_axpy, dim3(grid_for(n_out)), dim3(kBlock), 0, V0,
@@ -810,6 +813,87 @@ int zk_cubic_rounds(zk_ctx *ctx, const uint64_t *mult, uint32_t m_bits, const ui
     ZK_API_END
 }
 
+int zk_fold_rounds2(zk_ctx *ctx, const uint64_t *V0, const uint64_t *M0, int32_t bits0, uint64_t live0, const uint64_t *V1, const uint64_t *M1, int32_t bits1,
+                    uint64_t live1, const uint64_t *r, uint32_t n_rounds, uint64_t *polys) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && polys && bits0 <= 28 && bits1 <= 28 && (bits0 >= 0 || bits1 >= 0) && n_rounds >= 1 && (int) n_rounds <= std::max(bits0, bits1) + (std::max(bits0, bits1) == 0), "bad arguments");
+    ZK_REQUIRE((bits0 < 0 || (V0 && M0 && live0 <= (1ull << bits0))) && (bits1 < 0 || (V1 && M1 && live1 <= (1ull << bits1))), "bad tables");
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
+    const uint64_t *Vs[2] = {V0, V1}, *Ms[2] = {M0, M1};
+    const int32_t bits[2] = {bits0, bits1};
+    const uint64_t lives[2] = {live0, live1};
+    for (int b = 0; b < 2; ++b) {
+        pair_t &P = ctx->pair[b];
+        pair_reset(P, (int8_t) bits[b], bits[b] >= 0 ? (uint32_t) lives[b] : 0);
+        if (bits[b] < 0) continue;
+        fr_t *dv = table_init_buf(P.v, 1ull << bits[b]), *dm = table_init_buf(P.m, 1ull << bits[b]);
+        rt::h2d(dv, Vs[b], lives[b] * 32, ctx->stream);
+        rt::h2d(dm, Ms[b], lives[b] * 32, ctx->stream);
+    }
+    ctx->in_dotprod_p1 = false;
+    ctx->add_term = fr_t::zero();
+    ctx->round = 0;
+    for (uint32_t j = 0; j < n_rounds; ++j) {
+        const fr_t prev = j == 0 ? fr_t::zero() : fr_load(r + 4 * (j - 1));
+        ++ctx->round;
+        ctx->add_term = ctx->add_term * (fr_t::one() - prev);
+        fr_t abc[3];
+        round_quadratic(ctx, prev, 3u, abc);
+        abc[1] = abc[1] - ctx->add_term;
+        abc[2] = abc[2] + ctx->add_term;
+        for (int k = 0; k < 3; ++k) fr_store(polys + (size_t) (3 * j + k) * 4, abc[k]);
+    }
+    ctx->pair[0].n_eval = ctx->pair[1].n_eval = 0;
+    ZK_API_END
+}
+
+int zk_mle_eval(zk_ctx *ctx, const uint64_t *values, uint32_t n, const uint64_t *r, uint32_t r_size, uint64_t *out) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && values && out && n >= 1 && r_size <= 24 && n <= (1u << r_size) && (r || r_size == 0), "bad arguments");
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
+    ensure_round_scratch(ctx);
+    rt::dbuf dv;
+    dv.ensure((size_t) n * 32);
+    rt::h2d(dv.p, values, (size_t) n * 32, ctx->stream);
+    ctx->d_r.ensure(2 * 64 * sizeof(fr_t));
+    rt::h2d(ctx->d_r.p, r, (size_t) r_size * 32, ctx->stream);
+    ctx->vres_scratch.ensure(sizeof(fr_t) << r_size);
+    ZK_KLAUNCH(ctx, k_vres, dim3(1), dim3(kBlock), 0, dv.as<fr_t>(), n, ctx->d_r.as<fr_t>(), r_size, ctx->vres_scratch.as<fr_t>(), ctx->round_out.as<fr_t>());
+    rt::d2h(ctx->h_out, ctx->round_out.p, sizeof(fr_t), ctx->stream);
+    rt::sync(ctx->stream);
+    fr_store(out, ctx->h_out[0]);
+    ZK_API_END
+}
+
+int zk_debug_table_hash(zk_ctx *ctx, int sel, uint64_t *fnv1a, uint64_t *n_entries) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && fnv1a && n_entries && sel >= 0 && sel <= 4, "bad arguments");
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
+    const fr_t *src = nullptr;
+    uint64_t n = 0, live = 0;
+    if (sel == 4) { src = ctx->mdp.cur; n = live = ctx->mdp_n; }
+    else {
+        const pair_t &P = ctx->pair[sel >> 1];
+        if (P.exists && P.n_eval) {
+            src = (sel & 1) ? P.m.cur : P.v.cur;
+            n = P.n_eval;
+            live = std::min<uint64_t>(n, (sel == 3 && ctx->in_dotprod_p1) ? ctx->dp_live0 : P.live);
+        }
+    }
+    std::vector<fr_t> h(live);
+    if (live) d2h_staged(ctx, h.data(), src, live * sizeof(fr_t));
+    uint64_t hash = 0xcbf29ce484222325ULL;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (i < live) h[i].to_canonical(c);
+        const uint8_t *b = reinterpret_cast<const uint8_t *>(c);
+        for (int k = 0; k < 32; ++k) { hash ^= b[k]; hash *= 0x100000001b3ULL; }
+    }
+    *fnv1a = hash;
+    *n_entries = n;
+    ZK_API_END
+}
+
 // ---- micro-benchmarks of the K2 kernels and of the field multiplier (CUDA events on the launching stream) -------------------------
 // sustained Fp (is_fp != 0) or Fr multiplications per second, in units of 10^9
 int zk_bench_field_mul(zk_ctx *ctx, int is_fp, float *gmul_per_s) {
@@ -910,6 +994,7 @@ int zk_sumcheck_liu_init(zk_ctx *ctx, const uint64_t *s_u, const uint64_t *s_v, 
     ZK_REQUIRE(L0.n_val >= d0.size, "input layer witness missing");
     pair_reset(ctx->pair[0], -1, 0);
     pair_reset(ctx->pair[1], d0.bit_length, d0.size);
+    ctx->in_dotprod_p1 = false;
     pair_t &P = ctx->pair[1];
     ctx->r_u[0].resize(d0.bit_length);
     ctx->add_term = fr_t::zero();

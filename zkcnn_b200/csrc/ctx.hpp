@@ -106,6 +106,7 @@ struct zk_ctx {
     zk::pair_t pair[2];
     zk::table_t mdp;            // DOT_PROD multiplier table (mult_array[1] of size 2^fft_bl)
     uint32_t mdp_n = 0;
+    bool in_dotprod_p1 = false; // pair[1].m plays V_mult[0] of a DOT_PROD phase (live below dp_live0)
     uint32_t dp_live0 = 0;      // live entries of V_mult[0] in the DOT_PROD phase (cubic_args_t::live0)
     zk::rt::dbuf beta_g, beta_g_alt, beta_gs, beta_u;
     uint32_t beta_g_entries = 0;

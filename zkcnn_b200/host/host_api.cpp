@@ -76,6 +76,8 @@ struct zkh_session {
     vector<G> last_gens;
     bool built = false;
     int device = 0;
+    FILE *table_dump = nullptr;
+    ~zkh_session() { if (table_dump) fclose(table_dump); }
 };
 
 #define ZKH_BEGIN try {
@@ -216,6 +218,18 @@ void *zkh_context(zkh_session *s) { return s ? s->p.context() : nullptr; }
 int zkh_inferred_class(zkh_session *s, int picture) {
     if (!s || picture < 0 || (size_t) picture >= s->nn->inferred.size()) return -1;
     return s->nn->inferred[picture];
+}
+
+int zkh_table_dump(zkh_session *s, const char *path) {
+    ZKH_BEGIN
+    if (!s) throw std::invalid_argument("null session");
+    if (s->table_dump) { fclose(s->table_dump); s->table_dump = nullptr; }
+    if (path) {
+        s->table_dump = fopen(path, "w");
+        if (!s->table_dump) throw std::runtime_error(std::string("cannot write ") + path);
+    }
+    s->p.setTableDump(s->table_dump);
+    ZKH_END
 }
 
 int zkh_circuit_dump(zkh_session *s, const char *path, int with_hashes) {

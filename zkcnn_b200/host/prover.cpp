@@ -204,30 +204,48 @@ void prover::sumcheckInitAll(const vector<F>::const_iterator &r_0_from_v) {   //
     prove_timer.start();
     check(zk_sumcheck_init_all(ctx_, last_bl ? w(r_0_from_v[0]) : nullptr, last_bl), "zk_sumcheck_init_all");
     prove_timer.stop();
+    level_ = (int) C.size;
 }
 
 void prover::sumcheckInit(const F &alpha_0, const F &beta_0) {   // src/prover.cpp:43-52
     prove_timer.start();
     check(zk_sumcheck_init(ctx_, w(alpha_0), w(beta_0)), "zk_sumcheck_init");
     prove_timer.stop();
+    --level_;   // sumcheck_id of the reference (src/prover.cpp:50)
+}
+
+void prover::dumpTables(int layer, const char *tag, bool dot, int first_b) {
+    if (!table_dump_) return;
+    for (int b = first_b; b < 2; ++b) {
+        uint64_t hv = 0, hm = 0, n = 0, nm = 0;
+        // DOT_PROD phase 1: the device keeps V_mult[1] as the V table and V_mult[0] as the mult table of pair 1, the 2^fft_bl multiplier apart
+        const int sel_v = dot ? (b == 0 ? 3 : 2) : 2 * b, sel_m = dot ? 4 : 2 * b + 1;
+        check(zk_debug_table_hash(ctx_, sel_v, &hv, &n), "zk_debug_table_hash");
+        if (dot && b == 1) hm = 0xcbf29ce484222325ULL;
+        else check(zk_debug_table_hash(ctx_, sel_m, &hm, &nm), "zk_debug_table_hash");
+        fprintf(table_dump_, "T %d %s %d n %lu v %016lx m %016lx\n", layer, tag, b, (unsigned long) n, (unsigned long) hv, (unsigned long) hm);
+    }
 }
 
 void prover::sumcheckDotProdInitPhase1() {   // src/prover.cpp:57-95
     prove_timer.start();
     check(zk_sumcheck_dotprod_init_phase1(ctx_), "zk_sumcheck_dotprod_init_phase1");
     prove_timer.stop();
+    dumpTables(level_, "dp1", true, 0);
 }
 
 void prover::sumcheckInitPhase1(const F &relu_rou_0) {   // src/prover.cpp:155-239
     prove_timer.start();
     check(zk_sumcheck_init_phase1(ctx_, w(relu_rou_0)), "zk_sumcheck_init_phase1");
     prove_timer.stop();
+    dumpTables(level_, "p1", false, 0);
 }
 
 void prover::sumcheckInitPhase2() {   // src/prover.cpp:241-310
     prove_timer.start();
     check(zk_sumcheck_init_phase2(ctx_), "zk_sumcheck_init_phase2");
     prove_timer.stop();
+    dumpTables(level_, "p2", false, 0);
 }
 
 cubic_poly prover::sumcheckDotProdUpdate1(const F &previous_random) {   // src/prover.cpp:103-144
@@ -308,6 +326,7 @@ void prover::sumcheckLiuInit(const vector<F> &s_u, const vector<F> &s_v) {   // 
     prove_timer.start();
     check(zk_sumcheck_liu_init(ctx_, w(s_u[0]), w(s_v[0]), (uint32_t) s_u.size()), "zk_sumcheck_liu_init");
     prove_timer.stop();
+    dumpTables(0, "liu", false, 1);
 }
 
 quadratic_poly prover::sumcheckLiuUpdate(const F &previous_random) {   // src/prover.cpp:385-394
@@ -365,7 +384,7 @@ hyrax_bls12_381::polyProver &prover::commitInput(const vector<G> &gens) {   // s
         for (size_t i = old; i < val[0].size(); ++i) val[0][i].clear();
     }
 #ifdef ZKCNN_DROPIN_CPU_HYRAX
-    poly_p = std::make_unique<hyrax_bls12_381::polyProver>(val[0], gens);
+    poly_p = std::make_unique<hyrax_bls12_381::polyProver>(val[0], gens, transcript_);
 #else
     // the device copy of val[0] is already zero-padded (zk_witness_layer); nothing is uploaded again
     poly_p = std::make_unique<hyrax_bls12_381::polyProver>(ctx_, gens, (unsigned char) C.circuit[0].bit_length, transcript_);

@@ -14,6 +14,8 @@
 #ifdef ZKCNN_DROPIN
 #ifndef ZKCNN_DROPIN_CPU_HYRAX
 #include "polyProver.hpp"   // ours first: its include guard keeps the reference's hyrax/src/polyProver.hpp out
+#else
+#include "cpu_hyrax_proxy.hpp"   // the reference's CPU polyProver behind a recording forwarder
 #endif
 #include "global_var.hpp"   // reference: src/
 #include "circuit.h"
@@ -97,6 +99,9 @@ public:
     // page-lock val[] so that the witness upload is a direct DMA from host memory (call after val is final; undone by the destructor)
     void pinWitness();
     void unpinWitness();
+    // test hook: after every Init* call append one line per table pair to `f` with the hashes of the bookkeeping tables, in the format of
+    // oracle/harness/record_proxy.hpp (ref_run --dump-dir): per-function parity of K4 / K4b / K5 / K5b / K6 against the reference
+    void setTableDump(FILE *f) { table_dump_ = f; }
     uint64_t lastUploadBytes() const { return last_upload_bytes_; }
     uint64_t gpuLaunches() const { return ctx_ ? zk_ctx_launch_count(ctx_) : 0; }
     zk_ctx *context() { return ctx_; }
@@ -127,6 +132,9 @@ private:
     std::vector<const void *> pinned_;
     u64 proof_size = 0;
     zkcnn_b200::Transcript *transcript_ = nullptr;
+    FILE *table_dump_ = nullptr;
+    int level_ = 0;   // the layer whose sumcheck is running
+    void dumpTables(int layer, const char *tag, bool dot, int first_b);
     unique_ptr<hyrax_bls12_381::polyProver> poly_p;
 
     friend neuralNetwork;
