@@ -63,6 +63,8 @@ int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_
  *   "tma_min_entries"  (131072) fold rounds on tables of at least this many entries use the TMA-staged k_round_quad_tma
  *   "derive_b"         (1)      streaming rounds take b from the previous round's polynomial (0: always three products)
  *   "pdl"              (1)      k_round_quad_thin is launched with programmatic stream serialization
+ *   "unit_batch"       (0)      zk_fold_rounds2 runs its rounds through the phase-batched path (as zk_sumcheck_update_batch does)
+ *   "tail"             (1)      batched phases run all rounds on tables of at most tail_max_entries (1024) in one launch (k_round_tail)
  *   "cubic_tma"        (1)      DOT_PROD fold rounds on tables of at least tma_min_entries use k_round_cubic_tma
  *   "cubic_max_grid"   (none)   cap on the CTAs of a K2 launch (tests: several iterations per thread on small tables)
  *   "cubic_factored_min_iters" (4) k_round_cubic switches to the factored form from this many output pairs per thread

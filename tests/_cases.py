@@ -117,6 +117,22 @@ def case_cubic_rounds(lib, shapes=((1, 0, 2, 2), (3, 1, 5, 8), (5, 2, 12, 29), (
             assert [tuple(fr_from_words(got[j])) for j in range(bits)] == want, (bits, m_bits, live0, live1)
 
 
+def case_fold_rounds_two_pairs(lib, shapes=((3, 5, 2, 4), (6, 40, 4, 9), (9, 400, 11, 2048), (11, 1500, 5, 32), (12, 4096, 12, 3000), (13, 8000, 7, 100)), tunables=None):
+    """two table pairs in lock step (prover::sumcheckUpdate, src/prover.cpp:368-383) against the port: (bits0, live0, bits1, live1); the
+    shorter pair collapses into add_term on the way.  With unit_batch the rounds go through the phase-batched path and its fused tail."""
+    rng = O.SplitMix64(424)
+    with Context(lib) as ctx:
+        for k, v in (tunables or {}).items():
+            ctx.set_tunable(k, v)
+        for b0, l0, b1, l1 in shapes:
+            V0, M0, V1, M1 = rand_fr(rng, l0, "witness"), rand_fr(rng, l0), rand_fr(rng, l1), rand_fr(rng, l1, "witness")
+            n = max(b0, b1)
+            ch = rand_fr(rng, n)
+            want = O.sumcheck_rounds([O.FoldState(V0, M0, b0), O.FoldState(V1, M1, b1)], ch, n)
+            got = ctx.fold_rounds2(fr_to_words(V0), fr_to_words(M0), b0, fr_to_words(V1), fr_to_words(M1), b1, fr_to_words(ch), n)
+            assert [tuple(fr_from_words(got[j])) for j in range(n)] == want, (b0, l0, b1, l1)
+
+
 def case_round_kats(lib, kat, tunables=None):
     """K1 / K2 / K6b against known answers minted by calling the REFERENCE prover's own round functions on hand-made tables
     (oracle/harness/kat_gen.cpp: sumcheckUpdate, sumcheckDotProdUpdate1, Vres; tests/golden/kat.json)"""
@@ -239,8 +255,9 @@ def case_hyrax_vs_port(lib, bl=7, seed=606):
         assert fr_from_words(ctx.poly_bullet_open()) == [hp.bullet_open()]
 
 
-def prove_and_compare(hostlib, model, network, pic_cnt, input_path, seed, flags, golden_name, golden_dir, device=0):
-    """whole proof through the stand-alone host side; transcript and circuit must equal the reference's"""
+def prove_and_compare(hostlib, model, network, pic_cnt, input_path, seed, flags, golden_name, golden_dir, device=0, tables=False):
+    """whole proof through the stand-alone host side; transcript and circuit must equal the reference's.  tables: also compare the
+    hashes of the bookkeeping tables after every Init* call with the reference's (see tables_and_compare)"""
     import tempfile
     with Session(hostlib, model, network, pic_cnt, device) as s:
         s.input_file(input_path)
@@ -250,8 +267,17 @@ def prove_and_compare(hostlib, model, network, pic_cnt, input_path, seed, flags,
             mine = f.read()
         want = open(os.path.join(golden_dir, golden_name + ".circuit.txt")).read()
         assert mine == want, "circuit (gates / ori_id / values) differs from the reference's"
-        st = s.prove(seed, flags)
-        proof = s.proof()
+        with tempfile.NamedTemporaryFile("r", suffix=".txt") as f:
+            if tables:
+                s.table_dump(f.name)
+            st = s.prove(seed, flags)
+            proof = s.proof()
+            if tables:
+                s.table_dump(None)
+                mine_t = f.read().splitlines()
+                want_t = open(os.path.join(golden_dir, golden_name + ".tables.txt")).read().splitlines()
+                bad = [(x, y) for x, y in zip(mine_t, want_t) if x != y]
+                assert len(mine_t) == len(want_t) and not bad, f"first differing table: ours {bad[0][0]!r} reference {bad[0][1]!r}" if bad else "table count"
     want = open(os.path.join(golden_dir, golden_name + ".transcript.bin"), "rb").read()
     assert len(proof) == len(want)
     assert proof == want, "proof transcript differs from the reference's"

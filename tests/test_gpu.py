@@ -64,6 +64,14 @@ def test_cubic_rounds_every_kernel_variant(gpu_lib):
     cases.case_cubic_rounds(gpu_lib, shapes=multi, tunables={"cubic_max_grid": 40, "tma_min_entries": 128})
 
 
+def test_fold_rounds_two_pairs_and_fused_tail(gpu_lib, kat):
+    cases.case_fold_rounds_two_pairs(gpu_lib)
+    cases.case_fold_rounds_two_pairs(gpu_lib, tunables={"unit_batch": 1})
+    cases.case_fold_rounds_two_pairs(gpu_lib, tunables={"unit_batch": 1, "tail_max_entries": 64})
+    cases.case_fold_rounds_two_pairs(gpu_lib, tunables={"unit_batch": 1, "tail": 0})
+    cases.case_round_kats(gpu_lib, kat, tunables={"unit_batch": 1})
+
+
 def test_round_kats_from_the_reference(gpu_lib, kat):
     cases.case_round_kats(gpu_lib, kat)
     cases.case_round_kats(gpu_lib, kat, tunables={"thin_max_pairs": 0, "tma_min_entries": 1 << 40, "cubic_factored_min_iters": 1, "cubic_tma": 0})

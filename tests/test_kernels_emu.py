@@ -33,6 +33,15 @@ def test_cubic_rounds(emu_lib):
     cases.case_cubic_rounds(emu_lib, shapes=multi, tunables={"cubic_max_grid": 3, "cubic_factored_min_iters": 1 << 30})
 
 
+def test_fold_rounds_two_pairs_and_fused_tail(emu_lib, kat):
+    small = ((3, 5, 2, 4), (6, 40, 4, 9), (9, 400, 11, 2048), (11, 1500, 5, 32))
+    cases.case_fold_rounds_two_pairs(emu_lib, shapes=small)
+    cases.case_fold_rounds_two_pairs(emu_lib, shapes=small, tunables={"unit_batch": 1})                         # fused tail from 1024 entries down
+    cases.case_fold_rounds_two_pairs(emu_lib, shapes=small, tunables={"unit_batch": 1, "tail_max_entries": 64})
+    cases.case_fold_rounds_two_pairs(emu_lib, shapes=small, tunables={"unit_batch": 1, "tail": 0})
+    cases.case_round_kats(emu_lib, kat, tunables={"unit_batch": 1})
+
+
 def test_round_kats_from_the_reference(emu_lib, kat):
     cases.case_round_kats(emu_lib, kat)
     cases.case_round_kats(emu_lib, kat, tunables={"thin_max_pairs": 0, "cubic_factored_min_iters": 1})

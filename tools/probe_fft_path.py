@@ -15,9 +15,17 @@ s = zkcnn_b200.session("vgg", gen.CONFIGS[model], pics, device=0)
 s.input_values(gen.generate(model).astype(np.float64))
 t0 = time.perf_counter(); s.build(); print(f"build {time.perf_counter() - t0:.1f} s", file=sys.stderr)
 t0 = time.perf_counter(); st = s.prove(1, 0); print(f"first proof (upload + schedules) {time.perf_counter() - t0:.2f} s fnv {st['fnv1a']:016x} ok {st['ok']} launches {st['gpu_launches']}", file=sys.stderr)
+nvtx = None
+if os.environ.get("PROBE_NVTX"):      # ncu --nvtx --nvtx-include "proof/": profile exactly the launches of the last un-instrumented proof
+    import torch
+    nvtx = torch.cuda.nvtx
 for i in range(n):
+    if nvtx and i == n - 1:
+        nvtx.range_push("proof")
     t0 = time.perf_counter(); st = s.prove(100 + i, REAL_GENERATORS | WITNESS_RESIDENT | PROVER_ONLY)
-    print(f"resident {i}: {(time.perf_counter() - t0) * 1e3:.2f} ms  prove_s {st['prove_s']:.4f} poly_s {st['poly_s']:.4f} launches {st['gpu_launches']}", file=sys.stderr)
+    if nvtx and i == n - 1:
+        nvtx.range_pop()
+    print(f"resident {i}: {(time.perf_counter() - t0 - 0) * 1e3:.2f} ms  prove_s {st['prove_s']:.4f} poly_s {st['poly_s']:.4f} launches {st['gpu_launches']}", file=sys.stderr)
 ctx = s.context_handle()
 lib.dll.zk_profile_enable(ctx, 1)
 t0 = time.perf_counter(); s.prove(100, REAL_GENERATORS | WITNESS_RESIDENT | PROVER_ONLY); wall = time.perf_counter() - t0

@@ -62,6 +62,9 @@ int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
     else if (n == "tma_min_entries") ctx->tma_min_entries = value;
     else if (n == "derive_b") ctx->derive_b_enabled = value ? 1u : 0u;
     else if (n == "pdl") ctx->pdl_enabled = value ? 1u : 0u;
+    else if (n == "unit_batch") ctx->unit_batch = value ? 1u : 0u;
+    else if (n == "tail") ctx->tail_enabled = value ? 1u : 0u;
+    else if (n == "tail_max_entries") ctx->tail_max_entries = (uint32_t) std::min<uint64_t>(value, kTailMaxEntries);
     else if (n == "cubic_tma") ctx->cubic_tma_enabled = value ? 1u : 0u;
     else if (n == "cubic_max_grid") ctx->cubic_max_grid = (uint32_t) std::max<uint64_t>(1, value);
     else if (n == "cubic_factored_min_iters") ctx->cubic_factored_min_iters = (uint32_t) std::max<uint64_t>(1, value);
@@ -833,6 +836,18 @@ int zk_fold_rounds2(zk_ctx *ctx, const uint64_t *V0, const uint64_t *M0, int32_t
     ctx->in_dotprod_p1 = false;
     ctx->add_term = fr_t::zero();
     ctx->round = 0;
+    if (ctx->unit_batch) {   // the phase-batched path (zk_sumcheck_update_batch), fused tail included
+        std::vector<fr_t> prevs(n_rounds, fr_t::zero());
+        for (uint32_t j = 1; j < n_rounds; ++j) prevs[j] = fr_load(r + 4 * (j - 1));
+        round_quadratic_batch(ctx, prevs.data(), n_rounds, 3u, [&](uint32_t j, const round_rec_t &rec, const fr_t *h_res) {
+            ctx->add_term = ctx->add_term * (fr_t::one() - prevs[j]);
+            fr_t abc[3];
+            round_quadratic_book(ctx, rec, h_res, abc);
+            abc[1] = abc[1] - ctx->add_term;
+            abc[2] = abc[2] + ctx->add_term;
+            for (int k = 0; k < 3; ++k) fr_store(polys + (size_t) (3 * j + k) * 4, abc[k]);
+        });
+    } else
     for (uint32_t j = 0; j < n_rounds; ++j) {
         const fr_t prev = j == 0 ? fr_t::zero() : fr_load(r + 4 * (j - 1));
         ++ctx->round;

@@ -702,6 +702,65 @@ static void round_quadratic(zk_ctx *ctx, const fr_t &prev, unsigned mask, fr_t a
         round_quadratic_book(ctx, rec, got, abc);
     } else round_quadratic_book(ctx, rec, ctx->res_h, abc);
 }
+// The remaining rounds of a phase in ONE launch (k_round_tail): same per-round results in the same slots as round_quadratic_launch
+// would leave, the host-side table state advanced to what the round-by-round path would have reached.
+static void round_tail_launch(zk_ctx *ctx, const fr_t *prevs, uint32_t n_rounds, unsigned mask, fr_t *slots_d, round_rec_t *recs) {
+#ifndef ZK_EMU
+    static const bool attr_set = [] {
+        rt::check(cudaFuncSetAttribute(k_round_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTailSmemBytes), "cudaFuncSetAttribute");
+        return true;
+    }();
+    (void) attr_set;
+#endif
+    tail_args_t A;
+    memset(&A, 0, sizeof A);
+    A.first = ctx->round == 0 ? 1u : 0u;
+    A.n_rounds = n_rounds;
+    for (uint32_t j = 0; j < n_rounds; ++j) A.r[j] = prevs[j];
+    A.slots = slots_d;
+    uint64_t bytes = 0;
+    for (int b = 0; b < 2; ++b) {
+        pair_t &P = ctx->pair[b];
+        if (!(mask & (1u << b)) || P.n_eval == 0) continue;
+        A.v_in[b] = P.v.cur; A.m_in[b] = P.m.cur;
+        A.n_in[b] = P.n_eval; A.live[b] = P.live;
+        bytes += (uint64_t) std::min(P.live, P.n_eval) * 64;
+    }
+    // host-side state, round by round (sizes only: which pair folds, which collapses)
+    for (uint32_t j = 0; j < n_rounds; ++j) {
+        ++ctx->round;
+        const bool first = ctx->round == 1;
+        round_rec_t &rec = recs[j];
+        rec = round_rec_t();
+        rec.first = first;
+        for (int b = 0; b < 2; ++b) {
+            pair_t &P = ctx->pair[b];
+            if (!(mask & (1u << b)) || P.n_eval == 0) continue;
+            const uint32_t n_after = first ? P.n_eval : P.n_eval >> 1;
+            if (n_after == 1) {
+                rec.fin[b] = rec.any_final = true;
+                P.collapsed = true;
+                P.n_eval = 0;
+            } else {
+                rec.quad[b] = rec.any_quad = true;
+                if (!first) { P.n_eval >>= 1; P.live = (P.live + 1) >> 1; }
+            }
+        }
+    }
+    for (int b = 0; b < 2; ++b) {
+        pair_t &P = ctx->pair[b];
+        if (!A.n_in[b]) continue;
+        A.v_out[b] = table_fold_buf(P.v, 2);
+        A.m_out[b] = table_fold_buf(P.m, 2);
+        if (P.n_eval) {   // what is left for the Finalize call
+            table_advance(P.v);
+            table_advance(P.m);
+            P.live = std::min(P.live, P.n_eval);
+        }
+    }
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_FOLD_SMALL, bytes, k_round_tail, dim3(1), dim3(kTailBlock), kTailSmemBytes, A);
+}
+
 // A whole phase queued without waiting for the host in between: round j folds with prevs[j] (prevs[0] = 0).  Legitimate
 // because the verifier draws every challenge of a phase BEFORE its first round (src/verifier.cpp:156-160, 207, 275-279):
 // the prover messages are the same field elements as in the round-by-round protocol, in the same order.  `hook` books
@@ -716,6 +775,14 @@ template <class Hook> static void round_quadratic_batch(zk_ctx *ctx, const fr_t 
     }
     std::vector<round_rec_t> recs(n_rounds);
     for (uint32_t j = 0; j < n_rounds; ++j) {
+        // the tail of the phase in one launch once every table that takes part fits the CTA-resident kernel
+        uint32_t biggest = 0;
+        for (int b = 0; b < 2; ++b)
+            if (mask & (1u << b)) biggest = std::max(biggest, ctx->pair[b].n_eval);
+        if (ctx->tail_enabled && biggest <= ctx->tail_max_entries && n_rounds - j <= (uint32_t) kTailMaxRounds && n_rounds - j >= 2) {
+            round_tail_launch(ctx, prevs + j, n_rounds - j, mask, ctx->batch_res.as<fr_t>() + (size_t) j * 16, recs.data() + j);
+            break;
+        }
         ++ctx->round;
         recs[j] = round_quadratic_launch(ctx, prevs[j], mask, ctx->batch_res.as<fr_t>() + (size_t) j * 16);
     }

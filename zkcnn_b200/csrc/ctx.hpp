@@ -128,6 +128,9 @@ struct zk_ctx {
     uint64_t tma_min_entries = 1ull << 17;
     uint32_t pdl_enabled = 1;                // k_round_quad_thin launched with programmatic stream serialization
     uint32_t derive_b_enabled = 1;           // streaming rounds: b from the previous round's polynomial (0: always three products)
+    uint32_t unit_batch = 0;                 // zk_fold_rounds2 goes through the phase-batched path (tests)
+    uint32_t tail_enabled = 1;               // batched phases: all rounds on tables of at most tail_max_entries in one launch (k_round_tail)
+    uint32_t tail_max_entries = 1024;
     uint32_t cubic_tma_enabled = 1;          // DOT_PROD fold rounds on large tables use k_round_cubic_tma
     uint32_t cubic_max_grid = 1u << 20;       // cap on the CTAs of a K2 launch (tests: forces several iterations per thread on small tables)
     uint32_t cubic_factored_min_iters = 4;   // k_round_cubic: factored form from this many output pairs per thread

@@ -513,6 +513,154 @@ __global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A)
     round_quad_publish(A, sh_tot, sh_fr);
 }
 
+// --------------------------------------------------------------------------------------------------------------------
+// K1, the TAIL of a phase in ONE launch (batched phases only: every challenge of the phase is known up front).  Once both
+// table pairs are down to kTailMaxEntries entries, a single CTA keeps them in shared memory and runs all remaining rounds:
+// per round the four-lane split of k_round_quad_thin, the exact limb sums inside the CTA, the collapse of an exhausted pair
+// (src/prover.cpp:400-404) and, after the last round, the (at most two) surviving entries of each table written back for the
+// Finalize call.  Replaces ~10 dependent launches per phase (about a thousand per vgg11 proof) by one.
+// --------------------------------------------------------------------------------------------------------------------
+constexpr int kTailBlock = 512;
+constexpr uint32_t kTailMaxEntries = 1024;
+constexpr int kTailMaxRounds = 12;
+constexpr uint32_t kTailSmemBytes = 4 * (kTailMaxEntries + kTailMaxEntries / 2) * sizeof(fr_t);   // per table: buffer A (1024) + buffer B (512)
+
+struct tail_args_t {
+    const fr_t *v_in[2], *m_in[2];   // tables at the start of the tail: n_in entries, the first `live` non-zero
+    uint32_t n_in[2], live[2];       // n_in == 0: the pair takes no part
+    uint32_t first;                  // the first tail round is the first round of the phase (previous_random = 0): no fold
+    uint32_t n_rounds;
+    fr_t r[kTailMaxRounds];          // previous_random of each tail round
+    fr_t *slots;                     // [n_rounds][16] result blocks: (a, b, c) at 0, collapse values (v, m) of pair p at 8 + 2p
+    fr_t *v_out[2], *m_out[2];       // the entries left after the last round (<= 2 per table)
+};
+
+__global__ void __launch_bounds__(kTailBlock, 1) k_round_tail(tail_args_t A) {
+    ZK_DYN_SMEM(fr_t, sm);
+    __shared__ unsigned long long sh_warp[(kTailBlock / 32) * kRoundLimbs];
+    __shared__ unsigned long long sh_tot[kRoundLimbs];
+    __shared__ fr_t sh_fr[12];
+    ZK_PDL_ENTRY();
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, role = tid & 3u, grp = tid >> 2;
+    constexpr uint32_t kGroups = kTailBlock / 4;
+    // table t = 2 * pair + (0: V, 1: mult); buffer A of table t at sm + t * 1536, buffer B behind it
+    fr_t *cur[4], *nxt[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { cur[t] = sm + t * (kTailMaxEntries + kTailMaxEntries / 2); nxt[t] = cur[t] + kTailMaxEntries; }
+    uint32_t n[2] = {A.n_in[0], A.n_in[1]};
+    for (int p = 0; p < 2; ++p)
+        for (uint32_t i = tid; i < n[p]; i += kTailBlock) {
+            st_fr(cur[2 * p] + i, ld_fr_live(A.v_in[p], i, A.live[p]));
+            st_fr(cur[2 * p + 1] + i, ld_fr_live(A.m_in[p], i, A.live[p]));
+        }
+    __syncthreads();
+    for (uint32_t j = 0; j < A.n_rounds; ++j) {
+        const bool fold = !(A.first && j == 0);
+        const fr_t r = A.r[j];
+        fr_t *slot = A.slots + (size_t) j * 16;
+        uint32_t Q[2], fin[2];
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t n_after = n[p] ? (fold ? n[p] >> 1 : n[p]) : 0;
+            fin[p] = n_after == 1;
+            Q[p] = fin[p] ? 0 : n_after >> 1;
+        }
+        // collapse of an exhausted pair: its two tables evaluated at r (four lanes of warp 15 -- idle in every round that has one)
+        if (tid >= kTailBlock - 4) {
+            const int t = tid - (kTailBlock - 4), p = t >> 1;
+            if (fin[p]) {
+                fr_t x0 = ld_fr(cur[t]);
+                if (fold) { const fr_t x1 = ld_fr(cur[t] + 1); x0 = x0 + r * (x1 - x0); }
+                st_fr(slot + 8 + 2 * p + (t & 1), x0);
+            }
+        }
+        const uint32_t tasks = Q[0] + Q[1];
+        fr_lazy_t acc;
+        acc.clear();
+        for (uint32_t t0 = 0; t0 < tasks; t0 += kGroups) {   // CTA-uniform trip count: every lane takes part in the shuffles
+            const uint32_t t = t0 + grp;
+            const bool on = t < tasks;
+            const int p = (on && t >= Q[0]) ? 1 : 0;
+            const uint32_t q = on ? (p ? t - Q[0] : t) : 0;
+            fr_t a_op = fr_t::zero(), b_op = fr_t::zero();
+            if (fold) {
+                const fr_t *src = cur[2 * p + (role >> 1)];          // roles 0, 1: the V table, roles 2, 3: the mult table
+                const uint32_t idx = 4 * q + 2 * (role & 1u);
+                const fr_t x0 = on ? ld_fr(src + idx) : fr_t::zero(), x1 = on ? ld_fr(src + idx + 1) : fr_t::zero();
+                const fr_t y = x0 + r * fr_t::sub_lazy(x1, x0);
+                if (on) st_fr(nxt[2 * p + (role >> 1)] + 2 * q + (role & 1u), y);
+                fr_t o1, o2, d, d2;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o1.v[k] = __shfl_xor_sync(0xffffffffu, y.v[k], 1);
+                d = (role & 1u) ? fr_t::sub_lazy(y, o1) : fr_t::sub_lazy(o1, y);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    o2.v[k] = __shfl_xor_sync(0xffffffffu, y.v[k], 2);
+                    d2.v[k] = __shfl_xor_sync(0xffffffffu, d.v[k], 2);
+                }
+                if (role < 2) { a_op = y; b_op = o2; }          // v0 m0 (role 0), v1 m1 (role 1)
+                else if (role == 2) { a_op = d; b_op = d2; }    // (m1 - m0)(v1 - v0)
+            } else if (on) {
+                const fr_t *v = cur[2 * p], *m = cur[2 * p + 1];
+                if (role < 2) { a_op = ld_fr(v + 2 * q + role); b_op = ld_fr(m + 2 * q + role); }
+                else if (role == 2) {
+                    a_op = fr_t::sub_lazy(ld_fr(v + 2 * q + 1), ld_fr(v + 2 * q));
+                    b_op = fr_t::sub_lazy(ld_fr(m + 2 * q + 1), ld_fr(m + 2 * q));
+                }
+            }
+            acc.mac(a_op, b_op);
+        }
+        // exact limb sums: role 2 -> A, role 0 -> C, role 1 -> E; only the warps that had a task take part
+        const uint32_t active_groups = tasks < kGroups ? tasks : kGroups;
+        const uint32_t active_warps = (active_groups * 4 + 31) >> 5;
+#ifdef ZK_EMU
+        const bool take_part = true;    // (the test emulator implements warp collectives with a CTA-wide exchange: every thread must call them)
+#else
+        const bool take_part = warp < active_warps;
+#endif
+        if (take_part) {
+#pragma unroll
+            for (int sl = 0; sl < 3; ++sl) {
+                const bool mine = role == (sl == 0 ? 2u : sl == 1 ? 0u : 1u);
+#pragma unroll
+                for (int k = 0; k < fr_lazy_t::W; ++k) {
+                    const uint32_t x = mine ? acc.w[k] : 0u;
+                    const uint32_t lo = __reduce_add_sync(0xffffffffu, x & 0xffffu);
+                    const uint32_t hi = __reduce_add_sync(0xffffffffu, x >> 16);
+                    if (lane == (uint32_t) (k & 31)) sh_warp[warp * kRoundLimbs + sl * fr_lazy_t::W + k] = (unsigned long long) lo + ((unsigned long long) hi << 16);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < kRoundLimbs) {
+            unsigned long long t = 0;
+            for (uint32_t w = 0; w < active_warps; ++w) t += sh_warp[w * kRoundLimbs + tid];
+            sh_tot[tid] = t;
+        }
+        __syncthreads();
+        round_args_t R;
+        R.out = slot;
+        R.flag = nullptr;
+        R.tagged = nullptr;
+        R.seq = 0;
+        round_quad_publish(R, sh_tot, sh_fr);    // (a, b, c) = (A, E - A - C, C) -> slot[0..2]
+        for (int p = 0; p < 2; ++p) {
+            if (fin[p]) n[p] = 0;
+            else if (fold && n[p]) {
+                n[p] >>= 1;
+                fr_t *t0 = cur[2 * p], *t1 = cur[2 * p + 1];
+                cur[2 * p] = nxt[2 * p]; cur[2 * p + 1] = nxt[2 * p + 1];
+                nxt[2 * p] = t0; nxt[2 * p + 1] = t1;
+            }
+        }
+        __syncthreads();   // the folded tables and sh_* are settled before the next round touches them
+    }
+    for (int p = 0; p < 2; ++p)
+        if (tid < n[p]) {
+            st_fr(A.v_out[p] + tid, ld_fr(cur[2 * p] + tid));
+            st_fr(A.m_out[p] + tid, ld_fr(cur[2 * p + 1] + tid));
+        }
+}
+
 #if !defined(ZK_EMU)
 // --------------------------------------------------------------------------------------------------------------------
 // K1, HBM-streaming rounds (tables of 2^17 entries and more): the same arithmetic as k_round_quad, fed by TMA.
