@@ -63,6 +63,7 @@ int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_
  *   "tma_min_entries"  (131072) fold rounds on tables of at least this many entries use the TMA-staged k_round_quad_tma
  *   "derive_b"         (1)      streaming rounds take b from the previous round's polynomial (0: always three products)
  *   "pdl"              (1)      k_round_quad_thin is launched with programmatic stream serialization
+ *   "eval_schedules"   (1)      zk_circuit_layer also builds the evaluation schedules of zk_witness_generate (+12 bytes per gate)
  *   "unit_batch"       (0)      zk_fold_rounds2 runs its rounds through the phase-batched path (as zk_sumcheck_update_batch does)
  *   "tail"             (1)      batched phases run all rounds on tables of at most tail_max_entries (1024) in one launch (k_round_tail)
  *   "cubic_tma"        (1)      DOT_PROD fold rounds on tables of at least tma_min_entries use k_round_cubic_tma
@@ -116,6 +117,21 @@ int zk_witness_commit_prefetch(zk_ctx *ctx);
  * prefetch != 0: into the shadow buffer on the copy stream, made current by zk_witness_commit_prefetch */
 int zk_witness_layer_compact(zk_ctx *ctx, uint32_t layer_id, const int64_t *small, uint64_t n, const uint32_t *wide_idx, const uint64_t *wide_val,
                              uint32_t n_wide, int prefetch);
+
+/* ---- witness generation on the device: what neuralNetwork::create computes while it builds the circuit (src/neuralNetwork.cpp:899-965,
+ * src/utils.cpp:105-145): gate values layer by layer, number-theoretic transforms of the FFT layers, bit decompositions -----------------
+ * zk_circuit_aux_ops: the auxiliary inputs the construction of layer `layer_id` derives from earlier gate values (prepareSignBit /
+ * prepareDecmpBit / prepareMax), n triples {src, dst, meta}: dst indexes val[0]; meta bits 0-7 = bit position, bits 8-9 = 0 sign bit,
+ * 1 magnitude bit, 2 running maximum of max(0, value); bit 10 = the source is val[0][src], else val[layer_id - 1][src].  Call it for every
+ * layer >= 1 (n = 0 where there is none) after zk_circuit_layer. */
+int zk_circuit_aux_ops(zk_ctx *ctx, uint32_t layer_id, const uint32_t *ops, uint64_t n);
+/* val[0][0, n_image) <- image, then every auxiliary input and every layer re-evaluated on the device; the weights in val[0] are the
+ * resident ones (upload a complete witness once).  ranges (NULL or 2 x n_layers values): per layer the largest non-negative value and
+ * the largest magnitude of a negative one (what getNextBit, :967-977, turns into the next quantisation scale). */
+int zk_witness_generate(zk_ctx *ctx, const uint64_t *image, uint64_t n_image, uint64_t *ranges);
+int zk_witness_read(zk_ctx *ctx, uint32_t layer_id, uint64_t first, uint64_t n, uint64_t *out);
+/* FNV-1a-64 of the canonical encodings of val[layer_id][0, n) on the device (parity tests: the h_val column of the golden circuit dumps) */
+int zk_debug_layer_hash(zk_ctx *ctx, uint32_t layer_id, uint64_t n, uint64_t *fnv1a);
 
 /* ---- GKR prover: one entry point per public member of class prover ---------------------------------------------- */
 int zk_prover_init(zk_ctx *ctx);                                                             /* prover.cpp:17  */

@@ -52,7 +52,7 @@ typedef struct {
     double gkr_kb, poly_kb;     /* proof size as the reference counts it */
     uint64_t h2d_bytes;         /* witness bytes copied host->device for this proof */
     uint32_t checks;            /* what the verifier checked: ZKH_CHECKED_* */
-    uint32_t reserved;
+    uint32_t witness_path;      /* 0: the witness zkh_build made (zkh_prove); 1: regenerated on the device; 2: circuit rebuilt on the host (zkh_prove_image) */
 } zkh_stats;
 enum {
     ZKH_CHECKED_ROUND_SUMS = 1,   /* p(0) + p(1) = claim for every sumcheck round; y and bulletOpen of the opening */
@@ -71,6 +71,16 @@ int zkh_input_file(zkh_session *s, const char *path);                    /* the 
 int zkh_input_values(zkh_session *s, const double *values, uint64_t n);  /* same numbers, in memory */
 int zkh_build(zkh_session *s);                                           /* circuit + witness (neuralNetwork::create) */
 int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out);
+/* A NEW PICTURE for the model zkh_build prepared (same weights): `pixels` are the picture's decimals in the reference's order (the first
+ * zkh_input_count() - weights values of the input stream).  The witness is regenerated ON THE DEVICE (zk_witness_generate: only the picture
+ * crosses PCIe; layer values, transforms and bit decompositions are recomputed by CUDA kernels from the resident quantised weights), then
+ * proved like zkh_prove.  If the picture leads to different quantisation decisions than the one the circuit was built for (its own scale,
+ * or the activation scales that getNextBit derives, src/neuralNetwork.cpp:967-977, which fix the widths of the bit decompositions), or the
+ * model uses average pooling, the circuit is rebuilt on the host for the new picture instead; zkh_stats.witness_path says which path ran. */
+int zkh_prove_image(zkh_session *s, const double *pixels, uint64_t n_pixels, uint64_t seed, uint32_t flags, zkh_stats *out);
+/* only the witness part of zkh_prove_image; returns the path taken (1: regenerated on the device, 2: rebuilt on the host) or -1.  Follow it with
+ * zkh_prove(..., ZKH_WITNESS_RESIDENT) when it returned 1. */
+int zkh_set_image(zkh_session *s, const double *pixels, uint64_t n_pixels);
 /* start the host->device copy of the witness for the next zkh_prove now, on a second stream (what ZKH_PREFETCH_NEXT does
  * from inside a proof) */
 int zkh_prefetch_witness(zkh_session *s);

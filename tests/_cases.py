@@ -8,7 +8,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
 import zkcnn_oracle as O  # noqa: E402
-from zkcnn_b200._binding import (CHECK_PREDICATES, PROVER_ONLY, REAL_GENERATORS, Context, Session, fr_from_words, fr_to_words, g1_from_words,  # noqa: E402
+from zkcnn_b200._binding import (CHECK_PREDICATES, PROVER_ONLY, REAL_GENERATORS, WITNESS_RESIDENT, Context, Session, fr_from_words, fr_to_words, g1_from_words,  # noqa: E402
                                  g1_to_words)
 
 H = lambda s: int(s, 16)  # noqa: E731
@@ -288,6 +288,36 @@ def prove_and_compare(hostlib, model, network, pic_cnt, input_path, seed, flags,
         # polyProver.cpp:81-82 vs polyVerifier.cpp:58); the drop-in reproduces exactly that outcome
         assert st["ok"] == int(ref["ok"])
     return st
+
+
+def device_witness_case(lib, hostlib, model, network, pic_cnt, values, n_pix, golden_name, golden_dir, seed, other_image, device=0):
+    """a different picture first (so that every layer is really recomputed), then the golden picture again, both through the
+    device witness generator; the values of EVERY layer on the device must hash to the h_val the reference's circuit dump records for
+    the golden picture, and the proof of the regenerated witness must be the golden transcript"""
+    import ctypes as C
+    lib.dll.zk_debug_layer_hash.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint64)]
+    with Session(hostlib, model, network, pic_cnt, device) as s:
+        s.input_values(values)
+        s.build()
+        first = s.set_image(other_image)
+        assert first in (1, 2)
+        if first == 2:           # the other picture took different quantisation decisions: the circuit was rebuilt for it; rebuild for ours
+            assert s.set_image(values[:n_pix]) == 2
+        assert s.set_image(values[:n_pix]) == 1, "the picture the circuit was built for must take the device path"
+        ctx = s.context_handle()
+        bad = []
+        for ln in open(os.path.join(golden_dir, golden_name + ".circuit.txt")):
+            t = ln.split()
+            layer, nval, want = int(t[1]), int(t[t.index("nval") + 1]), t[t.index("h_val") + 1]
+            h = C.c_uint64(0)
+            assert lib.dll.zk_debug_layer_hash(ctx, layer, nval, C.byref(h)) == 0, lib.last_error()
+            if f"{h.value:016x}" != want:
+                bad.append((layer, t[2]))
+        assert not bad, f"device-generated witness differs from the reference's values in layers {bad}"
+        st = s.prove(seed, WITNESS_RESIDENT)
+        assert st["ok"] == 1 and st["checks"] == 15 and st["h2d_bytes"] == 0
+        assert s.proof() == open(os.path.join(golden_dir, golden_name + ".transcript.bin"), "rb").read()
+        return first
 
 
 def case_msm_many_rows(lib, n=64, rows=20, seed=808):

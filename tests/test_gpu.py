@@ -177,6 +177,22 @@ def test_against_the_reference_run_here(gpu_host, synthetic_inputs, tmp_path):
             assert s.proof() == out.read_bytes()
 
 
+def test_device_witness_generation(gpu_lib, gpu_host, synthetic_inputs):
+    """SURVEY 8 f-1 on the GPU: every layer of the device-generated witness hashes to the reference's values; golden transcript"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_synthetic_input as gen
+    lenet = gen.generate("lenet", 11).astype(np.float64)
+    other = np.random.default_rng(1).random(1024)
+    assert cases.device_witness_case(gpu_lib, gpu_host, "lenet", "", 2, lenet, 1024, "lenet_syn_p2_seed4", GOLDEN, 4, other) == 1
+    assert cases.device_witness_case(gpu_lib, gpu_host, "lenet", "", 1, lenet, 1024, "lenet_syn_p1_seed3", GOLDEN, 3, other) == 1
+    cfg = synthetic_inputs["smallvgg_config"]
+    vgg = gen.generate("vgg11", 5, cfg).astype(np.float64)
+    nudged = vgg[:3072].copy()
+    nudged[100:110] *= 0.999
+    cases.device_witness_case(gpu_lib, gpu_host, "vgg", cfg, 1, vgg, 3072, "smallvgg_p1_seed7", GOLDEN, 7, nudged)
+    cases.device_witness_case(gpu_lib, gpu_host, "vgg", cfg, 2, vgg, 3072, "smallvgg_p2_seed7", GOLDEN, 7, nudged)
+
+
 def test_vgg11_full_size(gpu_host, tmp_path):
     """BASELINE config 3: vgg11 / CIFAR-shaped input, pic_cnt = 1, 2^24-entry input layer, synthetic weights.  Circuit dump and
     transcript hash must equal what the compiled reference produced for the same input and seed (tests/golden)."""
@@ -203,6 +219,16 @@ def test_vgg11_full_size(gpu_host, tmp_path):
         assert st4["ok"] == 1 and st4["fnv1a"] == st["fnv1a"]
         # double-buffered witness: this proof uploads and starts the copy for the next one (SM-driven, from mapped host memory),
         # the next one adopts it
+        # a new picture: only 3072 field elements cross PCIe, the 16.7 M-entry witness is regenerated on the device; then the golden
+        # picture again the same way: the proof must be the golden one
+        nudged = values[:3072].astype(np.float64).copy()
+        nudged[500:600] *= 0.998
+        sti = s.prove_image(nudged, 1, PROVER_ONLY)
+        assert sti["ok"] == 1 and sti["fnv1a"] != st["fnv1a"]
+        if sti["witness_path"] == 1:
+            assert sti["h2d_bytes"] == 3072 * 32
+            stj = s.prove_image(values[:3072].astype(np.float64), 1, PROVER_ONLY)
+            assert stj["ok"] == 1 and stj["witness_path"] == 1 and stj["fnv1a"] == st["fnv1a"]
         st5 = s.prove(1, PREFETCH_NEXT | PROVER_ONLY)
         st6 = s.prove(1, PREFETCH_NEXT | PROVER_ONLY)
         st7 = s.prove(1, PROVER_ONLY)

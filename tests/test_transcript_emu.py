@@ -92,6 +92,24 @@ def test_challenge_sources(emu_host, synthetic_inputs):
         assert c["ok"] == 1 and c["checks"] == 15 and s.proof() == pc and d["fnv1a"] == c["fnv1a"] and pc != g_syn and pc != pa
 
 
+def test_device_witness_generation(emu_lib, emu_host, synthetic_inputs):
+    """witness generation on the device (gate evaluation, NTT of the FFT layers, DOT_PROD products, ReLU / max-pool decompositions):
+    LeNet with two pictures (FFT-convolution path) and the small VGG with naive convolutions"""
+    import numpy as np
+    sys_path = os.path.join(os.path.dirname(GOLDEN), "..", "tools")
+    import sys
+    sys.path.insert(0, sys_path)
+    import gen_synthetic_input as gen
+    lenet = gen.generate("lenet", 11).astype(np.float64)
+    other = np.random.default_rng(1).random(1024)
+    assert cases.device_witness_case(emu_lib, emu_host, "lenet", "", 2, lenet, 1024, "lenet_syn_p2_seed4", GOLDEN, 4, other) == 1
+    cfg = synthetic_inputs["smallvgg_config"]
+    vgg = gen.generate("vgg11", 5, cfg).astype(np.float64)
+    nudged = vgg[:3072].copy()
+    nudged[100:110] *= 0.999      # a slightly different picture: same quantisation decisions
+    cases.device_witness_case(emu_lib, emu_host, "vgg", cfg, 1, vgg, 3072, "smallvgg_p1_seed7", GOLDEN, 7, nudged)
+
+
 def test_tampered_witness_is_rejected(emu_host, synthetic_inputs, tmp_path):
     """soundness smoke: a different image gives a different (still accepted) proof; bad arguments are errors"""
     from zkcnn_b200._binding import ZkError

@@ -309,7 +309,7 @@ class Stats(C.Structure):
                 ("proof_bytes", C.c_uint64), ("fnv1a", C.c_uint64), ("challenges", C.c_uint64), ("gpu_launches", C.c_uint64),
                 ("prove_s", C.c_double), ("poly_s", C.c_double), ("upload_s", C.c_double), ("wall_s", C.c_double),
                 ("verifier_s", C.c_double), ("gkr_kb", C.c_double), ("poly_kb", C.c_double), ("h2d_bytes", C.c_uint64), ("checks", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("witness_path", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -340,6 +340,8 @@ class HostLib:
         d.zkh_build.argtypes = [C.c_void_p]
         d.zkh_prefetch_witness.argtypes = [C.c_void_p]
         d.zkh_prove.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(Stats)]
+        d.zkh_prove_image.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(Stats)]
+        d.zkh_set_image.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64]
         d.zkh_proof.restype = C.POINTER(C.c_uint8)
         d.zkh_proof.argtypes = [C.c_void_p, _u64p]
         d.zkh_inferred_class.argtypes = [C.c_void_p, C.c_int]
@@ -396,6 +398,22 @@ class Session:
         st = Stats()
         self._check(self.lib.dll.zkh_prove(self.h, seed, flags, C.byref(st)), "zkh_prove")
         return st.as_dict()
+
+    def prove_image(self, pixels, seed, flags=0):
+        """a new picture for the built model: witness regenerated on the device (stats["witness_path"] == 1) or, if the picture does not
+        fit the circuit's quantisation decisions, circuit + witness rebuilt on the host (== 2)"""
+        v = np.ascontiguousarray(pixels, dtype=np.float64)
+        st = Stats()
+        self._check(self.lib.dll.zkh_prove_image(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), len(v), seed, flags, C.byref(st)), "zkh_prove_image")
+        return st.as_dict()
+
+    def set_image(self, pixels):
+        """the witness part of prove_image; returns 1 (regenerated on the device) or 2 (circuit + witness rebuilt on the host)"""
+        v = np.ascontiguousarray(pixels, dtype=np.float64)
+        rc = self.lib.dll.zkh_set_image(self.h, v.ctypes.data_as(C.POINTER(C.c_double)), len(v))
+        if rc < 0:
+            raise ZkError("zkh_set_image: " + self.lib.last_error())
+        return rc
 
     def proof(self):
         n = C.c_uint64(0)

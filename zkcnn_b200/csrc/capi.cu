@@ -1,6 +1,7 @@
 // C ABI implementation (include/zkcnn_b200.h).  Host-side orchestration of the sm_100a kernels; the control flow of
 // every entry point mirrors the reference member function cited in the header, the arithmetic runs on the device.
 #include "capi_sumcheck.cuh"
+#include "capi_witness.cuh"
 #include "capi_hyrax.cuh"
 
 using namespace zk;
@@ -62,6 +63,7 @@ int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
     else if (n == "tma_min_entries") ctx->tma_min_entries = value;
     else if (n == "derive_b") ctx->derive_b_enabled = value ? 1u : 0u;
     else if (n == "pdl") ctx->pdl_enabled = value ? 1u : 0u;
+    else if (n == "eval_schedules") ctx->eval_schedules = value != 0;
     else if (n == "unit_batch") ctx->unit_batch = value ? 1u : 0u;
     else if (n == "tail") ctx->tail_enabled = value ? 1u : 0u;
     else if (n == "tail_max_entries") ctx->tail_max_entries = (uint32_t) std::min<uint64_t>(value, kTailMaxEntries);
@@ -150,6 +152,7 @@ int zk_circuit_layer(zk_ctx *ctx, uint32_t id, const zk_layer_desc *D) {
     rt::sync(ctx->stream);
     build_layer_schedules(ctx, id, D);
     L.have_desc = true;
+    L.aux_loaded = false;
     ZK_API_END
 }
 

@@ -214,10 +214,55 @@ static void build_schedule(zk_ctx *ctx, schedule_t &S, std::vector<src_t> &src, 
     }
 }
 
+// evaluation order for the device witness generator: the gates of a layer sorted by OUTPUT gate (calcNormalLayer,
+// src/neuralNetwork.cpp:918-932); layer-0 operands as absolute indices into val[0] (the gate arrays hold positions in ori_id_*)
+static void build_eval_schedule(zk_ctx *ctx, uint32_t id, const zk_layer_desc *D) {
+    layer_t &L = ctx->layers[id];
+    if (D->ty == ZK_LAYER_DOT_PROD) {   // CSR by output block (calcDotProdLayer, :934-944)
+        const uint32_t fft_bl = D->fft_bit_length;
+        const uint32_t n_rows = D->size >> fft_bl;
+        std::vector<uint32_t> ptr(n_rows + 1, 0);
+        for (uint64_t i = 0; i < D->n_bin; ++i) {
+            ZK_REQUIRE(D->bin_gates[i].g < n_rows, "DOT_PROD gate.g out of range");
+            ++ptr[D->bin_gates[i].g + 1];
+        }
+        for (uint32_t i = 0; i < n_rows; ++i) ptr[i + 1] += ptr[i];
+        std::vector<dp_eval_t> g(D->n_bin);
+        std::vector<uint32_t> fill(ptr.begin(), ptr.end() - 1);
+        for (uint64_t i = 0; i < D->n_bin; ++i) g[fill[D->bin_gates[i].g]++] = {D->bin_gates[i].u, D->bin_gates[i].v};
+        L.dpe_rows = n_rows;
+        L.dpe_rowptr.ensure(ptr.size() * 4);
+        L.dpe_gates.ensure(std::max<size_t>(1, g.size()) * sizeof(dp_eval_t));
+        rt::h2d(L.dpe_rowptr.p, ptr.data(), ptr.size() * 4, ctx->stream);
+        rt::h2d(L.dpe_gates.p, g.data(), g.size() * sizeof(dp_eval_t), ctx->stream);
+        rt::sync(ctx->stream);
+        return;
+    }
+    std::vector<src_t> src;
+    src.reserve(D->n_uni + D->n_bin);
+    for (uint64_t i = 0; i < D->n_uni; ++i) {
+        const zk_uni_gate &G = D->uni_gates[i];
+        src_t s;
+        s.rowkey = G.g;
+        s.rec = {0u, G.lu != 0 ? G.u : D->ori_id_u[G.u], (uint32_t) G.sc | (G.lu != 0 ? kEvUPrev : 0u)};
+        src.push_back(s);
+    }
+    for (uint64_t i = 0; i < D->n_bin; ++i) {
+        const zk_bin_gate &G = D->bin_gates[i];
+        const bool u_prev = G.l != 0, v_prev = (G.l & 1) != 0;
+        src_t s;
+        s.rowkey = G.g;
+        s.rec = {v_prev ? G.v : D->ori_id_v[G.v], u_prev ? G.u : D->ori_id_u[G.u], (uint32_t) G.sc | kEvBin | (u_prev ? kEvUPrev : 0u) | (v_prev ? kEvVPrev : 0u)};
+        src.push_back(s);
+    }
+    build_schedule(ctx, L.ev, src, 1u << D->bit_length, 0, false);
+}
+
 static void build_layer_schedules(zk_ctx *ctx, uint32_t id, const zk_layer_desc *D) {
     layer_t &L = ctx->layers[id];
     const int ty = D->ty;
     if (id == 0 || ty == ZK_LAYER_FFT || ty == ZK_LAYER_IFFT) return;
+    if (ctx->eval_schedules) build_eval_schedule(ctx, id, D);
     auto v_abs = [&](uint32_t v) { return D->ori_id_v[v]; };
     const uint32_t rows_u0 = D->bit_length_u[0] >= 0 ? 1u << D->bit_length_u[0] : 0;
     const uint32_t rows_u1 = D->bit_length_u[1] >= 0 ? 1u << D->bit_length_u[1] : 0;

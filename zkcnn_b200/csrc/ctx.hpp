@@ -5,6 +5,7 @@
 #include "rt.hpp"
 #include "sc_kernels.cuh"
 #include "cubic_kernels.cuh"
+#include "witness_kernels.cuh"
 #include <memory>
 #include <vector>
 
@@ -29,6 +30,15 @@ struct layer_t {
     fr_t scale;
     rt::dbuf ori_u, ori_v;     // device copies of ori_id_u / ori_id_v
     schedule_t p1, p2;
+    // witness generation on the device (capi_witness.cuh): gates sorted by OUTPUT gate; DOT_PROD: CSR by output block; the auxiliary
+    // inputs this layer's construction derives from earlier layers (bit decompositions, window maxima), in execution order
+    schedule_t ev;
+    rt::dbuf dpe_rowptr, dpe_gates;
+    uint32_t dpe_rows = 0;
+    rt::dbuf aux_bits_prev, aux_max, aux_bits_l0;   // aux_op_t arrays: bits of val[l-1] entries, maxima over val[l-1] entries, bits of val[0] entries
+    uint64_t n_aux_bits_prev = 0, n_aux_max = 0, n_aux_bits_l0 = 0;
+    uint32_t aux_max_base = 0, aux_max_count = 0;   // the maxima land in val[0][base, base + count)
+    bool aux_loaded = false;
     rt::dbuf dp_rowptr, dp_gates;  // DOT_PROD phase 1: CSR by u
     uint32_t dp_rows = 0;
     uint32_t dp_rows_live = 0;     // rows u < dp_rows_live carry gates: V_mult[0] of the DOT_PROD phase is zero beyond them
@@ -98,6 +108,7 @@ struct zk_ctx {
     std::vector<zk::fr_t> two_mul_h;
     zk::rt::dbuf two_mul;
     bool circuit_ready = false;
+    bool eval_schedules = true;   // zk_circuit_layer also builds the evaluation schedules of the device witness generator (+12 bytes per gate)
 
     // sumcheck state (members of class prover, src/prover.hpp:55-72)
     uint32_t sumcheck_id = 0, round = 0;
@@ -138,6 +149,7 @@ struct zk_ctx {
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 
     zk::hyrax_t hy;
+    zk::rt::dbuf wit_scratch;   // device witness generation: window maxima / layer ranges
     zk::rt::dbuf fb_k, fb_out;
     zk::rt::dbuf fb_comb;       // zk_g1_fixed_base_mul: comb table of the last base point
     uint64_t fb_hash = 0;

@@ -77,6 +77,9 @@ struct zkh_session {
     bool built = false;
     int device = 0;
     FILE *table_dump = nullptr;
+    vector<double> values;     // the input stream of the last zkh_input_* call (image + weights): a host rebuild for a new picture needs the weights again
+    std::string input_path;
+    int image_path = 0;        // path of the last zkh_set_image / zkh_prove_image
     ~zkh_session() { if (table_dump) fclose(table_dump); }
 };
 
@@ -131,6 +134,8 @@ int zkh_input_file(zkh_session *s, const char *path) {
     ZKH_BEGIN
     if (!s || !path) throw std::invalid_argument("bad arguments");
     s->nn->setInput(std::unique_ptr<NumberSource>(new FastFileNumbers(path)));
+    s->input_path = path;
+    s->values.clear();
     ZKH_END
 }
 
@@ -139,6 +144,8 @@ int zkh_input_values(zkh_session *s, const double *values, uint64_t n) {
     if (!s || !values) throw std::invalid_argument("bad arguments");
     if ((int64_t) n < s->nn->inputCount()) throw std::invalid_argument("zkh_input_values: too few values for this model");
     s->nn->setInput(std::unique_ptr<NumberSource>(new ArrayNumbers(values, n)));
+    s->values.assign(values, values + n);
+    s->input_path.clear();
     ZKH_END
 }
 
@@ -205,6 +212,74 @@ int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
         out->checks = ZKH_CHECKED_ROUND_SUMS | (v.checkPredicates ? ZKH_CHECKED_PREDICATES | ZKH_CHECKED_INPUT_GR | ZKH_CHECKED_G1 : 0);
     }
     ZKH_END
+}
+
+// the witness part of zkh_prove_image: returns the path taken (1 device, 2 host rebuild) or -1
+static int set_image(zkh_session *s, const double *pixels, uint64_t n_pixels, uint64_t *h2d_bytes, double *seconds) {
+    auto t0 = std::chrono::steady_clock::now();
+    int path = 2;
+    if ((int64_t) n_pixels < s->nn->imagePixels()) throw std::invalid_argument("too few pixel values");
+    vector<F> image;
+    if (s->nn->deviceWitnessSupported() && s->nn->quantizeImage(pixels, n_pixels, image)) {
+        std::vector<uint64_t> ranges;
+        s->p.generateWitnessOnDevice(image, ranges);
+        if (h2d_bytes) *h2d_bytes = image.size() * sizeof(F);
+        if (s->nn->scalesMatch(ranges.data(), s->p.C.size)) {
+            const u32 last = s->p.C.size - 1;
+            s->nn->inferFromOutput(s->p.readLayer(last, s->p.C.circuit[last].size));
+            path = 1;
+        }
+    }
+    if (path == 2) {   // the circuit's structure does not fit this picture: build circuit + witness for it on the host
+        if (s->values.empty() && !s->input_path.empty()) {
+            FastFileNumbers f(s->input_path);
+            const int64_t n = s->nn->inputCount();
+            s->values.resize(n);
+            for (auto &x : s->values) x = f.next();
+        }
+        if (s->values.empty()) throw std::logic_error("the weights are not available for a host rebuild");
+        std::copy(pixels, pixels + s->nn->imagePixels(), s->values.begin());
+        s->nn->setInput(std::unique_ptr<NumberSource>(new ArrayNumbers(s->values.data(), s->values.size())));
+        s->p.unpinWitness();
+        s->nn->create(s->p, false);
+        s->p.invalidateCircuit();
+        s->p.pinWitness();
+        if (h2d_bytes) *h2d_bytes = 0;   // (zkh_prove uploads and counts the rebuilt witness)
+    }
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return path;
+}
+
+int zkh_set_image(zkh_session *s, const double *pixels, uint64_t n_pixels) {
+    if (!s || !s->built || !pixels) { g_err = "zkh_set_image: call zkh_build first"; return -1; }
+    try {
+        s->image_path = set_image(s, pixels, n_pixels, nullptr, nullptr);
+        return s->image_path;
+    } catch (const std::exception &e) {
+        g_err = std::string("zkh_set_image: ") + e.what();
+        return -1;
+    }
+}
+
+int zkh_prove_image(zkh_session *s, const double *pixels, uint64_t n_pixels, uint64_t seed, uint32_t flags, zkh_stats *out) {
+    if (!s || !s->built || !pixels) { g_err = "zkh_prove_image: call zkh_build first"; return -1; }
+    int path;
+    double gen_s = 0;
+    uint64_t img_bytes = 0;
+    try {
+        path = set_image(s, pixels, n_pixels, &img_bytes, &gen_s);
+    } catch (const std::exception &e) {
+        g_err = std::string("zkh_prove_image: ") + e.what();
+        return -1;
+    }
+    s->image_path = path;
+    const int rc = zkh_prove(s, seed, path == 1 ? (flags | ZKH_WITNESS_RESIDENT) & ~(uint32_t) ZKH_PREFETCH_NEXT : flags & ~(uint32_t) ZKH_WITNESS_RESIDENT, out);
+    if (rc == 0 && out) {
+        out->witness_path = (uint32_t) path;
+        out->upload_s += gen_s;
+        if (path == 1) out->h2d_bytes = img_bytes;
+    }
+    return rc;
 }
 
 const uint8_t *zkh_proof(zkh_session *s, uint64_t *n_bytes) {

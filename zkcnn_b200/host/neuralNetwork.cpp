@@ -99,6 +99,11 @@ void neuralNetwork::create(prover &pr, bool only_compute) {
     initParam();
     pr.C.init(Q_BIT_SIZE, SIZE);
     pr.val.assign(SIZE, vector<F>());
+    pr.aux_ops.assign(SIZE, vector<uint32_t>());
+    aux_ops_ = &pr.aux_ops;
+    aux_supported_ = true;
+    aux_step_ = 0;
+    scale_decisions_.clear();
     val = pr.val.begin();
     two_mul = pr.C.two_mul.begin();
 
@@ -131,6 +136,7 @@ void neuralNetwork::create(prover &pr, bool only_compute) {
             }
             // quantisation scale of the next activations
             x_next_bit = getNextBit(layer_id - 1);
+            scale_decisions_.push_back({(int) layer_id - 1, x_bit, w_bit, x_next_bit});
             T = x_bit + w_bit - x_next_bit;
             Q_MAX = Q + T;
             if (pool_ty != MAX) reluActConvLayer(pr.C.circuit[layer_id], layer_id);
@@ -152,6 +158,7 @@ void neuralNetwork::create(prover &pr, bool only_compute) {
         fullyConnLayer(pr.C.circuit[layer_id], layer_id, fc.weight_start_id, fc.bias_start_id);
         if (i == full_conn.size() - 1) break;
         x_next_bit = getNextBit(layer_id - 1);
+        scale_decisions_.push_back({(int) layer_id - 1, x_bit, w_bit, x_next_bit});
         T = x_bit + w_bit - x_next_bit;
         Q_MAX = Q + T;
         reluActFconLayer(pr.C.circuit[layer_id], layer_id);
@@ -670,6 +677,7 @@ void neuralNetwork::calcInputLayer(layer &circuit) {
         mn = min(mn, x);
     }
     x_next_bit = quantBits(mx, mn, Q);
+    image_bit_ = x_next_bit;
     auto it = val[0].begin();
     for (i64 p = 0; p < pic_parallel; ++p)
         for (i64 i = 0; i < n_pix; ++i) *it++ = F((i64) (dat[i] * exp2(x_next_bit)));
@@ -710,20 +718,74 @@ void neuralNetwork::readFconWeight(i64 first_fc_id) {
 }
 
 // ---- auxiliary witnesses (:899-916) ------------------------------------------------------------------------------------------------------
+// Every auxiliary input is a function of ONE earlier gate value; besides computing it, remember how (for zk_circuit_aux_ops): the layer
+// being built is the source layer + 1, or, for the decomposition of a value that itself sits in val[0] (the window maxima), the step
+// of the ops that produced it.  kind: 0 sign bit, 1 magnitude bit, 2 running maximum of max(0, value).
+void neuralNetwork::recordAux(i64 src_layer, i64 src_idx, i64 dst_idx, u32 kind, i64 bit) {
+    if (!aux_ops_) return;
+    if (src_layer != 0) aux_step_ = src_layer + 1;
+    if (aux_step_ <= 0 || aux_step_ >= (i64) aux_ops_->size() || bit < 0 || bit > 255) { aux_supported_ = false; return; }
+    auto &ops = (*aux_ops_)[aux_step_];
+    ops.push_back((uint32_t) src_idx);
+    ops.push_back((uint32_t) dst_idx);
+    ops.push_back((uint32_t) bit | (kind << 8) | (src_layer == 0 ? 1u << 10 : 0u));
+}
 void neuralNetwork::prepareDecmpBit(i64 layer_id, i64 idx, i64 dcmp_id, i64 bit_shift) {
     i64 data = std::abs(val[layer_id].at(idx).getInt64());
     val[0].at(dcmp_id) = F((i64) ((data >> bit_shift) & 1));
+    recordAux(layer_id, idx, dcmp_id, 1, bit_shift);
 }
 void neuralNetwork::prepareFieldBit(const F &data, i64 dcmp_id, i64 bit_shift) {
     i64 tmp = std::abs(data.getInt64());
     val[0].at(dcmp_id) = F((i64) ((tmp >> bit_shift) & 1));
+    aux_supported_ = false;   // (average pooling decomposes a window SUM: not one of the recorded op kinds; such models keep the host path)
 }
 void neuralNetwork::prepareSignBit(i64 layer_id, i64 idx, i64 dcmp_id) {
     val[0].at(dcmp_id) = val[layer_id].at(idx).isNegative() ? F_ONE : F_ZERO;
+    recordAux(layer_id, idx, dcmp_id, 0, 0);
 }
 void neuralNetwork::prepareMax(i64 layer_id, i64 idx, i64 max_id) {
     F data = val[layer_id].at(idx).isNegative() ? F_ZERO : val[layer_id].at(idx);
     if (data > val[0].at(max_id)) val[0].at(max_id) = data;
+    recordAux(layer_id, idx, max_id, 2, 0);
+}
+
+bool neuralNetwork::quantizeImage(const double *pixels, size_t n, vector<F> &out) const {
+    const i64 n_pix = imagePixels();
+    if ((i64) n < n_pix) throw std::invalid_argument("quantizeImage: too few pixel values");
+    double mx = -10000, mn = 10000;
+    for (i64 i = 0; i < n_pix; ++i) { mx = max(mx, pixels[i]); mn = min(mn, pixels[i]); }
+    if (quantBits(mx, mn, Q) != image_bit_) return false;
+    out.resize((size_t) n_pix * pic_parallel);
+    auto it = out.begin();
+    for (i64 p = 0; p < pic_parallel; ++p)
+        for (i64 i = 0; i < n_pix; ++i) *it++ = F((i64) (pixels[i] * exp2(image_bit_)));
+    return true;
+}
+
+bool neuralNetwork::scalesMatch(const uint64_t *ranges, size_t n_layers) const {
+    for (const auto &d : scale_decisions_) {
+        if ((size_t) d.layer >= n_layers) return false;
+        const i64 x = (i64) (ranges[2 * d.layer] + ranges[2 * d.layer + 1]);   // getNextBit: (mx + mn).getInt64()
+        const double real_scale = x / exp2(d.x_bit + d.w_bit);
+        if ((int) log2(((1 << (Q - 1)) - 1) / real_scale) != d.next_bit) return false;
+    }
+    return true;
+}
+
+void neuralNetwork::inferFromOutput(const vector<F> &output) {
+    inferred.assign(pic_parallel, -1);
+    if (full_conn.empty()) return;
+    const int n_class = full_conn.back().channel_out;
+    for (int p = 0; p < pic_parallel; ++p) {
+        int k = -1;
+        F best;
+        for (int c = 0; c < n_class; ++c) {
+            const F &tmp = output.at(matIdx(p, c, n_class));
+            if (!tmp.isNegative() && (k == -1 || best < tmp)) { k = c; best = tmp; }
+        }
+        inferred[p] = k;
+    }
 }
 
 // ---- circuit evaluation (:918-965) ----------------------------------------------------------------------------------------------------------

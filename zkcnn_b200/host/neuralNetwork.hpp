@@ -55,6 +55,21 @@ public:
     int hostThreads = 0;          // witness evaluation threads (0 = hardware concurrency)
     vector<int> inferred;         // argmax per picture (what the reference writes to o_file)
 
+    // ---- a new picture for the circuit create() built (device witness generation) --------------------------------
+    // create() also records, for the prover (prover::aux_ops), the auxiliary inputs every layer's construction derives from earlier gate
+    // values, and the data-dependent quantisation decisions it took: the scale of the picture (calcInputLayer) and of every activation
+    // tensor (getNextBit).  Those decide the bit widths of the ReLU / pooling decompositions, i.e. the circuit's STRUCTURE: a new picture
+    // can reuse the circuit iff it leads to the same decisions.
+    bool deviceWitnessSupported() const { return aux_supported_; }
+    // the picture as create() would put it into val[0] (quantised, replicated pic_parallel times); false: its scale differs from the built circuit's
+    bool quantizeImage(const double *pixels, size_t n, vector<F> &out) const;
+    // ranges[2 * layer], ranges[2 * layer + 1] = largest non-negative value / largest magnitude of a negative value of that layer
+    // (zk_witness_generate); true iff every getNextBit decision of create() comes out the same
+    bool scalesMatch(const uint64_t *ranges, size_t n_layers) const;
+    i64 imagePixels() const { return pic_size_x * pic_size_y * pic_channel; }
+    // argmax of the output layer (what printInfer does) from its values
+    void inferFromOutput(const vector<F> &output);
+
 protected:
     void initParam();
     int getNextBit(int layer_id);
@@ -123,6 +138,15 @@ protected:
 
     std::unique_ptr<NumberSource> in;
     string o_file;
+
+    // recorded by create()
+    struct ScaleDecision { int layer, x_bit, w_bit, next_bit; };
+    vector<ScaleDecision> scale_decisions_;
+    int image_bit_ = 0;
+    bool aux_supported_ = true;
+    vector<vector<uint32_t>> *aux_ops_ = nullptr;   // prover::aux_ops
+    i64 aux_step_ = 0;
+    void recordAux(i64 src_layer, i64 src_idx, i64 dst_idx, u32 kind, i64 bit);
 };
 
 // ---- model zoo (src/models.hpp) -------------------------------------------------------------------------------------------

@@ -53,6 +53,10 @@ void prover::uploadCircuit() {
         d.ori_id_u = cur.ori_id_u.data();
         d.ori_id_v = cur.ori_id_v.data();
         check(zk_circuit_layer(ctx_, i, &d), "zk_circuit_layer");
+        if (i >= 1) {
+            const bool have = aux_ops.size() == (size_t) C.size;
+            check(zk_circuit_aux_ops(ctx_, i, have && !aux_ops[i].empty() ? aux_ops[i].data() : nullptr, have ? aux_ops[i].size() / 3 : 0), "zk_circuit_aux_ops");
+        }
     }
     check(zk_circuit_end(ctx_), "zk_circuit_end");
     circuit_uploaded_ = true;
@@ -197,6 +201,30 @@ void prover::init() {   // src/prover.cpp:17-21 (+ upload of what the reference 
     if (prefetch_next_) prefetchWitness();
     check(zk_prover_init(ctx_), "zk_prover_init");
     upload_timer.stop();
+}
+
+void prover::generateWitnessOnDevice(const vector<F> &image, std::vector<uint64_t> &ranges) {
+    upload_timer.start();
+    joinPrefetch();
+    prefetch_pending_ = false;
+    if (!ctx_) {
+        int dev = device_;
+        if (dev < 0) { const char *e = getenv("ZKCNN_DEVICE"); dev = e ? atoi(e) : 0; }
+        ctx_ = zk_ctx_create(dev);
+        if (!ctx_) throw std::runtime_error(std::string("zkcnn_b200: cannot create a device context: ") + zk_last_error());
+    }
+    if (!circuit_uploaded_) { uploadCircuit(); witness_uploaded_ = false; }
+    if (!witness_uploaded_) uploadWitness();   // once: the quantised weights stay resident in val[0]
+    ranges.assign((size_t) 2 * C.size, 0);
+    check(zk_witness_generate(ctx_, w(image[0]), image.size(), ranges.data()), "zk_witness_generate");
+    last_upload_bytes_ = image.size() * sizeof(F);
+    upload_timer.stop();
+}
+
+vector<F> prover::readLayer(u32 layer, size_t n) {
+    vector<F> out(n);
+    if (n) check(zk_witness_read(ctx_, layer, 0, n, w(out[0])), "zk_witness_read");
+    return out;
 }
 
 void prover::sumcheckInitAll(const vector<F>::const_iterator &r_0_from_v) {   // src/prover.cpp:28-36

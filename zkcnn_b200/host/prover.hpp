@@ -82,6 +82,14 @@ public:
     vector<vector<F>> val;        // the output of each gate
 
     // ---- additions of the B200 build (not in the reference interface) ----------------------------------------------
+    // auxiliary-input recipes per layer, written by neuralNetwork::create next to C and val (triples, see zk_circuit_aux_ops); uploaded with
+    // the circuit so that zk_witness_generate can rebuild the whole witness on the device for a new picture
+    std::vector<std::vector<uint32_t>> aux_ops;
+    // new picture, same circuit: upload `image` (val[0][0, image.size())), regenerate every auxiliary input and layer on the device and make
+    // that the current witness (the host copy `val` is NOT updated).  ranges: 2 x C.size values (zk_witness_generate).  The circuit and one
+    // complete witness are uploaded first if they are not there yet.
+    void generateWitnessOnDevice(const vector<F> &image, std::vector<uint64_t> &ranges);
+    vector<F> readLayer(u32 layer, size_t n);   // values of a (short) layer as they stand on the device
     // CUDA device used by this prover (default: env ZKCNN_DEVICE or 0).  Call before init().
     void setDevice(int device) { device_ = device; }
     // record every prover->verifier message in SURVEY.md App. A order (nullptr = off)
