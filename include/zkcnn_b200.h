@@ -173,6 +173,23 @@ int zk_poly_bullet_prove(zk_ctx *ctx, uint64_t *lcomm, uint64_t *rcomm, uint64_t
 int zk_poly_bullet_update(zk_ctx *ctx, const uint64_t *randomness);                           /* :98  */
 int zk_poly_bullet_open(zk_ctx *ctx, uint64_t *out);                                          /* :111 */
 
+/* ---- verifier side on the device (the caller of the hot path): the wiring predicates of verifier::betaInitPhase1/2
+ * and predicatePhase1/2 (src/verifier.cpp:36-123) and the input-layer term gr (:307-325), computed from the VERIFIER's challenges with the
+ * kernels of the prover's Init* passes over the resident circuit topology.  Tables live in slots 0..7 of the context. ------------------- */
+/* slot <- init0 * eq(r0) (+ init1 * eq(r1) if r1 != NULL) over `bits` variables; entries >= tail_start times tail_scale if tail_scale != NULL */
+int zk_vtab_eq(zk_ctx *ctx, int slot, uint32_t bits, const uint64_t *r0, const uint64_t *init0, const uint64_t *r1, const uint64_t *init1, uint32_t tail_start,
+               const uint64_t *tail_scale);
+/* slot_out[g] = hi[g >> lo_bits] * lo[g & (2^lo_bits - 1)] */
+int zk_vtab_outer(zk_ctx *ctx, int slot_out, int slot_hi, int slot_lo, uint32_t bits, uint32_t lo_bits);
+/* slot <- phiGInit(rx, scale, n, is_ifft), 2^n entries */
+int zk_vtab_phi(zk_ctx *ctx, int slot, const uint64_t *rx, const uint64_t *scale, uint32_t n, int is_ifft);
+/* out = sum_{i < n} slot_a[i] * slot_b[i] */
+int zk_vtab_dot(zk_ctx *ctx, int slot_a, int slot_b, uint64_t n, uint64_t *out);
+/* out[5 Fr] = uni_value[0], uni_value[1] (before the beta_v[0] factor of src/verifier.cpp:111-112), bin_value[0..2]; slot_beta_v < 0: no phase 2 */
+int zk_verifier_layer_predicates(zk_ctx *ctx, uint32_t layer_id, int slot_beta_g, int slot_beta_u, int slot_beta_v, uint64_t *out);
+/* gr of verifier::verifyFirstLayer; r_u / r_v = the challenge vectors of the layers that have layer-0 operands, back to back */
+int zk_verifier_input_predicate(zk_ctx *ctx, int slot_beta0, const uint64_t *s_u, const uint64_t *s_v, const uint64_t *r_u, const uint64_t *r_v, uint64_t *out);
+
 /* ---- stateless primitives: the kernels behind the calls above, exposed for parity tests and micro-benchmarks ------ */
 /* out[i] = a[i] (+,-,*) b[i];  op: 0 add, 1 sub, 2 mul */
 int zk_fr_vec_op(zk_ctx *ctx, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, uint64_t n);

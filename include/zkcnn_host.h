@@ -29,6 +29,7 @@ enum {
                                  Hyrax opening (src/verifier.cpp:36-116,307-325; polyVerifier.cpp:25-27,53-58); zkh_stats.checks says what ran */
     ZKH_CSPRNG_CHALLENGES = 256, /* draw the challenges from the operating system's CSPRNG like the reference (Fr::setByCSPRNG,
                                  src/verifier.cpp:124,139,...) instead of the seeded stream: `seed` is ignored, the transcript is not reproducible */
+    ZKH_HOST_PREDICATES  = 1024,/* evaluate the verifier's wiring predicates on host threads instead of on the device (zk_verifier_*) */
     ZKH_FIAT_SHAMIR      = 512,/* non-interactive mode: every challenge is derived from the transcript so far (see host/challenge_stream.hpp) */
     ZKH_ROUND_BY_ROUND   = 16  /* one device round trip per sumcheck round (the reference's call pattern) instead of one per phase:
                                  the verifier draws a phase's challenges before its first round either way (src/verifier.cpp:156-160),

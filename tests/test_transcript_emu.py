@@ -48,8 +48,9 @@ def test_round_by_round_driver_gives_the_same_transcript(emu_host, synthetic_inp
 
 def test_shipped_lenet_image(emu_host, mnist_input):
     """BASELINE config 1: the reference's own MNIST demo input (script/demo_lenet.sh)"""
-    st = cases.prove_and_compare(emu_host, "lenet", "", 1, mnist_input, 1, 0, "lenet_p1_seed1", GOLDEN)
-    assert st["ok"] == 1 and st["checks"] == 15
+    from zkcnn_b200._binding import HOST_PREDICATES
+    st = cases.prove_and_compare(emu_host, "lenet", "", 1, mnist_input, 1, HOST_PREDICATES, "lenet_p1_seed1", GOLDEN)   # predicates on host threads here,
+    assert st["ok"] == 1 and st["checks"] == 15                                                                          # on the device everywhere else
 
 
 def test_witness_lifecycle(emu_host, synthetic_inputs, mnist_input):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Device-timed micro-benchmarks of the two headline kernels (CUDA events inside the library, inputs resident in HBM).
-usage: microbench.py fold [bits] [iters] | msm [log_rows] [log_cols] [mix] [iters]      -- also the target of ncu captures"""
+usage: microbench.py fold [bits] [iters] | cubic [bits] [iters] | msm [log_rows] [log_cols] [mix] [iters]      -- also the target of ncu captures"""
 import json
 import os
 import sys
@@ -20,6 +20,11 @@ def main():
             ms = c.bench_fold(bits, iters, True)
             gbs = 96 * (1 << bits) / 1e9 / (ms / 1e3)
             print(json.dumps({"kernel": "k_round_quad", "bits": bits, "ms": ms, "algorithmic_GB/s": gbs, "frac_of_measured_hbm": gbs / PEAK}))
+        elif what == "cubic":
+            bits, iters = (a + [24, 10][len(a):])[:2]
+            ms = c.bench_cubic(bits, 7, iters)
+            gbs = 96 * (1 << bits) / 1e9 / (ms / 1e3)
+            print(json.dumps({"kernel": "k_round_cubic_tma", "bits": bits, "ms": ms, "algorithmic_GB/s": gbs, "frac_of_measured_hbm": gbs / PEAK}))
         else:
             lr, lc, mix, iters = (a + [12, 12, 2, 3])[len(a):] if False else (a + [12, 12, 2, 3][len(a):])[:4]
             ms = c.bench_msm(lr, lc, mix, iters)

@@ -5,7 +5,7 @@ only loads it.  There is no CPU fallback: without the built library or without a
 """
 import os
 
-from ._binding import (CHECKED_ALL, CHECK_PREDICATES, CSPRNG_CHALLENGES, FIAT_SHAMIR, FIXED_GENERATORS, PROVER_ONLY, NO_HASH, PREFETCH_NEXT, REAL_GENERATORS, ROUND_BY_ROUND, WITNESS_RESIDENT, Context, HostLib, Lib, Session, ZkError,
+from ._binding import (CHECKED_ALL, CHECK_PREDICATES, CSPRNG_CHALLENGES, FIAT_SHAMIR, FIXED_GENERATORS, HOST_PREDICATES, PROVER_ONLY, NO_HASH, PREFETCH_NEXT, REAL_GENERATORS, ROUND_BY_ROUND, WITNESS_RESIDENT, Context, HostLib, Lib, Session, ZkError,
                        PROF_CLASSES, fr_from_words, fr_to_words, g1_from_words, g1_to_words)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

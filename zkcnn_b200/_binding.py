@@ -316,7 +316,7 @@ class Stats(C.Structure):
 
 
 REAL_GENERATORS, CHECK_PREDICATES, WITNESS_RESIDENT, FIXED_GENERATORS, ROUND_BY_ROUND, PREFETCH_NEXT, NO_HASH = 1, 2, 4, 8, 16, 32, 64
-PROVER_ONLY, CSPRNG_CHALLENGES, FIAT_SHAMIR = 128, 256, 512
+PROVER_ONLY, CSPRNG_CHALLENGES, FIAT_SHAMIR, HOST_PREDICATES = 128, 256, 512, 1024
 CHECKED_ROUND_SUMS, CHECKED_PREDICATES, CHECKED_INPUT_GR, CHECKED_G1 = 1, 2, 4, 8
 CHECKED_ALL = 15
 

@@ -3,6 +3,7 @@
 #include "capi_sumcheck.cuh"
 #include "capi_witness.cuh"
 #include "capi_hyrax.cuh"
+#include "capi_verifier.cuh"
 
 using namespace zk;
 

@@ -149,6 +149,8 @@ struct zk_ctx {
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 
     zk::hyrax_t hy;
+    zk::rt::dbuf vt[8], vt_m[2];    // verifier-side tables (capi_verifier.cuh): eq / phi tables by slot, mult-table scratch
+    uint64_t vt_n[8] = {};
     zk::rt::dbuf wit_scratch;   // device witness generation: window maxima / layer ranges
     zk::rt::dbuf fb_k, fb_out;
     zk::rt::dbuf fb_comb;       // zk_g1_fixed_base_mul: comb table of the last base point

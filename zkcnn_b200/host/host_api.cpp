@@ -186,6 +186,7 @@ int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out) {
     v.realGenerators = (flags & ZKH_REAL_GENERATORS) != 0;
     v.batchRounds = (flags & ZKH_ROUND_BY_ROUND) == 0;
     v.fiatShamir = (flags & ZKH_FIAT_SHAMIR) != 0 && !os_rng;
+    v.devicePredicates = (flags & ZKH_HOST_PREDICATES) == 0;
     if ((flags & ZKH_FIXED_GENERATORS) && !s->last_gens.empty()) v.fixedGenerators = &s->last_gens;
     const bool ok = v.verify();
     auto t1 = std::chrono::steady_clock::now();

@@ -298,6 +298,76 @@ void verifier::predicatePhase2(u8 layer_id) {   // src/verifier.cpp:110-123
     for (int k = 0; k < 3; ++k) bin_value[k] = s[k];
 }
 
+// The same five values as betaInitPhase1/2 + predicatePhase1/2 above, computed on the device (include/zkcnn_b200.h, "verifier side")
+void verifier::predicatesOnDevice(u8 depth, const F &alpha, const F &beta, const F &relu_rou) {
+    zk_ctx *ctx = p->context();
+    const layer &L = C.circuit[depth];
+    const int bl = L.bit_length, fft_bl = L.fft_bit_length, fft_blh = fft_bl - 1;
+    const vector<F> &r_0 = r_u[depth + 1], &r_1 = r_v[depth + 1];
+    const F one = F_ONE;
+    auto ptr = [](const vector<F> &v, size_t off = 0) -> const uint64_t * { return v.size() > off ? w(v[off]) : nullptr; };
+    enum { G = 0, U = 1, V = 2, T0 = 3, T1 = 4 };
+    uni_value[0] = uni_value[1] = bin_value[0] = bin_value[1] = bin_value[2] = F_ZERO;
+    if (L.ty == layerType::FFT || L.ty == layerType::IFFT) {   // sum_u phi(r_0)[u] eq(r_u)[u]
+        require(zk_vtab_phi(ctx, T0, ptr(r_0), w(L.scale), fft_bl, L.ty == layerType::IFFT), "zk_vtab_phi");
+        require(zk_vtab_eq(ctx, U, L.max_bl_u, ptr(r_u[depth]), w(one), nullptr, nullptr, 0, nullptr), "zk_vtab_eq");
+        require(zk_vtab_dot(ctx, T0, U, (uint64_t) 1 << L.max_bl_u, reinterpret_cast<uint64_t *>(&uni_value[1])), "zk_vtab_dot");
+        return;
+    }
+    switch (L.ty) {
+        case layerType::PADDING: {
+            const F &a2 = alpha, &b2 = beta;
+            require(zk_vtab_eq(ctx, T0, bl - fft_blh, ptr(r_u[depth + 2], fft_bl), w(a2), b2.isZero() ? nullptr : ptr(r_v[depth + 2]), w(b2), 0, nullptr), "zk_vtab_eq");
+            require(zk_vtab_eq(ctx, T1, fft_blh, ptr(r_0), w(one), nullptr, nullptr, 0, nullptr), "zk_vtab_eq");
+            require(zk_vtab_outer(ctx, G, T0, T1, bl, fft_blh), "zk_vtab_outer");
+            require(zk_vtab_eq(ctx, U, L.max_bl_u, ptr(r_u[depth]), w(one), nullptr, nullptr, 0, nullptr), "zk_vtab_eq");
+            break;
+        }
+        case layerType::DOT_PROD: {
+            const int cnt_bl = bl - fft_bl, cnt_bl2 = L.max_bl_u - fft_bl;
+            require(zk_vtab_eq(ctx, G, cnt_bl, ptr(r_u[depth + 2], fft_bl - 1), w(alpha), nullptr, nullptr, 0, nullptr), "zk_vtab_eq");
+            F same = F_ONE;
+            for (int j = 0; j < fft_bl; ++j) same *= r_0[j] * r_u[depth][j] + (F_ONE - r_0[j]) * (F_ONE - r_u[depth][j]);
+            require(zk_vtab_eq(ctx, U, cnt_bl2, ptr(r_u[depth], fft_bl), w(same), nullptr, nullptr, 0, nullptr), "zk_vtab_eq");
+            break;
+        }
+        default: {
+            const F a = alpha * L.scale, b = beta * L.scale;
+            const bool tail = L.zero_start_id < L.size;
+            require(zk_vtab_eq(ctx, G, bl, ptr(r_0), w(a), b.isZero() ? nullptr : ptr(r_1), w(b), tail ? L.zero_start_id : 0, tail ? w(relu_rou) : nullptr), "zk_vtab_eq");
+            require(zk_vtab_eq(ctx, U, L.max_bl_u, ptr(r_u[depth]), w(one), nullptr, nullptr, 0, nullptr), "zk_vtab_eq");
+        }
+    }
+    F bv0 = F_ONE;
+    if (L.need_phase2) {
+        require(zk_vtab_eq(ctx, V, L.max_bl_v, ptr(r_v[depth]), w(one), nullptr, nullptr, 0, nullptr), "zk_vtab_eq");
+        for (int j = 0; j < L.max_bl_v; ++j) bv0 *= F_ONE - r_v[depth][j];   // beta_v[0]
+    }
+    F out[5];
+    require(zk_verifier_layer_predicates(ctx, depth, G, U, L.need_phase2 ? V : -1, reinterpret_cast<uint64_t *>(&out[0])), "zk_verifier_layer_predicates");
+    uni_value[0] = out[0] * bv0;
+    uni_value[1] = out[1] * bv0;
+    for (int k = 0; k < 3; ++k) bin_value[k] = out[2 + k];
+}
+
+F verifier::inputPredicateOnDevice(const vector<F> &sig_u, const vector<F> &sig_v) {
+    zk_ctx *ctx = p->context();
+    const layer &in = C.circuit[0];
+    const F one = F_ONE;
+    require(zk_vtab_eq(ctx, 0, in.bit_length, r_u[0].empty() ? nullptr : w(r_u[0][0]), w(one), nullptr, nullptr, 0, nullptr), "zk_vtab_eq");
+    vector<F> ru, rv;
+    for (int i = 1; i < C.size; ++i) {
+        const layer &L = C.circuit[i];
+        if (L.bit_length_u[0] != -1) ru.insert(ru.end(), r_u[i].begin(), r_u[i].begin() + L.bit_length_u[0]);
+        if (L.bit_length_v[0] != -1) rv.insert(rv.end(), r_v[i].begin(), r_v[i].begin() + L.bit_length_v[0]);
+    }
+    ru.push_back(F_ZERO);   // (never empty: a valid pointer for the call)
+    rv.push_back(F_ZERO);
+    F gr;
+    require(zk_verifier_input_predicate(ctx, 0, w(sig_u[0]), w(sig_v[0]), w(ru[0]), w(rv[0]), reinterpret_cast<uint64_t *>(&gr)), "zk_verifier_input_predicate");
+    return gr;
+}
+
 bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
     const layer &out = C.circuit[C.size - 1];
     F alpha = F_ONE, beta = F_ZERO, relu_rou, claim_u1, claim_v1;
@@ -352,7 +422,7 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
         else p->sumcheckFinalize1(prev, final_claim_u0[i], claim_u1);
 
         total_slow_timer.start();
-        if (checkPredicates) {
+        if (checkPredicates && !devicePredicates) {
             betaInitPhase1(i, alpha, beta, r_u[i + 1], r_v[i + 1], relu_rou);
             predicatePhase1(i);
         }
@@ -379,10 +449,15 @@ bool verifier::verifyInnerLayers() {   // src/verifier.cpp:132-266
             }
             p->sumcheckFinalize2(prev, final_claim_v0[i], claim_v1);
             total_slow_timer.start();
-            if (checkPredicates) {
+            if (checkPredicates && !devicePredicates) {
                 betaInitPhase2(i);
                 predicatePhase2(i);
             }
+            total_slow_timer.stop();
+        }
+        if (checkPredicates && devicePredicates) {
+            total_slow_timer.start();
+            predicatesOnDevice(i, alpha, beta, relu_rou);
             total_slow_timer.stop();
         }
         if (checkPredicates && sum != getFinalValue(final_claim_u0[i], claim_u1, final_claim_v0[i], claim_v1)) {
@@ -439,7 +514,15 @@ bool verifier::verifyFirstLayer() {   // src/verifier.cpp:268-357
     }
     p->sumcheckLiuFinalize(prev, eval_in);
 
-    if (checkPredicates) {   // gr = sum over all layer-0 operand slots of eq(r_u[0])[ori_id] * sigma-weighted eq(r_u[i] / r_v[i])
+    if (checkPredicates && devicePredicates) {
+        total_slow_timer.start();
+        const F gr = inputPredicateOnDevice(sig_u, sig_v);
+        total_slow_timer.stop();
+        if (eval_in * gr != sum) {
+            fprintf(stderr, "Liu fail, semi final, circuit 0.\n");
+            return false;
+        }
+    } else if (checkPredicates) {   // gr = sum over all layer-0 operand slots of eq(r_u[0])[ori_id] * sigma-weighted eq(r_u[i] / r_v[i])
         total_slow_timer.start();
         eqTable(beta_g, in.bit_length, r_u[0].data(), F_ONE);
         F gr = F_ZERO;

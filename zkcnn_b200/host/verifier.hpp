@@ -49,6 +49,9 @@ public:
     bool realGenerators = false;
     // one device call per phase (prover::sumcheckUpdateAll) instead of one per round; the messages and their order are the same
     bool batchRounds = true;
+    // true: the wiring predicates (betaInitPhase1/2, predicatePhase1/2) and the input-layer term gr run on the device through the
+    // zk_vtab_* / zk_verifier_* entry points (same kernels as the prover's Init* passes, the verifier's own challenges); false: on host threads
+    bool devicePredicates = true;
     // Fiat-Shamir mode (the active ChallengeStream derives every challenge from the transcript so far): a round's challenge is
     // drawn AFTER the round's message instead of before the phase (src/verifier.cpp:156-160 draws them up front, which is only
     // sound for an interactive verifier), so the rounds go one by one
@@ -73,6 +76,8 @@ private:
     F bin_value[3];
     void predicatePhase1(u8 layer_id);
     void predicatePhase2(u8 layer_id);
+    void predicatesOnDevice(u8 depth, const F &alpha, const F &beta, const F &relu_rou);   // both phases: fills uni_value / bin_value
+    F inputPredicateOnDevice(const vector<F> &sig_u, const vector<F> &sig_v);              // gr of verifyFirstLayer
     F getFinalValue(const F &claim_u0, const F &claim_u1, const F &claim_v0, const F &claim_v1);
 
     F eval_in;
