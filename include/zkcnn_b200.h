@@ -64,6 +64,7 @@ int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_
  *   "derive_b"         (1)      streaming rounds take b from the previous round's polynomial (0: always three products)
  *   "pdl"              (1)      k_round_quad_thin is launched with programmatic stream serialization
  *   "eval_schedules"   (1)      zk_circuit_layer also builds the evaluation schedules of zk_witness_generate (+12 bytes per gate)
+ *   "axpy_splits"      (0)      K5b: threads that share one output of k_dotprod_axpy (0: chosen from the shape)
  *   "unit_batch"       (0)      zk_fold_rounds2 runs its rounds through the phase-batched path (as zk_sumcheck_update_batch does)
  *   "tail"             (1)      batched phases run all rounds on tables of at most tail_max_entries (1024) in one launch (k_round_tail)
  *   "cubic_tma"        (1)      DOT_PROD fold rounds on tables of at least tma_min_entries use k_round_cubic_tma

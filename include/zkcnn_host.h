@@ -70,6 +70,10 @@ void zkh_destroy(zkh_session *s);
 int64_t zkh_input_count(zkh_session *s);                                 /* decimals build() consumes */
 int zkh_input_file(zkh_session *s, const char *path);                    /* the reference's text format */
 int zkh_input_values(zkh_session *s, const double *values, uint64_t n);  /* same numbers, in memory */
+/* the reference's text format (whitespace-separated decimals, src/neuralNetwork.cpp:805-897) parsed once into doubles: up to `cap` values
+ * into `out`, returns how many the file holds (or -1).  What the input cache / the weight broadcast of zkcnn_b200.load_input build on:
+ * the 124 MB vgg11 file costs the reference ~20 s of `ifstream >> double` in every run. */
+int64_t zkh_parse_numbers(const char *path, double *out, uint64_t cap);
 int zkh_build(zkh_session *s);                                           /* circuit + witness (neuralNetwork::create) */
 int zkh_prove(zkh_session *s, uint64_t seed, uint32_t flags, zkh_stats *out);
 /* A NEW PICTURE for the model zkh_build prepared (same weights): `pixels` are the picture's decimals in the reference's order (the first

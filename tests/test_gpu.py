@@ -129,6 +129,16 @@ def test_transcripts(gpu_host, synthetic_inputs, mnist_input, model, net, pics, 
     assert st["gpu_launches"] > 100
 
 
+def test_fft_path_with_other_kernel_variants(gpu_host, synthetic_inputs, monkeypatch):
+    """whole FFT-path proofs with the kernel selection pushed the other way (ZK_TUNABLES is read when the prover's context is created)"""
+    net = synthetic_inputs["smallvgg_config"]
+    for tun in ("axpy_splits=5,cubic_max_grid=9,cubic_factored_min_iters=1,tail_max_entries=64,tma_min_entries=128",
+                "axpy_splits=1,cubic_tma=0,cubic_factored_min_iters=1000000,tail=0,thin_max_pairs=0"):
+        monkeypatch.setenv("ZK_TUNABLES", tun)
+        cases.prove_and_compare(gpu_host, "vgg", net, 2, synthetic_inputs["smallvgg"], 7, PROVER_ONLY, "smallvgg_p2_seed7", GOLDEN)
+        cases.prove_and_compare(gpu_host, "lenet", "", 2, synthetic_inputs["lenet_syn"], 4, 0, "lenet_syn_p2_seed4", GOLDEN)
+
+
 def test_proofs_in_flight_on_one_gpu(gpu_host, synthetic_inputs, mnist_input):
     """three provers (own context, stream, witness, challenge stream) driven from three host threads on one GPU, several proofs each:
     every transcript must be the golden one of its (input, seed) whatever the interleaving of the kernels"""

@@ -25,6 +25,15 @@ def test_lenet_two_pictures_fft_path(emu_host, synthetic_inputs):
     assert st["ok"] == 1
 
 
+def test_fft_path_with_other_kernel_variants(emu_host, synthetic_inputs, monkeypatch):
+    """the same proof with the kernel selection pushed the other way (ZK_TUNABLES is read when the prover's context is created):
+    K5b rows split over three threads, K2 grids capped (several iterations per thread) and factored everywhere, a short fused tail"""
+    monkeypatch.setenv("ZK_TUNABLES", "axpy_splits=3,cubic_max_grid=7,cubic_factored_min_iters=1,tail_max_entries=64")
+    from zkcnn_b200._binding import PROVER_ONLY
+    st = cases.prove_and_compare(emu_host, "lenet", "", 2, synthetic_inputs["lenet_syn"], 4, PROVER_ONLY, "lenet_syn_p2_seed4", GOLDEN)
+    assert st["ok"] == 1
+
+
 def test_small_vgg_naive_conv(emu_host, synthetic_inputs):
     st = cases.prove_and_compare(emu_host, "vgg", synthetic_inputs["smallvgg_config"], 1, synthetic_inputs["smallvgg"], 7, 0,
                                  "smallvgg_p1_seed7", GOLDEN)

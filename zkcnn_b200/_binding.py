@@ -336,6 +336,8 @@ class HostLib:
         d.zkh_input_count.restype = C.c_int64
         d.zkh_input_count.argtypes = [C.c_void_p]
         d.zkh_input_file.argtypes = [C.c_void_p, C.c_char_p]
+        d.zkh_parse_numbers.restype = C.c_int64
+        d.zkh_parse_numbers.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_uint64]
         d.zkh_input_values.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_uint64]
         d.zkh_build.argtypes = [C.c_void_p]
         d.zkh_prefetch_witness.argtypes = [C.c_void_p]
@@ -352,6 +354,16 @@ class HostLib:
 
     def last_error(self):
         return self.dll.zkh_last_error().decode()
+
+    def parse_numbers(self, path):
+        """the reference's text input format -> float64 array (block-wise strtod; the reference re-parses with `ifstream >> double` in every run)"""
+        n = self.dll.zkh_parse_numbers(str(path).encode(), None, 0)
+        if n < 0:
+            raise ZkError("zkh_parse_numbers: " + self.last_error())
+        out = np.empty(n, dtype=np.float64)
+        if self.dll.zkh_parse_numbers(str(path).encode(), out.ctypes.data_as(C.POINTER(C.c_double)), n) != n:
+            raise ZkError("zkh_parse_numbers: file changed while reading")
+        return out
 
 
 class Session:

@@ -29,7 +29,19 @@ zk_ctx *zk_ctx_create(int device) {
         std::unique_ptr<zk_ctx> c(new zk_ctx);
         c->device = device;
         c->stream = rt::stream_create();
-        return c.release();
+        zk_ctx *ctx = c.release();
+        if (const char *env = getenv("ZK_TUNABLES")) {   // "name=value,name=value": kernel-selection tunables for contexts the caller does not hold (tests)
+            std::string e(env);
+            size_t pos = 0;
+            while (pos < e.size()) {
+                const size_t end = e.find(',', pos), eq = e.find('=', pos);
+                if (eq != std::string::npos && (end == std::string::npos || eq < end))
+                    zk_set_tunable(ctx, e.substr(pos, eq - pos).c_str(), strtoull(e.c_str() + eq + 1, nullptr, 0));
+                if (end == std::string::npos) break;
+                pos = end + 1;
+            }
+        }
+        return ctx;
     } catch (const std::exception &e) {
         g_last_error = e.what();
         return nullptr;
@@ -65,6 +77,7 @@ int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
     else if (n == "derive_b") ctx->derive_b_enabled = value ? 1u : 0u;
     else if (n == "pdl") ctx->pdl_enabled = value ? 1u : 0u;
     else if (n == "eval_schedules") ctx->eval_schedules = value != 0;
+    else if (n == "axpy_splits") ctx->axpy_splits = (uint32_t) std::min<uint64_t>(value, 64);
     else if (n == "unit_batch") ctx->unit_batch = value ? 1u : 0u;
     else if (n == "tail") ctx->tail_enabled = value ? 1u : 0u;
     else if (n == "tail_max_entries") ctx->tail_max_entries = (uint32_t) std::min<uint64_t>(value, kTailMaxEntries);
@@ -650,9 +663,24 @@ int zk_sumcheck_dotprod_init_phase1(zk_ctx *ctx) {   // src/prover.cpp:57-95
     ctx->dp_live0 = std::min<uint32_t>(L.dp_rows_live << fft_bl, P.live);
     ctx->in_dotprod_p1 = true;
     const uint64_t n_out = (uint64_t) L.dp_rows_live << fft_bl;
-    if (n_out)
-        ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, (uint64_t) d.n_bin * (32ull << fft_bl) + n_out * 32, k_dotprod_axpy, dim3(grid_for(n_out)), dim3(kBlock), 0, V0,
-                       prev.val.as<fr_t>(), ctx->beta_g.as<fr_t>(), L.dp_rowptr.as<uint32_t>(), L.dp_gates.as<dp_gate_t>(), L.dp_rows_live, fft_bl);
+    if (n_out) {
+        // enough threads to fill the machine: the gates of a row are dealt to `splits` threads whose partial sums k_colsum_finish adds up
+        const uint64_t gates_per_row = std::max<uint64_t>(1, d.n_bin / std::max(1u, L.dp_rows_live));
+        const uint32_t splits = ctx->axpy_splits ? ctx->axpy_splits
+                                                 : (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(32, gates_per_row / 8), ((uint64_t) ZK_SM_COUNT * 8 * kBlock) / n_out));
+        fr_t *dst = V0;
+        if (splits > 1) {
+            ctx->dense_partial.ensure(n_out * splits * sizeof(fr_t));
+            dst = ctx->dense_partial.as<fr_t>();
+        }
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, (uint64_t) d.n_bin * (32ull << fft_bl) + n_out * 32, k_dotprod_axpy, dim3(grid_for(n_out * splits)), dim3(kBlock), 0, dst,
+                       prev.val.as<fr_t>(), ctx->beta_g.as<fr_t>(), L.dp_rowptr.as<uint32_t>(), L.dp_gates.as<dp_gate_t>(), L.dp_rows_live, fft_bl, splits);
+        if (splits > 1) {
+            const uint32_t groups = (uint32_t) ((n_out + kBlock / 32 - 1) / (kBlock / 32));
+            ZK_KLAUNCH_PDL(ctx, ZK_PROF_DENSE, n_out * (splits + 1) * 32, k_colsum_finish, dim3(std::min<uint32_t>(groups, kMaxGridX)), dim3(kBlock), 0, (const fr_t *) dst, (uint32_t) n_out,
+                           splits, V0);
+        }
+    }
     ctx->round = 0;
     ZK_API_END
 }

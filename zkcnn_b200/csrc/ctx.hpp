@@ -139,6 +139,7 @@ struct zk_ctx {
     uint64_t tma_min_entries = 1ull << 17;
     uint32_t pdl_enabled = 1;                // k_round_quad_thin launched with programmatic stream serialization
     uint32_t derive_b_enabled = 1;           // streaming rounds: b from the previous round's polynomial (0: always three products)
+    uint32_t axpy_splits = 0;                // K5b: threads per output of k_dotprod_axpy (0: chosen from the shape)
     uint32_t unit_batch = 0;                 // zk_fold_rounds2 goes through the phase-batched path (tests)
     uint32_t tail_enabled = 1;               // batched phases: all rounds on tables of at most tail_max_entries in one launch (k_round_tail)
     uint32_t tail_max_entries = 1024;

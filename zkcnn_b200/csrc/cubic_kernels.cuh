@@ -339,21 +339,27 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_cubic_tma(
 // (src/prover.cpp:86-91).  CSR by u built at upload; one thread per (u, t), coalesced over t; rows >= n_rows stay unwritten
 // (they are beyond live0).
 struct dp_gate_t { uint32_t g, v; };
-__global__ void __launch_bounds__(kBlock) k_dotprod_axpy(fr_t *out, const fr_t *val, const fr_t *beta_g, const uint32_t *row_ptr,
-                                                         const dp_gate_t *gates, uint32_t n_rows, uint32_t fft_bl) {
+// `splits` threads share one output (u, t): thread s takes every splits-th gate of the row and leaves a partial sum in
+// dst[s * total + idx] (splits == 1: dst is the table itself); k_colsum_finish adds the partials.  With two pictures a layer has as
+// few as 6 rows of 512 gates each: without the split the launch would be 128 CTAs walking 512 gates one after the other.
+__global__ void __launch_bounds__(kBlock) k_dotprod_axpy(fr_t *dst, const fr_t *val, const fr_t *beta_g, const uint32_t *row_ptr,
+                                                         const dp_gate_t *gates, uint32_t n_rows, uint32_t fft_bl, uint32_t splits) {
     ZK_PDL_ENTRY();
     const uint32_t fft_len = 1u << fft_bl;
-    const size_t total = (size_t) n_rows << fft_bl;
-    for (size_t idx = (size_t) blockIdx.x * kBlock + threadIdx.x; idx < total; idx += (size_t) gridDim.x * kBlock) {
+    const size_t total = (size_t) n_rows << fft_bl, work = total * splits;
+    for (size_t w = (size_t) blockIdx.x * kBlock + threadIdx.x; w < work; w += (size_t) gridDim.x * kBlock) {
+        const size_t idx = w % total;
+        const uint32_t sp = (uint32_t) (w / total);
         const uint32_t u = (uint32_t) (idx >> fft_bl), t = (uint32_t) idx & (fft_len - 1);
         const uint32_t k0 = row_ptr[u], k1 = row_ptr[u + 1];
         fr_lazy_t acc;
         acc.clear();
-        for (uint32_t k = k0; k < k1; ++k) {
+        uint32_t cnt = 0;
+        for (uint32_t k = k0 + sp; k < k1; k += splits, ++cnt) {
             const dp_gate_t G = gates[k];
             acc.mac(ld_fr(beta_g + G.g), ld_fr(val + (((size_t) G.v << fft_bl) | t)));
         }
-        st_fr(out + idx, k1 - k0 <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
+        st_fr(dst + w, cnt <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
     }
 }
 

@@ -28,7 +28,8 @@ public:
         buf_.resize(1 << 22);
     }
     ~FastFileNumbers() override { if (f_) fclose(f_); }
-    double next() override {
+    double next() override { return next(nullptr); }
+    double next(bool *end) {
         for (;;) {
             while (pos_ < len_ && isspace((unsigned char) buf_[pos_])) ++pos_;
             // a token must end inside the buffer (or at EOF) before it is parsed
@@ -42,7 +43,7 @@ public:
                 pos_ = e;
                 return x;
             }
-            if (eof_) return 0.0;
+            if (eof_) { if (end) *end = true; return 0.0; }
             refill();
         }
     }
@@ -137,6 +138,24 @@ int zkh_input_file(zkh_session *s, const char *path) {
     s->input_path = path;
     s->values.clear();
     ZKH_END
+}
+
+int64_t zkh_parse_numbers(const char *path, double *out, uint64_t cap) {
+    try {
+        if (!path) throw std::invalid_argument("null path");
+        FastFileNumbers f(path);
+        uint64_t n = 0;
+        for (;; ++n) {
+            bool end = false;
+            const double x = f.next(&end);
+            if (end) break;
+            if (out && n < cap) out[n] = x;
+        }
+        return (int64_t) n;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
 }
 
 int zkh_input_values(zkh_session *s, const double *values, uint64_t n) {
