@@ -178,7 +178,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     model, pics = args.model, args.pics
-    M = args.inflight if args.inflight > 0 else max(1, min(3, (os.cpu_count() or 2) // (2 * world)))
+    M = args.inflight if args.inflight > 0 else max(1, min(6, (os.cpu_count() or 2) // (2 * world)))
     config = NETWORKS.get(model, args.network)
     lib = zkcnn_b200.load()
     # M independent provers per GPU (own zk_ctx, own stream, own witness): M proofs in flight.  Session 0 of rank 0 proves the golden image
@@ -529,7 +529,7 @@ def main():
     ap.add_argument("--model", default="vgg11", choices=["vgg11", "vgg16", "vgg", "lenet"])
     ap.add_argument("--pics", type=int, default=1, help="pictures per proof (pic_cnt); > 1 switches the convolutions to the FFT path (BASELINE config 5)")
     ap.add_argument("--inflight", type=int, default=0,
-                    help="independent provers (own context, stream and witness) per GPU, each on its own host thread; 0 = 3, or fewer when the box has less than two host "
+                    help="independent provers (own context, stream and witness) per GPU, each on its own host thread; 0 = 6, or fewer when the box has less than two host "
                          "cores per prover thread")
     ap.add_argument("--network", default=VGG11)
     ap.add_argument("--e2e", default="image", choices=["image", "upload"],

@@ -130,6 +130,8 @@ int zk_circuit_aux_ops(zk_ctx *ctx, uint32_t layer_id, const uint32_t *ops, uint
  * resident ones (upload a complete witness once).  ranges (NULL or 2 x n_layers values): per layer the largest non-negative value and
  * the largest magnitude of a negative one (what getNextBit, :967-977, turns into the next quantisation scale). */
 int zk_witness_generate(zk_ctx *ctx, const uint64_t *image, uint64_t n_image, uint64_t *ranges);
+/* the same with the ranges restricted to the layers whose flag is set in want_range[n_layers] (NULL: all) */
+int zk_witness_generate_layers(zk_ctx *ctx, const uint64_t *image, uint64_t n_image, uint64_t *ranges, const uint8_t *want_range);
 int zk_witness_read(zk_ctx *ctx, uint32_t layer_id, uint64_t first, uint64_t n, uint64_t *out);
 /* FNV-1a-64 of the canonical encodings of val[layer_id][0, n) on the device (parity tests: the h_val column of the golden circuit dumps) */
 int zk_debug_layer_hash(zk_ctx *ctx, uint32_t layer_id, uint64_t n, uint64_t *fnv1a);

@@ -255,6 +255,13 @@ static void build_eval_schedule(zk_ctx *ctx, uint32_t id, const zk_layer_desc *D
         s.rec = {v_prev ? G.v : D->ori_id_v[G.v], u_prev ? G.u : D->ori_id_u[G.u], (uint32_t) G.sc | kEvBin | (u_prev ? kEvUPrev : 0u) | (v_prev ? kEvVPrev : 0u)};
         src.push_back(s);
     }
+    {   // how many output gates have a source at all
+        std::vector<bool> seen(D->size, false);
+        uint32_t covered = 0;
+        for (auto &x : src)
+            if (x.rowkey < D->size && !seen[x.rowkey]) { seen[x.rowkey] = true; ++covered; }
+        L.ev_rows_covered = covered;
+    }
     build_schedule(ctx, L.ev, src, 1u << D->bit_length, 0, false);
 }
 

@@ -8,8 +8,9 @@ static void eval_normal_layer(zk_ctx *ctx, uint32_t id) {
     layer_t &L = ctx->layers[id];
     layer_t &prev = ctx->layers[id - 1];
     fr_t *out = L.val.as<fr_t>();
-    rt::dzero(out, (size_t) L.d.size * sizeof(fr_t), ctx->stream);   // gates without any source stay zero (src/neuralNetwork.cpp:920)
     const schedule_t &S = L.ev;
+    // gates without any source stay zero (src/neuralNetwork.cpp:920); a layer whose every gate has a source is written completely by the items
+    if (L.ev_rows_covered < L.d.size || S.levels.empty()) rt::dzero(out, (size_t) L.d.size * sizeof(fr_t), ctx->stream);
     if (S.levels.empty()) return;
     ctx->gate_partial[0].ensure((size_t) std::max(1u, S.max_partials) * sizeof(fr_t));
     ctx->gate_partial[1].ensure((size_t) std::max(1u, S.max_partials) * sizeof(fr_t));
@@ -124,7 +125,12 @@ int zk_circuit_aux_ops(zk_ctx *ctx, uint32_t layer_id, const uint32_t *ops /* n 
 // resident ones (a complete witness must have been uploaded once).  ranges (may be NULL) receives, per layer, the largest non-negative
 // value and the largest magnitude of a negative one (2 x n_layers values): what getNextBit (:967-977) derives the next quantisation scale
 // from -- the caller checks that the circuit's structure (bit widths of the decompositions) still fits the new picture.
+int zk_witness_generate_layers(zk_ctx *ctx, const uint64_t *image, uint64_t n_image, uint64_t *ranges, const uint8_t *want_range);
 int zk_witness_generate(zk_ctx *ctx, const uint64_t *image, uint64_t n_image, uint64_t *ranges) {
+    return zk_witness_generate_layers(ctx, image, n_image, ranges, nullptr);
+}
+// want_range (NULL: every layer): n_layers flags, ranges are only computed for the layers whose flag is set (the others read as zero)
+int zk_witness_generate_layers(zk_ctx *ctx, const uint64_t *image, uint64_t n_image, uint64_t *ranges, const uint8_t *want_range) {
     ZK_API_BEGIN
     using namespace zk;
     ZK_REQUIRE(ctx && ctx->circuit_ready && image && n_image >= 1, "bad arguments");
@@ -151,7 +157,7 @@ int zk_witness_generate(zk_ctx *ctx, const uint64_t *image, uint64_t n_image, ui
         if (L.d.ty == ZK_LAYER_FFT || L.d.ty == ZK_LAYER_IFFT) eval_fft_layer(ctx, i);
         else if (L.d.ty == ZK_LAYER_DOT_PROD) eval_dotprod_layer(ctx, i);
         else eval_normal_layer(ctx, i);
-        if (ranges)
+        if (ranges && (!want_range || want_range[i]))
             ZK_KLAUNCH(ctx, k_layer_range, dim3(std::min<uint32_t>(grid_for(L.d.size), ZK_SM_COUNT * 4)), dim3(kBlock), 0, (const fr_t *) L.val.as<fr_t>(), (uint64_t) L.d.size,
                        ctx->vres_scratch.as<unsigned long long>() + 2 * i);
     }

@@ -33,6 +33,7 @@ struct layer_t {
     // witness generation on the device (capi_witness.cuh): gates sorted by OUTPUT gate; DOT_PROD: CSR by output block; the auxiliary
     // inputs this layer's construction derives from earlier layers (bit decompositions, window maxima), in execution order
     schedule_t ev;
+    uint32_t ev_rows_covered = 0;   // output gates that have at least one source gate (== size: no zero-fill needed)
     rt::dbuf dpe_rowptr, dpe_gates;
     uint32_t dpe_rows = 0;
     rt::dbuf aux_bits_prev, aux_max, aux_bits_l0;   // aux_op_t arrays: bits of val[l-1] entries, maxima over val[l-1] entries, bits of val[0] entries

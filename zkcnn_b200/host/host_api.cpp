@@ -242,7 +242,8 @@ static int set_image(zkh_session *s, const double *pixels, uint64_t n_pixels, ui
     vector<F> image;
     if (s->nn->deviceWitnessSupported() && s->nn->quantizeImage(pixels, n_pixels, image)) {
         std::vector<uint64_t> ranges;
-        s->p.generateWitnessOnDevice(image, ranges);
+        const std::vector<uint8_t> want = s->nn->scaleDecisionLayers(s->p.C.size);
+        s->p.generateWitnessOnDevice(image, ranges, &want);
         if (h2d_bytes) *h2d_bytes = image.size() * sizeof(F);
         if (s->nn->scalesMatch(ranges.data(), s->p.C.size)) {
             const u32 last = s->p.C.size - 1;

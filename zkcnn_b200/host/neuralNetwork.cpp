@@ -773,6 +773,13 @@ bool neuralNetwork::scalesMatch(const uint64_t *ranges, size_t n_layers) const {
     return true;
 }
 
+std::vector<uint8_t> neuralNetwork::scaleDecisionLayers(size_t n_layers) const {
+    std::vector<uint8_t> f(n_layers, 0);
+    for (const auto &d : scale_decisions_)
+        if ((size_t) d.layer < n_layers) f[d.layer] = 1;
+    return f;
+}
+
 void neuralNetwork::inferFromOutput(const vector<F> &output) {
     inferred.assign(pic_parallel, -1);
     if (full_conn.empty()) return;

@@ -66,6 +66,7 @@ public:
     // ranges[2 * layer], ranges[2 * layer + 1] = largest non-negative value / largest magnitude of a negative value of that layer
     // (zk_witness_generate); true iff every getNextBit decision of create() comes out the same
     bool scalesMatch(const uint64_t *ranges, size_t n_layers) const;
+    std::vector<uint8_t> scaleDecisionLayers(size_t n_layers) const;   // flag per layer: a getNextBit decision was taken on its values
     i64 imagePixels() const { return pic_size_x * pic_size_y * pic_channel; }
     // argmax of the output layer (what printInfer does) from its values
     void inferFromOutput(const vector<F> &output);

@@ -203,7 +203,7 @@ void prover::init() {   // src/prover.cpp:17-21 (+ upload of what the reference 
     upload_timer.stop();
 }
 
-void prover::generateWitnessOnDevice(const vector<F> &image, std::vector<uint64_t> &ranges) {
+void prover::generateWitnessOnDevice(const vector<F> &image, std::vector<uint64_t> &ranges, const std::vector<uint8_t> *want_range) {
     upload_timer.start();
     joinPrefetch();
     prefetch_pending_ = false;
@@ -216,7 +216,8 @@ void prover::generateWitnessOnDevice(const vector<F> &image, std::vector<uint64_
     if (!circuit_uploaded_) { uploadCircuit(); witness_uploaded_ = false; }
     if (!witness_uploaded_) uploadWitness();   // once: the quantised weights stay resident in val[0]
     ranges.assign((size_t) 2 * C.size, 0);
-    check(zk_witness_generate(ctx_, w(image[0]), image.size(), ranges.data()), "zk_witness_generate");
+    check(zk_witness_generate_layers(ctx_, w(image[0]), image.size(), ranges.data(), want_range && want_range->size() == (size_t) C.size ? want_range->data() : nullptr),
+          "zk_witness_generate");
     last_upload_bytes_ = image.size() * sizeof(F);
     upload_timer.stop();
 }

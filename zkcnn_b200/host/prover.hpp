@@ -88,7 +88,7 @@ public:
     // new picture, same circuit: upload `image` (val[0][0, image.size())), regenerate every auxiliary input and layer on the device and make
     // that the current witness (the host copy `val` is NOT updated).  ranges: 2 x C.size values (zk_witness_generate).  The circuit and one
     // complete witness are uploaded first if they are not there yet.
-    void generateWitnessOnDevice(const vector<F> &image, std::vector<uint64_t> &ranges);
+    void generateWitnessOnDevice(const vector<F> &image, std::vector<uint64_t> &ranges, const std::vector<uint8_t> *want_range = nullptr);
     vector<F> readLayer(u32 layer, size_t n);   // values of a (short) layer as they stand on the device
     // CUDA device used by this prover (default: env ZKCNN_DEVICE or 0).  Call before init().
     void setDevice(int device) { device_ = device; }
