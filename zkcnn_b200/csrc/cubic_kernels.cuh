@@ -53,10 +53,10 @@ ZK_HD __forceinline__ fr_t fr_lazy_reduce_any(const fr_lazy_t &a) {
 struct cubic_mult_t { fr_t m0, dm; };
 __device__ __forceinline__ fr_t cubic_fold_entry(const cubic_args_t &A, uint32_t k) {   // entry k of the current multiplier table
     if (A.fold && A.m_n >= 2) {
-        const fr_t x0 = ld_fr(A.m_in + 2 * k), x1 = ld_fr(A.m_in + 2 * k + 1);
+        const fr_t x0 = ld_fr_g(A.m_in + 2 * k), x1 = ld_fr_g(A.m_in + 2 * k + 1);
         return x0 + A.r * (x1 - x0);
     }
-    return ld_fr(A.m_in + k);
+    return ld_fr_g(A.m_in + k);
 }
 __device__ __forceinline__ uint32_t cubic_cur_n(const cubic_args_t &A) { return (A.fold && A.m_n >= 2) ? A.m_n >> 1 : A.m_n; }
 __device__ __forceinline__ cubic_mult_t cubic_mult_of(const cubic_args_t &A, uint32_t first_pair) {
@@ -155,8 +155,8 @@ template <bool FACTORED> __global__ void __launch_bounds__(kRoundBlock) k_round_
             const uint32_t base = i << 2;
             const fr_t x0 = ld_fr_live(A.v1_in, base, A.live1), x1 = ld_fr_live(A.v1_in, base + 1, A.live1);
             const fr_t x2 = ld_fr_live(A.v1_in, base + 2, A.live1), x3 = ld_fr_live(A.v1_in, base + 3, A.live1);
-            st_fr(A.v1_out + 2 * i, x0 + r * fr_t::sub_lazy(x1, x0));
-            st_fr(A.v1_out + 2 * i + 1, x2 + r * fr_t::sub_lazy(x3, x2));
+            st_fr_g(A.v1_out + 2 * i, x0 + r * fr_t::sub_lazy(x1, x0));
+            st_fr_g(A.v1_out + 2 * i + 1, x2 + r * fr_t::sub_lazy(x3, x2));
         }
         return;
     }
@@ -164,7 +164,7 @@ template <bool FACTORED> __global__ void __launch_bounds__(kRoundBlock) k_round_
     const uint32_t first = blockIdx.x * kRoundBlock + threadIdx.x;
     // the folded multiplier table for the next round
     if (A.fold && A.m_n >= 2)
-        for (uint32_t k = first; k < (A.m_n >> 1); k += stride) st_fr(A.m_out + k, cubic_fold_entry(A, k));
+        for (uint32_t k = first; k < (A.m_n >> 1); k += stride) st_fr_g(A.m_out + k, cubic_fold_entry(A, k));
     const cubic_mult_t M = cubic_mult_of(A, first);
     fr_lazy_t co[4], q[3];
 #pragma unroll
@@ -179,14 +179,14 @@ template <bool FACTORED> __global__ void __launch_bounds__(kRoundBlock) k_round_
             fr_t x2 = ld_fr_live(A.v1_in, base + 2, A.live1), x3 = ld_fr_live(A.v1_in, base + 3, A.live1);
             q0 = x0 + r * fr_t::sub_lazy(x1, x0);
             q1 = x2 + r * fr_t::sub_lazy(x3, x2);
-            st_fr(A.v1_out + 2 * i, q0);
-            st_fr(A.v1_out + 2 * i + 1, q1);
+            st_fr_g(A.v1_out + 2 * i, q0);
+            st_fr_g(A.v1_out + 2 * i + 1, q1);
             x0 = ld_fr_live(A.v0_in, base, A.live0); x1 = ld_fr_live(A.v0_in, base + 1, A.live0);
             x2 = ld_fr_live(A.v0_in, base + 2, A.live0); x3 = ld_fr_live(A.v0_in, base + 3, A.live0);
             p0 = x0 + r * fr_t::sub_lazy(x1, x0);
             p1 = x2 + r * fr_t::sub_lazy(x3, x2);
-            st_fr(A.v0_out + 2 * i, p0);
-            st_fr(A.v0_out + 2 * i + 1, p1);
+            st_fr_g(A.v0_out + 2 * i, p0);
+            st_fr_g(A.v0_out + 2 * i + 1, p1);
         } else {
             q0 = ld_fr_live(A.v1_in, 2 * i, A.live1); q1 = ld_fr_live(A.v1_in, 2 * i + 1, A.live1);
             p0 = ld_fr_live(A.v0_in, 2 * i, A.live0); p1 = ld_fr_live(A.v0_in, 2 * i + 1, A.live0);
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kRoundBlock, kTmaCtasPerSm) k_round_cubic_tma(
     if (!seg1) {
         const uint32_t tg = bx * kRoundBlock + threadIdx.x, tstride = A.nb0 * kRoundBlock;
         if (A.m_n >= 2)
-            for (uint32_t k = tg; k < (A.m_n >> 1); k += tstride) st_fr(A.m_out + k, cubic_fold_entry(A, k));
+            for (uint32_t k = tg; k < (A.m_n >> 1); k += tstride) st_fr_g(A.m_out + k, cubic_fold_entry(A, k));
         M = cubic_mult_of(A, first_pair);
     }
     fr_lazy_t q[3];
@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(kBlock) k_dotprod_axpy(fr_t *dst, const fr_t *
         uint32_t cnt = 0;
         for (uint32_t k = k0 + sp; k < k1; k += splits, ++cnt) {
             const dp_gate_t G = gates[k];
-            acc.mac(ld_fr(beta_g + G.g), ld_fr(val + (((size_t) G.v << fft_bl) | t)));
+            acc.mac(ld_fr_g(beta_g + G.g), ld_fr_g(val + (((size_t) G.v << fft_bl) | t)));
         }
-        st_fr(dst + w, cnt <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
+        st_fr_g(dst + w, cnt <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
     }
 }
 
@@ -374,8 +374,8 @@ __global__ void __launch_bounds__(kBlock) k_dense_colsum(const fr_t *val, const 
     fr_lazy_t acc;
     acc.clear();
     uint32_t cnt = 0;
-    for (uint64_t i = t; i < total; i += T, ++cnt) acc.mac(ld_fr(val + i), ld_fr(beta_g + (i >> shift)));
-    st_fr(partial + t, cnt <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
+    for (uint64_t i = t; i < total; i += T, ++cnt) acc.mac(ld_fr_g(val + i), ld_fr_g(beta_g + (i >> shift)));
+    st_fr_g(partial + t, cnt <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
 }
 // out[u] = sum_k partial[u + k * n_u], k < per_u; one warp per column u
 __global__ void __launch_bounds__(kBlock) k_colsum_finish(const fr_t *partial, uint32_t n_u, uint32_t per_u, fr_t *out) {
@@ -388,11 +388,11 @@ __global__ void __launch_bounds__(kBlock) k_colsum_finish(const fr_t *partial, u
         if (u < n_u) {
             uint32_t k = lane;
             for (; k + 96 < per_u; k += 128) {   // four independent loads in flight
-                const fr_t a = ld_fr(partial + u + (size_t) k * n_u), b = ld_fr(partial + u + (size_t) (k + 32) * n_u);
-                const fr_t c = ld_fr(partial + u + (size_t) (k + 64) * n_u), d = ld_fr(partial + u + (size_t) (k + 96) * n_u);
+                const fr_t a = ld_fr_g(partial + u + (size_t) k * n_u), b = ld_fr_g(partial + u + (size_t) (k + 32) * n_u);
+                const fr_t c = ld_fr_g(partial + u + (size_t) (k + 64) * n_u), d = ld_fr_g(partial + u + (size_t) (k + 96) * n_u);
                 acc = acc + ((a + b) + (c + d));
             }
-            for (; k < per_u; k += 32) acc = acc + ld_fr(partial + u + (size_t) k * n_u);
+            for (; k < per_u; k += 32) acc = acc + ld_fr_g(partial + u + (size_t) k * n_u);
         }
         for (uint32_t d = 16; d; d >>= 1) {
             fr_t o;
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kBlock) k_colsum_finish(const fr_t *partial, u
             for (int j = 0; j < 8; ++j) o.v[j] = __shfl_xor_sync(0xffffffffu, acc.v[j], d);
             acc = acc + o;
         }
-        if (lane == 0 && u < n_u) st_fr(out + u, acc);
+        if (lane == 0 && u < n_u) st_fr_g(out + u, acc);
     }
 }
 
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kBlock) k_dense_rowdot(fr_t *out, const fr_t *
         fr_lazy_t acc;
         acc.clear();
         if (v < n_rows)
-            for (uint32_t t = sub; t < fft_len; t += lanes) acc.mac(ld_fr(val + (((size_t) v << fft_bl) | t)), ld_fr(beta_gs + t));
+            for (uint32_t t = sub; t < fft_len; t += lanes) acc.mac(ld_fr_g(val + (((size_t) v << fft_bl) | t)), ld_fr_g(beta_gs + t));
         for (uint32_t d = lanes >> 1; d; d >>= 1) {
             uint32_t o[fr_lazy_t::W];
 #pragma unroll
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kBlock) k_dense_rowdot(fr_t *out, const fr_t *
                 c >>= 32;
             }
         }
-        if (sub == 0 && v < n_rows) st_fr(out + v, fr_lazy_reduce_any(acc));
+        if (sub == 0 && v < n_rows) st_fr_g(out + v, fr_lazy_reduce_any(acc));
     }
 }
 

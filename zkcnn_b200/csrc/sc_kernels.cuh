@@ -64,6 +64,26 @@ ZK_HD __forceinline__ void st_fr(fr_t *p, const fr_t &x) {
     *p = x;
 #endif
 }
+// The same for pointers known to be in GLOBAL memory and 32-byte aligned (every table, witness layer and schedule-addressed element is):
+// ONE 256-bit access (LDG.E.256 / STG.E.256, sm_100) instead of two 128-bit ones -- a random 32-byte gather is one request, one sector.
+ZK_HD __forceinline__ fr_t ld_fr_g(const fr_t *p) {
+#if ZK_ON_DEVICE
+    fr_t r;
+    asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+#else
+    return *p;
+#endif
+}
+ZK_HD __forceinline__ void st_fr_g(fr_t *p, const fr_t &x) {
+#if ZK_ON_DEVICE
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]),
+                 "r"(x.v[6]), "r"(x.v[7]) : "memory");
+#else
+    *p = x;
+#endif
+}
 // L2-coherent load for data produced by other CTAs of the same launch ("last CTA finishes" reductions)
 ZK_HD __forceinline__ fr_t ld_fr_cg(const fr_t *p) {
 #if ZK_ON_DEVICE
@@ -79,7 +99,7 @@ ZK_HD __forceinline__ fr_t ld_fr_cg(const fr_t *p) {
 }
 // guarded load: entries at or beyond `live` are zero by construction (src/prover.cpp:409-417 clears them)
 ZK_HD __forceinline__ fr_t ld_fr_live(const fr_t *p, uint32_t idx, uint32_t live) {
-    return idx < live ? ld_fr(p + idx) : fr_t::zero();
+    return idx < live ? ld_fr_g(p + idx) : fr_t::zero();
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -405,12 +425,12 @@ __global__ void __launch_bounds__(kRoundBlock, ZK_ROUND_CTAS_PER_SM) k_round_qua
             fr_t y2 = ld_fr_live(m_in, base + 2, live), y3 = ld_fr_live(m_in, base + 3, live);
             const fr_t v0 = x0 + r * fr_t::sub_lazy(x1, x0);
             const fr_t v1 = x2 + r * fr_t::sub_lazy(x3, x2);
-            st_fr(v_out + 2 * i, v0);
-            st_fr(v_out + 2 * i + 1, v1);
+            st_fr_g(v_out + 2 * i, v0);
+            st_fr_g(v_out + 2 * i + 1, v1);
             const fr_t m0 = y0 + r * fr_t::sub_lazy(y1, y0);
             const fr_t m1 = y2 + r * fr_t::sub_lazy(y3, y2);
-            st_fr(m_out + 2 * i, m0);
-            st_fr(m_out + 2 * i + 1, m1);
+            st_fr_g(m_out + 2 * i, m0);
+            st_fr_g(m_out + 2 * i + 1, m1);
             acc[0].mac(fr_t::sub_lazy(m1, m0), fr_t::sub_lazy(v1, v0));
             acc[1].mac(m0, v0);
             if (!derive) acc[2].mac(m1, v1);
@@ -472,7 +492,7 @@ __global__ void __launch_bounds__(kRoundBlock) k_round_quad_thin(round_args_t A)
             const uint32_t idx = 4 * q + 2 * (role & 1u);
             const fr_t x0 = on ? ld_fr_live(src, idx, live) : fr_t::zero(), x1 = on ? ld_fr_live(src, idx + 1, live) : fr_t::zero();
             const fr_t y = x0 + r * fr_t::sub_lazy(x1, x0);
-            if (on) st_fr((role < 2 ? v_out : m_out) + 2 * q + (role & 1u), y);
+            if (on) st_fr_g((role < 2 ? v_out : m_out) + 2 * q + (role & 1u), y);
             fr_t o1, o2, d, d2;
 #pragma unroll
             for (int j = 0; j < 8; ++j) o1.v[j] = __shfl_xor_sync(0xffffffffu, y.v[j], 1);
@@ -656,8 +676,8 @@ __global__ void __launch_bounds__(kTailBlock, 1) k_round_tail(tail_args_t A) {
     }
     for (int p = 0; p < 2; ++p)
         if (tid < n[p]) {
-            st_fr(A.v_out[p] + tid, ld_fr(cur[2 * p] + tid));
-            st_fr(A.m_out[p] + tid, ld_fr(cur[2 * p + 1] + tid));
+            st_fr_g(A.v_out[p] + tid, ld_fr(cur[2 * p] + tid));
+            st_fr_g(A.m_out[p] + tid, ld_fr(cur[2 * p + 1] + tid));
         }
 }
 
@@ -864,15 +884,15 @@ __global__ void __launch_bounds__(kBlock) k_expand_i64(fr_t *out, const long lon
     uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x;
     for (; i + 3 * stride < n; i += 4 * stride) {
         const long long a = in[i], b = in[i + stride], c = in[i + 2 * stride], d = in[i + 3 * stride];
-        st_fr(out + i, fr_t::from_i64(a));
-        st_fr(out + i + stride, fr_t::from_i64(b));
-        st_fr(out + i + 2 * stride, fr_t::from_i64(c));
-        st_fr(out + i + 3 * stride, fr_t::from_i64(d));
+        st_fr_g(out + i, fr_t::from_i64(a));
+        st_fr_g(out + i + stride, fr_t::from_i64(b));
+        st_fr_g(out + i + 2 * stride, fr_t::from_i64(c));
+        st_fr_g(out + i + 3 * stride, fr_t::from_i64(d));
     }
-    for (; i < n; i += stride) st_fr(out + i, fr_t::from_i64(in[i]));
+    for (; i < n; i += stride) st_fr_g(out + i, fr_t::from_i64(in[i]));
 }
 __global__ void __launch_bounds__(kBlock) k_scatter_fr(fr_t *out, const uint32_t *idx, const fr_t *val, uint32_t n) {
-    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr(out + idx[i], ld_fr(val + i));
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr_g(out + idx[i], ld_fr_g(val + i));
 }
 
 // fold a 2-entry table pair down to single values (the "total == 1" collapse, src/prover.cpp:400-404, and the
@@ -951,10 +971,10 @@ __global__ void __launch_bounds__(kBlock) k_beta_expand(beta_args_t A) {
     ZK_PDL_ENTRY();
     const uint32_t n = 1u << A.bits, mask = (1u << A.first_half) - 1;
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-        fr_t x = A.f0 ? ld_fr(A.f0 + (i & mask)) * ld_fr(A.s0 + (i >> A.first_half)) : fr_t::zero();
-        if (A.f1) x = x + ld_fr(A.f1 + (i & mask)) * ld_fr(A.s1 + (i >> A.first_half));
+        fr_t x = A.f0 ? ld_fr_g(A.f0 + (i & mask)) * ld_fr_g(A.s0 + (i >> A.first_half)) : fr_t::zero();
+        if (A.f1) x = x + ld_fr_g(A.f1 + (i & mask)) * ld_fr_g(A.s1 + (i >> A.first_half));
         if (i >= A.tail_start) x = x * A.tail_scale;
-        st_fr(A.out + i, x);
+        st_fr_g(A.out + i, x);
     }
 }
 
@@ -964,9 +984,9 @@ __global__ void __launch_bounds__(kBlock) k_beta_outer(fr_t *out, const fr_t *hi
     ZK_PDL_ENTRY();
     const uint32_t n = 1u << bits, mask = (1u << blh) - 1;
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-        fr_t x = ld_fr(hi + (i >> blh)) * ld_fr(lo + (i & mask));
+        fr_t x = ld_fr_g(hi + (i >> blh)) * ld_fr_g(lo + (i & mask));
         if (i >= tail_start) x = x * tail_scale;
-        st_fr(out + i, x);
+        st_fr_g(out + i, x);
     }
 }
 
@@ -1046,9 +1066,9 @@ struct gate_args_t {
 
 __device__ __forceinline__ void store_item(const gate_args_t &A, uint32_t dest, const fr_t &acc) {
     if (dest & kDestFinal) {
-        if (dest & kDestScalar) st_fr(A.out_scalar, acc);
-        else st_fr(((dest & kDestTable1) ? A.out1 : A.out0) + (dest & 0x1fffffffu), acc);
-    } else st_fr(A.partial + dest, acc);
+        if (dest & kDestScalar) st_fr_g(A.out_scalar, acc);
+        else st_fr_g(((dest & kDestTable1) ? A.out1 : A.out0) + (dest & 0x1fffffffu), acc);
+    } else st_fr_g(A.partial + dest, acc);
 }
 
 // An item's <= 16 products are accumulated unreduced (lazy_acc_t) and reduced once (fr_lazy_reduce_upto16): these kernels
@@ -1062,12 +1082,12 @@ __global__ void __launch_bounds__(kBlock) k_gate_items_p1(gate_args_t A) {
         acc.clear();
         for (uint32_t k = 0; k < cnt; ++k) {
             const gate_rec_t R = A.recs[I.begin + k];
-            const fr_t bg = ld_fr(A.beta_g + R.g);
+            const fr_t bg = ld_fr_g(A.beta_g + R.g);
             const uint32_t kind = (R.meta >> 16) & 3u, sc = R.meta & 0x1ffu;
-            if (kind == 0) acc.mac(bg, sc ? ld_fr(A.two_mul + sc) : fr_t::one());
+            if (kind == 0) acc.mac(bg, sc ? ld_fr_g(A.two_mul + sc) : fr_t::one());
             else {
-                const fr_t v = ld_fr((kind == 1 ? A.val0 : A.val_prev) + R.x);
-                if (sc) acc.mac(bg * v, ld_fr(A.two_mul + sc));
+                const fr_t v = ld_fr_g((kind == 1 ? A.val0 : A.val_prev) + R.x);
+                if (sc) acc.mac(bg * v, ld_fr_g(A.two_mul + sc));
                 else acc.mac(bg, v);
             }
         }
@@ -1084,9 +1104,9 @@ __global__ void __launch_bounds__(kBlock) k_gate_items_p2(gate_args_t A) {
         acc.clear();
         for (uint32_t k = 0; k < cnt; ++k) {
             const gate_rec_t R = A.recs[I.begin + k];
-            const fr_t bg = ld_fr(A.beta_g + R.g), bu = ld_fr(A.beta_u + R.x);
+            const fr_t bg = ld_fr_g(A.beta_g + R.g), bu = ld_fr_g(A.beta_u + R.x);
             const uint32_t sc = R.meta & 0x1ffu;
-            if (sc) acc.mac(bg * bu, ld_fr(A.two_mul + sc));
+            if (sc) acc.mac(bg * bu, ld_fr_g(A.two_mul + sc));
             else acc.mac(bg, bu);
         }
         store_item(A, I.dest, fr_lazy_reduce_upto16(acc) * A.vu[(I.count_flags >> 16) & 1u]);
@@ -1100,7 +1120,7 @@ __global__ void __launch_bounds__(kBlock) k_sum_partials(gate_args_t A, const fr
         const item_t I = A.items[it];
         const uint32_t cnt = I.count_flags & 0xffffu;
         fr_t acc = fr_t::zero();
-        for (uint32_t k = 0; k < cnt; ++k) acc = acc + ld_fr(src + I.begin + k);
+        for (uint32_t k = 0; k < cnt; ++k) acc = acc + ld_fr_g(src + I.begin + k);
         store_item(A, I.dest, acc);
     }
 }
@@ -1108,7 +1128,7 @@ __global__ void __launch_bounds__(kBlock) k_sum_partials(gate_args_t A, const fr
 // V table of operands that live in layer 0: V[u] = val[0][ori_id[u]]  (getCirValue, src/prover.cpp:499-501)
 __global__ void __launch_bounds__(kBlock) k_gather(fr_t *out, const fr_t *val0, const uint32_t *ori, uint32_t n) {
     ZK_PDL_ENTRY();
-    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr(out + i, ld_fr(val0 + ori[i]));
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr_g(out + i, ld_fr_g(val0 + ori[i]));
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -1121,9 +1141,9 @@ __global__ void __launch_bounds__(kBlock) k_liu_scatter(fr_t *mult, const uint32
     ZK_PDL_ENTRY();
     const uint32_t mask = (1u << first_half) - 1;
     for (uint32_t h = blockIdx.x * kBlock + threadIdx.x; h < n; h += gridDim.x * kBlock) {
-        fr_t b = ld_fr(f + (h & mask)) * ld_fr(s + (h >> first_half));
+        fr_t b = ld_fr_g(f + (h & mask)) * ld_fr_g(s + (h >> first_half));
         const uint32_t x = ori[h];
-        st_fr(mult + x, ld_fr(mult + x) + b);
+        st_fr_g(mult + x, ld_fr_g(mult + x) + b);
     }
 }
 

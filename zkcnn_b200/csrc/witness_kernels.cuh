@@ -45,19 +45,19 @@ __global__ void __launch_bounds__(kBlock) k_eval_items(gate_args_t A) {
         for (uint32_t k = 0; k < cnt; ++k) {
             const gate_rec_t R = A.recs[I.begin + k];
             const uint32_t sc = R.meta & 0x1ffu;
-            const fr_t x = ld_fr(((R.meta & kEvUPrev) ? A.val_prev : A.val0) + R.x);
+            const fr_t x = ld_fr_g(((R.meta & kEvUPrev) ? A.val_prev : A.val0) + R.x);
             if (R.meta & kEvBin) {
-                const fr_t y = ld_fr(((R.meta & kEvVPrev) ? A.val_prev : A.val0) + R.g);
-                if (sc) acc.mac(x * y, ld_fr(A.two_mul + sc));
+                const fr_t y = ld_fr_g(((R.meta & kEvVPrev) ? A.val_prev : A.val0) + R.g);
+                if (sc) acc.mac(x * y, ld_fr_g(A.two_mul + sc));
                 else acc.mac(x, y);
-            } else acc.mac(x, sc ? ld_fr(A.two_mul + sc) : fr_t::one());
+            } else acc.mac(x, sc ? ld_fr_g(A.two_mul + sc) : fr_t::one());
         }
         store_item(A, I.dest, fr_lazy_reduce_upto16(acc));
     }
 }
 
 __global__ void __launch_bounds__(kBlock) k_scale_vec(fr_t *v, uint64_t n, fr_t s) {
-    for (uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t) gridDim.x * kBlock) st_fr(v + i, ld_fr(v + i) * s);
+    for (uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t) gridDim.x * kBlock) st_fr_g(v + i, ld_fr_g(v + i) * s);
 }
 
 // DOT_PROD layer: CSR by output block g of (u block, v block) pairs; one thread per (g, t)
@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(kBlock) k_dotprod_eval(fr_t *out, const fr_t *
         acc.clear();
         for (uint32_t k = k0; k < k1; ++k) {
             const dp_eval_t G = gates[k];
-            acc.mac(ld_fr(src + (((size_t) G.u << fft_bl) | t)), ld_fr(src + (((size_t) G.v << fft_bl) | t)));
+            acc.mac(ld_fr_g(src + (((size_t) G.u << fft_bl) | t)), ld_fr_g(src + (((size_t) G.v << fft_bl) | t)));
         }
-        st_fr(out + idx, k1 - k0 <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
+        st_fr_g(out + idx, k1 - k0 <= 16 ? fr_lazy_reduce_upto16(acc) : fr_lazy_reduce_any(acc));
     }
 }
 
@@ -91,14 +91,14 @@ __global__ void __launch_bounds__(kBlock) k_ntt_blocks(fr_t *out, const fr_t *sr
         const fr_t *in = src + (size_t) blk * (inverse ? len : half);
         for (uint32_t i = threadIdx.x; i < len; i += kBlock) {   // bit-reversed load
             const uint32_t rev = n ? __brev(i) >> (32 - n) : 0;
-            st_fr(a + rev, (inverse || i < half) ? ld_fr(in + i) : fr_t::zero());
+            st_fr(a + rev, (inverse || i < half) ? ld_fr_g(in + i) : fr_t::zero());
         }
         __syncthreads();
         for (uint32_t span = 2; span <= len; span <<= 1) {
             const uint32_t hs = span >> 1, step = len / span;
             for (uint32_t b = threadIdx.x; b < half; b += kBlock) {
                 const uint32_t k = b & (hs - 1), j = (b / hs) * span;
-                const fr_t u = ld_fr(a + j + k), v = ld_fr(a + j + k + hs) * ld_fr(pw + (size_t) step * k);
+                const fr_t u = ld_fr(a + j + k), v = ld_fr(a + j + k + hs) * ld_fr_g(pw + (size_t) step * k);
                 st_fr(a + j + k, u + v);
                 st_fr(a + j + k + hs, u - v);
             }
@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(kBlock) k_ntt_blocks(fr_t *out, const fr_t *sr
         }
         fr_t *o = out + (size_t) blk * (inverse ? half : len);
         if (inverse)
-            for (uint32_t i = threadIdx.x; i < half; i += kBlock) st_fr(o + i, ld_fr(a + i) * ilen);
+            for (uint32_t i = threadIdx.x; i < half; i += kBlock) st_fr_g(o + i, ld_fr(a + i) * ilen);
         else
-            for (uint32_t i = threadIdx.x; i < len; i += kBlock) st_fr(o + i, ld_fr(a + i));
+            for (uint32_t i = threadIdx.x; i < len; i += kBlock) st_fr_g(o + i, ld_fr(a + i));
         __syncthreads();
     }
 }
@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(kBlock) k_aux_bits(fr_t *val0, const fr_t *src
     for (uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x; i < n_ops; i += (uint64_t) gridDim.x * kBlock) {
         const aux_op_t op = ops[i];
         unsigned long long mag;
-        const bool neg = fr_sign_magnitude(ld_fr(src + op.src), &mag);
+        const bool neg = fr_sign_magnitude(ld_fr_g(src + op.src), &mag);
         const bool bit = ((op.meta >> 8) & 3u) == kAuxSign ? neg : ((mag >> (op.meta & 0xffu)) & 1ull) != 0;
-        st_fr(val0 + op.dst, bit ? fr_t::one() : fr_t::zero());
+        st_fr_g(val0 + op.dst, bit ? fr_t::one() : fr_t::zero());
     }
 }
 // running maximum of max(0, value) over the window elements of a pooling cell: scratch[dst - base] (zero on entry)
@@ -136,13 +136,13 @@ __global__ void __launch_bounds__(kBlock) k_aux_max(unsigned long long *scratch,
     for (uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x; i < n_ops; i += (uint64_t) gridDim.x * kBlock) {
         const aux_op_t op = ops[i];
         unsigned long long mag;
-        const bool neg = fr_sign_magnitude(ld_fr(src + op.src), &mag);
+        const bool neg = fr_sign_magnitude(ld_fr_g(src + op.src), &mag);
         if (!neg && mag) atomicMax(scratch + (op.dst - base), mag);
     }
 }
 __global__ void __launch_bounds__(kBlock) k_aux_max_store(fr_t *val0, uint32_t base, const unsigned long long *scratch, uint32_t n) {
     ZK_PDL_ENTRY();
-    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr(val0 + base + i, fr_t::from_u64(scratch[i]));
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) st_fr_g(val0 + base + i, fr_t::from_u64(scratch[i]));
 }
 
 // out[0] = largest non-negative value, out[1] = largest magnitude of a negative value (both zero on entry)
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kBlock) k_layer_range(const fr_t *val, uint64_
     unsigned long long mx = 0, mn = 0;
     for (uint64_t i = (uint64_t) blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t) gridDim.x * kBlock) {
         unsigned long long mag;
-        if (fr_sign_magnitude(ld_fr(val + i), &mag)) mn = mag > mn ? mag : mn;
+        if (fr_sign_magnitude(ld_fr_g(val + i), &mag)) mn = mag > mn ? mag : mn;
         else mx = mag > mx ? mag : mx;
     }
     if (mx) atomicMax(out, mx);
