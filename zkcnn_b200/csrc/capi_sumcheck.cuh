@@ -144,7 +144,7 @@ static void build_schedule(zk_ctx *ctx, schedule_t &S, std::vector<src_t> &src, 
     std::vector<src_t>().swap(src);
 
     // level 0 items
-    std::vector<gate_rec_t> recs(sorted.size());
+    std::vector<gate_rec_t> recs;
     std::vector<item_t> items;
     std::vector<uint32_t> item_row;
     items.reserve(sorted.size() / kItemLen + 16);
@@ -164,9 +164,33 @@ static void build_schedule(zk_ctx *ctx, schedule_t &S, std::vector<src_t> &src, 
         item_row.push_back(rk);
         i = j;
     }
-    for (size_t i = 0; i < sorted.size(); ++i) recs[i] = sorted[i].rec;
+    // Record layout: items are handed to threads in order (item i -> lane i mod 32 of a warp), so the records of every group of 32
+    // consecutive items are stored TRANSPOSED: record k of item i sits at group_base + 32 k + (i mod 32).  The k-th record loads of a
+    // warp then fall into one 384-byte run (12 wavefronts) instead of 32 runs 192 bytes apart (96): the gate kernels are bound by
+    // load/store wavefronts, and the record loads were more than half of them.  Groups are padded to their longest item.
+    {
+        size_t total = 0;
+        for (size_t g0 = 0; g0 < items.size(); g0 += kItemGroup) {
+            uint32_t longest = 0;
+            for (size_t i = g0; i < std::min(items.size(), g0 + kItemGroup); ++i) longest = std::max(longest, items[i].count_flags & 0xffffu);
+            total += (size_t) longest * kItemGroup;
+        }
+        ZK_REQUIRE(total < (1ull << 32), "schedule too large for 32-bit record offsets");
+        recs.assign(total, gate_rec_t{0u, 0u, 0u});
+        size_t base = 0;
+        for (size_t g0 = 0; g0 < items.size(); g0 += kItemGroup) {
+            uint32_t longest = 0;
+            for (size_t i = g0; i < std::min(items.size(), g0 + kItemGroup); ++i) {
+                const uint32_t cnt = items[i].count_flags & 0xffffu, first = items[i].begin;
+                longest = std::max(longest, cnt);
+                for (uint32_t k = 0; k < cnt; ++k) recs[base + (size_t) k * kItemGroup + (i - g0)] = sorted[first + k].rec;
+                items[i].begin = (uint32_t) (base + (i - g0));
+            }
+            base += (size_t) longest * kItemGroup;
+        }
+    }
     std::vector<src_t>().swap(sorted);
-    S.recs.ensure(recs.size() * sizeof(gate_rec_t));
+    S.recs.ensure(std::max<size_t>(1, recs.size()) * sizeof(gate_rec_t));
     rt::h2d(S.recs.p, recs.data(), recs.size() * sizeof(gate_rec_t), ctx->stream);
     rt::sync(ctx->stream);
     std::vector<gate_rec_t>().swap(recs);

@@ -1035,6 +1035,7 @@ __global__ void __launch_bounds__(kBlock) k_phi_table(fr_t *phi, const fr_t *rx,
 // dependence (Fr addition is exact), one thread per item.
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int kItemLen = 16;   // <= 16: the bound fr_lazy_reduce_upto16 relies on
+constexpr int kItemGroup = 32;  // items per record group: record k of item i at item.begin + kItemGroup * k (see build_schedule)
 
 struct gate_rec_t {   // 12 bytes
     uint32_t g;       // output gate -> index into beta_g
@@ -1044,7 +1045,7 @@ struct gate_rec_t {   // 12 bytes
 // phase-1 kinds: 0 = uni gate (no value factor), 1 = v operand in layer 0, 2 = v operand in layer l-1
 // phase-2 kinds: 0 = scale by V_u0, 1 = scale by V_u1
 struct item_t {       // 12 bytes
-    uint32_t begin;   // first record (level 0) or first partial (level >= 1)
+    uint32_t begin;   // level 0: position of the item's first record (its records are kItemGroup apart); level >= 1: first partial
     uint32_t dest;    // bit 31: 1 = final (index into out table selected by bit 30), 0 = partial slot
     uint32_t count_flags;  // bits 0-15: count;  bits 16-17: kind of the records (phase 2 only)
 };
@@ -1081,7 +1082,7 @@ __global__ void __launch_bounds__(kBlock) k_gate_items_p1(gate_args_t A) {
         fr_lazy_t acc;
         acc.clear();
         for (uint32_t k = 0; k < cnt; ++k) {
-            const gate_rec_t R = A.recs[I.begin + k];
+            const gate_rec_t R = A.recs[I.begin + kItemGroup * k];
             const fr_t bg = ld_fr_g(A.beta_g + R.g);
             const uint32_t kind = (R.meta >> 16) & 3u, sc = R.meta & 0x1ffu;
             if (kind == 0) acc.mac(bg, sc ? ld_fr_g(A.two_mul + sc) : fr_t::one());
@@ -1103,7 +1104,7 @@ __global__ void __launch_bounds__(kBlock) k_gate_items_p2(gate_args_t A) {
         fr_lazy_t acc;
         acc.clear();
         for (uint32_t k = 0; k < cnt; ++k) {
-            const gate_rec_t R = A.recs[I.begin + k];
+            const gate_rec_t R = A.recs[I.begin + kItemGroup * k];
             const fr_t bg = ld_fr_g(A.beta_g + R.g), bu = ld_fr_g(A.beta_u + R.x);
             const uint32_t sc = R.meta & 0x1ffu;
             if (sc) acc.mac(bg * bu, ld_fr_g(A.two_mul + sc));

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kBlock) k_eval_items(gate_args_t A) {
         fr_lazy_t acc;
         acc.clear();
         for (uint32_t k = 0; k < cnt; ++k) {
-            const gate_rec_t R = A.recs[I.begin + k];
+            const gate_rec_t R = A.recs[I.begin + kItemGroup * k];
             const uint32_t sc = R.meta & 0x1ffu;
             const fr_t x = ld_fr_g(((R.meta & kEvUPrev) ? A.val_prev : A.val0) + R.x);
             if (R.meta & kEvBin) {
