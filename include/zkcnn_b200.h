@@ -57,6 +57,9 @@ enum { ZK_PROF_FOLD = 0,   /* K1/K2 sumcheck round kernels                    */
        ZK_PROF_CLASSES };
 int zk_profile_enable(zk_ctx *ctx, int on);     /* also clears the counters */
 int zk_profile_get(zk_ctx *ctx, int cls, double *ms, uint64_t *launches, uint64_t *bytes);
+/* out[2]: mixed point additions performed by the MSM kernels since profiling was enabled: [0] small-multiples kernel (one per non-zero
+ * one-byte scalar), [1] bucket accumulation of the window kernel.  11 Fp multiplications each: the ALU-side work of the MSM class. */
+int zk_profile_msm_ops(zk_ctx *ctx, uint64_t *out);
 
 /* Kernel-selection thresholds of the sumcheck rounds (tests and experiments; defaults in parentheses):
  *   "thin_max_pairs"   (16384)  rounds with at most this many output pairs per table use k_round_quad_thin

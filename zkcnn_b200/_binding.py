@@ -89,6 +89,7 @@ class Lib:
         d.zk_ctx_launch_count.argtypes = [C.c_void_p]
         d.zk_profile_enable.argtypes = [C.c_void_p, C.c_int]
         d.zk_set_tunable.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        d.zk_profile_msm_ops.argtypes = [C.c_void_p, _u64p]
         d.zk_profile_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), _u64p, _u64p]
         d.zk_fr_vec_op.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint64]
         d.zk_beta_table.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, _u64p]

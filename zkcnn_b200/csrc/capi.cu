@@ -96,7 +96,24 @@ int zk_profile_enable(zk_ctx *ctx, int on) {
     rt::sync(ctx->stream);
     prof_resolve(ctx);
     for (int c = 0; c < ZK_PROF_CLASSES; ++c) { ctx->prof_ms[c] = 0; ctx->prof_launches[c] = 0; ctx->prof_bytes[c] = 0; }
+    if (ctx->prof_ops.p) { rt::dzero(ctx->prof_ops.p, 64, ctx->stream); rt::sync(ctx->stream); }
     ctx->prof_on = on != 0;
+    ZK_API_END
+}
+
+// point additions the MSM kernels performed since zk_profile_enable(ctx, 1): out[0] = mixed additions of the small-multiples kernel (one per
+// non-zero one-byte scalar), out[1] = mixed additions into buckets of the window kernel (its bucket reductions are not counted)
+int zk_profile_msm_ops(zk_ctx *ctx, uint64_t *out) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ctx && out, "bad arguments");
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
+    out[0] = out[1] = 0;
+    if (ctx->prof_ops.p) {
+        unsigned long long h[2];
+        d2h_staged(ctx, h, ctx->prof_ops.p, sizeof h);
+        out[0] = h[0];
+        out[1] = h[1];
+    }
     ZK_API_END
 }
 

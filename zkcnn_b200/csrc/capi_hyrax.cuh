@@ -97,6 +97,7 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         S.n_rows = n_rows; S.n_seg = n_seg; S.seg_len = seg_len;
         S.partial = H.msm_small.as<g1_jac_t>();
         S.rowinfo = H.msm_rowinfo.as<uint32_t>();
+        S.ops = ctx->prof_on ? prof_ops_counter(ctx) : nullptr;
         const uint64_t warps = (uint64_t) n_rows * n_seg;
         ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, alg_bytes, k_msm_small, dim3((uint32_t) ((warps + kSmallWarps - 1) / kSmallWarps)), dim3(kSmallWarps * 32), 0, S);
     } else {
@@ -116,6 +117,7 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     A.chunk = chunk;
     A.wide_only = small_path ? 1u : 0u;
     A.partial = H.msm_out.as<g1_jac_t>();
+    A.ops = ctx->prof_on ? prof_ops_counter(ctx) + 1 : nullptr;
     const bool waited = H.table_pending;   // a cross-stream wait sits between this launch and its predecessor: plain launch then
     msm_wait_table(ctx, H);
     // grid.x is limited to 2^31-1, grid.y to 65535: rows * chunks in x, windows in y

@@ -107,6 +107,15 @@ static inline zk::rt::event_t prof_event(zk_ctx *ctx) {
 #define ZK_KLAUNCH_PDL(ctx, cls, bytes, kernel, grid, block, smem, ...) ZK_KLAUNCH_C(ctx, cls, bytes, kernel, grid, block, smem, __VA_ARGS__)
 #endif
 
+// device counters of the MSM kernels under profiling: [0] mixed additions of k_msm_small, [1] bucket (mixed) additions of k_msm_window
+static unsigned long long *prof_ops_counter(zk_ctx *ctx) {
+    if (!ctx->prof_ops.p) {
+        ctx->prof_ops.ensure(64);
+        zk::rt::dzero(ctx->prof_ops.p, 64, ctx->stream);
+    }
+    return ctx->prof_ops.as<unsigned long long>();
+}
+
 static void prof_resolve(zk_ctx *ctx) {
     for (auto &r : ctx->prof_pending) {
         zk::rt::event_sync(r.b);

@@ -166,4 +166,5 @@ struct zk_ctx {
     std::vector<zk::rt::event_t> prof_pool;
     double prof_ms[ZK_PROF_CLASSES] = {};
     uint64_t prof_launches[ZK_PROF_CLASSES] = {}, prof_bytes[ZK_PROF_CLASSES] = {};
+    zk::rt::dbuf prof_ops;      // device counters of point additions (MSM kernels, profiling only)
 };

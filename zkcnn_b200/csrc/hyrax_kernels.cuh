@@ -144,6 +144,7 @@ struct msm_args_t {
     uint32_t chunk;          // entries per CTA (<= kMsmChunk)
     uint32_t wide_only;      // 1: scalars that fit one byte are skipped (the small-multiples path took them, msm_kernels.cuh)
     g1_jac_t *partial;       // [n_rows][n_chunks][kMsmWindows] window sums
+    unsigned long long *ops; // != nullptr (profiling): += bucket additions (mixed) of this CTA; the reduction's 2 x 255 full additions are added by the host
 };
 
 // grid = (n_rows * n_chunks, kMsmWindows)
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
     }
     __syncthreads();
     const uint32_t E = S->off[kMsmBuckets];
+    if (A.ops && t == 0 && E) atomicAdd(A.ops, (unsigned long long) E);
     if (E == 0) {
         if (t == 0) *dst = g1_jac_t::inf();
         return;

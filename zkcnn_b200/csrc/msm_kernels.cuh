@@ -68,6 +68,7 @@ struct msm_small_args_t {
     uint32_t n_rows, n_seg, seg_len;   // seg_len <= 65536
     g1_jac_t *partial;         // [n_rows][n_seg]
     uint32_t *rowinfo;         // widest magnitude (bytes) among the scalars that do NOT fit one byte, per row (atomicMax)
+    unsigned long long *ops;   // != nullptr (profiling): += mixed additions performed (one per non-zero one-byte scalar)
 };
 #ifndef ZK_SMALL_WARPS
 #define ZK_SMALL_WARPS 4
@@ -89,7 +90,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
     uint32_t head = 0, pending = 0, wide = 0;
     (void) q; (void) head; (void) pending;   // unused by the (uncompacted) emulator path
 
+    uint32_t n_adds = 0;
     auto consume = [&](uint32_t code) {
+        ++n_adds;
         const uint32_t j = code & 0xffffu, d = (code >> 16) & 0xffu, neg = code >> 24;
         const g1_aff_t *e = A.table + ((base + j) * kMultiples + (d - 1));
         g1_aff_t pt;
@@ -134,6 +137,14 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
     if (lane < pending) consume(q[(head + lane) & 63u]);
 #endif
     if (wide) atomicMax(A.rowinfo + row, wide);
+    if (A.ops) {
+#if ZK_ON_DEVICE
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, n_adds);
+        if (lane == 0 && tot) atomicAdd(A.ops, (unsigned long long) tot);
+#else
+        if (n_adds) atomicAdd(A.ops, (unsigned long long) n_adds);
+#endif
+    }
     // warp-level sum of the 32 accumulators
     g1_jac_t *my = sh + threadIdx.x;
     *my = acc;
