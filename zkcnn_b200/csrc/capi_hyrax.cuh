@@ -27,8 +27,12 @@ static void msm_configure() {
 
 // (re)build the fixed-base window table for a generator set given as host Jacobian points
 static void msm_prepare_table(zk_ctx *ctx, hyrax_t &H, const uint64_t *gens, uint32_t n_gens) {
-    const uint64_t h = fnv1a64(gens, (size_t) n_gens * sizeof(g1_jac_t)) ^ n_gens;
-    if (H.table_ready && H.gens_hash == h && H.n_gens == n_gens) return;   // same public generators as last time
+    // same public generators as last time?  The 64-bit hash only short-cuts the comparison: the generators are caller-supplied input, so a
+    // hit is confirmed byte for byte against the host copy kept from the last build (a collision must not reuse a stale table)
+    const size_t bytes = (size_t) n_gens * sizeof(g1_jac_t);
+    const uint64_t h = fnv1a64(gens, bytes) ^ n_gens;
+    if (H.table_ready && H.gens_hash == h && H.n_gens == n_gens && H.gens_host.size() == bytes && memcmp(H.gens_host.data(), gens, bytes) == 0) return;
+    H.gens_host.assign(reinterpret_cast<const uint8_t *>(gens), reinterpret_cast<const uint8_t *>(gens) + bytes);
     H.n_gens = n_gens;
     rt::dbuf &tmp = H.gens_jac;
     tmp.ensure((size_t) n_gens * sizeof(g1_jac_t));
@@ -417,8 +421,8 @@ int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scal
     using namespace zk;
     ZK_REQUIRE(ctx && base && scalars && out && n >= 1 && n < (1ull << 24), "bad arguments");
     rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
-    const uint64_t h = fnv1a64(base, sizeof(g1_jac_t));
-    if (!ctx->fb_ready || ctx->fb_hash != h) {   // comb[w][d-1] = d * 2^(8w) * base
+    if (!ctx->fb_ready || memcmp(ctx->fb_base, base, sizeof(g1_jac_t)) != 0) {   // comb[w][d-1] = d * 2^(8w) * base  (cached per base point, compared byte for byte)
+        memcpy(ctx->fb_base, base, sizeof(g1_jac_t));
         rt::dbuf jb, ab, win, scr;
         jb.ensure(sizeof(g1_jac_t)); ab.ensure(sizeof(g1_aff_t)); win.ensure((size_t) kMsmWindows * sizeof(g1_aff_t));
         scr.ensure((size_t) 2 * kMsmWindows * sizeof(fp_t));
@@ -430,7 +434,6 @@ int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scal
         ZK_KLAUNCH(ctx, k_msm_multiples_build, dim3((kMsmWindows * kMulThreadsPerGen + 127) / 128), dim3(128), 0, win.as<g1_aff_t>(),
                    ctx->fb_comb.as<g1_aff_t>(), (uint32_t) kMsmWindows);
         rt::sync(ctx->stream);
-        ctx->fb_hash = h;
         ctx->fb_ready = true;
     }
     rt::dbuf &dk = ctx->fb_k, &dout = ctx->fb_out;

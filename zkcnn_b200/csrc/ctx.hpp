@@ -85,6 +85,7 @@ struct hyrax_t {
     rt::dbuf mult;             // small-multiples table [n_gens][255] affine, entry = d * gens[j]  (msm_kernels.cuh)
     bool mult_ready = false;
     uint64_t gens_hash = 0;
+    std::vector<uint8_t> gens_host;   // the generator set the tables were built for (confirms a hash hit)
     rt::dbuf L, R, RZ, a, a_next, coef, scal;
     std::vector<fr_t> t;       // remaining opening point (lx)
     fr_t scale;
@@ -156,7 +157,7 @@ struct zk_ctx {
     zk::rt::dbuf wit_scratch;   // device witness generation: window maxima / layer ranges
     zk::rt::dbuf fb_k, fb_out;
     zk::rt::dbuf fb_comb;       // zk_g1_fixed_base_mul: comb table of the last base point
-    uint64_t fb_hash = 0;
+    uint64_t fb_base[ZK_G1_WORDS] = {};   // the base point the comb table was built for
     bool fb_ready = false;
 
     // optional per-kernel-class timing (zk_profile_*): CUDA events around every launch of the stream
