@@ -107,61 +107,62 @@ void neuralNetwork::create(prover &pr, bool only_compute) {
     val = pr.val.begin();
     two_mul = pr.C.two_mul.begin();
 
+    // the network as a flat list of stages, then one pass that emits the layers of each stage in order
+    struct Stage { enum Kind { CONV, POOL, FCON } kind; size_t a, b; };
+    vector<Stage> plan;
+    for (size_t i = 0; i < conv_section.size(); ++i) {
+        for (size_t j = 0; j < conv_section[i].size(); ++j) plan.push_back({Stage::CONV, i, j});
+        if (i < pool.size()) plan.push_back({Stage::POOL, i, 0});
+    }
+    for (size_t i = 0; i < full_conn.size(); ++i) plan.push_back({Stage::FCON, i, 0});
+
     i64 layer_id = 0;
     inputLayer(pr.C.circuit[layer_id++]);
-
     new_nx_in = pic_size_x;
     new_ny_in = pic_size_y;
-    for (size_t i = 0; i < conv_section.size(); ++i) {
-        auto &sec = conv_section[i];
-        for (size_t j = 0; j < sec.size(); ++j) {
-            auto &conv = sec[j];
-            refreshConvParam(new_nx_in, new_ny_in, conv);
-            pool_ty = i < pool.size() && j == sec.size() - 1 ? pool[i].ty : NONE;
-            x_bit = x_next_bit;
-            switch (conv.ty) {
-                case FFT:
-                    paddingLayer(pr.C.circuit[layer_id], layer_id, conv.weight_start_id);
-                    fftLayer(pr.C.circuit[layer_id], layer_id);
-                    dotProdLayer(pr.C.circuit[layer_id], layer_id);
-                    ifftLayer(pr.C.circuit[layer_id], layer_id);
-                    addBiasLayer(pr.C.circuit[layer_id], layer_id, conv.bias_start_id);
-                    break;
-                case NAIVE_FAST:
-                    naiveConvLayerFast(pr.C.circuit[layer_id], layer_id, conv.weight_start_id, conv.bias_start_id);
-                    break;
-                default:
-                    naiveConvLayerMul(pr.C.circuit[layer_id], layer_id, conv.weight_start_id);
-                    naiveConvLayerAdd(pr.C.circuit[layer_id], layer_id, conv.bias_start_id);
-            }
-            // quantisation scale of the next activations
-            x_next_bit = getNextBit(layer_id - 1);
-            scale_decisions_.push_back({(int) layer_id - 1, x_bit, w_bit, x_next_bit});
-            T = x_bit + w_bit - x_next_bit;
-            Q_MAX = Q + T;
-            if (pool_ty != MAX) reluActConvLayer(pr.C.circuit[layer_id], layer_id);
-        }
-        if (i >= pool.size()) continue;
-        calcSizeAfterPool(pool[i]);
-        switch (pool[i].ty) {
-            case AVG: avgPoolingLayer(pr.C.circuit[layer_id], layer_id); break;
-            case MAX: maxPoolingLayer(pr.C, layer_id, pool[i].dcmp_start_id, pool[i].max_start_id, pool[i].max_dcmp_start_id); break;
-            default: break;
-        }
-    }
-
-    pool_ty = NONE;
-    for (size_t i = 0; i < full_conn.size(); ++i) {
-        auto &fc = full_conn[i];
-        refreshFCParam(fc);
-        x_bit = x_next_bit;
-        fullyConnLayer(pr.C.circuit[layer_id], layer_id, fc.weight_start_id, fc.bias_start_id);
-        if (i == full_conn.size() - 1) break;
-        x_next_bit = getNextBit(layer_id - 1);
-        scale_decisions_.push_back({(int) layer_id - 1, x_bit, w_bit, x_next_bit});
+    // after a layer whose outputs get re-quantised: the scale of the next activations decides the widths of the decompositions that follow
+    auto rescale = [&](i64 produced_layer) {
+        x_next_bit = getNextBit((int) produced_layer);
+        scale_decisions_.push_back({(int) produced_layer, x_bit, w_bit, x_next_bit});
         T = x_bit + w_bit - x_next_bit;
         Q_MAX = Q + T;
-        reluActFconLayer(pr.C.circuit[layer_id], layer_id);
+    };
+    for (const Stage &st : plan) {
+        auto next = [&]() -> layer & { return pr.C.circuit[layer_id]; };
+        if (st.kind == Stage::CONV) {
+            const convKernel &conv = conv_section[st.a][st.b];
+            refreshConvParam(new_nx_in, new_ny_in, conv);
+            const bool last_of_section = st.b + 1 == conv_section[st.a].size();
+            pool_ty = st.a < pool.size() && last_of_section ? pool[st.a].ty : NONE;
+            x_bit = x_next_bit;
+            if (conv.ty == FFT) {
+                paddingLayer(next(), layer_id, conv.weight_start_id);
+                fftLayer(next(), layer_id);
+                dotProdLayer(next(), layer_id);
+                ifftLayer(next(), layer_id);
+                addBiasLayer(next(), layer_id, conv.bias_start_id);
+            } else if (conv.ty == NAIVE_FAST) {
+                naiveConvLayer(next(), layer_id, ConvEmit::FUSED, conv.weight_start_id, conv.bias_start_id);
+            } else {
+                naiveConvLayer(next(), layer_id, ConvEmit::PRODUCTS, conv.weight_start_id, -1);
+                naiveConvLayer(next(), layer_id, ConvEmit::SUMS, -1, conv.bias_start_id);
+            }
+            rescale(layer_id - 1);
+            if (pool_ty != MAX) reluLayer(next(), layer_id, nx_out * ny_out * channel_out * pic_parallel);   // (max pooling clamps at zero itself)
+        } else if (st.kind == Stage::POOL) {
+            calcSizeAfterPool(pool[st.a]);
+            if (pool[st.a].ty == AVG) avgPoolingLayer(next(), layer_id);
+            else if (pool[st.a].ty == MAX) maxPoolingLayer(pr.C, layer_id, pool[st.a].dcmp_start_id, pool[st.a].max_start_id, pool[st.a].max_dcmp_start_id);
+        } else {
+            const fconKernel &fc = full_conn[st.a];
+            pool_ty = NONE;
+            refreshFCParam(fc);
+            x_bit = x_next_bit;
+            fullyConnLayer(next(), layer_id, fc.weight_start_id, fc.bias_start_id);
+            if (st.a + 1 == full_conn.size()) break;
+            rescale(layer_id - 1);
+            reluLayer(next(), layer_id, channel_out * pic_parallel);
+        }
     }
     if (SIZE != layer_id) throw std::logic_error("neuralNetwork::create: layer count mismatch");
 
@@ -259,188 +260,134 @@ void neuralNetwork::addBiasLayer(layer &circuit, i64 &layer_id, i64 first_bias_i
     ++layer_id;
 }
 
-void neuralNetwork::naiveConvLayerFast(layer &circuit, i64 &layer_id, i64 first_conv_id, i64 first_bias_id) {   // :254-282
-    initLayer(circuit, nx_out * ny_out * channel_out * pic_parallel, layerType::NCONV);
-    circuit.need_phase2 = true;
+// Direct ("naive") convolution (:254-342).  The reference has three builders over the same loop nest; here one walk over the
+// (picture, output channel, input channel, output position) grid and its in-bounds kernel taps feeds the three gate shapes:
+//   FUSED     one layer: out[g] = bias + sum over taps of x * w                                   (NCONV)
+//   PRODUCTS  first of two layers: one gate per tap, out[k] = x * w, k counting the taps           (NCONV_MUL)
+//   SUMS      second of two layers: out[g] = bias + the products of g's taps, taken in order       (NCONV_ADD)
+template <class PerOutput, class PerTap> void neuralNetwork::walkConvolution(PerOutput per_output, PerTap per_tap) {
     const i64 lo = -padding, hx = nx_in + padding, hy = ny_in + padding, stride = 1 << log_stride;
-    const u8 l_code = 2 * (u8) (layer_id > 1);   // u from the previous layer (or the image), v = weight in layer 0
-    circuit.bin_gates.reserve((size_t) pic_parallel * channel_out * channel_in * nx_out * ny_out * m * m);
     for (i64 p = 0; p < pic_parallel; ++p)
         for (i64 co = 0; co < channel_out; ++co)
             for (i64 ci = 0; ci < channel_in; ++ci)
                 for (i64 x = lo; x + m <= hx; x += stride)
                     for (i64 y = lo; y + m <= hy; y += stride) {
                         const i64 g = tesIdx(p, co, (x - lo) >> log_stride, (y - lo) >> log_stride, channel_out, nx_out, ny_out);
-                        if (ci == 0 && ~first_bias_id) circuit.uni_gates.emplace_back(g, first_bias_id + co, 0, 0);
-                        for (i64 tx = x; tx < x + m; ++tx)
-                            for (i64 ty = y; ty < y + m; ++ty) {
-                                if (!inside(tx, ty, nx_in, ny_in)) continue;
-                                i64 u = tesIdx(p, ci, tx, ty, channel_in, nx_in, ny_in);
-                                i64 v = first_conv_id + tesIdx(co, ci, tx - x, ty - y, channel_in, m, m);
-                                circuit.bin_gates.emplace_back(g, u, v, 0, l_code);
-                            }
-                    }
-    readConvWeight(first_conv_id);
-    if (~first_bias_id) readBias(first_bias_id);
-    calcNormalLayer(circuit, layer_id);
-    ++layer_id;
-}
-
-void neuralNetwork::naiveConvLayerMul(layer &circuit, i64 &layer_id, i64 first_conv_id) {   // :284-309
-    const i64 lo = -padding, hx = nx_in + padding, hy = ny_in + padding, stride = 1 << log_stride;
-    const u8 l_code = 2 * (u8) (layer_id > 1);
-    i64 g = 0;
-    for (i64 p = 0; p < pic_parallel; ++p)
-        for (i64 co = 0; co < channel_out; ++co)
-            for (i64 ci = 0; ci < channel_in; ++ci)
-                for (i64 x = lo; x + m <= hx; x += stride)
-                    for (i64 y = lo; y + m <= hy; y += stride)
-                        for (i64 tx = x; tx < x + m; ++tx)
-                            for (i64 ty = y; ty < y + m; ++ty) {
-                                if (!inside(tx, ty, nx_in, ny_in)) continue;
-                                i64 u = tesIdx(p, ci, tx, ty, channel_in, nx_in, ny_in);
-                                i64 v = first_conv_id + tesIdx(co, ci, tx - x, ty - y, channel_in, m, m);
-                                circuit.bin_gates.emplace_back(g++, u, v, 0, l_code);
-                            }
-    initLayer(circuit, g, layerType::NCONV_MUL);
-    circuit.need_phase2 = true;
-    readConvWeight(first_conv_id);
-    calcNormalLayer(circuit, layer_id);
-    ++layer_id;
-}
-
-void neuralNetwork::naiveConvLayerAdd(layer &circuit, i64 &layer_id, i64 first_bias_id) {   // :311-342
-    initLayer(circuit, nx_out * ny_out * channel_out * pic_parallel, layerType::NCONV_ADD);
-    const i64 lo = -padding, hx = nx_in + padding, hy = ny_in + padding, stride = 1 << log_stride;
-    i64 u = 0;
-    for (i64 p = 0; p < pic_parallel; ++p)
-        for (i64 co = 0; co < channel_out; ++co)
-            for (i64 ci = 0; ci < channel_in; ++ci)
-                for (i64 x = lo; x + m <= hx; x += stride)
-                    for (i64 y = lo; y + m <= hy; y += stride) {
-                        const i64 g = tesIdx(p, co, (x - lo) >> log_stride, (y - lo) >> log_stride, channel_out, nx_out, ny_out);
-                        if (ci == 0 && ~first_bias_id) circuit.uni_gates.emplace_back(g, first_bias_id + co, 0, 0);
+                        per_output(g, co, ci);
                         for (i64 tx = x; tx < x + m; ++tx)
                             for (i64 ty = y; ty < y + m; ++ty)
-                                if (inside(tx, ty, nx_in, ny_in)) circuit.uni_gates.emplace_back(g, u++, layer_id - 1, 0);
+                                if (inside(tx, ty, nx_in, ny_in))
+                                    per_tap(g, tesIdx(p, ci, tx, ty, channel_in, nx_in, ny_in), tesIdx(co, ci, tx - x, ty - y, channel_in, m, m));
                     }
-    if (~first_bias_id) readBias(first_bias_id);
+}
+
+void neuralNetwork::naiveConvLayer(layer &circuit, i64 &layer_id, ConvEmit mode, i64 first_conv_id, i64 first_bias_id) {
+    const u8 prev_code = 2 * (u8) (layer_id > 1);   // u from the previous layer (or the picture), v = weight in layer 0
+    const bool with_bias = mode != ConvEmit::PRODUCTS && ~first_bias_id;
+    i64 counter = 0;                                  // PRODUCTS: next output gate; SUMS: next product of the previous layer
+    if (mode != ConvEmit::PRODUCTS) initLayer(circuit, nx_out * ny_out * channel_out * pic_parallel, mode == ConvEmit::FUSED ? layerType::NCONV : layerType::NCONV_ADD);
+    if (mode == ConvEmit::FUSED) circuit.bin_gates.reserve((size_t) pic_parallel * channel_out * channel_in * nx_out * ny_out * m * m);
+    walkConvolution(
+        [&](i64 g, i64 co, i64 ci) { if (with_bias && ci == 0) circuit.uni_gates.emplace_back(g, first_bias_id + co, 0, 0); },
+        [&](i64 g, i64 u, i64 w_idx) {
+            switch (mode) {
+                case ConvEmit::FUSED: circuit.bin_gates.emplace_back(g, u, first_conv_id + w_idx, 0, prev_code); break;
+                case ConvEmit::PRODUCTS: circuit.bin_gates.emplace_back(counter++, u, first_conv_id + w_idx, 0, prev_code); break;
+                case ConvEmit::SUMS: circuit.uni_gates.emplace_back(g, counter++, layer_id - 1, 0); break;
+            }
+        });
+    if (mode == ConvEmit::PRODUCTS) initLayer(circuit, counter, layerType::NCONV_MUL);
+    if (mode != ConvEmit::SUMS) { circuit.need_phase2 = true; readConvWeight(first_conv_id); }
+    if (with_bias) readBias(first_bias_id);
     calcNormalLayer(circuit, layer_id);
     ++layer_id;
 }
 
-// ReLU after a convolution (:344-395).  Rows: [0, B) rescaled positive part, [B, 2B) "value == signed bit recomposition",
-// [2B, 2B + B*Q_MAX) "every witness bit is a bit"; B = number of activations.
-void neuralNetwork::reluActConvLayer(layer &circuit, i64 &layer_id) {
-    const i64 block_len = nx_out * ny_out * channel_out * pic_parallel;
-    const i64 dcmp_cnt = block_len * Q_MAX;
-    const i64 first_dcmp_id = val[0].size();
-    val[0].resize(val[0].size() + dcmp_cnt);
-    total_relu_in_size += dcmp_cnt;
-    initLayer(circuit, block_len * (2 + Q_MAX), layerType::RELU);
+// ReLU (:344-439; the reference has one copy after convolutions and one after fully connected layers -- they differ only in how they
+// count the activations).  For each of the B activations x of the previous layer, Q_MAX witness bits in val[0]: a sign bit and the
+// magnitude bits, most significant first.  Rows of the layer:
+//   [0, B)             the re-quantised positive part: (1 - sign) * (top Q-1 magnitude bits recomposed)
+//   [B, 2B)            x + sign-corrected recomposition of all magnitude bits == 0            (checked to be zero: zero_start_id = B)
+//   [2B, 2B + B Q_MAX) b * b - b == 0 for every witness bit
+void neuralNetwork::reluLayer(layer &circuit, i64 &layer_id, i64 B) {
+    const i64 n_bits = B * Q_MAX;
+    const i64 first_bit = val[0].size();
+    val[0].resize(val[0].size() + n_bits);
+    total_relu_in_size += n_bits;
+    initLayer(circuit, B * (2 + Q_MAX), layerType::RELU);
     circuit.need_phase2 = true;
-    circuit.zero_start_id = block_len;
+    circuit.zero_start_id = B;
+    const u8 prev_code = 2 * (u8) (layer_id > 1);   // binGate::l of "u in the previous layer, v in layer 0"
+    auto bits_of = [&](i64 act) { return first_bit + act * Q_MAX; };
 
-    for (i64 g = 0; g < block_len; ++g) {
-        const i64 sign_u = first_dcmp_id + g * Q_MAX;
+    for (i64 act = 0; act < B; ++act) {              // row act: sum_s 2^(Q-1-s) bit_s  -  sign * the same
+        const i64 sign = bits_of(act);
         for (i64 s = 1; s < Q; ++s) {
-            circuit.uni_gates.emplace_back(g, sign_u + s, 0, Q - 1 - s);
-            circuit.bin_gates.emplace_back(g, sign_u, sign_u + s, Q - s + Q_BIT_SIZE, 0);
+            circuit.uni_gates.emplace_back(act, sign + s, 0, Q - 1 - s);
+            circuit.bin_gates.emplace_back(act, sign, sign + s, Q - s + Q_BIT_SIZE, 0);
         }
     }
-    const i64 lo = -padding, hx = nx_in + padding, hy = ny_in + padding, stride = 1 << log_stride;
-    const u8 l_code = 2 * (u8) (layer_id > 1);
-    for (i64 p = 0; p < pic_parallel; ++p)
-        for (i64 co = 0; co < channel_out; ++co)
-            for (i64 x = lo; x + m <= hx; x += stride)
-                for (i64 y = lo; y + m <= hy; y += stride) {
-                    const i64 u = tesIdx(p, co, (x - lo) >> log_stride, (y - lo) >> log_stride, channel_out, nx_out, ny_out);
-                    const i64 g = block_len + u, sign_v = first_dcmp_id + u * Q_MAX;
-                    circuit.uni_gates.emplace_back(g, u, layer_id - 1, Q_BIT_SIZE + 1);
-                    circuit.bin_gates.emplace_back(g, u, sign_v, 1, l_code);
-                    prepareSignBit(layer_id - 1, u, sign_v);
-                    for (i64 s = 1; s < Q_MAX; ++s) {
-                        circuit.uni_gates.emplace_back(g, sign_v + s, 0, Q_MAX - s - 1);
-                        prepareDecmpBit(layer_id - 1, u, sign_v + s, Q_MAX - s - 1);
-                    }
-                }
-    for (i64 g = block_len << 1; g < (block_len << 1) + block_len * Q_MAX; ++g) {
-        const i64 u = first_dcmp_id + g - (block_len << 1);
-        circuit.bin_gates.emplace_back(g, u, u, 0, 0);
-        circuit.uni_gates.emplace_back(g, u, 0, Q_BIT_SIZE + 1);
-    }
-    calcNormalLayer(circuit, layer_id);
-    ++layer_id;
-}
-
-void neuralNetwork::reluActFconLayer(layer &circuit, i64 &layer_id) {   // :397-439
-    const i64 block_len = channel_out * pic_parallel;
-    initLayer(circuit, block_len * (2 + Q_MAX), layerType::RELU);
-    circuit.zero_start_id = block_len;
-    circuit.need_phase2 = true;
-    const i64 dcmp_cnt = block_len * Q_MAX;
-    const i64 first_dcmp_id = val[0].size();
-    val[0].resize(val[0].size() + dcmp_cnt);
-    total_relu_in_size += dcmp_cnt;
-
-    for (i64 g = 0; g < block_len; ++g) {
-        const i64 sign_u = first_dcmp_id + g * Q_MAX;
-        for (i64 s = 1; s < Q; ++s) {
-            circuit.uni_gates.emplace_back(g, sign_u + s, 0, Q - s - 1);
-            circuit.bin_gates.emplace_back(g, sign_u, sign_u + s, Q - s + Q_BIT_SIZE, 0);
-        }
-    }
-    const u8 l_code = 2 * (u8) (layer_id > 1);
-    for (i64 u = 0; u < block_len; ++u) {
-        const i64 g = block_len + u, sign_v = first_dcmp_id + u * Q_MAX;
-        circuit.uni_gates.emplace_back(g, u, layer_id - 1, Q_BIT_SIZE + 1);
-        circuit.bin_gates.emplace_back(g, u, sign_v, 1, l_code);
-        prepareSignBit(layer_id - 1, u, sign_v);
+    for (i64 act = 0; act < B; ++act) {              // row B + act: -x + 2 sign x + sum_s 2^(Q_MAX-1-s) bit_s, and the witnesses themselves
+        const i64 row = B + act, sign = bits_of(act);
+        circuit.uni_gates.emplace_back(row, act, layer_id - 1, Q_BIT_SIZE + 1);
+        circuit.bin_gates.emplace_back(row, act, sign, 1, prev_code);
+        prepareSignBit(layer_id - 1, act, sign);
         for (i64 s = 1; s < Q_MAX; ++s) {
-            circuit.uni_gates.emplace_back(g, sign_v + s, 0, Q_MAX - s - 1);
-            prepareDecmpBit(layer_id - 1, u, sign_v + s, Q_MAX - s - 1);
+            circuit.uni_gates.emplace_back(row, sign + s, 0, Q_MAX - s - 1);
+            prepareDecmpBit(layer_id - 1, act, sign + s, Q_MAX - s - 1);
         }
     }
-    for (i64 g = block_len << 1; g < (block_len << 1) + block_len * Q_MAX; ++g) {
-        const i64 u = first_dcmp_id + g - (block_len << 1);
-        circuit.bin_gates.emplace_back(g, u, u, 0, 0);
-        circuit.uni_gates.emplace_back(g, u, 0, Q_BIT_SIZE + 1);
+    for (i64 k = 0; k < n_bits; ++k) {               // row 2B + k: bit^2 - bit
+        const i64 row = 2 * B + k, bit = first_bit + k;
+        circuit.bin_gates.emplace_back(row, bit, bit, 0, 0);
+        circuit.uni_gates.emplace_back(row, bit, 0, Q_BIT_SIZE + 1);
     }
     calcNormalLayer(circuit, layer_id);
     ++layer_id;
 }
 
-void neuralNetwork::avgPoolingLayer(layer &circuit, i64 &layer_id) {   // :441-484
-    const i64 zero_start_id = new_nx_in * new_ny_in * channel_out * pic_parallel;
-    const u8 dpool_bl = pool_bl << 1;
-    initLayer(circuit, zero_start_id + getPoolDecmpSize(), layerType::AVG_POOL);
-    F::inv(circuit.scale, F((i64) sqr(pool_sz)));
-    circuit.zero_start_id = zero_start_id;
-    circuit.need_phase2 = true;
-    const i64 first_gate_id = val[0].size();
-    val[0].resize(val[0].size() + zero_start_id * dpool_bl);
-    total_ave_in_size += zero_start_id * dpool_bl;
-
+// every pooling window of the current tensor in the reference's order (picture, channel, window row, window column): per_elem for each of
+// its pool_sz x pool_sz elements (cell index, offset inside the window, index of the element in the previous layer), then per_cell once
+template <class PerElem, class PerCell> void neuralNetwork::walkPooling(PerElem per_elem, PerCell per_cell) {
     for (i64 p = 0; p < pic_parallel; ++p)
         for (i64 co = 0; co < channel_out; ++co)
             for (i64 x = 0; x + pool_sz <= nx_out; x += pool_stride)
                 for (i64 y = 0; y + pool_sz <= ny_out; y += pool_stride) {
-                    const i64 g = tesIdx(p, co, x >> pool_stride_bl, y >> pool_stride_bl, channel_out, new_nx_in, new_ny_in);
-                    F data = F_ZERO;
-                    for (i64 tx = x; tx < x + pool_sz; ++tx)
-                        for (i64 ty = y; ty < y + pool_sz; ++ty) {
-                            i64 u = tesIdx(p, co, tx, ty, channel_out, nx_out, ny_out);
-                            circuit.uni_gates.emplace_back(g, u, layer_id - 1, 0);
-                            data = data + val[layer_id - 1][u];
-                        }
-                    for (i64 rm_i = 0; rm_i < dpool_bl; ++rm_i) {
-                        const i64 idx = matIdx(g, rm_i, dpool_bl), u = first_gate_id + idx, g_bit = zero_start_id + idx;
-                        circuit.uni_gates.emplace_back(g, u, 0, dpool_bl - rm_i + Q_BIT_SIZE);
-                        prepareFieldBit(data, u, dpool_bl - rm_i - 1);
-                        circuit.bin_gates.emplace_back(g_bit, u, u, 0, 0);
-                        circuit.uni_gates.emplace_back(g_bit, u, 0, Q_BIT_SIZE + 1);
-                    }
+                    const i64 cell = tesIdx(p, co, x >> pool_stride_bl, y >> pool_stride_bl, channel_out, new_nx_in, new_ny_in);
+                    for (i64 dx = 0; dx < pool_sz; ++dx)
+                        for (i64 dy = 0; dy < pool_sz; ++dy) per_elem(cell, dx, dy, tesIdx(p, co, x + dx, y + dy, channel_out, nx_out, ny_out));
+                    per_cell(cell);
                 }
+}
+
+// Average pooling (:441-484): cell = (window sum - its low 2 log2(pool_sz) bits) / pool_sz^2, the dropped bits being witnesses in val[0]
+// that a second block of rows proves to be bits.
+void neuralNetwork::avgPoolingLayer(layer &circuit, i64 &layer_id) {
+    const i64 n_cells = new_nx_in * new_ny_in * channel_out * pic_parallel;
+    const u8 n_low = pool_bl << 1;
+    initLayer(circuit, n_cells + getPoolDecmpSize(), layerType::AVG_POOL);
+    F::inv(circuit.scale, F((i64) sqr(pool_sz)));
+    circuit.zero_start_id = n_cells;
+    circuit.need_phase2 = true;
+    const i64 first_bit = val[0].size();
+    val[0].resize(val[0].size() + n_cells * n_low);
+    total_ave_in_size += n_cells * n_low;
+    F window_sum = F_ZERO;
+    walkPooling(
+        [&](i64 cell, i64, i64, i64 u) {
+            circuit.uni_gates.emplace_back(cell, u, layer_id - 1, 0);
+            window_sum = window_sum + val[layer_id - 1][u];
+        },
+        [&](i64 cell) {
+            for (i64 k = 0; k < n_low; ++k) {
+                const i64 slot = matIdx(cell, k, n_low), bit = first_bit + slot, row = n_cells + slot;
+                circuit.uni_gates.emplace_back(cell, bit, 0, n_low - k + Q_BIT_SIZE);
+                prepareFieldBit(window_sum, bit, n_low - k - 1);
+                circuit.bin_gates.emplace_back(row, bit, bit, 0, 0);
+                circuit.uni_gates.emplace_back(row, bit, 0, Q_BIT_SIZE + 1);
+            }
+            window_sum = F_ZERO;
+        });
     calcNormalLayer(circuit, layer_id);
     ++layer_id;
 }
@@ -468,21 +415,14 @@ void neuralNetwork::maxPoolingLayer(layeredCircuit &C, i64 &layer_id, i64 first_
         layer &circuit = C.circuit[layer_id];
         initLayer(circuit, tot_new_size * pool_sz_sqr + tot_new_size, layerType::MAX_POOL);
         circuit.zero_start_id = tot_new_size * pool_sz_sqr;
-        for (i64 p = 0; p < pic_parallel; ++p)
-            for (i64 co = 0; co < channel_out; ++co)
-                for (i64 x = 0; x + pool_sz <= nx_out; x += pool_stride)
-                    for (i64 y = 0; y + pool_sz <= ny_out; y += pool_stride) {
-                        const i64 cell = tesIdx(p, co, x >> pool_stride_bl, y >> pool_stride_bl, channel_out, new_nx_in, new_ny_in);
-                        const i64 u_max = first_max_id + cell;
-                        for (i64 tx = x; tx < x + pool_sz; ++tx)
-                            for (i64 ty = y; ty < y + pool_sz; ++ty) {
-                                const i64 g = cubIdx(cell, tx - x, ty - y, pool_sz, pool_sz);
-                                const i64 u_g = tesIdx(p, co, tx, ty, channel_out, nx_out, ny_out);
-                                circuit.uni_gates.emplace_back(g, u_max, 0, 0);
-                                circuit.uni_gates.emplace_back(g, u_g, layer_id - 1, Q_BIT_SIZE + 1);
-                                prepareMax(layer_id - 1, u_g, u_max);
-                            }
-                    }
+        walkPooling(
+            [&](i64 cell, i64 dx, i64 dy, i64 u_g) {
+                const i64 g = cubIdx(cell, dx, dy, pool_sz, pool_sz), u_max = first_max_id + cell;
+                circuit.uni_gates.emplace_back(g, u_max, 0, 0);
+                circuit.uni_gates.emplace_back(g, u_g, layer_id - 1, Q_BIT_SIZE + 1);
+                prepareMax(layer_id - 1, u_g, u_max);
+            },
+            [](i64) {});
         for (i64 i_new = 0; i_new < tot_new_size; ++i_new) {
             const i64 g_new = circuit.zero_start_id + i_new, u_new = first_max_id + i_new;
             circuit.uni_gates.emplace_back(g_new, u_new, 0, Q_BIT_SIZE + 1);

@@ -3,8 +3,8 @@
 //
 // This is the caller-side data format of the hot path, written from scratch but producing,
 // gate for gate and value for value, what the reference's neuralNetwork::create does (src/neuralNetwork.cpp:60-142 and
-// the layer builders :144-649) -- tests/test_circuit_builder.py checks per-layer hashes of gates, ori_id and values
-// against the compiled reference.  Public interface = the reference's (src/neuralNetwork.hpp:57-66, src/models.hpp).
+// the layer builders :144-649) -- tests/_cases.py: prove_and_compare checks per-layer hashes of gates, ori_id and values
+// against dumps of the compiled reference (tests/golden/*.circuit.txt), up to full-size vgg11 and vgg16.  Public interface = the reference's (src/neuralNetwork.hpp:57-66, src/models.hpp).
 #pragma once
 #include "prover.hpp"
 #include <functional>
@@ -97,11 +97,11 @@ protected:
     void dotProdLayer(layer &circuit, i64 &layer_id);
     void ifftLayer(layer &circuit, i64 &layer_id);
     void addBiasLayer(layer &circuit, i64 &layer_id, i64 first_bias_id);
-    void naiveConvLayerFast(layer &circuit, i64 &layer_id, i64 first_conv_id, i64 first_bias_id);
-    void naiveConvLayerMul(layer &circuit, i64 &layer_id, i64 first_conv_id);
-    void naiveConvLayerAdd(layer &circuit, i64 &layer_id, i64 first_bias_id);
-    void reluActConvLayer(layer &circuit, i64 &layer_id);
-    void reluActFconLayer(layer &circuit, i64 &layer_id);
+    enum class ConvEmit { FUSED, PRODUCTS, SUMS };
+    template <class PerOutput, class PerTap> void walkConvolution(PerOutput per_output, PerTap per_tap);
+    void naiveConvLayer(layer &circuit, i64 &layer_id, ConvEmit mode, i64 first_conv_id, i64 first_bias_id);
+    void reluLayer(layer &circuit, i64 &layer_id, i64 n_activations);
+    template <class PerElem, class PerCell> void walkPooling(PerElem per_elem, PerCell per_cell);
     void avgPoolingLayer(layer &circuit, i64 &layer_id);
     void maxPoolingLayer(layeredCircuit &C, i64 &layer_id, i64 first_dcmp_id, i64 first_max_id, i64 first_max_dcmp_id);
     void fullyConnLayer(layer &circuit, i64 &layer_id, i64 first_fc_id, i64 first_bias_id);
