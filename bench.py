@@ -401,8 +401,8 @@ def run_ours(args):
             p = prof[name]
             ach = p["bytes"] / 1e9 / (p["ms"] / 1e3) if p["ms"] > 0 else 0.0
             r = {"bound": "alu" if name == "msm" else "latency" if name in ("fold_small", "other") else "hbm", "kernel_class": name, "achieved": round(ach, 2), "peak": peak,
-                 "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu.get("class_" + name), "launches": p["launches"],
-                 "device_ms": round(p["ms"], 3), "algorithmic_bytes": p["bytes"]}
+                 "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu.get("class_" + name), "traffic_unit": "DRAM bytes of ONE proof (ncu), compare with algorithmic_bytes_per_proof",
+                 "launches": p["launches"], "device_ms": round(p["ms"], 3), "algorithmic_bytes": p["bytes"], "algorithmic_bytes_per_proof": p["bytes"] // max(1, args.steps)}
             if name == "msm" and "fp_mul" in micro and p["ms"] > 0:
                 # ALU view of the MSM class: measured mixed additions (11 Fp multiplications each) of the commitment and bucket kernels per second
                 # against the Fp-multiplier rate of this GPU measured in this run; table builds and bucket reductions are left out of the count
