@@ -180,13 +180,16 @@ def run_ours(args):
     model, pics = args.model, args.pics
     if args.inflight > 0:
         M = args.inflight
-    else:   # up to six provers per GPU, bounded by the host: two cores and ~8 GB of RAM (circuit + witness of vgg11, more with several pictures) per prover
+    else:   # up to six provers per GPU, bounded by the host's memory: ~8 GB of RAM (circuit + witness of vgg11, more with several pictures) per prover
         try:
             avail_gb = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) / 1e6
         except Exception:
             avail_gb = 64
         per_gb = 1 if model == "lenet" else 8 * (1 if pics == 1 else 1.5 * pics) * (1.5 if model == "vgg16" else 1)
-        M = max(1, min(6, (os.cpu_count() or 2) // (2 * world), int(avail_gb * 0.5 / (world * per_gb))))
+        M = max(1, min(6, int(avail_gb * 0.5 / (world * per_gb))))
+    # more prover threads than cores to spin on: the waits for the GPU sleep instead (rt.hpp: ZK_BLOCKING_SYNC); read when the library first waits
+    if "ZK_BLOCKING_SYNC" not in os.environ and M * world * 2 > (os.cpu_count() or 2):
+        os.environ["ZK_BLOCKING_SYNC"] = "1"
     config = NETWORKS.get(model, args.network)
     lib = zkcnn_b200.load()
     # M independent provers per GPU (own zk_ctx, own stream, own witness): M proofs in flight.  Session 0 of rank 0 proves the golden image
@@ -422,7 +425,7 @@ def run_ours(args):
                                     " (BASELINE config 5: batched pictures, FFT-convolution path)" if pics > 1 else "")),
                        "arithmetic": "exact modular integer arithmetic on 32-bit limbs: BLS12-381 Fr (255-bit) and Fp (381-bit) in Montgomery form",
                        "network": config, "pictures_per_proof": pics, "input_layer": st0["input_size"], "layers": st0["n_layers"], "generators": "non-degenerate (G * challenge)",
-                       "proofs_in_flight_per_gpu": M,
+                       "proofs_in_flight_per_gpu": M, "host_wait": "sleeping (blocking-sync events)" if os.environ.get("ZK_BLOCKING_SYNC", "0") not in ("", "0") else "spinning (cudaStreamSynchronize)",
                        "rounds": "one device call per sumcheck round" if args.round_by_round else "one device call per sumcheck phase (challenges of a phase are drawn before its rounds, as in src/verifier.cpp:156-160)",
                        "l2": "tables larger than L2 (2^24 x 32 B witness, 537 MB)", "parallelism": f"one proof stream per GPU x{world} ({M} provers in flight each, distinct pictures), final all-gather of all K proofs of every rank",
                        "timer": "host clock around synchronous API calls, barrier + cuda synchronize on both sides; value and e2e un-instrumented; per-kernel-class device "

@@ -73,7 +73,8 @@ int zk_profile_msm_ops(zk_ctx *ctx, uint64_t *out);
  *   "cubic_tma"        (1)      DOT_PROD fold rounds on tables of at least tma_min_entries use k_round_cubic_tma
  *   "cubic_max_grid"   (none)   cap on the CTAs of a K2 launch (tests: several iterations per thread on small tables)
  *   "cubic_factored_min_iters" (4) k_round_cubic switches to the factored form from this many output pairs per thread
- *   "msm_few_rows_chunk" (2048) entries per CTA of the bucket kernel for MSMs of at most 8 rows */
+ *   "msm_few_rows_chunk" (2048) (generator, window) entries per work item of the bucket kernels for MSMs of at most 8 rows
+ *   "msm_split" (1)      MSMs of at most 8 rows as accumulate / merge / reduce launches; 0: the self-contained bucket kernel */
 int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value);
 
 /* page-lock / unlock a caller-owned host buffer so that uploads from it are direct DMA (cudaHostRegister) */

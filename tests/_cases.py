@@ -321,8 +321,8 @@ def device_witness_case(lib, hostlib, model, network, pic_cnt, values, n_pix, go
 
 
 def case_msm_many_rows(lib, n=64, rows=20, seed=808):
-    """>= 16 rows over one generator set: the small-multiples path (k_msm_small) with the bucket kernel in wide-only mode;
-    rows mix zero / one-byte / wide / sign-boundary scalars, one row is all zero, one base is the point at infinity"""
+    """>= 16 rows over one generator set: the small-multiples path (k_msm_small, byte levels) with the bucket kernel in wide-only mode;
+    rows mix zero / one-byte / 2-4 byte / wide / sign-boundary scalars, one row is all zero, one base is the point at infinity"""
     rng = O.SplitMix64(seed)
     pts = [O.g1_mul(O.G1_GEN, rng.fr()) for _ in range(n)]
     pts[3] = None
@@ -332,10 +332,43 @@ def case_msm_many_rows(lib, n=64, rows=20, seed=808):
     ks[2 * n] , ks[2 * n + 1], ks[2 * n + 2], ks[2 * n + 3] = 255, O.R - 255, 256, O.R - 256   # both sides of the one-byte boundary
     ks[3 * n + 5] = (O.R - 1) // 2
     ks[3 * n + 6] = (O.R + 1) // 2
+    # the byte levels of the small-multiples path (2, 3, 4 bytes, both signs, zero middle bytes) and the first width beyond it
+    ks[4 * n + 1:4 * n + 9] = [65536 + 5, O.R - (1 << 24) - 3, (1 << 32) - 1, O.R - ((1 << 32) - 1), 1 << 32, O.R - (1 << 32), 0x01000000, 0x00ff00]
+    ks[6 * n:7 * n] = [(rng.next() % (1 << 17) - (1 << 16)) % O.R for _ in range(n)]          # a row of 2-3 byte scalars only
     with Context(lib) as ctx:
         got = g1_from_words(ctx.msm(g1_to_words(pts), fr_to_words(ks), rows))
     assert got == [O.g1_mul_vec(pts, ks[i * n:(i + 1) * n]) for i in range(rows)]
     assert got[0] is None
+
+
+def case_msm_bucket_shapes(lib, n=150, seed=828):
+    """the bucket kernel's work items: several chunks of generators per row (n > 128), uniform full-width scalars (every window live),
+    a row whose scalars are all equal (every entry of a window in one bucket: runs shared by many threads), a many-row MSM with one
+    fully wide row, one row with a single wide scalar and the rest one-byte"""
+    rng = O.SplitMix64(seed)
+    pts = [O.g1_mul(O.G1_GEN, rng.fr()) for _ in range(n)]
+    pts[n - 1] = None
+    same = rng.fr()
+    ks = rand_fr(rng, n, "uniform") + [same] * n
+    with Context(lib) as ctx:
+        want0 = O.g1_mul_vec(pts, ks[:n])
+        total = None
+        for p_ in pts:
+            total = O.g1_add(total, p_)
+        want1 = O.g1_mul(total, same)
+        # few rows: the accumulate / merge / reduce launches (default), small and large work items, and the self-contained bucket kernel
+        for tun in ({}, {"msm_few_rows_chunk": 256}, {"msm_few_rows_chunk": 4096}, {"msm_split": 0}, {"msm_split": 0, "msm_few_rows_chunk": 1024}):
+            for k, v in tun.items():
+                ctx.set_tunable(k, v)
+            assert g1_from_words(ctx.msm(g1_to_words(pts), fr_to_words(ks), 2)) == [want0, want1], tun
+        ctx.set_tunable("msm_split", 1)
+        ctx.set_tunable("msm_few_rows_chunk", 2048)
+        rows = 16
+        ks = [(rng.next() % 511 - 255) % O.R for _ in range(n * rows)]
+        ks[5 * n:6 * n] = rand_fr(rng, n, "uniform")
+        ks[9 * n + 140] = rng.fr()
+        got = g1_from_words(ctx.msm(g1_to_words(pts), fr_to_words(ks), rows))
+    assert got == [O.g1_mul_vec(pts, ks[i * n:(i + 1) * n]) for i in range(rows)]
 
 
 def case_fixed_base_mul(lib, kat):

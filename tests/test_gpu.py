@@ -99,6 +99,7 @@ def test_msm(gpu_lib, kat):
 def test_msm_many_rows_and_fixed_base(gpu_lib, kat):
     cases.case_msm_many_rows(gpu_lib, n=64, rows=20)
     cases.case_msm_many_rows(gpu_lib, n=300, rows=33, seed=818)
+    cases.case_msm_bucket_shapes(gpu_lib)
     cases.case_fixed_base_mul(gpu_lib, kat)
 
 

@@ -67,6 +67,10 @@ def test_msm_many_rows(emu_lib):
     cases.case_msm_many_rows(emu_lib, n=40, rows=17)
 
 
+def test_msm_bucket_shapes(emu_lib):
+    cases.case_msm_bucket_shapes(emu_lib)
+
+
 def test_fixed_base_mul(emu_lib, kat):
     cases.case_fixed_base_mul(emu_lib, kat)
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Per-kernel-class device time of ONE vgg11 proof (zk_profile_*), for A/B runs under ZK_TUNABLES.  usage: probe_classes.py [pics]"""
+"""Per-kernel-class device time of ONE vgg11 proof (zk_profile_*), for A/B runs under ZK_TUNABLES.  usage: probe_classes.py [pics]
+ZK_PROF_KERNELS=1 adds one line per kernel name (launches, device ms) on stderr."""
 import ctypes as C, json, os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -22,5 +23,6 @@ for k, name in enumerate(PROF_CLASSES):
     ms, cnt, b = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
     lib.dll.zk_profile_get(ctx, k, C.byref(ms), C.byref(cnt), C.byref(b))
     out[name] = [round(ms.value, 3), cnt.value]
+lib.dll.zk_profile_enable(ctx, 0)
 print(json.dumps(out))
 s.close()

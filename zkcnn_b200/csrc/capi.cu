@@ -84,6 +84,7 @@ int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
     else if (n == "cubic_tma") ctx->cubic_tma_enabled = value ? 1u : 0u;
     else if (n == "cubic_max_grid") ctx->cubic_max_grid = (uint32_t) std::max<uint64_t>(1, value);
     else if (n == "cubic_factored_min_iters") ctx->cubic_factored_min_iters = (uint32_t) std::max<uint64_t>(1, value);
+    else if (n == "msm_split") ctx->msm_split = value ? 1u : 0u;
     else if (n == "msm_few_rows_chunk") ctx->msm_few_rows_chunk = (uint32_t) std::max<uint64_t>(256, std::min<uint64_t>(value, kMsmChunk));
     else ZK_REQUIRE(false, "unknown tunable");
     ZK_API_END
@@ -95,6 +96,7 @@ int zk_profile_enable(zk_ctx *ctx, int on) {
     rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
     rt::sync(ctx->stream);
     prof_resolve(ctx);
+    if (!on) prof_print_kernels(ctx);   // (ZK_PROF_KERNELS=1)
     for (int c = 0; c < ZK_PROF_CLASSES; ++c) { ctx->prof_ms[c] = 0; ctx->prof_launches[c] = 0; ctx->prof_bytes[c] = 0; }
     if (ctx->prof_ops.p) { rt::dzero(ctx->prof_ops.p, 64, ctx->stream); rt::sync(ctx->stream); }
     ctx->prof_on = on != 0;

@@ -19,6 +19,8 @@ static void msm_configure() {
     static const bool done = [] {   // (thread-safe: several contexts may start at once)
         rt::check(cudaFuncSetAttribute(k_msm_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(msm_smem_t)),
                   "cudaFuncSetAttribute(k_msm_window)");
+        rt::check(cudaFuncSetAttribute(k_msm_bucket_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(msm_fill_smem_t)),
+                  "cudaFuncSetAttribute(k_msm_bucket_fill)");
         return true;
     }();
     (void) done;
@@ -82,18 +84,19 @@ static void msm_prepare_multiples(zk_ctx *ctx, hyrax_t &H) {
 static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n, uint32_t n_rows, g1_jac_t *out_dev) {
     ZK_REQUIRE(H.table_ready && n <= H.n_gens, "MSM: generator table missing or too small");
     msm_configure();
-    H.msm_rowinfo.ensure((size_t) n_rows * 4);
-    rt::dzero(H.msm_rowinfo.p, (size_t) n_rows * 4, ctx->stream);
+    H.msm_rowinfo.ensure((size_t) (2 * n_rows + 1) * 4);   // [n_rows]: length of the wide-row list; [n_rows + 1 + row]: byte levels of the row (small path)
+    rt::dzero(H.msm_rowinfo.p, (size_t) (2 * n_rows + 1) * 4, ctx->stream);
     const uint64_t alg_bytes = n * n_rows * 32 + n * 96 + (uint64_t) n_rows * 144;
-    // many rows over one generator set: the one-byte scalars go through the small-multiples table, the bucket kernel
-    // below only sees what is left (rows whose widest leftover is 0 bytes leave it at once)
+    // many rows over one generator set: scalars of up to kSmallBytes bytes go through the small-multiples table, the bucket kernel
+    // below only sees what is left (the rows k_msm_small lists as holding wider scalars)
     const bool small_path = n_rows >= 16 && H.n_gens <= kMultiplesMaxGens;
     uint32_t n_seg = 0;
     if (small_path) {
         msm_prepare_multiples(ctx, H);
         const uint32_t seg_len = (uint32_t) std::min<uint64_t>(n, 2048);
         n_seg = (uint32_t) ((n + seg_len - 1) / seg_len);
-        H.msm_small.ensure((size_t) n_rows * n_seg * sizeof(g1_jac_t));
+        H.msm_small.ensure((size_t) n_rows * n_seg * kSmallBytes * sizeof(g1_jac_t));
+        H.msm_wide_rows.ensure((size_t) n_rows * 4);
         msm_small_args_t S;
         S.scalars = scalars_dev;
         S.table = H.mult.as<g1_aff_t>();
@@ -101,34 +104,62 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         S.n_rows = n_rows; S.n_seg = n_seg; S.seg_len = seg_len;
         S.partial = H.msm_small.as<g1_jac_t>();
         S.rowinfo = H.msm_rowinfo.as<uint32_t>();
+        S.wide_rows = H.msm_wide_rows.as<uint32_t>();
         S.ops = ctx->prof_on ? prof_ops_counter(ctx) : nullptr;
         const uint64_t warps = (uint64_t) n_rows * n_seg;
         ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, alg_bytes, k_msm_small, dim3((uint32_t) ((warps + kSmallWarps - 1) / kSmallWarps)), dim3(kSmallWarps * 32), 0, S);
     } else {
         ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
     }
-    const uint32_t chunk = n_rows <= 8 ? std::min<uint32_t>(ctx->msm_few_rows_chunk, kMsmChunk) : kMsmChunk;   // few rows: more CTAs per row
+    // work items of the bucket kernel: (row, chunk of generators), all windows of a chunk in one item.  Few rows: smaller chunks, more CTAs
+    const uint32_t chunk = n_rows <= 8 ? std::max<uint32_t>(1, std::min<uint32_t>(ctx->msm_few_rows_chunk / kMsmWindows, kMsmGensPerItem)) : kMsmGensPerItem;
     const uint32_t n_chunks = (uint32_t) ((n + chunk - 1) / chunk);
-    const size_t per_row = (size_t) n_chunks * kMsmWindows;
-    H.msm_out.ensure((size_t) n_rows * per_row * sizeof(g1_jac_t));
+    const bool waited = H.table_pending;   // a cross-stream wait sits between the next launch and its predecessor: plain launch then
+    msm_wait_table(ctx, H);
+    if (!small_path && ctx->msm_split && n_rows <= 8 && (uint64_t) n_rows * n_chunks <= 4096) {
+        // few rows (the opening): accumulate / merge / reduce as three lean launches (hyrax_kernels.cuh)
+        const uint32_t n_items = n_rows * n_chunks;
+        H.msm_buckets.ensure((size_t) n_items * kMsmBuckets * sizeof(g1_jac_t));
+        H.msm_item_entries.ensure((size_t) n_items * 4);
+        H.msm_merged.ensure((size_t) n_rows * kMsmBuckets * sizeof(g1_jac_t));
+        msm_fill_args_t F;
+        F.scalars = scalars_dev;
+        F.table = H.table.as<g1_aff_t>();
+        F.rowinfo = H.msm_rowinfo.as<uint32_t>();
+        F.n = n;
+        F.n_rows = n_rows; F.n_table = H.n_gens; F.n_chunks = n_chunks; F.chunk = chunk;
+        F.buckets = H.msm_buckets.as<g1_jac_t>();
+        F.item_entries = H.msm_item_entries.as<uint32_t>();
+        F.ops = ctx->prof_on ? prof_ops_counter(ctx) + 1 : nullptr;
+        const uint32_t fgrid = std::min<uint32_t>(n_items, 3 * ZK_SM_COUNT);
+        if (waited) ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, alg_bytes, k_msm_bucket_fill, dim3(fgrid), dim3(kFillThreads), sizeof(msm_fill_smem_t), F);
+        else ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, alg_bytes, k_msm_bucket_fill, dim3(fgrid), dim3(kFillThreads), sizeof(msm_fill_smem_t), F);
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_bucket_merge, dim3(n_rows * kMsmBuckets / (kBlock / 32)), dim3(kBlock), 0, H.msm_buckets.as<g1_jac_t>(),
+                       H.msm_item_entries.as<uint32_t>(), n_rows, n_chunks, H.msm_merged.as<g1_jac_t>());
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_bucket_reduce, dim3(n_rows), dim3(kBlock), 0, H.msm_merged.as<g1_jac_t>(), n_rows, out_dev);
+        return;
+    }
+    H.msm_out.ensure((size_t) n_rows * n_chunks * sizeof(g1_jac_t));
     msm_args_t A;
     A.scalars = scalars_dev;
     A.table = H.table.as<g1_aff_t>();
     A.rowinfo = H.msm_rowinfo.as<uint32_t>();
+    A.wide_rows = small_path ? H.msm_wide_rows.as<uint32_t>() : nullptr;
     A.n = n;
+    A.n_rows = n_rows;
     A.n_table = H.n_gens;
     A.n_chunks = n_chunks;
     A.chunk = chunk;
-    A.wide_only = small_path ? 1u : 0u;
+    A.wide_only = small_path ? (uint32_t) kSmallBytes : 0u;
     A.partial = H.msm_out.as<g1_jac_t>();
     A.ops = ctx->prof_on ? prof_ops_counter(ctx) + 1 : nullptr;
-    const bool waited = H.table_pending;   // a cross-stream wait sits between this launch and its predecessor: plain launch then
-    msm_wait_table(ctx, H);
-    // grid.x is limited to 2^31-1, grid.y to 65535: rows * chunks in x, windows in y
-    if (waited) ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
-    else ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(n_rows * n_chunks, kMsmWindows), dim3(kBlock), sizeof(msm_smem_t), A);
+    // persistent CTAs (one per SM: the kernel's shared memory) walk the items; with wide_only their number is only known on the device
+    const uint32_t grid = (uint32_t) std::min<uint64_t>((uint64_t) n_rows * n_chunks, 2 * ZK_SM_COUNT);
+    if (waited) ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(grid), dim3(kBlock), sizeof(msm_smem_t), A);
+    else ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(grid), dim3(kBlock), sizeof(msm_smem_t), A);
     ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kSmallWarps - 1) / kSmallWarps), dim3(kSmallWarps * 32), 0,
-                 small_path ? H.msm_small.as<g1_jac_t>() : (const g1_jac_t *) nullptr, n_seg, H.msm_out.as<g1_jac_t>(), (uint32_t) per_row, n_rows, out_dev);
+                 small_path ? H.msm_small.as<g1_jac_t>() : (const g1_jac_t *) nullptr, n_seg, H.msm_out.as<g1_jac_t>(), n_chunks,
+                 H.msm_rowinfo.as<uint32_t>(), small_path ? 1u : 0u, n_rows, out_dev);
 }
 
 static void hyrax_bind(zk_ctx *ctx, const fr_t *Z, uint32_t bit_length, const uint64_t *gens, uint32_t n_gens) {

@@ -66,7 +66,7 @@ static inline zk::rt::event_t prof_event(zk_ctx *ctx) {
 // the same on an explicit stream (side work that overlaps the main stream, e.g. the window-table build)
 #define ZK_KLAUNCH_S(ctx, strm, cls, bytes, kernel, grid, block, smem, ...)               \
     do {                                                                                  \
-        zk_ctx::prof_rec zk_pr_{(cls), nullptr, nullptr};                                 \
+        zk_ctx::prof_rec zk_pr_{(cls), nullptr, nullptr, #kernel};                        \
         if ((ctx)->prof_on) {                                                             \
             zk_pr_.a = zk::prof_event(ctx);                                               \
             zk_pr_.b = zk::prof_event(ctx);                                               \
@@ -116,10 +116,25 @@ static unsigned long long *prof_ops_counter(zk_ctx *ctx) {
     return ctx->prof_ops.as<unsigned long long>();
 }
 
+static bool prof_by_kernel_enabled() { static const bool on = [] { const char *e = getenv("ZK_PROF_KERNELS"); return e && *e && *e != '0'; }(); return on; }
+static void prof_print_kernels(zk_ctx *ctx) {
+    if (ctx->prof_by_kernel.empty()) return;
+    std::vector<std::pair<std::string, std::pair<uint64_t, double>>> v(ctx->prof_by_kernel.begin(), ctx->prof_by_kernel.end());
+    std::sort(v.begin(), v.end(), [](const auto &a, const auto &b) { return a.second.second > b.second.second; });
+    double tot = 0;
+    for (auto &e : v) tot += e.second.second;
+    fprintf(stderr, "[zk_prof] %-28s %8s %10s %6s %9s\n", "kernel", "launches", "ms", "share", "avg us");
+    for (auto &e : v) fprintf(stderr, "[zk_prof] %-28s %8lu %10.3f %5.1f%% %9.2f\n", e.first.c_str(), (unsigned long) e.second.first, e.second.second,
+                              100.0 * e.second.second / tot, 1e3 * e.second.second / e.second.first);
+    fprintf(stderr, "[zk_prof] total %.3f ms (CUDA events around every launch on the launching stream)\n", tot);
+    ctx->prof_by_kernel.clear();
+}
 static void prof_resolve(zk_ctx *ctx) {
     for (auto &r : ctx->prof_pending) {
         zk::rt::event_sync(r.b);
-        ctx->prof_ms[r.cls] += zk::rt::event_elapsed_ms(r.a, r.b);
+        const float ms = zk::rt::event_elapsed_ms(r.a, r.b);
+        ctx->prof_ms[r.cls] += ms;
+        if (prof_by_kernel_enabled() && r.name) { auto &e = ctx->prof_by_kernel[r.name]; ++e.first; e.second += ms; }
         ctx->prof_pool.push_back(r.a);
         ctx->prof_pool.push_back(r.b);
     }

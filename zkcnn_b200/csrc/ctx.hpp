@@ -1,5 +1,6 @@
 // Device-resident prover state behind the C ABI (include/zkcnn_b200.h).
 #pragma once
+#include <map>
 #include "../../include/zkcnn_b200.h"
 #include "g1.cuh"
 #include "rt.hpp"
@@ -92,7 +93,7 @@ struct hyrax_t {
     uint32_t cur = 0;          // current length of bullet_a
     uint32_t round = 0;
     std::vector<fr_t> rinv;    // 1 / randomness of the finished rounds
-    rt::dbuf msm_out, msm_small, msm_rowinfo, pts_out;
+    rt::dbuf msm_out, msm_small, msm_rowinfo, msm_wide_rows, msm_buckets, msm_item_entries, msm_merged, pts_out;
 };
 
 }  // namespace zk
@@ -148,7 +149,8 @@ struct zk_ctx {
     uint32_t cubic_tma_enabled = 1;          // DOT_PROD fold rounds on large tables use k_round_cubic_tma
     uint32_t cubic_max_grid = 1u << 20;       // cap on the CTAs of a K2 launch (tests: forces several iterations per thread on small tables)
     uint32_t cubic_factored_min_iters = 4;   // k_round_cubic: factored form from this many output pairs per thread
-    uint32_t msm_few_rows_chunk = 2048;      // entries per CTA of k_msm_window when an MSM has at most 8 rows
+    uint32_t msm_split = 1;                  // MSMs of at most 8 rows: accumulate / merge / reduce launches (k_msm_bucket_*) instead of k_msm_window
+    uint32_t msm_few_rows_chunk = 2048;      // (generator, window) entries per work item of k_msm_window when an MSM has at most 8 rows (32 per generator)
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft
 
     zk::hyrax_t hy;
@@ -162,7 +164,8 @@ struct zk_ctx {
 
     // optional per-kernel-class timing (zk_profile_*): CUDA events around every launch of the stream
     bool prof_on = false;
-    struct prof_rec { int cls; zk::rt::event_t a, b; };
+    struct prof_rec { int cls; zk::rt::event_t a, b; const char *name = nullptr; };
+    std::map<std::string, std::pair<uint64_t, double>> prof_by_kernel;   // ZK_PROF_KERNELS=1: launches and device ms per kernel name (printed by zk_profile_enable(ctx, 0))
     std::vector<prof_rec> prof_pending;
     std::vector<zk::rt::event_t> prof_pool;
     double prof_ms[ZK_PROF_CLASSES] = {};

@@ -23,7 +23,7 @@
 namespace zk {
 
 constexpr int kMsmWindows = 32;      // 8-bit digits of a < 2^255 magnitude (|x| <= (r-1)/2 < 2^254)
-constexpr int kMsmChunk = 4096;      // entries per CTA
+constexpr int kMsmChunk = 4096;      // upper bound of the "msm_few_rows_chunk" tunable ((generator, window) entries per work item)
 constexpr int kMsmBuckets = 256;
 
 ZK_HD __forceinline__ fp_t ld_fp(const fp_t *p) {
@@ -122,149 +122,369 @@ __global__ void __launch_bounds__(kBlock) k_msm_rowinfo(const fr_t *scalars, uin
     }
 }
 
-struct msm_smem_t {
-    g1_jac_t bucket[kMsmBuckets];
-    g1_jac_t first[kBlock];
-    g1_jac_t last[kBlock];
-    uint32_t count[kMsmBuckets];
-    uint32_t off[kMsmBuckets + 1];
-    uint32_t cursor[kMsmBuckets];
-    uint16_t sorted[kMsmChunk];
-    uint8_t dig[kMsmChunk];
-    uint8_t sgn[kMsmChunk];
-};
-
-struct msm_args_t {
-    const fr_t *scalars;     // [n_rows][n]
-    const g1_aff_t *table;   // [kMsmWindows][n_table]
-    const uint32_t *rowinfo; // widest magnitude per row, bytes
-    uint64_t n;              // row length (== number of generators used)
-    uint32_t n_table;        // generators in the table (row stride of the table)
-    uint32_t n_chunks;       // CTAs per row and window
-    uint32_t chunk;          // entries per CTA (<= kMsmChunk)
-    uint32_t wide_only;      // 1: scalars that fit one byte are skipped (the small-multiples path took them, msm_kernels.cuh)
-    g1_jac_t *partial;       // [n_rows][n_chunks][kMsmWindows] window sums
-    unsigned long long *ops; // != nullptr (profiling): += bucket additions (mixed) of this CTA; the reduction's 2 x 255 full additions are added by the host
-};
-
-// grid = (n_rows * n_chunks, kMsmWindows)
-__global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
-    ZK_PDL_ENTRY();
-    ZK_DYN_SMEM(msm_smem_t, S);
+// Balanced bucket accumulation over a digit-sorted entry list, shared by the bucket kernels.  Thread t of NT adds up the entries
+// sorted[t*q, (t+1)*q) run by run (a run = consecutive entries of one bucket).  A run that neither continues from the previous thread
+// nor into the next one is a whole bucket: emit(bucket, sum).  A bucket that spans threads is the chain
+//     last[lo] + last[lo+1] + ... + last[hi-1] + first[hi]
+// (runs that extend to the right go to `last`, the terminal piece to `first`), summed by a segmented inclusive scan over `last` --
+// log2(NT) dependent additions however skewed the digits are (one hot bucket used to cost one addition per thread it spanned).
+// entry: generator (7 bits) | window << 7 (5 bits) | negative << 12 | digit << 13.  Every thread of the CTA must call this.
+template <int NT, class Emit>
+__device__ __forceinline__ void msm_accumulate_runs(const uint32_t *sorted, uint32_t E, const g1_aff_t *T, uint32_t n_table, g1_jac_t *first,
+                                                     g1_jac_t *last, uint32_t *chain_start, uint32_t *term_bucket, Emit emit) {
     const uint32_t t = threadIdx.x;
-    const uint32_t row = blockIdx.x / A.n_chunks, chunk = blockIdx.x % A.n_chunks, w = blockIdx.y;
-    g1_jac_t *dst = A.partial + ((size_t) blockIdx.x * kMsmWindows + w);
-    if (w >= A.rowinfo[row]) {   // no scalar of this row reaches this window
-        if (t == 0) *dst = g1_jac_t::inf();
-        return;
-    }
-    const uint64_t base = (uint64_t) chunk * A.chunk;
-    const uint32_t nc = (uint32_t) (A.n - base < (uint64_t) A.chunk ? A.n - base : (uint64_t) A.chunk);
-    const fr_t *sc = A.scalars + (uint64_t) row * A.n + base;
-    const g1_aff_t *T = A.table + (size_t) w * A.n_table + base;
-
-    S->count[t] = 0;
-    S->bucket[t] = g1_jac_t::inf();
-    S->first[t] = g1_jac_t::inf();
-    S->last[t] = g1_jac_t::inf();
-    __syncthreads();
-    // digits of this window + histogram
-    for (uint32_t j = t; j < nc; j += kBlock) {
-        fr_t s = ld_fr(sc + j);
-        uint32_t d = 0, neg = 0;
-        if (!s.is_zero()) {
-            uint32_t mag[8];
-            const uint32_t nb = scalar_sign_mag(s, mag, neg);
-            d = (mag[w >> 2] >> ((w & 3) * 8)) & 0xffu;
-            if (A.wide_only && nb <= 1) d = 0;
-        }
-        S->dig[j] = (uint8_t) d;
-        S->sgn[j] = (uint8_t) neg;
-        if (d) atomicAdd(&S->count[d], 1u);
-    }
-    __syncthreads();
-    if (t == 0) {
-        uint32_t o = 0;
-        S->off[0] = 0;
-        S->off[1] = 0;
-        for (int b = 1; b < kMsmBuckets; ++b) {
-            S->cursor[b] = o;
-            o += S->count[b];
-            S->off[b + 1] = o;
-        }
-    }
-    __syncthreads();
-    const uint32_t E = S->off[kMsmBuckets];
-    if (A.ops && t == 0 && E) atomicAdd(A.ops, (unsigned long long) E);
-    if (E == 0) {
-        if (t == 0) *dst = g1_jac_t::inf();
-        return;
-    }
-    for (uint32_t j = t; j < nc; j += kBlock) {
-        const uint32_t d = S->dig[j];
-        if (d) S->sorted[atomicAdd(&S->cursor[d], 1u)] = (uint16_t) (j | ((uint32_t) S->sgn[j] << 15));
-    }
-    __syncthreads();
-    // balanced accumulation: thread t owns sorted[t*q, (t+1)*q)
-    const uint32_t q = (E + kBlock - 1) / kBlock;
+    const uint32_t q = (E + NT - 1) / NT;
     const uint32_t sb = t * q, se = sb + q < E ? sb + q : E;
+    last[t] = g1_jac_t::inf();
+    chain_start[t] = 1u;
+    term_bucket[t] = 0u;   // bucket 0 is never used: "no terminal piece"
     if (sb < E) {
         g1_jac_t acc = g1_jac_t::inf();
-        uint32_t cur_b = S->dig[S->sorted[sb] & 0x7fffu], run_start = sb;
+        uint32_t cur_b = sorted[sb] >> 13, run_start = sb;
         for (uint32_t p = sb; p <= se; ++p) {
-            uint32_t b = 0, j = 0, neg = 0;
+            uint32_t b = 0, e = 0;
             if (p < se) {
-                const uint32_t e = S->sorted[p];
-                j = e & 0x7fffu;
-                neg = e >> 15;
-                b = S->dig[j];
+                e = sorted[p];
+                b = e >> 13;
             }
             if (p == se || b != cur_b) {   // flush the finished run
-                if (S->off[cur_b] >= sb && S->off[cur_b + 1] <= se) S->bucket[cur_b] = acc;   // bucket lies inside this span
-                else if (run_start == sb) S->first[t] = acc;
-                else S->last[t] = acc;
+                const bool from_left = run_start == sb && sb > 0 && (sorted[sb - 1] >> 13) == cur_b;
+                const bool to_right = p == se && se < E && (sorted[se] >> 13) == cur_b;
+                if (to_right) {
+                    last[t] = acc;
+                    chain_start[t] = from_left ? 0u : 1u;
+                } else if (from_left) {
+                    first[t] = acc;
+                    term_bucket[t] = cur_b;
+                } else emit(cur_b, acc);
                 if (p == se) break;
                 acc = g1_jac_t::inf();
                 cur_b = b;
                 run_start = p;
             }
+            const g1_aff_t *src = T + (size_t) ((e >> 7) & 31u) * n_table + (e & 127u);
             g1_aff_t pt;
-            pt.x = ld_fp(&T[j].x);
-            pt.y = ld_fp(&T[j].y);
-            if (neg) pt.y = -pt.y;   // (0,0) stays (0,0): infinity is its own negative
+            pt.x = ld_fp(&src->x);
+            pt.y = ld_fp(&src->y);
+            if ((e >> 12) & 1u) pt.y = -pt.y;   // (0,0) stays (0,0): infinity is its own negative
             acc = g1_add_mixed(acc, pt);
         }
     }
     __syncthreads();
-    // buckets shared by several threads: add up their partial runs
-    if (t >= 1 && S->count[t]) {
-        const uint32_t lo = S->off[t] / q, hi = (S->off[t + 1] - 1) / q;
-        if (lo != hi) {
-            g1_jac_t s = g1_jac_t::inf();
-            for (uint32_t k = lo; k <= hi; ++k) s = g1_add(s, S->off[t] <= k * q ? S->first[k] : S->last[k]);
-            S->bucket[t] = s;
-        }
-    }
-    __syncthreads();
-    // sum_b b * B_b = sum_{k = 1..255} S_k with the suffix sums S_k = sum_{b >= k} B_b: a parallel suffix scan (8 steps of one
-    // addition per thread, ping-pong between `bucket` and `first`, which is free by now) and a tree sum of S_1..S_255 -- 16
-    // dependent point additions instead of the 8 doublings + up to 8 additions + 8 tree levels of scaling every bucket by b.
-    {
-        g1_jac_t *in = S->bucket, *out = S->first;
-        for (uint32_t d = 1; d < (uint32_t) kMsmBuckets; d <<= 1) {
-            out[t] = t + d < (uint32_t) kMsmBuckets ? g1_add(in[t], in[t + d]) : in[t];
-            __syncthreads();
-            g1_jac_t *tmp = in; in = out; out = tmp;
-        }
-        // 8 steps: the result is back in S->bucket; bucket 0 is empty by construction and its suffix sum is not a term
-        if (t == 0) S->bucket[0] = g1_jac_t::inf();
-    }
-    __syncthreads();
-    for (uint32_t s = kBlock / 2; s > 0; s >>= 1) {
-        if (t < s) S->bucket[t] = g1_add(S->bucket[t], S->bucket[t + s]);
+    for (uint32_t d = 1; d < (uint32_t) NT; d <<= 1) {   // segmented inclusive scan, in place (read, barrier, write, barrier)
+        const bool take = t >= d && !chain_start[t];
+        g1_jac_t left = g1_jac_t::inf();
+        uint32_t left_start = 0;
+        if (take) { left = last[t - d]; left_start = chain_start[t - d]; }
+        __syncthreads();
+        if (take) { last[t] = g1_add(left, last[t]); chain_start[t] = left_start; }
         __syncthreads();
     }
-    if (t == 0) *dst = S->bucket[0];
+    if (term_bucket[t]) emit(term_bucket[t], g1_add(last[t - 1], first[t]));
+}
+
+constexpr int kMsmEntries = 4096;             // (generator, window) entries one work item sorts in shared memory
+constexpr int kMsmGensPerItem = kMsmEntries / kMsmWindows;   // 128 generators x 32 windows
+constexpr int kMsmSeg = 8;                    // buckets per segment of the final reduction
+constexpr int kMsmSegs = kMsmBuckets / kMsmSeg;
+
+struct msm_smem_t {
+    g1_jac_t bucket[kMsmBuckets];
+    g1_jac_t first[kBlock];      // partial run at the start of a thread's span; later the segments' weighted sums W_s
+    g1_jac_t last[kBlock];       // partial run at the end of a thread's span; later the segments' plain sums T_s (ping-pong halves)
+    uint32_t count[kMsmBuckets];
+    uint32_t off[kMsmBuckets + 1];
+    uint32_t cursor[kMsmBuckets];
+    uint32_t scan[2][kMsmBuckets];
+    uint32_t sorted[kMsmEntries];   // generator (7 bits) | window << 7 (5 bits) | negative << 12 | digit << 13
+};
+
+struct msm_args_t {
+    const fr_t *scalars;     // [n_rows][n]
+    const g1_aff_t *table;   // [kMsmWindows][n_table]
+    const uint32_t *rowinfo; // widest magnitude per row, bytes; rowinfo[n_rows] = number of rows listed in wide_rows
+    const uint32_t *wide_rows;   // wide_only: the rows that hold a scalar wider than one byte (appended by k_msm_small)
+    uint64_t n;              // row length (== number of generators used)
+    uint32_t n_rows;
+    uint32_t n_table;        // generators in the table (row stride of the table)
+    uint32_t n_chunks;       // work items per row
+    uint32_t chunk;          // generators per work item (<= kMsmGensPerItem)
+    uint32_t wide_only;      // != 0: scalars of at most this many bytes are skipped (the small-multiples path took them, msm_kernels.cuh)
+    g1_jac_t *partial;       // [n_rows][n_chunks] bucket-method sums
+    unsigned long long *ops; // != nullptr (profiling): += bucket additions (mixed) of this CTA; the reductions are added by the host
+};
+
+// Bucket method over ALL windows at once.  The table already carries the 2^(8w) factor of window w, so the digits of every window of
+// a scalar go into ONE set of 255 buckets: a work item is (row, chunk of <= 128 generators) with up to 32 entries per generator, and
+// one bucket reduction serves all windows (32 of them before).  Persistent CTAs walk the work items; with wide_only the items are
+// (listed wide row, chunk), the list being written by k_msm_small, so a witness with a handful of wide scalars costs a handful of
+// items.  The reduction  sum_b b * B_b  is done per segment of 8 buckets by 32 threads (running sums: W_s = sum_i i * B_{8s+i},
+// T_s = sum_i B_{8s+i}), then  sum_s W_s + 8 * sum_s s * T_s  with a 32-wide suffix scan + tree: ~1000 point additions per item
+// instead of the 4096 of a 256-wide scan.
+__global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
+    ZK_PDL_ENTRY();
+    ZK_DYN_SMEM(msm_smem_t, S);
+    const uint32_t t = threadIdx.x;
+    const uint32_t n_items = (A.wide_only ? A.rowinfo[A.n_rows] : A.n_rows) * A.n_chunks;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t ri = item / A.n_chunks, chunk = item % A.n_chunks;
+        const uint32_t row = A.wide_only ? A.wide_rows[ri] : ri;
+        g1_jac_t *dst = A.partial + ((size_t) row * A.n_chunks + chunk);
+        const uint32_t nw = A.rowinfo[row] < (uint32_t) kMsmWindows ? A.rowinfo[row] : (uint32_t) kMsmWindows;   // live windows of this row
+        const uint64_t base = (uint64_t) chunk * A.chunk;
+        const uint32_t nc = (uint32_t) (A.n - base < (uint64_t) A.chunk ? A.n - base : (uint64_t) A.chunk);
+        const fr_t *sc = A.scalars + (uint64_t) row * A.n + base;
+        const g1_aff_t *T = A.table + base;
+
+        S->count[t] = 0;
+        S->bucket[t] = g1_jac_t::inf();
+        __syncthreads();
+        // thread t takes half of the windows of generator t / 2: digits + histogram
+        const uint32_t g = t >> 1, w0 = (t & 1u) * (kMsmWindows / 2);
+        uint32_t dg[4] = {0, 0, 0, 0}, neg = 0;   // the 16 digits of this thread's windows
+        if (g < nc && w0 < nw) {
+            const fr_t s = ld_fr(sc + g);
+            if (!s.is_zero()) {
+                uint32_t mag[8];
+                const uint32_t nb = scalar_sign_mag(s, mag, neg);
+                if (!(A.wide_only && nb <= A.wide_only)) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dg[k] = mag[(w0 >> 2) + k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kMsmWindows / 2; ++k) {
+                const uint32_t d = (dg[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                if (d && w0 + k < nw) atomicAdd(&S->count[d], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive prefix sum of the histogram (bucket 0 stays empty)
+        {
+            uint32_t (*sa)[kMsmBuckets] = S->scan;
+            sa[0][t] = t ? S->count[t] : 0u;
+            __syncthreads();
+            int cur = 0;
+            for (uint32_t d = 1; d < (uint32_t) kMsmBuckets; d <<= 1) {
+                sa[cur ^ 1][t] = sa[cur][t] + (t >= d ? sa[cur][t - d] : 0u);
+                __syncthreads();
+                cur ^= 1;
+            }
+            const uint32_t incl = sa[cur][t], excl = incl - (t ? S->count[t] : 0u);
+            S->off[t] = excl;
+            S->cursor[t] = excl;
+            if (t == kBlock - 1) S->off[kMsmBuckets] = incl;
+        }
+        __syncthreads();
+        const uint32_t E = S->off[kMsmBuckets];
+        if (E == 0) {   // (uniform over the CTA)
+            if (t == 0) *dst = g1_jac_t::inf();
+            continue;
+        }
+        if (A.ops && t == 0) atomicAdd(A.ops, (unsigned long long) E);
+        if (g < nc && w0 < nw) {
+#pragma unroll
+            for (int k = 0; k < kMsmWindows / 2; ++k) {
+                const uint32_t d = (dg[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                if (d && w0 + k < nw) S->sorted[atomicAdd(&S->cursor[d], 1u)] = g | ((w0 + k) << 7) | (neg << 12) | (d << 13);
+            }
+        }
+        __syncthreads();
+        msm_accumulate_runs<kBlock>(S->sorted, E, T, A.n_table, S->first, S->last, S->cursor, S->scan[0], [&](uint32_t b, const g1_jac_t &sum) { S->bucket[b] = sum; });
+        __syncthreads();
+        // segments: thread s < 32 walks buckets 8s+7 .. 8s with a running sum; W_s = sum_i i * B_{8s+i} -> first[s], T_s -> last[s]
+        if (t < (uint32_t) kMsmSegs) {
+            g1_jac_t run = g1_jac_t::inf(), wsum = g1_jac_t::inf();
+            for (int i = kMsmSeg - 1; i >= 0; --i) {
+                const g1_jac_t b = S->bucket[t * kMsmSeg + i];
+                if (!b.is_inf()) run = g1_add(run, b);
+                if (i > 0 && !run.is_inf()) wsum = g1_add(wsum, run);
+            }
+            S->first[t] = wsum;
+            S->last[t] = run;
+        }
+        __syncthreads();
+        // sum_s s * T_s = sum_{k >= 1} (suffix sum of T from k): 5-step suffix scan by threads 0..31 (ping-pong inside `last`), while
+        // threads 32..63 tree-sum the W_s
+        {
+            g1_jac_t *in = S->last, *out = S->last + kMsmSegs;
+            for (uint32_t d = 1; d < (uint32_t) kMsmSegs; d <<= 1) {
+                if (t < (uint32_t) kMsmSegs) out[t] = t + d < (uint32_t) kMsmSegs ? g1_add(in[t], in[t + d]) : in[t];
+                else if (t < 2u * kMsmSegs) {
+                    const uint32_t i = t - kMsmSegs, st = (uint32_t) kMsmSegs / (2 * d);   // 16, 8, 4, 2, 1
+                    if (i < st) S->first[i] = g1_add(S->first[i], S->first[i + st]);
+                }
+                __syncthreads();
+                g1_jac_t *tmp = in; in = out; out = tmp;
+            }
+            // `in` holds the suffix sums; the k = 0 term is not part of the sum
+            if (t == 0) in[0] = g1_jac_t::inf();
+            __syncthreads();
+            for (uint32_t st = kMsmSegs / 2; st > 0; st >>= 1) {
+                if (t < st) in[t] = g1_add(in[t], in[t + st]);
+                __syncthreads();
+            }
+            if (t == 0) {
+                g1_jac_t r = in[0];
+                for (int k = 1; k < kMsmSeg; k <<= 1) r = g1_dbl(r);   // * 8
+                *dst = g1_add(r, S->first[0]);
+            }
+        }
+        __syncthreads();   // the next item reuses the shared arrays
+    }
+}
+
+// ---- few rows (the opening's two MSMs per round): accumulate / merge / reduce as three lean launches -------------------------------
+// k_msm_window keeps a whole SM (register file, 130 KB of shared memory) for as long as its slowest phase -- a reduction 32 threads wide --
+// takes.  With several proofs in flight that idles the machine, so MSMs of a few rows split the work by the parallelism it has:
+//   k_msm_bucket_fill    (row, chunk) items as above, 128 threads, ~57 KB: sort + balanced accumulation only; the 255 bucket sums of
+//                        the item go to global memory (three CTAs per SM, every thread adding points for most of the CTA's life)
+//   k_msm_bucket_merge   one warp per (row, bucket): sum over the row's items (lanes stride the items, 5-level tree)
+//   k_msm_bucket_reduce  one CTA per row:  sum_b b * B_b = sum_{k<8} 2^k * S_k,  S_k = sum of the buckets whose index has bit k set
+//                        (eight 128-leaf trees side by side, then 7 doublings + 7 additions); the result is normalised in place
+constexpr int kFillThreads = 128;
+struct msm_fill_smem_t {
+    g1_jac_t first[kFillThreads];   // partial run at the start / end of a thread's span (buckets shared with the neighbours)
+    g1_jac_t last[kFillThreads];
+    uint32_t count[kMsmBuckets];
+    uint32_t off[kMsmBuckets + 1];
+    uint32_t cursor[kMsmBuckets];
+    uint32_t scan[2][kFillThreads];
+    uint32_t sorted[kMsmEntries];   // generator (7 bits) | window << 7 | negative << 12 | digit << 13
+};
+struct msm_fill_args_t {
+    const fr_t *scalars;     // [n_rows][n]
+    const g1_aff_t *table;   // [kMsmWindows][n_table]
+    const uint32_t *rowinfo; // widest magnitude per row, bytes
+    uint64_t n;
+    uint32_t n_rows, n_table, n_chunks, chunk;   // chunk: generators per item (<= kMsmGensPerItem)
+    g1_jac_t *buckets;       // [n_rows * n_chunks][kMsmBuckets]; written for items with entries only
+    uint32_t *item_entries;  // [n_rows * n_chunks] entries of the item (0: its buckets were not written)
+    unsigned long long *ops; // != nullptr (profiling): += bucket additions (mixed)
+};
+
+__global__ void __launch_bounds__(kFillThreads, 3) k_msm_bucket_fill(msm_fill_args_t A) {
+    ZK_PDL_ENTRY();
+    ZK_DYN_SMEM(msm_fill_smem_t, S);
+    const uint32_t t = threadIdx.x;
+    const uint32_t n_items = A.n_rows * A.n_chunks;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t row = item / A.n_chunks, chunk = item % A.n_chunks;
+        const uint32_t nw = A.rowinfo[row] < (uint32_t) kMsmWindows ? A.rowinfo[row] : (uint32_t) kMsmWindows;
+        const uint64_t base = (uint64_t) chunk * A.chunk;
+        const uint32_t nc = (uint32_t) (A.n - base < (uint64_t) A.chunk ? A.n - base : (uint64_t) A.chunk);
+        const fr_t *sc = A.scalars + (uint64_t) row * A.n + base;
+        const g1_aff_t *T = A.table + base;
+        g1_jac_t *gout = A.buckets + (size_t) item * kMsmBuckets;
+
+        S->count[t] = 0;
+        S->count[t + kFillThreads] = 0;
+        __syncthreads();
+        // thread t takes generator t: the 32 digits of its magnitude + histogram
+        uint32_t dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, neg = 0;
+        if (t < nc && nw) {
+            const fr_t s = ld_fr(sc + t);
+            if (!s.is_zero()) scalar_sign_mag(s, dg, neg);
+#pragma unroll
+            for (int k = 0; k < kMsmWindows; ++k) {
+                const uint32_t d = (dg[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                if (d && (uint32_t) k < nw) atomicAdd(&S->count[d], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive prefix sum of the 256 counts: pairs of buckets per thread, 7-step scan over the pair sums
+        {
+            const uint32_t c0 = S->count[2 * t], c1 = S->count[2 * t + 1];
+            S->scan[0][t] = c0 + c1;
+            __syncthreads();
+            int cur = 0;
+            for (uint32_t d = 1; d < (uint32_t) kFillThreads; d <<= 1) {
+                S->scan[cur ^ 1][t] = S->scan[cur][t] + (t >= d ? S->scan[cur][t - d] : 0u);
+                __syncthreads();
+                cur ^= 1;
+            }
+            const uint32_t incl = S->scan[cur][t], excl = incl - (c0 + c1);
+            S->off[2 * t] = excl;
+            S->off[2 * t + 1] = excl + c0;
+            S->cursor[2 * t] = excl;
+            S->cursor[2 * t + 1] = excl + c0;
+            if (t == kFillThreads - 1) S->off[kMsmBuckets] = incl;
+        }
+        __syncthreads();
+        const uint32_t E = S->off[kMsmBuckets];
+        if (t == 0) {
+            A.item_entries[item] = E;
+            if (A.ops && E) atomicAdd(A.ops, (unsigned long long) E);
+        }
+        if (E == 0) continue;   // (uniform over the CTA)
+        if (t < nc) {
+#pragma unroll
+            for (int k = 0; k < kMsmWindows; ++k) {
+                const uint32_t d = (dg[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                if (d && (uint32_t) k < nw) S->sorted[atomicAdd(&S->cursor[d], 1u)] = t | ((uint32_t) k << 7) | (neg << 12) | (d << 13);
+            }
+        }
+        __syncthreads();
+        // empty buckets first (count is not touched below), then the sums: every bucket of a non-empty item is written exactly once
+        for (uint32_t b = t; b < (uint32_t) kMsmBuckets; b += kFillThreads)
+            if (b && S->count[b] == 0) gout[b] = g1_jac_t::inf();
+        msm_accumulate_runs<kFillThreads>(S->sorted, E, T, A.n_table, S->first, S->last, S->cursor, S->scan[0], [&](uint32_t b, const g1_jac_t &sum) { gout[b] = sum; });
+        __syncthreads();   // the next item reuses the shared arrays
+    }
+}
+
+// merged[row][b] = sum over the row's items of buckets[item][b]; one warp per (row, b), kBlock / 32 buckets per CTA
+__global__ void __launch_bounds__(kBlock) k_msm_bucket_merge(const g1_jac_t *buckets, const uint32_t *item_entries, uint32_t n_rows, uint32_t n_chunks,
+                                                              g1_jac_t *merged) {
+    ZK_PDL_ENTRY();
+    __shared__ g1_jac_t sh[kBlock];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t idx = blockIdx.x * (kBlock / 32) + warp;   // row * 256 + b
+    const uint32_t row = idx / kMsmBuckets, b = idx % kMsmBuckets;
+    const bool active = row < n_rows && b != 0;
+    g1_jac_t acc = g1_jac_t::inf();
+    if (active)
+        for (uint32_t k = lane; k < n_chunks; k += 32) {
+            const size_t item = (size_t) row * n_chunks + k;
+            if (item_entries[item] == 0) continue;
+            const g1_jac_t p = buckets[item * kMsmBuckets + b];
+            if (!p.is_inf()) acc = g1_add(acc, p);
+        }
+    g1_jac_t *my = sh + threadIdx.x;
+    *my = acc;
+    __syncwarp();
+    for (uint32_t st = 16; st > 0; st >>= 1) {
+        if (lane < st) *my = g1_add(*my, my[st]);
+        __syncwarp();
+    }
+    if (row < n_rows && lane == 0) merged[idx] = *my;
+}
+
+// out[row] = normalised sum_b b * merged[row][b]; one CTA per row, thread (k, u) = (threadIdx.x / 32, threadIdx.x % 32) works on S_k
+__global__ void __launch_bounds__(kBlock) k_msm_bucket_reduce(const g1_jac_t *merged, uint32_t n_rows, g1_jac_t *out) {
+    ZK_PDL_ENTRY();
+    __shared__ g1_jac_t sh[kBlock];
+    const uint32_t row = blockIdx.x, k = threadIdx.x >> 5, u = threadIdx.x & 31u;
+    const g1_jac_t *B = merged + (size_t) row * kMsmBuckets;
+    // the v-th bucket index with bit k set: bit k inserted into the 7-bit number v
+    g1_jac_t acc = g1_jac_t::inf();
+    for (uint32_t v = u; v < (uint32_t) kMsmBuckets / 2; v += 32) {
+        const uint32_t i = ((v >> k) << (k + 1)) | (1u << k) | (v & ((1u << k) - 1u));
+        const g1_jac_t p = B[i];
+        if (!p.is_inf()) acc = g1_add(acc, p);
+    }
+    g1_jac_t *my = sh + threadIdx.x;
+    *my = acc;
+    __syncthreads();
+    for (uint32_t st = 16; st > 0; st >>= 1) {
+        if (u < st) *my = g1_add(*my, my[st]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        g1_jac_t r = sh[7 * 32];
+        for (int kk = 6; kk >= 0; --kk) r = g1_add(g1_dbl(r), sh[kk * 32]);
+        out[row] = g1_normalize(r);
+    }
 }
 
 // out[row] = normalised sum of the row's (chunk, window) partial sums

@@ -61,14 +61,21 @@ __global__ void __launch_bounds__(128) k_msm_multiples_build(const g1_aff_t *gen
 }
 
 // ---- one warp per (row, segment): comm partial = sum of table points selected by the small scalars ---------------------------
+// Scalars of up to kSmallBytes bytes stay on this path: byte p of the magnitude selects a table point in pass p, the warp writes one
+// partial sum per byte level and k_msm_finish_rows combines the levels as  L_0 + 256 * (L_1 + 256 * (L_2 + ...))  -- 8 doublings per
+// level and row instead of a bucket reduction per (row, chunk).  The zkCNN witness has ~25 000 scalars of 2-3 bytes among 2^24 (biases
+// scaled to the accumulator's fixed point): passes beyond the first only run in the warps that met one.
+constexpr int kSmallBytes = 4;
 struct msm_small_args_t {
     const fr_t *scalars;       // [n_rows][n]
     const g1_aff_t *table;     // [n][255]
     uint64_t n;
     uint32_t n_rows, n_seg, seg_len;   // seg_len <= 65536
-    g1_jac_t *partial;         // [n_rows][n_seg]
-    uint32_t *rowinfo;         // widest magnitude (bytes) among the scalars that do NOT fit one byte, per row (atomicMax)
-    unsigned long long *ops;   // != nullptr (profiling): += mixed additions performed (one per non-zero one-byte scalar)
+    g1_jac_t *partial;         // [n_rows][n_seg][kSmallBytes] (levels a warp did not reach are written as infinity)
+    uint32_t *rowinfo;         // [n_rows] widest magnitude (bytes) among the scalars wider than kSmallBytes (atomicMax); [n_rows] = length of
+                               // wide_rows; [n_rows + 1 + row] = byte levels present in the row (<= kSmallBytes)
+    uint32_t *wide_rows;       // the rows with a scalar wider than kSmallBytes, in the order they were found (work list of k_msm_window)
+    unsigned long long *ops;   // != nullptr (profiling): += mixed additions performed (one per non-zero byte of a small scalar)
 };
 #ifndef ZK_SMALL_WARPS
 #define ZK_SMALL_WARPS 4
@@ -86,11 +93,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
     const uint64_t end = !active ? base : base + A.seg_len < A.n ? base + A.seg_len : A.n;
     const fr_t *sc = A.scalars + (uint64_t) row * A.n;
     uint32_t *q = queue[warp];
-    g1_jac_t acc = g1_jac_t::inf();
-    uint32_t head = 0, pending = 0, wide = 0;
-    (void) q; (void) head; (void) pending;   // unused by the (uncompacted) emulator path
-
-    uint32_t n_adds = 0;
+    (void) q;   // unused by the (uncompacted) emulator path
+    g1_jac_t acc;
+    uint32_t wide = 0, levels = 0, n_adds = 0;
     auto consume = [&](uint32_t code) {
         ++n_adds;
         const uint32_t j = code & 0xffffu, d = (code >> 16) & 0xffu, neg = code >> 24;
@@ -101,42 +106,73 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
         if (neg) pt.y = -pt.y;
         acc = g1_add_mixed(acc, pt);
     };
-
-    for (uint64_t b = base; b < end; b += 32) {
-        const uint64_t j = b + lane;
-        uint32_t code = 0;
-        if (j < end) {
-            const fr_t s = ld_fr(sc + j);
-            if (!s.is_zero()) {
-                uint32_t mag[8], neg;
-                const uint32_t nb = scalar_sign_mag(s, mag, neg);
-                if (nb > 1) wide = wide > nb ? wide : nb;
-                else code = (uint32_t) (j - base) | (mag[0] << 16) | (neg << 24);
-            }
-        }
-        // compact the non-zero small scalars of these 32 entries into the warp's queue, so that every lane of the warp
-        // has a point addition to do whenever the queue is drained (the witness is 40 % zeros)
 #if ZK_ON_DEVICE
-        const uint32_t mask = __ballot_sync(0xffffffffu, code != 0);
-        const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
-        if (code) q[(head + pending + rank) & 63u] = code;
-        pending += __popc(mask);
-        __syncwarp();
-        if (pending >= 32) {
-            const uint32_t c = q[(head + lane) & 63u];
-            head = (head + 32) & 63u;
-            pending -= 32;
-            __syncwarp();
-            consume(c);
-        }
+    uint32_t n_pass = 1;   // known after pass 0 (warp-uniform)
 #else
-        if (code) consume(code);
+    const uint32_t n_pass = kSmallBytes;   // the emulator's barriers want the same trip count in every thread
 #endif
-    }
+    for (uint32_t p = 0; p < n_pass; ++p) {
+        acc = g1_jac_t::inf();
+        uint32_t head = 0, pending = 0;
+        (void) head; (void) pending;
+        for (uint64_t b = base; b < end; b += 32) {
+            const uint64_t j = b + lane;
+            uint32_t code = 0;
+            if (j < end) {
+                const fr_t s = ld_fr(sc + j);
+                if (!s.is_zero()) {
+                    uint32_t mag[8], neg;
+                    const uint32_t nb = scalar_sign_mag(s, mag, neg);
+                    if (nb > (uint32_t) kSmallBytes) wide = wide > nb ? wide : nb;
+                    else {
+                        levels = levels > nb ? levels : nb;
+                        const uint32_t d = (mag[0] >> (8 * p)) & 0xffu;
+                        if (d) code = (uint32_t) (j - base) | (d << 16) | (neg << 24);
+                    }
+                }
+            }
+            // compact the non-zero digits of these 32 entries into the warp's queue, so that every lane of the warp
+            // has a point addition to do whenever the queue is drained (the witness is 40 % zeros)
 #if ZK_ON_DEVICE
-    if (lane < pending) consume(q[(head + lane) & 63u]);
+            const uint32_t mask = __ballot_sync(0xffffffffu, code != 0);
+            const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
+            if (code) q[(head + pending + rank) & 63u] = code;
+            pending += __popc(mask);
+            __syncwarp();
+            if (pending >= 32) {
+                const uint32_t c = q[(head + lane) & 63u];
+                head = (head + 32) & 63u;
+                pending -= 32;
+                __syncwarp();
+                consume(c);
+            }
+#else
+            if (code) consume(code);
 #endif
-    if (wide) atomicMax(A.rowinfo + row, wide);
+        }
+#if ZK_ON_DEVICE
+        if (lane < pending) consume(q[(head + lane) & 63u]);
+        __syncwarp();
+        if (p == 0) {
+            levels = __reduce_max_sync(0xffffffffu, levels);
+            n_pass = levels > 1 ? levels : 1;
+        }
+#endif
+        // warp-level sum of the 32 accumulators
+        g1_jac_t *my = sh + threadIdx.x;
+        *my = acc;
+        __syncwarp();
+        for (uint32_t st = 16; st > 0; st >>= 1) {
+            if (lane < st) *my = g1_add(*my, my[st]);
+            __syncwarp();
+        }
+        if (active && lane == 0) A.partial[gw * kSmallBytes + p] = *my;
+        __syncwarp();
+    }
+    if (active && lane == 0)
+        for (uint32_t p = n_pass; p < (uint32_t) kSmallBytes; ++p) A.partial[gw * kSmallBytes + p] = g1_jac_t::inf();
+    if (wide && atomicMax(A.rowinfo + row, wide) == 0) A.wide_rows[atomicAdd(A.rowinfo + A.n_rows, 1u)] = row;   // first to mark the row lists it
+    if (levels > 1 && (!ZK_ON_DEVICE || lane == 0)) atomicMax(A.rowinfo + A.n_rows + 1 + row, levels);
     if (A.ops) {
 #if ZK_ON_DEVICE
         const uint32_t tot = __reduce_add_sync(0xffffffffu, n_adds);
@@ -145,29 +181,23 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
         if (n_adds) atomicAdd(A.ops, (unsigned long long) n_adds);
 #endif
     }
-    // warp-level sum of the 32 accumulators
-    g1_jac_t *my = sh + threadIdx.x;
-    *my = acc;
-    __syncwarp();
-    for (uint32_t st = 16; st > 0; st >>= 1) {
-        if (lane < st) *my = g1_add(*my, my[st]);
-        __syncwarp();
-    }
-    if (active && lane == 0) A.partial[gw] = *my;
 }
 
-// ---- out[row] = normalised (sum of the row's small-path partials + sum of its bucket-path partials); one warp per row ------------
+// ---- out[row] = normalised (byte levels of the row's small-path partials + sum of its bucket-path partials); one warp per row ----------
+// (bucket partials of a row exist when the bucket kernel visited it: every row, or with wide_only the rows whose rowinfo is non-zero)
 __global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_jac_t *small, uint32_t n_small, const g1_jac_t *bucket,
-                                                                        uint32_t n_bucket, uint32_t n_rows, g1_jac_t *out) {
+                                                                        uint32_t n_bucket, const uint32_t *rowinfo, uint32_t wide_only,
+                                                                        uint32_t n_rows, g1_jac_t *out) {
     ZK_PDL_ENTRY();
     __shared__ g1_jac_t sh[kSmallWarps * 32];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t row = blockIdx.x * kSmallWarps + warp;
     const bool active = row < n_rows;
     if (!active) n_small = n_bucket = 0;
+    else if (wide_only && rowinfo[row] == 0) n_bucket = 0;
     g1_jac_t acc = g1_jac_t::inf();
     for (uint32_t k = lane; k < n_small; k += 32) {
-        const g1_jac_t p = small[(size_t) row * n_small + k];
+        const g1_jac_t p = small[((size_t) row * n_small + k) * kSmallBytes];   // level 0
         if (!p.is_inf()) acc = g1_add(acc, p);
     }
     for (uint32_t k = lane; k < n_bucket; k += 32) {
@@ -181,7 +211,23 @@ __global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_j
         if (lane < st) *my = g1_add(*my, my[st]);
         __syncwarp();
     }
-    if (active && lane == 0) out[row] = g1_normalize(*my);
+    if (active && lane == 0) {
+        g1_jac_t tot = *my;
+        const uint32_t levels = n_small ? rowinfo[n_rows + 1 + row] : 0u;   // > 1 only in the rare rows with 2..kSmallBytes-byte scalars
+        if (levels > 1) {
+            g1_jac_t hi = g1_jac_t::inf();
+            for (uint32_t p = levels - 1; p >= 1; --p) {
+                for (int k = 0; k < 8; ++k) hi = g1_dbl(hi);
+                for (uint32_t k = 0; k < n_small; ++k) {
+                    const g1_jac_t x = small[((size_t) row * n_small + k) * kSmallBytes + p];
+                    if (!x.is_inf()) hi = g1_add(hi, x);
+                }
+            }
+            for (int k = 0; k < 8; ++k) hi = g1_dbl(hi);
+            tot = g1_add(tot, hi);
+        }
+        out[row] = g1_normalize(tot);
+    }
 }
 
 // ---- fixed-base scalar multiplication: out[i] = k_i * B for ONE base point ------------------------------------------------------

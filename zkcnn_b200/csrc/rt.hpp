@@ -1,6 +1,7 @@
 // Thin runtime layer under the C ABI: device memory, copies, stream sync.  CUDA in the product; plain host memory
 // when the sources are compiled for the test-only emulator (ZK_EMU).
 #pragma once
+#include <sched.h>
 #include "zk_platform.cuh"
 #include <ctime>
 #include <map>
@@ -199,7 +200,43 @@ inline zk_stream_t stream_create(bool high = true) {
     return s;
 }
 inline void stream_destroy(zk_stream_t s) { if (s) cudaStreamDestroy(s); }
-inline void sync(zk_stream_t s) { check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); }
+// Waiting for a stream.  cudaStreamSynchronize spins on a host core, which is the lowest latency while every prover thread has a core
+// of its own.  With several provers per GPU and several GPUs per box the waiting threads outnumber the cores, so the wait can give
+// the core away:  ZK_HOST_WAIT=spin (default) | yield (poll an event, sched_yield between polls: as fast as spinning on an idle host,
+// lets runnable threads in when there are none to spare) | block (sleep on a blocking-sync event: no core burnt, a few tens of
+// microseconds more per wait).  ZK_BLOCKING_SYNC=1 is the older spelling of "block".
+enum wait_mode_t { kWaitSpin = 0, kWaitYield = 1, kWaitBlock = 2 };
+inline wait_mode_t wait_mode() {
+    static const wait_mode_t m = [] {
+        const char *e = getenv("ZK_HOST_WAIT");
+        if (e && !strcmp(e, "yield")) return kWaitYield;
+        if (e && !strcmp(e, "block")) return kWaitBlock;
+        if (e && *e && strcmp(e, "spin")) fprintf(stderr, "zkcnn_b200: ZK_HOST_WAIT=%s not understood (spin | yield | block); spinning\n", e);
+        const char *b = getenv("ZK_BLOCKING_SYNC");
+        return (!e || !*e) && b && *b && *b != '0' ? kWaitBlock : kWaitSpin;
+    }();
+    return m;
+}
+inline void sync(zk_stream_t s) {
+    const wait_mode_t mode = wait_mode();
+    if (mode == kWaitSpin) { check(cudaStreamSynchronize(s), "cudaStreamSynchronize"); return; }
+    static thread_local cudaEvent_t ev = nullptr;
+    static thread_local int ev_dev = -1;
+    int dev = 0;
+    check(cudaGetDevice(&dev), "cudaGetDevice");
+    if (!ev || ev_dev != dev) {
+        check(cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming), "cudaEventCreate");
+        ev_dev = dev;
+    }
+    check(cudaEventRecord(ev, s), "cudaEventRecord");
+    if (mode == kWaitYield) {
+        cudaError_t q;
+        while ((q = cudaEventQuery(ev)) == cudaErrorNotReady) sched_yield();
+        check(q, "cudaEventQuery");
+        return;
+    }
+    check(cudaEventSynchronize(ev), "cudaEventSynchronize");
+}
 // make stream `s` wait (on the device) for everything queued on `other` so far
 inline void stream_wait_stream(zk_stream_t s, zk_stream_t other) {
     cudaEvent_t e;

@@ -144,6 +144,33 @@ void prover::buildCompactWitness() {
             for (uint32_t i : wv) { wide_idx_[l].push_back(i); wide_val_[l].push_back(val[l][i]); }
     }
     compact_ready_ = true;
+    if (getenv("ZKH_WITNESS_STATS")) {   // diagnostic: how the input layer's scalars fall on the commitment MSM's paths (rows of 2^ceil(bl/2) generators)
+        const size_t n = witnessLength(0);
+        u32 bl = 0;
+        while (((size_t) 1 << bl) < n) ++bl;
+        const size_t row_len = (size_t) 1 << (bl - bl / 2);
+        size_t zero = 0, byte1 = 0, by_bytes[9] = {}, full = wide_idx_[0].size();
+        std::vector<uint8_t> row_wide((n + row_len - 1) / row_len, 0), item_wide((n + 127) / 128, 0);
+        for (size_t i = 0; i < n; ++i) {
+            const int64_t x = compact_[0][i];
+            const uint64_t m = (uint64_t) (x < 0 ? -x : x);
+            if (m == 0) { ++zero; continue; }
+            if (m < 256) { ++byte1; continue; }
+            int nb = 0;
+            for (uint64_t t = m; t; t >>= 8) ++nb;
+            ++by_bytes[nb];
+            row_wide[i / row_len] = 1;
+            item_wide[i / 128] = 1;
+        }
+        zero -= full;   // the wide-list entries are zero in the int64 image
+        for (uint32_t i : wide_idx_[0]) { row_wide[i / row_len] = 1; item_wide[i / 128] = 1; }
+        size_t rows = 0, items = 0;
+        for (auto r : row_wide) rows += r;
+        for (auto r : item_wide) items += r;
+        fprintf(stderr, "[witness] input layer: %zu scalars, rows of %zu; zero %zu, one byte %zu, wider:", n, row_len, zero, byte1);
+        for (int b = 2; b <= 8; ++b) fprintf(stderr, " %dB %zu", b, by_bytes[b]);
+        fprintf(stderr, ", beyond int64 %zu; rows with a wide scalar %zu of %zu, 128-generator chunks with one %zu\n", full, rows, row_wide.size(), items);
+    }
 #endif
 }
 
