@@ -180,16 +180,20 @@ def run_ours(args):
     model, pics = args.model, args.pics
     if args.inflight > 0:
         M = args.inflight
-    else:   # up to six provers per GPU, bounded by the host's memory: ~8 GB of RAM (circuit + witness of vgg11, more with several pictures) per prover
+    else:   # up to --max-inflight provers per GPU, bounded by the host's memory: ~8 GB of RAM (circuit + witness of vgg11, more with several pictures) per prover
         try:
             avail_gb = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) / 1e6
         except Exception:
             avail_gb = 64
         per_gb = 1 if model == "lenet" else 8 * (1 if pics == 1 else 1.5 * pics) * (1.5 if model == "vgg16" else 1)
-        M = max(1, min(6, int(avail_gb * 0.5 / (world * per_gb))))
-    # more prover threads than cores to spin on: the waits for the GPU sleep instead (rt.hpp: ZK_BLOCKING_SYNC); read when the library first waits
-    if "ZK_BLOCKING_SYNC" not in os.environ and M * world * 2 > (os.cpu_count() or 2):
-        os.environ["ZK_BLOCKING_SYNC"] = "1"
+        m_max = max(1, min(args.max_inflight, int(avail_gb * 0.5 / (world * per_gb))))
+        rounds = -(-args.steps // m_max)            # the K proofs of the timed region are dealt round-robin: as few rounds as m_max allows,
+        M = max(1, -(-args.steps // rounds))        # then the smallest number of provers that still does it in that many (even shares)
+    # A prover thread needs ~25 ms of host time per vgg11 proof and waits for the GPU the rest of the time.  With fewer cores than waiting
+    # threads the waits poll with sched_yield instead of spinning inside the driver (rt.hpp: ZK_HOST_WAIT; measured on 4 cores with six
+    # provers: 41.8 proofs/s against 39.0 spinning and 37.4 sleeping); read when the library first waits
+    if "ZK_HOST_WAIT" not in os.environ and "ZK_BLOCKING_SYNC" not in os.environ and M * world * 2 > (os.cpu_count() or 2):
+        os.environ["ZK_HOST_WAIT"] = "yield"
     config = NETWORKS.get(model, args.network)
     lib = zkcnn_b200.load()
     # M independent provers per GPU (own zk_ctx, own stream, own witness): M proofs in flight.  Session 0 of rank 0 proves the golden image
@@ -425,7 +429,7 @@ def run_ours(args):
                                     " (BASELINE config 5: batched pictures, FFT-convolution path)" if pics > 1 else "")),
                        "arithmetic": "exact modular integer arithmetic on 32-bit limbs: BLS12-381 Fr (255-bit) and Fp (381-bit) in Montgomery form",
                        "network": config, "pictures_per_proof": pics, "input_layer": st0["input_size"], "layers": st0["n_layers"], "generators": "non-degenerate (G * challenge)",
-                       "proofs_in_flight_per_gpu": M, "host_wait": "sleeping (blocking-sync events)" if os.environ.get("ZK_BLOCKING_SYNC", "0") not in ("", "0") else "spinning (cudaStreamSynchronize)",
+                       "proofs_in_flight_per_gpu": M, "host_wait": {"yield": "polling an event with sched_yield", "block": "sleeping (blocking-sync events)"}.get(os.environ.get("ZK_HOST_WAIT", "block" if os.environ.get("ZK_BLOCKING_SYNC", "0") not in ("", "0") else ""), "spinning (cudaStreamSynchronize)"), "host_cores": os.cpu_count(),
                        "rounds": "one device call per sumcheck round" if args.round_by_round else "one device call per sumcheck phase (challenges of a phase are drawn before its rounds, as in src/verifier.cpp:156-160)",
                        "l2": "tables larger than L2 (2^24 x 32 B witness, 537 MB)", "parallelism": f"one proof stream per GPU x{world} ({M} provers in flight each, distinct pictures), final all-gather of all K proofs of every rank",
                        "timer": "host clock around synchronous API calls, barrier + cuda synchronize on both sides; value and e2e un-instrumented; per-kernel-class device "
@@ -572,6 +576,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=0,
                     help="independent provers (own context, stream and witness) per GPU, each on its own host thread; 0 = 6, or fewer when the box has less than two host "
                          "cores per prover thread")
+    ap.add_argument("--max-inflight", type=int, default=10, help="upper bound of the default number of provers per GPU (--inflight 0)")
     ap.add_argument("--network", default=VGG11)
     ap.add_argument("--e2e", default="image", choices=["image", "upload"],
                     help="image: a distinct picture per step, witness regenerated on the device (default); upload: the host-built witness re-uploaded every step")

@@ -74,7 +74,8 @@ int zk_profile_msm_ops(zk_ctx *ctx, uint64_t *out);
  *   "cubic_max_grid"   (none)   cap on the CTAs of a K2 launch (tests: several iterations per thread on small tables)
  *   "cubic_factored_min_iters" (4) k_round_cubic switches to the factored form from this many output pairs per thread
  *   "msm_few_rows_chunk" (2048) (generator, window) entries per work item of the bucket kernels for MSMs of at most 8 rows
- *   "msm_split" (1)      MSMs of at most 8 rows as accumulate / merge / reduce launches; 0: the self-contained bucket kernel */
+ *   "msm_split" (1)      MSMs of at most 8 rows as accumulate / merge / reduce launches; 0: the self-contained bucket kernel
+ *   "msm_host_finish" (1) opening rounds: the last 14 point operations and the normalisation of the two points on the host */
 int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value);
 
 /* page-lock / unlock a caller-owned host buffer so that uploads from it are direct DMA (cudaHostRegister) */
@@ -179,6 +180,12 @@ int zk_poly_init_bullet_prove(zk_ctx *ctx, const uint64_t *lx, uint32_t n_lx, co
 int zk_poly_bullet_prove(zk_ctx *ctx, uint64_t *lcomm, uint64_t *rcomm, uint64_t *ly, uint64_t *ry);  /* :76  */
 int zk_poly_bullet_update(zk_ctx *ctx, const uint64_t *randomness);                           /* :98  */
 int zk_poly_bullet_open(zk_ctx *ctx, uint64_t *out);                                          /* :111 */
+/* Not in the reference: all remaining rounds (bulletProve + bulletUpdate, :76-109) in one device pass, for a caller that has drawn the
+ * randomness of every round beforehand -- the reference's verifier draws it from its RNG independently of the prover's messages
+ * (polyVerifier.cpp:48-50), so the messages are the same.  n_rounds must be the number of rounds left (log2 of the current length);
+ * lcomm / rcomm receive n_rounds points (18 words each), ly / ry n_rounds scalars.  Afterwards only zk_poly_bullet_open remains. */
+int zk_poly_bullet_prove_all(zk_ctx *ctx, const uint64_t *randomness, uint32_t n_rounds, uint64_t *lcomm, uint64_t *rcomm, uint64_t *ly,
+                             uint64_t *ry);
 
 /* ---- verifier side on the device (the caller of the hot path): the wiring predicates of verifier::betaInitPhase1/2
  * and predicatePhase1/2 (src/verifier.cpp:36-123) and the input-layer term gr (:307-325), computed from the VERIFIER's challenges with the

@@ -228,6 +228,13 @@ def case_hyrax_kat(lib, kat):
             assert fr_from_words([ly, ry]) == [H(rd["ly"]), H(rd["ry"])]
             ctx.poly_bullet_update(fr_to_words([H(rd["randomness"])])[0])
         assert fr_from_words(ctx.poly_bullet_open()) == [H(h["open"])]
+        # the same opening with every round in one device pass (the randomness of all rounds known beforehand)
+        ctx.poly_init_bullet_prove(fr_to_words(x[:lbl]), fr_to_words(x[lbl:]))
+        lc, rc, ly, ry = ctx.poly_bullet_prove_all(fr_to_words([H(rd["randomness"]) for rd in h["rounds"]]))
+        for k, rd in enumerate(h["rounds"]):
+            assert g1_from_words([lc[k], rc[k]]) == [P(rd["lcomm"]), P(rd["rcomm"])]
+            assert fr_from_words([ly[k], ry[k]]) == [H(rd["ly"]), H(rd["ry"])]
+        assert fr_from_words(ctx.poly_bullet_open()) == [H(h["open"])]
 
 
 def case_hyrax_vs_port(lib, bl=7, seed=606):
@@ -245,14 +252,24 @@ def case_hyrax_vs_port(lib, bl=7, seed=606):
         assert fr_from_words(ctx.poly_evaluate(fr_to_words(x))) == [hp.evaluate(x)]
         ctx.poly_init_bullet_prove(fr_to_words(x[:lbl]), fr_to_words(x[lbl:]))
         hp.init_bullet_prove(x[:lbl], x[lbl:])
+        want, rhos = [], []
         for _ in range(lbl):
             lc, rc, ly, ry = ctx.poly_bullet_prove()
             wl, wr, wly, wry = hp.bullet_prove()
             assert g1_from_words([lc, rc]) == [wl, wr] and fr_from_words([ly, ry]) == [wly, wry]
+            want.append((wl, wr, wly, wry))
             rho = rng.fr()
+            rhos.append(rho)
             ctx.poly_bullet_update(fr_to_words([rho])[0])
             hp.bullet_update(rho)
-        assert fr_from_words(ctx.poly_bullet_open()) == [hp.bullet_open()]
+        opened = hp.bullet_open()
+        assert fr_from_words(ctx.poly_bullet_open()) == [opened]
+        # every round in one device pass
+        ctx.poly_init_bullet_prove(fr_to_words(x[:lbl]), fr_to_words(x[lbl:]))
+        lc, rc, ly, ry = ctx.poly_bullet_prove_all(fr_to_words(rhos))
+        for k in range(lbl):
+            assert (*g1_from_words([lc[k], rc[k]]), *fr_from_words([ly[k], ry[k]])) == want[k], k
+        assert fr_from_words(ctx.poly_bullet_open()) == [opened]
 
 
 def prove_and_compare(hostlib, model, network, pic_cnt, input_path, seed, flags, golden_name, golden_dir, device=0, tables=False):

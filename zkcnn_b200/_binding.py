@@ -112,6 +112,7 @@ class Lib:
         d.zk_poly_init_bullet_prove.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, C.c_uint32]
         d.zk_poly_bullet_prove.argtypes = [C.c_void_p, _u64p, _u64p, _u64p, _u64p]
         d.zk_poly_bullet_update.argtypes = [C.c_void_p, _u64p]
+        d.zk_poly_bullet_prove_all.argtypes = [C.c_void_p, _u64p, C.c_uint32, _u64p, _u64p, _u64p, _u64p]
         d.zk_poly_bullet_open.argtypes = [C.c_void_p, _u64p]
 
     def version(self):
@@ -298,6 +299,15 @@ class Context:
     def poly_bullet_update(self, r):
         r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
         self._check(self.lib.dll.zk_poly_bullet_update(self.h, _ptr(r)), "zk_poly_bullet_update")
+
+    def poly_bullet_prove_all(self, rands):
+        """every remaining round at once; returns (lcomm[n][18], rcomm[n][18], ly[n][4], ry[n][4])"""
+        rands = np.ascontiguousarray(rands, dtype=np.uint64).reshape(-1, 4)
+        n = len(rands)
+        lc, rc = np.empty((n, 18), dtype=np.uint64), np.empty((n, 18), dtype=np.uint64)
+        ly, ry = np.empty((n, 4), dtype=np.uint64), np.empty((n, 4), dtype=np.uint64)
+        self._check(self.lib.dll.zk_poly_bullet_prove_all(self.h, _ptr(rands), n, _ptr(lc), _ptr(rc), _ptr(ly), _ptr(ry)), "zk_poly_bullet_prove_all")
+        return lc, rc, ly, ry
 
     def poly_bullet_open(self):
         out = np.empty(4, dtype=np.uint64)

@@ -80,8 +80,15 @@ static void msm_prepare_multiples(zk_ctx *ctx, hyrax_t &H) {
     H.mult_ready = true;
 }
 
-// out_dev[k] (normalised) = sum_j scalars[k*n + j] * G_j  for k < n_rows, generators taken from H.table
-static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n, uint32_t n_rows, g1_jac_t *out_dev) {
+// out_dev[k] (normalised) = sum_j scalars[k*n + j] * G_j  for k < n_rows, generators taken from H.table.
+// host_S != nullptr: the caller is about to wait for the stream anyway and wants the points on the host.  When the MSM takes the few-row
+// path, *host_S is set to a pinned array of 8 partial sums per row (copy queued on the stream) that msm_finish_host turns into the
+// normalised points after the wait, and out_dev is NOT written; otherwise *host_S = nullptr and out_dev holds the result as usual.
+// wide_scalars: the caller knows the scalars are full-width field elements (the opening's rows): the bucket kernels take all of them, whatever
+// the number of rows.
+static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n, uint32_t n_rows, g1_jac_t *out_dev, g1_jac_t **host_S = nullptr,
+                    bool wide_scalars = false) {
+    if (host_S) *host_S = nullptr;
     ZK_REQUIRE(H.table_ready && n <= H.n_gens, "MSM: generator table missing or too small");
     msm_configure();
     H.msm_rowinfo.ensure((size_t) (2 * n_rows + 1) * 4);   // [n_rows]: length of the wide-row list; [n_rows + 1 + row]: byte levels of the row (small path)
@@ -89,7 +96,8 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     const uint64_t alg_bytes = n * n_rows * 32 + n * 96 + (uint64_t) n_rows * 144;
     // many rows over one generator set: scalars of up to kSmallBytes bytes go through the small-multiples table, the bucket kernel
     // below only sees what is left (the rows k_msm_small lists as holding wider scalars)
-    const bool small_path = n_rows >= 16 && H.n_gens <= kMultiplesMaxGens;
+    const bool small_path = !wide_scalars && n_rows >= 16 && H.n_gens <= kMultiplesMaxGens;
+    const bool few_rows = n_rows <= 8 || wide_scalars;
     uint32_t n_seg = 0;
     if (small_path) {
         msm_prepare_multiples(ctx, H);
@@ -112,11 +120,11 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
     }
     // work items of the bucket kernel: (row, chunk of generators), all windows of a chunk in one item.  Few rows: smaller chunks, more CTAs
-    const uint32_t chunk = n_rows <= 8 ? std::max<uint32_t>(1, std::min<uint32_t>(ctx->msm_few_rows_chunk / kMsmWindows, kMsmGensPerItem)) : kMsmGensPerItem;
+    const uint32_t chunk = few_rows ? std::max<uint32_t>(1, std::min<uint32_t>(ctx->msm_few_rows_chunk / kMsmWindows, kMsmGensPerItem)) : kMsmGensPerItem;
     const uint32_t n_chunks = (uint32_t) ((n + chunk - 1) / chunk);
     const bool waited = H.table_pending;   // a cross-stream wait sits between the next launch and its predecessor: plain launch then
     msm_wait_table(ctx, H);
-    if (!small_path && ctx->msm_split && n_rows <= 8 && (uint64_t) n_rows * n_chunks <= 4096) {
+    if (!small_path && ctx->msm_split && few_rows && (uint64_t) n_rows * n_chunks <= 4096) {
         // few rows (the opening): accumulate / merge / reduce as three lean launches (hyrax_kernels.cuh)
         const uint32_t n_items = n_rows * n_chunks;
         H.msm_buckets.ensure((size_t) n_items * kMsmBuckets * sizeof(g1_jac_t));
@@ -136,7 +144,14 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         else ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, alg_bytes, k_msm_bucket_fill, dim3(fgrid), dim3(kFillThreads), sizeof(msm_fill_smem_t), F);
         ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_bucket_merge, dim3(n_rows * kMsmBuckets / (kBlock / 32)), dim3(kBlock), 0, H.msm_buckets.as<g1_jac_t>(),
                        H.msm_item_entries.as<uint32_t>(), n_rows, n_chunks, H.msm_merged.as<g1_jac_t>());
-        ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_bucket_reduce, dim3(n_rows), dim3(kBlock), 0, H.msm_merged.as<g1_jac_t>(), n_rows, out_dev);
+        if (host_S && ctx->msm_host_finish && n_rows <= 8) {
+            H.msm_S.ensure((size_t) n_rows * 8 * sizeof(g1_jac_t));
+            if (!ctx->msm_S_h) ctx->msm_S_h = static_cast<g1_jac_t *>(rt::hmalloc_pinned((size_t) 8 * 8 * sizeof(g1_jac_t)));
+            ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_bucket_reduce, dim3(n_rows), dim3(kBlock), 0, H.msm_merged.as<g1_jac_t>(), n_rows, out_dev, H.msm_S.as<g1_jac_t>());
+            rt::d2h(ctx->msm_S_h, H.msm_S.p, (size_t) n_rows * 8 * sizeof(g1_jac_t), ctx->stream);
+            *host_S = ctx->msm_S_h;
+        } else
+            ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_bucket_reduce, dim3(n_rows), dim3(kBlock), 0, H.msm_merged.as<g1_jac_t>(), n_rows, out_dev, (g1_jac_t *) nullptr);
         return;
     }
     H.msm_out.ensure((size_t) n_rows * n_chunks * sizeof(g1_jac_t));
@@ -287,13 +302,15 @@ int zk_poly_bullet_prove(zk_ctx *ctx, uint64_t *lcomm, uint64_t *rcomm, uint64_t
     ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_bullet_scalars, dim3(grid_for(lsize)), dim3(kBlock), 0, H.a.as<fr_t>(), H.coef.as<fr_t>(), lsize, m, H.scal.as<fr_t>());
     rt::dbuf &pts = H.pts_out;
     pts.ensure(2 * sizeof(g1_jac_t));
-    msm_run(ctx, H, H.scal.as<fr_t>(), lsize, 2, pts.as<g1_jac_t>());
+    g1_jac_t *S_h = nullptr;
+    msm_run(ctx, H, H.scal.as<fr_t>(), lsize, 2, pts.as<g1_jac_t>(), &S_h, true);
     // ly, ry
     ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_dot2, dim3(1), dim3(kBlock), 0, H.a.as<fr_t>(), H.L.as<fr_t>(), h, ctx->round_out.as<fr_t>());
     rt::d2h(ctx->h_out, ctx->round_out.p, 2 * sizeof(fr_t), ctx->stream);
     g1_jac_t hp[2];
-    rt::d2h(hp, pts.p, sizeof hp, ctx->stream);
+    if (!S_h) rt::d2h(hp, pts.p, sizeof hp, ctx->stream);
     rt::sync(ctx->stream);
+    if (S_h) { hp[0] = msm_finish_host(S_h); hp[1] = msm_finish_host(S_h + 8); }   // the last 14 point operations + the inversion of each point
     H.scale = H.scale * (fr_t::one() - H.t.back()).inverse();
     fr_store(ly, ctx->h_out[0] * H.scale);
     fr_store(ry, ctx->h_out[1] * H.scale);
@@ -320,6 +337,56 @@ int zk_poly_bullet_update(zk_ctx *ctx, const uint64_t *randomness) {   // polyPr
     H.cur = h;
     ++H.round;
     H.t.pop_back();
+    ZK_API_END
+}
+
+// Every round of the inner-product argument in one device pass (bulletProve + bulletUpdate of polyProver.cpp:76-109, n_rounds times).
+// The reference's verifier draws a round's randomness from its RNG after the round's message (polyVerifier.cpp:48-50) but independently of
+// it, so a caller that draws the randomness of all rounds first gets the same messages: the folds of `a` and of the generator coefficients
+// run back to back, the 2 * n_rounds MSMs over the original generators become ONE bucket MSM of 2 * n_rounds rows, and the host waits once.
+int zk_poly_bullet_prove_all(zk_ctx *ctx, const uint64_t *randomness, uint32_t n_rounds, uint64_t *lcomm, uint64_t *rcomm, uint64_t *ly, uint64_t *ry) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(ctx && ctx->hy.bound && randomness && lcomm && rcomm && ly && ry && n_rounds >= 1 && n_rounds <= 30, "bulletProveAll: bad arguments");
+    hyrax_t &H = ctx->hy;
+    ZK_REQUIRE(H.cur == (1u << n_rounds) && H.t.size() == n_rounds, "bulletProveAll: n_rounds must be the number of rounds left");
+    rt::bind(ctx->device, ctx->stream, ctx->aux_stream, ctx->copy_stream);
+    ensure_round_scratch(ctx);
+    const uint32_t lsize = 1u << H.l_bits;
+    H.scal.ensure((size_t) 2 * n_rounds * lsize * sizeof(fr_t));
+    H.bullet_dots.ensure((size_t) 2 * n_rounds * sizeof(fr_t));
+    uint32_t m = H.cur;
+    for (uint32_t k = 0; k < n_rounds; ++k) {
+        const uint32_t h = m >> 1;
+        const fr_t r = fr_load(randomness + 4 * (size_t) k);
+        const fr_t rinv = r.inverse();
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_bullet_scalars, dim3(grid_for(lsize)), dim3(kBlock), 0, H.a.as<fr_t>(), H.coef.as<fr_t>(), lsize, m,
+                       H.scal.as<fr_t>() + (size_t) 2 * k * lsize);
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_dot2, dim3(1), dim3(kBlock), 0, H.a.as<fr_t>(), H.L.as<fr_t>(), h, H.bullet_dots.as<fr_t>() + 2 * k);
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_bullet_fold, dim3(grid_for(h)), dim3(kBlock), 0, H.a.as<fr_t>(), H.a_next.as<fr_t>(), h, r);
+        std::swap(H.a, H.a_next);
+        uint32_t bit = 0;
+        while ((1u << bit) < h) ++bit;
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_OTHER, 0, k_bullet_coef, dim3(grid_for(lsize)), dim3(kBlock), 0, H.coef.as<fr_t>(), lsize, bit, rinv);
+        m = h;
+    }
+    rt::dbuf &pts = H.pts_out;
+    pts.ensure((size_t) 2 * n_rounds * sizeof(g1_jac_t));
+    msm_run(ctx, H, H.scal.as<fr_t>(), lsize, 2 * n_rounds, pts.as<g1_jac_t>(), nullptr, true);
+    std::vector<fr_t> dots(2 * n_rounds);
+    std::vector<g1_jac_t> hp(2 * n_rounds);
+    d2h_staged(ctx, dots.data(), H.bullet_dots.p, dots.size() * sizeof(fr_t));
+    d2h_staged(ctx, hp.data(), pts.p, hp.size() * sizeof(g1_jac_t));
+    for (uint32_t k = 0; k < n_rounds; ++k) {
+        H.scale = H.scale * (fr_t::one() - H.t.back()).inverse();
+        H.t.pop_back();
+        fr_store(ly + 4 * (size_t) k, dots[2 * k] * H.scale);
+        fr_store(ry + 4 * (size_t) k, dots[2 * k + 1] * H.scale);
+        memcpy(lcomm + 18 * (size_t) k, &hp[2 * k], sizeof(g1_jac_t));
+        memcpy(rcomm + 18 * (size_t) k, &hp[2 * k + 1], sizeof(g1_jac_t));
+    }
+    H.cur = 1;
+    H.round += n_rounds;
     ZK_API_END
 }
 

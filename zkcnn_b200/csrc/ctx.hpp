@@ -87,13 +87,13 @@ struct hyrax_t {
     bool mult_ready = false;
     uint64_t gens_hash = 0;
     std::vector<uint8_t> gens_host;   // the generator set the tables were built for (confirms a hash hit)
-    rt::dbuf L, R, RZ, a, a_next, coef, scal;
+    rt::dbuf L, R, RZ, a, a_next, coef, scal, bullet_dots;
     std::vector<fr_t> t;       // remaining opening point (lx)
     fr_t scale;
     uint32_t cur = 0;          // current length of bullet_a
     uint32_t round = 0;
     std::vector<fr_t> rinv;    // 1 / randomness of the finished rounds
-    rt::dbuf msm_out, msm_small, msm_rowinfo, msm_wide_rows, msm_buckets, msm_item_entries, msm_merged, pts_out;
+    rt::dbuf msm_out, msm_small, msm_rowinfo, msm_wide_rows, msm_buckets, msm_item_entries, msm_merged, msm_S, pts_out;
 };
 
 }  // namespace zk
@@ -128,6 +128,7 @@ struct zk_ctx {
     // scratch
     zk::rt::dbuf half[4], d_r, partials, counters, round_acc, cubic_acc, round_state, round_out, gate_partial[2], dense_partial, vres_scratch, scalar_slot;
     zk::fr_t *h_out = nullptr;  // pinned mirror of round_out
+    zk::g1_jac_t *msm_S_h = nullptr;   // pinned: partial sums of a few-row MSM finished on the host (msm_finish_host)
     // result mailbox of the per-round kernels: mapped pinned host memory the last CTA writes directly, followed by a
     // sequence number; the host spins on the sequence number instead of copying + synchronising the stream
     zk::fr_t *res_h = nullptr, *res_d = nullptr;          // [32] host / device view
@@ -149,6 +150,7 @@ struct zk_ctx {
     uint32_t cubic_tma_enabled = 1;          // DOT_PROD fold rounds on large tables use k_round_cubic_tma
     uint32_t cubic_max_grid = 1u << 20;       // cap on the CTAs of a K2 launch (tests: forces several iterations per thread on small tables)
     uint32_t cubic_factored_min_iters = 4;   // k_round_cubic: factored form from this many output pairs per thread
+    uint32_t msm_host_finish = 1;            // opening rounds: the last 14 point operations + the normalisation of the two points on the host
     uint32_t msm_split = 1;                  // MSMs of at most 8 rows: accumulate / merge / reduce launches (k_msm_bucket_*) instead of k_msm_window
     uint32_t msm_few_rows_chunk = 2048;      // (generator, window) entries per work item of k_msm_window when an MSM has at most 8 rows (32 per generator)
     std::vector<std::pair<uint32_t, zk::rt::dbuf>> phi_pw;  // cached powers of roots of unity, key = n * 2 + is_ifft

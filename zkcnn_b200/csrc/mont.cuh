@@ -251,6 +251,48 @@ template <class C> struct alignas(16) mont_t {
     static ZK_HD __forceinline__ void mul_portable(uint32_t *r, const uint32_t *a, const uint32_t *b) {
         const uint32_t *p = C::mod();
         uint32_t t[N + 1];
+#if !ZK_ON_DEVICE && defined(__SIZEOF_INT128__)
+        // host code: the same interleaved Montgomery multiplication on 64-bit limbs (the quotient digits of a + m * p == 0 mod 2^(32N) are
+        // unique, so the unreduced result equals the 32-bit loop's); ~5x faster, which the host-side finish of the opening MSMs relies on
+        static_assert(N % 2 == 0, "64-bit host path packs pairs of limbs");
+        {
+            typedef unsigned __int128 u128;
+            constexpr int M = N / 2;
+            uint64_t A[M], B[M], P[M], T[M + 2];
+            for (int i = 0; i < M; ++i) {
+                A[i] = (uint64_t) a[2 * i] | ((uint64_t) a[2 * i + 1] << 32);
+                B[i] = (uint64_t) b[2 * i] | ((uint64_t) b[2 * i + 1] << 32);
+                P[i] = (uint64_t) p[2 * i] | ((uint64_t) p[2 * i + 1] << 32);
+            }
+            for (int i = 0; i < M + 2; ++i) T[i] = 0;
+            uint64_t pinv = (uint64_t) (0u - C::INV);   // p^-1 mod 2^32 (INV is -p^-1), one Newton step doubles the precision
+            pinv *= 2 - P[0] * pinv;
+            const uint64_t inv64 = 0 - pinv;
+            for (int i = 0; i < M; ++i) {
+                u128 c = 0;
+                for (int j = 0; j < M; ++j) {
+                    const u128 x = (u128) A[j] * B[i] + T[j] + c;
+                    T[j] = (uint64_t) x;
+                    c = x >> 64;
+                }
+                u128 top = (u128) T[M] + c;
+                T[M] = (uint64_t) top;
+                T[M + 1] = (uint64_t) (top >> 64);
+                const uint64_t m = T[0] * inv64;
+                c = ((u128) m * P[0] + T[0]) >> 64;
+                for (int j = 1; j < M; ++j) {
+                    const u128 x = (u128) m * P[j] + T[j] + c;
+                    T[j - 1] = (uint64_t) x;
+                    c = x >> 64;
+                }
+                top = (u128) T[M] + c;
+                T[M - 1] = (uint64_t) top;
+                T[M] = T[M + 1] + (uint64_t) (top >> 64);
+            }
+            for (int i = 0; i < M; ++i) { t[2 * i] = (uint32_t) T[i]; t[2 * i + 1] = (uint32_t) (T[i] >> 32); }
+            t[N] = (uint32_t) T[M];
+        }
+#else
 #pragma unroll
         for (int i = 0; i <= N; ++i) t[i] = 0;
 #pragma unroll
@@ -275,6 +317,7 @@ template <class C> struct alignas(16) mont_t {
             t[N - 1] = (uint32_t) top;
             t[N] = (uint32_t) (top >> 32);
         }
+#endif
         // result < 2p: one conditional subtraction
         uint32_t d[N];
         int64_t bw = 0;

@@ -1,6 +1,7 @@
 // See polyProver.hpp.  Mirrors 3rd/hyrax-bls12-381/src/polyProver.cpp; all arithmetic is behind the C ABI.
 #include "polyProver.hpp"
 #include <cmath>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
@@ -74,15 +75,43 @@ void polyProver::initBulletProve(const vector<Fr> &_lx, const vector<Fr> &_rx) {
     pt.stop();
 }
 
-void polyProver::bulletProve(G1 &lcomm, G1 &rcomm, Fr &ly, Fr &ry) {   // polyProver.cpp:76-96
+void polyProver::bulletProveAll(const vector<Fr> &randomness) {
+    if (randomness.empty()) return;
     pt.start();
-    check(zk_poly_bullet_prove(ctx_, w(lcomm), w(rcomm), w(ly), w(ry)), "zk_poly_bullet_prove");
+    const size_t n = randomness.size();
+    vector<G1> lc(n), rc(n);
+    vector<Fr> ly(n), ry(n);
+    check(zk_poly_bullet_prove_all(ctx_, w(randomness[0]), (uint32_t) n, w(lc[0]), w(rc[0]), w(ly[0]), w(ry[0])), "zk_poly_bullet_prove_all");
     pt.stop();
+    ahead_.resize(n);
+    for (size_t k = 0; k < n; ++k) ahead_[k] = {lc[k], rc[k], ly[k], ry[k], randomness[k]};
+    ahead_next_ = 0;
+    ahead_update_due_ = false;
+}
+
+void polyProver::bulletProve(G1 &lcomm, G1 &rcomm, Fr &ly, Fr &ry) {   // polyProver.cpp:76-96
+    if (ahead_next_ < ahead_.size()) {
+        if (ahead_update_due_) throw std::logic_error("polyProver: bulletProve twice without bulletUpdate");
+        const round_msg &m = ahead_[ahead_next_];
+        lcomm = m.lcomm; rcomm = m.rcomm; ly = m.ly; ry = m.ry;
+        ahead_update_due_ = true;
+    } else {
+        pt.start();
+        check(zk_poly_bullet_prove(ctx_, w(lcomm), w(rcomm), w(ly), w(ry)), "zk_poly_bullet_prove");
+        pt.stop();
+    }
     ps += (ZK_G1_BYTES + ZK_FR_BYTES) * 2;
     if (tr_) { tr_->put_g1(w(lcomm)); tr_->put_g1(w(rcomm)); tr_->put_fr(w(ly)); tr_->put_fr(w(ry)); }
 }
 
 void polyProver::bulletUpdate(const Fr &randomness) {   // polyProver.cpp:98-109
+    if (ahead_update_due_) {   // folded on the device already, with the randomness announced to bulletProveAll
+        if (memcmp(&randomness, &ahead_[ahead_next_].randomness, sizeof(Fr)) != 0)
+            throw std::logic_error("polyProver: bulletUpdate with another randomness than the one given to bulletProveAll");
+        ++ahead_next_;
+        ahead_update_due_ = false;
+        return;
+    }
     pt.start();
     check(zk_poly_bullet_update(ctx_, w(randomness)), "zk_poly_bullet_update");
     pt.stop();

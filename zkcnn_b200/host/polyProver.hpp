@@ -44,6 +44,10 @@ public:
     void bulletUpdate(const Fr &randomness);
     Fr bulletOpen();
     const vector<G1> &getGens() const;
+    // Not in the reference: every remaining round in one device pass (zk_poly_bullet_prove_all) for a verifier that has drawn the
+    // randomness of all rounds beforehand.  The messages are kept here: the bulletProve calls that follow hand them out in order and
+    // bulletUpdate only checks that the verifier uses the randomness it announced.
+    void bulletProveAll(const vector<Fr> &randomness);
 
 private:
     void check(int rc, const char *what) const;
@@ -54,6 +58,10 @@ private:
     timer pt;
     unsigned long long ps;
     zkcnn_b200::Transcript *tr_;
+    struct round_msg { G1 lcomm, rcomm; Fr ly, ry, randomness; };
+    vector<round_msg> ahead_;      // rounds computed by bulletProveAll and not yet handed out
+    size_t ahead_next_ = 0;
+    bool ahead_update_due_ = false;
 };
 }  // namespace hyrax_bls12_381
 

@@ -167,6 +167,16 @@ void prover::buildCompactWitness() {
         size_t rows = 0, items = 0;
         for (auto r : row_wide) rows += r;
         for (auto r : item_wide) items += r;
+        size_t ones = 0, bit_blocks = 0, bit_block_ones = 0, nonempty_bit_blocks = 0;
+        for (size_t i = 0; i + 8 <= n; i += 8) {
+            bool pure = true;
+            size_t c = 0;
+            for (size_t k = 0; k < 8; ++k) { const int64_t x = compact_[0][i + k]; pure = pure && (x == 0 || x == 1); c += x == 1; }
+            if (pure) { ++bit_blocks; bit_block_ones += c; nonempty_bit_blocks += c != 0; }
+        }
+        for (size_t i = 0; i < n; ++i) ones += compact_[0][i] == 1;
+        fprintf(stderr, "[witness] ones %zu; aligned blocks of 8 scalars that hold only 0/1: %zu of %zu (%zu non-empty, %zu ones inside)\n", ones, bit_blocks, n / 8,
+                nonempty_bit_blocks, bit_block_ones);
         fprintf(stderr, "[witness] input layer: %zu scalars, rows of %zu; zero %zu, one byte %zu, wider:", n, row_len, zero, byte1);
         for (int b = 2; b <= 8; ++b) fprintf(stderr, " %dB %zu", b, by_bytes[b]);
         fprintf(stderr, ", beyond int64 %zu; rows with a wide scalar %zu of %zu, 128-generator chunks with one %zu\n", full, rows, row_wide.size(), items);

@@ -136,10 +136,17 @@ bool polyVerifier::bulletVerify(vector<G1> g, vector<Fr> t, G1 comm, Fr y) {   /
     Fr ly, ry;
     const size_t logn = t.size();
     if (logn == 0) throw std::logic_error("polyVerifier: empty opening point");
-    for (;;) {
+    vector<Fr> ahead;
+    if (batchRounds) {
+        ahead.resize(logn);
+        for (auto &r : ahead) r.setByCSPRNG();
+        p.bulletProveAll(ahead);
+    }
+    for (size_t round = 0;; ++round) {
         p.bulletProve(lcomm, rcomm, ly, ry);
         Fr rho, irho;
-        rho.setByCSPRNG();
+        if (batchRounds) rho = ahead[round];
+        else rho.setByCSPRNG();
         Fr::inv(irho, rho);
         p.bulletUpdate(rho);
         if (check_points) {
@@ -205,6 +212,7 @@ bool verifier::verify() {   // src/verifier.cpp:118-130
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t1 = now();
     poly_v.reset(new hyrax_bls12_381::polyVerifier(p->commitInput(generators), generators, p->context(), checkPredicates));
+    poly_v->batchRounds = batchRounds && !fiatShamir;
     const auto t2 = now();
     const bool ok1 = verifyInnerLayers();
     const auto t3 = now();

@@ -13,6 +13,10 @@ public:
     polyVerifier(polyProver &_p, const vector<G1> &_gens, zk_ctx *ctx, bool check_points);
     bool verify(const vector<Fr> &_x, const Fr &RZL);
     double getVT() { return vt.elapse_sec() - p.getPT(); }
+    // draw the randomness of every opening round first and let the prover run all rounds in one device pass (polyProver::bulletProveAll);
+    // the draws come from the same stream in the same order, so the transcript is the one of the round-by-round exchange.  Off in
+    // Fiat-Shamir mode, where a round's randomness depends on the round's message.
+    bool batchRounds = false;
 private:
     bool bulletVerify(vector<G1> g, vector<Fr> t, G1 comm, Fr y);
     polyProver &p;
