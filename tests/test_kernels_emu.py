@@ -6,6 +6,13 @@ def test_fr_vec_ops(emu_lib):
     cases.case_fr_vec_ops(emu_lib)
 
 
+def test_selftest(emu_lib):
+    """the device self-test's identities on the host build of the same arithmetic (multiplier variants, lazy sums, the three inversions)"""
+    from zkcnn_b200._binding import Context
+    with Context(emu_lib) as ctx:
+        ctx.selftest(seed=7, n=1024)
+
+
 def test_fr_kat(emu_lib, kat):
     cases.case_fr_kat(emu_lib, kat)
 

@@ -19,6 +19,7 @@ static void msm_configure() {
     static const bool done = [] {   // (thread-safe: several contexts may start at once)
         rt::check(cudaFuncSetAttribute(k_msm_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(msm_smem_t)),
                   "cudaFuncSetAttribute(k_msm_window)");
+        rt::check(cudaFuncSetAttribute(k_msm_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(msm_small_smem_t)), "cudaFuncSetAttribute(k_msm_small)");
         rt::check(cudaFuncSetAttribute(k_msm_bucket_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(msm_fill_smem_t)),
                   "cudaFuncSetAttribute(k_msm_bucket_fill)");
         return true;
@@ -101,9 +102,10 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     uint32_t n_seg = 0;
     if (small_path) {
         msm_prepare_multiples(ctx, H);
-        const uint32_t seg_len = (uint32_t) std::min<uint64_t>(n, 2048);
+        const uint32_t seg_len = (uint32_t) std::min<uint64_t>(n, ctx->msm_small_seg);
         n_seg = (uint32_t) ((n + seg_len - 1) / seg_len);
-        H.msm_small.ensure((size_t) n_rows * n_seg * kSmallBytes * sizeof(g1_jac_t));
+        H.msm_small.ensure((size_t) n_rows * n_seg * 32 * sizeof(g1_jac_t));
+        H.msm_small_hi.ensure((size_t) n_rows * n_seg * (kSmallBytes - 1) * sizeof(g1_jac_t));
         H.msm_wide_rows.ensure((size_t) n_rows * 4);
         msm_small_args_t S;
         S.scalars = scalars_dev;
@@ -111,11 +113,12 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         S.n = n;
         S.n_rows = n_rows; S.n_seg = n_seg; S.seg_len = seg_len;
         S.partial = H.msm_small.as<g1_jac_t>();
+        S.partial_hi = H.msm_small_hi.as<g1_jac_t>();
         S.rowinfo = H.msm_rowinfo.as<uint32_t>();
         S.wide_rows = H.msm_wide_rows.as<uint32_t>();
         S.ops = ctx->prof_on ? prof_ops_counter(ctx) : nullptr;
         const uint64_t warps = (uint64_t) n_rows * n_seg;
-        ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, alg_bytes, k_msm_small, dim3((uint32_t) ((warps + kSmallWarps - 1) / kSmallWarps)), dim3(kSmallWarps * 32), 0, S);
+        ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, alg_bytes, k_msm_small, dim3((uint32_t) ((warps + kSmallWarps - 1) / kSmallWarps)), dim3(kSmallWarps * 32), sizeof(msm_small_smem_t), S);
     } else {
         ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
     }
@@ -173,8 +176,10 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     if (waited) ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(grid), dim3(kBlock), sizeof(msm_smem_t), A);
     else ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(grid), dim3(kBlock), sizeof(msm_smem_t), A);
     ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kSmallWarps - 1) / kSmallWarps), dim3(kSmallWarps * 32), 0,
-                 small_path ? H.msm_small.as<g1_jac_t>() : (const g1_jac_t *) nullptr, n_seg, H.msm_out.as<g1_jac_t>(), n_chunks,
+                 small_path ? H.msm_small.as<g1_jac_t>() : (const g1_jac_t *) nullptr, small_path ? H.msm_small_hi.as<g1_jac_t>() : (const g1_jac_t *) nullptr, n_seg,
+                 H.msm_out.as<g1_jac_t>(), n_chunks,
                  H.msm_rowinfo.as<uint32_t>(), small_path ? 1u : 0u, n_rows, out_dev);
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_g1_normalize_rows, dim3((n_rows + 127) / 128), dim3(128), 0, out_dev, n_rows);
 }
 
 static void hyrax_bind(zk_ctx *ctx, const fr_t *Z, uint32_t bit_length, const uint64_t *gens, uint32_t n_gens) {

@@ -93,7 +93,7 @@ struct hyrax_t {
     uint32_t cur = 0;          // current length of bullet_a
     uint32_t round = 0;
     std::vector<fr_t> rinv;    // 1 / randomness of the finished rounds
-    rt::dbuf msm_out, msm_small, msm_rowinfo, msm_wide_rows, msm_buckets, msm_item_entries, msm_merged, msm_S, pts_out;
+    rt::dbuf msm_out, msm_small, msm_small_hi, msm_rowinfo, msm_wide_rows, msm_buckets, msm_item_entries, msm_merged, msm_S, pts_out;
 };
 
 }  // namespace zk
@@ -150,6 +150,7 @@ struct zk_ctx {
     uint32_t cubic_tma_enabled = 1;          // DOT_PROD fold rounds on large tables use k_round_cubic_tma
     uint32_t cubic_max_grid = 1u << 20;       // cap on the CTAs of a K2 launch (tests: forces several iterations per thread on small tables)
     uint32_t cubic_factored_min_iters = 4;   // k_round_cubic: factored form from this many output pairs per thread
+    uint32_t msm_small_seg = 1024;           // scalars per warp of k_msm_small (one row segment)
     uint32_t msm_host_finish = 1;            // opening rounds: the last 14 point operations + the normalisation of the two points on the host
     uint32_t msm_split = 1;                  // MSMs of at most 8 rows: accumulate / merge / reduce launches (k_msm_bucket_*) instead of k_msm_window
     uint32_t msm_few_rows_chunk = 2048;      // (generator, window) entries per work item of k_msm_window when an MSM has at most 8 rows (32 per generator)

@@ -685,6 +685,15 @@ __global__ void __launch_bounds__(kBlock) k_selftest(uint64_t seed, uint32_t n, 
         bad += ((c - d) + d) != c;
         bad += (c * (d + c)) != (x + c * c);
     }
+    if (i < 512) {   // inversion: the binary algorithm (host), plain Fermat and windowed Fermat (device) agree, and x * x^-1 == 1
+        bad += a.inverse_fermat_w4() != a.inverse_fermat();
+        bad += c.inverse_fermat_w4() != c.inverse_fermat();
+        bad += a.inverse() != a.inverse_fermat();
+        bad += c.inverse() != c.inverse_fermat();
+        bad += !a.is_zero() && (a * a.inverse()) != fr_t::one();
+        bad += !c.is_zero() && (c * c.inverse()) != fp_t::one();
+        bad += !fr_t::zero().inverse().is_zero();
+    }
     if (bad) atomicAdd(mismatches, bad);
 }
 

@@ -654,6 +654,29 @@ template <class C> struct alignas(16) mont_t {
     }
     // multiplicative inverse by Fermat (0 -> 0); kept as the cross-check of inverse()
     ZK_HD inline mont_t inverse_fermat() const { return pow_limbs(C::modm2()); }
+    // the same with 4-bit windows: 4 squarings + at most one multiplication per nibble of p - 2 (~32 N squarings + ~8 N multiplications).
+    // Tried as the device's inverse() (-DZK_DEVICE_FERMAT_INVERSE) and dropped: normalising one point per thread takes 498 us with it and
+    // 521 us with the binary algorithm below, the kernels that invert inside a longer chain got slower (k_g1_to_affine 211 -> 676 us,
+    // k_msm_bucket_reduce 515 -> 869 us).  Kept as a third opinion for the self-test.
+    ZK_HD inline mont_t inverse_fermat_w4() const {
+        mont_t pw[16];
+        pw[0] = one();
+        pw[1] = *this;
+        for (int i = 2; i < 16; ++i) pw[i] = pw[i - 1] * *this;
+        const uint32_t *e = C::modm2();
+        mont_t acc = one();
+        bool started = false;
+        for (int i = N - 1; i >= 0; --i)
+            for (int b = 28; b >= 0; b -= 4) {
+                const uint32_t nib = (e[i] >> b) & 15u;
+                if (started) acc = acc.sqr().sqr().sqr().sqr();
+                if (nib) {
+                    acc = started ? acc * pw[nib] : pw[nib];
+                    started = true;
+                }
+            }
+        return acc;
+    }
 
     // ---- raw multi-limb helpers for the binary inversion ---------------------------------------------------------------
     static ZK_HD __forceinline__ bool raw_is_one(const uint32_t *a) {
@@ -703,6 +726,9 @@ template <class C> struct alignas(16) mont_t {
     // instructions for Fp).  Field elements are unique, so the value equals mcl's Fr::inv / Fp::inv.
     ZK_HD inline mont_t inverse() const {
         if (is_zero()) return *this;
+#if ZK_ON_DEVICE && defined(ZK_DEVICE_FERMAT_INVERSE)
+        return inverse_fermat_w4();   // measured slower on a B200 in every kernel that inverts (one dependent Fp multiplication is ~1 us for a lone warp)
+#endif
         uint32_t pm[N], u[N], w[N], x1[N], x2[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) { pm[i] = C::mod()[i]; u[i] = v[i]; w[i] = pm[i]; x1[i] = i == 0 ? 1u : 0u; x2[i] = 0u; }

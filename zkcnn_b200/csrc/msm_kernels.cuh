@@ -61,17 +61,20 @@ __global__ void __launch_bounds__(128) k_msm_multiples_build(const g1_aff_t *gen
 }
 
 // ---- one warp per (row, segment): comm partial = sum of table points selected by the small scalars ---------------------------
-// Scalars of up to kSmallBytes bytes stay on this path: byte p of the magnitude selects a table point in pass p, the warp writes one
-// partial sum per byte level and k_msm_finish_rows combines the levels as  L_0 + 256 * (L_1 + 256 * (L_2 + ...))  -- 8 doublings per
-// level and row instead of a bucket reduction per (row, chunk).  The zkCNN witness has ~25 000 scalars of 2-3 bytes among 2^24 (biases
-// scaled to the accumulator's fixed point): passes beyond the first only run in the warps that met one.
-constexpr int kSmallBytes = 4;
+// Scalars of up to kSmallBytes bytes stay on this path: byte k of the magnitude selects a table point that is added into the warp's
+// accumulator of LEVEL k, the warp writes one partial sum per level and k_msm_finish_rows combines the levels as
+// L_0 + 256 * (L_1 + 256 * L_2)  -- 8 doublings per level and row instead of a bucket reduction per (row, chunk).  The zkCNN witness
+// has ~25 000 scalars of 2-3 bytes among 2^24 (biases scaled to the accumulator's fixed point).  Level 0 lives in registers, the
+// rarely used higher levels in shared memory; all digits go through the same queue, so the lanes stay balanced.
+constexpr int kSmallBytes = 3;
 struct msm_small_args_t {
     const fr_t *scalars;       // [n_rows][n]
     const g1_aff_t *table;     // [n][255]
     uint64_t n;
     uint32_t n_rows, n_seg, seg_len;   // seg_len <= 65536
-    g1_jac_t *partial;         // [n_rows][n_seg][kSmallBytes] (levels a warp did not reach are written as infinity)
+    g1_jac_t *partial;         // level 0: [n_rows][n_seg][32], the 32 lane accumulators of every warp as they are (k_msm_finish_rows adds them
+                               // up: a 5-level tree per warp here would be a sixth of this kernel's time)
+    g1_jac_t *partial_hi;      // levels 1 ..: [n_rows][n_seg][kSmallBytes - 1] warp sums (levels a warp did not use are written as infinity)
     uint32_t *rowinfo;         // [n_rows] widest magnitude (bytes) among the scalars wider than kSmallBytes (atomicMax); [n_rows] = length of
                                // wide_rows; [n_rows + 1 + row] = byte levels present in the row (<= kSmallBytes)
     uint32_t *wide_rows;       // the rows with a scalar wider than kSmallBytes, in the order they were found (work list of k_msm_window)
@@ -81,10 +84,13 @@ struct msm_small_args_t {
 #define ZK_SMALL_WARPS 4
 #endif
 constexpr int kSmallWarps = ZK_SMALL_WARPS;   // 4 warps per CTA: three CTAs (12 warps) fit the register file of an SM, one 8-warp CTA would be alone
+struct msm_small_smem_t {
+    g1_jac_t lvl[kSmallBytes][kSmallWarps * 32];   // per thread and level: the accumulator while it is not the one in registers, then the tree sums
+    uint32_t queue[kSmallWarps][64];
+};
 
 __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_msm_small(msm_small_args_t A) {
-    __shared__ g1_jac_t sh[kSmallWarps * 32];
-    __shared__ uint32_t queue[kSmallWarps][64];
+    ZK_DYN_SMEM(msm_small_smem_t, S);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t gw = (uint64_t) blockIdx.x * kSmallWarps + warp;
     const bool active = gw < (uint64_t) A.n_rows * A.n_seg;   // idle warps of the last CTA keep walking through the barriers
@@ -92,49 +98,53 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
     const uint64_t base = (uint64_t) seg * A.seg_len;
     const uint64_t end = !active ? base : base + A.seg_len < A.n ? base + A.seg_len : A.n;
     const fr_t *sc = A.scalars + (uint64_t) row * A.n;
-    uint32_t *q = queue[warp];
+    uint32_t *q = S->queue[warp];
     (void) q;   // unused by the (uncompacted) emulator path
-    g1_jac_t acc;
-    uint32_t wide = 0, levels = 0, n_adds = 0;
+    // ONE accumulator in registers, of level acc_level (0 nearly always); a digit of another level swaps it with that level's slot
+    g1_jac_t acc = g1_jac_t::inf();
+    uint32_t acc_level = 0;
+#pragma unroll
+    for (int l = 1; l < kSmallBytes; ++l) S->lvl[l][threadIdx.x] = g1_jac_t::inf();
+    uint32_t wide = 0, used = 0, n_adds = 0, head = 0, pending = 0;
+    (void) head; (void) pending;
+    // code: generator within the segment (16 bits) | digit << 16 | negative << 24 | level << 25
     auto consume = [&](uint32_t code) {
         ++n_adds;
-        const uint32_t j = code & 0xffffu, d = (code >> 16) & 0xffu, neg = code >> 24;
+        const uint32_t j = code & 0xffffu, d = (code >> 16) & 0xffu, neg = (code >> 24) & 1u, level = code >> 25;
         const g1_aff_t *e = A.table + ((base + j) * kMultiples + (d - 1));
         g1_aff_t pt;
         pt.x = ld_fp(&e->x);
         pt.y = ld_fp(&e->y);
         if (neg) pt.y = -pt.y;
+        if (level != acc_level) {
+            S->lvl[acc_level][threadIdx.x] = acc;
+            acc = S->lvl[level][threadIdx.x];
+            acc_level = level;
+            used |= 1u << level;
+        }
         acc = g1_add_mixed(acc, pt);
     };
-#if ZK_ON_DEVICE
-    uint32_t n_pass = 1;   // known after pass 0 (warp-uniform)
-#else
-    const uint32_t n_pass = kSmallBytes;   // the emulator's barriers want the same trip count in every thread
-#endif
-    for (uint32_t p = 0; p < n_pass; ++p) {
-        acc = g1_jac_t::inf();
-        uint32_t head = 0, pending = 0;
-        (void) head; (void) pending;
-        for (uint64_t b = base; b < end; b += 32) {
-            const uint64_t j = b + lane;
-            uint32_t code = 0;
-            if (j < end) {
-                const fr_t s = ld_fr(sc + j);
-                if (!s.is_zero()) {
-                    uint32_t mag[8], neg;
-                    const uint32_t nb = scalar_sign_mag(s, mag, neg);
-                    if (nb > (uint32_t) kSmallBytes) wide = wide > nb ? wide : nb;
-                    else {
-                        levels = levels > nb ? levels : nb;
-                        const uint32_t d = (mag[0] >> (8 * p)) & 0xffu;
-                        if (d) code = (uint32_t) (j - base) | (d << 16) | (neg << 24);
-                    }
-                }
+    for (uint64_t b = base; b < end; b += 32) {
+        const uint64_t j = b + lane;
+        uint32_t digits = 0, neg = 0;   // up to kSmallBytes digits of this lane's scalar
+        if (j < end) {
+            const fr_t s = ld_fr(sc + j);
+            if (!s.is_zero()) {
+                uint32_t mag[8];
+                const uint32_t nb = scalar_sign_mag(s, mag, neg);
+                if (nb > (uint32_t) kSmallBytes) wide = wide > nb ? wide : nb;
+                else digits = mag[0];
             }
+        }
+#pragma unroll
+        for (int k = 0; k < kSmallBytes; ++k) {
+            const uint32_t d = (digits >> (8 * k)) & 0xffu;
+            const uint32_t code = d ? ((uint32_t) (j - base) | (d << 16) | (neg << 24) | ((uint32_t) k << 25)) : 0u;
             // compact the non-zero digits of these 32 entries into the warp's queue, so that every lane of the warp
             // has a point addition to do whenever the queue is drained (the witness is 40 % zeros)
 #if ZK_ON_DEVICE
             const uint32_t mask = __ballot_sync(0xffffffffu, code != 0);
+            if (mask == 0) continue;   // (warp-uniform; the usual case for k >= 1)
             const uint32_t rank = __popc(mask & ((1u << lane) - 1u));
             if (code) q[(head + pending + rank) & 63u] = code;
             pending += __popc(mask);
@@ -150,29 +160,32 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
             if (code) consume(code);
 #endif
         }
+    }
 #if ZK_ON_DEVICE
-        if (lane < pending) consume(q[(head + lane) & 63u]);
-        __syncwarp();
-        if (p == 0) {
-            levels = __reduce_max_sync(0xffffffffu, levels);
-            n_pass = levels > 1 ? levels : 1;
-        }
+    if (lane < pending) consume(q[(head + lane) & 63u]);
+    __syncwarp();
+    used = __reduce_or_sync(0xffffffffu, used);
+#else
+    used = (1u << kSmallBytes) - 2u;   // the emulator's barriers want the same trip count in every thread: sum every level
 #endif
-        // warp-level sum of the 32 accumulators
-        g1_jac_t *my = sh + threadIdx.x;
-        *my = acc;
+    S->lvl[acc_level][threadIdx.x] = acc;
+    if (active) A.partial[gw * 32 + lane] = S->lvl[0][threadIdx.x];
+    // warp-level sums of the 32 accumulators of the higher levels in use
+    for (uint32_t l = 1; l < (uint32_t) kSmallBytes; ++l) {
+        g1_jac_t *my = S->lvl[l] + threadIdx.x;
+        if (!((used >> l) & 1u)) {   // (warp-uniform)
+            if (active && lane == 0) A.partial_hi[gw * (kSmallBytes - 1) + (l - 1)] = g1_jac_t::inf();
+            continue;
+        }
         __syncwarp();
         for (uint32_t st = 16; st > 0; st >>= 1) {
             if (lane < st) *my = g1_add(*my, my[st]);
             __syncwarp();
         }
-        if (active && lane == 0) A.partial[gw * kSmallBytes + p] = *my;
-        __syncwarp();
+        if (active && lane == 0) A.partial_hi[gw * (kSmallBytes - 1) + (l - 1)] = *my;
     }
-    if (active && lane == 0)
-        for (uint32_t p = n_pass; p < (uint32_t) kSmallBytes; ++p) A.partial[gw * kSmallBytes + p] = g1_jac_t::inf();
     if (wide && atomicMax(A.rowinfo + row, wide) == 0) A.wide_rows[atomicAdd(A.rowinfo + A.n_rows, 1u)] = row;   // first to mark the row lists it
-    if (levels > 1 && (!ZK_ON_DEVICE || lane == 0)) atomicMax(A.rowinfo + A.n_rows + 1 + row, levels);
+    if (used > 1u && (!ZK_ON_DEVICE || lane == 0)) atomicMax(A.rowinfo + A.n_rows + 1 + row, 32u - (uint32_t) __clz(used));
     if (A.ops) {
 #if ZK_ON_DEVICE
         const uint32_t tot = __reduce_add_sync(0xffffffffu, n_adds);
@@ -183,11 +196,12 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
     }
 }
 
-// ---- out[row] = normalised (byte levels of the row's small-path partials + sum of its bucket-path partials); one warp per row ----------
+// ---- out[row] = (byte levels of the row's small-path partials + sum of its bucket-path partials), Jacobian; one warp per row ----------
+// small: the lane accumulators of the row's n_small segments (level 0), small_hi: their warp sums of the higher levels.
 // (bucket partials of a row exist when the bucket kernel visited it: every row, or with wide_only the rows whose rowinfo is non-zero)
-__global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_jac_t *small, uint32_t n_small, const g1_jac_t *bucket,
-                                                                        uint32_t n_bucket, const uint32_t *rowinfo, uint32_t wide_only,
-                                                                        uint32_t n_rows, g1_jac_t *out) {
+__global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_jac_t *small, const g1_jac_t *small_hi, uint32_t n_small,
+                                                                        const g1_jac_t *bucket, uint32_t n_bucket, const uint32_t *rowinfo,
+                                                                        uint32_t wide_only, uint32_t n_rows, g1_jac_t *out) {
     ZK_PDL_ENTRY();
     __shared__ g1_jac_t sh[kSmallWarps * 32];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -196,8 +210,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_j
     if (!active) n_small = n_bucket = 0;
     else if (wide_only && rowinfo[row] == 0) n_bucket = 0;
     g1_jac_t acc = g1_jac_t::inf();
-    for (uint32_t k = lane; k < n_small; k += 32) {
-        const g1_jac_t p = small[((size_t) row * n_small + k) * kSmallBytes];   // level 0
+    for (uint32_t k = lane; k < n_small * 32; k += 32) {
+        const g1_jac_t p = small[(size_t) row * n_small * 32 + k];
         if (!p.is_inf()) acc = g1_add(acc, p);
     }
     for (uint32_t k = lane; k < n_bucket; k += 32) {
@@ -219,15 +233,22 @@ __global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_j
             for (uint32_t p = levels - 1; p >= 1; --p) {
                 for (int k = 0; k < 8; ++k) hi = g1_dbl(hi);
                 for (uint32_t k = 0; k < n_small; ++k) {
-                    const g1_jac_t x = small[((size_t) row * n_small + k) * kSmallBytes + p];
+                    const g1_jac_t x = small_hi[((size_t) row * n_small + k) * (kSmallBytes - 1) + (p - 1)];
                     if (!x.is_inf()) hi = g1_add(hi, x);
                 }
             }
             for (int k = 0; k < 8; ++k) hi = g1_dbl(hi);
             tot = g1_add(tot, hi);
         }
-        out[row] = g1_normalize(tot);
+        out[row] = tot;   // Jacobian; k_g1_normalize_rows follows
     }
+}
+// in place: every point to z = 1 (infinity -> all zero), one thread per point.  Separate from k_msm_finish_rows, where one lane per warp
+// would walk through the inversion with the 31 others idle: here 4096 commitment rows are 128 warps instead of 4096.
+__global__ void __launch_bounds__(128) k_g1_normalize_rows(g1_jac_t *pts, uint32_t n) {
+    ZK_PDL_ENTRY();
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i < n) pts[i] = g1_normalize(pts[i]);
 }
 
 // ---- fixed-base scalar multiplication: out[i] = k_i * B for ONE base point ------------------------------------------------------

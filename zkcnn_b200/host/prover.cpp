@@ -165,6 +165,9 @@ void prover::buildCompactWitness() {
         zero -= full;   // the wide-list entries are zero in the int64 image
         for (uint32_t i : wide_idx_[0]) { row_wide[i / row_len] = 1; item_wide[i / 128] = 1; }
         size_t rows = 0, items = 0;
+        fprintf(stderr, "[witness] rows with a wide scalar:");
+        for (size_t r = 0; r < row_wide.size(); ++r) if (row_wide[r]) fprintf(stderr, " %zu", r);
+        fprintf(stderr, "\n");
         for (auto r : row_wide) rows += r;
         for (auto r : item_wide) items += r;
         size_t ones = 0, bit_blocks = 0, bit_block_ones = 0, nonempty_bit_blocks = 0;
