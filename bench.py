@@ -411,8 +411,9 @@ def run_ours(args):
                  "peak_source": peak_src, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": ncu.get("class_" + name), "traffic_unit": "DRAM bytes of ONE proof (ncu), compare with algorithmic_bytes_per_proof",
                  "launches": p["launches"], "device_ms": round(p["ms"], 3), "algorithmic_bytes": p["bytes"], "algorithmic_bytes_per_proof": p["bytes"] // max(1, args.steps)}
             if name == "msm" and "fp_mul" in micro and p["ms"] > 0:
-                # ALU view of the MSM class: measured mixed additions (11 Fp multiplications each) of the commitment and bucket kernels per second
-                # against the Fp-multiplier rate of this GPU measured in this run; table builds and bucket reductions are left out of the count
+                # ALU view of the MSM class: measured mixed additions (11 Fp multiplications each) of the commitment (one per non-zero byte of a
+                # scalar) and of the opening's bucket accumulation per second against the Fp-multiplier rate of this GPU measured in this run; table
+                # builds, bucket merges / reductions and normalisations are left out of the count
                 adds = int(msm_ops[0]) + int(msm_ops[1])
                 r["alu"] = {"mixed_additions": adds, "fp_mul_per_s": round(adds * 11 / (p["ms"] / 1e3) / 1e9, 2), "peak_fp_mul_per_s": micro["fp_mul"]["G_mul_per_s"], "unit": "G mul/s"}
                 r["alu_frac"] = round(r["alu"]["fp_mul_per_s"] / micro["fp_mul"]["G_mul_per_s"], 4)
@@ -430,7 +431,7 @@ def run_ours(args):
                        "arithmetic": "exact modular integer arithmetic on 32-bit limbs: BLS12-381 Fr (255-bit) and Fp (381-bit) in Montgomery form",
                        "network": config, "pictures_per_proof": pics, "input_layer": st0["input_size"], "layers": st0["n_layers"], "generators": "non-degenerate (G * challenge)",
                        "proofs_in_flight_per_gpu": M, "host_wait": {"yield": "polling an event with sched_yield", "block": "sleeping (blocking-sync events)"}.get(os.environ.get("ZK_HOST_WAIT", "block" if os.environ.get("ZK_BLOCKING_SYNC", "0") not in ("", "0") else ""), "spinning (cudaStreamSynchronize)"), "host_cores": os.cpu_count(),
-                       "rounds": "one device call per sumcheck round" if args.round_by_round else "one device call per sumcheck phase (challenges of a phase are drawn before its rounds, as in src/verifier.cpp:156-160)",
+                       "rounds": "one device call per sumcheck round" if args.round_by_round else "one device call per sumcheck phase (challenges of a phase are drawn before its rounds, as in src/verifier.cpp:156-160) and one for all rounds of the opening (their randomness is drawn first; one bucket MSM of 2 x rounds rows)",
                        "l2": "tables larger than L2 (2^24 x 32 B witness, 537 MB)", "parallelism": f"one proof stream per GPU x{world} ({M} provers in flight each, distinct pictures), final all-gather of all K proofs of every rank",
                        "timer": "host clock around synchronous API calls, barrier + cuda synchronize on both sides; value and e2e un-instrumented; per-kernel-class device "
                                 "times from a separate pass of K proofs on one prover with CUDA events around every launch on the launching stream (profiled_ms_per_step)",

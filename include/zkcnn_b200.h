@@ -75,6 +75,7 @@ int zk_profile_msm_ops(zk_ctx *ctx, uint64_t *out);
  *   "cubic_factored_min_iters" (4) k_round_cubic switches to the factored form from this many output pairs per thread
  *   "msm_few_rows_chunk" (2048) (generator, window) entries per work item of the bucket kernels for MSMs of at most 8 rows
  *   "msm_split" (1)      MSMs of at most 8 rows as accumulate / merge / reduce launches; 0: the self-contained bucket kernel
+ *   "msm_batch_chunk" (4096) the same for the MSM of the batched opening (zk_poly_bullet_prove_all)
  *   "msm_small_seg" (1024) scalars of a row that one warp of the small-multiples kernel takes
  *   "msm_host_finish" (1) opening rounds: the last 14 point operations and the normalisation of the two points on the host */
 int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value);

@@ -123,7 +123,8 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_rowinfo, dim3(grid_for(n * n_rows)), dim3(kBlock), 0, scalars_dev, n, n_rows, H.msm_rowinfo.as<uint32_t>());
     }
     // work items of the bucket kernel: (row, chunk of generators), all windows of a chunk in one item.  Few rows: smaller chunks, more CTAs
-    const uint32_t chunk = few_rows ? std::max<uint32_t>(1, std::min<uint32_t>(ctx->msm_few_rows_chunk / kMsmWindows, kMsmGensPerItem)) : kMsmGensPerItem;
+    const uint32_t chunk = few_rows ? std::max<uint32_t>(1, std::min<uint32_t>((n_rows <= 8 ? ctx->msm_few_rows_chunk : ctx->msm_batch_chunk) / kMsmWindows, kMsmGensPerItem))
+                                    : kMsmGensPerItem;
     const uint32_t n_chunks = (uint32_t) ((n + chunk - 1) / chunk);
     const bool waited = H.table_pending;   // a cross-stream wait sits between the next launch and its predecessor: plain launch then
     msm_wait_table(ctx, H);
@@ -142,10 +143,12 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         F.buckets = H.msm_buckets.as<g1_jac_t>();
         F.item_entries = H.msm_item_entries.as<uint32_t>();
         F.ops = ctx->prof_on ? prof_ops_counter(ctx) + 1 : nullptr;
+        // three CTAs per SM, all of them: an even split over fewer CTAs (1536 items as 384 x 4 instead of 444 x 3.46) measured slower,
+        // the SMs left with two CTAs lose more than the last partial pass costs
         const uint32_t fgrid = std::min<uint32_t>(n_items, 3 * ZK_SM_COUNT);
         if (waited) ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, alg_bytes, k_msm_bucket_fill, dim3(fgrid), dim3(kFillThreads), sizeof(msm_fill_smem_t), F);
         else ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, alg_bytes, k_msm_bucket_fill, dim3(fgrid), dim3(kFillThreads), sizeof(msm_fill_smem_t), F);
-        ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_bucket_merge, dim3(n_rows * kMsmBuckets / (kBlock / 32)), dim3(kBlock), 0, H.msm_buckets.as<g1_jac_t>(),
+        ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_bucket_merge, dim3(n_rows * kMsmBuckets / (kMergeThreads / kGroup)), dim3(kMergeThreads), 0, H.msm_buckets.as<g1_jac_t>(),
                        H.msm_item_entries.as<uint32_t>(), n_rows, n_chunks, H.msm_merged.as<g1_jac_t>());
         if (host_S && ctx->msm_host_finish && n_rows <= 8) {
             H.msm_S.ensure((size_t) n_rows * 8 * sizeof(g1_jac_t));
@@ -175,7 +178,7 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     const uint32_t grid = (uint32_t) std::min<uint64_t>((uint64_t) n_rows * n_chunks, 2 * ZK_SM_COUNT);
     if (waited) ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(grid), dim3(kBlock), sizeof(msm_smem_t), A);
     else ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, small_path ? 0 : alg_bytes, k_msm_window, dim3(grid), dim3(kBlock), sizeof(msm_smem_t), A);
-    ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kSmallWarps - 1) / kSmallWarps), dim3(kSmallWarps * 32), 0,
+    ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kFinishRows - 1) / kFinishRows), dim3(kFinishRows * kGroup), 0,
                  small_path ? H.msm_small.as<g1_jac_t>() : (const g1_jac_t *) nullptr, small_path ? H.msm_small_hi.as<g1_jac_t>() : (const g1_jac_t *) nullptr, n_seg,
                  H.msm_out.as<g1_jac_t>(), n_chunks,
                  H.msm_rowinfo.as<uint32_t>(), small_path ? 1u : 0u, n_rows, out_dev);

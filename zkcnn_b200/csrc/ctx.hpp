@@ -150,6 +150,7 @@ struct zk_ctx {
     uint32_t cubic_tma_enabled = 1;          // DOT_PROD fold rounds on large tables use k_round_cubic_tma
     uint32_t cubic_max_grid = 1u << 20;       // cap on the CTAs of a K2 launch (tests: forces several iterations per thread on small tables)
     uint32_t cubic_factored_min_iters = 4;   // k_round_cubic: factored form from this many output pairs per thread
+    uint32_t msm_batch_chunk = 4096;         // the same for the batched opening (2 x rounds rows in one MSM)
     uint32_t msm_small_seg = 1024;           // scalars per warp of k_msm_small (one row segment)
     uint32_t msm_host_finish = 1;            // opening rounds: the last 14 point operations + the normalisation of the two points on the host
     uint32_t msm_split = 1;                  // MSMs of at most 8 rows: accumulate / merge / reduce launches (k_msm_bucket_*) instead of k_msm_window

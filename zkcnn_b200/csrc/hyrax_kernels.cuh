@@ -433,31 +433,41 @@ __global__ void __launch_bounds__(kFillThreads, 3) k_msm_bucket_fill(msm_fill_ar
     }
 }
 
-// merged[row][b] = sum over the row's items of buckets[item][b]; one warp per (row, b), kBlock / 32 buckets per CTA
-__global__ void __launch_bounds__(kBlock) k_msm_bucket_merge(const g1_jac_t *buckets, const uint32_t *item_entries, uint32_t n_rows, uint32_t n_chunks,
-                                                              g1_jac_t *merged) {
+// sum of the eight accumulators of a group of 8 consecutive threads (3 tree levels through shared memory); the result is in the group's
+// first thread.  Eight lanes per sum instead of a warp per sum: a 5-level tree over 32 lanes spends 5 additions of warp time on 31 useful
+// ones, this spends 3 on 28 (four sums per warp), and the sequential part before it keeps every lane busy.
+constexpr int kGroup = 8;
+__device__ __forceinline__ g1_jac_t group8_sum(const g1_jac_t &acc, g1_jac_t *sh) {
+    g1_jac_t *my = sh + threadIdx.x;
+    const uint32_t sub = threadIdx.x & (kGroup - 1);
+    *my = acc;
+    __syncwarp();
+    for (uint32_t st = kGroup / 2; st > 0; st >>= 1) {
+        if (sub < st) *my = g1_add(*my, my[st]);
+        __syncwarp();
+    }
+    return *my;
+}
+
+// merged[row][b] = sum over the row's items of buckets[item][b]; eight threads per (row, b), each striding the items
+constexpr int kMergeThreads = 128;
+__global__ void __launch_bounds__(kMergeThreads, 3) k_msm_bucket_merge(const g1_jac_t *buckets, const uint32_t *item_entries, uint32_t n_rows, uint32_t n_chunks,
+                                                                        g1_jac_t *merged) {
     ZK_PDL_ENTRY();
-    __shared__ g1_jac_t sh[kBlock];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t idx = blockIdx.x * (kBlock / 32) + warp;   // row * 256 + b
+    __shared__ g1_jac_t sh[kMergeThreads];
+    const uint32_t sub = threadIdx.x & (kGroup - 1);
+    const uint32_t idx = blockIdx.x * (kMergeThreads / kGroup) + threadIdx.x / kGroup;   // row * 256 + b
     const uint32_t row = idx / kMsmBuckets, b = idx % kMsmBuckets;
-    const bool active = row < n_rows && b != 0;
     g1_jac_t acc = g1_jac_t::inf();
-    if (active)
-        for (uint32_t k = lane; k < n_chunks; k += 32) {
+    if (row < n_rows && b != 0)
+        for (uint32_t k = sub; k < n_chunks; k += kGroup) {
             const size_t item = (size_t) row * n_chunks + k;
             if (item_entries[item] == 0) continue;
             const g1_jac_t p = buckets[item * kMsmBuckets + b];
             if (!p.is_inf()) acc = g1_add(acc, p);
         }
-    g1_jac_t *my = sh + threadIdx.x;
-    *my = acc;
-    __syncwarp();
-    for (uint32_t st = 16; st > 0; st >>= 1) {
-        if (lane < st) *my = g1_add(*my, my[st]);
-        __syncwarp();
-    }
-    if (row < n_rows && lane == 0) merged[idx] = *my;
+    const g1_jac_t tot = group8_sum(acc, sh);
+    if (row < n_rows && sub == 0) merged[idx] = tot;
 }
 
 // out[row] = normalised sum_b b * merged[row][b]; one CTA per row, thread (k, u) = (threadIdx.x / 32, threadIdx.x % 32) works on S_k.

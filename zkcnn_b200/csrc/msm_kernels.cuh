@@ -196,37 +196,31 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
     }
 }
 
-// ---- out[row] = (byte levels of the row's small-path partials + sum of its bucket-path partials), Jacobian; one warp per row ----------
+// ---- out[row] = (byte levels of the row's small-path partials + sum of its bucket-path partials), Jacobian; eight threads per row -------
 // small: the lane accumulators of the row's n_small segments (level 0), small_hi: their warp sums of the higher levels.
 // (bucket partials of a row exist when the bucket kernel visited it: every row, or with wide_only the rows whose rowinfo is non-zero)
-__global__ void __launch_bounds__(kSmallWarps * 32) k_msm_finish_rows(const g1_jac_t *small, const g1_jac_t *small_hi, uint32_t n_small,
-                                                                        const g1_jac_t *bucket, uint32_t n_bucket, const uint32_t *rowinfo,
-                                                                        uint32_t wide_only, uint32_t n_rows, g1_jac_t *out) {
+constexpr int kFinishRows = 16;   // rows per CTA
+__global__ void __launch_bounds__(kFinishRows * kGroup, 3) k_msm_finish_rows(const g1_jac_t *small, const g1_jac_t *small_hi, uint32_t n_small,
+                                                                              const g1_jac_t *bucket, uint32_t n_bucket, const uint32_t *rowinfo,
+                                                                              uint32_t wide_only, uint32_t n_rows, g1_jac_t *out) {
     ZK_PDL_ENTRY();
-    __shared__ g1_jac_t sh[kSmallWarps * 32];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t row = blockIdx.x * kSmallWarps + warp;
+    __shared__ g1_jac_t sh[kFinishRows * kGroup];
+    const uint32_t sub = threadIdx.x & (kGroup - 1);
+    const uint32_t row = blockIdx.x * kFinishRows + threadIdx.x / kGroup;
     const bool active = row < n_rows;
     if (!active) n_small = n_bucket = 0;
     else if (wide_only && rowinfo[row] == 0) n_bucket = 0;
     g1_jac_t acc = g1_jac_t::inf();
-    for (uint32_t k = lane; k < n_small * 32; k += 32) {
+    for (uint32_t k = sub; k < n_small * 32; k += kGroup) {
         const g1_jac_t p = small[(size_t) row * n_small * 32 + k];
         if (!p.is_inf()) acc = g1_add(acc, p);
     }
-    for (uint32_t k = lane; k < n_bucket; k += 32) {
+    for (uint32_t k = sub; k < n_bucket; k += kGroup) {
         const g1_jac_t p = bucket[(size_t) row * n_bucket + k];
         if (!p.is_inf()) acc = g1_add(acc, p);
     }
-    g1_jac_t *my = sh + threadIdx.x;
-    *my = acc;
-    __syncwarp();
-    for (uint32_t st = 16; st > 0; st >>= 1) {
-        if (lane < st) *my = g1_add(*my, my[st]);
-        __syncwarp();
-    }
-    if (active && lane == 0) {
-        g1_jac_t tot = *my;
+    g1_jac_t tot = group8_sum(acc, sh);
+    if (active && sub == 0) {
         const uint32_t levels = n_small ? rowinfo[n_rows + 1 + row] : 0u;   // > 1 only in the rare rows with 2..kSmallBytes-byte scalars
         if (levels > 1) {
             g1_jac_t hi = g1_jac_t::inf();
