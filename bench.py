@@ -180,12 +180,13 @@ def run_ours(args):
     model, pics = args.model, args.pics
     if args.inflight > 0:
         M = args.inflight
-    else:   # up to --max-inflight provers per GPU, bounded by the host's memory: ~8 GB of RAM (circuit + witness of vgg11, more with several pictures) per prover
+    else:   # up to --max-inflight provers per GPU, bounded by the host's memory: a vgg11 prover holds 3 GB (circuit + witness) and peaks at ~5 GB while its
+            # schedules are built; 6 GB each (more with several pictures) may take half of what is available
         try:
             avail_gb = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) / 1e6
         except Exception:
             avail_gb = 64
-        per_gb = 1 if model == "lenet" else 8 * (1 if pics == 1 else 1.5 * pics) * (1.5 if model == "vgg16" else 1)
+        per_gb = 1 if model == "lenet" else 6 * (1 if pics == 1 else 2 * pics) * (1.5 if model == "vgg16" else 1)
         m_max = max(1, min(args.max_inflight, int(avail_gb * 0.5 / (world * per_gb))))
         rounds = -(-args.steps // m_max)            # the K proofs of the timed region are dealt round-robin: as few rounds as m_max allows,
         M = max(1, -(-args.steps // rounds))        # then the smallest number of provers that still does it in that many (even shares)

@@ -185,13 +185,11 @@ __device__ __forceinline__ void msm_accumulate_runs(const uint32_t *sorted, uint
 
 constexpr int kMsmEntries = 4096;             // (generator, window) entries one work item sorts in shared memory
 constexpr int kMsmGensPerItem = kMsmEntries / kMsmWindows;   // 128 generators x 32 windows
-constexpr int kMsmSeg = 8;                    // buckets per segment of the final reduction
-constexpr int kMsmSegs = kMsmBuckets / kMsmSeg;
 
 struct msm_smem_t {
     g1_jac_t bucket[kMsmBuckets];
-    g1_jac_t first[kBlock];      // partial run at the start of a thread's span; later the segments' weighted sums W_s
-    g1_jac_t last[kBlock];       // partial run at the end of a thread's span; later the segments' plain sums T_s (ping-pong halves)
+    g1_jac_t first[kBlock];      // terminal piece of a bucket that spans threads; later the ping-pong partner of `bucket` in the suffix scan
+    g1_jac_t last[kBlock];       // a thread's run that extends into the next thread's span (msm_accumulate_runs)
     uint32_t count[kMsmBuckets];
     uint32_t off[kMsmBuckets + 1];
     uint32_t cursor[kMsmBuckets];
@@ -218,9 +216,7 @@ struct msm_args_t {
 // a scalar go into ONE set of 255 buckets: a work item is (row, chunk of <= 128 generators) with up to 32 entries per generator, and
 // one bucket reduction serves all windows (32 of them before).  Persistent CTAs walk the work items; with wide_only the items are
 // (listed wide row, chunk), the list being written by k_msm_small, so a witness with a handful of wide scalars costs a handful of
-// items.  The reduction  sum_b b * B_b  is done per segment of 8 buckets by 32 threads (running sums: W_s = sum_i i * B_{8s+i},
-// T_s = sum_i B_{8s+i}), then  sum_s W_s + 8 * sum_s s * T_s  with a 32-wide suffix scan + tree: ~1000 point additions per item
-// instead of the 4096 of a 256-wide scan.
+// items.
 __global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
     ZK_PDL_ENTRY();
     ZK_DYN_SMEM(msm_smem_t, S);
@@ -292,44 +288,26 @@ __global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
         __syncthreads();
         msm_accumulate_runs<kBlock>(S->sorted, E, T, A.n_table, S->first, S->last, S->cursor, S->scan[0], [&](uint32_t b, const g1_jac_t &sum) { S->bucket[b] = sum; });
         __syncthreads();
-        // segments: thread s < 32 walks buckets 8s+7 .. 8s with a running sum; W_s = sum_i i * B_{8s+i} -> first[s], T_s -> last[s]
-        if (t < (uint32_t) kMsmSegs) {
-            g1_jac_t run = g1_jac_t::inf(), wsum = g1_jac_t::inf();
-            for (int i = kMsmSeg - 1; i >= 0; --i) {
-                const g1_jac_t b = S->bucket[t * kMsmSeg + i];
-                if (!b.is_inf()) run = g1_add(run, b);
-                if (i > 0 && !run.is_inf()) wsum = g1_add(wsum, run);
-            }
-            S->first[t] = wsum;
-            S->last[t] = run;
-        }
-        __syncthreads();
-        // sum_s s * T_s = sum_{k >= 1} (suffix sum of T from k): 5-step suffix scan by threads 0..31 (ping-pong inside `last`), while
-        // threads 32..63 tree-sum the W_s
+        // sum_b b * B_b = sum_{k = 1..255} S_k with the suffix sums S_k = sum_{b >= k} B_b: a parallel suffix scan (8 steps of one addition
+        // per thread, ping-pong between `bucket` and `first`, which is free by now) and a tree sum of S_1..S_255 -- 16 dependent point
+        // additions.  (Per segment of 8 buckets with running sums it is ~1000 additions instead of 4096 but 30 dependent ones, and this
+        // kernel holds its SM alone either way: the uniform-scalar 4096 x 4096 MSM took 669 ms that way, 571 ms this way.)
         {
-            g1_jac_t *in = S->last, *out = S->last + kMsmSegs;
-            for (uint32_t d = 1; d < (uint32_t) kMsmSegs; d <<= 1) {
-                if (t < (uint32_t) kMsmSegs) out[t] = t + d < (uint32_t) kMsmSegs ? g1_add(in[t], in[t + d]) : in[t];
-                else if (t < 2u * kMsmSegs) {
-                    const uint32_t i = t - kMsmSegs, st = (uint32_t) kMsmSegs / (2 * d);   // 16, 8, 4, 2, 1
-                    if (i < st) S->first[i] = g1_add(S->first[i], S->first[i + st]);
-                }
+            g1_jac_t *in = S->bucket, *out = S->first;
+            for (uint32_t d = 1; d < (uint32_t) kMsmBuckets; d <<= 1) {
+                out[t] = t + d < (uint32_t) kMsmBuckets ? g1_add(in[t], in[t + d]) : in[t];
                 __syncthreads();
                 g1_jac_t *tmp = in; in = out; out = tmp;
             }
-            // `in` holds the suffix sums; the k = 0 term is not part of the sum
-            if (t == 0) in[0] = g1_jac_t::inf();
-            __syncthreads();
-            for (uint32_t st = kMsmSegs / 2; st > 0; st >>= 1) {
-                if (t < st) in[t] = g1_add(in[t], in[t + st]);
-                __syncthreads();
-            }
-            if (t == 0) {
-                g1_jac_t r = in[0];
-                for (int k = 1; k < kMsmSeg; k <<= 1) r = g1_dbl(r);   // * 8
-                *dst = g1_add(r, S->first[0]);
-            }
+            // 8 steps: the result is back in S->bucket; bucket 0 is empty by construction and its suffix sum is not a term
+            if (t == 0) S->bucket[0] = g1_jac_t::inf();
         }
+        __syncthreads();
+        for (uint32_t st = kBlock / 2; st > 0; st >>= 1) {
+            if (t < st) S->bucket[t] = g1_add(S->bucket[t], S->bucket[t + st]);
+            __syncthreads();
+        }
+        if (t == 0) *dst = S->bucket[0];
         __syncthreads();   // the next item reuses the shared arrays
     }
 }
@@ -339,7 +317,7 @@ __global__ void __launch_bounds__(kBlock) k_msm_window(msm_args_t A) {
 // takes.  With several proofs in flight that idles the machine, so MSMs of a few rows split the work by the parallelism it has:
 //   k_msm_bucket_fill    (row, chunk) items as above, 128 threads, ~57 KB: sort + balanced accumulation only; the 255 bucket sums of
 //                        the item go to global memory (three CTAs per SM, every thread adding points for most of the CTA's life)
-//   k_msm_bucket_merge   one warp per (row, bucket): sum over the row's items (lanes stride the items, 5-level tree)
+//   k_msm_bucket_merge   eight threads per (row, bucket): sum over the row's items (the lanes stride the items, then a 3-level tree)
 //   k_msm_bucket_reduce  one CTA per row:  sum_b b * B_b = sum_{k<8} 2^k * S_k,  S_k = sum of the buckets whose index has bit k set
 //                        (eight 128-leaf trees side by side, then 7 doublings + 7 additions); the result is normalised in place
 constexpr int kFillThreads = 128;
