@@ -75,6 +75,8 @@ int zk_profile_msm_ops(zk_ctx *ctx, uint64_t *out);
  *   "cubic_factored_min_iters" (4) k_round_cubic switches to the factored form from this many output pairs per thread
  *   "msm_few_rows_chunk" (2048) (generator, window) entries per work item of the bucket kernels for MSMs of at most 8 rows
  *   "msm_split" (1)      MSMs of at most 8 rows as accumulate / merge / reduce launches; 0: the self-contained bucket kernel
+ *   "msm_digit_bits" (8)  digit width of the small-multiples commitment path: 2^bits - 1 multiples per generator are tabulated and a scalar
+ *                         costs one addition per non-zero digit; 6 suits witnesses whose magnitudes are mostly below 64 (zkh_build picks it)
  *   "msm_batch_chunk" (4096) the same for the MSM of the batched opening (zk_poly_bullet_prove_all)
  *   "msm_small_seg" (1024) scalars of a row that one warp of the small-multiples kernel takes
  *   "msm_host_finish" (1) opening rounds: the last 14 point operations and the normalisation of the two points on the host */

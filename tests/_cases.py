@@ -352,9 +352,12 @@ def case_msm_many_rows(lib, n=64, rows=20, seed=808):
     # the byte levels of the small-multiples path (2, 3, 4 bytes, both signs, zero middle bytes) and the first width beyond it
     ks[4 * n + 1:4 * n + 9] = [65536 + 5, O.R - (1 << 24) - 3, (1 << 32) - 1, O.R - ((1 << 32) - 1), 1 << 32, O.R - (1 << 32), 0x01000000, 0x00ff00]
     ks[6 * n:7 * n] = [(rng.next() % (1 << 17) - (1 << 16)) % O.R for _ in range(n)]          # a row of 2-3 byte scalars only
+    want = [O.g1_mul_vec(pts, ks[i * n:(i + 1) * n]) for i in range(rows)]
     with Context(lib) as ctx:
-        got = g1_from_words(ctx.msm(g1_to_words(pts), fr_to_words(ks), rows))
-    assert got == [O.g1_mul_vec(pts, ks[i * n:(i + 1) * n]) for i in range(rows)]
+        for bits in (8, 6, 7):     # digit width of the small-multiples table: 255, 63, 127 multiples per generator
+            ctx.set_tunable("msm_digit_bits", bits)
+            got = g1_from_words(ctx.msm(g1_to_words(pts), fr_to_words(ks), rows))
+            assert got == want, bits
     assert got[0] is None
 
 

@@ -86,6 +86,7 @@ int zk_set_tunable(zk_ctx *ctx, const char *name, uint64_t value) {
     else if (n == "cubic_max_grid") ctx->cubic_max_grid = (uint32_t) std::max<uint64_t>(1, value);
     else if (n == "cubic_factored_min_iters") ctx->cubic_factored_min_iters = (uint32_t) std::max<uint64_t>(1, value);
     else if (n == "msm_split") ctx->msm_split = value ? 1u : 0u;
+    else if (n == "msm_digit_bits") { ZK_REQUIRE(value >= 6 && value <= 8, "msm_digit_bits: 6, 7 or 8"); ctx->msm_digit_bits = (uint32_t) value; }
     else if (n == "msm_batch_chunk") ctx->msm_batch_chunk = (uint32_t) std::max<uint64_t>(256, std::min<uint64_t>(value, kMsmChunk));
     else if (n == "msm_small_seg") ctx->msm_small_seg = (uint32_t) std::max<uint64_t>(32, std::min<uint64_t>(value, 65536));
     else if (n == "msm_host_finish") ctx->msm_host_finish = value ? 1u : 0u;

@@ -73,12 +73,15 @@ static void msm_wait_table(zk_ctx *ctx, hyrax_t &H) {
 // small-multiples table M[j][d-1] = d * G_j for the current generator set (msm_kernels.cuh); built on first use
 constexpr uint32_t kMultiplesMaxGens = 1u << 13;   // 8192 generators -> 200 MB
 static void msm_prepare_multiples(zk_ctx *ctx, hyrax_t &H) {
-    if (H.mult_ready) return;
-    H.mult.ensure((size_t) H.n_gens * kMultiples * sizeof(g1_aff_t));
-    const uint32_t threads = H.n_gens * kMulThreadsPerGen;
-    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, (uint64_t) H.n_gens * kMultiples * 96, k_msm_multiples_build, dim3((threads + 127) / 128), dim3(128), 0,
-                 H.gens_aff.as<g1_aff_t>(), H.mult.as<g1_aff_t>(), H.n_gens);
+    const uint32_t bits = ctx->msm_digit_bits;
+    if (H.mult_ready && H.mult_bits == bits) return;
+    const uint32_t n_mult = (1u << bits) - 1u;
+    H.mult.ensure((size_t) H.n_gens * n_mult * sizeof(g1_aff_t));
+    const uint32_t threads = H.n_gens * ((n_mult + kMulSeg - 1) / kMulSeg);
+    ZK_KLAUNCH_C(ctx, ZK_PROF_MSM, (uint64_t) H.n_gens * n_mult * 96, k_msm_multiples_build, dim3((threads + 127) / 128), dim3(128), 0,
+                 H.gens_aff.as<g1_aff_t>(), H.mult.as<g1_aff_t>(), H.n_gens, n_mult);
     H.mult_ready = true;
+    H.mult_bits = bits;
 }
 
 // out_dev[k] (normalised) = sum_j scalars[k*n + j] * G_j  for k < n_rows, generators taken from H.table.
@@ -105,13 +108,14 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
         const uint32_t seg_len = (uint32_t) std::min<uint64_t>(n, ctx->msm_small_seg);
         n_seg = (uint32_t) ((n + seg_len - 1) / seg_len);
         H.msm_small.ensure((size_t) n_rows * n_seg * 32 * sizeof(g1_jac_t));
-        H.msm_small_hi.ensure((size_t) n_rows * n_seg * (kSmallBytes - 1) * sizeof(g1_jac_t));
+        H.msm_small_hi.ensure((size_t) n_rows * n_seg * (kSmallLevels - 1) * sizeof(g1_jac_t));
         H.msm_wide_rows.ensure((size_t) n_rows * 4);
         msm_small_args_t S;
         S.scalars = scalars_dev;
         S.table = H.mult.as<g1_aff_t>();
         S.n = n;
         S.n_rows = n_rows; S.n_seg = n_seg; S.seg_len = seg_len;
+        S.digit_bits = H.mult_bits;
         S.partial = H.msm_small.as<g1_jac_t>();
         S.partial_hi = H.msm_small_hi.as<g1_jac_t>();
         S.rowinfo = H.msm_rowinfo.as<uint32_t>();
@@ -181,7 +185,7 @@ static void msm_run(zk_ctx *ctx, hyrax_t &H, const fr_t *scalars_dev, uint64_t n
     ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_msm_finish_rows, dim3((n_rows + kFinishRows - 1) / kFinishRows), dim3(kFinishRows * kGroup), 0,
                  small_path ? H.msm_small.as<g1_jac_t>() : (const g1_jac_t *) nullptr, small_path ? H.msm_small_hi.as<g1_jac_t>() : (const g1_jac_t *) nullptr, n_seg,
                  H.msm_out.as<g1_jac_t>(), n_chunks,
-                 H.msm_rowinfo.as<uint32_t>(), small_path ? 1u : 0u, n_rows, out_dev);
+                 H.msm_rowinfo.as<uint32_t>(), small_path ? 1u : 0u, n_rows, H.mult_bits, out_dev);
     ZK_KLAUNCH_PDL(ctx, ZK_PROF_MSM, 0, k_g1_normalize_rows, dim3((n_rows + 127) / 128), dim3(128), 0, out_dev, n_rows);
 }
 
@@ -538,7 +542,7 @@ int zk_g1_fixed_base_mul(zk_ctx *ctx, const uint64_t *base, const uint64_t *scal
                    scr.as<fp_t>() + kMsmWindows, 1u);
         ctx->fb_comb.ensure((size_t) kMsmWindows * kMultiples * sizeof(g1_aff_t));
         ZK_KLAUNCH(ctx, k_msm_multiples_build, dim3((kMsmWindows * kMulThreadsPerGen + 127) / 128), dim3(128), 0, win.as<g1_aff_t>(),
-                   ctx->fb_comb.as<g1_aff_t>(), (uint32_t) kMsmWindows);
+                   ctx->fb_comb.as<g1_aff_t>(), (uint32_t) kMsmWindows, (uint32_t) kMultiples);
         rt::sync(ctx->stream);
         ctx->fb_ready = true;
     }

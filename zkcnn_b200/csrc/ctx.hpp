@@ -85,6 +85,7 @@ struct hyrax_t {
     rt::dbuf table_scratch;    // z's and prefix products of the table build
     rt::dbuf mult;             // small-multiples table [n_gens][255] affine, entry = d * gens[j]  (msm_kernels.cuh)
     bool mult_ready = false;
+    uint32_t mult_bits = 8;    // digit width the table was built for: 2^mult_bits - 1 entries per generator
     uint64_t gens_hash = 0;
     std::vector<uint8_t> gens_host;   // the generator set the tables were built for (confirms a hash hit)
     rt::dbuf L, R, RZ, a, a_next, coef, scal, bullet_dots;
@@ -150,6 +151,7 @@ struct zk_ctx {
     uint32_t cubic_tma_enabled = 1;          // DOT_PROD fold rounds on large tables use k_round_cubic_tma
     uint32_t cubic_max_grid = 1u << 20;       // cap on the CTAs of a K2 launch (tests: forces several iterations per thread on small tables)
     uint32_t cubic_factored_min_iters = 4;   // k_round_cubic: factored form from this many output pairs per thread
+    uint32_t msm_digit_bits = 8;             // digit width of the small-multiples path (6, 7 or 8): the table has 2^bits - 1 entries per generator
     uint32_t msm_batch_chunk = 4096;         // the same for the batched opening (2 x rounds rows in one MSM)
     uint32_t msm_small_seg = 1024;           // scalars per warp of k_msm_small (one row segment)
     uint32_t msm_host_finish = 1;            // opening rounds: the last 14 point operations + the normalisation of the two points on the host

@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(kBlock) k_g1_to_affine(const g1_jac_t *in, g1_
 
 // T[w][j] = 2^(8w) * G_j, affine.  One thread per generator (once per generator set): a chain of 248 doublings in Jacobian
 // form, then ONE inversion for all 31 points (Montgomery's trick; zs / pre are [31][n] scratch for the z's and their prefix
-// products).  32-thread CTAs spread the n chains over as many SMs as possible: the chain is latency bound.
-constexpr int kTableBuildBlock = 32;
+// products).  The chain is latency bound and runs next to the commitment's kernels: 128-thread CTAs (one warp per scheduler of 32 SMs)
+// instead of 32-thread CTAs on 128 SMs -- each of those took a CTA slot away from k_msm_small for the whole 2.7 ms (commit 11.0 -> 10.1 ms).
+constexpr int kTableBuildBlock = 128;
 __global__ void __launch_bounds__(kTableBuildBlock) k_msm_table_build(const g1_aff_t *gens, g1_aff_t *table, fp_t *zs, fp_t *pre, uint32_t n) {
     const uint32_t j = blockIdx.x * kTableBuildBlock + threadIdx.x;
     if (j >= n) return;

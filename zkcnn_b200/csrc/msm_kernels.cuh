@@ -21,13 +21,15 @@ constexpr int kMulThreadsPerGen = 8;     // 8 * 32 = 256 >= 255
 // ---- M[j][d-1] = d * G_j ------------------------------------------------------------------------------------------------
 // thread (j, s) produces d = 32 s + 1 .. 32 s + 32: a chain of mixed additions in Jacobian form, then ONE inversion of the
 // product of all z (Montgomery's trick) to normalise the 32 points.
-__global__ void __launch_bounds__(128) k_msm_multiples_build(const g1_aff_t *gens, g1_aff_t *table, uint32_t n) {
+// n_mult entries per generator (d = 1 .. n_mult; 255 for byte digits, 63 for 6-bit digits), (n_mult + 31) / 32 threads per generator
+__global__ void __launch_bounds__(128) k_msm_multiples_build(const g1_aff_t *gens, g1_aff_t *table, uint32_t n, uint32_t n_mult) {
     const uint32_t idx = blockIdx.x * 128 + threadIdx.x;
-    const uint32_t j = idx / kMulThreadsPerGen, s = idx % kMulThreadsPerGen;
+    const uint32_t tpg = (n_mult + kMulSeg - 1) / kMulSeg;
+    const uint32_t j = idx / tpg, s = idx % tpg;
     if (j >= n) return;
     const g1_aff_t G = gens[j];
-    g1_aff_t *out = table + (size_t) j * kMultiples + s * kMulSeg;
-    const int cnt = (s + 1) * kMulSeg > kMultiples ? kMultiples - s * kMulSeg : kMulSeg;
+    g1_aff_t *out = table + (size_t) j * n_mult + s * kMulSeg;
+    const int cnt = (s + 1) * kMulSeg > n_mult ? (int) (n_mult - s * kMulSeg) : kMulSeg;
     if (G.is_inf()) {
         for (int k = 0; k < cnt; ++k) out[k] = g1_aff_t::inf();
         return;
@@ -66,15 +68,17 @@ __global__ void __launch_bounds__(128) k_msm_multiples_build(const g1_aff_t *gen
 // L_0 + 256 * (L_1 + 256 * L_2)  -- 8 doublings per level and row instead of a bucket reduction per (row, chunk).  The zkCNN witness
 // has ~25 000 scalars of 2-3 bytes among 2^24 (biases scaled to the accumulator's fixed point).  Level 0 lives in registers, the
 // rarely used higher levels in shared memory; all digits go through the same queue, so the lanes stay balanced.
-constexpr int kSmallBytes = 3;
+constexpr int kSmallBytes = 3;    // scalars of up to 3 bytes (24 bits) stay on the small-multiples path
+constexpr int kSmallLevels = 4;   // digit levels a warp can hold: 24 bits = 3 levels of 8, 4 levels of 6 or 7 bits
 struct msm_small_args_t {
     const fr_t *scalars;       // [n_rows][n]
-    const g1_aff_t *table;     // [n][255]
+    const g1_aff_t *table;     // [n][2^digit_bits - 1]
     uint64_t n;
     uint32_t n_rows, n_seg, seg_len;   // seg_len <= 65536
+    uint32_t digit_bits;       // 6, 7 or 8: width of a digit = log2(table entries per generator + 1)
     g1_jac_t *partial;         // level 0: [n_rows][n_seg][32], the 32 lane accumulators of every warp as they are (k_msm_finish_rows adds them
                                // up: a 5-level tree per warp here would be a sixth of this kernel's time)
-    g1_jac_t *partial_hi;      // levels 1 ..: [n_rows][n_seg][kSmallBytes - 1] warp sums (levels a warp did not use are written as infinity)
+    g1_jac_t *partial_hi;      // levels 1 ..: [n_rows][n_seg][kSmallLevels - 1] warp sums (levels a warp did not use are written as infinity)
     uint32_t *rowinfo;         // [n_rows] widest magnitude (bytes) among the scalars wider than kSmallBytes (atomicMax); [n_rows] = length of
                                // wide_rows; [n_rows + 1 + row] = byte levels present in the row (<= kSmallBytes)
     uint32_t *wide_rows;       // the rows with a scalar wider than kSmallBytes, in the order they were found (work list of k_msm_window)
@@ -85,7 +89,8 @@ struct msm_small_args_t {
 #endif
 constexpr int kSmallWarps = ZK_SMALL_WARPS;   // 4 warps per CTA: three CTAs (12 warps) fit the register file of an SM, one 8-warp CTA would be alone
 struct msm_small_smem_t {
-    g1_jac_t lvl[kSmallBytes][kSmallWarps * 32];   // per thread and level: the accumulator while it is not the one in registers, then the tree sums
+    g1_jac_t lvl[kSmallLevels - 1][kSmallWarps * 32];   // per thread: slot k holds the accumulator of level k + 1 -- or the one of level 0 while
+                                                        // level k + 1 is the one in registers; at the end the tree sums of levels 1 ..
     uint32_t queue[kSmallWarps][64];
 };
 
@@ -104,21 +109,28 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
     g1_jac_t acc = g1_jac_t::inf();
     uint32_t acc_level = 0;
 #pragma unroll
-    for (int l = 1; l < kSmallBytes; ++l) S->lvl[l][threadIdx.x] = g1_jac_t::inf();
+    for (int l = 0; l < kSmallLevels - 1; ++l) S->lvl[l][threadIdx.x] = g1_jac_t::inf();
+    auto swap_with = [&](uint32_t level) {   // registers: level 0 <-> `level`
+        g1_jac_t *slot = &S->lvl[level - 1][threadIdx.x];
+        const g1_jac_t t = *slot;
+        *slot = acc;
+        acc = t;
+    };
+    const uint32_t w = A.digit_bits, dmask = (1u << w) - 1u, n_mult = dmask;
     uint32_t wide = 0, used = 0, n_adds = 0, head = 0, pending = 0;
     (void) head; (void) pending;
-    // code: generator within the segment (16 bits) | digit << 16 | negative << 24 | level << 25
+    // code: generator within the segment (16 bits) | digit << 16 (<= 8 bits) | negative << 24 | level << 25
     auto consume = [&](uint32_t code) {
         ++n_adds;
         const uint32_t j = code & 0xffffu, d = (code >> 16) & 0xffu, neg = (code >> 24) & 1u, level = code >> 25;
-        const g1_aff_t *e = A.table + ((base + j) * kMultiples + (d - 1));
+        const g1_aff_t *e = A.table + ((base + j) * n_mult + (d - 1));
         g1_aff_t pt;
         pt.x = ld_fp(&e->x);
         pt.y = ld_fp(&e->y);
         if (neg) pt.y = -pt.y;
         if (level != acc_level) {
-            S->lvl[acc_level][threadIdx.x] = acc;
-            acc = S->lvl[level][threadIdx.x];
+            if (acc_level) swap_with(acc_level);
+            if (level) swap_with(level);
             acc_level = level;
             used |= 1u << level;
         }
@@ -137,8 +149,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
             }
         }
 #pragma unroll
-        for (int k = 0; k < kSmallBytes; ++k) {
-            const uint32_t d = (digits >> (8 * k)) & 0xffu;
+        for (int k = 0; k < kSmallLevels; ++k) {
+            const uint32_t d = (digits >> (w * k)) & dmask;
             const uint32_t code = d ? ((uint32_t) (j - base) | (d << 16) | (neg << 24) | ((uint32_t) k << 25)) : 0u;
             // compact the non-zero digits of these 32 entries into the warp's queue, so that every lane of the warp
             // has a point addition to do whenever the queue is drained (the witness is 40 % zeros)
@@ -166,15 +178,15 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
     __syncwarp();
     used = __reduce_or_sync(0xffffffffu, used);
 #else
-    used = (1u << kSmallBytes) - 2u;   // the emulator's barriers want the same trip count in every thread: sum every level
+    used = (1u << kSmallLevels) - 2u;   // the emulator's barriers want the same trip count in every thread: sum every level
 #endif
-    S->lvl[acc_level][threadIdx.x] = acc;
-    if (active) A.partial[gw * 32 + lane] = S->lvl[0][threadIdx.x];
+    if (acc_level) swap_with(acc_level);
+    if (active) A.partial[gw * 32 + lane] = acc;
     // warp-level sums of the 32 accumulators of the higher levels in use
-    for (uint32_t l = 1; l < (uint32_t) kSmallBytes; ++l) {
-        g1_jac_t *my = S->lvl[l] + threadIdx.x;
+    for (uint32_t l = 1; l < (uint32_t) kSmallLevels; ++l) {
+        g1_jac_t *my = S->lvl[l - 1] + threadIdx.x;
         if (!((used >> l) & 1u)) {   // (warp-uniform)
-            if (active && lane == 0) A.partial_hi[gw * (kSmallBytes - 1) + (l - 1)] = g1_jac_t::inf();
+            if (active && lane == 0) A.partial_hi[gw * (kSmallLevels - 1) + (l - 1)] = g1_jac_t::inf();
             continue;
         }
         __syncwarp();
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
             if (lane < st) *my = g1_add(*my, my[st]);
             __syncwarp();
         }
-        if (active && lane == 0) A.partial_hi[gw * (kSmallBytes - 1) + (l - 1)] = *my;
+        if (active && lane == 0) A.partial_hi[gw * (kSmallLevels - 1) + (l - 1)] = *my;
     }
     if (wide && atomicMax(A.rowinfo + row, wide) == 0) A.wide_rows[atomicAdd(A.rowinfo + A.n_rows, 1u)] = row;   // first to mark the row lists it
     if (used > 1u && (!ZK_ON_DEVICE || lane == 0)) atomicMax(A.rowinfo + A.n_rows + 1 + row, 32u - (uint32_t) __clz(used));
@@ -202,7 +214,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, kSmallWarps == 4 ? 3 : 1) k_
 constexpr int kFinishRows = 16;   // rows per CTA
 __global__ void __launch_bounds__(kFinishRows * kGroup, 3) k_msm_finish_rows(const g1_jac_t *small, const g1_jac_t *small_hi, uint32_t n_small,
                                                                               const g1_jac_t *bucket, uint32_t n_bucket, const uint32_t *rowinfo,
-                                                                              uint32_t wide_only, uint32_t n_rows, g1_jac_t *out) {
+                                                                              uint32_t wide_only, uint32_t n_rows, uint32_t digit_bits, g1_jac_t *out) {
     ZK_PDL_ENTRY();
     __shared__ g1_jac_t sh[kFinishRows * kGroup];
     const uint32_t sub = threadIdx.x & (kGroup - 1);
@@ -221,17 +233,17 @@ __global__ void __launch_bounds__(kFinishRows * kGroup, 3) k_msm_finish_rows(con
     }
     g1_jac_t tot = group8_sum(acc, sh);
     if (active && sub == 0) {
-        const uint32_t levels = n_small ? rowinfo[n_rows + 1 + row] : 0u;   // > 1 only in the rare rows with 2..kSmallBytes-byte scalars
+        const uint32_t levels = n_small ? rowinfo[n_rows + 1 + row] : 0u;   // > 1 only in the rows with a scalar of more than one digit
         if (levels > 1) {
             g1_jac_t hi = g1_jac_t::inf();
             for (uint32_t p = levels - 1; p >= 1; --p) {
-                for (int k = 0; k < 8; ++k) hi = g1_dbl(hi);
+                for (uint32_t k = 0; k < digit_bits; ++k) hi = g1_dbl(hi);
                 for (uint32_t k = 0; k < n_small; ++k) {
-                    const g1_jac_t x = small_hi[((size_t) row * n_small + k) * (kSmallBytes - 1) + (p - 1)];
+                    const g1_jac_t x = small_hi[((size_t) row * n_small + k) * (kSmallLevels - 1) + (p - 1)];
                     if (!x.is_inf()) hi = g1_add(hi, x);
                 }
             }
-            for (int k = 0; k < 8; ++k) hi = g1_dbl(hi);
+            for (uint32_t k = 0; k < digit_bits; ++k) hi = g1_dbl(hi);
             tot = g1_add(tot, hi);
         }
         out[row] = tot;   // Jacobian; k_g1_normalize_rows follows

@@ -144,7 +144,30 @@ void prover::buildCompactWitness() {
             for (uint32_t i : wv) { wide_idx_[l].push_back(i); wide_val_[l].push_back(val[l][i]); }
     }
     compact_ready_ = true;
-    if (getenv("ZKH_WITNESS_STATS")) {   // diagnostic: how the input layer's scalars fall on the commitment MSM's paths (rows of 2^ceil(bl/2) generators)
+    // Digit width of the commitment's small-multiples path (zk_set_tunable "msm_digit_bits").  A scalar costs one point addition per
+    // non-zero digit of its magnitude and the table 2^w - 1 entries per generator, rebuilt for every proof's generators: count both
+    // for w = 6, 7, 8 in field multiplications (11 per addition, ~39 per table entry) over the input layer.
+    if (C.size && !getenv("ZKH_MSM_DIGIT_BITS")) {
+        const size_t n = witnessLength(0);
+        uint64_t adds[3] = {0, 0, 0};
+        for (size_t i = 0; i < n; ++i) {
+            const int64_t x = compact_[0][i];
+            const uint64_t m = (uint64_t) (x < 0 ? -x : x);
+            if (m == 0 || m >> 24) continue;   // zero, or beyond the small path whatever the width
+            for (int k = 0; k < 3; ++k) {
+                const unsigned w = 6 + k;
+                for (uint64_t t = m; t; t >>= w) adds[k] += (t & ((1u << w) - 1)) != 0;
+            }
+        }
+        const uint64_t n_gens = 1ULL << ((C.circuit[0].bit_length + 1) / 2);
+        uint64_t best = ~0ULL;
+        for (int k = 0; k < 3; ++k) {
+            const uint64_t cost = adds[k] * 11 + n_gens * ((1u << (6 + k)) - 1) * 39;
+            if (cost < best) { best = cost; msm_digit_bits_ = 6 + k; }
+        }
+    } else if (const char *e = getenv("ZKH_MSM_DIGIT_BITS")) msm_digit_bits_ = (unsigned) atoi(e);
+    if (getenv("ZKH_WITNESS_STATS")) {
+        fprintf(stderr, "[witness] digit width of the commitment's small-multiples path: %u bits\n", msm_digit_bits_);   // diagnostic: how the input layer's scalars fall on the commitment MSM's paths (rows of 2^ceil(bl/2) generators)
         const size_t n = witnessLength(0);
         u32 bl = 0;
         while (((size_t) 1 << bl) < n) ++bl;
@@ -170,6 +193,18 @@ void prover::buildCompactWitness() {
         fprintf(stderr, "\n");
         for (auto r : row_wide) rows += r;
         for (auto r : item_wide) items += r;
+        size_t hist[9] = {};   // one-byte magnitudes by bit length
+        for (size_t i = 0; i < n; ++i) {
+            const int64_t x = compact_[0][i];
+            const uint64_t m = (uint64_t) (x < 0 ? -x : x);
+            if (m == 0 || m > 255) continue;
+            int bl2 = 0;
+            for (uint64_t t = m; t; t >>= 1) ++bl2;
+            ++hist[bl2];
+        }
+        fprintf(stderr, "[witness] one-byte magnitudes by bit length 1..8:");
+        for (int b = 1; b <= 8; ++b) fprintf(stderr, " %zu", hist[b]);
+        fprintf(stderr, "\n");
         size_t ones = 0, bit_blocks = 0, bit_block_ones = 0, nonempty_bit_blocks = 0;
         for (size_t i = 0; i + 8 <= n; i += 8) {
             bool pure = true;
@@ -456,6 +491,7 @@ hyrax_bls12_381::polyProver &prover::commitInput(const vector<G> &gens) {   // s
     poly_p = std::make_unique<hyrax_bls12_381::polyProver>(val[0], gens, transcript_);
 #else
     // the device copy of val[0] is already zero-padded (zk_witness_layer); nothing is uploaded again
+    if (msm_digit_bits_ >= 6 && msm_digit_bits_ <= 8) check(zk_set_tunable(ctx_, "msm_digit_bits", msm_digit_bits_), "zk_set_tunable");
     poly_p = std::make_unique<hyrax_bls12_381::polyProver>(ctx_, gens, (unsigned char) C.circuit[0].bit_length, transcript_);
 #endif
     return *poly_p;

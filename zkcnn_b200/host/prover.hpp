@@ -126,6 +126,7 @@ private:
     std::vector<std::vector<uint32_t>> wide_idx_;
     std::vector<std::vector<F>> wide_val_;
     bool compact_ready_ = false;
+    unsigned msm_digit_bits_ = 0;      // digit width of the commitment's small-multiples path chosen from the witness (0: library default)
     uint64_t compactBytes(u32 layer) const { return compact_[layer].size() * 8 + wide_idx_[layer].size() * 36; }
 
     zk_ctx *ctx_ = nullptr;
