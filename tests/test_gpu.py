@@ -170,6 +170,22 @@ def test_proofs_in_flight_on_one_gpu(gpu_host, synthetic_inputs, mnist_input):
     assert not errors, errors
 
 
+def test_host_wait_modes(synthetic_inputs):
+    """ZK_HOST_WAIT=yield / block (csrc/rt.hpp: how a prover thread waits for its stream; read once per process, hence the child processes):
+    the LeNet proof is the reference's whatever the wait"""
+    import subprocess
+    import sys
+    golden = os.path.join(GOLDEN, "lenet_syn_p1_seed3.transcript.bin")
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import gen_synthetic_input as gen, zkcnn_b200\n"
+            "s = zkcnn_b200.session('lenet', '', 1, 0); s.input_values(gen.generate('lenet', 11).astype(np.float64)); s.build()\n"
+            "st = s.prove(3, 0); assert st['ok'] == 1\n"
+            "assert s.proof() == open(%r, 'rb').read(), 'transcript differs'\n"
+            "print('same transcript')" % (ROOT, os.path.join(ROOT, "tools"), golden))
+    for mode in ("yield", "block"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, ZK_HOST_WAIT=mode), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "same transcript" in r.stdout, (mode, r.stderr[-2000:])
+
+
 def test_against_the_reference_run_here(gpu_host, synthetic_inputs, tmp_path):
     """a seed no golden file holds: the compiled reference (oracle/_ref/ref_run, built from /root/reference by
     oracle/Makefile) proves on this box's CPU and the GPU transcript must be byte-identical"""
