@@ -8,7 +8,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
 import zkcnn_oracle as O  # noqa: E402
-from zkcnn_b200._binding import (CHECK_PREDICATES, PROVER_ONLY, REAL_GENERATORS, WITNESS_RESIDENT, Context, Session, fr_from_words, fr_to_words, g1_from_words,  # noqa: E402
+from zkcnn_b200._binding import (CHECK_PREDICATES, PROVER_ONLY, REAL_GENERATORS, WITNESS_RESIDENT, Context, Session, ZkError, fr_from_words, fr_to_words, g1_from_words,  # noqa: E402
                                  g1_to_words)
 
 H = lambda s: int(s, 16)  # noqa: E731
@@ -230,7 +230,14 @@ def case_hyrax_kat(lib, kat):
         assert fr_from_words(ctx.poly_bullet_open()) == [H(h["open"])]
         # the same opening with every round in one device pass (the randomness of all rounds known beforehand)
         ctx.poly_init_bullet_prove(fr_to_words(x[:lbl]), fr_to_words(x[lbl:]))
-        lc, rc, ly, ry = ctx.poly_bullet_prove_all(fr_to_words([H(rd["randomness"]) for rd in h["rounds"]]))
+        rands = fr_to_words([H(rd["randomness"]) for rd in h["rounds"]])
+        if len(rands) > 1:   # the call is for ALL remaining rounds: anything else is refused and leaves the state alone
+            try:
+                ctx.poly_bullet_prove_all(rands[:-1])
+                raise AssertionError("zk_poly_bullet_prove_all accepted too few rounds")
+            except ZkError:
+                pass
+        lc, rc, ly, ry = ctx.poly_bullet_prove_all(rands)
         for k, rd in enumerate(h["rounds"]):
             assert g1_from_words([lc[k], rc[k]]) == [P(rd["lcomm"]), P(rd["rcomm"])]
             assert fr_from_words([ly[k], ry[k]]) == [H(rd["ly"]), H(rd["ry"])]
