@@ -181,13 +181,13 @@ def run_ours(args):
     if args.inflight > 0:
         M = args.inflight
     else:   # up to --max-inflight provers per GPU, bounded by the host's memory: a vgg11 prover holds 3 GB (circuit + witness) and peaks at ~5 GB while its
-            # schedules are built; 6 GB each (more with several pictures) may take half of what is available
+            # schedules are built; 6 GB each (more with several pictures) may take 70 % of what is available
         try:
             avail_gb = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) / 1e6
         except Exception:
             avail_gb = 64
         per_gb = 1 if model == "lenet" else 6 * (1 if pics == 1 else 2 * pics) * (1.5 if model == "vgg16" else 1)
-        m_max = max(1, min(args.max_inflight, int(avail_gb * 0.5 / (world * per_gb))))
+        m_max = max(1, min(args.max_inflight, int(avail_gb * 0.7 / (world * per_gb))))
         rounds = -(-args.steps // m_max)            # the K proofs of the timed region are dealt round-robin: as few rounds as m_max allows,
         M = max(1, -(-args.steps // rounds))        # then the smallest number of provers that still does it in that many (even shares)
     # A prover thread needs ~25 ms of host time per vgg11 proof and waits for the GPU the rest of the time.  With fewer cores than waiting
