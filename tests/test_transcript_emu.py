@@ -55,6 +55,16 @@ def test_round_by_round_driver_gives_the_same_transcript(emu_host, synthetic_inp
     assert st["ok"] == 1 and st["checks"] == 1
 
 
+@pytest.mark.parametrize("bits", [6, 7, 8])
+def test_commitment_digit_widths_give_the_same_transcript(emu_host, synthetic_inputs, monkeypatch, bits):
+    """the commitment's small-multiples path with 63 / 127 / 255 multiples per generator (zkh_build picks the width from the witness;
+    ZKH_MSM_DIGIT_BITS forces it): real generators, so the commitment points are in the transcript"""
+    from zkcnn_b200._binding import PROVER_ONLY, REAL_GENERATORS
+    monkeypatch.setenv("ZKH_MSM_DIGIT_BITS", str(bits))
+    cases.prove_and_compare(emu_host, "vgg", synthetic_inputs["smallvgg_config"], 1, synthetic_inputs["smallvgg"], 8, REAL_GENERATORS | PROVER_ONLY,
+                            "smallvgg_p1_seed8_realgens", GOLDEN)
+
+
 def test_shipped_lenet_image(emu_host, mnist_input):
     """BASELINE config 1: the reference's own MNIST demo input (script/demo_lenet.sh)"""
     from zkcnn_b200._binding import HOST_PREDICATES
