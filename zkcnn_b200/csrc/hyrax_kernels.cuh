@@ -1,7 +1,8 @@
 // Hyrax commitment kernels (hot loop (3) of BASELINE.json north_star).
 //
-//   K8  k_msm_rowinfo / k_msm_window / k_msm_finish   polyProver::commit -> G1::mulVec
-//                                                     3rd/hyrax-bls12-381/src/polyProver.cpp:19-34, mcl ec.hpp:1570-1597
+//   K8  k_msm_rowinfo / k_msm_window                  polyProver::commit -> G1::mulVec  (scalars beyond the small-multiples path of
+//       (+ msm_kernels.cuh: k_msm_small, row sums)    msm_kernels.cuh)   3rd/hyrax-bls12-381/src/polyProver.cpp:19-34, mcl ec.hpp:1570-1597
+//   K9  k_msm_bucket_fill / _merge / _reduce          the MSMs of bulletProve, all rounds in one pass (few rows, full-width scalars)
 //   K9  k_bullet_scalars / k_dot2 / k_bullet_fold     polyProver::bulletProve / bulletUpdate   polyProver.cpp:76-109
 //       (RZ = R^T Z of initBulletProve, polyProver.cpp:66-68, reuses k_dense_colsum of sc_kernels.cuh)
 //
@@ -9,10 +10,9 @@
 // table T[w][j] = 2^(8w) * G_j (affine) is built once per generator set.  A scalar is split into sign and magnitude
 // (mcl's isNegative convention: x >= (r+1)/2 is handled as -(r-x) with the negated point), and the magnitude into
 // unsigned 8-bit digits; digit d of window w adds +-T[w][j] into bucket d.  Because the table already carries the
-// 2^(8w) factor, every window's bucket sum is simply added up at the end: no doubling chain.  One CTA handles one
-// (row, chunk, window): counting sort of the digits in shared memory, balanced bucket accumulation with mixed adds,
-// parallel  sum_b b * B_b.  The zkCNN witness is tiny-valued (hard part 3): windows above the
-// row's widest magnitude exit immediately, so a typical row costs one window.
+// 2^(8w) factor, the digits of ALL windows share one set of 255 buckets: a work item is (row, chunk of generators) with
+// up to 32 entries per generator -- counting sort of the entries by digit in shared memory, balanced accumulation with
+// mixed adds, one  sum_b b * B_b  per item.  Windows above the row's widest magnitude contribute no entries.
 //
 // mcl's mulVec is interleaved wNAF (not Pippenger); results agree as GROUP ELEMENTS, which is why every point that
 // leaves the device is normalised to affine.
@@ -486,18 +486,6 @@ inline g1_jac_t msm_finish_host(const g1_jac_t *S) {
     g1_jac_t r = S[7];
     for (int k = 6; k >= 0; --k) r = g1_add(g1_dbl(r), S[k]);
     return g1_normalize(r);
-}
-
-// out[row] = normalised sum of the row's (chunk, window) partial sums
-__global__ void __launch_bounds__(64) k_msm_finish(const g1_jac_t *partial, uint32_t n_rows, uint32_t per_row, g1_jac_t *out) {
-    const uint32_t row = blockIdx.x * 64 + threadIdx.x;
-    if (row >= n_rows) return;
-    g1_jac_t s = g1_jac_t::inf();
-    for (uint32_t k = 0; k < per_row; ++k) {
-        g1_jac_t p = partial[(size_t) row * per_row + k];
-        if (!p.is_inf()) s = g1_add(s, p);
-    }
-    out[row] = g1_normalize(s);
 }
 
 // ---- bullet (inner-product argument) rounds ---------------------------------------------------------------------------

@@ -1,14 +1,14 @@
 // Small-scalar fast path of the Hyrax commitment MSM (K8) and fixed-base scalar multiplication.
 //
-// The zkCNN witness is tiny-valued (hard part 3): 40 % of the 2^24 scalars are zero and 99.9 % of the
-// rest satisfy |x| <= 255 once mcl's sign convention is applied.  All sqrt(n) commitment rows share one generator set,
-// so a table of small multiples  M[j][d-1] = d * G_j  (d = 1..255, affine, 96 B)  turns a row commitment into ONE mixed
-// addition per non-zero scalar -- no buckets, no window reduction:
-//     comm[i] = sum_j sign(z_ij) * M[j][|z_ij|]          (k_msm_small)
-// The table is 255 * 96 B per generator (100 MB for the 4096 vgg11 generators, L2-resident for the most part) and is
-// rebuilt whenever the generator set changes (k_msm_multiples_build, ~20 field multiplications per entry thanks to one
-// shared inversion per 32 entries).  Scalars wider than one byte are left to the generic bucket kernel (k_msm_window in
-// "wide only" mode) and both partial results meet in k_msm_finish_rows.
+// The zkCNN witness is tiny-valued (hard part 3): of the 2^24 scalars of vgg11 a fifth is zero and 99.8 % of the
+// rest satisfy |x| < 64 once mcl's sign convention is applied; a few ten thousand are 2-3 bytes wide, none wider.  All sqrt(n)
+// commitment rows share one generator set, so a table of small multiples  M[j][d-1] = d * G_j  (d = 1 .. 2^w - 1, affine, 96 B)  turns
+// a row commitment into ONE mixed addition per non-zero w-bit digit of a scalar -- no buckets, no window reduction:
+//     comm[i] = sum_k 2^(wk) * sum_j sign(z_ij) * M[j][digit_k(|z_ij|)]          (k_msm_small, k_msm_finish_rows)
+// The table has 2^w - 1 entries per generator (w = 6: 25 MB for the 4096 vgg11 generators, L2 resident; w = 8: 100 MB) and is rebuilt
+// whenever the generator set changes (k_msm_multiples_build, ~39 field multiplications per entry with one shared inversion per 32
+// entries).  Scalars of more than 24 bits are left to the bucket kernel (k_msm_window of hyrax_kernels.cuh in "wide only" mode) and
+// both partial results meet in k_msm_finish_rows.
 #pragma once
 #include "hyrax_kernels.cuh"
 
